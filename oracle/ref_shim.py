@@ -1,0 +1,83 @@
+"""TEST INFRASTRUCTURE ONLY — loader for the *real* reference modules.
+
+The reference (`/root/reference`, pure Python/PyTorch) cannot be imported with a
+plain ``import nnsvs``: ``nnsvs/__init__.py:1`` pulls in ``nnsvs.util`` which needs
+pyworld / hydra / omegaconf, and ``nnsvs/usfgan/utils/utils.py:15`` needs h5py,
+``nnsvs/usfgan/models/discriminator.py:16`` needs tkinter.  None of those are on
+the hot path, so this shim registers a namespace stub for ``nnsvs`` (skipping its
+``__init__``) plus empty stubs for ``h5py``/``tkinter``.
+
+It exists for exactly two users, both of which run only in the build container
+(``/root/reference`` does not travel to the GPU box):
+
+* ``oracle/make_golden.py`` — generates ``tests/golden/*.npz`` from the reference.
+* ``tests/test_oracle_vs_reference.py`` — pins the oracle restatement against the
+  live reference (skipped when the reference tree is absent).
+
+Nothing in the product package may import this file.
+"""
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("SVSK_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "nnsvs", "diffsinger"))
+
+
+def _stub(name, **attrs):
+    if name in sys.modules:
+        return sys.modules[name]
+    m = types.ModuleType(name)
+    for k, v in attrs.items():
+        setattr(m, k, v)
+    sys.modules[name] = m
+    return m
+
+
+def load_reference():
+    """Returns a namespace with the reference hot-path classes (unmodified code)."""
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found under {REFERENCE_ROOT}")
+    if "nnsvs" not in sys.modules or not getattr(sys.modules["nnsvs"], "_svsk_shim", False):
+        pkg = types.ModuleType("nnsvs")
+        pkg.__path__ = [os.path.join(REFERENCE_ROOT, "nnsvs")]
+        pkg._svsk_shim = True
+        sys.modules["nnsvs"] = pkg
+    _stub("h5py")
+    _stub("tkinter", W="w")
+
+    ns = types.SimpleNamespace()
+    from nnsvs.diffsinger.denoiser import DiffNet
+    from nnsvs.diffsinger.diffusion import GaussianDiffusion
+    from nnsvs.wavenet import WaveNet
+    import nnsvs.usfgan.models.generator as gen
+    import nnsvs.usfgan.layers.residual_block as rb
+    import nnsvs.usfgan.layers.upsample as up
+    import nnsvs.usfgan.utils.index as index
+    import nnsvs.usfgan.utils.features as features
+    from nnsvs.usfgan import USFGANWrapper
+
+    # pd_indexing/index_initial call .cuda() whenever CUDA is visible
+    # (nnsvs/usfgan/utils/index.py:32-33,44-45,81-83); the CPU oracle use of the
+    # reference therefore needs CUDA hidden.  We do not patch the reference; callers
+    # run this with CUDA_VISIBLE_DEVICES="" when a GPU is present.
+    ns.DiffNet = DiffNet
+    ns.GaussianDiffusion = GaussianDiffusion
+    ns.WaveNet = WaveNet
+    ns.USFGANGenerator = gen.USFGANGenerator
+    ns.CascadeHnUSFGANGenerator = gen.CascadeHnUSFGANGenerator
+    ns.ParallelHnUSFGANGenerator = gen.ParallelHnUSFGANGenerator
+    ns.FixedBlock = rb.FixedBlock
+    ns.AdaptiveBlock = rb.AdaptiveBlock
+    ns.ResidualBlocks = rb.ResidualBlocks
+    ns.PeriodicityEstimator = rb.PeriodicityEstimator
+    ns.ConvInUpsampleNetwork = up.ConvInUpsampleNetwork
+    ns.pd_indexing = index.pd_indexing
+    ns.index_initial = index.index_initial
+    ns.SignalGenerator = features.SignalGenerator
+    ns.dilated_factor = features.dilated_factor
+    ns.USFGANWrapper = USFGANWrapper
+    return ns
