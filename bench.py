@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py — one JSON line for the hot path's headline metric.
+
+Workload (BASELINE.json configs[1]): DiffSinger DiffNet denoiser (20 residual layers, 256 ch, mel 80) run for a
+100-step DDPM sampling over a 6-part ensemble batch x 2000 frames on one B200.  A "step" is ONE full 100-step
+sampling pass over one batch; the metric is denoiser frame-steps per second (B*T*K_step per pass).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 (torchrun): every rank samples its own 6-track batch (tracks are independent work items, no data-path
+collective) -> weak scaling; the time is the max over ranks.
+--impl reference: the reference's CPU arithmetic (oracle port, torch CPU fp32, all host threads) on a bounded sample
+of the same workload; rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG = dict(in_dim=80, encoder_hidden_dim=256, residual_layers=20, residual_channels=256, dilation_cycle_length=4)
+K_STEP, B, T = 100, 6, 2000
+MAC_PER_FRAME_STEP = 13_213_696          # reference formulation incl. conditioner projection
+BLOCK_MAC_PER_FRAME = 655_360            # one fused block launch: 2C*(3C+H) + 2C*C per frame
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+def build_model(seed=1234):
+    from ensemble_svs_with_interactions_b200.diffsinger import DiffNet, GaussianDiffusion
+    torch.manual_seed(seed)
+    den = DiffNet(**CFG)
+    with torch.no_grad():
+        den.output_projection.weight.normal_(0, 0.02)   # zero-init in the reference would make the work vacuous
+    return GaussianDiffusion(CFG["encoder_hidden_dim"], CFG["in_dim"], den, K_step=K_STEP).eval()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    def __init__(self, index):
+        self.rows, self.stop = [], threading.Event()
+        self.cmd = ["nvidia-smi", "-i", str(index),
+                    "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                    "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                    "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits"]
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(self.cmd, capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_baseline(sample_steps=2, threads=None):
+    """Oracle port (torch CPU fp32 == the arithmetic the reference runs on a CPU host) on a bounded sample:
+    `sample_steps` DDPM steps of the full B x T batch.  Returns (frame-steps/s, cores, description, seconds)."""
+    from oracle import svs_oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    m = build_model()
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(1234)
+    cond = torch.randn(B, T, CFG["encoder_hidden_dim"], generator=g)
+    x_T = torch.randn(B, 1, CFG["in_dim"], T, generator=g)
+    z = torch.randn(K_STEP, B, 1, CFG["in_dim"], T, generator=g)[:sample_steps]
+    den = {k[len("denoise_fn."):]: v for k, v in sd.items() if k.startswith("denoise_fn.")}
+    tab = {k: sd[k] for k in O.SCHEDULE_BUFFERS}
+    c = cond.transpose(1, 2).contiguous()
+
+    def run():
+        x = x_T
+        for i in reversed(range(K_STEP - sample_steps, K_STEP)):
+            t = torch.full((B,), i, dtype=torch.long)
+            eps = O.diffnet_forward(den, x, t, c, CFG["residual_layers"], CFG["dilation_cycle_length"])
+            x = O.ddpm_update(tab, x, t, eps, z[i - (K_STEP - sample_steps)])
+        return x
+
+    with torch.no_grad():
+        run()  # warm-up
+        t0 = time.perf_counter()
+        run()
+        dt = time.perf_counter() - t0
+    return B * T * sample_steps / dt, threads, f"{sample_steps} of {K_STEP} DDPM steps of the full {B}x{T} batch", dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, cores, sample, dt = cpu_baseline(sample_steps=1)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    v = sum(x[0] for x in vals) / len(vals)
+    line = {"metric": "denoiser frame-steps/sec (DiffNet 20x256, 100-step DDPM sampling)", "value": v,
+            "unit": "frame-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sum(x[1] for x in vals) / len(vals), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"DiffNet(80,256,L20,C256) DDPM sampling, {B} tracks x {T} frames",
+                       "note": "each step = 1 DDPM step (bounded sample of the 100-step pass) on host cores"},
+            "cpu_baseline": {"value": v, "unit": "frame-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "frame-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    from ensemble_svs_with_interactions_b200 import _lib
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    m = build_model().to(dev)
+    den = m.denoise_fn
+    g = torch.Generator().manual_seed(1234 + rank)       # every rank: its own 6-track work item
+    cond_host = torch.randn(B, T, CFG["encoder_hidden_dim"], generator=g).pin_memory()
+    cond_dev = cond_host.to(dev)
+    out_host = torch.empty(B, T, CFG["in_dim"]).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_pass_resident():
+        return m.inference(cond_dev)
+
+    def one_pass_e2e():
+        c = cond_host.to(dev, non_blocking=True)
+        y = m.inference(c)
+        out_host.copy_(y, non_blocking=True)
+        return y
+
+    def timed(fn, n_warm, n_steps):
+        for _ in range(n_warm):
+            fn()
+        barrier()
+        total = 0.0
+        n0 = _lib.launch_count
+        for _ in range(n_steps):
+            flush.fill_(1.0)                     # evict L2 between timed iterations (outside the event pair)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        n_launch = _lib.launch_count - n0
+        barrier()
+        t = torch.tensor([total], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / 1e3, n_launch
+
+    with ClockSampler(local_rank) as clk:
+        sec, gpu_launches = timed(one_pass_resident, args.warmup, args.steps)   # libsvsk launches, timed region only
+        sec_e2e, _ = timed(one_pass_e2e, 1, args.steps)
+
+    # dominant kernel: the fused block (20 launches per DDPM step).  Timed live: 10 x 20 launches between two events.
+    plan = den.bf16_plan()
+    from ensemble_svs_with_interactions_b200 import ops
+    condb, _ = ops.nct_to_ntc(cond_dev.transpose(1, 2).contiguous())
+    x32s = torch.randn(B, T, plan.Mp, device=dev)
+    table = m._step_table()
+    sb = [tl[50] for tl in table]
+    xb0 = torch.randn(B, T, plan.C, device=dev).to(torch.bfloat16)
+    xb1 = torch.empty_like(xb0)
+    x32 = torch.randn(B, T, plan.C, device=dev)
+    skip32 = torch.zeros(B, T, plan.C, device=dev)
+
+    def blocks():
+        cur, nxt = xb0, xb1
+        for i, lw in enumerate(plan.layers):
+            ops.diffnet_block_bf16(cur, nxt, x32, skip32, condb, lw["w1p"], lw["woutp"], sb[i], lw["bout"],
+                                   dilation=lw["dilation"], stepbias_batch_stride=0, init_skip=(i == 0), write_x=True)
+            cur, nxt = nxt, cur
+
+    for _ in range(3):
+        blocks()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        blocks()
+    e1.record()
+    e1.synchronize()
+    block_ms = e0.elapsed_time(e1) / (reps * len(plan.layers))
+    flops_per_launch = 2.0 * B * T * BLOCK_MAC_PER_FRAME
+    peaks = _peaks()
+    peak_tf = (peaks or {}).get("bf16_tflops_sustained", 1400.0)
+    achieved_tf = flops_per_launch / (block_ms * 1e-3) / 1e12
+
+    if rank == 0:
+        total_units = world * B * T * K_STEP * args.steps
+        value = total_units / sec
+        e2e = total_units / sec_e2e
+        line = {
+            "metric": "denoiser frame-steps/sec (DiffNet 20x256, 100-step DDPM sampling)",
+            "value": value, "unit": "frame-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"DiffNet(80,256,L20,C256) DDPM sampling, {B} tracks x {T} frames per GPU, "
+                                   f"K_step={K_STEP}", "precision": den.resolved_precision(),
+                       "sharding": "one 6-track batch per rank, no collective",
+                       "l2": "256 MB flush between timed passes; 384 MB noise tensor per pass > L2",
+                       "audio_sec_per_sec_equiv": value / K_STEP / 200.0},
+            "e2e": {"value": e2e, "unit": "frame-steps/s", "h2d_bytes_per_step": cond_host.numel() * 4,
+                    "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": 1e3 * sec_e2e / args.steps},
+            "gpu_launches": gpu_launches,
+            "clocks": clk.summary(),
+            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf, "traffic": None, "kernel": "diffnet_block_kernel",
+                         "us_per_launch": block_ms * 1e3, "flops_per_launch": flops_per_launch,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400"},
+            "whole_pass_tflops": 2.0 * MAC_PER_FRAME_STEP * B * T * K_STEP * args.steps * world / sec / 1e12,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample, dt = cpu_baseline(sample_steps=2)
+            line["cpu_baseline"] = {"value": v, "unit": "frame-steps/s", "cores": cores, "kind": "port",
+                                    "sample": sample, "seconds": dt}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,135 @@
+"""ctypes binding of libsvsk.so (include/svsk.h).
+
+There is no fallback: if the library is missing or a call fails, a RuntimeError is raised with the
+library's own message (``svsk_last_error``).  PyTorch is only used for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libsvsk.so")
+
+_lib = None
+_lock = threading.Lock()
+
+
+class Conv1dF32Params(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("in_bias", C.c_void_p),
+        ("residual", C.c_void_p), ("idx_past", C.c_void_p), ("idx_future", C.c_void_p), ("y", C.c_void_p),
+        ("B", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32), ("T", C.c_int32),
+        ("ksize", C.c_int32), ("dilation", C.c_int32), ("tap_origin", C.c_int32), ("pad_mode", C.c_int32),
+        ("accumulate", C.c_int32), ("act", C.c_int32), ("in_relu", C.c_int32), ("out_scale", C.c_float),
+    ]
+
+
+class DiffnetBlockParams(C.Structure):
+    _fields_ = [
+        ("xb_in", C.c_void_p), ("xb_out", C.c_void_p), ("x32", C.c_void_p), ("skip32", C.c_void_p),
+        ("cond", C.c_void_p), ("w1p", C.c_void_p), ("woutp", C.c_void_p), ("stepbias", C.c_void_p),
+        ("bout", C.c_void_p),
+        ("B", C.c_int32), ("T", C.c_int32), ("C", C.c_int32), ("H", C.c_int32),
+        ("dilation", C.c_int32), ("stepbias_batch_stride", C.c_int32), ("init_skip", C.c_int32),
+        ("write_x", C.c_int32), ("time_tile", C.c_int32),
+    ]
+
+
+class LinearBf16Params(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("y_bf16", C.c_void_p), ("y_f32", C.c_void_p),
+        ("N", C.c_int64), ("K", C.c_int32), ("Cout", C.c_int32),
+        ("lda", C.c_int32), ("ldy_b", C.c_int32), ("ldy_f", C.c_int32), ("act", C.c_int32),
+    ]
+
+
+class UsfganBlockParams(C.Structure):
+    _fields_ = [
+        ("xb_in", C.c_void_p), ("xb_out", C.c_void_p), ("aux", C.c_void_p),
+        ("w1p", C.c_void_p), ("woutp", C.c_void_p), ("bias1", C.c_void_p), ("bout", C.c_void_p),
+        ("idx_past", C.c_void_p), ("idx_future", C.c_void_p),
+        ("B", C.c_int32), ("T", C.c_int32), ("C", C.c_int32), ("A", C.c_int32),
+        ("dilation", C.c_int32), ("adaptive", C.c_int32),
+    ]
+
+
+# name -> argtypes (all return int except where noted)
+_V, _I, _F, _Z = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_SIGNATURES = {
+    "svsk_version": [],
+    "svsk_device_check": [_I],
+    "svsk_conv1d_f32": [C.POINTER(Conv1dF32Params), _V],
+    "svsk_gated_act_f32": [_V, _V, _I, _I, _I, _I, _V],
+    "svsk_diffnet_residual_skip_f32": [_V, _V, _V, _I, _I, _I, _I, _V],
+    "svsk_scale_act_f32": [_V, _V, _Z, _F, _I, _V],
+    "svsk_sinusoidal_embedding_f32": [_V, _V, _I, _I, _V],
+    "svsk_ddpm_update_f32": [_V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _I, _Z, _I, _V],
+    "svsk_q_sample_f32": [_V, _V, _V, _V, _V, _V, _I, _Z, _V],
+    "svsk_plms_transfer_f32": [_V, _V, _V, _V, _I, _V, _I, _Z, _V],
+    "svsk_lincomb_f32": [C.POINTER(C.c_void_p), C.POINTER(C.c_float), _I, _V, _Z, _V],
+    "svsk_pd_index": [_V, _V, _V, _I, _I, _I, _V],
+    "svsk_upsample_smooth_f32": [_V, _V, _V, _I, _I, _I, _V],
+    "svsk_periodic_mix_f32": [_V, _V, _V, _V, _V, _V, _Z, _V],
+    "svsk_nct_to_ntc": [_V, _V, _V, _I, _I, _I, _I, _V],
+    "svsk_ntc_to_nct_f32": [_V, _V, _I, _I, _I, _I, _F, _V],
+    "svsk_cast_scale_bf16": [_V, _V, _Z, _F, _I, _V],
+    "svsk_diffnet_block_bf16": [C.POINTER(DiffnetBlockParams), _V],
+    "svsk_diffnet_pack_block": [_V, _V, _V, _V, _V, _I, _I, _V],
+    "svsk_diffnet_packed_row": [_I, _I],
+    "svsk_linear_bf16": [C.POINTER(LinearBf16Params), _V],
+}
+EXPORTED_SYMBOLS = ["svsk_last_error"] + list(_SIGNATURES)
+
+
+def lib() -> C.CDLL:
+    """Loads libsvsk.so (once).  Raises if it has not been built — there is no other code path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} not found: build it with `python -m ensemble_svs_with_interactions_b200.csrc.build` "
+                    "(or __graft_entry__.build()).  This package has no CPU or PyTorch fallback.")
+            l = C.CDLL(LIB_PATH)
+            l.svsk_last_error.restype = C.c_char_p
+            l.svsk_last_error.argtypes = []
+            for name, args in _SIGNATURES.items():
+                fn = getattr(l, name)
+                fn.argtypes = args
+                fn.restype = C.c_int
+            _lib = l
+    return _lib
+
+
+launch_count = 0  # successful libsvsk kernel enqueues of this process (bench.py's gpu_launches evidence)
+
+
+def check(rc: int, what: str) -> None:
+    global launch_count
+    launch_count += 1
+    if rc != 0:
+        msg = lib().svsk_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libsvsk {what} failed (code {rc}): {msg}")
+
+
+def stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t, dtype=None, name="tensor"):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return C.c_void_p(0)
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: libsvsk has no CPU path")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous, got strides {t.stride()} for shape {tuple(t.shape)}")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    return C.c_void_p(t.data_ptr())

@@ -1,0 +1,203 @@
+// Time-major bf16 GEMM with fused bias/activation epilogue on tcgen05: Y[n][co] = act(A[n][:] . W[co][:] + b[co]).
+// Replaces the 1x1 projections around the stacks (denoiser.py:110-112,121-123; generator.py:461-466,492-493).
+// M = 128 time rows per CTA (TMEM lanes), N = Cout (<= 256 columns), K streamed in 64-channel TMA boxes.
+#include <cuda_bf16.h>
+
+#include "sm100_ptx.cuh"
+#include "svsk_common.cuh"
+#include "tma_util.cuh"
+
+namespace svsk {
+
+constexpr int kLinStages = 4;
+constexpr int kLinABytes = 128 * 128;  // 128 rows x 64 bf16
+
+struct LinearArgs {
+  const float* bias;
+  __nv_bfloat16* y_b;
+  float* y_f;
+  long long N;
+  int K, Cout, ldy_b, ldy_f, act, tmem_cols;
+};
+
+struct __align__(8) LinearBarriers {
+  uint64_t full[kLinStages];
+  uint64_t empty[kLinStages];
+  uint64_t d_full;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float lin_act(float v, int act) {
+  if (act == SVSK_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == SVSK_ACT_SIGMOID) return ptx::sigmoid_approx(v);
+  return v;
+}
+
+__global__ void __launch_bounds__(192, 1)
+linear_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+                   const LinearArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int wbytes = a.Cout * 128;
+  const int stage_bytes = kLinABytes + wbytes;
+  LinearBarriers* bars = reinterpret_cast<LinearBarriers*>(smem + kLinStages * stage_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long n0 = (long long)blockIdx.x * 128;
+  const int KB = (a.K + 63) / 64;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_a);
+    ptx::prefetch_tmap(&tm_w);
+    for (int i = 0; i < kLinStages; ++i) {
+      ptx::mbar_init(&bars->full[i], 1);
+      ptx::mbar_init(&bars->empty[i], 1);
+    }
+    ptx::mbar_init(&bars->d_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&bars->tmem_base, a.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < KB; ++kb) {
+        ptx::mbar_wait(&bars->empty[s], ph ^ 1);
+        uint8_t* As = smem + s * stage_bytes;
+        ptx::mbar_arrive_expect_tx(&bars->full[s], stage_bytes);
+        ptx::tma_load_2d(As, &tm_a, &bars->full[s], kb * 64, (int)n0);
+        ptx::tma_load_2d(As + kLinABytes, &tm_w, &bars->full[s], kb * 64, 0);
+        if (++s == kLinStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16_f32(128, a.Cout);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < KB; ++kb) {
+        ptx::mbar_wait(&bars->full[s], ph);
+        ptx::tc_fence_after();
+        const uint32_t a0 = ptx::smem_u32(smem + s * stage_bytes);
+        const uint32_t b0 = a0 + kLinABytes;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+          ptx::umma_bf16(tmem, ptx::umma_desc_k_sw128(a0 + k4 * 32), ptx::umma_desc_k_sw128(b0 + k4 * 32), idesc,
+                         (kb | k4) != 0);
+        ptx::umma_commit(&bars->empty[s]);
+        if (++s == kLinStages) { s = 0; ph ^= 1; }
+      }
+      ptx::umma_commit(&bars->d_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const long long n = n0 + q * 32 + lane;
+    ptx::mbar_wait(&bars->d_full, 0);
+    ptx::tc_fence_after();
+    const bool vec_f = a.y_f && (a.ldy_f % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.y_f) & 15) == 0);
+    const bool vec_b = a.y_b && (a.ldy_b % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.y_b) & 15) == 0);
+    for (int c0 = 0; c0 < a.Cout; c0 += 16) {
+      uint32_t r[16];
+      ptx::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, r);
+      ptx::tmem_ld_wait();
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = lin_act(__uint_as_float(r[i]) + (a.bias ? a.bias[c0 + i] : 0.f), a.act);
+      if (n < a.N) {
+        if (a.y_f) {
+          float* dst = a.y_f + n * a.ldy_f + c0;
+          if (vec_f) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dst[i] = v[i];
+          }
+        }
+        if (a.y_b) {
+          __nv_bfloat16* dst = a.y_b + n * a.ldy_b + c0;
+          if (vec_b) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+              pk[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dst[i] = __float2bfloat16_rn(v[i]);
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem, a.tmem_cols);
+}
+
+}  // namespace svsk
+
+using namespace svsk;
+
+extern "C" int svsk_linear_bf16(const svsk_linear_bf16_params* pp, void* stream) {
+  SVSK_REQUIRE(pp != nullptr, SVSK_E_ARG, "linear_bf16: null params");
+  const svsk_linear_bf16_params& p = *pp;
+  SVSK_REQUIRE(p.a && p.w && (p.y_bf16 || p.y_f32), SVSK_E_ARG, "linear_bf16: null tensor");
+  SVSK_REQUIRE(p.N > 0 && p.N < (1ll << 31), SVSK_E_ARG, "linear_bf16: N=%lld", (long long)p.N);
+  SVSK_REQUIRE(p.K > 0 && p.K % 8 == 0, SVSK_E_ARG, "linear_bf16: K=%d must be a multiple of 8", p.K);
+  SVSK_REQUIRE(p.Cout >= 16 && p.Cout <= 256 && p.Cout % 16 == 0, SVSK_E_ARG,
+               "linear_bf16: Cout=%d must be a multiple of 16 in [16,256]", p.Cout);
+  SVSK_REQUIRE(p.lda >= p.K && p.lda % 8 == 0, SVSK_E_ALIGN, "linear_bf16: lda=%d", p.lda);
+  SVSK_REQUIRE(!p.y_bf16 || p.ldy_b >= p.Cout, SVSK_E_ARG, "linear_bf16: ldy_b");
+  SVSK_REQUIRE(!p.y_f32 || p.ldy_f >= p.Cout, SVSK_E_ARG, "linear_bf16: ldy_f");
+  int rc = require_sm100();
+  if (rc) return rc;
+
+  CUtensorMap tm_a, tm_w;
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
+    uint64_t str[1] = {(uint64_t)p.lda * 2};
+    uint32_t box[2] = {64, 128};
+    if ((rc = make_tmap_bf16(&tm_a, p.a, 2, dims, str, box))) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.Cout};
+    uint64_t str[1] = {(uint64_t)p.K * 2};
+    uint32_t box[2] = {64, (uint32_t)p.Cout};
+    if ((rc = make_tmap_bf16(&tm_w, p.w, 2, dims, str, box))) return rc;
+  }
+  const int stage_bytes = kLinABytes + p.Cout * 128;
+  const int smem_bytes = kLinStages * stage_bytes + (int)sizeof(LinearBarriers) + 1024;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static bool attr_set[64] = {false};
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(linear_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return fail((int)e, "linear_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  LinearArgs a;
+  a.bias = p.bias;
+  a.y_b = (__nv_bfloat16*)p.y_bf16;
+  a.y_f = p.y_f32;
+  a.N = p.N;
+  a.K = p.K;
+  a.Cout = p.Cout;
+  a.ldy_b = p.ldy_b;
+  a.ldy_f = p.ldy_f;
+  a.act = p.act;
+  a.tmem_cols = p.Cout <= 32 ? 32 : (p.Cout <= 64 ? 64 : (p.Cout <= 128 ? 128 : 256));
+  unsigned grid = (unsigned)((p.N + 127) / 128);
+  linear_bf16_kernel<<<grid, 192, smem_bytes, as_stream(stream)>>>(tm_a, tm_w, a);
+  return check_launch("linear_bf16");
+}

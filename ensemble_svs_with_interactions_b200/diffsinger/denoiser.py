@@ -1,0 +1,261 @@
+"""DiffNet denoiser — drop-in for ``nnsvs.diffsinger.denoiser.DiffNet`` (nnsvs/diffsinger/denoiser.py:69-124).
+
+Same constructor kwargs, ``forward(spec, diffusion_step, cond)`` signature and ``state_dict`` keys/shapes.  The
+``nn.Conv1d`` / ``nn.Linear`` sub-modules only HOLD the parameters (so checkpoints load with strict=True); the
+arithmetic runs in libsvsk:
+
+* ``precision="bf16"``: one fused tcgen05 kernel per residual layer (svsk_diffnet_block_bf16) + tcgen05 1x1
+  projections (svsk_linear_bf16); fp32 residual/skip masters, bf16 MMA operands, fp32 accumulation.
+* ``precision="fp32"``: CUDA-core kernels in the reference's own fp32 arithmetic (svsk_conv1d_f32 ...).
+* ``precision="auto"`` (default): bf16 when the shapes fit the tensor-core kernel (C in {128,256}, H % 64 == 0),
+  else fp32.  Both are CUDA kernels of this library; there is no PyTorch/CPU path for the forward pass.
+"""
+from __future__ import annotations
+
+import math
+from math import sqrt
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+f32 = torch.float32
+bf16 = torch.bfloat16
+
+
+def _ceil_to(v, m):
+    return (v + m - 1) // m * m
+
+
+class Mish(nn.Module):
+    """Parameter-free placeholder keeping ``mlp`` indices (mlp.0 / mlp.2) identical to denoiser.py:84-86.
+    The activation itself runs inside svsk_conv1d_f32 (SVSK_ACT_MISH)."""
+
+    def forward(self, x):  # pragma: no cover - never on the product path
+        raise RuntimeError("Mish is evaluated inside libsvsk; call DiffNet.forward")
+
+
+class SinusoidalPosEmb(nn.Module):
+    """denoiser.py:14-26, evaluated by svsk_sinusoidal_embedding_f32."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+
+    def forward(self, x):
+        return ops.sinusoidal_embedding_f32(x, self.dim)
+
+
+def Conv1d(*args, **kwargs):
+    """Parameter holder with the reference's kaiming-normal init (denoiser.py:29-32)."""
+    layer = nn.Conv1d(*args, **kwargs)
+    nn.init.kaiming_normal_(layer.weight)
+    return layer
+
+
+class ResidualBlock(nn.Module):
+    """Parameter holder for one gated block (denoiser.py:40-52); computed by DiffNet's engine."""
+
+    def __init__(self, encoder_hidden, residual_channels, dilation):
+        super().__init__()
+        self.dilation = dilation
+        self.dilated_conv = Conv1d(residual_channels, 2 * residual_channels, 3, padding=dilation, dilation=dilation)
+        self.diffusion_projection = nn.Linear(residual_channels, residual_channels)
+        self.conditioner_projection = Conv1d(encoder_hidden, 2 * residual_channels, 1)
+        self.output_projection = Conv1d(residual_channels, 2 * residual_channels, 1)
+
+    def forward(self, x, conditioner, diffusion_step):
+        """Stand-alone block call in fp32 (same maths as denoiser.py:54-66)."""
+        dp = ops.linear_f32(diffusion_step.contiguous(), self.diffusion_projection.weight, self.diffusion_projection.bias)
+        return _block_fp32(self, x.contiguous(), conditioner.contiguous(), dp)
+
+
+def _block_fp32(layer: ResidualBlock, x, cond, dp, skip=None, init_skip=True):
+    y = ops.conv1d_f32(x, layer.dilated_conv.weight, layer.dilated_conv.bias, dilation=layer.dilation, tap_origin=1,
+                       pad_mode=ops.PAD_ZEROS, in_bias=dp)
+    ops.conv1d_f32(cond, layer.conditioner_projection.weight, layer.conditioner_projection.bias, out=y, accumulate=True)
+    z = ops.gated_act_f32(y, ops.GATE_SIGMOID_TANH)
+    o = ops.conv1d_f32(z, layer.output_projection.weight, layer.output_projection.bias)
+    if skip is None:
+        C = x.shape[1]
+        x_new = x.clone()
+        skip = torch.empty_like(x)
+        ops.diffnet_residual_skip_f32(o, x_new, skip, True)
+        return x_new, skip
+    ops.diffnet_residual_skip_f32(o, x, skip, init_skip)
+    return x, skip
+
+
+class _Bf16Plan:
+    """Packed weights of one DiffNet for the tensor-core path (rebuilt when any parameter changes)."""
+
+    def __init__(self, net: "DiffNet", device):
+        C, H, M, L = net.residual_channels, net.encoder_hidden_dim, net.in_dim, len(net.residual_layers)
+        self.C, self.H, self.M, self.L = C, H, M, L
+        self.Mp = _ceil_to(M, 16)
+        with torch.no_grad():
+            perm = ops.diffnet_packed_rows(C).to(device)  # reference row -> packed row
+            w_in = torch.zeros((C, self.Mp), device=device, dtype=f32)
+            w_in[:, :M] = net.input_projection.weight[:, :, 0]
+            self.w_in = w_in.to(bf16).contiguous()
+            self.b_in = net.input_projection.bias.detach().to(f32).contiguous()
+            self.w_skip = net.skip_projection.weight[:, :, 0].to(bf16).contiguous()
+            self.b_skip = net.skip_projection.bias.detach().to(f32).contiguous()
+            w_out = torch.zeros((self.Mp, C), device=device, dtype=f32)
+            w_out[:M] = net.output_projection.weight[:, :, 0]
+            self.w_out = w_out.to(bf16).contiguous()
+            b_out = torch.zeros((self.Mp,), device=device, dtype=f32)
+            b_out[:M] = net.output_projection.bias
+            self.b_out = b_out
+            self.layers = []
+            for layer in net.residual_layers:
+                dw = layer.dilated_conv.weight.detach().to(f32)
+                cw = layer.conditioner_projection.weight.detach().to(f32)
+                ow = layer.output_projection.weight.detach().to(f32)
+                w1p, woutp = ops.diffnet_pack_block(dw, cw, ow)
+                # step-embedding taps: stepw[j*2C + perm[r]] = dilated_w[r, :, j]  (so that stepbias = stepw @ dp + stepb
+                # gives, per tap j, W_j . (diffusion_projection(e)) in packed row order); the conv and conditioner
+                # biases ride on the centre tap, which every frame has.
+                stepw = torch.zeros((3 * 2 * C, C), device=device, dtype=f32)
+                stepb = torch.zeros((3 * 2 * C,), device=device, dtype=f32)
+                for j in range(3):
+                    stepw[j * 2 * C + perm] = dw[:, :, j]
+                stepb[2 * C + perm] = layer.dilated_conv.bias.detach().to(f32) + layer.conditioner_projection.bias.detach().to(f32)
+                self.layers.append(dict(
+                    w1p=w1p, woutp=woutp, dilation=layer.dilation,
+                    bout=layer.output_projection.bias.detach().to(f32).contiguous(),
+                    stepw=stepw.unsqueeze(-1).contiguous(), stepb=stepb,
+                    dpw=layer.diffusion_projection.weight.detach().to(f32).contiguous(),
+                    dpb=layer.diffusion_projection.bias.detach().to(f32).contiguous()))
+        self.step_table = None  # [L][K, 3*2C], filled by GaussianDiffusion for t = 0..K-1
+
+
+class DiffNet(nn.Module):
+    def __init__(self, in_dim=80, encoder_hidden_dim=256, residual_layers=20, residual_channels=256,
+                 dilation_cycle_length=4, precision="auto"):
+        super().__init__()
+        self.in_dim = in_dim
+        self.encoder_hidden_dim = encoder_hidden_dim
+        self.residual_channels = residual_channels
+        self.precision = precision
+
+        self.input_projection = Conv1d(in_dim, residual_channels, 1)
+        self.diffusion_embedding = SinusoidalPosEmb(residual_channels)
+        dim = residual_channels
+        self.mlp = nn.Sequential(nn.Linear(dim, dim * 4), Mish(), nn.Linear(dim * 4, dim))
+        self.residual_layers = nn.ModuleList(
+            [ResidualBlock(encoder_hidden_dim, residual_channels, 2 ** (i % dilation_cycle_length))
+             for i in range(residual_layers)])
+        self.skip_projection = Conv1d(residual_channels, residual_channels, 1)
+        self.output_projection = Conv1d(residual_channels, in_dim, 1)
+        nn.init.zeros_(self.output_projection.weight)
+        self._plan = None
+        self._plan_key = None
+
+    # ------------------------------------------------------------------ precision / plans
+    def resolved_precision(self) -> str:
+        ok = self.residual_channels in (128, 256) and self.encoder_hidden_dim % 64 == 0
+        if self.precision == "auto":
+            return "bf16" if ok else "fp32"
+        if self.precision == "bf16" and not ok:
+            raise RuntimeError("DiffNet precision='bf16' needs residual_channels in {128,256} and "
+                               f"encoder_hidden_dim % 64 == 0 (got {self.residual_channels}, {self.encoder_hidden_dim})")
+        if self.precision not in ("bf16", "fp32"):
+            raise RuntimeError(f"unknown precision {self.precision!r}")
+        return self.precision
+
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def bf16_plan(self) -> _Bf16Plan:
+        key = self._param_key()
+        if self._plan is None or self._plan_key != key:
+            self._plan = _Bf16Plan(self, self.input_projection.weight.device)
+            self._plan_key = key
+        return self._plan
+
+    # ------------------------------------------------------------------ step embedding (denoiser.py:113-114)
+    def step_embedding(self, t):
+        """mlp(SinusoidalPosEmb(t)) -> (Bt, C) fp32, all in libsvsk."""
+        emb = self.diffusion_embedding(t)
+        h = ops.linear_f32(emb, self.mlp[0].weight, self.mlp[0].bias, act=ops.ACT_MISH)
+        return ops.linear_f32(h, self.mlp[2].weight, self.mlp[2].bias)
+
+    def step_bias_bf16(self, t):
+        """Per-layer [Bt, 3*2C] tap biases for the fused kernel (packed row order)."""
+        plan = self.bf16_plan()
+        e = self.step_embedding(t)
+        out = []
+        for lw in plan.layers:
+            dp = ops.linear_f32(e, lw["dpw"], lw["dpb"])
+            out.append(ops.linear_f32(dp, lw["stepw"], lw["stepb"]))
+        return out
+
+    # ------------------------------------------------------------------ engines
+    def denoise_ntc_bf16(self, x32s, condb, stepbias, stride, plan=None):
+        """x32s [B,T,Mp] fp32 (channels >= M are ignored), condb [B,T,H] bf16, stepbias: list of L tensors.
+        Returns eps [B,T,Mp] fp32 (padded channels = 0)."""
+        plan = self.bf16_plan() if plan is None else plan
+        B, T, _ = x32s.shape
+        C, L = plan.C, plan.L
+        dev = x32s.device
+        specb = ops.cast_scale_bf16(x32s)
+        xb0 = torch.empty((B, T, C), device=dev, dtype=bf16)
+        xb1 = torch.empty((B, T, C), device=dev, dtype=bf16)
+        x32 = torch.empty((B, T, C), device=dev, dtype=f32)
+        skip32 = torch.empty((B, T, C), device=dev, dtype=f32)
+        ops.linear_bf16(specb, plan.w_in, plan.b_in, act=ops.ACT_RELU, out_bf16=xb0, out_f32=x32)
+        cur, nxt = xb0, xb1
+        for i, lw in enumerate(plan.layers):
+            ops.diffnet_block_bf16(cur, nxt, x32, skip32, condb, lw["w1p"], lw["woutp"], stepbias[i], lw["bout"],
+                                   dilation=lw["dilation"], stepbias_batch_stride=stride, init_skip=(i == 0),
+                                   write_x=(i < L - 1), time_tile=getattr(self, "time_tile", 0))
+            cur, nxt = nxt, cur
+        skipb = ops.cast_scale_bf16(skip32, alpha=1.0 / sqrt(L))
+        hb, _ = ops.linear_bf16(skipb, plan.w_skip, plan.b_skip, act=ops.ACT_RELU, want_bf16=True)
+        _, eps = ops.linear_bf16(hb, plan.w_out, plan.b_out, want_f32=True)
+        return eps
+
+    def denoise_nct_fp32(self, x_in, cond, t):
+        """x_in [B,M,T], cond [B,H,T], t [B] -> eps [B,M,T]; the reference's fp32 arithmetic."""
+        L = len(self.residual_layers)
+        x = ops.conv1d_f32(x_in, self.input_projection.weight, self.input_projection.bias, act=ops.ACT_RELU)
+        e = self.step_embedding(t)
+        skip = torch.empty_like(x)
+        for i, layer in enumerate(self.residual_layers):
+            dp = ops.linear_f32(e, layer.diffusion_projection.weight, layer.diffusion_projection.bias)
+            _block_fp32(layer, x, cond, dp, skip, init_skip=(i == 0))
+        s = ops.scale_act_f32(skip, alpha=1.0 / sqrt(L))
+        h = ops.conv1d_f32(s, self.skip_projection.weight, self.skip_projection.bias, act=ops.ACT_RELU)
+        return ops.conv1d_f32(h, self.output_projection.weight, self.output_projection.bias)
+
+    def _forward_no_grad(self, spec, diffusion_step, cond):
+        x_in = spec[:, 0].to(f32).contiguous()
+        cond = cond.to(f32).contiguous()
+        t = diffusion_step.reshape(-1).to(torch.int64).contiguous()
+        if self.resolved_precision() == "fp32":
+            return self.denoise_nct_fp32(x_in, cond, t)[:, None]
+        plan = self.bf16_plan()
+        _, x32s = ops.nct_to_ntc(x_in, Cp=plan.Mp, want_bf16=False, want_f32=True)
+        condb, _ = ops.nct_to_ntc(cond)
+        sb = self.step_bias_bf16(t)
+        eps = self.denoise_ntc_bf16(x32s, condb, sb, stride=6 * plan.C)
+        return ops.ntc_to_nct_f32(eps, plan.M)[:, None]
+
+    def forward(self, spec, diffusion_step, cond):
+        """
+        :param spec: [B, 1, M, T]
+        :param diffusion_step: [B] (int64 step indices)
+        :param cond: [B, H, T]
+        :return: [B, 1, M, T]
+        """
+        if not spec.is_cuda:
+            raise RuntimeError("DiffNet runs on CUDA (sm_100a) only: libsvsk has no CPU path")
+        needs_grad = torch.is_grad_enabled() and (
+            spec.requires_grad or cond.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if needs_grad:
+            from .training import diffnet_forward_with_grad
+            return diffnet_forward_with_grad(self, spec, diffusion_step, cond)
+        with torch.no_grad():
+            return self._forward_no_grad(spec, diffusion_step, cond)

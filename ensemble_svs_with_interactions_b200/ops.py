@@ -1,0 +1,253 @@
+"""Host-side wrappers: one Python function per libsvsk entry point (include/svsk.h).
+
+Every function only enqueues kernels on the current CUDA stream; outputs are allocated with the caching
+allocator (or taken from ``out=``) so whole loops are CUDA-graph capturable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+PAD_ZEROS, PAD_REFLECT, PAD_REPLICATE, PAD_VALID, PAD_INDEXED = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_MISH = 0, 1, 2, 3
+GATE_SIGMOID_TANH, GATE_TANH_SIGMOID = 0, 1
+
+f32 = torch.float32
+bf16 = torch.bfloat16
+
+
+def conv1d_f32(x, w, bias=None, *, dilation=1, tap_origin=None, pad_mode=PAD_ZEROS, in_bias=None, residual=None,
+               idx=None, out=None, accumulate=False, act=ACT_NONE, in_relu=False, out_scale=1.0):
+    """svsk_conv1d_f32: x [B,Cin,T_in], w [Cout,Cin,k] -> y [B,Cout,T]."""
+    B, Cin, T_in = x.shape
+    Cout, Cin_w, k = w.shape
+    if Cin_w != Cin:
+        raise RuntimeError(f"conv1d_f32: weight expects {Cin_w} input channels, got {Cin}")
+    if tap_origin is None:
+        tap_origin = (k - 1) // 2
+    T = T_in - (k - 1) * dilation if pad_mode == PAD_VALID else T_in
+    if out is None:
+        if accumulate:
+            raise RuntimeError("conv1d_f32: accumulate needs out=")
+        out = torch.empty((B, Cout, T), device=x.device, dtype=f32)
+    p = L.Conv1dF32Params()
+    p.x, p.w, p.y = L.ptr(x, f32, "x"), L.ptr(w, f32, "w"), L.ptr(out, f32, "out")
+    p.bias, p.in_bias, p.residual = L.ptr(bias, f32, "bias"), L.ptr(in_bias, f32, "in_bias"), L.ptr(residual, f32, "residual")
+    if idx is not None:
+        p.idx_past, p.idx_future = L.ptr(idx[0], torch.int32, "idx_past"), L.ptr(idx[1], torch.int32, "idx_future")
+    p.B, p.Cin, p.Cout, p.T = B, Cin, Cout, T
+    p.ksize, p.dilation, p.tap_origin, p.pad_mode = k, dilation, tap_origin, pad_mode
+    p.accumulate, p.act, p.in_relu, p.out_scale = int(accumulate), act, int(in_relu), float(out_scale)
+    L.check(L.lib().svsk_conv1d_f32(C.byref(p), L.stream_ptr()), "conv1d_f32")
+    return out
+
+
+def linear_f32(x, w, bias=None, act=ACT_NONE):
+    """nn.Linear on [B,Cin] through the conv kernel (T = 1)."""
+    y = conv1d_f32(x.unsqueeze(-1), w.unsqueeze(-1) if w.dim() == 2 else w, bias, act=act)
+    return y.squeeze(-1)
+
+
+def gated_act_f32(y, order):
+    B, H2, T = y.shape
+    z = torch.empty((B, H2 // 2, T), device=y.device, dtype=f32)
+    L.check(L.lib().svsk_gated_act_f32(L.ptr(y, f32), L.ptr(z), B, H2 // 2, T, order, L.stream_ptr()), "gated_act_f32")
+    return z
+
+
+def diffnet_residual_skip_f32(o, x, skip, init_skip):
+    B, C2, T = o.shape
+    L.check(L.lib().svsk_diffnet_residual_skip_f32(L.ptr(o, f32), L.ptr(x, f32), L.ptr(skip, f32), B, C2 // 2, T,
+                                                   int(init_skip), L.stream_ptr()), "diffnet_residual_skip_f32")
+
+
+def scale_act_f32(x, alpha=1.0, act=ACT_NONE, out=None):
+    out = torch.empty_like(x) if out is None else out
+    L.check(L.lib().svsk_scale_act_f32(L.ptr(x, f32), L.ptr(out, f32), x.numel(), float(alpha), act, L.stream_ptr()),
+            "scale_act_f32")
+    return out
+
+
+def sinusoidal_embedding_f32(t, dim):
+    t = t.to(torch.int64).contiguous()
+    out = torch.empty((t.shape[0], dim), device=t.device, dtype=f32)
+    L.check(L.lib().svsk_sinusoidal_embedding_f32(L.ptr(t, torch.int64), L.ptr(out), t.shape[0], dim, L.stream_ptr()),
+            "sinusoidal_embedding_f32")
+    return out
+
+
+def ddpm_update_f32(x, eps, z, t, tables, clip_denoised=True, out=None):
+    """tables: dict of the reference's registered buffers (fp32 CUDA tensors)."""
+    B = x.shape[0]
+    out = torch.empty_like(x) if out is None else out
+    L.check(L.lib().svsk_ddpm_update_f32(
+        L.ptr(x, f32, "x"), L.ptr(eps, f32, "eps"), L.ptr(z, f32, "z"), L.ptr(out, f32, "out"), L.ptr(t, torch.int64, "t"),
+        L.ptr(tables["sqrt_recip_alphas_cumprod"], f32), L.ptr(tables["sqrt_recipm1_alphas_cumprod"], f32),
+        L.ptr(tables["posterior_mean_coef1"], f32), L.ptr(tables["posterior_mean_coef2"], f32),
+        L.ptr(tables["posterior_log_variance_clipped"], f32), B, x.numel() // B, int(clip_denoised), L.stream_ptr()),
+        "ddpm_update_f32")
+    return out
+
+
+def q_sample_f32(x0, noise, t, tables):
+    B = x0.shape[0]
+    out = torch.empty_like(x0)
+    L.check(L.lib().svsk_q_sample_f32(L.ptr(x0, f32), L.ptr(noise, f32), L.ptr(out), L.ptr(t, torch.int64),
+                                      L.ptr(tables["sqrt_alphas_cumprod"], f32),
+                                      L.ptr(tables["sqrt_one_minus_alphas_cumprod"], f32), B, x0.numel() // B,
+                                      L.stream_ptr()), "q_sample_f32")
+    return out
+
+
+def plms_transfer_f32(x, noise_t, t, interval, alphas_cumprod):
+    B = x.shape[0]
+    out = torch.empty_like(x)
+    L.check(L.lib().svsk_plms_transfer_f32(L.ptr(x, f32), L.ptr(noise_t, f32), L.ptr(out), L.ptr(t, torch.int64),
+                                           int(interval), L.ptr(alphas_cumprod, f32), B, x.numel() // B,
+                                           L.stream_ptr()), "plms_transfer_f32")
+    return out
+
+
+def lincomb_f32(tensors: Sequence[torch.Tensor], coefs: Sequence[float]):
+    n = len(tensors)
+    ptrs = (C.c_void_p * n)(*[L.ptr(t, f32).value for t in tensors])
+    cs = (C.c_float * n)(*[float(c) for c in coefs])
+    out = torch.empty_like(tensors[0])
+    L.check(L.lib().svsk_lincomb_f32(ptrs, cs, n, L.ptr(out), out.numel(), L.stream_ptr()), "lincomb_f32")
+    return out
+
+
+def pd_index(d, dilation):
+    """d (B,1,T) fp32 -> (idx_past, idx_future) int32 [B,T]; -1 marks a zero tap."""
+    B, _, T = d.shape
+    ip = torch.empty((B, T), device=d.device, dtype=torch.int32)
+    iff = torch.empty((B, T), device=d.device, dtype=torch.int32)
+    L.check(L.lib().svsk_pd_index(L.ptr(d, f32, "d"), L.ptr(ip), L.ptr(iff), B, T, int(dilation), L.stream_ptr()),
+            "pd_index")
+    return ip, iff
+
+
+def upsample_smooth_f32(x, taps, scale):
+    """x [B,C,Tin] -> [B,C,Tin*scale]: nearest stretch then (2*scale+1)-tap smoothing."""
+    B, Cc, Tin = x.shape
+    out = torch.empty((B, Cc, Tin * scale), device=x.device, dtype=f32)
+    L.check(L.lib().svsk_upsample_smooth_f32(L.ptr(x, f32), L.ptr(taps, f32), L.ptr(out), B * Cc, Tin, int(scale),
+                                             L.stream_ptr()), "upsample_smooth_f32")
+    return out
+
+
+def periodic_mix_f32(a, h, n, want_parts=False):
+    s = torch.empty_like(h)
+    h2 = torch.empty_like(h) if want_parts else None
+    n2 = torch.empty_like(h) if want_parts else None
+    L.check(L.lib().svsk_periodic_mix_f32(L.ptr(a, f32), L.ptr(h, f32), L.ptr(n, f32), L.ptr(s), L.ptr(h2), L.ptr(n2),
+                                          h.numel(), L.stream_ptr()), "periodic_mix_f32")
+    return s, h2, n2
+
+
+def nct_to_ntc(x, Cp=None, want_bf16=True, want_f32=False, out_bf16=None, out_f32=None):
+    B, Cc, T = x.shape
+    Cp = Cc if Cp is None else Cp
+    if want_bf16 and out_bf16 is None:
+        out_bf16 = torch.empty((B, T, Cp), device=x.device, dtype=bf16)
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty((B, T, Cp), device=x.device, dtype=f32)
+    L.check(L.lib().svsk_nct_to_ntc(L.ptr(x, f32, "x"), L.ptr(out_bf16), L.ptr(out_f32), B, Cc, T, Cp, L.stream_ptr()),
+            "nct_to_ntc")
+    return out_bf16, out_f32
+
+
+def ntc_to_nct_f32(x, Cc, alpha=1.0):
+    B, T, Cp = x.shape
+    y = torch.empty((B, Cc, T), device=x.device, dtype=f32)
+    L.check(L.lib().svsk_ntc_to_nct_f32(L.ptr(x, f32, "x"), L.ptr(y), B, Cc, T, Cp, float(alpha), L.stream_ptr()),
+            "ntc_to_nct_f32")
+    return y
+
+
+def cast_scale_bf16(x, alpha=1.0, relu=False, out=None):
+    out = torch.empty(x.shape, device=x.device, dtype=bf16) if out is None else out
+    L.check(L.lib().svsk_cast_scale_bf16(L.ptr(x, f32, "x"), L.ptr(out, bf16), x.numel(), float(alpha), int(relu),
+                                         L.stream_ptr()), "cast_scale_bf16")
+    return out
+
+
+def diffnet_pack_block(dilated_w, cond_w, out_w):
+    C2, Cc, _ = dilated_w.shape
+    H = cond_w.shape[1]
+    w1p = torch.empty((C2, 3 * Cc + H), device=dilated_w.device, dtype=bf16)
+    woutp = torch.empty((C2, Cc), device=dilated_w.device, dtype=bf16)
+    L.check(L.lib().svsk_diffnet_pack_block(L.ptr(dilated_w.contiguous(), f32), L.ptr(cond_w.contiguous(), f32),
+                                            L.ptr(out_w.contiguous(), f32), L.ptr(w1p), L.ptr(woutp), Cc, H,
+                                            L.stream_ptr()), "diffnet_pack_block")
+    return w1p, woutp
+
+
+def diffnet_packed_rows(Cc):
+    """perm[r] = packed row of reference row r (host-side, for bias / step-weight packing)."""
+    l = L.lib()
+    return torch.tensor([l.svsk_diffnet_packed_row(r, Cc) for r in range(2 * Cc)], dtype=torch.long)
+
+
+def diffnet_block_bf16(xb_in, xb_out, x32, skip32, cond, w1p, woutp, stepbias, bout, *, dilation, stepbias_batch_stride,
+                       init_skip, write_x=True, time_tile=0):
+    B, T, Cc = xb_in.shape
+    p = L.DiffnetBlockParams()
+    p.xb_in, p.xb_out = L.ptr(xb_in, bf16, "xb_in"), L.ptr(xb_out, bf16, "xb_out")
+    p.x32, p.skip32 = L.ptr(x32, f32, "x32"), L.ptr(skip32, f32, "skip32")
+    p.cond, p.w1p, p.woutp = L.ptr(cond, bf16, "cond"), L.ptr(w1p, bf16, "w1p"), L.ptr(woutp, bf16, "woutp")
+    p.stepbias, p.bout = L.ptr(stepbias, f32, "stepbias"), L.ptr(bout, f32, "bout")
+    p.B, p.T, p.C, p.H = B, T, Cc, cond.shape[2]
+    p.dilation, p.stepbias_batch_stride = int(dilation), int(stepbias_batch_stride)
+    p.init_skip, p.write_x, p.time_tile = int(init_skip), int(write_x), int(time_tile)
+    L.check(L.lib().svsk_diffnet_block_bf16(C.byref(p), L.stream_ptr()), "diffnet_block_bf16")
+
+
+def linear_bf16(a, w, bias=None, *, act=ACT_NONE, want_bf16=False, want_f32=False, out_bf16=None, out_f32=None):
+    """a [..., K] bf16 (row-major rows), w [Cout, K] bf16 -> [..., Cout]."""
+    K = a.shape[-1]
+    N = a.numel() // K
+    Cout = w.shape[0]
+    lead = a.shape[:-1]
+    if want_bf16 and out_bf16 is None:
+        out_bf16 = torch.empty((*lead, Cout), device=a.device, dtype=bf16)
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty((*lead, Cout), device=a.device, dtype=f32)
+    p = L.LinearBf16Params()
+    p.a, p.w, p.bias = L.ptr(a, bf16, "a"), L.ptr(w, bf16, "w"), L.ptr(bias, f32, "bias")
+    p.y_bf16, p.y_f32 = L.ptr(out_bf16, bf16), L.ptr(out_f32, f32)
+    p.N, p.K, p.Cout = N, K, Cout
+    p.lda, p.ldy_b, p.ldy_f, p.act = K, Cout, Cout, act
+    L.check(L.lib().svsk_linear_bf16(C.byref(p), L.stream_ptr()), "linear_bf16")
+    return out_bf16, out_f32
+
+
+def usfgan_pack_block(w_taps, w_aux, w_out):
+    """w_taps [G,C,3] (past/current/future or k=3 conv), w_aux [G,A,1], w_out [C,G/2,1] -> packed bf16."""
+    G, Cc, _ = w_taps.shape
+    A = w_aux.shape[1]
+    Ap = (A + 63) // 64 * 64
+    w1p = torch.empty((G, 3 * Cc + Ap), device=w_taps.device, dtype=bf16)
+    woutp = torch.empty((Cc, G // 2), device=w_taps.device, dtype=bf16)
+    L.check(L.lib().svsk_usfgan_pack_block(L.ptr(w_taps.contiguous(), f32), L.ptr(w_aux.contiguous(), f32),
+                                           L.ptr(w_out.contiguous(), f32), L.ptr(w1p), L.ptr(woutp), Cc, A, G,
+                                           L.stream_ptr()), "usfgan_pack_block")
+    return w1p, woutp
+
+
+def usfgan_block_bf16(xb_in, xb_out, aux, w1p, woutp, bias1, bout, *, dilation=1, idx=None):
+    B, T, Cc = xb_in.shape
+    p = L.UsfganBlockParams()
+    p.xb_in, p.xb_out, p.aux = L.ptr(xb_in, bf16, "xb_in"), L.ptr(xb_out, bf16, "xb_out"), L.ptr(aux, bf16, "aux")
+    p.w1p, p.woutp = L.ptr(w1p, bf16), L.ptr(woutp, bf16)
+    p.bias1, p.bout = L.ptr(bias1, f32), L.ptr(bout, f32)
+    if idx is not None:
+        p.idx_past, p.idx_future = L.ptr(idx[0], torch.int32), L.ptr(idx[1], torch.int32)
+    p.B, p.T, p.C, p.A = B, T, Cc, aux.shape[2]
+    p.dilation, p.adaptive = int(dilation), int(idx is not None)
+    L.check(L.lib().svsk_usfgan_block_bf16(C.byref(p), L.stream_ptr()), "usfgan_block_bf16")

@@ -1,0 +1,217 @@
+"""uSFGAN generators with the constructor / forward / state_dict contract of ``nnsvs.usfgan.models.generator``
+(USFGANGenerator generator.py:20-166, CascadeHnUSFGANGenerator :169-356, ParallelHnUSFGANGenerator :359-544).
+
+``forward(x, c, d)`` returns the same tuples as the reference.  ``wave_only=True`` (what USFGANWrapper.inference uses)
+skips the extra ``conv_last`` evaluations of s/h/n that the wrapper throws away (usfgan/__init__.py:63).
+"""
+from logging import getLogger
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ..layers import Conv1d1x1, ResidualBlocks, effective_weight, upsample
+from ..layers.residual_block import PeriodicityEstimator
+from ..utils import index_initial  # noqa: F401  (API parity)
+
+logger = getLogger(__name__)
+f32 = torch.float32
+
+
+def _conv1x1(m, x, in_relu=False):
+    return ops.conv1d_f32(x, effective_weight(m), m.bias, in_relu=in_relu)
+
+
+class _GeneratorBase(nn.Module):
+    def _build_common(self, in_channels, out_channels, residual_channels, skip_channels, aux_channels,
+                      aux_context_window, upsample_params):
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.aux_channels = aux_channels
+        self.n_ch = residual_channels
+        self.upsample_net = getattr(upsample, "ConvInUpsampleNetwork")(
+            **upsample_params, aux_channels=aux_channels, aux_context_window=aux_context_window)
+
+    def _make_conv_last(self, skip_channels, out_channels):
+        return nn.Sequential(nn.ReLU(), Conv1d1x1(skip_channels, skip_channels), nn.ReLU(),
+                             Conv1d1x1(skip_channels, out_channels))
+
+    def _conv_last(self, x):
+        x = _conv1x1(self.conv_last[1], x, in_relu=True)
+        return _conv1x1(self.conv_last[3], x, in_relu=True)
+
+    @staticmethod
+    def _check(x):
+        if not x.is_cuda:
+            raise RuntimeError("uSFGAN generators run on CUDA (sm_100a) only: libsvsk has no CPU path")
+
+    def remove_weight_norm(self):
+        """Remove weight normalization from all layers (generator.py:146-155)."""
+
+        def _remove(m):
+            try:
+                nn.utils.remove_weight_norm(m)
+            except ValueError:
+                return
+
+        self.apply(_remove)
+
+    def apply_weight_norm(self):
+        """Apply old-style weight normalization to every Conv1d / Conv2d holder (generator.py:157-166)."""
+
+        def _apply(m):
+            if isinstance(m, (nn.Conv1d, nn.Conv2d)):
+                nn.utils.weight_norm(m)
+
+        self.apply(_apply)
+
+
+def _with_widths(params, residual_channels, gate_channels, skip_channels, aux_channels):
+    p = dict(params)
+    p.update(residual_channels=residual_channels, gate_channels=gate_channels, skip_channels=skip_channels,
+             aux_channels=aux_channels)
+    return p
+
+
+class USFGANGenerator(_GeneratorBase):
+    def __init__(self,
+                 source_network_params={"blockA": 30, "cycleA": 3, "blockF": 0, "cycleF": 0, "cascade_mode": 0},
+                 filter_network_params={"blockA": 0, "cycleA": 0, "blockF": 30, "cycleF": 3, "cascade_mode": 0},
+                 in_channels=1, out_channels=1, residual_channels=64, gate_channels=128, skip_channels=64,
+                 aux_channels=80, aux_context_window=2, use_weight_norm=True,
+                 upsample_params={"upsample_scales": [5, 4, 3, 2]}):
+        super().__init__()
+        self.conv_first = Conv1d1x1(in_channels, residual_channels)
+        self._build_common(in_channels, out_channels, residual_channels, skip_channels, aux_channels,
+                           aux_context_window, upsample_params)
+        widths = (residual_channels, gate_channels, skip_channels, aux_channels)
+        self.source_network = ResidualBlocks(**_with_widths(source_network_params, *widths))
+        self.filter_network = ResidualBlocks(**_with_widths(filter_network_params, *widths))
+        self.conv_mid = Conv1d1x1(out_channels, skip_channels)
+        self.conv_last = self._make_conv_last(skip_channels, out_channels)
+        if use_weight_norm:
+            self.apply_weight_norm()
+
+    @torch.no_grad()
+    def forward(self, x, c, d):
+        """x (B,1,T), c (B,C,T'), d (B,1,T) -> (x, s)   (generator.py:113-144)."""
+        self._check(x)
+        cache = {}
+        c = self.upsample_net(c)
+        assert c.size(-1) == x.size(-1)
+        x = _conv1x1(self.conv_first, x.to(f32).contiguous())
+        x = self.source_network(x, c, d, idx_cache=cache)
+        s = self._conv_last(x)
+        x = _conv1x1(self.conv_mid, s)
+        x = self.filter_network(x, c, d, idx_cache=cache)
+        return self._conv_last(x), s
+
+
+class _HnBase(_GeneratorBase):
+    supports_wave_only = True
+    has_merge = False
+
+    def _build_hn(self, harmonic_network_params, noise_network_params, filter_network_params,
+                  periodicity_estimator_params, in_channels, out_channels, residual_channels, gate_channels,
+                  skip_channels, aux_channels, aux_context_window, upsample_params):
+        # registration order == the reference's, so state_dict key order matches too
+        self.conv_first_sine = Conv1d1x1(in_channels, residual_channels)
+        self.conv_first_noise = Conv1d1x1(in_channels, residual_channels)
+        if self.has_merge:
+            self.conv_merge = Conv1d1x1(residual_channels * 2, residual_channels)
+        self._build_common(in_channels, out_channels, residual_channels, skip_channels, aux_channels,
+                           aux_context_window, upsample_params)
+
+    def _build_networks(self, harmonic_network_params, noise_network_params, filter_network_params,
+                        periodicity_estimator_params, residual_channels, gate_channels, skip_channels, aux_channels,
+                        out_channels):
+        widths = (residual_channels, gate_channels, skip_channels, aux_channels)
+        self.harmonic_network = ResidualBlocks(**_with_widths(harmonic_network_params, *widths))
+        self.noise_network = ResidualBlocks(**_with_widths(noise_network_params, *widths))
+        self.filter_network = ResidualBlocks(**_with_widths(filter_network_params, *widths))
+        # NB like the reference (generator.py:453-455) the estimator's width is NOT tied to residual_channels:
+        # it is 64 unless periodicity_estimator_params carries "residual_channels".
+        self.periodicity_estimator = PeriodicityEstimator(**periodicity_estimator_params, in_channels=aux_channels)
+        self.conv_last = self._make_conv_last(skip_channels, out_channels)
+
+    def _front(self, x, c):
+        c = self.upsample_net(c)
+        assert c.size(-1) == x.size(-1)
+        a = self.periodicity_estimator(c)
+        x = x.to(f32)
+        sine, noise = x[:, 0:1].contiguous(), x[:, 1:2].contiguous()
+        return c, a, _conv1x1(self.conv_first_sine, sine), _conv1x1(self.conv_first_noise, noise)
+
+    def _outputs(self, y, s, h, n, a, wave_only):
+        y = self._conv_last(y)
+        if wave_only:
+            return y, None, None, None, a
+        return y, self._conv_last(s), self._conv_last(h), self._conv_last(n), a
+
+
+_DEFAULT_HARMONIC = {"blockA": 20, "cycleA": 4, "blockF": 0, "cycleF": 0, "cascade_mode": 0}
+_DEFAULT_NOISE = {"blockA": 0, "cycleA": 0, "blockF": 5, "cycleF": 5, "cascade_mode": 0}
+_DEFAULT_FILTER = {"blockA": 0, "cycleA": 0, "blockF": 30, "cycleF": 3, "cascade_mode": 0}
+_DEFAULT_PE = {"conv_blocks": 3, "kernel_size": 5, "dilation": 1, "padding_mode": "replicate"}
+
+
+class CascadeHnUSFGANGenerator(_HnBase):
+    has_merge = True
+
+    def __init__(self, harmonic_network_params=_DEFAULT_HARMONIC, noise_network_params=_DEFAULT_NOISE,
+                 filter_network_params=_DEFAULT_FILTER, periodicity_estimator_params=_DEFAULT_PE, in_channels=1,
+                 out_channels=1, residual_channels=64, gate_channels=128, skip_channels=64, aux_channels=80,
+                 aux_context_window=2, use_weight_norm=True, upsample_params={"upsample_scales": [5, 4, 3, 2]}):
+        super().__init__()
+        self._build_hn(harmonic_network_params, noise_network_params, filter_network_params,
+                       periodicity_estimator_params, in_channels, out_channels, residual_channels, gate_channels,
+                       skip_channels, aux_channels, aux_context_window, upsample_params)
+        self._build_networks(harmonic_network_params, noise_network_params, filter_network_params,
+                             periodicity_estimator_params, residual_channels, gate_channels, skip_channels,
+                             aux_channels, out_channels)
+        if use_weight_norm:
+            self.apply_weight_norm()
+
+    @torch.no_grad()
+    def forward(self, x, c, d, wave_only=False):
+        """(x, s, h, n, a)   (generator.py:283-334): harmonic -> a*h -> merge with noise input -> noise net."""
+        self._check(x)
+        cache = {}
+        c, a, h, n = self._front(x, c)
+        h = self.harmonic_network(h, c, d, idx_cache=cache)
+        zeros = torch.zeros_like(h)
+        _, h, _ = ops.periodic_mix_f32(a, h, zeros, want_parts=True)     # h <- a * h
+        n = _conv1x1(self.conv_merge, torch.cat([h, n], dim=1))
+        n = self.noise_network(n, c, d, idx_cache=cache)
+        _, _, n = ops.periodic_mix_f32(a, zeros, n, want_parts=True)     # n <- (1 - a) * n
+        s = ops.lincomb_f32([h, n], [1.0, 1.0])
+        y = self.filter_network(s, c, d, idx_cache=cache)
+        return self._outputs(y, s, h, n, a, wave_only)
+
+
+class ParallelHnUSFGANGenerator(_HnBase):
+    def __init__(self, harmonic_network_params=_DEFAULT_HARMONIC, noise_network_params=_DEFAULT_NOISE,
+                 filter_network_params=_DEFAULT_FILTER, periodicity_estimator_params=_DEFAULT_PE, in_channels=1,
+                 out_channels=1, residual_channels=64, gate_channels=128, skip_channels=64, aux_channels=80,
+                 aux_context_window=2, use_weight_norm=True, upsample_params={"upsample_scales": [5, 4, 3, 2]}):
+        super().__init__()
+        self._build_hn(harmonic_network_params, noise_network_params, filter_network_params,
+                       periodicity_estimator_params, in_channels, out_channels, residual_channels, gate_channels,
+                       skip_channels, aux_channels, aux_context_window, upsample_params)
+        self._build_networks(harmonic_network_params, noise_network_params, filter_network_params,
+                             periodicity_estimator_params, residual_channels, gate_channels, skip_channels,
+                             aux_channels, out_channels)
+        if use_weight_norm:
+            self.apply_weight_norm()
+
+    @torch.no_grad()
+    def forward(self, x, c, d, wave_only=False):
+        """(x, s, h, n, a)   (generator.py:472-522): harmonic || noise -> a*h + (1-a)*n -> filter."""
+        self._check(x)
+        cache = {}
+        c, a, h, n = self._front(x, c)
+        h = self.harmonic_network(h, c, d, idx_cache=cache)
+        n = self.noise_network(n, c, d, idx_cache=cache)
+        s, h, n = ops.periodic_mix_f32(a, h, n, want_parts=True)
+        y = self.filter_network(s, c, d, idx_cache=cache)
+        return self._outputs(y, s, h, n, a, wave_only)

@@ -1,0 +1,68 @@
+"""uSFGAN front-end helpers with the API of ``nnsvs.usfgan.utils.features``
+(``dilated_factor`` features.py:56-75, ``SignalGenerator`` features.py:78-180).
+
+Front-end only — SURVEY.md §8(f) row 2 schedules its fusion into libsvsk after the residual stacks.  Until then these
+stay small numpy / torch expressions evaluated on the device ``f0`` lives on (they are inputs to the kernels, and to
+both sides of every parity test).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def dilated_factor(batch_f0, fs, dense_factor):
+    """Dilation in samples that puts ``dense_factor`` taps in one pitch period: fs / (f0 * dense_factor).
+    Unvoiced frames (f0 == 0) are first set to fs / dense_factor (factor 1), IN PLACE as the reference does."""
+    unvoiced = batch_f0 == 0
+    batch_f0[unvoiced] = fs / dense_factor
+    factors = np.full(batch_f0.shape, float(fs)) / batch_f0 / dense_factor
+    if not np.all(factors > 0):
+        raise AssertionError("dilated factors must be positive")
+    return factors
+
+
+class SignalGenerator:
+    """Builds the generator's input channels from frame-level F0 (B, 1, frames): NSF-style sine, Gaussian noise
+    and/or a V/UV mask, each upsampled by ``hop_size`` with nearest-neighbour hold, concatenated on dim 1."""
+
+    def __init__(self, sample_rate=24000, hop_size=120, sine_amp=0.1, noise_amp=0.003, signal_types=["sine", "noise"]):
+        self.sample_rate = sample_rate
+        self.hop_size = hop_size
+        self.sine_amp = sine_amp
+        self.noise_amp = noise_amp
+        self.signal_types = signal_types
+
+    def _hold(self, frames):
+        # F.interpolate(nearest) rather than repeat_interleave: identical index arithmetic to the reference
+        return F.interpolate(frames, frames.shape[-1] * self.hop_size)
+
+    def _voiced_mask(self, f0):
+        return self._hold((f0 > 0).to(f0.dtype))
+
+    @torch.no_grad()
+    def random_noise(self, f0):
+        return torch.randn((f0.shape[0], 1, f0.shape[-1] * self.hop_size), device=f0.device)
+
+    @torch.no_grad()
+    def vuv_binary(self, f0):
+        return self._voiced_mask(f0)
+
+    @torch.no_grad()
+    def sinusoid(self, f0):
+        voiced = self._voiced_mask(f0)
+        cycles_per_sample = torch.remainder(self._hold(f0) / self.sample_rate, 1)
+        phase = torch.cumsum(cycles_per_sample, dim=2) * 2 * math.pi
+        wave = voiced * torch.sin(phase) * self.sine_amp
+        if self.noise_amp > 0:
+            # voiced frames get noise_amp, unvoiced ones a third of it (NSF)
+            sigma = voiced * self.noise_amp + (1.0 - voiced) * self.noise_amp / 3.0
+            wave = wave + torch.randn(wave.shape, device=f0.device) * sigma
+        return wave
+
+    @torch.no_grad()
+    def __call__(self, f0):
+        makers = {"noise": self.random_noise, "sine": self.sinusoid, "uv": self.vuv_binary}
+        parts = [makers[kind](f0) for kind in self.signal_types if kind in makers]
+        return parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)

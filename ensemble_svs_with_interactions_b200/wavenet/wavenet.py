@@ -1,0 +1,85 @@
+"""WaveNet — drop-in for ``nnsvs.wavenet.WaveNet`` (nnsvs/wavenet/wavenet.py:7-171)."""
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from .. import ops
+from .modules import Conv1d1x1, ResSkipBlock, _w
+
+f32 = torch.float32
+
+
+class WaveNet(nn.Module):
+    def __init__(self, in_dim=334, out_dim=206, layers=10, stacks=1, residual_channels=64, gate_channels=128,
+                 skip_out_channels=64, kernel_size=3):
+        super().__init__()
+        self.in_dim = in_dim
+        self.out_dim = out_dim
+        self.first_conv = Conv1d1x1(out_dim, residual_channels)
+        self.main_conv_layers = nn.ModuleList()
+        layers_per_stack = layers // stacks
+        for layer in range(layers):
+            self.main_conv_layers.append(ResSkipBlock(residual_channels, gate_channels, kernel_size, skip_out_channels,
+                                                      dilation=2 ** (layer % layers_per_stack), cin_channels=in_dim))
+        self.last_conv_layers = nn.ModuleList([nn.ReLU(), Conv1d1x1(skip_out_channels, skip_out_channels), nn.ReLU(),
+                                               Conv1d1x1(skip_out_channels, out_dim)])
+
+    @torch.no_grad()
+    def forward(self, c, x, lengths=None):
+        """c (B,T,in_dim) conditioning, x (B,T,out_dim) targets -> (B,T,out_dim)   (wavenet.py:60-87)."""
+        if not x.is_cuda:
+            raise RuntimeError("WaveNet runs on CUDA (sm_100a) only: libsvsk has no CPU path")
+        x = x.to(f32).transpose(1, 2).contiguous()
+        c = c.to(f32).transpose(1, 2).contiguous()
+        x = ops.conv1d_f32(x, _w(self.first_conv), self.first_conv.bias)
+        skip_ch = self.last_conv_layers[1].in_channels
+        skips = torch.empty((x.shape[0], skip_ch, x.shape[2]), device=x.device, dtype=f32)
+        for i, f in enumerate(self.main_conv_layers):
+            x = f.run(x, c, skips, i == 0)
+        l1, l3 = self.last_conv_layers[1], self.last_conv_layers[3]
+        x = ops.conv1d_f32(skips, _w(l1), l1.bias, in_relu=True)
+        x = ops.conv1d_f32(x, _w(l3), l3.bias, in_relu=True)
+        return x.transpose(1, 2)
+
+    @torch.no_grad()
+    def inference(self, c, num_time_steps=100, tqdm=lambda x: x):
+        """Autoregressive sampling (wavenet.py:89-149): per-sample ring buffers + categorical draw."""
+        self.clear_buffer()
+        B = c.shape[0]
+        outputs = []
+        current = torch.zeros(B, 1, self.out_dim, device=c.device)
+        steps = range(num_time_steps) if tqdm is None else tqdm(range(num_time_steps))
+        for t in steps:
+            if t > 0:
+                current = outputs[-1]
+            ct = c[:, t, :].unsqueeze(1)
+            x = self.first_conv.incremental_forward(current)
+            skips = 0
+            for f in self.main_conv_layers:
+                x, h = f.incremental_forward(x, ct)
+                skips = skips + h
+            x = skips
+            for f in self.last_conv_layers:
+                x = f.incremental_forward(x) if hasattr(f, "incremental_forward") else f(x)
+            probs = F.softmax(x.view(B, -1), dim=1)
+            outputs.append(torch.distributions.OneHotCategorical(probs).sample().view(B, 1, -1))
+        out = torch.cat(outputs, dim=1)
+        self.clear_buffer()
+        return out
+
+    def clear_buffer(self):
+        self.first_conv.clear_buffer()
+        for f in self.main_conv_layers:
+            f.clear_buffer()
+        for f in self.last_conv_layers:
+            if hasattr(f, "clear_buffer"):
+                f.clear_buffer()
+
+    def remove_weight_norm_(self):
+        def _remove(m):
+            try:
+                torch.nn.utils.remove_weight_norm(m)
+            except ValueError:
+                return
+
+        self.apply(_remove)

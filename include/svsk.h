@@ -1,0 +1,207 @@
+/*
+ * svsk.h — C ABI of libsvsk.so: hand-written sm_100a CUDA kernels for the gated dilated-Conv1d
+ * residual stacks of sarulab-speech/ensemble_svs_with_interactions (NNSVS-derived).
+ *
+ * The reference has no FFI of its own (it is pure Python/PyTorch): the seam is the
+ * nn.Module protocol.  Each entry point below therefore cites the reference *function* it replaces
+ * (paths relative to the reference root).  The drop-in nn.Modules in
+ * ensemble_svs_with_interactions_b200/ bind these symbols with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - the caller owns every buffer (inputs, outputs, workspace); kernels never allocate or synchronise;
+ *  - every call only enqueues work on `stream` (a cudaStream_t passed as void*) and is CUDA-graph capturable;
+ *  - return value: 0 = ok; <0 = SVSK_E* argument/arch error detected before launch; >0 = cudaError_t;
+ *    svsk_last_error() returns a thread-local message for the last non-zero return;
+ *  - there is no CPU path: on a non-sm_100 device the tensor-core entry points return SVSK_E_ARCH;
+ *  - layouts: "NCT" = [B][C][T] fp32 (the reference's layout); "NTC" = [B][T][C] channel-last
+ *    (bf16 MMA operands, fp32 residual/skip masters).
+ */
+#ifndef SVSK_H_
+#define SVSK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVSK_VERSION 100
+
+#if defined(__GNUC__)
+#define SVSK_API __attribute__((visibility("default")))
+#else
+#define SVSK_API
+#endif
+
+enum {
+  SVSK_OK = 0,
+  SVSK_E_ARG = -1,      /* bad shape / null pointer / unsupported combination */
+  SVSK_E_ALIGN = -2,    /* pointer or stride alignment */
+  SVSK_E_ARCH = -3,     /* device is not sm_100 */
+  SVSK_E_DRIVER = -4,   /* could not obtain cuTensorMapEncodeTiled */
+  SVSK_E_WORKSPACE = -5 /* workspace too small */
+};
+
+/* padding / tap-index modes of svsk_conv1d_f32 */
+enum {
+  SVSK_PAD_ZEROS = 0,     /* 0 outside [0,T)                       (nn.Conv1d default; DiffNet, WaveNet) */
+  SVSK_PAD_REFLECT = 1,   /* i<0 -> -i ; i>=T -> 2(T-1)-i          (uSFGAN FixedBlock)                    */
+  SVSK_PAD_REPLICATE = 2, /* clamp                                  (uSFGAN PeriodicityEstimator)          */
+  SVSK_PAD_VALID = 3,     /* no padding: T_out = T_in-(k-1)*dil     (uSFGAN upsample conv_in)              */
+  SVSK_PAD_INDEXED = 4    /* k==3: taps at idx_past[b,t], t, idx_future[b,t]; index<0 -> 0 (AdaptiveBlock) */
+};
+
+enum { SVSK_ACT_NONE = 0, SVSK_ACT_RELU = 1, SVSK_ACT_SIGMOID = 2, SVSK_ACT_MISH = 3 };
+
+/* gate orders of svsk_gated_act_f32 */
+enum {
+  SVSK_GATE_SIGMOID_TANH = 0, /* sigmoid(first half) * tanh(second half): DiffNet (denoiser.py:60-61)        */
+  SVSK_GATE_TANH_SIGMOID = 1  /* tanh(first half) * sigmoid(second half): WaveNet / uSFGAN                   */
+};
+
+SVSK_API const char* svsk_last_error(void);
+SVSK_API int svsk_version(void);
+/* 0 iff `device` is an sm_100 (B200) part; SVSK_E_ARCH otherwise; >0 cudaError_t when no driver/GPU. */
+SVSK_API int svsk_device_check(int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * fp32 exact path (CUDA cores), NCT layout.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* General Conv1d as a sum of taps.  Replaces every nn.Conv1d / Conv1d1x1 / nn.Linear call on the path:
+ *   nnsvs/diffsinger/denoiser.py:43-52,80,97-98 ; nnsvs/usfgan/layers/residual_block.py:104-120,187-201,358-366 ;
+ *   nnsvs/usfgan/layers/upsample.py:165-167 ; nnsvs/wavenet/modules.py:46-62 ; nnsvs/wavenet/wavenet.py:33,52-57.
+ *   y[b,co,t] = act( ( bias[co] + sum_j sum_ci w[co,ci,j] * X(b,ci,src_j(t)) + residual[b,co,t] ) * out_scale )
+ *   src_j(t)  = t + (j - tap_origin) * dilation, resolved by pad_mode;
+ *   X(b,ci,u) = in_relu?relu(x):x  (+ in_bias[b,ci] when u is in range: DiffNet's x + step embedding, added
+ *               BEFORE zero padding, denoiser.py:57-59).
+ *   accumulate != 0: y += (...) instead of y = (...).  T is the OUTPUT length. */
+typedef struct svsk_conv1d_f32_params {
+  const float* x;        /* [B][Cin][T_in]; T_in == T except SVSK_PAD_VALID */
+  const float* w;        /* [Cout][Cin][ksize] */
+  const float* bias;     /* [Cout] or NULL */
+  const float* in_bias;  /* [B][Cin] or NULL */
+  const float* residual; /* [B][Cout][T] or NULL (may alias y) */
+  const int32_t* idx_past;   /* [B][T] (SVSK_PAD_INDEXED) */
+  const int32_t* idx_future; /* [B][T] (SVSK_PAD_INDEXED) */
+  float* y;              /* [B][Cout][T] */
+  int32_t B, Cin, Cout, T;
+  int32_t ksize, dilation, tap_origin, pad_mode;
+  int32_t accumulate, act, in_relu;
+  float out_scale;
+} svsk_conv1d_f32_params;
+SVSK_API int svsk_conv1d_f32(const svsk_conv1d_f32_params* p, void* stream);
+
+/* z[b,h,t] = gate(y[b,h,t], y[b,H+h,t]).  denoiser.py:60-61 ; residual_block.py:140-149 ; modules.py:104-112 */
+SVSK_API int svsk_gated_act_f32(const float* y, float* z, int B, int H, int T, int order, void* stream);
+
+/* DiffNet block tail, denoiser.py:63-66:  x = (x + o[:, :C]) / sqrt(2) ;  skip (+)= o[:, C:]  (skip = when init_skip) */
+SVSK_API int svsk_diffnet_residual_skip_f32(const float* o, float* x, float* skip, int B, int C, int T, int init_skip,
+                                   void* stream);
+
+/* y = alpha * act(x) elementwise over n elements (skip-sum / sqrt(L), Mish of the step MLP ...). */
+SVSK_API int svsk_scale_act_f32(const float* x, float* y, size_t n, float alpha, int act, void* stream);
+
+/* Sinusoidal step embedding, denoiser.py:14-26: out[b] = cat(sin(t_b f), cos(t_b f)), f_i = 10000^(-i/(dim/2-1)). */
+SVSK_API int svsk_sinusoidal_embedding_f32(const int64_t* t, float* out, int B, int dim, void* stream);
+
+/* One ancestral DDPM update, diffusion.py:164-204 (p_sample after the denoiser call), any layout (flat per batch):
+ *   x0 = clamp(sra[t] x - srm1[t] eps, +-1) ; mean = c1[t] x0 + c2[t] x ; out = mean + [t>0] exp(.5 plv[t]) z
+ * tables are the reference's registered fp32 buffers (diffusion.py:112-145); t is [B] int64. */
+SVSK_API int svsk_ddpm_update_f32(const float* x, const float* eps, const float* z, float* out, const int64_t* t,
+                         const float* sqrt_recip_alphas_cumprod, const float* sqrt_recipm1_alphas_cumprod,
+                         const float* posterior_mean_coef1, const float* posterior_mean_coef2,
+                         const float* posterior_log_variance_clipped, int B, size_t per_batch, int clip_denoised,
+                         void* stream);
+
+/* q_sample, diffusion.py:261-267: out = sac[t] x0 + somac[t] noise. */
+SVSK_API int svsk_q_sample_f32(const float* x0, const float* noise, float* out, const int64_t* t,
+                      const float* sqrt_alphas_cumprod, const float* sqrt_one_minus_alphas_cumprod, int B,
+                      size_t per_batch, void* stream);
+
+/* PLMS transfer get_x_pred, diffusion.py:213-230: out = x + x_delta(alphas_cumprod[t], alphas_cumprod[max(t-interval,0)]). */
+SVSK_API int svsk_plms_transfer_f32(const float* x, const float* noise_t, float* out, const int64_t* t, int interval,
+                           const float* alphas_cumprod, int B, size_t per_batch, void* stream);
+
+/* out = sum_i coef[i] * in[i] over n elements, 1 <= n_in <= 4 (PLMS multistep combination, diffusion.py:236-256). */
+SVSK_API int svsk_lincomb_f32(const float* const* in, const float* coef, int n_in, float* out, size_t n, void* stream);
+
+/* Pitch-dependent tap indices, nnsvs/usfgan/utils/index.py:12-54 (bit-faithful fp32 rounding):
+ *   past[b,t] = rint(-(d*dil) + (t-T)) + T   (-1 when < 0)
+ *   future[b,t] = rint((d*dil) + t)           (-1 when >= T)          d is [B][T] (the (B,1,T) tensor). */
+SVSK_API int svsk_pd_index(const float* d, int32_t* idx_past, int32_t* idx_future, int B, int T, int dilation, void* stream);
+
+/* uSFGAN upsample stage, upsample.py:15-44,87-101: nearest stretch by `scale` then the (1, 2*scale+1) smoothing
+ * filter (zero padding `scale`), same taps for every channel.  in [R][Tin] -> out [R][Tin*scale], R = B*C rows. */
+SVSK_API int svsk_upsample_smooth_f32(const float* in, const float* taps, float* out, int R, int Tin, int scale, void* stream);
+
+/* Periodicity mix, generator.py:505-507: h2 = a*h ; n2 = (1-a)*n ; s = h2 + n2   (h2/n2 may be NULL). */
+SVSK_API int svsk_periodic_mix_f32(const float* a, const float* h, const float* n, float* s, float* h2, float* n2, size_t cnt,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * layout / precision conversion between the two paths
+ * ------------------------------------------------------------------------------------------------ */
+/* [B][C][T] fp32 -> [B][T][Cp] bf16 (channels >= C zero-filled up to Cp) and optionally the fp32 NTC master. */
+SVSK_API int svsk_nct_to_ntc(const float* x, void* out_bf16, float* out_f32, int B, int C, int T, int Cp, void* stream);
+/* [B][T][Cp] fp32 -> [B][C][T] fp32 (first C channels), scaled by alpha. */
+SVSK_API int svsk_ntc_to_nct_f32(const float* x, float* y, int B, int C, int T, int Cp, float alpha, void* stream);
+/* flat fp32 -> bf16 with scale and optional ReLU (skip-sum / sqrt(L) before the tail GEMM). */
+SVSK_API int svsk_cast_scale_bf16(const float* x, void* y_bf16, size_t n, float alpha, int relu, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * bf16 tensor-core path (tcgen05 + TMEM + TMA), NTC layout.  sm_100a only.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Fused DiffNet residual block — replaces ResidualBlock.forward, nnsvs/diffsinger/denoiser.py:54-66, one launch:
+ *   D1 = W1p . [x(t-d) ; x(t) ; x(t+d) ; cond(t)]           implicit GEMM, K = 3C + H, zero padding by TMA OOB fill
+ *   D1 += stepbias (per tap, masked at the sequence ends = exact `x + diffusion_step` before zero padding)
+ *   G  = sigmoid(D1[gate rows]) * tanh(D1[filter rows])       TMEM -> registers -> swizzled smem (bf16)
+ *   D2 = Woutp . G + bout                                     second GEMM from smem
+ *   x32 <- (x32 + D2[:C]) / sqrt(2)  (fp32 master, in place) ; xb_out <- bf16(x32) ; skip32 (+)= D2[C:]
+ * Weights are pre-packed by svsk_diffnet_pack_block (row permutation: 128-row gate block then its filter block).
+ * Constraints: C % 128 == 0, C <= 256, H % 64 == 0, T >= 1.  xb_in and xb_out must differ (neighbour tiles read
+ * xb_in halos).  stepbias is [B or 1][3][2C] fp32 in PACKED row order; stepbias_batch_stride = 0 broadcasts. */
+typedef struct svsk_diffnet_block_params {
+  const void* xb_in;   /* [B][T][C] bf16 */
+  void* xb_out;        /* [B][T][C] bf16 */
+  float* x32;          /* [B][T][C] fp32, in place */
+  float* skip32;       /* [B][T][C] fp32, in place */
+  const void* cond;    /* [B][T][H] bf16 */
+  const void* w1p;     /* [2C][3C+H] bf16 packed */
+  const void* woutp;   /* [2C][C] bf16 packed */
+  const float* stepbias; /* [.][3][2C] */
+  const float* bout;   /* [2C] fp32: [0,C) residual rows, [C,2C) skip rows */
+  int32_t B, T, C, H;
+  int32_t dilation;
+  int32_t stepbias_batch_stride; /* in floats; 0 = same for every batch row */
+  int32_t init_skip;   /* 1: skip32 = ..., 0: skip32 += ... */
+  int32_t write_x;     /* 0 on the last layer (x is dead after it, denoiser.py:117-120) */
+  int32_t time_tile;   /* 0 = choose; else one of 32..128, multiple of 16 */
+} svsk_diffnet_block_params;
+SVSK_API int svsk_diffnet_block_bf16(const svsk_diffnet_block_params* p, void* stream);
+
+/* Pack one block's weights (fp32, reference state_dict layout) for svsk_diffnet_block_bf16.
+ *   dilated_w [2C][C][3], cond_w [2C][H][1], out_w [2C][C][1]  ->  w1p [2C][3C+H] bf16, woutp [2C][C] bf16.
+ * Row r of the reference maps to packed row perm(r): gate rows of channel block q at 256q..256q+127, filter rows at
+ * 256q+128..256q+255.  Also applies to the stepbias/bias vectors: svsk_diffnet_packed_row(). */
+SVSK_API int svsk_diffnet_pack_block(const float* dilated_w, const float* cond_w, const float* out_w, void* w1p, void* woutp,
+                            int C, int H, void* stream);
+SVSK_API int svsk_diffnet_packed_row(int reference_row, int C);
+
+/* Time-major bf16 GEMM with fused epilogue — replaces the 1x1 projections around the stacks
+ * (denoiser.py:110-112,121-123 ; generator.py:461-466,492-493):
+ *   Y[n][co] = act( sum_k A[n][k] W[co][k] + bias[co] )      n = B*T rows, K % 16 == 0, Cout % 16 == 0, Cout <= 256
+ * A [N][lda] bf16 ; W [Cout][K] bf16 ; outputs optional: y_bf16 [N][ldy_b], y_f32 [N][ldy_f]. */
+typedef struct svsk_linear_bf16_params {
+  const void* a; const void* w; const float* bias;
+  void* y_bf16; float* y_f32;
+  int64_t N; int32_t K, Cout; int32_t lda, ldy_b, ldy_f; int32_t act;
+} svsk_linear_bf16_params;
+SVSK_API int svsk_linear_bf16(const svsk_linear_bf16_params* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVSK_H_ */

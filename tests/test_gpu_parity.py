@@ -1,0 +1,457 @@
+"""GPU parity tests (run with -m gpu on a B200): every libsvsk path against the CPU oracle / golden vectors.
+
+Tolerances (stated per test):
+  fp32 path  : max-abs <= 2e-4 * max(1, |ref|_max)      (CUDA-core fp32, differs from the reference only by
+                                                          summation order and libm ulps)
+  bf16 path  : rel-L2 <= 2e-2 and max-abs <= 6e-2 * |ref|_max for one denoiser call (bf16 operands, fp32 accumulate,
+               tanh.approx); the sampled mel after K steps is checked with rel-L2 <= 5e-2.
+  index work : bit exact.
+"""
+import math
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import svs_oracle as O
+from tests.golden_util import Golden, max_abs, rel_l2
+
+warnings.filterwarnings("ignore", category=FutureWarning)
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from ensemble_svs_with_interactions_b200 import ops
+    return ops
+
+
+def close32(a, b, tol=2e-4):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    scale = max(1.0, b.abs().max().item())
+    err = max_abs(a, b)
+    assert err <= tol * scale, f"max_abs {err:.3e} rel_l2 {rel_l2(a, b):.3e} (tol {tol * scale:.1e})"
+
+
+def close_bf16(a, b, l2=2e-2, mx=6e-2):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    r, m = rel_l2(a, b), max_abs(a, b) / max(b.abs().max().item(), 1e-12)
+    assert r <= l2 and m <= mx, f"rel_l2 {r:.3e} (tol {l2}) max_abs/|ref|max {m:.3e} (tol {mx})"
+    return r, m
+
+
+def cuda_sd(sd):
+    return {k: v.to(DEV) for k, v in sd.items()}
+
+
+# ------------------------------------------------------------------------------------------------ generic fp32 kernels
+@pytest.mark.parametrize("pad,k,dil,origin", [(0, 3, 2, 1), (0, 3, 4, 2), (1, 3, 8, 1), (2, 5, 1, 2), (3, 5, 1, 0),
+                                              (0, 1, 1, 0), (1, 3, 64, 1)])
+@pytest.mark.parametrize("B,Cin,Cout,T", [(2, 5, 7, 37), (1, 64, 128, 130), (3, 80, 64, 257)])
+def test_conv1d_f32_modes(pad, k, dil, origin, B, Cin, Cout, T):
+    ops = _ops()
+    if pad == 1 and max(origin, k - 1 - origin) * dil >= T:
+        pytest.skip("reflect needs T > reach")
+    g = torch.Generator().manual_seed(B * 1000 + T + pad)
+    T_in = T + (k - 1) * dil if pad == 3 else T
+    x = torch.randn(B, Cin, T_in, generator=g)
+    w = torch.randn(Cout, Cin, k, generator=g) / math.sqrt(Cin * k)
+    b = torch.randn(Cout, generator=g)
+    mode = {0: "zeros", 1: "reflect", 2: "replicate"}.get(pad)
+    if pad == 3:
+        ref = torch.nn.functional.conv1d(x, w, b, dilation=dil)
+    else:
+        ref = O.conv_taps(x, w, b, [(j - origin) * dil for j in range(k)], mode)
+    y = ops.conv1d_f32(x.to(DEV), w.to(DEV), b.to(DEV), dilation=dil, tap_origin=origin, pad_mode=pad)
+    close32(y, ref)
+
+
+def test_conv1d_f32_epilogue_options():
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    B, Cin, Cout, T = 2, 16, 24, 50
+    x = torch.randn(B, Cin, T, generator=g); w = torch.randn(Cout, Cin, 3, generator=g) * 0.2
+    bias = torch.randn(Cout, generator=g); e = torch.randn(B, Cin, generator=g); res = torch.randn(B, Cout, T, generator=g)
+    # in_bias is added BEFORE zero padding (DiffNet x + step)
+    ref = O.conv_taps(x + e[:, :, None], w, bias, (-2, 0, 2), "zeros")
+    y = ops.conv1d_f32(x.to(DEV), w.to(DEV), bias.to(DEV), dilation=2, in_bias=e.to(DEV))
+    close32(y, ref)
+    # residual + scale + relu-in + accumulate
+    ref2 = (O.conv_taps(torch.relu(x), w, bias, (-1, 0, 1), "zeros") + res) * 0.5
+    y2 = ops.conv1d_f32(x.to(DEV), w.to(DEV), bias.to(DEV), residual=res.to(DEV), out_scale=0.5, in_relu=True)
+    close32(y2, ref2)
+    acc = res.to(DEV).clone()
+    ops.conv1d_f32(x.to(DEV), w.to(DEV), None, out=acc, accumulate=True, act=ops.ACT_RELU)
+    close32(acc, res + torch.relu(O.conv_taps(x, w, None, (-1, 0, 1), "zeros")))
+
+
+def test_conv1d_f32_rejects_bad_arguments():
+    ops = _ops()
+    x = torch.zeros(1, 4, 8, device=DEV); w = torch.zeros(4, 4, 3, device=DEV)
+    with pytest.raises(RuntimeError, match="reflect"):
+        ops.conv1d_f32(x, w, dilation=8, pad_mode=ops.PAD_REFLECT)
+    with pytest.raises(RuntimeError, match="input channels"):
+        ops.conv1d_f32(torch.zeros(1, 5, 8, device=DEV), w)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        ops.conv1d_f32(torch.zeros(1, 8, 4, device=DEV).transpose(1, 2), w)
+
+
+def test_elementwise_kernels():
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    y = torch.randn(2, 12, 33, generator=g) * 3
+    close32(ops.gated_act_f32(y.to(DEV), ops.GATE_SIGMOID_TANH), torch.sigmoid(y[:, :6]) * torch.tanh(y[:, 6:]), 1e-5)
+    close32(ops.gated_act_f32(y.to(DEV), ops.GATE_TANH_SIGMOID), torch.tanh(y[:, :6]) * torch.sigmoid(y[:, 6:]), 1e-5)
+    t = torch.tensor([0, 1, 50, 99])
+    close32(ops.sinusoidal_embedding_f32(t.to(DEV), 256), O.sinusoidal_embedding(t.float(), 256), 2e-5)
+    x = torch.randn(4, 40, generator=g) * 4
+    close32(ops.scale_act_f32(x.to(DEV), 1.0, ops.ACT_MISH), O.mish(x), 1e-5)
+    a = torch.rand(3, 8, 20, generator=g); h = torch.randn(3, 8, 20, generator=g); n = torch.randn(3, 8, 20, generator=g)
+    s, h2, n2 = ops.periodic_mix_f32(a.to(DEV), h.to(DEV), n.to(DEV), want_parts=True)
+    close32(s, a * h + (1 - a) * n, 1e-6); close32(h2, a * h, 1e-6); close32(n2, (1 - a) * n, 1e-6)
+
+
+def test_ddpm_qsample_plms_kernels():
+    ops = _ops()
+    tab = O.diffusion_tables(O.beta_schedule(100, "linear", max_beta=0.06))
+    tabc = cuda_sd(tab)
+    g = torch.Generator().manual_seed(3)
+    B = 5
+    t = torch.tensor([0, 1, 37, 98, 99])
+    x = torch.randn(B, 1, 20, 33, generator=g) * 2; eps = torch.randn(B, 1, 20, 33, generator=g); z = torch.randn(B, 1, 20, 33, generator=g)
+    out = ops.ddpm_update_f32(x.to(DEV), eps.to(DEV), z.to(DEV), t.to(DEV), tabc)
+    close32(out, O.ddpm_update(tab, x, t, eps, z), 1e-5)
+    close32(out[0], O.ddpm_update(tab, x, t, eps, z * 0)[0], 1e-5)  # t == 0: the noise term is masked
+    close32(ops.q_sample_f32(x.to(DEV), z.to(DEV), t.to(DEV), tabc), O.q_sample(tab, x, t, z), 1e-6)
+    close32(ops.plms_transfer_f32(x.to(DEV), eps.to(DEV), t.to(DEV), 5, tabc["alphas_cumprod"]),
+            O.plms_x_pred(tab, x, eps, t, 5), 1e-5)
+    close32(ops.lincomb_f32([x.to(DEV), eps.to(DEV), z.to(DEV)], [23 / 12, -16 / 12, 5 / 12]),
+            (23 * x - 16 * eps + 5 * z) / 12, 1e-5)
+
+
+def test_pd_index_bit_exact_and_indexed_conv():
+    from ensemble_svs_with_interactions_b200.usfgan.utils import pd_indexing
+    g = Golden("usfgan_blocks_fullwidth")
+    x, d = g.inp["x"].to(DEV), g.inp["d"].to(DEV)
+    xP, xF = pd_indexing(x, d, g.cfg["dilation_adaptive"])
+    assert torch.equal(xP.cpu(), g.out["xP"]) and torch.equal(xF.cpu(), g.out["xF"])
+    # large T: the reference rounds the SUM t + d*dil in fp32 (index.py:27-47) -> must match the oracle bit for bit
+    gen = torch.Generator().manual_seed(1)
+    T = 300000
+    dd = torch.empty(1, 1, T).uniform_(0.6, 60.0, generator=gen)
+    dd[0, 0, :8] = torch.tensor([0.5, 1.5, 2.5, 3.5, 4.5, 5.5, 6.5, 7.5])
+    xx = torch.arange(T, dtype=torch.float32).view(1, 1, T) + 1.0
+    rp, rf = O.pd_gather(xx, dd, 16)
+    ops = _ops()
+    ip, iff = ops.pd_index(dd.to(DEV), 16)
+    gp = torch.where(ip >= 0, ip.float() + 1.0, torch.zeros_like(ip, dtype=torch.float32)).view(1, 1, T)
+    gf = torch.where(iff >= 0, iff.float() + 1.0, torch.zeros_like(iff, dtype=torch.float32)).view(1, 1, T)
+    assert torch.equal(gp.cpu(), rp) and torch.equal(gf.cpu(), rf)
+
+
+def test_layout_conversions_roundtrip():
+    ops = _ops()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(3, 60, 77, generator=g)
+    xb, xf = ops.nct_to_ntc(x.to(DEV), Cp=64, want_bf16=True, want_f32=True)
+    assert xb.shape == (3, 77, 64) and torch.count_nonzero(xf[:, :, 60:]) == 0
+    assert torch.equal(xf[:, :, :60].cpu(), x.transpose(1, 2))
+    assert torch.equal(xb.float().cpu()[:, :, :60], x.transpose(1, 2).to(torch.bfloat16).float())
+    assert torch.equal(ops.ntc_to_nct_f32(xf, 60).cpu(), x)
+    y = ops.cast_scale_bf16(xf, alpha=0.5, relu=True)
+    assert torch.equal(y.float().cpu(), torch.relu(xf.cpu() * 0.5).to(torch.bfloat16).float())
+
+
+# ------------------------------------------------------------------------------------------------ fp32 model parity
+def test_diffnet_fp32_vs_golden():
+    from ensemble_svs_with_interactions_b200.diffsinger import DiffNet
+    g = Golden("diffnet_small")
+    m = DiffNet(**g.cfg).to(DEV).eval()
+    m.load_state_dict(g.sd)
+    assert m.resolved_precision() == "fp32"
+    y = m(g.inp["spec"].to(DEV), g.inp["t"].to(DEV), g.inp["cond"].to(DEV))
+    close32(y, g.out["y"])
+    close32(m.step_embedding(g.inp["t"].to(DEV)), g.out["emb"], 2e-5)
+    x1, s1 = m.residual_layers[0](g.out["x0"].to(DEV), g.inp["cond"].to(DEV), g.out["emb"].to(DEV))
+    close32(x1, g.out["x1"]); close32(s1, g.out["s1"])
+
+
+def test_gaussian_diffusion_fp32_vs_golden():
+    from ensemble_svs_with_interactions_b200.diffsinger import DiffNet, GaussianDiffusion
+    g = Golden("diffusion_small")
+    m = GaussianDiffusion(20, 12, DiffNet(**g.cfg["denoiser"]), K_step=g.cfg["K_step"]).to(DEV).eval()
+    m.load_state_dict(g.sd)
+    out = m.inference(g.inp["cond"].to(DEV), x_T=g.inp["x_T"].to(DEV), z=g.inp["z"].to(DEV))
+    close32(out, g.out["out"], 5e-4)
+    # step-by-step through the reference-shaped p_sample API with an injected noise_fn
+    x = g.inp["x_T"].to(DEV)
+    c = g.inp["cond"].to(DEV).transpose(1, 2).contiguous()
+    z = g.inp["z"].to(DEV)
+    for n, i in enumerate(reversed(range(g.cfg["K_step"]))):
+        t = torch.full((x.shape[0],), i, device=DEV, dtype=torch.long)
+        x = m.p_sample(x, t, c, noise_fn=lambda *s, device=None, _i=i: z[_i])
+        close32(x, g.out["steps"][n], 5e-4)
+    # training forward with injected t / noise
+    noise, eps = m(g.inp["cond"].to(DEV), None, g.inp["y"].to(DEV), t=g.inp["t_train"].to(DEV),
+                   noise=g.inp["noise_train"].to(DEV))
+    close32(eps, g.out["train_eps"]); close32(noise, g.out["train_noise"], 0.0)
+    # shapes with own RNG (tests/test_diffusion.py:58-94 of the reference)
+    y = m.inference(g.inp["cond"].to(DEV))
+    assert y.shape == g.out["out"].shape and torch.isfinite(y).all()
+    # PLMS (attribute set after construction)
+    m.pndm_speedup = 2
+    from collections import deque
+    m.noise_list = deque(maxlen=4)
+    xp = g.inp["x_T"].to(DEV)
+    for n, i in enumerate(reversed(range(0, g.cfg["K_step"], 2))):
+        xp = m.p_sample_plms(xp, torch.full((xp.shape[0],), i, device=DEV, dtype=torch.long), 2, c)
+        close32(xp, g.out["plms"][n], 1e-3)
+    y = m.inference(g.inp["cond"].to(DEV), x_T=g.inp["x_T"].to(DEV))
+    close32(y, g.out["plms"][-1][:, 0].transpose(1, 2) * 10, 1e-3)
+
+
+@pytest.mark.parametrize("name", ["wavenet_small", "wavenet_test_shape"])
+def test_wavenet_vs_golden(name):
+    from ensemble_svs_with_interactions_b200.wavenet import WaveNet
+    g = Golden(name)
+    m = WaveNet(**g.cfg).to(DEV).eval()
+    m.load_state_dict(g.sd)
+    y = m(g.inp["c"].to(DEV), g.inp["x"].to(DEV))
+    close32(y, g.out["y"])
+    # AR inference: shape contract of tests/test_wavenet.py:11-17
+    for T in (3, 10):
+        o = m.inference(g.inp["c"].to(DEV)[:, :T], num_time_steps=T, tqdm=None)
+        assert o.shape == (g.inp["c"].shape[0], T, g.cfg["out_dim"]) and torch.all(o.sum(-1) == 1)
+    m.remove_weight_norm_()
+    close32(m(g.inp["c"].to(DEV), g.inp["x"].to(DEV)), g.out["y"])
+
+
+def _hn_kwargs(c):
+    return dict(harmonic_network_params=c["harmonic"], noise_network_params=c["noise"],
+                filter_network_params=c["filt"], periodicity_estimator_params=c["pe"], **c["common"])
+
+
+def test_parallel_hn_vs_golden():
+    from ensemble_svs_with_interactions_b200.usfgan.models import ParallelHnUSFGANGenerator
+    g = Golden("usfgan_parallel_hn_small")
+    m = ParallelHnUSFGANGenerator(**_hn_kwargs(g.cfg)).to(DEV).eval()
+    m.load_state_dict(g.sd)
+    outs = m(g.inp["x"].to(DEV), g.inp["c"].to(DEV), g.inp["d"].to(DEV))
+    for o, k in zip(outs, "yshna"):
+        close32(o, g.out[k])
+    yw = m(g.inp["x"].to(DEV), g.inp["c"].to(DEV), g.inp["d"].to(DEV), wave_only=True)[0]
+    assert torch.equal(yw, outs[0])
+    g2 = Golden("usfgan_parallel_hn_small_nowm")
+    m.remove_weight_norm()
+    m.load_state_dict(g2.sd)
+    close32(m(g.inp["x"].to(DEV), g.inp["c"].to(DEV), g.inp["d"].to(DEV))[0], g2.out["y"])
+
+
+def test_cascade_and_plain_usfgan_vs_golden():
+    from ensemble_svs_with_interactions_b200.usfgan.models import CascadeHnUSFGANGenerator, USFGANGenerator
+    g = Golden("usfgan_cascade_hn_small")
+    m = CascadeHnUSFGANGenerator(**_hn_kwargs(g.cfg)).to(DEV).eval()
+    m.load_state_dict(g.sd)
+    for o, k in zip(m(g.inp["x"].to(DEV), g.inp["c"].to(DEV), g.inp["d"].to(DEV)), "yshna"):
+        close32(o, g.out[k])
+    g = Golden("usfgan_plain_small")
+    m = USFGANGenerator(source_network_params=g.cfg["source"], filter_network_params=g.cfg["filt"],
+                        **g.cfg["common"]).to(DEV).eval()
+    m.load_state_dict(g.sd)
+    y, s = m(g.inp["x"].to(DEV), g.inp["c"].to(DEV), g.inp["d"].to(DEV))
+    close32(y, g.out["y"]); close32(s, g.out["s"])
+
+
+def test_usfgan_blocks_fullwidth_vs_golden():
+    from ensemble_svs_with_interactions_b200.usfgan.layers import AdaptiveBlock, FixedBlock
+    g = Golden("usfgan_blocks_fullwidth")
+    fb = FixedBlock(64, 128, 64, 80, kernel_size=3, dilation=g.cfg["dilation_fixed"]).to(DEV)
+    fb.load_state_dict({k[len("fixed."):]: v for k, v in g.sd.items() if k.startswith("fixed.")})
+    ab = AdaptiveBlock(64, 128, 64, 80).to(DEV)
+    ab.load_state_dict({k[len("adaptive."):]: v for k, v in g.sd.items() if k.startswith("adaptive.")})
+    x, c = g.inp["x"].to(DEV), g.inp["c"].to(DEV)
+    with torch.no_grad():
+        close32(fb(x, c)[0], g.out["y_fixed"])
+        close32(ab(x, g.out["xP"].to(DEV), g.out["xF"].to(DEV), c)[0], g.out["y_adaptive"])
+
+
+def test_usfgan_wrapper_inference_shape():
+    """Vocoder entry point (gen.predict_waveform -> USFGANWrapper.inference): (T,1) f0 + (T,C) aux -> (1,1,T*hop)."""
+    from types import SimpleNamespace as NS
+    from ensemble_svs_with_interactions_b200.usfgan import USFGANWrapper
+    from ensemble_svs_with_interactions_b200.usfgan.models import ParallelHnUSFGANGenerator
+    g = Golden("usfgan_parallel_hn_small")
+    gen = ParallelHnUSFGANGenerator(**_hn_kwargs(g.cfg)).to(DEV).eval()
+    gen.load_state_dict(g.sd)
+    gen.remove_weight_norm()
+
+    class Cfg(dict):
+        __getattr__ = dict.__getitem__
+    config = NS(data=NS(sample_rate=240, hop_size=6, sine_amp=0.1, noise_amp=0.003, signal_types=["sine", "noise"],
+                        sine_f0_type="contf0", df_f0_type="contf0", dense_factor=4),
+                generator=Cfg(aux_context_window=2))
+    f0 = np.abs(np.random.RandomState(0).randn(24, 1)).astype(np.float32) * 30 + 20
+    f0[5:8] = 0
+    aux = torch.randn(24, 12, device=DEV)
+    wav = USFGANWrapper(config, gen).inference(f0, aux)
+    assert wav.shape == (1, 1, 24 * 6) and torch.isfinite(wav).all()
+
+
+# ------------------------------------------------------------------------------------------------ bf16 tensor-core path
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("N,K,Cout,act", [(300, 80, 256, 1), (129, 256, 80, 0), (1000, 256, 256, 1), (64, 64, 16, 2),
+                                          (12000, 80, 256, 1)])
+def test_linear_bf16(N, K, Cout, act):
+    ops = _ops()
+    g = torch.Generator().manual_seed(N + K)
+    a = torch.randn(N, K, generator=g); w = torch.randn(Cout, K, generator=g) / math.sqrt(K); b = torch.randn(Cout, generator=g)
+    ref = _bf(a) @ _bf(w).t() + b
+    ref = torch.relu(ref) if act == 1 else (torch.sigmoid(ref) if act == 2 else ref)
+    yb, yf = ops.linear_bf16(a.to(DEV).to(torch.bfloat16), w.to(DEV).to(torch.bfloat16), b.to(DEV), act=act,
+                             want_bf16=True, want_f32=True)
+    # same bf16 operands, fp32 accumulation: only summation order (and tanh.approx for sigmoid) differs
+    close32(yf, ref, 2e-3 if act == 2 else 2e-4)
+    close_bf16(yb.float(), ref, 5e-3, 1e-2)
+
+
+def _random_diffnet(C, H, M, L, seed, cycle=4):
+    from ensemble_svs_with_interactions_b200.diffsinger import DiffNet
+    torch.manual_seed(seed)
+    m = DiffNet(in_dim=M, encoder_hidden_dim=H, residual_layers=L, residual_channels=C, dilation_cycle_length=cycle)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        m.output_projection.weight.copy_(torch.randn(m.output_projection.weight.shape, generator=g) * 0.05)
+        for p in m.parameters():
+            if p.dim() == 1:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+    return m.eval()
+
+
+@pytest.mark.parametrize("C,H,T,dil,tile", [(256, 256, 333, 1, 0), (256, 256, 333, 8, 96), (256, 128, 200, 4, 128),
+                                            (128, 128, 97, 2, 32), (256, 256, 40, 8, 64), (128, 64, 517, 1, 112)])
+def test_diffnet_block_bf16_single_layer(C, H, T, dil, tile):
+    """One fused block vs the oracle block evaluated on the same bf16-rounded operands (tight: isolates the kernel)."""
+    ops = _ops()
+    m = _random_diffnet(C, H, 16, 1, seed=C + T + dil)
+    layer = m.residual_layers[0]
+    layer.dilation = dil
+    g = torch.Generator().manual_seed(T)
+    B = 2
+    x = torch.randn(B, C, T, generator=g); cond = torch.randn(B, H, T, generator=g); dp = torch.randn(B, C, generator=g) * 0.5
+    skip0 = torch.randn(B, C, T, generator=g)
+    # oracle on bf16-rounded weights/activations
+    sd = {k: v.detach() for k, v in layer.state_dict().items()}
+    W = _bf(sd["dilated_conv.weight"]); Wc = _bf(sd["conditioner_projection.weight"]); Wo = _bf(sd["output_projection.weight"])
+    xb = _bf(x)
+    y = O.conv_taps(xb, W, sd["dilated_conv.bias"], (-dil, 0, dil), "zeros")
+    # step term in fp32 (the kernel adds W_j . dp per valid tap in the epilogue, with fp32 W)
+    y = y + O.conv_taps(dp[:, :, None].expand(B, C, T).contiguous() * 1.0, sd["dilated_conv.weight"], None, (-dil, 0, dil), "zeros")
+    y = y + O.conv1x1(_bf(cond), Wc, sd["conditioner_projection.bias"])
+    z = _bf(torch.sigmoid(y[:, :C]) * torch.tanh(y[:, C:]))
+    o = O.conv1x1(z, Wo, sd["output_projection.bias"])
+    x_ref = (x + o[:, :C]) / math.sqrt(2.0)
+    s_ref = skip0 + o[:, C:]
+
+    m = m.to(DEV)
+    plan = m.bf16_plan()
+    lw = plan.layers[0]
+    xbd, x32 = ops.nct_to_ntc(x.to(DEV), want_bf16=True, want_f32=True)
+    _, skip32 = ops.nct_to_ntc(skip0.to(DEV), want_bf16=False, want_f32=True)
+    condb, _ = ops.nct_to_ntc(cond.to(DEV))
+    sb = ops.linear_f32(dp.to(DEV), lw["stepw"], lw["stepb"])
+    xb_out = torch.full_like(xbd, float("nan"))
+    ops.diffnet_block_bf16(xbd, xb_out, x32, skip32, condb, lw["w1p"], lw["woutp"], sb, lw["bout"], dilation=dil,
+                           stepbias_batch_stride=6 * C, init_skip=False, write_x=True, time_tile=tile)
+    torch.cuda.synchronize()
+    close_bf16(x32.transpose(1, 2), x_ref, 3e-3, 1e-2)
+    close_bf16(skip32.transpose(1, 2), s_ref, 3e-3, 1e-2)
+    assert torch.equal(xb_out.float(), x32.to(torch.bfloat16).float())
+
+
+def test_diffnet_bf16_forward_vs_oracle():
+    """Full 20-layer denoiser at the recipe width vs the fp32 CPU oracle (true bf16-vs-fp32 error)."""
+    m = _random_diffnet(256, 256, 80, 20, seed=7)
+    B, T = 2, 300
+    g = torch.Generator().manual_seed(8)
+    spec = torch.randn(B, 1, 80, T, generator=g); cond = torch.randn(B, 256, T, generator=g); t = torch.tensor([3, 77])
+    ref = O.diffnet_forward({k: v.detach() for k, v in m.state_dict().items()}, spec, t, cond, 20, 4)
+    m = m.to(DEV)
+    assert m.resolved_precision() == "bf16"
+    y = m(spec.to(DEV), t.to(DEV), cond.to(DEV))
+    r, mx = close_bf16(y, ref)
+    print(f"diffnet bf16 vs fp32 oracle: rel_l2={r:.3e} max_abs/|ref|max={mx:.3e}")
+    m.precision = "fp32"
+    close32(m(spec.to(DEV), t.to(DEV), cond.to(DEV)), ref, 5e-4)
+
+
+@pytest.mark.parametrize("M,C,H,L", [(60, 256, 256, 8), (5, 128, 128, 6)])
+def test_diffusion_bf16_sampling_vs_oracle(M, C, H, L):
+    """mgc (M=60) and bap (M=5, C=H=128) shaped samplers: K steps with injected noise, graph and eager."""
+    from ensemble_svs_with_interactions_b200.diffsinger import GaussianDiffusion
+    K, B, T = 12, 2, 128
+    den = _random_diffnet(C, H, M, L, seed=M)
+    m = GaussianDiffusion(H, M, den, K_step=K).eval()
+    g = torch.Generator().manual_seed(M + 1)
+    cond = torch.randn(B, T, H, generator=g); x_T = torch.randn(B, 1, M, T, generator=g); z = torch.randn(K, B, 1, M, T, generator=g)
+    ref = O.diffusion_inference({k: v.detach() for k, v in m.state_dict().items()}, cond, x_T, z, K_step=K,
+                                residual_layers=L, dilation_cycle_length=4)
+    m = m.to(DEV)
+    m.use_cuda_graph = False
+    y_eager = m.inference(cond.to(DEV), x_T=x_T.to(DEV), z=z.to(DEV))
+    r, mx = close_bf16(y_eager, ref, 5e-2, 1.5e-1)
+    print(f"sampling M={M}: rel_l2={r:.3e} max_abs/|ref|max={mx:.3e}")
+    m.use_cuda_graph = True
+    y_graph = m.inference(cond.to(DEV), x_T=x_T.to(DEV), z=z.to(DEV))
+    assert torch.equal(y_graph, y_eager)                      # graph replay is bit-identical to eager launches
+    y_again = m.inference(cond.to(DEV), x_T=x_T.to(DEV), z=z.to(DEV))
+    assert torch.equal(y_again, y_graph)                      # deterministic
+    y_rng = m.inference(cond.to(DEV))
+    assert y_rng.shape == (B, T, M) and torch.isfinite(y_rng).all()
+
+
+def test_diffnet_bf16_full_size_properties():
+    """BASELINE config 2 size (B=6, T=2000): properties that do not need the (slow) CPU oracle."""
+    m = _random_diffnet(256, 256, 80, 20, seed=11).to(DEV)
+    B, T = 6, 2000
+    g = torch.Generator().manual_seed(12)
+    spec = torch.randn(B, 1, 80, T, generator=g).to(DEV); cond = torch.randn(B, 256, T, generator=g).to(DEV)
+    t = torch.full((B,), 42, device=DEV)
+    y = m(spec, t, cond)
+    assert y.shape == (B, 1, 80, T) and torch.isfinite(y).all()
+    assert torch.equal(y, m(spec, t, cond))                                  # deterministic
+    # tracks are independent: a single track alone gives the same numbers (different tiling -> same per-column maths)
+    y3 = m(spec[3:4].contiguous(), t[3:4], cond[3:4].contiguous())
+    assert max_abs(y3.cpu(), y[3:4].cpu()) <= 1e-5 * max(1.0, y.abs().max().item())
+    # locality: receptive field is +-(1+2+4+8)*5 = 75 frames; a change at frame 1000 cannot move frames beyond it
+    cond2 = cond.clone(); cond2[:, :, 1000] += 1.0
+    y2 = m(spec, t, cond2)
+    assert torch.equal(y2[..., :924], y[..., :924]) and torch.equal(y2[..., 1076:], y[..., 1076:])
+    assert not torch.equal(y2[..., 1000], y[..., 1000])
+    # against the library's own fp32 path at full size
+    m.precision = "fp32"
+    r, mx = close_bf16(y, m(spec, t, cond))
+    print(f"full-size bf16 vs fp32 path: rel_l2={r:.3e} max={mx:.3e}")
+
+
+def test_diffnet_training_forward_backward():
+    """Training forward runs libsvsk; backward (interim) via autograd re-statement."""
+    from ensemble_svs_with_interactions_b200.diffsinger import GaussianDiffusion
+    den = _random_diffnet(128, 128, 60, 4, seed=21)
+    m = GaussianDiffusion(128, 60, den, K_step=100).to(DEV).train()
+    g = torch.Generator().manual_seed(22)
+    B, T = 2, 64
+    cond = torch.randn(B, T, 128, generator=g).to(DEV); y = torch.randn(B, T, 60, generator=g).to(DEV)
+    noise, eps = m(cond, None, y)
+    assert noise.shape == eps.shape == (B, T, 60) and eps.requires_grad
+    loss = (noise - eps).abs().mean()
+    loss.backward()
+    grads = [p.grad for p in m.parameters()]
+    assert all(gr is not None and torch.isfinite(gr).all() for gr in grads)
+    assert sum(float(gr.abs().sum()) for gr in grads) > 0

@@ -1,0 +1,123 @@
+"""CPU-only: drop-in boundary (constructor kwargs, state_dict layout, schedule buffers) against the golden fixtures."""
+import inspect
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from ensemble_svs_with_interactions_b200.base import BaseModel, PredictionType
+from ensemble_svs_with_interactions_b200.diffsinger import DiffNet, GaussianDiffusion, MultiSpeakerGaussianDiffusion
+from ensemble_svs_with_interactions_b200.usfgan.models import (CascadeHnUSFGANGenerator, ParallelHnUSFGANGenerator,
+                                                              USFGANGenerator)
+from ensemble_svs_with_interactions_b200.wavenet import WaveNet, receptive_field_size
+from tests.golden_util import Golden
+
+warnings.filterwarnings("ignore", category=FutureWarning)
+
+
+def _same_layout(module, golden_sd):
+    sd = module.state_dict()
+    assert list(sd.keys()) == list(golden_sd.keys())          # names AND order
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(golden_sd[k].shape), k
+    module.load_state_dict(golden_sd, strict=True)
+
+
+def test_diffnet_state_dict_layout():
+    g = Golden("diffnet_small")
+    _same_layout(DiffNet(**g.cfg), g.sd)
+
+
+def test_diffnet_ctor_signature_matches_reference():
+    names = list(inspect.signature(DiffNet.__init__).parameters)[1:6]
+    assert names == ["in_dim", "encoder_hidden_dim", "residual_layers", "residual_channels", "dilation_cycle_length"]
+    m = DiffNet()
+    assert (m.in_dim, len(m.residual_layers), m.residual_channels) == (80, 20, 256)
+    assert [l.dilation for l in m.residual_layers[:5]] == [1, 2, 4, 8, 1]
+    assert torch.count_nonzero(m.output_projection.weight) == 0   # zero init (denoiser.py:99)
+    assert 15.0e6 < sum(p.numel() for p in m.parameters()) < 15.2e6   # DiffNet 15.08 M
+
+
+def test_gaussian_diffusion_buffers_and_layout():
+    g = Golden("diffusion_small")
+    m = GaussianDiffusion(20, 12, DiffNet(**g.cfg["denoiser"]), K_step=g.cfg["K_step"])
+    sd = m.state_dict()
+    for k in list(g.sd)[:12]:
+        assert torch.equal(sd[k], g.sd[k]), k       # float64 schedule maths -> fp32, bit exact
+    _same_layout(m, g.sd)
+    assert m.prediction_type() == PredictionType.DIFFUSION
+    assert isinstance(m, BaseModel) and not m.is_autoregressive() and not m.has_residual_lf0_prediction()
+    with pytest.raises(NotImplementedError):
+        GaussianDiffusion(20, 12, DiffNet(**g.cfg["denoiser"]), pndm_speedup=4)
+    cos = GaussianDiffusion(20, 12, DiffNet(**g.cfg["denoiser"]), K_step=10, schedule_type="cosine")
+    assert cos.betas.shape == (10,) and float(cos.betas.max()) <= 0.999 + 1e-6
+
+
+def test_multispeaker_signature():
+    names = list(inspect.signature(MultiSpeakerGaussianDiffusion.__init__).parameters)
+    assert names[1:5] == ["in_dim", "out_dim", "denoise_fn", "speaker_embedding"]
+
+
+@pytest.mark.parametrize("name", ["wavenet_small", "wavenet_test_shape"])
+def test_wavenet_state_dict_layout(name):
+    g = Golden(name)
+    m = WaveNet(**g.cfg)
+    _same_layout(m, g.sd)
+    m.remove_weight_norm_()
+    assert "first_conv.weight" in m.state_dict() and "first_conv.weight_g" not in m.state_dict()
+    assert receptive_field_size(30, 3, 2) == 3070
+
+
+def _hn_kwargs(c):
+    return dict(harmonic_network_params=c["harmonic"], noise_network_params=c["noise"],
+                filter_network_params=c["filt"], periodicity_estimator_params=c["pe"], **c["common"])
+
+
+def test_usfgan_state_dict_layouts_with_and_without_weight_norm():
+    g = Golden("usfgan_parallel_hn_small")
+    m = ParallelHnUSFGANGenerator(**_hn_kwargs(g.cfg))
+    _same_layout(m, g.sd)
+    m.remove_weight_norm()
+    _same_layout(m, Golden("usfgan_parallel_hn_small_nowm").sd)
+    m.apply_weight_norm()
+    assert list(m.state_dict().keys()).count("conv_first_sine.weight_g") == 1
+    g = Golden("usfgan_cascade_hn_small")
+    _same_layout(CascadeHnUSFGANGenerator(**_hn_kwargs(g.cfg)), g.sd)
+    g = Golden("usfgan_plain_small")
+    _same_layout(USFGANGenerator(source_network_params=g.cfg["source"], filter_network_params=g.cfg["filt"],
+                                 **g.cfg["common"]), g.sd)
+
+
+def test_recipe_vocoder_key_counts():
+    """756 keys with weight norm, 484 after remove_weight_norm for the recipe ParallelHn generator."""
+    pe = {"conv_layers": 3, "kernel_size": 5, "dilation": 1, "padding_mode": "replicate"}
+    m = ParallelHnUSFGANGenerator(periodicity_estimator_params=pe)
+    assert len(m.state_dict()) == 756
+    m.remove_weight_norm()
+    assert len(m.state_dict()) == 484
+    dil = [b.dilation for b in m.filter_network.conv_dilated]
+    assert dil[:10] == [2 ** i for i in range(10)] and dil[10] == 1
+    with pytest.raises(TypeError):       # reference quirk kept: the default key "conv_blocks" is rejected
+        ParallelHnUSFGANGenerator()
+
+
+def test_default_dicts_are_not_mutated():
+    pe = {"conv_layers": 3, "kernel_size": 5, "dilation": 1, "padding_mode": "replicate"}
+    hp = {"blockA": 2, "cycleA": 1, "blockF": 0, "cycleF": 0, "cascade_mode": 0}
+    ParallelHnUSFGANGenerator(harmonic_network_params=hp, periodicity_estimator_params=pe)
+    assert set(hp) == {"blockA", "cycleA", "blockF", "cycleF", "cascade_mode"}
+
+
+def test_dilated_factor_and_signal_generator_cpu():
+    from ensemble_svs_with_interactions_b200.usfgan.utils import SignalGenerator, dilated_factor
+    g = Golden("usfgan_frontend")
+    cfg = g.cfg
+    f0 = g.inp["f0"].numpy()
+    df = dilated_factor(np.squeeze(f0.copy()), cfg["sample_rate"], cfg["dense_factor"]).repeat(cfg["hop_size"])
+    assert np.array_equal(df, g.out["df"].numpy())
+    sg = SignalGenerator(sample_rate=cfg["sample_rate"], hop_size=cfg["hop_size"], sine_amp=cfg["sine_amp"],
+                         noise_amp=cfg["noise_amp"], signal_types=["sine", "noise"])
+    torch.manual_seed(53)
+    sig = sg(torch.FloatTensor(f0).unsqueeze(0).transpose(2, 1))
+    assert torch.allclose(sig, g.out["in_signal"], atol=1e-6)
