@@ -14,6 +14,7 @@
 // filter of the same channel from two column ranges of its own lane.  Pair p's gating overlaps pair p+1's MMAs;
 // the residual epilogue of the second GEMM overlaps the skip half's MMAs.
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "sm100_ptx.cuh"
 #include "svsk_common.cuh"
@@ -33,6 +34,8 @@ struct DiffnetBlockArgs {
   const float* stepbias;
   const float* bout;
   int B, T, C, H, dilation, sb_stride, init_skip, write_x, NT, nstages;
+  unsigned long long* dbg;  // optional [num_ctas][16] clock64 timeline (SVSK_DIFFNET_TIMELINE)
+  int dbg_flags;            // ablation switches for profiling only
 };
 
 struct __align__(8) DiffnetBarriers {
@@ -88,6 +91,9 @@ diffnet_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  unsigned long long* dbg = a.dbg ? a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
+#define SVSK_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
+  if (threadIdx.x == 0) SVSK_STAMP(0);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -119,6 +125,7 @@ diffnet_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
           if (++s == a.nstages) { s = 0; ph ^= 1; }
         }
       }
+      SVSK_STAMP(1);  // all loads issued
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
@@ -144,10 +151,12 @@ diffnet_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
           if (++s == a.nstages) { s = 0; ph ^= 1; }
         }
         ptx::umma_commit(&bars->d1_full[p]);
+        SVSK_STAMP(2 + p);  // GEMM1 pair p issued
       }
       // second GEMM: A = Wout rows (two M blocks per stage), B = gated activations resident in smem
       ptx::mbar_wait(&bars->g_ready, 0);
       ptx::tc_fence_after();
+      SVSK_STAMP(4);  // G ready seen by the MMA thread
       const uint32_t g0 = ptx::smem_u32(g_smem);
       for (int p = 0; p < pairs; ++p) {
         for (int kb = 0; kb < KB2; ++kb) {
@@ -166,6 +175,7 @@ diffnet_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
           if (++s == a.nstages) { s = 0; ph ^= 1; }
         }
         ptx::umma_commit(&bars->d2_full[p]);
+        SVSK_STAMP(5 + p);  // GEMM2 pair p issued
       }
     }
   } else {
@@ -187,7 +197,9 @@ diffnet_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 
       ptx::mbar_wait(&bars->d1_full[p], 0);
       ptx::tc_fence_after();
+      if (warp == 2 && lane == 0) SVSK_STAMP(7 + 2 * p);   // D1 pair p complete
       for (int c0 = 0; c0 < NT; c0 += 16) {
+        if (a.dbg_flags & 2) break;
         uint32_t rg[16], rf[16];
         ptx::tmem_ld16(tmem + tlane + p * 2 * NT + c0, rg);
         ptx::tmem_ld16(tmem + tlane + p * 2 * NT + NT + c0, rf);
@@ -203,7 +215,9 @@ diffnet_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
               __float2bfloat16_rn(z);
         }
       }
+      if (warp == 2 && lane == 0) SVSK_STAMP(8 + 2 * p);  // gating of pair p done
     }
+    if (warp == 2 && lane == 0) SVSK_STAMP(11);  // gating done
     ptx::tc_fence_before();
     ptx::fence_proxy_async_smem();  // generic-proxy writes of G -> visible to the tensor core's async proxy
     ptx::mbar_arrive(&bars->g_ready);
@@ -212,7 +226,9 @@ diffnet_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     for (int p = 0; p < pairs; ++p) {
       ptx::mbar_wait(&bars->d2_full[p], 0);
       ptx::tc_fence_after();
+      if (warp == 2 && lane == 0) SVSK_STAMP(12 + p);  // D2 pair p complete
       for (int half = 0; half < 2; ++half) {
+        if (a.dbg_flags & 1) break;
         const int mb = 2 * p + half;
         const int orow = mb * 128 + q * 32 + lane;
         const bool is_res = (mb * 128) < C;  // warp-uniform
@@ -264,9 +280,12 @@ diffnet_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     }
   }
 
+  if (warp == 2 && lane == 0) SVSK_STAMP(14);  // epilogue done
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem, kTmemCols);
+  if (threadIdx.x == 0) SVSK_STAMP(15);
+#undef SVSK_STAMP
 }
 
 // reference row r in [0,2C) -> packed row (gate rows of channel block q at 256q.., filter rows at 256q+128..)
@@ -401,6 +420,10 @@ extern "C" int svsk_diffnet_block_bf16(const svsk_diffnet_block_params* pp, void
   a.write_x = p.write_x;
   a.NT = NT;
   a.nstages = nstages;
+  a.dbg = nullptr;
+  a.dbg_flags = 0;
+  if (const char* e = getenv("SVSK_DIFFNET_TIMELINE")) a.dbg = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
+  if (const char* e = getenv("SVSK_DIFFNET_ABLATE")) a.dbg_flags = atoi(e);
   dim3 grid(ceil_div(p.T, NT), p.B);
   diffnet_block_kernel<<<grid, 192, smem_bytes, as_stream(stream)>>>(tm_x, tm_cond, tm_w1, tm_wout, a);
   return check_launch("diffnet_block_bf16");

@@ -28,6 +28,7 @@ static EncodeTiledFn resolve_encode() {
 struct Key {
   const void* base;
   int rank;
+  int dtype;
   uint64_t dims[3];
   uint64_t strides[2];
   uint32_t box[3];
@@ -38,8 +39,8 @@ struct Entry {
   CUtensorMap m;
 };
 
-int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box) {
+static int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, CUtensorMapDataType dtype) {
   SVSK_REQUIRE(rank == 2 || rank == 3, SVSK_E_ARG, "tmap: rank %d", rank);
   SVSK_REQUIRE(((uintptr_t)base % 16) == 0, SVSK_E_ALIGN, "tmap: base pointer not 16-byte aligned");
   for (int i = 0; i < rank - 1; ++i)
@@ -51,6 +52,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   std::memset(&k, 0, sizeof(k));
   k.base = base;
   k.rank = rank;
+  k.dtype = (int)dtype;
   for (int i = 0; i < rank; ++i) {
     k.dims[i] = dims[i];
     k.box[i] = box[i];
@@ -78,7 +80,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   }
   for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
   CUtensorMap m;
-  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox,
+  CUresult r = enc(&m, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SVSK_REQUIRE(r == CUDA_SUCCESS, SVSK_E_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -89,6 +91,15 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   }
   *out = m;
   return 0;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  return make_tmap(out, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+}
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+  return make_tmap(out, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
 }
 
 }  // namespace svsk

@@ -12,5 +12,8 @@ namespace svsk {
 // strides_bytes[i] is the byte stride of dimension i+1.  Returns 0 or an SVSK_E* / cudaError code.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
+// same for fp32 tensors (box_inner 32 floats = 128 B swizzle span)
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
 
 }  // namespace svsk

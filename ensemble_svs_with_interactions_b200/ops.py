@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -195,7 +196,10 @@ def diffnet_packed_rows(Cc):
 
 
 def diffnet_block_bf16(xb_in, xb_out, x32, skip32, cond, w1p, woutp, stepbias, bout, *, dilation, stepbias_batch_stride,
-                       init_skip, write_x=True, time_tile=0):
+                       init_skip, write_x=True, time_tile=0, kernel=None):
+    """kernel=2: CTA-pair kernel (default); kernel=1: single-CTA kernel (time_tile selects its N tile)."""
+    if kernel is None:
+        kernel = 1 if time_tile else int(os.environ.get("SVSK_DIFFNET_KERNEL", "2"))
     B, T, Cc = xb_in.shape
     p = L.DiffnetBlockParams()
     p.xb_in, p.xb_out = L.ptr(xb_in, bf16, "xb_in"), L.ptr(xb_out, bf16, "xb_out")
@@ -205,7 +209,8 @@ def diffnet_block_bf16(xb_in, xb_out, x32, skip32, cond, w1p, woutp, stepbias, b
     p.B, p.T, p.C, p.H = B, T, Cc, cond.shape[2]
     p.dilation, p.stepbias_batch_stride = int(dilation), int(stepbias_batch_stride)
     p.init_skip, p.write_x, p.time_tile = int(init_skip), int(write_x), int(time_tile)
-    L.check(L.lib().svsk_diffnet_block_bf16(C.byref(p), L.stream_ptr()), "diffnet_block_bf16")
+    fn = L.lib().svsk_diffnet_block2_bf16 if kernel == 2 else L.lib().svsk_diffnet_block_bf16
+    L.check(fn(C.byref(p), L.stream_ptr()), "diffnet_block_bf16")
 
 
 def linear_bf16(a, w, bias=None, *, act=ACT_NONE, want_bf16=False, want_f32=False, out_bf16=None, out_f32=None):

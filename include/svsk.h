@@ -182,6 +182,11 @@ typedef struct svsk_diffnet_block_params {
 } svsk_diffnet_block_params;
 SVSK_API int svsk_diffnet_block_bf16(const svsk_diffnet_block_params* p, void* stream);
 
+/* Same contract and packed operands, CTA-pair kernel (tcgen05 cta_group::2, clusters of 2): time is the MMA M
+ * dimension (256 frames per pair), each SM stages half of every weight tile, N = 256 per MMA.  `time_tile` is ignored.
+ * Additionally requires x32 / skip32 / xb_out to be 16-byte aligned.  This is the kernel the drop-in modules use. */
+SVSK_API int svsk_diffnet_block2_bf16(const svsk_diffnet_block_params* p, void* stream);
+
 /* Pack one block's weights (fp32, reference state_dict layout) for svsk_diffnet_block_bf16.
  *   dilated_w [2C][C][3], cond_w [2C][H][1], out_w [2C][C][1]  ->  w1p [2C][3C+H] bf16, woutp [2C][C] bf16.
  * Row r of the reference maps to packed row perm(r): gate rows of channel block q at 256q..256q+127, filter rows at

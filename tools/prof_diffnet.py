@@ -1,0 +1,21 @@
+"""Profiling target: a few eager (no CUDA graph) DDPM steps of the BASELINE config-2 denoiser, so ncu sees every
+libsvsk launch.  usage: python tools/prof_diffnet.py [steps] [time_tile]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+m = bench.build_model().to("cuda")
+if len(sys.argv) > 2:
+    m.denoise_fn.time_tile = int(sys.argv[2])
+m.use_cuda_graph = False
+m.K_step = steps  # only the first `steps` entries of the schedule tables are used
+g = torch.Generator().manual_seed(0)
+cond = torch.randn(bench.B, bench.T, 256, generator=g).cuda()
+y = m.inference(cond)
+torch.cuda.synchronize()
+print("ok", tuple(y.shape), float(y.abs().mean()))
