@@ -52,8 +52,8 @@ class UsfganBlockParams(C.Structure):
         ("xb_in", C.c_void_p), ("xb_out", C.c_void_p), ("aux", C.c_void_p),
         ("w1p", C.c_void_p), ("woutp", C.c_void_p), ("bias1", C.c_void_p), ("bout", C.c_void_p),
         ("idx_past", C.c_void_p), ("idx_future", C.c_void_p),
-        ("B", C.c_int32), ("T", C.c_int32), ("C", C.c_int32), ("A", C.c_int32),
-        ("dilation", C.c_int32), ("adaptive", C.c_int32),
+        ("B", C.c_int32), ("T", C.c_int32), ("A", C.c_int32),
+        ("dilation", C.c_int32), ("adaptive", C.c_int32), ("out_scale", C.c_float),
     ]
 
 
@@ -82,6 +82,9 @@ _SIGNATURES = {
     "svsk_diffnet_pack_block": [_V, _V, _V, _V, _V, _I, _I, _V],
     "svsk_diffnet_packed_row": [_I, _I],
     "svsk_linear_bf16": [C.POINTER(LinearBf16Params), _V],
+    "svsk_usfgan_block_bf16": [C.POINTER(UsfganBlockParams), _V],
+    "svsk_usfgan_pack_block": [_V, _V, _V, _V, _V, _I, _I, _I, _V],
+    "svsk_ntc_bf16_to_nct_f32": [_V, _V, _I, _I, _I, _I, _V],
 }
 EXPORTED_SYMBOLS = ["svsk_last_error"] + list(_SIGNATURES)
 

@@ -71,6 +71,21 @@ __global__ void ntc_to_nct_kernel(const float* __restrict__ x, float* __restrict
   }
 }
 
+__global__ void ntc_bf16_to_nct_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int C, int T, int Cp) {
+  __shared__ float tile[32][33];
+  int b = blockIdx.z;
+  int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int t = t0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (t < T && c < C) ? __bfloat162float(x[((size_t)b * T + t) * Cp + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int c = c0 + i, t = t0 + threadIdx.x;
+    if (c < C && t < T) y[((size_t)b * C + c) * T + t] = tile[threadIdx.x][i];
+  }
+}
+
 __global__ void cast_scale_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n, float alpha,
                                        int relu) {
   size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -121,6 +136,14 @@ extern "C" int svsk_ntc_to_nct_f32(const float* x, float* y, int B, int C, int T
   dim3 grid(ceil_div(T, 32), ceil_div(C, 32), B);
   ntc_to_nct_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(x, y, C, T, Cp, alpha);
   return check_launch("ntc_to_nct_f32");
+}
+
+extern "C" int svsk_ntc_bf16_to_nct_f32(const void* x, float* y, int B, int C, int T, int Cp, void* stream) {
+  SVSK_REQUIRE(x && y, SVSK_E_ARG, "ntc_bf16_to_nct_f32: null");
+  SVSK_REQUIRE(B > 0 && B <= 65535 && C > 0 && T > 0 && Cp >= C, SVSK_E_ARG, "ntc_bf16_to_nct_f32: bad shape");
+  dim3 grid(ceil_div(T, 32), ceil_div(C, 32), B);
+  ntc_bf16_to_nct_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>((const __nv_bfloat16*)x, y, C, T, Cp);
+  return check_launch("ntc_bf16_to_nct_f32");
 }
 
 extern "C" int svsk_cast_scale_bf16(const float* x, void* y, size_t n, float alpha, int relu, void* stream) {

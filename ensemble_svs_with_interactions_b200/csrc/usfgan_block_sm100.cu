@@ -1,0 +1,420 @@
+// Fused uSFGAN / QPPWG residual block on sm_100a — replaces FixedBlock.forward and AdaptiveBlock.forward (+ pd_indexing)
+// nnsvs/usfgan/layers/residual_block.py:123-157, 198-234 and nnsvs/usfgan/utils/index.py:12-54 with ONE launch per block.
+//
+//   D1[t][128] = [x(tap0) ; x(t) ; x(tap2) ; aux(t)] . W1p^T        K = 3*64 + A (A = 80 / 65 aux channels)
+//   z = tanh(D1[:, :64] + b) * sigmoid(D1[:, 64:] + b)              (tanh on the FIRST half, unlike DiffNet)
+//   D2[t][64]  = z . Wout^T ;   x'(t) = (D2 + bout + x(t)) * sqrt(1/2)
+//   (conv1x1_skip is dead work in the reference, residual_block.py:333-336, and is not evaluated)
+//   taps: FixedBlock  -> t -/+ dilation with REFLECT padding;  AdaptiveBlock -> idx_past[b,t] / idx_future[b,t]
+//         (svsk_pd_index; -1 = zero).
+//
+// Persistent kernel, one CTA per SM looping over 128-sample tiles (time = MMA M).  The block's weights (88 KB bf16) are
+// loaded into shared memory ONCE per CTA and stay resident; only activations stream:
+//   warp 0      TMA producer: centre tap + aux k-blocks, and both side taps of interior fixed-block tiles
+//   warp 1      MMA issuer (tcgen05.mma cta_group::1, M=128, N=128 then N=64) + TMEM owner
+//   warps 2-5   gather producers (thread = row): side taps of adaptive blocks / boundary tiles via cp.async 16-byte
+//               copies into the swizzled tile, completion signalled with cp.async.mbarrier.arrive.noinc
+//   warps 6-9   epilogue (thread = sample): gate -> G (bf16, swizzled smem) ; residual -> same buffer -> TMA store
+// TMEM holds two D1 (2x128 columns) and two D2 (2x64) accumulators, so the MMAs of tile n+1 overlap the epilogue of
+// tile n.  The residual x(t) is prefetched by its epilogue thread (one 128-byte row per thread) at the top of the tile.
+#include <cuda_bf16.h>
+#include <cstdlib>
+
+#include "sm100_ptx.cuh"
+#include "svsk_common.cuh"
+#include "tma_util.cuh"
+
+namespace svsk {
+
+constexpr int kUTile = 128 * 128;  // 128 rows x 64 bf16
+constexpr int kUMaxStages = 6;
+constexpr int kUThreads = 320;
+constexpr int kUMaxKB = 8;         // 3 taps + up to 5 aux k-blocks (aux <= 320 channels)
+
+struct UsfganArgs {
+  const __nv_bfloat16* xb_in;
+  const float* bias1;
+  const float* bout;
+  const int32_t* idx_past;
+  const int32_t* idx_future;
+  int B, T, A, dilation, adaptive, nstages, akb, last_ksteps, tiles_per_row, total_tiles;
+  float out_scale;
+};
+
+struct __align__(8) UsfganBarriers {
+  uint64_t full_t[kUMaxStages];  // slot filled by TMA (1 arrival + tx bytes)
+  uint64_t full_g[kUMaxStages];  // slot filled by the 128 gather threads
+  uint64_t empty[kUMaxStages];
+  uint64_t d1_full[2], g_full[2], d2_full[2];
+  uint64_t w_full;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ptx::smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ptx::smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ bool tile_needs_gather(int t0, int T, int d, int adaptive) {
+  if (adaptive) return true;
+  const int last = min(t0 + 127, T - 1);
+  return (t0 - d < 0) || (last + d >= T);  // a reflected tap: rows are not a shifted copy any more
+}
+
+__global__ void __launch_bounds__(kUThreads, 1)
+usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_aux,
+                    const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_wout,
+                    const __grid_constant__ CUtensorMap tm_xout, const UsfganArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int KB = 3 + a.akb;                      // k-blocks per tile
+  uint8_t* w1_s = smem;                          // KB tiles of [128 rows][64]
+  uint8_t* wout_s = w1_s + KB * kUTile;          // [64 rows][64] = 8 KB
+  uint8_t* ring = wout_s + 8192;
+  uint8_t* gbuf = ring + a.nstages * kUTile;     // 2 x 16 KB: G, then the output tile, of tile parity p
+  float* bias_s = reinterpret_cast<float*>(gbuf + 2 * kUTile);  // [128] gate biases, [64] output biases
+  UsfganBarriers* bars = reinterpret_cast<UsfganBarriers*>(bias_s + 192);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = a.T;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_x);
+    ptx::prefetch_tmap(&tm_aux);
+    ptx::prefetch_tmap(&tm_w1);
+    ptx::prefetch_tmap(&tm_wout);
+    ptx::prefetch_tmap(&tm_xout);
+    for (int i = 0; i < a.nstages; ++i) {
+      ptx::mbar_init(&bars->full_t[i], 1);
+      ptx::mbar_init(&bars->full_g[i], 128);
+      ptx::mbar_init(&bars->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bars->d1_full[i], 1);
+      ptx::mbar_init(&bars->g_full[i], 128);
+      ptx::mbar_init(&bars->d2_full[i], 1);
+    }
+    ptx::mbar_init(&bars->w_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&bars->tmem_base, 512);
+    ptx::tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < 192; i += kUThreads) bias_s[i] = i < 128 ? a.bias1[i] : a.bout[i - 128];
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(&bars->w_full, KB * kUTile + 8192);
+      for (int kb = 0; kb < KB; ++kb) ptx::tma_load_2d(w1_s + kb * kUTile, &tm_w1, &bars->w_full, kb * 64, 0);
+      ptx::tma_load_2d(wout_s, &tm_wout, &bars->w_full, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int b = tile / a.tiles_per_row, t0 = (tile - b * a.tiles_per_row) * 128;
+        const bool gather = tile_needs_gather(t0, T, a.dilation, a.adaptive);
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(&bars->empty[s], ph ^ 1);
+          uint8_t* slot = ring + s * kUTile;
+          if (kb == 1) {
+            ptx::mbar_arrive_expect_tx(&bars->full_t[s], kUTile);
+            ptx::tma_load_3d(slot, &tm_x, &bars->full_t[s], 0, t0, b);
+          } else if (kb >= 3) {
+            ptx::mbar_arrive_expect_tx(&bars->full_t[s], kUTile);
+            ptx::tma_load_3d(slot, &tm_aux, &bars->full_t[s], (kb - 3) * 64, t0, b);
+          } else if (!gather) {
+            ptx::mbar_arrive_expect_tx(&bars->full_t[s], kUTile);
+            ptx::tma_load_3d(slot, &tm_x, &bars->full_t[s], 0, t0 + (kb - 1) * a.dilation, b);
+          }
+          if (++s == a.nstages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc1 = ptx::umma_idesc_bf16_f32(128, 128);
+      const uint32_t idesc2 = ptx::umma_idesc_bf16_f32(128, 64);
+      ptx::mbar_wait(&bars->w_full, 0);
+      ptx::tc_fence_after();
+      const uint32_t w1a = ptx::smem_u32(w1_s), woa = ptx::smem_u32(wout_s), ga = ptx::smem_u32(gbuf);
+      int s = 0;
+      uint32_t ph = 0, pht = 0, phg = 0;  // per-slot phase bits of full_t / full_g (each toggles only when used)
+      int n_issued = 0;  // tiles whose GEMM1 has been issued
+      for (int tile = blockIdx.x;; tile += gridDim.x) {
+        const bool have = tile < a.total_tiles;
+        if (have) {
+          const int b = tile / a.tiles_per_row, t0 = (tile - b * a.tiles_per_row) * 128;
+          const bool gather = tile_needs_gather(t0, T, a.dilation, a.adaptive);
+          const int p = n_issued & 1;
+          for (int kb = 0; kb < KB; ++kb) {
+            const bool from_gather = gather && (kb == 0 || kb == 2);
+            if (from_gather) {
+              ptx::mbar_wait(&bars->full_g[s], (phg >> s) & 1);
+              phg ^= 1u << s;
+              ptx::fence_proxy_async_smem();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+            } else {
+              ptx::mbar_wait(&bars->full_t[s], (pht >> s) & 1);
+              pht ^= 1u << s;
+            }
+            ptx::tc_fence_after();
+            const uint32_t a0 = ptx::smem_u32(ring + s * kUTile);
+            const int ks = (kb == KB - 1) ? a.last_ksteps : 4;
+            for (int k4 = 0; k4 < ks; ++k4)
+              ptx::umma_bf16(tmem + p * 128, ptx::umma_desc_k_sw128(a0 + k4 * 32),
+                             ptx::umma_desc_k_sw128(w1a + kb * kUTile + k4 * 32), idesc1, (kb | k4) != 0);
+            ptx::umma_commit(&bars->empty[s]);
+            if (++s == a.nstages) { s = 0; ph ^= 1; }
+          }
+          ptx::umma_commit(&bars->d1_full[p]);
+        }
+        if (n_issued > 0) {  // GEMM2 of the previous tile: its G is written while this tile's GEMM1 runs
+          const int m = n_issued - 1, p = m & 1;
+          ptx::mbar_wait(&bars->g_full[p], (m >> 1) & 1);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            ptx::umma_bf16(tmem + 256 + p * 64, ptx::umma_desc_k_sw128(ga + p * kUTile + k4 * 32),
+                           ptx::umma_desc_k_sw128(woa + k4 * 32), idesc2, k4 != 0);
+          ptx::umma_commit(&bars->d2_full[p]);
+        }
+        if (!have) break;
+        ++n_issued;
+      }
+      (void)ph;
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------ gather producers (thread = row of the tile)
+    const int r = threadIdx.x - 64;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      const int b = tile / a.tiles_per_row, t0 = (tile - b * a.tiles_per_row) * 128;
+      const bool gather = tile_needs_gather(t0, T, a.dilation, a.adaptive);
+      const int t = t0 + r;
+      for (int kb = 0; kb < KB; ++kb) {
+        if (gather && (kb == 0 || kb == 2)) {
+          ptx::mbar_wait(&bars->empty[s], ph ^ 1);
+          int src = -1;
+          if (t < T) {
+            if (a.adaptive) {
+              src = (kb == 0 ? a.idx_past : a.idx_future)[(size_t)b * T + t];
+            } else {
+              src = t + (kb - 1) * a.dilation;
+              if (src < 0) src = -src;
+              if (src >= T) src = 2 * (T - 1) - src;
+            }
+          }
+          const bool ok = src >= 0 && src < T;
+          const uint8_t* g = reinterpret_cast<const uint8_t*>(a.xb_in + ((size_t)b * T + (ok ? src : 0)) * 64);
+          uint8_t* slot = ring + s * kUTile;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            cp_async_16(slot + ptx::sw128_offset((uint32_t)r, (uint32_t)c), g + c * 16, ok ? 16u : 0u);
+          cp_async_arrive_noinc(&bars->full_g[s]);
+        }
+        if (++s == a.nstages) { s = 0; ph ^= 1; }
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else {
+    // ------------------------------------------------------------------ epilogue (thread = one sample)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t tlane = (uint32_t)(q * 32) << 16;
+    const bool elected = (warp == 6 && lane == 0);
+    int n = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++n) {
+      const int b = tile / a.tiles_per_row, t0 = (tile - b * a.tiles_per_row) * 128;
+      const int t = t0 + row, p = n & 1;
+      const uint32_t par = (n >> 1) & 1;
+      // residual row, prefetched: 64 bf16 = 8 x 16 bytes
+      uint4 xr[8];
+      if (t < T) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.xb_in + ((size_t)b * T + t) * 64);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) xr[c] = __ldg(src + c);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) xr[c] = make_uint4(0, 0, 0, 0);
+      }
+      uint8_t* gb = gbuf + p * kUTile;
+      if (n >= 2) {  // the TMA store of tile n-2 must have finished READING this buffer
+        if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        ptx::named_bar_sync(2, 128);
+      }
+      ptx::mbar_wait(&bars->d1_full[p], par);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t ra[16], rb[16];
+        ptx::tmem_ld16(tmem + tlane + p * 128 + c0, ra);
+        ptx::tmem_ld16(tmem + tlane + p * 128 + 64 + c0, rb);
+        ptx::tmem_ld_wait();
+        uint32_t o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float z0 = ptx::tanh_approx(__uint_as_float(ra[2 * e]) + bias_s[c0 + 2 * e]) *
+                           ptx::sigmoid_approx(__uint_as_float(rb[2 * e]) + bias_s[64 + c0 + 2 * e]);
+          const float z1 = ptx::tanh_approx(__uint_as_float(ra[2 * e + 1]) + bias_s[c0 + 2 * e + 1]) *
+                           ptx::sigmoid_approx(__uint_as_float(rb[2 * e + 1]) + bias_s[64 + c0 + 2 * e + 1]);
+          o[e] = ptx::pack_bf16(z0, z1);
+        }
+        ptx::st_shared_v4(gb + ptx::sw128_offset((uint32_t)row, (uint32_t)(c0 >> 3)), o[0], o[1], o[2], o[3]);
+        ptx::st_shared_v4(gb + ptx::sw128_offset((uint32_t)row, (uint32_t)(c0 >> 3) + 1), o[4], o[5], o[6], o[7]);
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&bars->g_full[p]);
+
+      ptx::mbar_wait(&bars->d2_full[p], par);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16) {  // fully unrolled: xr[] must stay in registers
+        uint32_t rd[16];
+        ptx::tmem_ld16(tmem + tlane + 256 + p * 64 + c0, rd);
+        ptx::tmem_ld_wait();
+        uint32_t o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const uint4 xv = xr[(c0 >> 3) + (e >> 2)];
+          const uint32_t xw = (e & 3) == 0 ? xv.x : ((e & 3) == 1 ? xv.y : ((e & 3) == 2 ? xv.z : xv.w));
+          const float lo = (__uint_as_float(rd[2 * e]) + bias_s[128 + c0 + 2 * e] + ptx::bf16_lo(xw)) * a.out_scale;
+          const float hi = (__uint_as_float(rd[2 * e + 1]) + bias_s[128 + c0 + 2 * e + 1] + ptx::bf16_hi(xw)) * a.out_scale;
+          o[e] = ptx::pack_bf16(lo, hi);
+        }
+        ptx::st_shared_v4(gb + ptx::sw128_offset((uint32_t)row, (uint32_t)(c0 >> 3)), o[0], o[1], o[2], o[3]);
+        ptx::st_shared_v4(gb + ptx::sw128_offset((uint32_t)row, (uint32_t)(c0 >> 3) + 1), o[4], o[5], o[6], o[7]);
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      ptx::named_bar_sync(2, 128);
+      if (elected) {
+        ptx::tma_store_3d(&tm_xout, gb, 0, t0, b);
+        ptx::bulk_commit_group();
+      }
+    }
+    if (elected) ptx::bulk_wait_all();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem, 512);
+}
+
+__global__ void usfgan_pack_kernel(const float* __restrict__ w_taps, const float* __restrict__ w_aux,
+                                   const float* __restrict__ w_out, __nv_bfloat16* __restrict__ w1p,
+                                   __nv_bfloat16* __restrict__ woutp, int C, int A, int G, int Ap) {
+  const int K1 = 3 * C + Ap;
+  const int r = blockIdx.x;
+  if (r < G) {
+    for (int k = threadIdx.x; k < K1; k += blockDim.x) {
+      float v = 0.f;
+      if (k < 3 * C) { int j = k / C, ci = k - j * C; v = w_taps[((size_t)r * C + ci) * 3 + j]; }
+      else if (k - 3 * C < A) v = w_aux[(size_t)r * A + (k - 3 * C)];
+      w1p[(size_t)r * K1 + k] = __float2bfloat16_rn(v);
+    }
+  }
+  if (r < C)
+    for (int k = threadIdx.x; k < G / 2; k += blockDim.x) woutp[(size_t)r * (G / 2) + k] = __float2bfloat16_rn(w_out[(size_t)r * (G / 2) + k]);
+}
+
+}  // namespace svsk
+
+using namespace svsk;
+
+extern "C" int svsk_usfgan_pack_block(const float* w_taps, const float* w_aux, const float* w_out, void* w1p,
+                                      void* woutp, int C, int A, int G, void* stream) {
+  SVSK_REQUIRE(w_taps && w_aux && w_out && w1p && woutp, SVSK_E_ARG, "usfgan_pack_block: null");
+  SVSK_REQUIRE(C == 64 && G == 128 && A >= 1 && A <= 320, SVSK_E_ARG,
+               "usfgan_pack_block: needs residual 64 / gate 128 / aux <= 320 (C=%d G=%d A=%d)", C, G, A);
+  const int Ap = (A + 63) / 64 * 64;
+  usfgan_pack_kernel<<<G, 128, 0, as_stream(stream)>>>(w_taps, w_aux, w_out, (__nv_bfloat16*)w1p, (__nv_bfloat16*)woutp,
+                                                       C, A, G, Ap);
+  return check_launch("usfgan_pack_block");
+}
+
+extern "C" int svsk_usfgan_block_bf16(const svsk_usfgan_block_params* pp, void* stream) {
+  SVSK_REQUIRE(pp != nullptr, SVSK_E_ARG, "usfgan_block_bf16: null params");
+  const svsk_usfgan_block_params& p = *pp;
+  SVSK_REQUIRE(p.xb_in && p.xb_out && p.aux && p.w1p && p.woutp && p.bias1 && p.bout, SVSK_E_ARG,
+               "usfgan_block_bf16: null tensor");
+  SVSK_REQUIRE(p.xb_in != p.xb_out, SVSK_E_ARG, "usfgan_block_bf16: xb_in and xb_out must differ (taps read neighbours)");
+  SVSK_REQUIRE(p.B > 0 && p.T > 0 && p.A >= 1 && p.A <= 320 && p.A % 8 == 0, SVSK_E_ARG,
+               "usfgan_block_bf16: bad shape B=%d T=%d A=%d (aux row pitch must be a multiple of 16 bytes)", p.B, p.T, p.A);
+  if (p.adaptive) SVSK_REQUIRE(p.idx_past && p.idx_future, SVSK_E_ARG, "usfgan_block_bf16: adaptive needs tap indices");
+  else SVSK_REQUIRE(p.dilation >= 1 && p.dilation < p.T, SVSK_E_ARG,
+                    "usfgan_block_bf16: reflect padding needs T > dilation (T=%d, dilation=%d)", p.T, p.dilation);
+  SVSK_REQUIRE((long long)p.B * ((p.T + 127) / 128) < (1ll << 31), SVSK_E_ARG, "usfgan_block_bf16: too many tiles");
+  int rc = require_sm100();
+  if (rc) return rc;
+
+  const int akb = (p.A + 63) / 64, KB = 3 + akb;
+  const int K1p = 3 * 64 + akb * 64;
+  const int fixed = KB * kUTile + 8192 + 2 * kUTile + 192 * 4 + (int)sizeof(UsfganBarriers) + 1024;
+  int nstages = (232448 - fixed) / kUTile;
+  if (nstages > kUMaxStages) nstages = kUMaxStages;
+  SVSK_REQUIRE(nstages >= 3, SVSK_E_ARG, "usfgan_block_bf16: not enough shared memory (aux too wide)");
+  const int smem_bytes = fixed + nstages * kUTile;
+
+  CUtensorMap tm_x, tm_aux, tm_w1, tm_wout, tm_xout;
+  {
+    uint64_t dims[3] = {64, (uint64_t)p.T, (uint64_t)p.B};
+    uint64_t str[2] = {128, (uint64_t)p.T * 128};
+    uint32_t box[3] = {64, 128, 1};
+    if ((rc = make_tmap_bf16(&tm_x, p.xb_in, 3, dims, str, box))) return rc;
+    if ((rc = make_tmap_bf16(&tm_xout, p.xb_out, 3, dims, str, box))) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)p.A, (uint64_t)p.T, (uint64_t)p.B};
+    uint64_t str[2] = {(uint64_t)p.A * 2, (uint64_t)p.T * p.A * 2};
+    uint32_t box[3] = {64, 128, 1};
+    if ((rc = make_tmap_bf16(&tm_aux, p.aux, 3, dims, str, box))) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K1p, 128};
+    uint64_t str[1] = {(uint64_t)K1p * 2};
+    uint32_t box[2] = {64, 128};
+    if ((rc = make_tmap_bf16(&tm_w1, p.w1p, 2, dims, str, box))) return rc;
+  }
+  {
+    uint64_t dims[2] = {64, 64};
+    uint64_t str[1] = {128};
+    uint32_t box[2] = {64, 64};
+    if ((rc = make_tmap_bf16(&tm_wout, p.woutp, 2, dims, str, box))) return rc;
+  }
+  int dev = 0, num_sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  static bool attr_set[64] = {false};
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(usfgan_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return fail((int)e, "usfgan_block_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  UsfganArgs a;
+  a.xb_in = (const __nv_bfloat16*)p.xb_in;
+  a.bias1 = p.bias1;
+  a.bout = p.bout;
+  a.idx_past = p.idx_past;
+  a.idx_future = p.idx_future;
+  a.B = p.B; a.T = p.T; a.A = p.A;
+  a.dilation = p.adaptive ? 0 : p.dilation;
+  a.adaptive = p.adaptive;
+  a.nstages = nstages;
+  a.akb = akb;
+  a.last_ksteps = (p.A - (akb - 1) * 64 + 15) / 16;
+  a.tiles_per_row = (p.T + 127) / 128;
+  a.total_tiles = p.B * a.tiles_per_row;
+  a.out_scale = p.out_scale;
+  const int grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
+  usfgan_block_kernel<<<grid, kUThreads, smem_bytes, as_stream(stream)>>>(tm_x, tm_aux, tm_w1, tm_wout, tm_xout, a);
+  return check_launch("usfgan_block_bf16");
+}

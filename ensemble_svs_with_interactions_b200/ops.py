@@ -232,8 +232,16 @@ def linear_bf16(a, w, bias=None, *, act=ACT_NONE, want_bf16=False, want_f32=Fals
     return out_bf16, out_f32
 
 
+def ntc_bf16_to_nct_f32(x, Cc):
+    B, T, Cp = x.shape
+    y = torch.empty((B, Cc, T), device=x.device, dtype=f32)
+    L.check(L.lib().svsk_ntc_bf16_to_nct_f32(L.ptr(x, bf16, "x"), L.ptr(y), B, Cc, T, Cp, L.stream_ptr()),
+            "ntc_bf16_to_nct_f32")
+    return y
+
+
 def usfgan_pack_block(w_taps, w_aux, w_out):
-    """w_taps [G,C,3] (past/current/future or k=3 conv), w_aux [G,A,1], w_out [C,G/2,1] -> packed bf16."""
+    """w_taps [128,64,3] (k=3 conv, or stacked convP/convC/convF), w_aux [128,A] (A % 8 == 0), w_out [64,64] -> bf16."""
     G, Cc, _ = w_taps.shape
     A = w_aux.shape[1]
     Ap = (A + 63) // 64 * 64
@@ -245,7 +253,7 @@ def usfgan_pack_block(w_taps, w_aux, w_out):
     return w1p, woutp
 
 
-def usfgan_block_bf16(xb_in, xb_out, aux, w1p, woutp, bias1, bout, *, dilation=1, idx=None):
+def usfgan_block_bf16(xb_in, xb_out, aux, w1p, woutp, bias1, bout, *, dilation=1, idx=None, out_scale=math.sqrt(0.5)):
     B, T, Cc = xb_in.shape
     p = L.UsfganBlockParams()
     p.xb_in, p.xb_out, p.aux = L.ptr(xb_in, bf16, "xb_in"), L.ptr(xb_out, bf16, "xb_out"), L.ptr(aux, bf16, "aux")
@@ -253,6 +261,6 @@ def usfgan_block_bf16(xb_in, xb_out, aux, w1p, woutp, bias1, bout, *, dilation=1
     p.bias1, p.bout = L.ptr(bias1, f32), L.ptr(bout, f32)
     if idx is not None:
         p.idx_past, p.idx_future = L.ptr(idx[0], torch.int32), L.ptr(idx[1], torch.int32)
-    p.B, p.T, p.C, p.A = B, T, Cc, aux.shape[2]
-    p.dilation, p.adaptive = int(dilation), int(idx is not None)
+    p.B, p.T, p.A = B, T, aux.shape[2]
+    p.dilation, p.adaptive, p.out_scale = int(dilation), int(idx is not None), float(out_scale)
     L.check(L.lib().svsk_usfgan_block_bf16(C.byref(p), L.stream_ptr()), "usfgan_block_bf16")

@@ -157,6 +157,62 @@ class ResidualBlocks(nn.Module):
         else:
             raise ValueError(f"Cascaded mode {cascade_mode} is not supported!")
 
+    # ------------------------------------------------------------------ bf16 tensor-core path (NTC layout)
+    def supports_bf16(self):
+        blocks = list(self.conv_dilated)
+        if not blocks:
+            return True
+        b0 = blocks[0]
+        res = b0.conv1x1_out.out_channels
+        gate = b0.conv1x1_out.in_channels * 2
+        aux = b0.conv1x1_aux.in_channels if b0.conv1x1_aux is not None else 0
+        fixed_ok = all(isinstance(b, AdaptiveBlock) or b.kernel_size == 3 for b in blocks)
+        return res == 64 and gate == 128 and 0 < aux <= 320 and fixed_ok
+
+    def _bf16_plan(self, aux_pad):
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters()) + (aux_pad,)
+        if getattr(self, "_plan_key", None) == key:
+            return self._plan
+        plan = []
+        with torch.no_grad():
+            for block, adaptive in zip(self.conv_dilated, self.block_modes):
+                if adaptive:
+                    w_taps, b1 = block.stacked_taps()
+                else:
+                    w_taps, b1 = effective_weight(block.conv).contiguous(), block.conv.bias
+                w_aux = effective_weight(block.conv1x1_aux)[:, :, 0]
+                if aux_pad > w_aux.shape[1]:
+                    w_aux = torch.nn.functional.pad(w_aux, (0, aux_pad - w_aux.shape[1]))
+                w_out = effective_weight(block.conv1x1_out)[:, :, 0]
+                w1p, woutp = ops.usfgan_pack_block(w_taps.to(f32), w_aux.to(f32).contiguous(), w_out.to(f32).contiguous())
+                zeros = torch.zeros(w_taps.shape[0], device=w_taps.device, dtype=f32)
+                plan.append(dict(w1p=w1p, woutp=woutp,
+                                 bias1=(b1.detach().to(f32).contiguous() if b1 is not None else zeros),
+                                 bout=block.conv1x1_out.bias.detach().to(f32).contiguous(),
+                                 dilation=getattr(block, "dilation", 1), adaptive=adaptive))
+        self._plan, self._plan_key = plan, key
+        return plan
+
+    def forward_ntc_bf16(self, xb, auxb, d, idx_cache=None):
+        """xb [B,T,64] bf16, auxb [B,T,A8] bf16 (A rounded up to a multiple of 8), d (B,1,T) fp32 -> [B,T,64] bf16.
+        One svsk_usfgan_block_bf16 launch per block; activations ping-pong between two buffers."""
+        plan = self._bf16_plan(auxb.shape[2])
+        idx_cache = {} if idx_cache is None else idx_cache
+        cur, nxt = xb, torch.empty_like(xb)
+        a_idx = 0
+        for pw in plan:
+            idx = None
+            if pw["adaptive"]:
+                dil = 2 ** (a_idx % self.blockA_per_cycle)
+                if dil not in idx_cache:
+                    idx_cache[dil] = ops.pd_index(d.to(f32).contiguous(), dil)
+                idx = idx_cache[dil]
+                a_idx += 1
+            ops.usfgan_block_bf16(cur, nxt, auxb, pw["w1p"], pw["woutp"], pw["bias1"], pw["bout"],
+                                  dilation=pw["dilation"], idx=idx)
+            cur, nxt = nxt, cur
+        return cur
+
     def forward(self, x, c, d, batch_index=None, ch_index=None, idx_cache=None):
         """x (B,C,T), c (B,aux,T), d (B,1,T) -> (B,C,T)   (residual_block.py:311-336).
         ``idx_cache``: dict dilation -> (idx_past, idx_future), shared across stacks of one generator call."""

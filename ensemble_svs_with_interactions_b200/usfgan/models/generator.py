@@ -23,6 +23,36 @@ def _conv1x1(m, x, in_relu=False):
 
 
 class _GeneratorBase(nn.Module):
+    precision = "auto"   # "auto" | "bf16" | "fp32": bf16 = fused tcgen05 block kernel for the residual stacks
+
+    def _stacks(self):
+        return [m for m in self.children() if isinstance(m, ResidualBlocks)]
+
+    def resolved_precision(self):
+        ok = all(st.supports_bf16() for st in self._stacks())
+        if self.precision == "auto":
+            return "bf16" if ok else "fp32"
+        if self.precision == "bf16" and not ok:
+            raise RuntimeError("uSFGAN precision='bf16' needs residual 64 / gate 128 channels, kernel size 3, aux <= 320")
+        if self.precision not in ("bf16", "fp32"):
+            raise RuntimeError(f"unknown precision {self.precision!r}")
+        return self.precision
+
+    def _run_stack(self, stack, x, c, d, cache, auxb):
+        """x NCT fp32 in / out; the stack itself runs NTC bf16 when auxb is given."""
+        if auxb is None or len(stack.conv_dilated) == 0:
+            return stack(x, c, d, idx_cache=cache)
+        xb, _ = ops.nct_to_ntc(x.contiguous())
+        yb = stack.forward_ntc_bf16(xb, auxb, d, cache)
+        return ops.ntc_bf16_to_nct_f32(yb, x.shape[1])
+
+    def _aux_ntc(self, c):
+        if self.resolved_precision() != "bf16":
+            return None
+        A = c.shape[1]
+        auxb, _ = ops.nct_to_ntc(c, Cp=(A + 7) // 8 * 8)
+        return auxb
+
     def _build_common(self, in_channels, out_channels, residual_channels, skip_channels, aux_channels,
                       aux_context_window, upsample_params):
         self.in_channels = in_channels
@@ -99,11 +129,12 @@ class USFGANGenerator(_GeneratorBase):
         cache = {}
         c = self.upsample_net(c)
         assert c.size(-1) == x.size(-1)
+        auxb = self._aux_ntc(c)
         x = _conv1x1(self.conv_first, x.to(f32).contiguous())
-        x = self.source_network(x, c, d, idx_cache=cache)
+        x = self._run_stack(self.source_network, x, c, d, cache, auxb)
         s = self._conv_last(x)
         x = _conv1x1(self.conv_mid, s)
-        x = self.filter_network(x, c, d, idx_cache=cache)
+        x = self._run_stack(self.filter_network, x, c, d, cache, auxb)
         return self._conv_last(x), s
 
 
@@ -178,14 +209,15 @@ class CascadeHnUSFGANGenerator(_HnBase):
         self._check(x)
         cache = {}
         c, a, h, n = self._front(x, c)
-        h = self.harmonic_network(h, c, d, idx_cache=cache)
+        auxb = self._aux_ntc(c)
+        h = self._run_stack(self.harmonic_network, h, c, d, cache, auxb)
         zeros = torch.zeros_like(h)
         _, h, _ = ops.periodic_mix_f32(a, h, zeros, want_parts=True)     # h <- a * h
         n = _conv1x1(self.conv_merge, torch.cat([h, n], dim=1))
-        n = self.noise_network(n, c, d, idx_cache=cache)
+        n = self._run_stack(self.noise_network, n, c, d, cache, auxb)
         _, _, n = ops.periodic_mix_f32(a, zeros, n, want_parts=True)     # n <- (1 - a) * n
         s = ops.lincomb_f32([h, n], [1.0, 1.0])
-        y = self.filter_network(s, c, d, idx_cache=cache)
+        y = self._run_stack(self.filter_network, s, c, d, cache, auxb)
         return self._outputs(y, s, h, n, a, wave_only)
 
 
@@ -210,8 +242,9 @@ class ParallelHnUSFGANGenerator(_HnBase):
         self._check(x)
         cache = {}
         c, a, h, n = self._front(x, c)
-        h = self.harmonic_network(h, c, d, idx_cache=cache)
-        n = self.noise_network(n, c, d, idx_cache=cache)
+        auxb = self._aux_ntc(c)
+        h = self._run_stack(self.harmonic_network, h, c, d, cache, auxb)
+        n = self._run_stack(self.noise_network, n, c, d, cache, auxb)
         s, h, n = ops.periodic_mix_f32(a, h, n, want_parts=True)
-        y = self.filter_network(s, c, d, idx_cache=cache)
+        y = self._run_stack(self.filter_network, s, c, d, cache, auxb)
         return self._outputs(y, s, h, n, a, wave_only)

@@ -195,6 +195,36 @@ SVSK_API int svsk_diffnet_pack_block(const float* dilated_w, const float* cond_w
                             int C, int H, void* stream);
 SVSK_API int svsk_diffnet_packed_row(int reference_row, int C);
 
+/* Fused uSFGAN / QPPWG residual block — replaces FixedBlock.forward / AdaptiveBlock.forward (+ pd_indexing),
+ * nnsvs/usfgan/layers/residual_block.py:123-157,198-234 and nnsvs/usfgan/utils/index.py:12-54, one launch per block:
+ *   D1 = W1p . [x(tap0) ; x(t) ; x(tap2) ; aux(t)] ; z = tanh(D1[:64]+b) * sigmoid(D1[64:]+b) ; D2 = Woutp . z
+ *   xb_out(t) = (D2 + bout + xb_in(t)) * out_scale
+ * taps: adaptive == 0: t -/+ dilation with reflect padding (needs T > dilation);
+ *       adaptive != 0: idx_past[b,t] / idx_future[b,t] from svsk_pd_index (-1 = zero tap).
+ * Shapes: residual 64 / gate 128 channels (the recipes' widths), aux A <= 320 with A % 8 == 0, NTC bf16 activations.
+ * Persistent kernel: weights stay resident in shared memory, activations stream through a TMA / cp.async ring. */
+typedef struct svsk_usfgan_block_params {
+  const void* xb_in;   /* [B][T][64] bf16 */
+  void* xb_out;        /* [B][T][64] bf16, != xb_in */
+  const void* aux;     /* [B][T][A] bf16 */
+  const void* w1p;     /* [128][192 + ceil64(A)] bf16 packed by svsk_usfgan_pack_block */
+  const void* woutp;   /* [64][64] bf16 */
+  const float* bias1;  /* [128] conv bias (adaptive: convP + convC + convF biases) */
+  const float* bout;   /* [64] */
+  const int32_t* idx_past;   /* [B][T] or NULL */
+  const int32_t* idx_future; /* [B][T] or NULL */
+  int32_t B, T, A;
+  int32_t dilation, adaptive;
+  float out_scale;     /* sqrt(0.5) in the reference */
+} svsk_usfgan_block_params;
+SVSK_API int svsk_usfgan_block_bf16(const svsk_usfgan_block_params* p, void* stream);
+/* w_taps [128][64][3] (k=3 conv, or stacked convP/convC/convF), w_aux [128][A], w_out [64][64] (fp32) -> packed bf16 */
+SVSK_API int svsk_usfgan_pack_block(const float* w_taps, const float* w_aux, const float* w_out, void* w1p, void* woutp,
+                                    int C, int A, int G, void* stream);
+
+/* [B][T][Cp] bf16 -> [B][C][T] fp32 (first C channels). */
+SVSK_API int svsk_ntc_bf16_to_nct_f32(const void* x_bf16, float* y, int B, int C, int T, int Cp, void* stream);
+
 /* Time-major bf16 GEMM with fused epilogue — replaces the 1x1 projections around the stacks
  * (denoiser.py:110-112,121-123 ; generator.py:461-466,492-493):
  *   Y[n][co] = act( sum_k A[n][k] W[co][k] + bias[co] )      n = B*T rows, K % 16 == 0, Cout % 16 == 0, Cout <= 256

@@ -460,3 +460,71 @@ def test_diffnet_training_forward_backward():
     grads = [p.grad for p in m.parameters()]
     assert all(gr is not None and torch.isfinite(gr).all() for gr in grads)
     assert sum(float(gr.abs().sum()) for gr in grads) > 0
+
+
+# ------------------------------------------------------------------------------------------------ uSFGAN tensor-core path
+def _usfgan_block_ref(w_taps, b1, w_aux, w_out, b_out, x, c, taps):
+    """Oracle maths on bf16-rounded operands.  taps: (xP, xF) already gathered (fp32 NCT)."""
+    xP, xF = taps
+    y = (O.conv1x1(_bf(xP), _bf(w_taps[:, :, 0:1]), None) + O.conv1x1(_bf(x), _bf(w_taps[:, :, 1:2]), None)
+         + O.conv1x1(_bf(xF), _bf(w_taps[:, :, 2:3]), None) + O.conv1x1(_bf(c), _bf(w_aux), None) + b1[None, :, None])
+    z = _bf(torch.tanh(y[:, :64]) * torch.sigmoid(y[:, 64:]))
+    return (O.conv1x1(z, _bf(w_out), b_out) + _bf(x)) * math.sqrt(0.5)
+
+
+@pytest.mark.parametrize("T,dil,adaptive,A", [(1000, 1, False, 80), (1000, 64, False, 80), (777, 512, False, 80),
+                                               (130, 2, False, 72), (1000, 4, True, 80), (333, 16, True, 80),
+                                               (20000, 8, False, 80), (20000, 2, True, 80)])
+def test_usfgan_block_bf16(T, dil, adaptive, A):
+    ops = _ops()
+    g = torch.Generator().manual_seed(T + dil)
+    B = 2
+    x = torch.randn(B, 64, T, generator=g); c = torch.randn(B, A, T, generator=g)
+    w_taps = torch.randn(128, 64, 3, generator=g) / math.sqrt(192); b1 = torch.randn(128, generator=g) * 0.1
+    w_aux = torch.randn(128, A, 1, generator=g) / math.sqrt(A)
+    w_out = torch.randn(64, 64, 1, generator=g) / 8; b_out = torch.randn(64, generator=g) * 0.1
+    if adaptive:
+        d = torch.empty(B, 1, T).uniform_(0.7, 9.0, generator=g)
+        taps = O.pd_gather(_bf(x), d, dil)
+    else:
+        taps = (O.shifted_tap(_bf(x), -dil, "reflect"), O.shifted_tap(_bf(x), dil, "reflect"))
+    ref = _usfgan_block_ref(w_taps, b1, w_aux, w_out, b_out, x, c, taps)
+
+    xb, _ = ops.nct_to_ntc(x.to(DEV)); auxb, _ = ops.nct_to_ntc(c.to(DEV))
+    w1p, woutp = ops.usfgan_pack_block(w_taps.to(DEV), w_aux[:, :, 0].contiguous().to(DEV), w_out[:, :, 0].contiguous().to(DEV))
+    out = torch.full_like(xb, float("nan"))
+    idx = ops.pd_index(d.to(DEV), dil) if adaptive else None
+    ops.usfgan_block_bf16(xb, out, auxb, w1p, woutp, b1.to(DEV), b_out.to(DEV), dilation=dil, idx=idx)
+    torch.cuda.synchronize()
+    close_bf16(out.float().transpose(1, 2), ref, 4e-3, 1.5e-2)
+
+
+def test_parallel_hn_fullwidth_bf16_vs_oracle():
+    """Recipe-width generator (64/128/64, aux 80) with short stacks: bf16 tensor-core stacks vs the fp32 CPU oracle."""
+    from ensemble_svs_with_interactions_b200.usfgan.models import ParallelHnUSFGANGenerator
+    torch.manual_seed(5)
+    hp = {"blockA": 4, "cycleA": 2, "blockF": 0, "cycleF": 0, "cascade_mode": 0}
+    np_ = {"blockA": 0, "cycleA": 0, "blockF": 2, "cycleF": 2, "cascade_mode": 0}
+    fp = {"blockA": 0, "cycleA": 0, "blockF": 6, "cycleF": 2, "cascade_mode": 0}
+    pe = {"conv_layers": 3, "kernel_size": 5, "dilation": 1, "padding_mode": "replicate"}
+    m = ParallelHnUSFGANGenerator(harmonic_network_params=hp, noise_network_params=np_, filter_network_params=fp,
+                                  periodicity_estimator_params=pe, upsample_params={"upsample_scales": [4, 3]}).eval()
+    g = torch.Generator().manual_seed(6)
+    with torch.no_grad():
+        last = m.periodicity_estimator.layers[-2]
+        last.weight_v.copy_(torch.randn(last.weight_v.shape, generator=g) * 0.1)
+    m.remove_weight_norm()
+    B, Fr, hop = 2, 50, 12
+    T = Fr * hop
+    c = torch.randn(B, 80, Fr + 4, generator=g)
+    d = torch.empty(B, 1, Fr).uniform_(1.0, 12.0, generator=g).repeat_interleave(hop, dim=-1)
+    x = torch.randn(B, 2, T, generator=g) * 0.3
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    ref = O.parallel_hn_usfgan_forward(sd, x, c, d, harmonic=hp, noise=np_, filt=fp, upsample_scales=[4, 3], pe=pe)
+    m = m.to(DEV)
+    assert m.resolved_precision() == "bf16"
+    outs = m(x.to(DEV), c.to(DEV), d.to(DEV))
+    r, mx = close_bf16(outs[0], ref[0], 3e-2, 8e-2)
+    print(f"parallel-hn bf16 stacks vs fp32 oracle: rel_l2={r:.3e} max={mx:.3e}")
+    m.precision = "fp32"
+    close32(m(x.to(DEV), c.to(DEV), d.to(DEV))[0], ref[0], 5e-4)
