@@ -118,6 +118,56 @@ def cpu_baseline(sample_steps=2, threads=None):
     return B * T * sample_steps / dt, threads, f"{sample_steps} of {K_STEP} DDPM steps of the full {B}x{T} batch", dt
 
 
+def vocoder_bench(dev, peaks, tracks=6, seconds=30.0, reps=3):
+    """Second half of the headline metric (BASELINE configs[2]): ParallelHn-uSFGAN, recipe config, 6 tracks x 30 s at
+    24 kHz, residual stacks on the fused tcgen05 block kernel.  Returns a dict for the JSON line."""
+    from ensemble_svs_with_interactions_b200 import ops
+    from ensemble_svs_with_interactions_b200.usfgan.models import ParallelHnUSFGANGenerator
+    fs, hop = 24000, 120
+    frames = int(seconds * fs / hop)
+    Tn = frames * hop
+    pe = {"conv_layers": 3, "kernel_size": 5, "dilation": 1, "padding_mode": "replicate"}
+    torch.manual_seed(1234)
+    m = ParallelHnUSFGANGenerator(periodicity_estimator_params=pe).eval()
+    with torch.no_grad():
+        m.periodicity_estimator.layers[-2].weight_v.normal_(0, 0.05)
+    m.remove_weight_norm()
+    m = m.to(dev)
+    g = torch.Generator().manual_seed(1)
+    c = torch.randn(tracks, 80, frames + 4, generator=g).to(dev)
+    f0 = torch.empty(tracks, 1, frames).uniform_(110, 880, generator=g)
+    d = (fs / (f0 * 4)).repeat_interleave(hop, dim=-1).to(dev)
+    x = (torch.randn(tracks, 2, Tn, generator=g) * 0.1).to(dev)
+    for _ in range(2):
+        m(x, c, d, wave_only=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        m(x, c, d, wave_only=True)
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    # dominant kernel of the vocoder: the fused block (30 filter blocks timed in isolation)
+    auxb, _ = ops.nct_to_ntc(m.upsample_net(c), Cp=80)
+    hb = torch.randn(tracks, Tn, 64, device=dev).to(torch.bfloat16)
+    m.filter_network.forward_ntc_bf16(hb, auxb, d, {})
+    torch.cuda.synchronize()
+    e0.record()
+    m.filter_network.forward_ntc_bf16(hb, auxb, d, {})
+    e1.record()
+    e1.synchronize()
+    blk_ms = e0.elapsed_time(e1) / 30
+    hbm = (peaks or {}).get("hbm_gbs", 6650.0)
+    gbs = tracks * Tn * 416 / (blk_ms * 1e-3) / 1e9          # SURVEY §8(d): 416 B per sample-block (bf16 x in/out + aux)
+    return {"metric": "vocoded audio-sec/sec (ParallelHn-uSFGAN, 24 kHz)", "value": tracks * seconds / (ms / 1e3),
+            "unit": "audio-sec/s", "ms_per_pass": ms, "precision": m.resolved_precision(),
+            "config": {"workload": f"{tracks} tracks x {seconds:.0f} s @ 24 kHz, hop 120, aux 80, 20A+5F+30F blocks"},
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                         "traffic": None, "kernel": "usfgan_block_kernel", "us_per_launch": blk_ms * 1e3,
+                         "tflops": 2.0 * tracks * Tn * 38912 / (blk_ms * 1e-3) / 1e12}}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -146,6 +196,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vocoder", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -245,6 +296,8 @@ def main():
     peak_tf = (peaks or {}).get("bf16_tflops_sustained", 1400.0)
     achieved_tf = flops_per_launch / (block_ms * 1e-3) / 1e12
 
+    voc = vocoder_bench(dev, peaks) if not args.no_vocoder else None
+
     if rank == 0:
         total_units = world * B * T * K_STEP * args.steps
         value = total_units / sec
@@ -264,11 +317,14 @@ def main():
             "gpu_launches": gpu_launches,
             "clocks": clk.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": None, "kernel": "diffnet_block_kernel",
+                         "frac": achieved_tf / peak_tf, "traffic": None, "kernel": "diffnet_block2_kernel (CTA pair, tcgen05 cta_group::2)",
                          "us_per_launch": block_ms * 1e3, "flops_per_launch": flops_per_launch,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400"},
             "whole_pass_tflops": 2.0 * MAC_PER_FRAME_STEP * B * T * K_STEP * args.steps * world / sec / 1e12,
         }
+        if voc is not None:
+            voc["value"] *= world   # one 6-track vocoder batch per rank, no collective
+            line["vocoder"] = voc
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample, dt = cpu_baseline(sample_steps=2)
             line["cpu_baseline"] = {"value": v, "unit": "frame-steps/s", "cores": cores, "kind": "port",

@@ -53,7 +53,16 @@ class UsfganBlockParams(C.Structure):
         ("w1p", C.c_void_p), ("woutp", C.c_void_p), ("bias1", C.c_void_p), ("bout", C.c_void_p),
         ("idx_past", C.c_void_p), ("idx_future", C.c_void_p),
         ("B", C.c_int32), ("T", C.c_int32), ("A", C.c_int32),
-        ("dilation", C.c_int32), ("adaptive", C.c_int32), ("out_scale", C.c_float),
+        ("dilation", C.c_int32), ("adaptive", C.c_int32), ("out_scale", C.c_float), ("out_relu", C.c_int32),
+    ]
+
+
+class Conv1dBf16Params(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("wp", C.c_void_p), ("bias", C.c_void_p), ("y", C.c_void_p),
+        ("B", C.c_int32), ("T", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
+        ("ksize", C.c_int32), ("dilation", C.c_int32), ("tap_origin", C.c_int32), ("pad_mode", C.c_int32),
+        ("act", C.c_int32),
     ]
 
 
@@ -63,6 +72,7 @@ _SIGNATURES = {
     "svsk_version": [],
     "svsk_device_check": [_I],
     "svsk_conv1d_f32": [C.POINTER(Conv1dF32Params), _V],
+    "svsk_linear_f32": [_V, _V, _V, _V, _I, _I, _I, _I, _V],
     "svsk_gated_act_f32": [_V, _V, _I, _I, _I, _I, _V],
     "svsk_diffnet_residual_skip_f32": [_V, _V, _V, _I, _I, _I, _I, _V],
     "svsk_scale_act_f32": [_V, _V, _Z, _F, _I, _V],
@@ -85,6 +95,10 @@ _SIGNATURES = {
     "svsk_usfgan_block_bf16": [C.POINTER(UsfganBlockParams), _V],
     "svsk_usfgan_pack_block": [_V, _V, _V, _V, _V, _I, _I, _I, _V],
     "svsk_ntc_bf16_to_nct_f32": [_V, _V, _I, _I, _I, _I, _V],
+    "svsk_conv1d_bf16": [C.POINTER(Conv1dBf16Params), _V],
+    "svsk_conv1d_pack_bf16": [_V, _V, _I, _I, _I, _V],
+    "svsk_periodic_mix_bf16": [_V, _V, _V, _V, _Z, _V],
+    "svsk_dot_rows_bf16": [_V, _V, _F, _V, _Z, _I, _V],
 }
 EXPORTED_SYMBOLS = ["svsk_last_error"] + list(_SIGNATURES)
 

@@ -284,6 +284,26 @@ __global__ void periodic_mix_kernel(const float* __restrict__ a, const float* __
   s[i] = hv + nv;
 }
 
+// y[b][co] = act(bias[co] + sum_ci w[co][ci] x[b][ci]): one warp per output channel keeps its weight row in
+// registers and walks over the (small) batch.  Used for the step-embedding MLP and the per-layer tap-bias tables.
+__global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ y, int Bt,
+                                                         int Cin, int Cout, int act) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co = blockIdx.x * 8 + warp;
+  if (co >= Cout) return;
+  const float* wr = w + (size_t)co * Cin;
+  const float bv = bias ? bias[co] : 0.f;
+  for (int b0 = blockIdx.y; b0 < Bt; b0 += gridDim.y) {
+    const float* xr = x + (size_t)b0 * Cin;
+    float acc = 0.f;
+    for (int ci = lane; ci < Cin; ci += 32) acc = fmaf(wr[ci], xr[ci], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[(size_t)b0 * Cout + co] = apply_act(acc + bv, act);
+  }
+}
+
 inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 }  // namespace svsk
@@ -312,6 +332,14 @@ extern "C" int svsk_conv1d_f32(const svsk_conv1d_f32_params* pp, void* stream) {
   dim3 grid(ceil_div(p.T, kTT), ceil_div(p.Cout, kCOT), p.B);
   conv1d_f32_kernel<<<grid, 256, 0, as_stream(stream)>>>(p, T_in);
   return check_launch("conv1d_f32");
+}
+
+extern "C" int svsk_linear_f32(const float* x, const float* w, const float* bias, float* y, int Bt, int Cin, int Cout,
+                               int act, void* stream) {
+  SVSK_REQUIRE(x && w && y && Bt > 0 && Cin > 0 && Cout > 0, SVSK_E_ARG, "linear_f32: bad args");
+  dim3 grid(ceil_div(Cout, 8), Bt < 64 ? Bt : 64);
+  linear_f32_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, w, bias, y, Bt, Cin, Cout, act);
+  return check_launch("linear_f32");
 }
 
 extern "C" int svsk_gated_act_f32(const float* y, float* z, int B, int H, int T, int order, void* stream) {

@@ -14,7 +14,8 @@
 //   warp 1      MMA issuer (tcgen05.mma cta_group::1, M=128, N=128 then N=64) + TMEM owner
 //   warps 2-5   gather producers (thread = row): side taps of adaptive blocks / boundary tiles via cp.async 16-byte
 //               copies into the swizzled tile, completion signalled with cp.async.mbarrier.arrive.noinc
-//   warps 6-9   epilogue (thread = sample): gate -> G (bf16, swizzled smem) ; residual -> same buffer -> TMA store
+//   warps 6-13  epilogue (thread = sample, two warps per TMEM lane quarter alternating 16-column chunks):
+//               gate -> G (bf16, swizzled smem) ; residual -> same buffer -> TMA store
 // TMEM holds two D1 (2x128 columns) and two D2 (2x64) accumulators, so the MMAs of tile n+1 overlap the epilogue of
 // tile n.  The residual x(t) is prefetched by its epilogue thread (one 128-byte row per thread) at the top of the tile.
 #include <cuda_bf16.h>
@@ -28,7 +29,7 @@ namespace svsk {
 
 constexpr int kUTile = 128 * 128;  // 128 rows x 64 bf16
 constexpr int kUMaxStages = 6;
-constexpr int kUThreads = 320;
+constexpr int kUThreads = 448;  // 2 + 4 gather + 8 epilogue warps
 constexpr int kUMaxKB = 8;         // 3 taps + up to 5 aux k-blocks (aux <= 320 channels)
 
 struct UsfganArgs {
@@ -39,6 +40,7 @@ struct UsfganArgs {
   const int32_t* idx_future;
   int B, T, A, dilation, adaptive, nstages, akb, last_ksteps, tiles_per_row, total_tiles;
   float out_scale;
+  int out_relu;
 };
 
 struct __align__(8) UsfganBarriers {
@@ -93,7 +95,7 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars->d1_full[i], 1);
-      ptx::mbar_init(&bars->g_full[i], 128);
+      ptx::mbar_init(&bars->g_full[i], 256);
       ptx::mbar_init(&bars->d2_full[i], 1);
     }
     ptx::mbar_init(&bars->w_full, 1);
@@ -200,8 +202,10 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
       const bool gather = tile_needs_gather(t0, T, a.dilation, a.adaptive);
       const int t = t0 + r;
       for (int kb = 0; kb < KB; ++kb) {
+        // Wait on EVERY slot, also the ones the TMA producer fills: parity waits only tell two consecutive phases apart,
+        // so this warp group must never run more than one ring wrap ahead of the MMA issuer.
+        ptx::mbar_wait(&bars->empty[s], ph ^ 1);
         if (gather && (kb == 0 || kb == 2)) {
-          ptx::mbar_wait(&bars->empty[s], ph ^ 1);
           int src = -1;
           if (t < T) {
             if (a.adaptive) {
@@ -225,8 +229,9 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
   } else {
-    // ------------------------------------------------------------------ epilogue (thread = one sample)
+    // ------------------------------------------------------------------ epilogue (thread = one sample, half the columns)
     const int q = warp & 3;
+    const int sub = (warp - 6) >> 2;  // 0: 16-column chunks 0 and 2, 1: chunks 1 and 3
     const int row = q * 32 + lane;
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
     const bool elected = (warp == 6 && lane == 0);
@@ -235,25 +240,29 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
       const int b = tile / a.tiles_per_row, t0 = (tile - b * a.tiles_per_row) * 128;
       const int t = t0 + row, p = n & 1;
       const uint32_t par = (n >> 1) & 1;
-      // residual row, prefetched: 64 bf16 = 8 x 16 bytes
-      uint4 xr[8];
-      if (t < T) {
-        const uint4* src = reinterpret_cast<const uint4*>(a.xb_in + ((size_t)b * T + t) * 64);
+      // residual row, prefetched: this thread's two 16-channel chunks = 2 x 2 x 16 bytes
+      uint4 xr[2][2];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) xr[c] = __ldg(src + c);
-      } else {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) xr[c] = make_uint4(0, 0, 0, 0);
+      for (int i = 0; i < 2; ++i) {
+        const int c0 = 16 * (2 * i + sub);
+        if (t < T) {
+          const uint4* src = reinterpret_cast<const uint4*>(a.xb_in + ((size_t)b * T + t) * 64 + c0);
+          xr[i][0] = __ldg(src);
+          xr[i][1] = __ldg(src + 1);
+        } else {
+          xr[i][0] = xr[i][1] = make_uint4(0, 0, 0, 0);
+        }
       }
       uint8_t* gb = gbuf + p * kUTile;
       if (n >= 2) {  // the TMA store of tile n-2 must have finished READING this buffer
         if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        ptx::named_bar_sync(2, 128);
+        ptx::named_bar_sync(2, 256);
       }
       ptx::mbar_wait(&bars->d1_full[p], par);
       ptx::tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 16) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c0 = 16 * (2 * i + sub);
         uint32_t ra[16], rb[16];
         ptx::tmem_ld16(tmem + tlane + p * 128 + c0, ra);
         ptx::tmem_ld16(tmem + tlane + p * 128 + 64 + c0, rb);
@@ -277,17 +286,18 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
       ptx::mbar_wait(&bars->d2_full[p], par);
       ptx::tc_fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 16) {  // fully unrolled: xr[] must stay in registers
+      for (int i = 0; i < 2; ++i) {
+        const int c0 = 16 * (2 * i + sub);
         uint32_t rd[16];
         ptx::tmem_ld16(tmem + tlane + 256 + p * 64 + c0, rd);
         ptx::tmem_ld_wait();
+        const uint32_t xw[8] = {xr[i][0].x, xr[i][0].y, xr[i][0].z, xr[i][0].w, xr[i][1].x, xr[i][1].y, xr[i][1].z, xr[i][1].w};
         uint32_t o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const uint4 xv = xr[(c0 >> 3) + (e >> 2)];
-          const uint32_t xw = (e & 3) == 0 ? xv.x : ((e & 3) == 1 ? xv.y : ((e & 3) == 2 ? xv.z : xv.w));
-          const float lo = (__uint_as_float(rd[2 * e]) + bias_s[128 + c0 + 2 * e] + ptx::bf16_lo(xw)) * a.out_scale;
-          const float hi = (__uint_as_float(rd[2 * e + 1]) + bias_s[128 + c0 + 2 * e + 1] + ptx::bf16_hi(xw)) * a.out_scale;
+          float lo = (__uint_as_float(rd[2 * e]) + bias_s[128 + c0 + 2 * e] + ptx::bf16_lo(xw[e])) * a.out_scale;
+          float hi = (__uint_as_float(rd[2 * e + 1]) + bias_s[128 + c0 + 2 * e + 1] + ptx::bf16_hi(xw[e])) * a.out_scale;
+          if (a.out_relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
           o[e] = ptx::pack_bf16(lo, hi);
         }
         ptx::st_shared_v4(gb + ptx::sw128_offset((uint32_t)row, (uint32_t)(c0 >> 3)), o[0], o[1], o[2], o[3]);
@@ -295,7 +305,7 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
       }
       ptx::tc_fence_before();
       ptx::fence_proxy_async_smem();
-      ptx::named_bar_sync(2, 128);
+      ptx::named_bar_sync(2, 256);
       if (elected) {
         ptx::tma_store_3d(&tm_xout, gb, 0, t0, b);
         ptx::bulk_commit_group();
@@ -414,6 +424,7 @@ extern "C" int svsk_usfgan_block_bf16(const svsk_usfgan_block_params* pp, void* 
   a.tiles_per_row = (p.T + 127) / 128;
   a.total_tiles = p.B * a.tiles_per_row;
   a.out_scale = p.out_scale;
+  a.out_relu = p.out_relu;
   const int grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
   usfgan_block_kernel<<<grid, kUThreads, smem_bytes, as_stream(stream)>>>(tm_x, tm_aux, tm_w1, tm_wout, tm_xout, a);
   return check_launch("usfgan_block_bf16");

@@ -49,9 +49,13 @@ def conv1d_f32(x, w, bias=None, *, dilation=1, tap_origin=None, pad_mode=PAD_ZER
 
 
 def linear_f32(x, w, bias=None, act=ACT_NONE):
-    """nn.Linear on [B,Cin] through the conv kernel (T = 1)."""
-    y = conv1d_f32(x.unsqueeze(-1), w.unsqueeze(-1) if w.dim() == 2 else w, bias, act=act)
-    return y.squeeze(-1)
+    """nn.Linear on [Bt,Cin] (svsk_linear_f32); w [Cout,Cin] or [Cout,Cin,1]."""
+    Bt, Cin = x.shape
+    Cout = w.shape[0]
+    y = torch.empty((Bt, Cout), device=x.device, dtype=f32)
+    L.check(L.lib().svsk_linear_f32(L.ptr(x, f32, "x"), L.ptr(w, f32, "w"), L.ptr(bias, f32, "bias"), L.ptr(y), Bt, Cin,
+                                    Cout, act, L.stream_ptr()), "linear_f32")
+    return y
 
 
 def gated_act_f32(y, order):
@@ -253,7 +257,47 @@ def usfgan_pack_block(w_taps, w_aux, w_out):
     return w1p, woutp
 
 
-def usfgan_block_bf16(xb_in, xb_out, aux, w1p, woutp, bias1, bout, *, dilation=1, idx=None, out_scale=math.sqrt(0.5)):
+def conv1d_pack_bf16(w):
+    """w [Cout,Cin,k] fp32 -> [Cout, k*ceil64(Cin)] bf16 (tap-major K)."""
+    Cout, Cin, k = w.shape
+    wp = torch.empty((Cout, k * ((Cin + 63) // 64 * 64)), device=w.device, dtype=bf16)
+    L.check(L.lib().svsk_conv1d_pack_bf16(L.ptr(w.contiguous(), f32), L.ptr(wp), Cout, Cin, k, L.stream_ptr()),
+            "conv1d_pack_bf16")
+    return wp
+
+
+def conv1d_bf16(x, wp, bias, Cout, ksize, *, dilation=1, tap_origin=None, pad_mode=PAD_ZEROS, act=ACT_NONE, out=None):
+    """x [B,T,Cin] bf16 NTC -> [B,T,Cout] bf16 on the tcgen05 conv kernel."""
+    B, T, Cin = x.shape
+    if tap_origin is None:
+        tap_origin = (ksize - 1) // 2
+    out = torch.empty((B, T, Cout), device=x.device, dtype=bf16) if out is None else out
+    p = L.Conv1dBf16Params()
+    p.x, p.wp, p.bias, p.y = L.ptr(x, bf16, "x"), L.ptr(wp, bf16, "wp"), L.ptr(bias, f32, "bias"), L.ptr(out, bf16, "out")
+    p.B, p.T, p.Cin, p.Cout = B, T, Cin, Cout
+    p.ksize, p.dilation, p.tap_origin, p.pad_mode, p.act = ksize, dilation, tap_origin, pad_mode, act
+    L.check(L.lib().svsk_conv1d_bf16(C.byref(p), L.stream_ptr()), "conv1d_bf16")
+    return out
+
+
+def periodic_mix_bf16(a, h, n):
+    s = torch.empty_like(h)
+    L.check(L.lib().svsk_periodic_mix_bf16(L.ptr(a, bf16), L.ptr(h, bf16), L.ptr(n, bf16), L.ptr(s), h.numel(),
+                                           L.stream_ptr()), "periodic_mix_bf16")
+    return s
+
+
+def dot_rows_bf16(x, w, bias):
+    """x [..., C] bf16, w [C] fp32 -> [...] fp32."""
+    Cc = x.shape[-1]
+    y = torch.empty(x.shape[:-1], device=x.device, dtype=f32)
+    L.check(L.lib().svsk_dot_rows_bf16(L.ptr(x, bf16), L.ptr(w, f32), float(bias), L.ptr(y), y.numel(), Cc,
+                                       L.stream_ptr()), "dot_rows_bf16")
+    return y
+
+
+def usfgan_block_bf16(xb_in, xb_out, aux, w1p, woutp, bias1, bout, *, dilation=1, idx=None, out_scale=math.sqrt(0.5),
+                      out_relu=False):
     B, T, Cc = xb_in.shape
     p = L.UsfganBlockParams()
     p.xb_in, p.xb_out, p.aux = L.ptr(xb_in, bf16, "xb_in"), L.ptr(xb_out, bf16, "xb_out"), L.ptr(aux, bf16, "aux")
@@ -263,4 +307,5 @@ def usfgan_block_bf16(xb_in, xb_out, aux, w1p, woutp, bias1, bout, *, dilation=1
         p.idx_past, p.idx_future = L.ptr(idx[0], torch.int32), L.ptr(idx[1], torch.int32)
     p.B, p.T, p.A = B, T, aux.shape[2]
     p.dilation, p.adaptive, p.out_scale = int(dilation), int(idx is not None), float(out_scale)
+    p.out_relu = int(out_relu)
     L.check(L.lib().svsk_usfgan_block_bf16(C.byref(p), L.stream_ptr()), "usfgan_block_bf16")

@@ -193,14 +193,14 @@ class ResidualBlocks(nn.Module):
         self._plan, self._plan_key = plan, key
         return plan
 
-    def forward_ntc_bf16(self, xb, auxb, d, idx_cache=None):
+    def forward_ntc_bf16(self, xb, auxb, d, idx_cache=None, relu_last=False):
         """xb [B,T,64] bf16, auxb [B,T,A8] bf16 (A rounded up to a multiple of 8), d (B,1,T) fp32 -> [B,T,64] bf16.
         One svsk_usfgan_block_bf16 launch per block; activations ping-pong between two buffers."""
         plan = self._bf16_plan(auxb.shape[2])
         idx_cache = {} if idx_cache is None else idx_cache
         cur, nxt = xb, torch.empty_like(xb)
         a_idx = 0
-        for pw in plan:
+        for n_blk, pw in enumerate(plan):
             idx = None
             if pw["adaptive"]:
                 dil = 2 ** (a_idx % self.blockA_per_cycle)
@@ -209,7 +209,7 @@ class ResidualBlocks(nn.Module):
                 idx = idx_cache[dil]
                 a_idx += 1
             ops.usfgan_block_bf16(cur, nxt, auxb, pw["w1p"], pw["woutp"], pw["bias1"], pw["bout"],
-                                  dilation=pw["dilation"], idx=idx)
+                                  dilation=pw["dilation"], idx=idx, out_relu=(relu_last and n_blk == len(plan) - 1))
             cur, nxt = nxt, cur
         return cur
 
@@ -249,6 +249,34 @@ class PeriodicityEstimator(nn.Module):
             modules += [conv, act]
             in_channels = residual_channels
         self.layers = nn.Sequential(*modules)
+
+    def supports_bf16(self):
+        convs = [self.layers[2 * n] for n in range(self.conv_layers)]
+        return all(c.out_channels % 16 == 0 and c.out_channels <= 256 and c.kernel_size[0] <= 8 for c in convs)
+
+    def forward_ntc_bf16(self, auxb):
+        """auxb [B,T,A8] bf16 (A padded to a multiple of 8 with zeros) -> a [B,T,Cout] bf16, tcgen05 conv kernel."""
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters()) + (auxb.shape[2],)
+        if getattr(self, "_plan_key", None) != key:
+            plan = []
+            with torch.no_grad():
+                cin = auxb.shape[2]
+                for n in range(self.conv_layers):
+                    conv = self.layers[2 * n]
+                    w = effective_weight(conv).to(f32)
+                    if cin > w.shape[1]:
+                        w = torch.nn.functional.pad(w, (0, 0, 0, cin - w.shape[1]))
+                    plan.append((ops.conv1d_pack_bf16(w.contiguous()), conv.bias.detach().to(f32).contiguous(),
+                                 conv.out_channels))
+                    cin = conv.out_channels
+            self._plan, self._plan_key = plan, key
+        pad = {"replicate": ops.PAD_REPLICATE, "reflect": ops.PAD_REFLECT, "zeros": ops.PAD_ZEROS}[self.padding_mode]
+        x = auxb
+        for n, (wp, bias, cout) in enumerate(self._plan):
+            act = ops.ACT_SIGMOID if n == self.conv_layers - 1 else ops.ACT_RELU
+            x = ops.conv1d_bf16(x, wp, bias, cout, self.kernel_size, dilation=self.dilation,
+                                tap_origin=self.kernel_size // 2, pad_mode=pad, act=act)
+        return x
 
     def forward(self, x):
         pad = {"replicate": ops.PAD_REPLICATE, "reflect": ops.PAD_REFLECT, "zeros": ops.PAD_ZEROS}[self.padding_mode]

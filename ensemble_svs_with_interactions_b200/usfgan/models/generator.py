@@ -173,6 +173,28 @@ class _HnBase(_GeneratorBase):
         sine, noise = x[:, 0:1].contiguous(), x[:, 1:2].contiguous()
         return c, a, _conv1x1(self.conv_first_sine, sine), _conv1x1(self.conv_first_noise, noise)
 
+    def _conv_last_ntc_bf16(self, yb_relu):
+        """conv_last on an NTC bf16 tensor that already went through the leading ReLU: 1x1 (tensor cores, ReLU fused)
+        then the C -> 1 projection.  Returns (B, 1, T) fp32."""
+        l1, l3 = self.conv_last[1], self.conv_last[3]
+        key = tuple((p.data_ptr(), p._version) for p in self.conv_last.parameters())
+        if getattr(self, "_last_key", None) != key:
+            with torch.no_grad():
+                self._last_plan = (ops.conv1d_pack_bf16(effective_weight(l1).to(f32).contiguous()),
+                                   l1.bias.detach().to(f32).contiguous(),
+                                   effective_weight(l3).to(f32).reshape(-1).contiguous(), float(l3.bias.detach()[0]))
+            self._last_key = key
+        wp, b1, w2, b2 = self._last_plan
+        hb = ops.conv1d_bf16(yb_relu, wp, b1, l1.out_channels, 1, act=ops.ACT_RELU)
+        return ops.dot_rows_bf16(hb, w2, b2).unsqueeze(1)
+
+    def _ntc_fast_path_ok(self):
+        l1, l3 = self.conv_last[1], self.conv_last[3]
+        pe_ok = self.periodicity_estimator.supports_bf16() and \
+            self.periodicity_estimator.layers[2 * (self.periodicity_estimator.conv_layers - 1)].out_channels == self.n_ch
+        return (self.resolved_precision() == "bf16" and pe_ok and l3.out_channels == 1 and l1.in_channels % 8 == 0
+                and l1.out_channels % 16 == 0 and self.in_channels == 1)
+
     def _outputs(self, y, s, h, n, a, wave_only):
         y = self._conv_last(y)
         if wave_only:
@@ -241,6 +263,20 @@ class ParallelHnUSFGANGenerator(_HnBase):
         """(x, s, h, n, a)   (generator.py:472-522): harmonic || noise -> a*h + (1-a)*n -> filter."""
         self._check(x)
         cache = {}
+        if wave_only and self._ntc_fast_path_ok():
+            # everything after the aux upsampling stays NTC bf16 on tensor cores
+            c = self.upsample_net(c)
+            assert c.size(-1) == x.size(-1)
+            auxb = self._aux_ntc(c)
+            ab = self.periodicity_estimator.forward_ntc_bf16(auxb)
+            xf = x.to(f32)
+            hb, _ = ops.nct_to_ntc(_conv1x1(self.conv_first_sine, xf[:, 0:1].contiguous()))
+            nb, _ = ops.nct_to_ntc(_conv1x1(self.conv_first_noise, xf[:, 1:2].contiguous()))
+            hb = self.harmonic_network.forward_ntc_bf16(hb, auxb, d, cache)
+            nb = self.noise_network.forward_ntc_bf16(nb, auxb, d, cache)
+            sb = ops.periodic_mix_bf16(ab, hb, nb)
+            yb = self.filter_network.forward_ntc_bf16(sb, auxb, d, cache, relu_last=True)
+            return self._conv_last_ntc_bf16(yb), None, None, None, ab
         c, a, h, n = self._front(x, c)
         auxb = self._aux_ntc(c)
         h = self._run_stack(self.harmonic_network, h, c, d, cache, auxb)

@@ -93,6 +93,11 @@ typedef struct svsk_conv1d_f32_params {
 } svsk_conv1d_f32_params;
 SVSK_API int svsk_conv1d_f32(const svsk_conv1d_f32_params* p, void* stream);
 
+/* nn.Linear on small batches, y[b][co] = act(bias[co] + sum_ci w[co][ci] x[b][ci]) — the step-embedding MLP and the
+ * per-layer diffusion_projection (denoiser.py:49,56,84-86,113-114). */
+SVSK_API int svsk_linear_f32(const float* x, const float* w, const float* bias, float* y, int Bt, int Cin, int Cout, int act,
+                             void* stream);
+
 /* z[b,h,t] = gate(y[b,h,t], y[b,H+h,t]).  denoiser.py:60-61 ; residual_block.py:140-149 ; modules.py:104-112 */
 SVSK_API int svsk_gated_act_f32(const float* y, float* z, int B, int H, int T, int order, void* stream);
 
@@ -216,11 +221,31 @@ typedef struct svsk_usfgan_block_params {
   int32_t B, T, A;
   int32_t dilation, adaptive;
   float out_scale;     /* sqrt(0.5) in the reference */
+  int32_t out_relu;    /* 1: xb_out = relu(...) — folds conv_last's leading ReLU into the last block (generator.py:461) */
 } svsk_usfgan_block_params;
 SVSK_API int svsk_usfgan_block_bf16(const svsk_usfgan_block_params* p, void* stream);
 /* w_taps [128][64][3] (k=3 conv, or stacked convP/convC/convF), w_aux [128][A], w_out [64][64] (fp32) -> packed bf16 */
 SVSK_API int svsk_usfgan_pack_block(const float* w_taps, const float* w_aux, const float* w_out, void* w1p, void* woutp,
                                     int C, int A, int G, void* stream);
+
+/* General NTC bf16 Conv1d on tensor cores (weights resident in smem, persistent over 128-sample tiles):
+ *   y[b][t][co] = act(bias[co] + sum_j sum_ci w[co][ci][j] x[b][t + (j - tap_origin)*dilation][ci])
+ * pad_mode: SVSK_PAD_ZEROS / REFLECT / REPLICATE.  Replaces PeriodicityEstimator's convs (residual_block.py:358-366) and
+ * conv_last's first 1x1 (generator.py:463).  Cin % 8 == 0, Cout % 16 == 0, Cout <= 256, packed weights must fit smem. */
+typedef struct svsk_conv1d_bf16_params {
+  const void* x;      /* [B][T][Cin] bf16 */
+  const void* wp;     /* [Cout][ksize * ceil64(Cin)] bf16 from svsk_conv1d_pack_bf16 */
+  const float* bias;  /* [Cout] or NULL */
+  void* y;            /* [B][T][Cout] bf16 */
+  int32_t B, T, Cin, Cout;
+  int32_t ksize, dilation, tap_origin, pad_mode, act;
+} svsk_conv1d_bf16_params;
+SVSK_API int svsk_conv1d_bf16(const svsk_conv1d_bf16_params* p, void* stream);
+SVSK_API int svsk_conv1d_pack_bf16(const float* w /* [Cout][Cin][ksize] */, void* wp, int Cout, int Cin, int ksize, void* stream);
+/* s = a*h + (1-a)*n on NTC bf16 tensors of cnt elements (generator.py:505-507). */
+SVSK_API int svsk_periodic_mix_bf16(const void* a, const void* h, const void* n, void* s, size_t cnt, void* stream);
+/* y[r] = bias + sum_c w[c] x[r][c]: the final C -> 1 projection of conv_last (generator.py:465). */
+SVSK_API int svsk_dot_rows_bf16(const void* x_bf16, const float* w, float bias, float* y, size_t rows, int C, void* stream);
 
 /* [B][T][Cp] bf16 -> [B][C][T] fp32 (first C channels). */
 SVSK_API int svsk_ntc_bf16_to_nct_f32(const void* x_bf16, float* y, int B, int C, int T, int Cp, void* stream);

@@ -474,7 +474,8 @@ def _usfgan_block_ref(w_taps, b1, w_aux, w_out, b_out, x, c, taps):
 
 @pytest.mark.parametrize("T,dil,adaptive,A", [(1000, 1, False, 80), (1000, 64, False, 80), (777, 512, False, 80),
                                                (130, 2, False, 72), (1000, 4, True, 80), (333, 16, True, 80),
-                                               (20000, 8, False, 80), (20000, 2, True, 80)])
+                                               (20000, 8, False, 80), (20000, 2, True, 80),
+                                               (400000, 512, False, 80), (400000, 16, True, 80)])
 def test_usfgan_block_bf16(T, dil, adaptive, A):
     ops = _ops()
     g = torch.Generator().manual_seed(T + dil)
@@ -528,3 +529,75 @@ def test_parallel_hn_fullwidth_bf16_vs_oracle():
     print(f"parallel-hn bf16 stacks vs fp32 oracle: rel_l2={r:.3e} max={mx:.3e}")
     m.precision = "fp32"
     close32(m(x.to(DEV), c.to(DEV), d.to(DEV))[0], ref[0], 5e-4)
+
+
+@pytest.mark.parametrize("Cin,Cout,k,dil,pad,act,T", [(80, 64, 5, 1, 2, 1, 1000), (64, 64, 5, 1, 2, 2, 777),
+                                                      (64, 64, 1, 1, 0, 1, 300), (72, 128, 3, 4, 1, 0, 513),
+                                                      (64, 128, 3, 2, 0, 0, 200), (80, 64, 5, 1, 2, 1, 40000)])
+def test_conv1d_bf16(Cin, Cout, k, dil, pad, act, T):
+    ops = _ops()
+    g = torch.Generator().manual_seed(Cin + Cout + T)
+    B = 2
+    x = torch.randn(B, Cin, T, generator=g); w = torch.randn(Cout, Cin, k, generator=g) / math.sqrt(Cin * k)
+    b = torch.randn(Cout, generator=g) * 0.2
+    mode = {0: "zeros", 1: "reflect", 2: "replicate"}[pad]
+    origin = (k - 1) // 2
+    ref = O.conv_taps(_bf(x), _bf(w), b, [(j - origin) * dil for j in range(k)], mode)
+    ref = torch.relu(ref) if act == 1 else (torch.sigmoid(ref) if act == 2 else ref)
+    xb, _ = ops.nct_to_ntc(x.to(DEV))
+    y = ops.conv1d_bf16(xb, ops.conv1d_pack_bf16(w.to(DEV)), b.to(DEV), Cout, k, dilation=dil, pad_mode=pad, act=act)
+    torch.cuda.synchronize()
+    close_bf16(y.float().transpose(1, 2), ref, 4e-3, 1.5e-2)
+
+
+def test_conv1d_bf16_rejects_oversized_weights():
+    ops = _ops()
+    x = torch.zeros(1, 64, 64, device=DEV, dtype=torch.bfloat16)
+    wp = ops.conv1d_pack_bf16(torch.zeros(256, 64, 5, device=DEV))
+    with pytest.raises(RuntimeError, match="do not fit"):
+        ops.conv1d_bf16(x, wp, None, 256, 5)
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        ops.conv1d_bf16(torch.zeros(1, 64, 60, device=DEV, dtype=torch.bfloat16), wp, None, 64, 1)
+
+
+def test_mix_and_dot_rows_bf16():
+    ops = _ops()
+    g = torch.Generator().manual_seed(4)
+    a = torch.rand(2, 100, 64, generator=g); h = torch.randn(2, 100, 64, generator=g); n = torch.randn(2, 100, 64, generator=g)
+    ab, hb, nb = (t.to(DEV).to(torch.bfloat16) for t in (a, h, n))
+    s = ops.periodic_mix_bf16(ab, hb, nb)
+    ref = _bf(a) * _bf(h) + (1 - _bf(a)) * _bf(n)
+    close_bf16(s.float(), ref, 4e-3, 1e-2)
+    w = torch.randn(64, generator=g)
+    y = ops.dot_rows_bf16(hb, w.to(DEV), 0.25)
+    close32(y, (_bf(h) * w).sum(-1) + 0.25, 1e-4)
+
+
+def test_parallel_hn_wave_only_fast_path_vs_oracle():
+    """USFGANWrapper's call (wave_only=True): PE, mix and conv_last also on the NTC bf16 tensor-core path."""
+    from ensemble_svs_with_interactions_b200.usfgan.models import ParallelHnUSFGANGenerator
+    torch.manual_seed(15)
+    hp = {"blockA": 4, "cycleA": 2, "blockF": 0, "cycleF": 0, "cascade_mode": 0}
+    np_ = {"blockA": 0, "cycleA": 0, "blockF": 2, "cycleF": 2, "cascade_mode": 0}
+    fp = {"blockA": 0, "cycleA": 0, "blockF": 6, "cycleF": 2, "cascade_mode": 0}
+    pe = {"conv_layers": 3, "kernel_size": 5, "dilation": 1, "padding_mode": "replicate"}
+    m = ParallelHnUSFGANGenerator(harmonic_network_params=hp, noise_network_params=np_, filter_network_params=fp,
+                                  periodicity_estimator_params=pe, upsample_params={"upsample_scales": [4, 3]}).eval()
+    g = torch.Generator().manual_seed(16)
+    with torch.no_grad():
+        last = m.periodicity_estimator.layers[-2]
+        last.weight_v.copy_(torch.randn(last.weight_v.shape, generator=g) * 0.1)
+    m.remove_weight_norm()
+    B, Fr, hop = 2, 60, 12
+    T = Fr * hop
+    c = torch.randn(B, 80, Fr + 4, generator=g)
+    d = torch.empty(B, 1, Fr).uniform_(1.0, 12.0, generator=g).repeat_interleave(hop, dim=-1)
+    x = torch.randn(B, 2, T, generator=g) * 0.3
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    ref = O.parallel_hn_usfgan_forward(sd, x, c, d, harmonic=hp, noise=np_, filt=fp, upsample_scales=[4, 3], pe=pe)
+    m = m.to(DEV)
+    assert m._ntc_fast_path_ok()
+    y, _, _, _, ab = m(x.to(DEV), c.to(DEV), d.to(DEV), wave_only=True)
+    r, mx = close_bf16(y, ref[0], 3e-2, 8e-2)
+    close_bf16(ab.float().transpose(1, 2), ref[4], 1e-2, 3e-2)
+    print(f"parallel-hn wave-only NTC path vs fp32 oracle: rel_l2={r:.3e} max={mx:.3e}")
