@@ -45,10 +45,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must end as a launch failure the host can see, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1  // nvcc otherwise unrolls this spin loop ~50x at every call site (tens of KB of SASS, I-cache misses)
   for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
     if (mbar_try_wait(bar, parity)) return;
   }
   __trap();
+}
+
+// Whole-warp wait with ONE polling lane: 32 lanes spinning on try_wait hammer the shared-memory port that the tensor
+// core needs for its operands (measured on the uSFGAN block kernel).  __syncwarp orders memory for the other lanes.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------- proxies / fences
@@ -180,6 +188,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
     if (mbar_try_wait_cluster(bar, parity)) return;
   }

@@ -41,6 +41,8 @@ struct UsfganArgs {
   int B, T, A, dilation, adaptive, nstages, akb, last_ksteps, tiles_per_row, total_tiles;
   float out_scale;
   int out_relu;
+  unsigned long long* dbg;  // profiling only: [grid][16] accumulated clock64 deltas per role
+  int dbg_flags;  // profiling only: 1 = skip epilogue math/stores, 4 = skip MMAs, 8 = skip TMA loads after the first ring fill
 };
 
 struct __align__(8) UsfganBarriers {
@@ -75,8 +77,8 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
   uint8_t* w1_s = smem;                          // KB tiles of [128 rows][64]
   uint8_t* wout_s = w1_s + KB * kUTile;          // [64 rows][64] = 8 KB
   uint8_t* ring = wout_s + 8192;
-  uint8_t* gbuf = ring + a.nstages * kUTile;     // 2 x 16 KB: G, then the output tile, of tile parity p
-  float* bias_s = reinterpret_cast<float*>(gbuf + 2 * kUTile);  // [128] gate biases, [64] output biases
+  uint8_t* gbuf = ring + a.nstages * kUTile;     // 3 x 16 KB, rotating: G, then the output tile, of tile n % 3
+  float* bias_s = reinterpret_cast<float*>(gbuf + 3 * kUTile);  // [128] gate biases, [64] output biases
   UsfganBarriers* bars = reinterpret_cast<UsfganBarriers*>(bias_s + 192);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -119,12 +121,20 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
       ptx::tma_load_2d(wout_s, &tm_wout, &bars->w_full, 0, 0);
       int s = 0;
       uint32_t ph = 0;
+      long long acc_p = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         const int b = tile / a.tiles_per_row, t0 = (tile - b * a.tiles_per_row) * 128;
         const bool gather = tile_needs_gather(t0, T, a.dilation, a.adaptive);
         for (int kb = 0; kb < KB; ++kb) {
+          const long long c_0 = clock64();
           ptx::mbar_wait(&bars->empty[s], ph ^ 1);
+          acc_p += clock64() - c_0;
           uint8_t* slot = ring + s * kUTile;
+          if ((a.dbg_flags & 8) && (tile != blockIdx.x) && !(gather && (kb == 0 || kb == 2))) {
+            ptx::mbar_arrive(&bars->full_t[s]);
+            if (++s == a.nstages) { s = 0; ph ^= 1; }
+            continue;
+          }
           if (kb == 1) {
             ptx::mbar_arrive_expect_tx(&bars->full_t[s], kUTile);
             ptx::tma_load_3d(slot, &tm_x, &bars->full_t[s], 0, t0, b);
@@ -138,6 +148,7 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
           if (++s == a.nstages) { s = 0; ph ^= 1; }
         }
       }
+      if (a.dbg) a.dbg[blockIdx.x * 16 + 0] = acc_p;  // producer: cycles waiting for free slots
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -150,6 +161,7 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
       int s = 0;
       uint32_t ph = 0, pht = 0, phg = 0;  // per-slot phase bits of full_t / full_g (each toggles only when used)
       int n_issued = 0;  // tiles whose GEMM1 has been issued
+      long long acc_full = 0, acc_g = 0, acc_fence = 0, acc_commit = 0, acc_total = clock64();
       for (int tile = blockIdx.x;; tile += gridDim.x) {
         const bool have = tile < a.total_tiles;
         if (have) {
@@ -158,6 +170,7 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
           const int p = n_issued & 1;
           for (int kb = 0; kb < KB; ++kb) {
             const bool from_gather = gather && (kb == 0 || kb == 2);
+            const long long c_0 = clock64();
             if (from_gather) {
               ptx::mbar_wait(&bars->full_g[s], (phg >> s) & 1);
               phg ^= 1u << s;
@@ -166,29 +179,46 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
               ptx::mbar_wait(&bars->full_t[s], (pht >> s) & 1);
               pht ^= 1u << s;
             }
+            const long long c_1 = clock64();
+            acc_full += c_1 - c_0;
             ptx::tc_fence_after();
+            const long long c_2 = clock64();
+            acc_fence += c_2 - c_1;
             const uint32_t a0 = ptx::smem_u32(ring + s * kUTile);
             const int ks = (kb == KB - 1) ? a.last_ksteps : 4;
-            for (int k4 = 0; k4 < ks; ++k4)
-              ptx::umma_bf16(tmem + p * 128, ptx::umma_desc_k_sw128(a0 + k4 * 32),
-                             ptx::umma_desc_k_sw128(w1a + kb * kUTile + k4 * 32), idesc1, (kb | k4) != 0);
-            ptx::umma_commit(&bars->empty[s]);
+            if (!(a.dbg_flags & 4))
+              for (int k4 = 0; k4 < ks; ++k4)
+                ptx::umma_bf16(tmem + p * 128, ptx::umma_desc_k_sw128(a0 + k4 * 32),
+                               ptx::umma_desc_k_sw128(w1a + kb * kUTile + k4 * 32), idesc1, (kb | k4) != 0);
+            const long long c_3 = clock64();
+            if (a.dbg_flags & 32) ptx::mbar_arrive(&bars->empty[s]); else ptx::umma_commit(&bars->empty[s]);
+            acc_commit += clock64() - c_3;
             if (++s == a.nstages) { s = 0; ph ^= 1; }
           }
-          ptx::umma_commit(&bars->d1_full[p]);
+          if (a.dbg_flags & 32) ptx::mbar_arrive(&bars->d1_full[p]); else ptx::umma_commit(&bars->d1_full[p]);
         }
         if (n_issued > 0) {  // GEMM2 of the previous tile: its G is written while this tile's GEMM1 runs
           const int m = n_issued - 1, p = m & 1;
+          const long long c_0 = clock64();
           ptx::mbar_wait(&bars->g_full[p], (m >> 1) & 1);
+          acc_g += clock64() - c_0;
           ptx::tc_fence_after();
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4)
-            ptx::umma_bf16(tmem + 256 + p * 64, ptx::umma_desc_k_sw128(ga + p * kUTile + k4 * 32),
+            ptx::umma_bf16(tmem + 256 + p * 64, ptx::umma_desc_k_sw128(ga + (m % 3) * kUTile + k4 * 32),
                            ptx::umma_desc_k_sw128(woa + k4 * 32), idesc2, k4 != 0);
-          ptx::umma_commit(&bars->d2_full[p]);
+          if (a.dbg_flags & 32) ptx::mbar_arrive(&bars->d2_full[p]); else ptx::umma_commit(&bars->d2_full[p]);
         }
         if (!have) break;
         ++n_issued;
+      }
+      if (a.dbg) {
+        a.dbg[blockIdx.x * 16 + 1] = acc_full;                 // MMA thread: waiting for operands
+        a.dbg[blockIdx.x * 16 + 2] = acc_g;                    // MMA thread: waiting for G
+        a.dbg[blockIdx.x * 16 + 3] = clock64() - acc_total;    // MMA thread: whole loop
+        a.dbg[blockIdx.x * 16 + 4] = n_issued;
+        a.dbg[blockIdx.x * 16 + 10] = acc_fence;
+        a.dbg[blockIdx.x * 16 + 11] = acc_commit;
       }
       (void)ph;
     }
@@ -204,7 +234,7 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
       for (int kb = 0; kb < KB; ++kb) {
         // Wait on EVERY slot, also the ones the TMA producer fills: parity waits only tell two consecutive phases apart,
         // so this warp group must never run more than one ring wrap ahead of the MMA issuer.
-        ptx::mbar_wait(&bars->empty[s], ph ^ 1);
+        ptx::mbar_wait_warp(&bars->empty[s], ph ^ 1);
         if (gather && (kb == 0 || kb == 2)) {
           int src = -1;
           if (t < T) {
@@ -235,83 +265,119 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     const int row = q * 32 + lane;
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
     const bool elected = (warp == 6 && lane == 0);
-    int n = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++n) {
-      const int b = tile / a.tiles_per_row, t0 = (tile - b * a.tiles_per_row) * 128;
-      const int t = t0 + row, p = n & 1;
-      const uint32_t par = (n >> 1) & 1;
-      // residual row, prefetched: this thread's two 16-channel chunks = 2 x 2 x 16 bytes
-      uint4 xr[2][2];
+    // Software-pipelined: iteration `it` gates tile it (so GEMM2(it) can be queued) and THEN finishes tile it-1, whose
+    // GEMM2 ran behind GEMM1(it) in the in-order tensor pipe while this warp group was gating.
+    const int my_tiles = a.total_tiles > (int)blockIdx.x ? (a.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    long long acc_d1 = 0, acc_gate = 0, acc_d2 = 0, acc_e2 = 0, acc_sync = 0;
+    uint4 xr_prev[2][2], xr_cur[2][2];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int c0 = 16 * (2 * i + sub);
-        if (t < T) {
-          const uint4* src = reinterpret_cast<const uint4*>(a.xb_in + ((size_t)b * T + t) * 64 + c0);
-          xr[i][0] = __ldg(src);
-          xr[i][1] = __ldg(src + 1);
-        } else {
-          xr[i][0] = xr[i][1] = make_uint4(0, 0, 0, 0);
+    for (int i = 0; i < 2; ++i) xr_prev[i][0] = xr_prev[i][1] = xr_cur[i][0] = xr_cur[i][1] = make_uint4(0, 0, 0, 0);
+    for (int it = 0; it <= my_tiles; ++it) {
+      if (it < my_tiles) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int b = tile / a.tiles_per_row, t0 = (tile - b * a.tiles_per_row) * 128;
+        const int t = t0 + row, p = it & 1;
+        // residual row of tile `it`, prefetched now and consumed one iteration later
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c0 = 16 * (2 * i + sub);
+          if (t < T) {
+            const uint4* src = reinterpret_cast<const uint4*>(a.xb_in + ((size_t)b * T + t) * 64 + c0);
+            xr_cur[i][0] = __ldg(src);
+            xr_cur[i][1] = __ldg(src + 1);
+          } else {
+            xr_cur[i][0] = xr_cur[i][1] = make_uint4(0, 0, 0, 0);
+          }
         }
-      }
-      uint8_t* gb = gbuf + p * kUTile;
-      if (n >= 2) {  // the TMA store of tile n-2 must have finished READING this buffer
-        if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        ptx::named_bar_sync(2, 256);
-      }
-      ptx::mbar_wait(&bars->d1_full[p], par);
-      ptx::tc_fence_after();
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int c0 = 16 * (2 * i + sub);
-        uint32_t ra[16], rb[16];
-        ptx::tmem_ld16(tmem + tlane + p * 128 + c0, ra);
-        ptx::tmem_ld16(tmem + tlane + p * 128 + 64 + c0, rb);
-        ptx::tmem_ld_wait();
-        uint32_t o[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float z0 = ptx::tanh_approx(__uint_as_float(ra[2 * e]) + bias_s[c0 + 2 * e]) *
-                           ptx::sigmoid_approx(__uint_as_float(rb[2 * e]) + bias_s[64 + c0 + 2 * e]);
-          const float z1 = ptx::tanh_approx(__uint_as_float(ra[2 * e + 1]) + bias_s[c0 + 2 * e + 1]) *
-                           ptx::sigmoid_approx(__uint_as_float(rb[2 * e + 1]) + bias_s[64 + c0 + 2 * e + 1]);
-          o[e] = ptx::pack_bf16(z0, z1);
+        uint8_t* gb = gbuf + (it % 3) * kUTile;
+        long long c_0 = clock64();
+        if (it >= 3) {  // buffer it%3 was the output tile of tile it-3: its TMA store must have finished reading
+          if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          ptx::named_bar_sync(2, 256);
         }
-        ptx::st_shared_v4(gb + ptx::sw128_offset((uint32_t)row, (uint32_t)(c0 >> 3)), o[0], o[1], o[2], o[3]);
-        ptx::st_shared_v4(gb + ptx::sw128_offset((uint32_t)row, (uint32_t)(c0 >> 3) + 1), o[4], o[5], o[6], o[7]);
-      }
-      ptx::tc_fence_before();
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&bars->g_full[p]);
-
-      ptx::mbar_wait(&bars->d2_full[p], par);
-      ptx::tc_fence_after();
+        acc_sync += clock64() - c_0;
+        c_0 = clock64();
+        ptx::mbar_wait_warp(&bars->d1_full[p], (it >> 1) & 1);
+        ptx::tc_fence_after();
+        acc_d1 += clock64() - c_0;
+        c_0 = clock64();
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int c0 = 16 * (2 * i + sub);
-        uint32_t rd[16];
-        ptx::tmem_ld16(tmem + tlane + 256 + p * 64 + c0, rd);
-        ptx::tmem_ld_wait();
-        const uint32_t xw[8] = {xr[i][0].x, xr[i][0].y, xr[i][0].z, xr[i][0].w, xr[i][1].x, xr[i][1].y, xr[i][1].z, xr[i][1].w};
-        uint32_t o[8];
+        for (int i = 0; i < 2; ++i) {
+          if (a.dbg_flags & 1) break;
+          const int c0 = 16 * (2 * i + sub);
+          uint32_t ra[16], rb[16];
+          ptx::tmem_ld16(tmem + tlane + p * 128 + c0, ra);
+          ptx::tmem_ld16(tmem + tlane + p * 128 + 64 + c0, rb);
+          ptx::tmem_ld_wait();
+          uint32_t o[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float lo = (__uint_as_float(rd[2 * e]) + bias_s[128 + c0 + 2 * e] + ptx::bf16_lo(xw[e])) * a.out_scale;
-          float hi = (__uint_as_float(rd[2 * e + 1]) + bias_s[128 + c0 + 2 * e + 1] + ptx::bf16_hi(xw[e])) * a.out_scale;
-          if (a.out_relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
-          o[e] = ptx::pack_bf16(lo, hi);
+          for (int e = 0; e < 8; ++e) {
+            const float z0 = ptx::tanh_approx(__uint_as_float(ra[2 * e]) + bias_s[c0 + 2 * e]) *
+                             ptx::sigmoid_approx(__uint_as_float(rb[2 * e]) + bias_s[64 + c0 + 2 * e]);
+            const float z1 = ptx::tanh_approx(__uint_as_float(ra[2 * e + 1]) + bias_s[c0 + 2 * e + 1]) *
+                             ptx::sigmoid_approx(__uint_as_float(rb[2 * e + 1]) + bias_s[64 + c0 + 2 * e + 1]);
+            o[e] = ptx::pack_bf16(z0, z1);
+          }
+          ptx::st_shared_v4(gb + ptx::sw128_offset((uint32_t)row, (uint32_t)(c0 >> 3)), o[0], o[1], o[2], o[3]);
+          ptx::st_shared_v4(gb + ptx::sw128_offset((uint32_t)row, (uint32_t)(c0 >> 3) + 1), o[4], o[5], o[6], o[7]);
         }
-        ptx::st_shared_v4(gb + ptx::sw128_offset((uint32_t)row, (uint32_t)(c0 >> 3)), o[0], o[1], o[2], o[3]);
-        ptx::st_shared_v4(gb + ptx::sw128_offset((uint32_t)row, (uint32_t)(c0 >> 3) + 1), o[4], o[5], o[6], o[7]);
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&bars->g_full[p]);
+        acc_gate += clock64() - c_0;
       }
-      ptx::tc_fence_before();
-      ptx::fence_proxy_async_smem();
-      ptx::named_bar_sync(2, 256);
-      if (elected) {
-        ptx::tma_store_3d(&tm_xout, gb, 0, t0, b);
-        ptx::bulk_commit_group();
+      if (it >= 1) {
+        const int m = it - 1, p = m & 1;
+        const int tile = blockIdx.x + m * gridDim.x;
+        const int b = tile / a.tiles_per_row, t0 = (tile - b * a.tiles_per_row) * 128;
+        uint8_t* gb = gbuf + (m % 3) * kUTile;
+        long long c_0 = clock64();
+        ptx::mbar_wait_warp(&bars->d2_full[p], (m >> 1) & 1);
+        ptx::tc_fence_after();
+        acc_d2 += clock64() - c_0;
+        c_0 = clock64();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          if (a.dbg_flags & 1) break;
+          const int c0 = 16 * (2 * i + sub);
+          uint32_t rd[16];
+          ptx::tmem_ld16(tmem + tlane + 256 + p * 64 + c0, rd);
+          ptx::tmem_ld_wait();
+          const uint32_t xw[8] = {xr_prev[i][0].x, xr_prev[i][0].y, xr_prev[i][0].z, xr_prev[i][0].w,
+                                  xr_prev[i][1].x, xr_prev[i][1].y, xr_prev[i][1].z, xr_prev[i][1].w};
+          uint32_t o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float lo = (__uint_as_float(rd[2 * e]) + bias_s[128 + c0 + 2 * e] + ptx::bf16_lo(xw[e])) * a.out_scale;
+            float hi = (__uint_as_float(rd[2 * e + 1]) + bias_s[128 + c0 + 2 * e + 1] + ptx::bf16_hi(xw[e])) * a.out_scale;
+            if (a.out_relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+            o[e] = ptx::pack_bf16(lo, hi);
+          }
+          ptx::st_shared_v4(gb + ptx::sw128_offset((uint32_t)row, (uint32_t)(c0 >> 3)), o[0], o[1], o[2], o[3]);
+          ptx::st_shared_v4(gb + ptx::sw128_offset((uint32_t)row, (uint32_t)(c0 >> 3) + 1), o[4], o[5], o[6], o[7]);
+        }
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async_smem();
+        acc_e2 += clock64() - c_0;
+        c_0 = clock64();
+        ptx::named_bar_sync(3, 256);
+        if (elected) {
+          ptx::tma_store_3d(&tm_xout, gb, 0, t0, b);
+          ptx::bulk_commit_group();
+        }
+        acc_sync += clock64() - c_0;
       }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { xr_prev[i][0] = xr_cur[i][0]; xr_prev[i][1] = xr_cur[i][1]; }
     }
     if (elected) ptx::bulk_wait_all();
+    if (a.dbg && elected) {
+      a.dbg[blockIdx.x * 16 + 5] = acc_d1;    // epilogue: waiting for D1
+      a.dbg[blockIdx.x * 16 + 6] = acc_gate;  // epilogue: gating + G stores + arrive
+      a.dbg[blockIdx.x * 16 + 7] = acc_d2;    // epilogue: waiting for D2
+      a.dbg[blockIdx.x * 16 + 8] = acc_e2;    // epilogue: residual maths + stores
+      a.dbg[blockIdx.x * 16 + 9] = acc_sync;  // epilogue: named barriers, TMA store issue, store-read waits
+    }
   }
 
   ptx::tc_fence_before();
@@ -368,7 +434,7 @@ extern "C" int svsk_usfgan_block_bf16(const svsk_usfgan_block_params* pp, void* 
 
   const int akb = (p.A + 63) / 64, KB = 3 + akb;
   const int K1p = 3 * 64 + akb * 64;
-  const int fixed = KB * kUTile + 8192 + 2 * kUTile + 192 * 4 + (int)sizeof(UsfganBarriers) + 1024;
+  const int fixed = KB * kUTile + 8192 + 3 * kUTile + 192 * 4 + (int)sizeof(UsfganBarriers) + 1024;
   int nstages = (232448 - fixed) / kUTile;
   if (nstages > kUMaxStages) nstages = kUMaxStages;
   SVSK_REQUIRE(nstages >= 3, SVSK_E_ARG, "usfgan_block_bf16: not enough shared memory (aux too wide)");
@@ -425,6 +491,10 @@ extern "C" int svsk_usfgan_block_bf16(const svsk_usfgan_block_params* pp, void* 
   a.total_tiles = p.B * a.tiles_per_row;
   a.out_scale = p.out_scale;
   a.out_relu = p.out_relu;
+  a.dbg_flags = 0;
+  a.dbg = nullptr;
+  if (const char* e = getenv("SVSK_USFGAN_ABLATE")) a.dbg_flags = atoi(e);
+  if (const char* e = getenv("SVSK_USFGAN_TIMELINE")) a.dbg = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
   const int grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
   usfgan_block_kernel<<<grid, kUThreads, smem_bytes, as_stream(stream)>>>(tm_x, tm_aux, tm_w1, tm_wout, tm_xout, a);
   return check_launch("usfgan_block_bf16");
