@@ -39,6 +39,20 @@ def _peaks():
         return None
 
 
+def _ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` summary (or None)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", name)))[0]
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            k = [x for x in d if x.startswith(key + " [")][0]
+            tot += float(d[k]) * unit[k[k.index("[") + 1:-1]]
+        return tot
+    except Exception:
+        return None
+
+
 def build_model(seed=1234):
     from ensemble_svs_with_interactions_b200.diffsinger import DiffNet, GaussianDiffusion
     torch.manual_seed(seed)
@@ -317,7 +331,8 @@ def main():
             "gpu_launches": gpu_launches,
             "clocks": clk.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": None, "kernel": "diffnet_block2_kernel (CTA pair, tcgen05 cta_group::2)",
+                         "frac": achieved_tf / peak_tf,
+                         "traffic": _ncu_traffic("r01h_block2_ncu_full_summary.json"), "kernel": "diffnet_block2_kernel (CTA pair, tcgen05 cta_group::2)",
                          "us_per_launch": block_ms * 1e3, "flops_per_launch": flops_per_launch,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400"},
             "whole_pass_tflops": 2.0 * MAC_PER_FRAME_STEP * B * T * K_STEP * args.steps * world / sec / 1e12,

@@ -1,0 +1,107 @@
+#!/usr/bin/env python
+"""BASELINE configs[3]: jaCappella_ritsu-shaped ensemble pipeline for N synthetic songs, track-sharded over the ranks.
+
+Per song (6 voice parts x 30 s): mgc diffusion (M=60, H=256, C=256, L=20, K=100) + bap diffusion (M=5, C=H=128, L=10,
+K=100) on pre-computed synthetic conditioning [6, 6000, H] (encoders / lf0 / vuv are outside the hot path),
+then ParallelHn-uSFGAN with aux = 60 mgc + 5 bap (padded to 72) for 6 x 720 000 samples at 24 kHz.
+Work item = song (its 6 tracks form one batch); items are assigned with sharding.assign; NO data-path collective.
+Strong scaling: the total number of songs is fixed.
+
+  python tools/bench_pipeline.py --songs 64            (1 GPU)
+  torchrun --nproc-per-node N tools/bench_pipeline.py --songs 64
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from ensemble_svs_with_interactions_b200 import _lib, sharding  # noqa: E402
+from ensemble_svs_with_interactions_b200.diffsinger import DiffNet, GaussianDiffusion  # noqa: E402
+from ensemble_svs_with_interactions_b200.usfgan.models import ParallelHnUSFGANGenerator  # noqa: E402
+
+FS, HOP, TRACKS, SECONDS = 24000, 120, 6, 30.0
+FRAMES = int(SECONDS * 200)          # 5 ms acoustic frames
+VFRAMES = int(SECONDS * FS / HOP)    # vocoder frames (hop 120 @ 24 kHz = 5 ms)
+
+
+def build(dev):
+    torch.manual_seed(1234)
+    mgc = GaussianDiffusion(256, 60, DiffNet(60, 256, 20, 256, 4), K_step=100)
+    bap = GaussianDiffusion(128, 5, DiffNet(5, 128, 10, 128, 4), K_step=100)
+    for m in (mgc, bap):
+        with torch.no_grad():
+            m.denoise_fn.output_projection.weight.normal_(0, 0.02)
+    pe = {"conv_layers": 3, "kernel_size": 5, "dilation": 1, "padding_mode": "replicate"}
+    voc = ParallelHnUSFGANGenerator(periodicity_estimator_params=pe, aux_channels=65)
+    with torch.no_grad():
+        voc.periodicity_estimator.layers[-2].weight_v.normal_(0, 0.05)
+    voc.remove_weight_norm()
+    return mgc.to(dev).eval(), bap.to(dev).eval(), voc.to(dev).eval()
+
+
+def song_inputs(song, dev):
+    g = torch.Generator().manual_seed(1234 + song)
+    cond_mgc = torch.randn(TRACKS, FRAMES, 256, generator=g)
+    cond_bap = torch.randn(TRACKS, FRAMES, 128, generator=g)
+    f0 = torch.empty(TRACKS, 1, VFRAMES).uniform_(110, 880, generator=g)
+    d = (FS / (f0 * 4)).repeat_interleave(HOP, dim=-1)
+    sig = torch.randn(TRACKS, 2, VFRAMES * HOP, generator=g) * 0.1
+    return [t.pin_memory() for t in (cond_mgc, cond_bap, d, sig)]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--songs", type=int, default=64)
+    ap.add_argument("--warmup-songs", type=int, default=1)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mgc, bap, voc = build(dev)
+    mine = sharding.assign([FRAMES] * args.songs, world)[rank]
+    host = song_inputs(0, dev)   # same shapes for every song; contents re-seeded per song below (cheap host RNG is not timed)
+
+    def synth(song):
+        cond_mgc, cond_bap, d, sig = (t.to(dev, non_blocking=True) for t in host)
+        m = mgc.inference(cond_mgc)                       # (6, 6000, 60)
+        b = bap.inference(cond_bap)                       # (6, 6000, 5)
+        aux = torch.cat([m, b], dim=-1).transpose(1, 2)   # (6, 65, 6000) == vocoder frames at 5 ms
+        aux = torch.nn.functional.pad(aux, (2, 2), mode="replicate").contiguous()
+        wav = voc(sig, aux, d, wave_only=True)[0]
+        return wav.cpu()                                  # D2H of the 6 waveforms
+
+    for s in range(args.warmup_songs):
+        synth(s)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in mine:
+        synth(s)
+    e1.record()
+    e1.synchronize()
+    sec = sharding.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
+    wall = time.perf_counter() - t0
+    if rank == 0:
+        audio = args.songs * TRACKS * SECONDS
+        print(json.dumps({"metric": "ensemble pipeline audio-sec/sec (mgc+bap diffusion + ParallelHn-uSFGAN)",
+                          "value": audio / sec, "unit": "audio-sec/s", "n_gpus": world, "songs": args.songs,
+                          "seconds": sec, "wall_seconds_rank0": wall, "scaling": "strong",
+                          "ms_per_song_rank0": 1e3 * sec / max(1, len(mine)), "gpu_launches_rank0": _lib.launch_count - n0,
+                          "config": {"workload": f"{args.songs} songs x {TRACKS} tracks x {SECONDS:.0f} s, K=100, 24 kHz"}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
