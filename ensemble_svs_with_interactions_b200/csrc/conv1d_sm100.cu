@@ -226,7 +226,7 @@ conv1d_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         ptx::bulk_commit_group();
       }
     }
-    if (elected) ptx::bulk_wait_all();
+    if (elected) ptx::bulk_wait_read_all();
   }
 
   ptx::tc_fence_before();

@@ -390,7 +390,7 @@ diffnet_block2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         }
       }
     }
-    if (elected) ptx::bulk_wait_all();
+    if (elected) ptx::bulk_wait_read_all();  // smem may be released; global visibility comes with grid completion
     if (stamp) SVSK_STAMP(14);
   }
 

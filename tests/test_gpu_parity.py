@@ -476,7 +476,8 @@ def _usfgan_block_ref(w_taps, b1, w_aux, w_out, b_out, x, c, taps):
                                                (130, 2, False, 72), (1000, 4, True, 80), (333, 16, True, 80),
                                                (20000, 8, False, 80), (20000, 2, True, 80),
                                                (400000, 512, False, 80), (400000, 16, True, 80)])
-def test_usfgan_block_bf16(T, dil, adaptive, A):
+@pytest.mark.parametrize("kernel", [2, 1])
+def test_usfgan_block_bf16(T, dil, adaptive, A, kernel):
     ops = _ops()
     g = torch.Generator().manual_seed(T + dil)
     B = 2
@@ -495,7 +496,7 @@ def test_usfgan_block_bf16(T, dil, adaptive, A):
     w1p, woutp = ops.usfgan_pack_block(w_taps.to(DEV), w_aux[:, :, 0].contiguous().to(DEV), w_out[:, :, 0].contiguous().to(DEV))
     out = torch.full_like(xb, float("nan"))
     idx = ops.pd_index(d.to(DEV), dil) if adaptive else None
-    ops.usfgan_block_bf16(xb, out, auxb, w1p, woutp, b1.to(DEV), b_out.to(DEV), dilation=dil, idx=idx)
+    ops.usfgan_block_bf16(xb, out, auxb, w1p, woutp, b1.to(DEV), b_out.to(DEV), dilation=dil, idx=idx, kernel=kernel)
     torch.cuda.synchronize()
     close_bf16(out.float().transpose(1, 2), ref, 4e-3, 1.5e-2)
 
@@ -601,3 +602,70 @@ def test_parallel_hn_wave_only_fast_path_vs_oracle():
     r, mx = close_bf16(y, ref[0], 3e-2, 8e-2)
     close_bf16(ab.float().transpose(1, 2), ref[4], 1e-2, 3e-2)
     print(f"parallel-hn wave-only NTC path vs fp32 oracle: rel_l2={r:.3e} max={mx:.3e}")
+
+
+# ------------------------------------------------------------------------------------------------ edge cases (ragged / tiny)
+@pytest.mark.parametrize("B,T", [(1, 1), (1, 5), (3, 37), (2, 129), (1, 257)])
+def test_diffnet_bf16_ragged_lengths(B, T):
+    """T smaller than a dilation, T = 1, T not a multiple of any tile: TMA zero-fill / clipping must hold."""
+    m = _random_diffnet(128, 64, 24, 5, seed=B * 100 + T)
+    g = torch.Generator().manual_seed(T)
+    spec = torch.randn(B, 1, 24, T, generator=g); cond = torch.randn(B, 64, T, generator=g)
+    t = torch.randint(0, 100, (B,), generator=g)
+    ref = O.diffnet_forward({k: v.detach() for k, v in m.state_dict().items()}, spec, t, cond, 5, 4)
+    m = m.to(DEV)
+    assert m.resolved_precision() == "bf16"
+    close_bf16(m(spec.to(DEV), t.to(DEV), cond.to(DEV)), ref, 2e-2, 6e-2)
+
+
+@pytest.mark.parametrize("T,dil", [(513, 512), (130, 64), (2, 1), (128, 1), (129, 128)])
+def test_usfgan_block_bf16_short_sequences(T, dil):
+    ops = _ops()
+    g = torch.Generator().manual_seed(T * 7 + dil)
+    x = torch.randn(1, 64, T, generator=g); c = torch.randn(1, 80, T, generator=g)
+    w_taps = torch.randn(128, 64, 3, generator=g) / 14; b1 = torch.randn(128, generator=g) * 0.1
+    w_aux = torch.randn(128, 80, 1, generator=g) / 9; w_out = torch.randn(64, 64, 1, generator=g) / 8
+    b_out = torch.randn(64, generator=g) * 0.1
+    taps = (O.shifted_tap(_bf(x), -dil, "reflect"), O.shifted_tap(_bf(x), dil, "reflect"))
+    ref = _usfgan_block_ref(w_taps, b1, w_aux, w_out, b_out, x, c, taps)
+    xb, _ = ops.nct_to_ntc(x.to(DEV)); auxb, _ = ops.nct_to_ntc(c.to(DEV))
+    w1p, woutp = ops.usfgan_pack_block(w_taps.to(DEV), w_aux[:, :, 0].contiguous().to(DEV), w_out[:, :, 0].contiguous().to(DEV))
+    for kernel in (1, 2):
+        out = torch.full_like(xb, float("nan"))
+        ops.usfgan_block_bf16(xb, out, auxb, w1p, woutp, b1.to(DEV), b_out.to(DEV), dilation=dil, kernel=kernel)
+        close_bf16(out.float().transpose(1, 2), ref, 4e-3, 1.5e-2)
+    with pytest.raises(RuntimeError, match="reflect"):
+        ops.usfgan_block_bf16(xb, out, auxb, w1p, woutp, b1.to(DEV), b_out.to(DEV), dilation=T)
+
+
+def test_usfgan_wrapper_recipe_width_bf16():
+    """USFGANWrapper.inference through the NTC bf16 fast path at the recipe widths (aux 65 -> padded to 72)."""
+    from types import SimpleNamespace as NS
+    from ensemble_svs_with_interactions_b200.usfgan import USFGANWrapper
+    from ensemble_svs_with_interactions_b200.usfgan.models import ParallelHnUSFGANGenerator
+    pe = {"conv_layers": 3, "kernel_size": 5, "dilation": 1, "padding_mode": "replicate"}
+    torch.manual_seed(3)
+    gen = ParallelHnUSFGANGenerator(harmonic_network_params={"blockA": 4, "cycleA": 2, "blockF": 0, "cycleF": 0, "cascade_mode": 0},
+                                    noise_network_params={"blockA": 0, "cycleA": 0, "blockF": 2, "cycleF": 2, "cascade_mode": 0},
+                                    filter_network_params={"blockA": 0, "cycleA": 0, "blockF": 4, "cycleF": 2, "cascade_mode": 0},
+                                    periodicity_estimator_params=pe, aux_channels=65).to(DEV).eval()
+    gen.remove_weight_norm()
+    assert gen._ntc_fast_path_ok()
+
+    class Cfg(dict):
+        __getattr__ = dict.__getitem__
+    config = NS(data=NS(sample_rate=24000, hop_size=120, sine_amp=0.1, noise_amp=0.003, signal_types=["sine", "noise"],
+                        sine_f0_type="contf0", df_f0_type="contf0", dense_factor=4),
+                generator=Cfg(aux_context_window=2))
+    frames = 40
+    f0 = np.full((frames, 1), 220.0, dtype=np.float32); f0[10:14] = 0
+    aux = torch.randn(frames, 65, device=DEV)
+    wav = USFGANWrapper(config, gen).inference(f0, aux)
+    assert wav.shape == (1, 1, frames * 120) and torch.isfinite(wav).all()
+    # same generator inputs through the fp32 path agree within the bf16 tolerance
+    torch.manual_seed(9)
+    w1 = USFGANWrapper(config, gen).inference(f0, aux)
+    gen.precision = "fp32"
+    torch.manual_seed(9)
+    w2 = USFGANWrapper(config, gen).inference(f0, aux)
+    close_bf16(w1, w2, 5e-2, 1.5e-1)
