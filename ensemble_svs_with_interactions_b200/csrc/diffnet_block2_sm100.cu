@@ -185,6 +185,7 @@ diffnet_block2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     // ------------------------------------------------------------------ MMA issuer: one thread of the leader CTA
     if (rank == 0 && lane == 0) {
       const uint32_t idesc = ptx::umma_idesc_bf16_f32(256, 256);
+      const uint32_t ring_lo = ptx::umma_desc_lo(ptx::smem_u32(smem)), g_lo = ptx::umma_desc_lo(ptx::smem_u32(g_smem));
       int s = 0;
       uint32_t ph = 0;
       for (int j = 0; j < NB; ++j) {
@@ -192,13 +193,12 @@ diffnet_block2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           ptx::mbar_wait(&bars->full[s], ph);
           ptx::mbar_wait(&bars->peer_full[s], ph);
           ptx::tc_fence_after();
-          const uint32_t a0 = ptx::smem_u32(smem + s * k2StageBytes);
-          const uint32_t b0 = a0 + k2TileBytes;
+          const uint32_t a_lo = ring_lo + s * (k2StageBytes >> 4), b_lo = a_lo + (k2TileBytes >> 4);
           if (!(a.dbg_flags & 4)) {
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              ptx::umma2_bf16(tmem + j * 256, ptx::umma_desc_k_sw128(a0 + k4 * 32),
-                              ptx::umma_desc_k_sw128(b0 + k4 * 32), idesc, (kb | k4) != 0);
+            ptx::umma2_bf16_lo(tmem + j * 256, a_lo, b_lo, idesc, kb != 0);
+            ptx::umma2_bf16_lo(tmem + j * 256, a_lo + 2, b_lo + 2, idesc, 1);
+            ptx::umma2_bf16_lo(tmem + j * 256, a_lo + 4, b_lo + 4, idesc, 1);
+            ptx::umma2_bf16_lo(tmem + j * 256, a_lo + 6, b_lo + 6, idesc, 1);
           }
           ptx::umma_commit2_mc(&bars->empty[s], 3);
           if (++s == a.nstages) { s = 0; ph ^= 1; }
@@ -209,18 +209,18 @@ diffnet_block2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       ptx::mbar_wait(&bars->g_ready, 0);
       ptx::tc_fence_after();
       SVSK_STAMP(4);
-      const uint32_t g0 = ptx::smem_u32(g_smem);
       for (int j = 0; j < NB; ++j) {
         for (int kb = 0; kb < KB2; ++kb) {
           ptx::mbar_wait(&bars->full[s], ph);
           ptx::mbar_wait(&bars->peer_full[s], ph);
           ptx::tc_fence_after();
-          const uint32_t b0 = ptx::smem_u32(smem + s * k2StageBytes) + k2TileBytes;
+          const uint32_t b_lo = ring_lo + s * (k2StageBytes >> 4) + (k2TileBytes >> 4);
+          const uint32_t gk_lo = g_lo + kb * (k2TileBytes >> 4);
           if (!(a.dbg_flags & 4)) {
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              ptx::umma2_bf16(tmem + j * 256, ptx::umma_desc_k_sw128(g0 + kb * k2TileBytes + k4 * 32),
-                              ptx::umma_desc_k_sw128(b0 + k4 * 32), idesc, (kb | k4) != 0);
+            ptx::umma2_bf16_lo(tmem + j * 256, gk_lo, b_lo, idesc, kb != 0);
+            ptx::umma2_bf16_lo(tmem + j * 256, gk_lo + 2, b_lo + 2, idesc, 1);
+            ptx::umma2_bf16_lo(tmem + j * 256, gk_lo + 4, b_lo + 4, idesc, 1);
+            ptx::umma2_bf16_lo(tmem + j * 256, gk_lo + 6, b_lo + 6, idesc, 1);
           }
           ptx::umma_commit2_mc(&bars->empty[s], 3);
           if (++s == a.nstages) { s = 0; ph ^= 1; }

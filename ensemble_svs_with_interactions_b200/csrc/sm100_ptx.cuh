@@ -43,6 +43,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe (mbarrier.test_wait): lets the MMA issuer look at the NEXT stage's barrier before it issues the current
+// stage's MMAs, so the probe's latency overlaps the issue instead of sitting on the serial chain.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must end as a launch failure the host can see, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #pragma unroll 1  // nvcc otherwise unrolls this spin loop ~50x at every call site (tens of KB of SASS, I-cache misses)
@@ -108,6 +121,12 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// The same descriptor as two 32-bit halves: only the low half depends on the address, so the MMA-issuing thread (whose
+// scalar instructions sit on the tensor pipe's critical path, tcgen05.mma issue being blocking) computes
+// lo = umma_desc_lo(base) once per operand tile and adds 2 per 32-byte K step; hi is the constant below.
+constexpr uint32_t kUmmaDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO=64, version=1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16); }
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, both operands K-major.
 //   [4,6) D format = 1 (F32) | [7,10) A format = 1 (BF16) | [10,13) B format = 1 (BF16)
 //   [15] A major = 0 (K) | [16] B major = 0 (K) | [17,23) N >> 3 | [24,29) M >> 4
@@ -123,6 +142,26 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHiSw128)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHiSw128)
       : "memory");
 }
 // Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed

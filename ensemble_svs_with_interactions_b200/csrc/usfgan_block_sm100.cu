@@ -11,7 +11,9 @@
 // Persistent kernel, one CTA per SM looping over 128-sample tiles (time = MMA M).  The block's weights (88 KB bf16) are
 // loaded into shared memory ONCE per CTA and stay resident; only activations stream:
 //   warp 0      TMA producer: centre tap + aux k-blocks, and both side taps of interior fixed-block tiles
-//   warp 1      MMA issuer (tcgen05.mma cta_group::1, M=128, N=128 then N=64) + TMEM owner
+//   warp 1      GEMM1 issuer (tcgen05.mma cta_group::1, M=128, N=128) + TMEM owner
+//   warp 14     GEMM2 issuer (N=64): tcgen05.mma issue blocks the issuing thread, so the second GEMM's waits and
+//               commits get their own thread instead of sitting in the first GEMM's serial instruction stream
 //   warps 2-5   gather producers (thread = row): side taps of adaptive blocks / boundary tiles via cp.async 16-byte
 //               copies into the swizzled tile, completion signalled with cp.async.mbarrier.arrive.noinc
 //   warps 6-13  epilogue (thread = sample, two warps per TMEM lane quarter alternating 16-column chunks):
@@ -29,7 +31,7 @@ namespace svsk {
 
 constexpr int kUTile = 128 * 128;  // 128 rows x 64 bf16
 constexpr int kUMaxStages = 6;
-constexpr int kUThreads = 448;  // 2 + 4 gather + 8 epilogue warps
+constexpr int kUThreads = 480;  // producer, GEMM1 issuer, 4 gather, 8 epilogue, GEMM2 issuer warps
 constexpr int kUMaxKB = 8;         // 3 taps + up to 5 aux k-blocks (aux <= 320 channels)
 
 struct UsfganArgs {
@@ -155,10 +157,9 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc1 = ptx::umma_idesc_bf16_f32(128, 128);
-      const uint32_t idesc2 = ptx::umma_idesc_bf16_f32(128, 64);
       ptx::mbar_wait(&bars->w_full, 0);
       ptx::tc_fence_after();
-      const uint32_t w1a = ptx::smem_u32(w1_s), woa = ptx::smem_u32(wout_s), ga = ptx::smem_u32(gbuf);
+      const uint32_t ring_lo = ptx::umma_desc_lo(ptx::smem_u32(ring)), w1_lo = ptx::umma_desc_lo(ptx::smem_u32(w1_s));
       int s = 0;
       uint32_t ph = 0, pht = 0, phg = 0;  // per-slot phase bits of full_t / full_g (each toggles only when used)
       int n_issued = 0;  // tiles whose GEMM1 has been issued
@@ -169,52 +170,53 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
           const int b = tile / a.tiles_per_row, t0 = (tile - b * a.tiles_per_row) * 128;
           const bool gather = tile_needs_gather(t0, T, a.dilation, a.adaptive);
           const int p = n_issued & 1;
+          // D1[p] is free once the epilogue has gated tile n_issued - 2 out of it (GEMM2 has its own issuing thread, so
+          // this thread has to observe g_full itself)
+          if (n_issued >= 2) {
+            const long long c_g = (kProf ? clock64() : 0ll);
+            ptx::mbar_wait(&bars->g_full[p], ((n_issued - 2) >> 1) & 1);
+            acc_g += (kProf ? clock64() : 0ll) - c_g;
+          }
+          // the first k-block's barrier is probed here, every later one while the previous k-block's MMAs are issued
+          bool ready = false;
           for (int kb = 0; kb < KB; ++kb) {
             const bool from_gather = gather && (kb == 0 || kb == 2);
+            uint64_t* fb = from_gather ? &bars->full_g[s] : &bars->full_t[s];
+            const uint32_t par = from_gather ? ((phg >> s) & 1) : ((pht >> s) & 1);
             const long long c_0 = (kProf ? clock64() : 0ll);
-            if ((kProf ? a.dbg_flags : 0) & 128) {
-              if (from_gather) phg ^= 1u << s; else pht ^= 1u << s;
-            } else if (from_gather) {
-              ptx::mbar_wait(&bars->full_g[s], (phg >> s) & 1);
-              phg ^= 1u << s;
-              ptx::fence_proxy_async_smem();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
-            } else {
-              ptx::mbar_wait(&bars->full_t[s], (pht >> s) & 1);
-              pht ^= 1u << s;
-            }
+            if (!ready) ptx::mbar_wait(fb, par);
+            if (from_gather) { phg ^= 1u << s; ptx::fence_proxy_async_smem(); } else { pht ^= 1u << s; }
             const long long c_1 = (kProf ? clock64() : 0ll);
             acc_full += c_1 - c_0;
             ptx::tc_fence_after();
             const long long c_2 = (kProf ? clock64() : 0ll);
             acc_fence += c_2 - c_1;
-            const uint32_t a0 = ptx::smem_u32(ring + s * kUTile);
+            // probe the next k-block of this tile (the next tile's first k-block is waited for normally)
+            const int s_next = (s + 1 == a.nstages) ? 0 : s + 1;
+            ready = false;
+            if (kb + 1 < KB) {
+              const bool ng = gather && (kb + 1 == 0 || kb + 1 == 2);
+              ready = ptx::mbar_test(ng ? &bars->full_g[s_next] : &bars->full_t[s_next],
+                                     ng ? ((phg >> s_next) & 1) : ((pht >> s_next) & 1));
+            }
+            const uint32_t a_lo = ring_lo + s * (kUTile >> 4), b_lo = w1_lo + kb * (kUTile >> 4);
             const int ks = (kb == KB - 1) ? a.last_ksteps : 4;
-            if (!((kProf ? a.dbg_flags : 0) & 4))
-              for (int k4 = 0; k4 < ks; ++k4)
-                ptx::umma_bf16(tmem + p * 128, ptx::umma_desc_k_sw128(a0 + k4 * 32),
-                               ptx::umma_desc_k_sw128(w1a + kb * kUTile + k4 * 32), idesc1, (kb | k4) != 0);
-            if ((kProf ? a.dbg_flags : 0) & 64)  // profiling: the same MMAs a second time into the unused TMEM columns 384..511
-              for (int k4 = 0; k4 < ks; ++k4)
-                ptx::umma_bf16(tmem + 384, ptx::umma_desc_k_sw128(a0 + k4 * 32),
-                               ptx::umma_desc_k_sw128(w1a + kb * kUTile + k4 * 32), idesc1, (kb | k4) != 0);
+            if (!((kProf ? a.dbg_flags : 0) & 4)) {
+              ptx::umma_bf16_lo(tmem + p * 128, a_lo, b_lo, idesc1, kb != 0);
+              if (ks == 4) {
+                ptx::umma_bf16_lo(tmem + p * 128, a_lo + 2, b_lo + 2, idesc1, 1);
+                ptx::umma_bf16_lo(tmem + p * 128, a_lo + 4, b_lo + 4, idesc1, 1);
+                ptx::umma_bf16_lo(tmem + p * 128, a_lo + 6, b_lo + 6, idesc1, 1);
+              } else {
+                for (int k4 = 1; k4 < ks; ++k4) ptx::umma_bf16_lo(tmem + p * 128, a_lo + 2 * k4, b_lo + 2 * k4, idesc1, 1);
+              }
+            }
             const long long c_3 = (kProf ? clock64() : 0ll);
             if ((kProf ? a.dbg_flags : 0) & 32) ptx::mbar_arrive(&bars->empty[s]); else ptx::umma_commit(&bars->empty[s]);
             acc_commit += (kProf ? clock64() : 0ll) - c_3;
             if (++s == a.nstages) { s = 0; ph ^= 1; }
           }
           if ((kProf ? a.dbg_flags : 0) & 32) ptx::mbar_arrive(&bars->d1_full[p]); else ptx::umma_commit(&bars->d1_full[p]);
-        }
-        if (n_issued > 0) {  // GEMM2 of the previous tile: its G is written while this tile's GEMM1 runs
-          const int m = n_issued - 1, p = m & 1;
-          const long long c_0 = (kProf ? clock64() : 0ll);
-          ptx::mbar_wait(&bars->g_full[p], (m >> 1) & 1);
-          acc_g += (kProf ? clock64() : 0ll) - c_0;
-          ptx::tc_fence_after();
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)
-            ptx::umma_bf16(tmem + 256 + p * 64, ptx::umma_desc_k_sw128(ga + (m % 3) * kUTile + k4 * 32),
-                           ptx::umma_desc_k_sw128(woa + k4 * 32), idesc2, k4 != 0);
-          if ((kProf ? a.dbg_flags : 0) & 32) ptx::mbar_arrive(&bars->d2_full[p]); else ptx::umma_commit(&bars->d2_full[p]);
         }
         if (!have) break;
         ++n_issued;
@@ -265,6 +267,24 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp == 14) {
+    // ------------------------------------------------------------------ GEMM2 issuer: D2 = G . Wout^T per tile
+    if (lane == 0) {
+      const uint32_t idesc2 = ptx::umma_idesc_bf16_f32(128, 64);
+      ptx::mbar_wait(&bars->w_full, 0);
+      ptx::tc_fence_after();
+      const uint32_t wo_lo = ptx::umma_desc_lo(ptx::smem_u32(wout_s)), g_lo = ptx::umma_desc_lo(ptx::smem_u32(gbuf));
+      int m = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++m) {
+        const int p = m & 1;
+        ptx::mbar_wait(&bars->g_full[p], (m >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t gl = g_lo + (m % 3) * (kUTile >> 4);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) ptx::umma_bf16_lo(tmem + 256 + p * 64, gl + 2 * k4, wo_lo + 2 * k4, idesc2, k4 != 0);
+        ptx::umma_commit(&bars->d2_full[p]);
+      }
+    }
   } else {
     // ------------------------------------------------------------------ epilogue (thread = one sample, half the columns)
     const int q = warp & 3;
