@@ -89,6 +89,7 @@ _SIGNATURES = {
     "svsk_cast_scale_bf16": [_V, _V, _Z, _F, _I, _V],
     "svsk_diffnet_block_bf16": [C.POINTER(DiffnetBlockParams), _V],
     "svsk_diffnet_block2_bf16": [C.POINTER(DiffnetBlockParams), _V],
+    "svsk_diffnet_block3_bf16": [C.POINTER(DiffnetBlockParams), _V],
     "svsk_diffnet_pack_block": [_V, _V, _V, _V, _V, _I, _I, _V],
     "svsk_diffnet_packed_row": [_I, _I],
     "svsk_linear_bf16": [C.POINTER(LinearBf16Params), _V],

@@ -85,7 +85,7 @@ diffnet_block2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   const uint32_t rank = ptx::cluster_ctarank();
   const int b = blockIdx.y;
   const int t_cta0 = (blockIdx.x >> 1) * 256 + (int)rank * 128;  // first frame of this CTA's 128 TMEM lanes
-  unsigned long long* dbg = a.dbg ? a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
+  unsigned long long* dbg = a.dbg ? a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 32 : nullptr;
 #define SVSK_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
   if (threadIdx.x == 0) SVSK_STAMP(0);
 
@@ -139,9 +139,12 @@ diffnet_block2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
+      long long acc_pe = 0;
       for (int j = 0; j < NB; ++j) {
         for (int kb = 0; kb < KB1; ++kb) {
+          const long long c_0 = dbg ? clock64() : 0ll;
           ptx::mbar_wait(&bars->empty[s], ph ^ 1);
+          if (dbg) acc_pe += clock64() - c_0;
           uint8_t* As = smem + s * k2StageBytes;
           uint8_t* Bs = As + k2TileBytes;
           if ((a.dbg_flags & 8) && (j * KB1 + kb) >= a.nstages) {
@@ -180,6 +183,7 @@ diffnet_block2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         }
       }
       SVSK_STAMP(1);
+      if (dbg) dbg[16] = acc_pe;  // producer: cycles waiting for free slots during GEMM1
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer: one thread of the leader CTA
@@ -188,10 +192,16 @@ diffnet_block2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       const uint32_t ring_lo = ptx::umma_desc_lo(ptx::smem_u32(smem)), g_lo = ptx::umma_desc_lo(ptx::smem_u32(g_smem));
       int s = 0;
       uint32_t ph = 0;
+      long long acc_wf = 0, acc_wp = 0, acc_is = 0;
       for (int j = 0; j < NB; ++j) {
         for (int kb = 0; kb < KB1; ++kb) {
+          const long long c_0 = dbg ? clock64() : 0ll;
           ptx::mbar_wait(&bars->full[s], ph);
+          const long long c_1 = dbg ? clock64() : 0ll;
           ptx::mbar_wait(&bars->peer_full[s], ph);
+          const long long c_2 = dbg ? clock64() : 0ll;
+          acc_wf += c_1 - c_0;
+          acc_wp += c_2 - c_1;
           ptx::tc_fence_after();
           const uint32_t a_lo = ring_lo + s * (k2StageBytes >> 4), b_lo = a_lo + (k2TileBytes >> 4);
           if (!(a.dbg_flags & 4)) {
@@ -201,11 +211,13 @@ diffnet_block2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             ptx::umma2_bf16_lo(tmem + j * 256, a_lo + 6, b_lo + 6, idesc, 1);
           }
           ptx::umma_commit2_mc(&bars->empty[s], 3);
+          if (dbg) acc_is += clock64() - c_2;
           if (++s == a.nstages) { s = 0; ph ^= 1; }
         }
         ptx::umma_commit2_mc(&bars->d1_full[j], 3);
         SVSK_STAMP(2 + j);
       }
+      if (dbg) { dbg[17] = acc_wf; dbg[18] = acc_wp; dbg[19] = acc_is; }  // GEMM1: wait own stage / peer stage / issue+commit
       ptx::mbar_wait(&bars->g_ready, 0);
       ptx::tc_fence_after();
       SVSK_STAMP(4);

@@ -65,6 +65,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   __trap();
 }
 
+// Pure polling wait (mbarrier.test_wait never suspends the thread): for the single-thread roles on a pipeline's critical
+// handshake path, where the wake-up latency of a suspended try_wait would add to every hop.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    if (mbar_test(bar, parity)) return;
+  }
+  __trap();
+}
+
 // Whole-warp wait with ONE polling lane: 32 lanes spinning on try_wait hammer the shared-memory port that the tensor
 // core needs for its operands (measured on the uSFGAN block kernel).  __syncwarp orders memory for the other lanes.
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
@@ -164,6 +174,53 @@ __device__ __forceinline__ void umma2_bf16_lo(uint32_t tmem_d, uint32_t a_lo, ui
       "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHiSw128)
       : "memory");
 }
+// KSTEPS K-steps of one 64-wide k-block (the descriptor low words advance by 2 per 32 bytes) PLUS a non-blocking probe
+// of another mbarrier whose result is consumed only after the MMAs have been issued.  Measured (tools/ubench_umma.py,
+// "issue loop"): an mbarrier try_wait/test_wait whose result is needed right away costs the issuing thread ~160 cycles
+// even when the phase completed long ago, and a loop of {2 waits, 4 MMAs} runs at 632 cycles per group whatever the MMA
+// shape — slower than the tensor pipe needs for the four MMAs (256 / 512 cycles at N = 128 / 256).  Probing the NEXT
+// ring entry's barrier here hides that latency behind the MMA issue.
+#define SVSK_UMMA_X4_PROBE(NAME, CG)                                                                                    \
+  __device__ __forceinline__ bool NAME(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,                  \
+                                       uint32_t accumulate_first, int ksteps, uint64_t* probe_bar, uint32_t probe_parity) { \
+    uint32_t ok;                                                                                                        \
+    asm volatile(                                                                                                       \
+        "{\n\t.reg .pred p, q, k2, k3, k4;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"                              \
+        "mbarrier.test_wait.parity.shared::cta.b64 q, [%8], %9;\n\t"                                                    \
+        "setp.ne.b32 p, %5, 0;\n\t"                                                                                     \
+        "setp.gt.s32 k2, %7, 1;\n\t"                                                                                    \
+        "setp.gt.s32 k3, %7, 2;\n\t"                                                                                    \
+        "setp.gt.s32 k4, %7, 3;\n\t"                                                                                    \
+        "mov.b64 da, {%2, %6};\n\t"                                                                                     \
+        "mov.b64 db, {%3, %6};\n\t"                                                                                     \
+        "tcgen05.mma.cta_group::" #CG ".kind::f16 [%1], da, db, %4, p;\n\t"                                             \
+        "setp.eq.b32 p, %4, %4;\n\t"                                                                                    \
+        "add.u32 al, %2, 2;\n\t"                                                                                        \
+        "add.u32 bl, %3, 2;\n\t"                                                                                        \
+        "mov.b64 da, {al, %6};\n\t"                                                                                     \
+        "mov.b64 db, {bl, %6};\n\t"                                                                                     \
+        "@k2 tcgen05.mma.cta_group::" #CG ".kind::f16 [%1], da, db, %4, p;\n\t"                                         \
+        "add.u32 al, %2, 4;\n\t"                                                                                        \
+        "add.u32 bl, %3, 4;\n\t"                                                                                        \
+        "mov.b64 da, {al, %6};\n\t"                                                                                     \
+        "mov.b64 db, {bl, %6};\n\t"                                                                                     \
+        "@k3 tcgen05.mma.cta_group::" #CG ".kind::f16 [%1], da, db, %4, p;\n\t"                                         \
+        "add.u32 al, %2, 6;\n\t"                                                                                        \
+        "add.u32 bl, %3, 6;\n\t"                                                                                        \
+        "mov.b64 da, {al, %6};\n\t"                                                                                     \
+        "mov.b64 db, {bl, %6};\n\t"                                                                                     \
+        "@k4 tcgen05.mma.cta_group::" #CG ".kind::f16 [%1], da, db, %4, p;\n\t"                                         \
+        "selp.u32 %0, 1, 0, q;\n\t}\n"                                                                                 \
+        : "=r"(ok)                                                                                                      \
+        : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate_first), "r"(kUmmaDescHiSw128), "r"(ksteps),     \
+          "r"(smem_u32(probe_bar)), "r"(probe_parity)                                                                   \
+        : "memory");                                                                                                    \
+    return ok != 0;                                                                                                     \
+  }
+SVSK_UMMA_X4_PROBE(umma_bf16_x4_probe, 1)
+SVSK_UMMA_X4_PROBE(umma2_bf16_x4_probe, 2)
+#undef SVSK_UMMA_X4_PROBE
+
 // Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -309,6 +366,11 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 __device__ __forceinline__ uint4 ld_shared_v4(const void* p) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+__device__ __forceinline__ float4 ld_shared_v4f(const void* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
   return v;
 }
 __device__ __forceinline__ void st_shared_v4f(void* p, float a, float b, float c, float d) {

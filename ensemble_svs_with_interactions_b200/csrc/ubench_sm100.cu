@@ -31,6 +31,54 @@ __global__ void __launch_bounds__(128, 1) ubench_umma_kernel(int N, int iters, i
     const uint32_t idesc = ptx::umma_idesc_bf16_f32(kCtaGroup == 2 ? 256 : 128, N);
     const uint32_t a0 = ptx::smem_u32(smem);             // A tiles: 16 KB each (128 rows x 64)
     const uint32_t b0 = a0 + 4 * 16384;                  // B tiles: up to 32 KB each (256 rows x 64)
+    if (advance >= 32) {
+      // issue-loop mode: groups of 4 MMAs with optional per-group extras, never waiting for the MMAs themselves:
+      // bit0 = two try_waits on a long-completed barrier, bit1 = tcgen05.fence::after_thread_sync, bit2 = commit to a
+      // barrier nobody waits on, bit3 = test_wait instead of try_wait.  Pipe-bound = 4 x nominal per group.
+      const int v = advance - 32;
+      __shared__ uint64_t done_bar, sink_bar;
+      ptx::mbar_init(&done_bar, 1);
+      ptx::mbar_init(&sink_bar, 1);
+      ptx::fence_mbar_init();
+      ptx::mbar_arrive(&done_bar);  // phase 0 of done_bar is complete from here on
+      const long long t0 = clock64();
+      for (int i = 0; i < iters; ++i) {
+        if (v & 1) {
+          if (v & 8) { ptx::mbar_wait_spin(&done_bar, 0); ptx::mbar_wait_spin(&done_bar, 0); }
+          else { ptx::mbar_wait(&done_bar, 0); ptx::mbar_wait(&done_bar, 0); }
+        }
+        if (v & 2) ptx::tc_fence_after();
+        for (int g = 0; g < 4; ++g) {
+          if (kCtaGroup == 2) ptx::umma2_bf16(tmem, ptx::umma_desc_k_sw128(a0 + g * 32), ptx::umma_desc_k_sw128(b0 + g * 32), idesc, 1);
+          else ptx::umma_bf16(tmem, ptx::umma_desc_k_sw128(a0 + g * 32), ptx::umma_desc_k_sw128(b0 + g * 32), idesc, 1);
+        }
+        if (v & 4) { if (kCtaGroup == 2) ptx::umma_commit2_mc(&sink_bar, 1); else ptx::umma_commit(&sink_bar); }
+      }
+      const long long t1 = clock64();
+      if (kCtaGroup == 2) ptx::umma_commit2_mc(&bar, 1); else ptx::umma_commit(&bar);
+      ptx::mbar_wait(&bar, 0);
+      const long long t2 = clock64();
+      out[blockIdx.x * 2] = t1 - t0;
+      out[blockIdx.x * 2 + 1] = t2 - t0;
+    } else if (advance >= 16) {
+      // serial mode: groups of (advance - 16 + 1) MMAs, each followed by commit + wait: (group time) - (MMA time) = latency
+      // from the last MMA's completion to the issuing thread seeing the barrier flip
+      const int group = advance - 16 + 1;
+      const long long t0 = clock64();
+      uint32_t ph = 0;
+      for (int i = 0; i < iters; ++i) {
+        for (int g = 0; g < group; ++g) {
+          if (kCtaGroup == 2) ptx::umma2_bf16(tmem, ptx::umma_desc_k_sw128(a0), ptx::umma_desc_k_sw128(b0), idesc, 1);
+          else ptx::umma_bf16(tmem, ptx::umma_desc_k_sw128(a0), ptx::umma_desc_k_sw128(b0), idesc, 1);
+        }
+        if (kCtaGroup == 2) ptx::umma_commit2_mc(&bar, 1); else ptx::umma_commit(&bar);
+        ptx::mbar_wait_spin(&bar, ph);
+        ph ^= 1;
+      }
+      const long long t1 = clock64();
+      out[blockIdx.x * 2] = t1 - t0;
+      out[blockIdx.x * 2 + 1] = t1 - t0;
+    } else {
     const long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
       const int sel = advance ? (i & 3) : 0;
@@ -45,11 +93,63 @@ __global__ void __launch_bounds__(128, 1) ubench_umma_kernel(int N, int iters, i
     const long long t2 = clock64();
     out[blockIdx.x * 2] = t1 - t0;      // issue time
     out[blockIdx.x * 2 + 1] = t2 - t0;  // until the last MMA has completed
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (kCtaGroup == 2) ptx::cluster_sync_all();
   if (warp == 1) { if (kCtaGroup == 2) ptx::tmem_dealloc2(tmem, 512); else ptx::tmem_dealloc(tmem, 512); }
+}
+
+// Correctness probe: does a K-major SWIZZLE_128B operand descriptor work when its start address is offset by a whole
+// number of 128-byte rows (not a multiple of the 1024-byte swizzle atom)?  A = rows r0 .. r0+127 of a window tile,
+// B = 64x64 identity, so D[m][n] must equal win[r0+m][n].  mode 0: base-offset field 0; mode 1: (addr >> 7) & 7.
+__global__ void __launch_bounds__(128, 1) ubench_rowshift_kernel(const __nv_bfloat16* win, int rows, int r0, int mode, float* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* wsm = smem;               // window: rows x 128 bytes
+  uint8_t* bsm = smem + 256 * 128;   // identity: 64 rows x 128 bytes
+  for (int i = threadIdx.x; i < rows * 8; i += 128) {
+    const int r = i >> 3, c = i & 7;
+    *reinterpret_cast<uint4*>(wsm + ptx::sw128_offset((uint32_t)r, (uint32_t)c)) =
+        *reinterpret_cast<const uint4*>(win + (size_t)r * 64 + c * 8);
+  }
+  for (int i = threadIdx.x; i < 64 * 64; i += 128) {
+    const int n = i >> 6, k = i & 63;
+    reinterpret_cast<__nv_bfloat16*>(bsm + ptx::sw128_offset((uint32_t)n, (uint32_t)(k >> 3)))[k & 7] =
+        __float2bfloat16_rn(n == k ? 1.f : 0.f);
+  }
+  if (threadIdx.x == 0) { ptx::mbar_init(&bar, 1); ptx::fence_mbar_init(); }
+  if (warp == 1) { ptx::tmem_alloc(&tmem_base, 64); ptx::tmem_relinquish(); }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_base;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = ptx::umma_idesc_bf16_f32(128, 64);
+    const uint32_t a_addr = ptx::smem_u32(wsm) + (uint32_t)r0 * 128u, b_addr = ptx::smem_u32(bsm);
+    for (int k = 0; k < 4; ++k) {
+      uint64_t da = ptx::umma_desc_k_sw128(a_addr + k * 32);
+      if (mode == 1) da |= (uint64_t)((a_addr >> 7) & 7) << 49;
+      ptx::umma_bf16(tmem, da, ptx::umma_desc_k_sw128(b_addr + k * 32), idesc, k != 0);
+    }
+    ptx::umma_commit(&bar);
+  }
+  ptx::mbar_wait(&bar, 0);
+  ptx::tc_fence_after();
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    uint32_t r[16];
+    ptx::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
+    ptx::tmem_ld_wait();
+    for (int e = 0; e < 16; ++e) out[(size_t)(warp * 32 + lane) * 64 + c0 + e] = __uint_as_float(r[e]);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem, 64);
 }
 
 }  // namespace svsk
@@ -83,4 +183,13 @@ extern "C" SVSK_API int svsk_ubench_umma(int cta_group, int N, int iters, int ad
     if (e != cudaSuccess) return fail((int)e, "ubench_umma: %s", cudaGetErrorString(e));
   }
   return check_launch("ubench_umma");
+}
+
+extern "C" SVSK_API int svsk_ubench_rowshift(const void* win, int rows, int r0, int mode, float* out, void* stream) {
+  SVSK_REQUIRE(win && out && rows >= 128 && rows <= 256 && r0 >= 0 && r0 + 128 <= rows, SVSK_E_ARG, "ubench_rowshift: bad args");
+  int rc = require_sm100();
+  if (rc) return rc;
+  const int smem_bytes = 256 * 128 + 64 * 128 + 1024;
+  ubench_rowshift_kernel<<<1, 128, smem_bytes, as_stream(stream)>>>((const __nv_bfloat16*)win, rows, r0, mode, out);
+  return check_launch("ubench_rowshift");
 }

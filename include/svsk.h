@@ -189,8 +189,17 @@ SVSK_API int svsk_diffnet_block_bf16(const svsk_diffnet_block_params* p, void* s
 
 /* Same contract and packed operands, CTA-pair kernel (tcgen05 cta_group::2, clusters of 2): time is the MMA M
  * dimension (256 frames per pair), each SM stages half of every weight tile, N = 256 per MMA.  `time_tile` is ignored.
- * Additionally requires x32 / skip32 / xb_out to be 16-byte aligned.  This is the kernel the drop-in modules use. */
+ * Additionally requires x32 / skip32 / xb_out to be 16-byte aligned. */
 SVSK_API int svsk_diffnet_block2_bf16(const svsk_diffnet_block_params* p, void* stream);
+
+/* Same contract and packed operands again, CTA-pair kernel with a resident activation window: the three taps of the
+ * dilated conv (denoiser.py:33-35,58) are one (128 + 16)-row shared-memory tile per 64 channels addressed at row
+ * offsets -d / 0 / +d, so activations are read once per tile and only weights stream through the ring.  Requires
+ * dilation <= 8 (the reference's dilation_cycle_length = 4 gives 1, 2, 4, 8; use svsk_diffnet_block2_bf16 beyond).
+ * Launched with programmatic stream serialization: the packed weights w1p / woutp are read BEFORE the kernel waits for
+ * its predecessor in the stream, so they must not be written by the kernel launched immediately before this one
+ * (pack once, up front); every other operand may be.  This is the kernel the drop-in modules use. */
+SVSK_API int svsk_diffnet_block3_bf16(const svsk_diffnet_block_params* p, void* stream);
 
 /* Pack one block's weights (fp32, reference state_dict layout) for svsk_diffnet_block_bf16.
  *   dilated_w [2C][C][3], cond_w [2C][H][1], out_w [2C][C][1]  ->  w1p [2C][3C+H] bf16, woutp [2C][C] bf16.

@@ -367,17 +367,37 @@ def test_diffnet_block_bf16_single_layer(C, H, T, dil, tile):
     _, skip32 = ops.nct_to_ntc(skip0.to(DEV), want_bf16=False, want_f32=True)
     condb, _ = ops.nct_to_ntc(cond.to(DEV))
     sb = ops.linear_f32(dp.to(DEV), lw["stepw"], lw["stepb"])
-    xb_out = torch.full_like(xbd, float("nan"))
-    ops.diffnet_block_bf16(xbd, xb_out, x32, skip32, condb, lw["w1p"], lw["woutp"], sb, lw["bout"], dilation=dil,
-                           stepbias_batch_stride=6 * C, init_skip=False, write_x=True, time_tile=tile)
+    for kernel in ((1,) if tile else (3, 2)):   # 3 = resident window (default), 2 = every tap streamed, 1 = single CTA
+        xb_out = torch.full_like(xbd, float("nan"))
+        _, skip32 = ops.nct_to_ntc(skip0.to(DEV), want_bf16=False, want_f32=True)
+        ops.diffnet_block_bf16(xbd, xb_out, x32, skip32, condb, lw["w1p"], lw["woutp"], sb, lw["bout"], dilation=dil,
+                               stepbias_batch_stride=6 * C, init_skip=False, write_x=True, time_tile=tile, kernel=kernel)
+        torch.cuda.synchronize()
+        close_bf16(skip32.transpose(1, 2), s_ref, 3e-3, 1e-2)
+        if tile:   # single-CTA kernel: fp32 residual master + its bf16 copy
+            close_bf16(x32.transpose(1, 2), x_ref, 3e-3, 1e-2)
+            assert torch.equal(xb_out.float(), x32.to(torch.bfloat16).float())
+        else:      # CTA-pair kernels: the residual stream is carried in bf16 (reference: x_ref from bf16(x))
+            x_ref_b = (_bf(x) + o[:, :C]) / math.sqrt(2.0)
+            close_bf16(xb_out.float().transpose(1, 2), x_ref_b, 4e-3, 1e-2)
+
+
+def test_diffnet_block3_rejects_wide_dilation_and_default_falls_back():
+    """The resident window holds 8 halo rows: kernel 3 refuses dilation 16, the default selection uses kernel 2 there."""
+    ops = _ops()
+    C = 128
+    m = _random_diffnet(C, 64, 16, 1, seed=3).to(DEV)
+    lw = m.bf16_plan().layers[0]
+    xb = torch.zeros(1, 200, C, device=DEV, dtype=torch.bfloat16); out = torch.empty_like(xb)
+    x32 = torch.zeros(1, 200, C, device=DEV); skip = torch.zeros(1, 200, C, device=DEV)
+    cond = torch.zeros(1, 200, 64, device=DEV, dtype=torch.bfloat16)
+    sb = torch.zeros(1, 6 * C, device=DEV)
+    kw = dict(dilation=16, stepbias_batch_stride=6 * C, init_skip=True, write_x=True)
+    with pytest.raises(RuntimeError, match="resident window"):
+        ops.diffnet_block_bf16(xb, out, x32, skip, cond, lw["w1p"], lw["woutp"], sb, lw["bout"], kernel=3, **kw)
+    ops.diffnet_block_bf16(xb, out, x32, skip, cond, lw["w1p"], lw["woutp"], sb, lw["bout"], **kw)
     torch.cuda.synchronize()
-    close_bf16(skip32.transpose(1, 2), s_ref, 3e-3, 1e-2)
-    if tile:   # single-CTA kernel: fp32 residual master + its bf16 copy
-        close_bf16(x32.transpose(1, 2), x_ref, 3e-3, 1e-2)
-        assert torch.equal(xb_out.float(), x32.to(torch.bfloat16).float())
-    else:      # CTA-pair kernel: the residual stream is carried in bf16 (reference: x_ref from bf16(x))
-        x_ref_b = (_bf(x) + o[:, :C]) / math.sqrt(2.0)
-        close_bf16(xb_out.float().transpose(1, 2), x_ref_b, 4e-3, 1e-2)
+    assert torch.isfinite(out.float()).all()
 
 
 def test_diffnet_bf16_forward_vs_oracle():

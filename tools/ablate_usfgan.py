@@ -19,7 +19,7 @@ b1 = torch.zeros(128, device="cuda"); bo = torch.zeros(64, device="cuda")
 d = torch.empty(B, 1, T, device="cuda").uniform_(2, 40)
 idx = ops.pd_index(d, 4)
 for name, kw in (("fixed d=8", dict(dilation=8)), ("adaptive", dict(idx=idx))):
-    for ab in ((0,) if KERNEL == 2 else (0, 1)):
+    for ab in ((0,) if KERNEL == 2 else (0, 1, 4, 5, 8, 9)):
         os.environ["SVSK_USFGAN_ABLATE"] = str(ab)
         for _ in range(2):
             ops.usfgan_block_bf16(xb, out, auxb, w1p, woutp, b1, bo, kernel=KERNEL, **kw)
@@ -30,15 +30,16 @@ for name, kw in (("fixed d=8", dict(dilation=8)), ("adaptive", dict(idx=idx))):
             ops.usfgan_block_bf16(xb, out, auxb, w1p, woutp, b1, bo, kernel=KERNEL, **kw)
         e1.record(); e1.synchronize()
         us = e0.elapsed_time(e1) / 5 * 1e3
-        print(f"{name:10s} ablate={ab:2d} (1=no epilogue, 64=MMAs twice, 128=MMA thread skips operand waits): {us:7.1f} us  "
+        print(f"{name:10s} ablate={ab:2d} (1=no epilogue, 4=no MMAs, 8=no TMA loads): {us:7.1f} us  "
               f"-> {us * 1e-6 * 1.85e9 / (B * ((T + 127) // 128) / 148):6.0f} cycles/tile", flush=True)
 
 # role accounting (cycles per tile, averaged over CTAs)
 if KERNEL == 2:
     sys.exit(0)
 names = ["prod wait empty", "mma wait operands", "mma wait G", "mma loop total", "tiles", "epi wait D1", "epi gating",
-         "epi wait D2", "epi residual", "epi sync/store", "mma fence_after", "mma commit/arrive"]
-for ab, name, kw in ((0, "fixed d=8", dict(dilation=8)), (64, "fixed 2x MMAs", dict(dilation=8))):
+         "epi wait D2", "epi residual", "epi sync/store", "mma fence_after", "mma commit/arrive", "mma probe", "mma issue"]
+for ab, name, kw in ((0, "fixed d=8", dict(dilation=8)), (0, "adaptive", dict(idx=idx)), (4, "fixed, no MMAs", dict(dilation=8)),
+                     (5, "fixed, no MMAs/epilogue", dict(dilation=8))):
     os.environ["SVSK_USFGAN_ABLATE"] = str(ab)
     dbg = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
     os.environ["SVSK_USFGAN_TIMELINE"] = str(dbg.data_ptr())

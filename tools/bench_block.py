@@ -22,13 +22,13 @@ xb1 = torch.empty_like(xb0)
 x32 = torch.randn(B, T, plan.C, device="cuda")
 skip32 = torch.zeros(B, T, plan.C, device="cuda")
 flops = 2.0 * B * T * bench.BLOCK_MAC_PER_FRAME
-for tile in (0, 96, 128):
+for tile, kernel in ((0, 3), (0, 2), (96, 1)):
     def blocks():
         cur, nxt = xb0, xb1
         for i, lw in enumerate(plan.layers):
             ops.diffnet_block_bf16(cur, nxt, x32, skip32, cond, lw["w1p"], lw["woutp"], sb[i], lw["bout"],
                                    dilation=lw["dilation"], stepbias_batch_stride=0, init_skip=(i == 0), write_x=True,
-                                   time_tile=tile, kernel=(2 if tile == 0 else 1))
+                                   time_tile=tile, kernel=kernel)
             cur, nxt = nxt, cur
     for _ in range(3):
         blocks()
@@ -40,4 +40,4 @@ for tile in (0, 96, 128):
     e1.record()
     e1.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / 200
-    print(f"B={B} T={T} tile={tile:3d}: {us:7.2f} us/launch  {flops / us / 1e6:7.1f} TFLOP/s", flush=True)
+    print(f"B={B} T={T} kernel={kernel} tile={tile:3d}: {us:7.2f} us/launch  {flops / us / 1e6:7.1f} TFLOP/s", flush=True)

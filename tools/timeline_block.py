@@ -39,21 +39,34 @@ def run(layer, tile, ablate, kernel=1):
         launch()
     e1.record(); e1.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / 50
-    dbg = torch.zeros(512 * 16, dtype=torch.int64, device="cuda")
+    dbg = torch.zeros(512 * 32, dtype=torch.int64, device="cuda")
     os.environ["SVSK_DIFFNET_TIMELINE"] = str(dbg.data_ptr())
     launch()
     torch.cuda.synchronize()
     os.environ.pop("SVSK_DIFFNET_TIMELINE", None)
-    d = dbg.view(512, 16).cpu()
+    d = dbg.view(512, 32).cpu()
     d = d[d[:, 15] > 0]
-    if kernel == 2:
+    if kernel >= 2:
         d = d[d[:, 2] > 0]   # leader CTAs carry the MMA stamps
-    rel = (d - d[:, :1]).float()
+    rel = (d[:, :16] - d[:, :1]).float()
     med = rel.median(dim=0).values
+    acc = d[:, 16:20].float().median(dim=0).values
     print(f"--- kernel {kernel} layer {layer} (dil {lw['dilation']}) tile {tile} ablate {ablate}: {us:.2f} us/launch, {d.shape[0]} CTAs; "
           f"median cycles since CTA start:")
     print("   " + "  ".join(f"{n}={int(v)}" for n, v in zip(names, med)))
+    if kernel == 3:
+        st = (d[:, 19:24] - d[:, :1]).float().median(dim=0).values
+        print("   kernel 3 (leader CTA, cycles): producer wait empty=%d | mma blocking waits (probe misses)=%d | "
+              "grid dependency resolved @%d | MMA thread starts @%d | first cond tile landed @%d | cond k-blocks issued @%d | window landed @%d"
+              % (int(acc[0]), int(acc[1]), int(st[2]), int(st[3]), int(st[4]), int(st[0]), int(st[1])))
+    if kernel == 2:
+        print("   GEMM1 accounting (leader CTA, cycles): producer wait empty=%d | mma wait own stage=%d | mma wait peer stage=%d | "
+              "mma issue+commit=%d" % tuple(int(v) for v in acc))
 
 
 for ab in (0,):
-    run(1, 0, ab, kernel=2)
+    run(1, 0, ab, kernel=3)
+os.environ['SVSK_NO_PDL'] = '1'
+run(1, 0, 0, kernel=3)
+os.environ.pop('SVSK_NO_PDL')
+run(1, 0, 0, kernel=2)

@@ -26,3 +26,29 @@ for grid in (2, 148):
             print(f"grid={grid:3d} cta_group={cg} M={M} N={N:3d} advance={adv}: issue {o[:, 0].mean() / iters:6.1f} "
                   f"cyc/MMA, complete {o[:, 1].mean() / iters:6.1f} cyc/MMA (nominal {nominal:.0f}); "
                   f"operand bytes/MMA/SM = {(128 + (N if cg == 1 else N // 2)) * 32}", flush=True)
+
+# commit latency: groups of G MMAs + commit + wait, serially
+for cg, N in ((1, 128), (2, 256)):
+    for G in (1, 4, 8):
+        out = torch.zeros(4, dtype=torch.int64, device="cuda")
+        it = 500
+        rc = l.svsk_ubench_umma(cg, N, it, 16 + G - 1, 2, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, l.svsk_last_error()
+        torch.cuda.synchronize()
+        per = float(out[0]) / it
+        nominal = 128 * cg * N / (256 * cg) * G
+        print(f"serial cta_group={cg} N={N} group={G}: {per:7.1f} cycles per (group + commit + wait); MMAs nominal {nominal:.0f} "
+              f"-> commit-to-visible latency ~ {per - nominal:.0f} cycles", flush=True)
+
+# issue loop with per-group extras (see ubench_sm100.cu): does anything in the MMA thread's loop stall behind the MMAs?
+names = {0: "MMAs only", 4: "+commit", 1: "+2 try_wait", 9: "+2 test_wait", 3: "+2 try_wait +fence", 7: "+2 try_wait +fence +commit",
+         15: "+2 test_wait +fence +commit", 6: "+fence +commit"}
+for cg, N in ((1, 128), (2, 256)):
+    for v, nm in names.items():
+        out = torch.zeros(4, dtype=torch.int64, device="cuda")
+        it = 500
+        rc = l.svsk_ubench_umma(cg, N, it, 32 + v, 2, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, l.svsk_last_error()
+        torch.cuda.synchronize()
+        print(f"issue loop cta_group={cg} N={N} [{nm:32s}]: issue {float(out[0]) / it:7.1f}  complete {float(out[1]) / it:7.1f} cycles per "
+              f"group of 4 MMAs (nominal {4 * 128 * N // 256})", flush=True)
