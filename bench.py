@@ -275,19 +275,29 @@ def main():
         sec, gpu_launches = timed(one_pass_resident, args.warmup, args.steps)   # libsvsk launches, timed region only
         sec_e2e, _ = timed(one_pass_e2e, 1, args.steps)
 
-    # dominant kernel: the fused block (20 launches per DDPM step).  Timed live: 10 x 20 launches between two events.
+    # dominant kernel: the residual stack.  When all its CTA pairs fit the device (they do at config 2) the 20 blocks of
+    # one denoiser call are ONE launch (diffnet_stack_kernel); otherwise 20 launches of the per-layer kernel.  Timed
+    # live: 10 denoiser calls' worth between two events on the launching stream.
     plan = den.bf16_plan()
     from ensemble_svs_with_interactions_b200 import ops
     condb, _ = ops.nct_to_ntc(cond_dev.transpose(1, 2).contiguous())
-    x32s = torch.randn(B, T, plan.Mp, device=dev)
     table = m._step_table()
     sb = [tl[50] for tl in table]
     xb0 = torch.randn(B, T, plan.C, device=dev).to(torch.bfloat16)
     xb1 = torch.empty_like(xb0)
+    xb2 = torch.empty_like(xb0)
     x32 = torch.randn(B, T, plan.C, device=dev)
     skip32 = torch.zeros(B, T, plan.C, device=dev)
+    flags = torch.empty((B * 2 * ((T + 255) // 256),), device=dev, dtype=torch.int32)
+    use_stack = (max(plan.dilations) <= 8 and os.environ.get("SVSK_DIFFNET_STACK", "1") != "0"
+                 and ops.diffnet_stack_fits(B, T, plan.C, plan.H))
 
     def blocks():
+        if use_stack:
+            ops.diffnet_stack_bf16(xb0, xb1, xb2, skip32, condb, plan.w1p_all, plan.woutp_all, table[:, 50:51],
+                                   plan.bout_all, flags, plan.dilations, stepbias_batch_stride=0,
+                                   stepbias_layer_stride=table.stride(0))
+            return
         cur, nxt = xb0, xb1
         for i, lw in enumerate(plan.layers):
             ops.diffnet_block_bf16(cur, nxt, x32, skip32, condb, lw["w1p"], lw["woutp"], sb[i], lw["bout"],
@@ -304,8 +314,9 @@ def main():
         blocks()
     e1.record()
     e1.synchronize()
-    block_ms = e0.elapsed_time(e1) / (reps * len(plan.layers))
-    flops_per_launch = 2.0 * B * T * BLOCK_MAC_PER_FRAME
+    launches_per_call = 1 if use_stack else len(plan.layers)
+    block_ms = e0.elapsed_time(e1) / (reps * launches_per_call)
+    flops_per_launch = 2.0 * B * T * BLOCK_MAC_PER_FRAME * (len(plan.layers) if use_stack else 1)
     peaks = _peaks()
     peak_tf = (peaks or {}).get("bf16_tflops_sustained", 1400.0)
     achieved_tf = flops_per_launch / (block_ms * 1e-3) / 1e12
@@ -332,7 +343,9 @@ def main():
             "clocks": clk.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf,
-                         "traffic": _ncu_traffic("r01h_block2_ncu_full_summary.json"), "kernel": "diffnet_block2_kernel (CTA pair, tcgen05 cta_group::2)",
+                         "traffic": _ncu_traffic("r01x_stack_ncu_full_summary.json" if use_stack else "r01h_block2_ncu_full_summary.json"),
+                         "kernel": ("diffnet_stack_kernel (all 20 residual blocks in one launch; CTA pairs, tcgen05 cta_group::2)"
+                                    if use_stack else "diffnet_block3_kernel (one residual block; CTA pairs, tcgen05 cta_group::2)"),
                          "us_per_launch": block_ms * 1e3, "flops_per_launch": flops_per_launch,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400"},
             "whole_pass_tflops": 2.0 * MAC_PER_FRAME_STEP * B * T * K_STEP * args.steps * world / sec / 1e12,

@@ -39,6 +39,16 @@ class DiffnetBlockParams(C.Structure):
     ]
 
 
+class DiffnetStackParams(C.Structure):
+    _fields_ = [
+        ("xb_in", C.c_void_p), ("edge0", C.c_void_p), ("edge1", C.c_void_p), ("skip32", C.c_void_p),
+        ("cond", C.c_void_p), ("w1p", C.c_void_p), ("woutp", C.c_void_p), ("stepbias", C.c_void_p),
+        ("bout", C.c_void_p), ("flags", C.c_void_p), ("dilation", C.POINTER(C.c_int32)),
+        ("B", C.c_int32), ("T", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("L", C.c_int32),
+        ("stepbias_batch_stride", C.c_int32), ("stepbias_layer_stride", C.c_int32), ("init_skip", C.c_int32),
+    ]
+
+
 class LinearBf16Params(C.Structure):
     _fields_ = [
         ("a", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("y_bf16", C.c_void_p), ("y_f32", C.c_void_p),
@@ -90,6 +100,8 @@ _SIGNATURES = {
     "svsk_diffnet_block_bf16": [C.POINTER(DiffnetBlockParams), _V],
     "svsk_diffnet_block2_bf16": [C.POINTER(DiffnetBlockParams), _V],
     "svsk_diffnet_block3_bf16": [C.POINTER(DiffnetBlockParams), _V],
+    "svsk_diffnet_stack_bf16": [C.POINTER(DiffnetStackParams), _V],
+    "svsk_diffnet_stack_fits": [C.c_int, C.c_int, C.c_int, C.c_int],
     "svsk_diffnet_pack_block": [_V, _V, _V, _V, _V, _I, _I, _V],
     "svsk_diffnet_packed_row": [_I, _I],
     "svsk_linear_bf16": [C.POINTER(LinearBf16Params), _V],

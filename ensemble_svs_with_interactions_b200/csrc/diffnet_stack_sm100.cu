@@ -1,0 +1,715 @@
+// The whole DiffNet residual stack in ONE launch: replaces the loop over ResidualBlock.forward in DiffNet.forward
+// (nnsvs/diffsinger/denoiser.py:114-118; block maths denoiser.py:54-66) for all L layers of one denoiser call.
+//
+// Why: the per-layer kernel (diffnet_block3_sm100.cu) computes for 20.5 k tensor-pipe cycles out of a 50 k-cycle
+// launch period (profiles/r01w_timeline_v3.log): 6 k cycles pass before the first MMA (barrier/TMEM set-up, cluster
+// sync, first loads), 5 k between a CTA's exit and its successor's start, the skip epilogue (6.7 k) runs with the
+// tensor pipe idle.  At the reference workload (6 tracks x 2000 frames) there is exactly one 128-frame tile per SM, so
+// every CTA can simply KEEP its tile for all layers:
+//   * set-up once per call instead of once per layer;
+//   * the centre rows of the activation window are updated in place by the residual epilogue and are already the next
+//     layer's centre tap: only the 8 halo rows either side come from the neighbouring tiles, through global memory
+//     (8 edge rows per side TMA-stored per layer, a per-tile layer counter with release/acquire semantics, the
+//     neighbour TMA-loads them into its window's halo rows);
+//   * the next layer's weights stream in while the skip epilogue of this layer drains TMEM: GEMM1 of layer l+1 starts
+//     on the first 256 TMEM columns as soon as the residual half has been read out.
+// Everything else (operand layouts, row-offset tap descriptors, gating, TMA epilogues) is the per-layer kernel's.
+//
+// Per layer, ring entries (16 KB weight tiles) in this order — producer, MMA issuer and the peer's forwarder agree:
+//   0: centre tap, block 0        (A = window rows 8..135, needs only this CTA pair's own previous epilogue)
+//   1: side taps, block 0         (A = window at rows 8 -/+ d, needs the neighbours' edge rows of the previous layer)
+//   2: conditioner, blocks 0..NB-1 (A = conditioner tiles in the G buffer, which the previous skip epilogue released)
+//   3: all taps, blocks 1..NB-1
+//   4: output projection, blocks 0..NB-1 (A = G)
+// Warps: 0 = weight producer (both CTAs), 1 = MMA issuer (leader) / forwarder (peer) + TMEM owner, 2..9 = epilogue,
+// 10 = activation producer (conditioner tiles, window / halo rows, edge-row publication).
+// All CTAs must be co-resident (neighbours wait for each other): the host entry checks the grid against
+// cudaOccupancyMaxActiveClusters and refuses otherwise (callers fall back to one svsk_diffnet_block3_bf16 per layer).
+#include <cuda_bf16.h>
+#include <cstdlib>
+
+#include "sm100_ptx.cuh"
+#include "svsk_common.cuh"
+#include "tma_util.cuh"
+
+namespace svsk {
+
+constexpr int kSTile = 128 * 128;            // 128 rows x 64 bf16
+constexpr int kSHalo = 8;                    // window rows either side of the tile: dilation <= 8
+constexpr int kSWinRows = 128 + 2 * kSHalo;
+constexpr int kSWinBytes = kSWinRows * 128;  // 18 KB, a multiple of the 1024-byte swizzle atom
+constexpr int kSHaloBytes = kSHalo * 128;    // 1 KB per window tile and side
+constexpr int kSMaxEntries = 8;
+constexpr int kSSmemLimit = 232448;
+constexpr int kSTmemCols = 512;
+constexpr int kSThreads = 352;
+constexpr int kSMaxLayers = 64;
+
+struct DiffnetStackArgs {
+  const float* stepbias;  // [batch][layer][6C] (strides below)
+  const float* bout;      // [layer][2C]
+  int* flags;             // [B * tiles_per_track] layers published per tile; zero at launch
+  int proxy_fence;        // 1: fence.proxy.async.global around the flag hand-over (default); 0: profiling experiment
+  int B, T, C, H, L, sb_batch_stride, sb_layer_stride, init_skip, nentries, tiles_per_track;
+  int dilation[kSMaxLayers];
+  unsigned long long* dbg;
+};
+
+struct __align__(8) DiffnetStackBarriers {
+  uint64_t full[kSMaxEntries];  // ring entry landed: own TMA bytes, and on the leader also the peer's (forwarded) arrival
+  uint64_t empty[kSMaxEntries];
+  uint64_t cd_full[8];          // conditioner tile hb of this layer landed (leader: in both CTAs)
+  uint64_t xw_full;             // layer 0: whole window landed; later layers: halo rows landed (leader: in both CTAs)
+  uint64_t xc_ready;            // leader: centre rows updated in place by every epilogue thread of both CTAs
+  uint64_t xe_ready;            // this CTA's centre rows updated (-> activation producer publishes the edge rows)
+  uint64_t d1_full[2];
+  uint64_t d2_full[2];
+  uint64_t d2_drained[2];       // leader: every epilogue thread of both CTAs has read block j out of TMEM
+  uint64_t g_ready;
+  uint64_t gc_free;             // this CTA's G buffer is free again (skip slabs read by the TMA unit)
+  uint32_t tmem_base;
+};
+
+// ring entry i of a layer -> which weight tile (see the order in the header comment)
+__device__ __forceinline__ void stack_entry(int i, int CB, int HB, int NB, int KB2, int& kcol, int& blk, bool& wout) {
+  wout = false;
+  if (i < CB) { kcol = CB + i; blk = 0; return; }
+  i -= CB;
+  if (i < 2 * CB) { kcol = (i / CB) * 2 * CB + i % CB; blk = 0; return; }
+  i -= 2 * CB;
+  if (i < HB * NB) { kcol = 3 * CB + i / NB; blk = i % NB; return; }
+  i -= HB * NB;
+  if (i < (NB - 1) * 3 * CB) { blk = 1 + i / (3 * CB); kcol = i % (3 * CB); return; }
+  i -= (NB - 1) * 3 * CB;
+  wout = true;
+  blk = i / KB2;
+  kcol = i % KB2;
+}
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kSThreads, 1)
+diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_constant__ CUtensorMap tm_e0,
+                     const __grid_constant__ CUtensorMap tm_e1, const __grid_constant__ CUtensorMap tm_cond,
+                     const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_wout,
+                     const __grid_constant__ CUtensorMap tm_skip, const DiffnetStackArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int C = a.C, H = a.H, T = a.T, L = a.L;
+  const int CB = C / 64, HB = H / 64;
+  const int KB2 = CB;
+  const int NB = (2 * C) / 256;  // 256-column output blocks of either GEMM
+  const int twoC = 2 * C;
+  uint8_t* xw_smem = smem;                         // CB window tiles
+  uint8_t* g_smem = xw_smem + CB * kSWinBytes;     // max(HB, KB2, 4) tiles: conditioner tiles, then G, then skip slabs
+  uint8_t* ring = g_smem + max(max(HB, KB2), 4) * kSTile;  // nentries x 16 KB (the G buffer holds >= 4 skip slabs)
+  float* sb_full = reinterpret_cast<float*>(ring + a.nentries * kSTile);
+  float* sb_l = sb_full + twoC;
+  float* sb_r = sb_l + twoC;
+  float* bo_s = sb_r + twoC;
+  DiffnetStackBarriers* bars = reinterpret_cast<DiffnetStackBarriers*>(bo_s + twoC);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int b = blockIdx.y;
+  const int t_cta0 = (blockIdx.x >> 1) * 256 + (int)rank * 128;  // first frame of this CTA's 128 TMEM lanes
+  const int w_row0 = (int)rank * 128;                             // this CTA's half of a 256-row weight block
+  const int n_layer = NB * (3 * CB + HB) + NB * KB2;              // ring entries per layer
+  const int n_total = L * n_layer;
+  unsigned long long* dbg = a.dbg ? a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 32 : nullptr;
+#define SVSK_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
+  if (threadIdx.x == 0) SVSK_STAMP(0);
+
+  int pre_issued = 0;  // weight producer: entries issued before the CTA-wide sync
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_xw0);
+    ptx::prefetch_tmap(&tm_e0);
+    ptx::prefetch_tmap(&tm_e1);
+    ptx::prefetch_tmap(&tm_cond);
+    ptx::prefetch_tmap(&tm_w1);
+    ptx::prefetch_tmap(&tm_wout);
+    ptx::prefetch_tmap(&tm_skip);
+    const uint32_t two = rank == 0 ? 2u : 1u;        // leader barriers also count the peer's forwarded arrival
+    const uint32_t all = rank == 0 ? 2u * 256u : 1u; // leader barriers every epilogue thread of the pair arrives on
+    for (int i = 0; i < a.nentries; ++i) {
+      ptx::mbar_init(&bars->full[i], two);
+      ptx::mbar_init(&bars->empty[i], 1);  // one multicast tcgen05.commit
+    }
+    for (int i = 0; i < HB; ++i) ptx::mbar_init(&bars->cd_full[i], two);
+    ptx::mbar_init(&bars->xw_full, two);
+    ptx::mbar_init(&bars->xc_ready, all);
+    ptx::mbar_init(&bars->xe_ready, 256);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bars->d1_full[i], 1);
+      ptx::mbar_init(&bars->d2_full[i], 1);
+      ptx::mbar_init(&bars->d2_drained[i], all);
+    }
+    ptx::mbar_init(&bars->g_ready, all);
+    ptx::mbar_init(&bars->gc_free, 1);
+    ptx::fence_mbar_init();
+    pre_issued = min(a.nentries, n_total);
+    for (int e = 0; e < pre_issued; ++e) {
+      int kcol, blk;
+      bool wout;
+      stack_entry(e, CB, HB, NB, KB2, kcol, blk, wout);
+      ptx::mbar_arrive_expect_tx(&bars->full[e], kSTile);
+      ptx::tma_load_3d(ring + e * kSTile, wout ? &tm_wout : &tm_w1, &bars->full[e], kcol * 64, blk * 256 + w_row0, 0);
+    }
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc2(&bars->tmem_base, kSTmemCols);
+    ptx::tmem_relinquish2();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ weight producer (both CTAs)
+    if (lane == 0) {
+      int s = pre_issued % a.nentries;
+      uint32_t ph = (pre_issued == a.nentries) ? 1u : 0u;
+      int l = pre_issued / n_layer, i = pre_issued - l * n_layer;
+      for (int e = pre_issued; e < n_total; ++e) {
+        ptx::mbar_wait(&bars->empty[s], ph ^ 1);
+        int kcol, blk;
+        bool wout;
+        stack_entry(i, CB, HB, NB, KB2, kcol, blk, wout);
+        ptx::mbar_arrive_expect_tx(&bars->full[s], kSTile);
+        ptx::tma_load_3d(ring + s * kSTile, wout ? &tm_wout : &tm_w1, &bars->full[s], kcol * 64, blk * 256 + w_row0, l);
+        if (++s == a.nentries) { s = 0; ph ^= 1; }
+        if (++i == n_layer) { i = 0; ++l; }
+      }
+    }
+  } else if (warp == 10) {
+    // ------------------------------------------------------------------ activation producer (both CTAs)
+    if (lane == 0) {
+      const int tile_idx = b * a.tiles_per_track + (t_cta0 >> 7);
+      const bool has_left = t_cta0 > 0, has_right = t_cta0 + 128 < T;
+      // layer 0: conditioner tiles and the whole window of the stack's input
+      for (int hb = 0; hb < HB; ++hb) {
+        ptx::mbar_arrive_expect_tx(&bars->cd_full[hb], kSTile);
+        ptx::tma_load_3d(g_smem + hb * kSTile, &tm_cond, &bars->cd_full[hb], hb * 64, t_cta0, b);
+      }
+      ptx::mbar_arrive_expect_tx(&bars->xw_full, CB * kSWinBytes);
+      for (int cb = 0; cb < CB; ++cb)
+        ptx::tma_load_3d(xw_smem + cb * kSWinBytes, &tm_xw0, &bars->xw_full, cb * 64, t_cta0 - kSHalo, b);
+      for (int l = 1; l < L; ++l) {
+        const uint32_t pp = (uint32_t)(l - 1) & 1u;
+        const CUtensorMap* tm_e = pp ? &tm_e1 : &tm_e0;
+        // publish the first / last 8 rows of layer l-1's output (the epilogue has written them in place)
+        ptx::mbar_wait(&bars->xe_ready, pp);
+        if (l == 1) SVSK_STAMP(9);
+        for (int cb = 0; cb < CB; ++cb) {
+          uint8_t* centre = xw_smem + cb * kSWinBytes + kSHalo * 128;
+          ptx::tma_store_3d(tm_e, centre, cb * 64, t_cta0, b);
+          ptx::tma_store_3d(tm_e, centre + (128 - kSHalo) * 128, cb * 64, t_cta0 + 128 - kSHalo, b);
+        }
+        ptx::bulk_commit_group();
+        ptx::bulk_wait_all();  // the stores are complete (not merely read out of shared memory)
+        if (l == 1) SVSK_STAMP(10);
+        if (a.proxy_fence) fence_proxy_async_global();
+        st_release_gpu(a.flags + tile_idx, l);
+        if (l == 1) SVSK_STAMP(11);
+        // halo rows of layer l's input: the neighbours' edge rows of layer l-1's output
+        for (uint32_t spin = 0;; ++spin) {  // both flags per round trip, relaxed; one acquire fence at the end
+          const int fl = has_left ? ld_relaxed_gpu(a.flags + tile_idx - 1) : l;
+          const int fr = has_right ? ld_relaxed_gpu(a.flags + tile_idx + 1) : l;
+          if (fl >= l && fr >= l) break;
+          if (spin > (1u << 21)) __trap();
+        }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        if (l == 1) SVSK_STAMP(12);
+        if (a.proxy_fence) fence_proxy_async_global();
+        ptx::mbar_arrive_expect_tx(&bars->xw_full, 2 * CB * kSHaloBytes);
+        for (int cb = 0; cb < CB; ++cb) {
+          uint8_t* tile = xw_smem + cb * kSWinBytes;
+          ptx::tma_load_3d(tile, tm_e, &bars->xw_full, cb * 64, t_cta0 - kSHalo, b);
+          ptx::tma_load_3d(tile + (kSHalo + 128) * 128, tm_e, &bars->xw_full, cb * 64, t_cta0 + 128, b);
+        }
+        if (l == 1) SVSK_STAMP(13);
+        // conditioner tiles of layer l, once the G buffer is free again
+        ptx::mbar_wait(&bars->gc_free, pp);
+        if (l == 1) SVSK_STAMP(14);
+        for (int hb = 0; hb < HB; ++hb) {
+          ptx::mbar_arrive_expect_tx(&bars->cd_full[hb], kSTile);
+          ptx::tma_load_3d(g_smem + hb * kSTile, &tm_cond, &bars->cd_full[hb], hb * 64, t_cta0, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer: one thread of the leader CTA
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16_f32(256, 256);
+      const uint32_t ring_lo = ptx::umma_desc_lo(ptx::smem_u32(ring)), g_lo = ptx::umma_desc_lo(ptx::smem_u32(g_smem));
+      const uint32_t xw_lo = ptx::umma_desc_lo(ptx::smem_u32(xw_smem));
+      int s = 0;
+      uint32_t ph = 0;
+      bool ready = false;  // the barrier of ring entry (s, ph) was already seen complete by the previous group's probe
+      // An mbarrier wait whose result is needed at once stalls this thread ~160 cycles even on a long-completed phase
+      // (tools/ubench_umma.py): every MMA group therefore probes the NEXT entry's barrier while its MMAs are issued.
+#define SVSK_WAIT_ENTRY()                                 \
+  do {                                                    \
+    if (!ready) ptx::mbar_wait(&bars->full[s], ph);       \
+    ready = false;                                        \
+    ptx::tc_fence_after();                                \
+  } while (0)
+#define SVSK_NEXT_ENTRY() do { if (++s == a.nentries) { s = 0; ph ^= 1; } } while (0)
+#define SVSK_ISSUE4(dcol, alo, blo, acc0)                                                                          \
+  do {                                                                                                             \
+    const int sn = (s + 1 == a.nentries) ? 0 : s + 1;                                                              \
+    ready = ptx::umma2_bf16_x4_probe(tmem + (dcol), alo, blo, idesc, acc0, 4, &bars->full[sn], sn ? ph : ph ^ 1);  \
+    ptx::umma_commit2_mc(&bars->empty[s], 3);                                                                      \
+    SVSK_NEXT_ENTRY();                                                                                             \
+  } while (0)
+      for (int l = 0; l < L; ++l) {
+        const uint32_t pl = (uint32_t)l & 1u, pp = pl ^ 1u;
+        const int d = a.dilation[l];
+        // ---- centre tap, block 0
+        if (l == 0) {
+          ptx::mbar_wait(&bars->xw_full, 0);
+        } else {
+          ptx::mbar_wait(&bars->xc_ready, pp);      // centre rows rewritten in place by the previous layer's epilogue
+          ptx::mbar_wait(&bars->d2_drained[0], pp); // and the first 256 TMEM columns read out
+        }
+        ptx::tc_fence_after();
+        if (l == 1) SVSK_STAMP(2);
+        for (int cb = 0; cb < CB; ++cb) {
+          SVSK_WAIT_ENTRY();
+          SVSK_ISSUE4(0, xw_lo + cb * (kSWinBytes >> 4) + kSHalo * 8, ring_lo + s * (kSTile >> 4), cb != 0);
+        }
+        // ---- side taps, block 0
+        if (l != 0) {
+          ptx::mbar_wait(&bars->xw_full, pl);  // halo rows of this layer
+          ptx::tc_fence_after();
+        }
+        if (l == 1) SVSK_STAMP(3);
+        for (int jt = 0; jt < 3; jt += 2) {
+          const uint32_t row_lo = xw_lo + (uint32_t)(kSHalo + (jt - 1) * d) * 8u;
+          for (int cb = 0; cb < CB; ++cb) {
+            SVSK_WAIT_ENTRY();
+            SVSK_ISSUE4(0, row_lo + cb * (kSWinBytes >> 4), ring_lo + s * (kSTile >> 4), 1);
+          }
+        }
+        // ---- conditioner k-blocks out of the (future) G buffer, all output blocks per tile
+        for (int hb = 0; hb < HB; ++hb) {
+          ptx::mbar_wait(&bars->cd_full[hb], pl);
+          if (hb == 0 && l != 0 && NB > 1) ptx::mbar_wait(&bars->d2_drained[1], pp);
+          ptx::tc_fence_after();
+          if (l == 1 && hb == 0) SVSK_STAMP(4);
+          const uint32_t a_lo = g_lo + hb * (kSTile >> 4);
+          for (int j = 0; j < NB; ++j) {
+            SVSK_WAIT_ENTRY();
+            SVSK_ISSUE4(j * 256, a_lo, ring_lo + s * (kSTile >> 4), (j == 0 || hb != 0) ? 1 : 0);
+          }
+        }
+        ptx::umma_commit2_mc(&bars->d1_full[0], 3);
+        if (l == 1) SVSK_STAMP(5);
+        // ---- all taps, blocks 1..
+        for (int j = 1; j < NB; ++j) {
+          for (int jt = 0; jt < 3; ++jt) {
+            const uint32_t row_lo = xw_lo + (uint32_t)(kSHalo + (jt - 1) * d) * 8u;
+            for (int cb = 0; cb < CB; ++cb) {
+              SVSK_WAIT_ENTRY();
+              SVSK_ISSUE4(j * 256, row_lo + cb * (kSWinBytes >> 4), ring_lo + s * (kSTile >> 4), 1);
+            }
+          }
+          ptx::umma_commit2_mc(&bars->d1_full[j], 3);
+        }
+        if (l == 1) SVSK_STAMP(6);
+        // ---- GEMM2
+        ptx::mbar_wait(&bars->g_ready, pl);
+        ptx::tc_fence_after();
+        if (l == 1) SVSK_STAMP(7);
+        for (int j = 0; j < NB; ++j) {
+          for (int kb = 0; kb < KB2; ++kb) {
+            SVSK_WAIT_ENTRY();
+            SVSK_ISSUE4(j * 256, g_lo + kb * (kSTile >> 4), ring_lo + s * (kSTile >> 4), kb != 0);
+          }
+          ptx::umma_commit2_mc(&bars->d2_full[j], 3);
+        }
+        if (l == 1) SVSK_STAMP(8);
+      }
+#undef SVSK_WAIT_ENTRY
+#undef SVSK_NEXT_ENTRY
+#undef SVSK_ISSUE4
+    } else if (rank == 1 && lane == 0) {
+      // peer CTA: second arrival on the leader's barriers ("mine has landed too"), in the order the leader waits
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t leader_full0 = ptx::mapa(ptx::smem_u32(&bars->full[0]), 0);
+      for (int l = 0; l < L; ++l) {
+        const uint32_t pl = (uint32_t)l & 1u;
+        int i = 0;
+        auto forward_entries = [&](int n) {
+          for (int k = 0; k < n; ++k, ++i) {
+            ptx::mbar_wait(&bars->full[s], ph);
+            ptx::mbar_arrive_cluster(leader_full0 + (uint32_t)s * 8u);
+            if (++s == a.nentries) { s = 0; ph ^= 1; }
+          }
+        };
+        auto forward_xw = [&]() {
+          ptx::mbar_wait(&bars->xw_full, pl);
+          ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->xw_full), 0));
+        };
+        if (l == 0) forward_xw();
+        forward_entries(CB);
+        if (l != 0) forward_xw();
+        forward_entries(2 * CB);
+        for (int hb = 0; hb < HB; ++hb) {
+          ptx::mbar_wait(&bars->cd_full[hb], pl);
+          ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->cd_full[hb]), 0));
+          forward_entries(NB);
+        }
+        forward_entries((NB - 1) * 3 * CB + NB * KB2);
+      }
+    }
+  } else if (warp >= 2 && warp < 10) {
+    // ------------------------------------------------------------------ epilogue warps (thread = one frame)
+    const int q = warp & 3;           // TMEM lane quarter this warp may read
+    const int sub = (warp - 2) >> 2;  // the two warps of a quarter alternate 16-column chunks
+    const int row = q * 32 + lane;
+    const int t = t_cta0 + row;
+    const uint32_t tlane = (uint32_t)(q * 32) << 16;
+    const bool in_seq = t < T;
+    const bool elected = (warp == 2 && lane == 0);
+    const uint32_t xc_leader = ptx::mapa(ptx::smem_u32(&bars->xc_ready), 0);
+    const uint32_t gr_leader = ptx::mapa(ptx::smem_u32(&bars->g_ready), 0);
+    const uint32_t dr_leader = ptx::mapa(ptx::smem_u32(&bars->d2_drained[0]), 0);
+    const float s2 = 0.70710678118654752f;
+
+    for (int l = 0; l < L; ++l) {
+      const uint32_t pl = (uint32_t)l & 1u;
+      const int d = a.dilation[l];
+      const bool has_l = (t - d) >= 0, has_r = (t + d) < T;
+      const bool last = (l == L - 1);
+      // per-column biases of this layer -> smem: sb_full = centre + left + right tap terms (an interior frame's sum)
+      {
+        const float* sb = a.stepbias + (size_t)b * a.sb_batch_stride + (size_t)l * a.sb_layer_stride;
+        const float* bo = a.bout + (size_t)l * twoC;
+        for (int i = threadIdx.x - 64; i < twoC; i += 256) {
+          const float lft = sb[i], c = sb[twoC + i], r = sb[2 * twoC + i];
+          sb_full[i] = c + lft + r;
+          sb_l[i] = lft;
+          sb_r[i] = r;
+          bo_s[i] = bo[i];
+        }
+        ptx::named_bar_sync(1, 256);
+      }
+
+      // ---- epilogue 1: gating -> G
+      for (int j = 0; j < NB; ++j) {
+        ptx::mbar_wait(&bars->d1_full[j], pl);
+        ptx::tc_fence_after();
+        uint32_t rgb[2][16], rfb[2][16];
+        ptx::tmem_ld16(tmem + tlane + j * 256 + 16 * sub, rgb[0]);
+        ptx::tmem_ld16(tmem + tlane + j * 256 + 128 + 16 * sub, rfb[0]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c0 = 16 * (2 * i + sub);
+          ptx::tmem_ld_wait();
+          if (i + 1 < 4) {  // next chunk's TMEM loads fly while this chunk is gated
+            ptx::tmem_ld16(tmem + tlane + j * 256 + c0 + 32, rgb[(i + 1) & 1]);
+            ptx::tmem_ld16(tmem + tlane + j * 256 + 128 + c0 + 32, rfb[(i + 1) & 1]);
+          }
+          const uint32_t* rg = rgb[i & 1];
+          const uint32_t* rf = rfb[i & 1];
+          const int pg = j * 256 + c0, pf = pg + 128;
+          float z[16];
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            const float4 bg = ptx::ld_shared_v4f(sb_full + pg + e);
+            const float4 bf = ptx::ld_shared_v4f(sb_full + pf + e);
+            float gv[4] = {__uint_as_float(rg[e]) + bg.x, __uint_as_float(rg[e + 1]) + bg.y,
+                           __uint_as_float(rg[e + 2]) + bg.z, __uint_as_float(rg[e + 3]) + bg.w};
+            float fv[4] = {__uint_as_float(rf[e]) + bf.x, __uint_as_float(rf[e + 1]) + bf.y,
+                           __uint_as_float(rf[e + 2]) + bf.z, __uint_as_float(rf[e + 3]) + bf.w};
+            if (!has_l) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) { gv[u] -= sb_l[pg + e + u]; fv[u] -= sb_l[pf + e + u]; }
+            }
+            if (!has_r) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) { gv[u] -= sb_r[pg + e + u]; fv[u] -= sb_r[pf + e + u]; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) z[e + u] = ptx::sigmoid_approx(gv[u]) * ptx::tanh_approx(fv[u]);
+          }
+          const int kc0 = j * 128 + c0;  // first gated channel of the chunk = K index of GEMM2
+          uint8_t* gk = g_smem + (kc0 >> 6) * kSTile;
+          const uint32_t ch16 = (uint32_t)((kc0 & 63) >> 3);
+          ptx::st_shared_v4(gk + ptx::sw128_offset((uint32_t)row, ch16), ptx::pack_bf16(z[0], z[1]),
+                            ptx::pack_bf16(z[2], z[3]), ptx::pack_bf16(z[4], z[5]), ptx::pack_bf16(z[6], z[7]));
+          ptx::st_shared_v4(gk + ptx::sw128_offset((uint32_t)row, ch16 + 1), ptx::pack_bf16(z[8], z[9]),
+                            ptx::pack_bf16(z[10], z[11]), ptx::pack_bf16(z[12], z[13]), ptx::pack_bf16(z[14], z[15]));
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();  // G (generic-proxy stores) -> visible to the tensor cores' async proxy
+      ptx::mbar_arrive_cluster(gr_leader);
+
+      // ---- epilogue 2: residual -> in place over the window's centre rows (the next layer's centre tap) ;
+      //      skip -> fp32 slabs in the G buffer -> TMA reduce-add (or plain store on the first layer)
+      int skip_slab = 0;  // running index of this layer's 32-column skip slabs
+      for (int j = 0; j < NB; ++j) {
+        ptx::mbar_wait(&bars->d2_full[j], pl);
+        ptx::tc_fence_after();
+        const int res_cols = min(max(C - j * 256, 0), 256);  // residual columns in this 256-column block
+        if (res_cols > 0 && !last) {
+          if (l == 0) ptx::mbar_wait(&bars->xw_full, 0);  // (long complete) makes the TMA-written window visible here
+#pragma unroll 1
+          for (int i = 0; i < res_cols / 32; ++i) {
+            const int c0 = 16 * (2 * i + sub);
+            const int oc0 = j * 256 + c0;  // output channel = residual channel
+            uint32_t r[16];
+            ptx::tmem_ld16(tmem + tlane + j * 256 + c0, r);
+            ptx::tmem_ld_wait();
+            uint8_t* xt = xw_smem + (oc0 >> 6) * kSWinBytes + kSHalo * 128;  // centre rows of the window tile
+            const uint32_t ch16 = (uint32_t)((oc0 & 63) >> 3);
+            uint8_t* p0 = xt + ptx::sw128_offset((uint32_t)row, ch16);
+            uint8_t* p1 = xt + ptx::sw128_offset((uint32_t)row, ch16 + 1);
+            const uint4 xa = ptx::ld_shared_v4(p0), xb = ptx::ld_shared_v4(p1);
+            const uint32_t xo[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            uint32_t o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float lo = (ptx::bf16_lo(xo[e]) + __uint_as_float(r[2 * e]) + bo_s[oc0 + 2 * e]) * s2;
+              const float hi = (ptx::bf16_hi(xo[e]) + __uint_as_float(r[2 * e + 1]) + bo_s[oc0 + 2 * e + 1]) * s2;
+              o[e] = in_seq ? ptx::pack_bf16(lo, hi) : 0u;  // rows past the end stay zero: they are the conv's zero padding
+            }
+            ptx::st_shared_v4(p0, o[0], o[1], o[2], o[3]);
+            ptx::st_shared_v4(p1, o[4], o[5], o[6], o[7]);
+          }
+          if (j * 256 + 256 >= C) {  // all residual columns of this frame are written
+            ptx::fence_proxy_async_smem();
+            ptx::mbar_arrive_cluster(xc_leader);
+            ptx::mbar_arrive(&bars->xe_ready);
+          }
+        }
+        // skip part: columns [res_cols, 256) of this block, 32 at a time (one 128-byte fp32 row per frame)
+        if (res_cols < 256) {
+          if (j != NB - 1) __trap();  // skip columns only live in the last block: GEMM2 is done, the G buffer is free
+#pragma unroll 1
+          for (int i = res_cols / 32; i < 8; i += 2, skip_slab += 2) {
+            uint32_t r0[16], r1[16];
+            ptx::tmem_ld16(tmem + tlane + j * 256 + 16 * (2 * i + sub), r0);
+            ptx::tmem_ld16(tmem + tlane + j * 256 + 16 * (2 * i + 2 + sub), r1);
+            ptx::tmem_ld_wait();
+            if (skip_slab != 0 && (skip_slab & 3) == 0) {  // the four slab buffers go round: wait until they were read
+              if (elected) ptx::bulk_wait_read_all();
+              ptx::named_bar_sync(1, 256);
+            }
+            uint8_t* slab[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) slab[u] = g_smem + ((skip_slab + u) & 3) * kSTile;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const uint32_t* r = u ? r1 : r0;
+              const int oc0 = j * 256 + 16 * (2 * (i + u) + sub);
+#pragma unroll
+              for (int e = 0; e < 16; e += 4) {
+                const float4 bo = ptx::ld_shared_v4f(bo_s + oc0 + e);
+                ptx::st_shared_v4f(slab[u] + ptx::sw128_offset((uint32_t)row, (uint32_t)(sub * 4 + (e >> 2))),
+                                   __uint_as_float(r[e]) + bo.x, __uint_as_float(r[e + 1]) + bo.y,
+                                   __uint_as_float(r[e + 2]) + bo.z, __uint_as_float(r[e + 3]) + bo.w);
+              }
+            }
+            ptx::fence_proxy_async_smem();
+            ptx::named_bar_sync(1, 256);
+            if (elected) {
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int ch0 = j * 256 + 32 * (i + u) - C;  // first skip channel of the slab
+                if (l == 0 && a.init_skip) ptx::tma_store_3d(&tm_skip, slab[u], ch0, t_cta0, b);
+                else ptx::tma_reduce_add_3d(&tm_skip, slab[u], ch0, t_cta0, b);
+              }
+              ptx::bulk_commit_group();
+            }
+          }
+        }
+        // block j has been read out of TMEM: the next layer's GEMM1 may overwrite it
+        ptx::tc_fence_before();
+        ptx::mbar_arrive_cluster(dr_leader + (uint32_t)j * 8u);
+      }
+      if (elected) {
+        ptx::bulk_wait_read_all();  // skip slabs read: the G buffer may take the next layer's conditioner tiles
+        ptx::mbar_arrive(&bars->gc_free);
+      }
+      // the bias arrays are rewritten at the top of the next layer: every epilogue thread must be done reading them
+      ptx::named_bar_sync(1, 256);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();  // the peer's smem / TMEM are in use by the leader's MMAs until here
+  if (warp == 1) ptx::tmem_dealloc2(tmem, kSTmemCols);
+  if (threadIdx.x == 0) SVSK_STAMP(15);
+#undef SVSK_STAMP
+}
+
+}  // namespace svsk
+
+using namespace svsk;
+
+static int stack_smem(int C, int H, int* nentries_out) {
+  const int CB = C / 64, HB = H / 64;
+  int gc_tiles = HB > CB ? HB : CB;
+  if (gc_tiles < 4) gc_tiles = 4;
+  const int fixed = CB * kSWinBytes + gc_tiles * kSTile + 4 * 2 * C * (int)sizeof(float) + (int)sizeof(DiffnetStackBarriers) + 1024;
+  int nentries = (kSSmemLimit - fixed) / kSTile;
+  if (nentries > kSMaxEntries) nentries = kSMaxEntries;
+  *nentries_out = nentries;
+  return fixed + nentries * kSTile;
+}
+
+static int stack_prepare(int C, int H, int* nentries, int* smem_bytes) {
+  SVSK_REQUIRE(C == 128 || C == 256, SVSK_E_ARG, "diffnet_stack_bf16: C=%d (need 128 or 256)", C);
+  SVSK_REQUIRE(H > 0 && H % 64 == 0 && H <= 512, SVSK_E_ARG, "diffnet_stack_bf16: H=%d (need a multiple of 64, at most 512)", H);
+  *smem_bytes = stack_smem(C, H, nentries);
+  SVSK_REQUIRE(*nentries >= 3, SVSK_E_ARG, "diffnet_stack_bf16: not enough shared memory");
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static bool attr_set[64] = {false};
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(diffnet_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemLimit);
+    if (e != cudaSuccess) return fail((int)e, "diffnet_stack_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  return 0;
+}
+
+static void stack_launch_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int B, int T, int smem_bytes, void* stream) {
+  *cfg = cudaLaunchConfig_t{};
+  cfg->gridDim = dim3(2 * ceil_div(T, 256), B);
+  cfg->blockDim = dim3(kSThreads);
+  cfg->dynamicSmemBytes = smem_bytes;
+  cfg->stream = as_stream(stream);
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg->attrs = attr;
+  cfg->numAttrs = 1;
+}
+
+extern "C" int svsk_diffnet_stack_fits(int B, int T, int C, int H) {
+  int nentries = 0, smem_bytes = 0;
+  int rc = require_sm100();
+  if (rc) return -1;
+  if (B <= 0 || T <= 0 || B > 65535) return 0;
+  if (stack_prepare(C, H, &nentries, &smem_bytes)) return 0;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  stack_launch_config(&cfg, attr, B, T, smem_bytes, nullptr);
+  int max_clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, diffnet_stack_kernel, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return ceil_div(T, 256) * B <= max_clusters ? 1 : 0;
+}
+
+extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void* stream) {
+  SVSK_REQUIRE(pp != nullptr, SVSK_E_ARG, "diffnet_stack_bf16: null params");
+  const svsk_diffnet_stack_params& p = *pp;
+  SVSK_REQUIRE(p.xb_in && p.edge0 && p.edge1 && p.skip32 && p.cond && p.w1p && p.woutp && p.stepbias && p.bout && p.flags &&
+                   p.dilation,
+               SVSK_E_ARG, "diffnet_stack_bf16: null tensor");
+  SVSK_REQUIRE(p.xb_in != p.edge0 && p.xb_in != p.edge1 && p.edge0 != p.edge1, SVSK_E_ARG,
+               "diffnet_stack_bf16: xb_in / edge0 / edge1 must be three different buffers");
+  SVSK_REQUIRE(p.L >= 1 && p.L <= kSMaxLayers, SVSK_E_ARG, "diffnet_stack_bf16: L=%d (1..%d)", p.L, kSMaxLayers);
+  SVSK_REQUIRE(p.B > 0 && p.B <= 65535 && p.T > 0, SVSK_E_ARG, "diffnet_stack_bf16: bad B/T");
+  for (int l = 0; l < p.L; ++l)
+    SVSK_REQUIRE(p.dilation[l] >= 1 && p.dilation[l] <= kSHalo, SVSK_E_ARG,
+                 "diffnet_stack_bf16: layer %d dilation %d outside the resident window (1..%d)", l, p.dilation[l], kSHalo);
+  SVSK_REQUIRE(p.stepbias_layer_stride >= 6 * p.C && (p.stepbias_batch_stride == 0 || p.stepbias_batch_stride >= 6 * p.C),
+               SVSK_E_ARG, "diffnet_stack_bf16: stepbias strides");
+  SVSK_REQUIRE(((uintptr_t)p.skip32 % 16) == 0 && ((uintptr_t)p.edge0 % 16) == 0 && ((uintptr_t)p.edge1 % 16) == 0, SVSK_E_ALIGN,
+               "diffnet_stack_bf16: skip32 / edge0 / edge1 must be 16-byte aligned");
+  int rc = require_sm100();
+  if (rc) return rc;
+  int nentries = 0, smem_bytes = 0;
+  if ((rc = stack_prepare(p.C, p.H, &nentries, &smem_bytes))) return rc;
+
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  stack_launch_config(&cfg, attr, p.B, p.T, smem_bytes, stream);
+  int max_clusters = 0;
+  cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, diffnet_stack_kernel, &cfg);
+  if (oe != cudaSuccess) return fail((int)oe, "diffnet_stack_bf16: cudaOccupancyMaxActiveClusters: %s", cudaGetErrorString(oe));
+  SVSK_REQUIRE(ceil_div(p.T, 256) * p.B <= max_clusters, SVSK_E_ARG,
+               "diffnet_stack_bf16: %d CTA pairs do not fit the device at once (%d); run the layers with svsk_diffnet_block3_bf16",
+               ceil_div(p.T, 256) * p.B, max_clusters);
+
+  CUtensorMap tm_xw0, tm_e0, tm_e1, tm_cond, tm_w1, tm_wout, tm_skip;
+  {
+    uint64_t dims[3] = {(uint64_t)p.C, (uint64_t)p.T, (uint64_t)p.B};
+    uint64_t str[2] = {(uint64_t)p.C * 2, (uint64_t)p.T * p.C * 2};
+    uint32_t boxw[3] = {64, (uint32_t)kSWinRows, 1};
+    uint32_t boxe[3] = {64, (uint32_t)kSHalo, 1};
+    if ((rc = make_tmap_bf16(&tm_xw0, p.xb_in, 3, dims, str, boxw))) return rc;
+    if ((rc = make_tmap_bf16(&tm_e0, p.edge0, 3, dims, str, boxe))) return rc;
+    if ((rc = make_tmap_bf16(&tm_e1, p.edge1, 3, dims, str, boxe))) return rc;
+    uint64_t str4[2] = {(uint64_t)p.C * 4, (uint64_t)p.T * p.C * 4};
+    uint32_t box4[3] = {32, 128, 1};
+    if ((rc = make_tmap_f32(&tm_skip, p.skip32, 3, dims, str4, box4))) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)p.H, (uint64_t)p.T, (uint64_t)p.B};
+    uint64_t str[2] = {(uint64_t)p.H * 2, (uint64_t)p.T * p.H * 2};
+    uint32_t box[3] = {64, 128, 1};
+    if ((rc = make_tmap_bf16(&tm_cond, p.cond, 3, dims, str, box))) return rc;
+  }
+  {
+    const uint64_t K1 = 3 * (uint64_t)p.C + p.H;
+    uint64_t dims[3] = {K1, (uint64_t)2 * p.C, (uint64_t)p.L};
+    uint64_t str[2] = {K1 * 2, K1 * 2 * 2 * p.C};
+    uint32_t box[3] = {64, 128, 1};
+    if ((rc = make_tmap_bf16(&tm_w1, p.w1p, 3, dims, str, box))) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)p.C, (uint64_t)2 * p.C, (uint64_t)p.L};
+    uint64_t str[2] = {(uint64_t)p.C * 2, (uint64_t)p.C * 2 * 2 * p.C};
+    uint32_t box[3] = {64, 128, 1};
+    if ((rc = make_tmap_bf16(&tm_wout, p.woutp, 3, dims, str, box))) return rc;
+  }
+
+  DiffnetStackArgs a;
+  a.stepbias = p.stepbias;
+  a.bout = p.bout;
+  a.flags = p.flags;
+  a.proxy_fence = getenv("SVSK_STACK_NO_PROXY_FENCE") ? 0 : 1;
+  a.B = p.B; a.T = p.T; a.C = p.C; a.H = p.H; a.L = p.L;
+  a.sb_batch_stride = p.stepbias_batch_stride;
+  a.sb_layer_stride = p.stepbias_layer_stride;
+  a.init_skip = p.init_skip;
+  a.nentries = nentries;
+  a.tiles_per_track = 2 * ceil_div(p.T, 256);
+  for (int l = 0; l < kSMaxLayers; ++l) a.dilation[l] = l < p.L ? p.dilation[l] : 1;
+  a.dbg = nullptr;
+  if (const char* e = getenv("SVSK_DIFFNET_TIMELINE")) a.dbg = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
+
+  cudaError_t e = cudaMemsetAsync(p.flags, 0, sizeof(int) * (size_t)p.B * a.tiles_per_track, as_stream(stream));
+  if (e != cudaSuccess) return fail((int)e, "diffnet_stack_bf16: flag reset: %s", cudaGetErrorString(e));
+  e = cudaLaunchKernelEx(&cfg, diffnet_stack_kernel, tm_xw0, tm_e0, tm_e1, tm_cond, tm_w1, tm_wout, tm_skip, a);
+  if (e != cudaSuccess) return fail((int)e, "diffnet_stack_bf16: launch: %s", cudaGetErrorString(e));
+  return check_launch("diffnet_stack_bf16");
+}

@@ -15,6 +15,8 @@ from __future__ import annotations
 import math
 from math import sqrt
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -108,12 +110,22 @@ class _Bf16Plan:
             b_out = torch.zeros((self.Mp,), device=device, dtype=f32)
             b_out[:M] = net.output_projection.bias
             self.b_out = b_out
+            # per-layer operands live in tensors stacked along a leading layer dimension (what the one-launch stack
+            # kernel reads); the per-layer entries below are views of them
+            K1 = 3 * C + H
+            self.w1p_all = torch.empty((L, 2 * C, K1), device=device, dtype=bf16)
+            self.woutp_all = torch.empty((L, 2 * C, C), device=device, dtype=bf16)
+            self.bout_all = torch.empty((L, 2 * C), device=device, dtype=f32)
+            self.dilations = [int(layer.dilation) for layer in net.residual_layers]
             self.layers = []
-            for layer in net.residual_layers:
+            for i, layer in enumerate(net.residual_layers):
                 dw = layer.dilated_conv.weight.detach().to(f32)
                 cw = layer.conditioner_projection.weight.detach().to(f32)
                 ow = layer.output_projection.weight.detach().to(f32)
                 w1p, woutp = ops.diffnet_pack_block(dw, cw, ow)
+                self.w1p_all[i].copy_(w1p)
+                self.woutp_all[i].copy_(woutp)
+                self.bout_all[i].copy_(layer.output_projection.bias.detach().to(f32))
                 # step-embedding taps: stepw[j*2C + perm[r]] = dilated_w[r, :, j]  (so that stepbias = stepw @ dp + stepb
                 # gives, per tap j, W_j . (diffusion_projection(e)) in packed row order); the conv and conditioner
                 # biases ride on the centre tap, which every frame has.
@@ -123,12 +135,11 @@ class _Bf16Plan:
                     stepw[j * 2 * C + perm] = dw[:, :, j]
                 stepb[2 * C + perm] = layer.dilated_conv.bias.detach().to(f32) + layer.conditioner_projection.bias.detach().to(f32)
                 self.layers.append(dict(
-                    w1p=w1p, woutp=woutp, dilation=layer.dilation,
-                    bout=layer.output_projection.bias.detach().to(f32).contiguous(),
+                    w1p=self.w1p_all[i], woutp=self.woutp_all[i], dilation=layer.dilation, bout=self.bout_all[i],
                     stepw=stepw.unsqueeze(-1).contiguous(), stepb=stepb,
                     dpw=layer.diffusion_projection.weight.detach().to(f32).contiguous(),
                     dpb=layer.diffusion_projection.bias.detach().to(f32).contiguous()))
-        self.step_table = None  # [L][K, 3*2C], filled by GaussianDiffusion for t = 0..K-1
+        self.step_table = None  # [L, K, 3*2C], filled by GaussianDiffusion for t = 0..K-1
 
 
 class DiffNet(nn.Module):
@@ -183,35 +194,50 @@ class DiffNet(nn.Module):
         return ops.linear_f32(h, self.mlp[2].weight, self.mlp[2].bias)
 
     def step_bias_bf16(self, t):
-        """Per-layer [Bt, 3*2C] tap biases for the fused kernel (packed row order)."""
+        """[L, Bt, 3*2C] tap biases for the fused kernels (packed row order), layer-major."""
         plan = self.bf16_plan()
         e = self.step_embedding(t)
-        out = []
-        for lw in plan.layers:
+        out = torch.empty((plan.L, e.shape[0], 6 * plan.C), device=e.device, dtype=f32)
+        for i, lw in enumerate(plan.layers):
             dp = ops.linear_f32(e, lw["dpw"], lw["dpb"])
-            out.append(ops.linear_f32(dp, lw["stepw"], lw["stepb"]))
+            ops.linear_f32(dp, lw["stepw"], lw["stepb"], out=out[i])
         return out
 
     # ------------------------------------------------------------------ engines
-    def denoise_ntc_bf16(self, x32s, condb, stepbias, stride, plan=None):
-        """x32s [B,T,Mp] fp32 (channels >= M are ignored), condb [B,T,H] bf16, stepbias: list of L tensors.
-        Returns eps [B,T,Mp] fp32 (padded channels = 0)."""
+    def denoise_ntc_bf16(self, x32s, condb, stepbias, plan=None):
+        """x32s [B,T,Mp] fp32 (channels >= M are ignored), condb [B,T,H] bf16, stepbias [L, Bt, 3*2C] fp32 (any layer
+        stride; Bt = B rows, or 1 row shared by the batch).  Returns eps [B,T,Mp] fp32 (padded channels = 0)."""
         plan = self.bf16_plan() if plan is None else plan
         B, T, _ = x32s.shape
         C, L = plan.C, plan.L
         dev = x32s.device
+        if stepbias.dim() != 3 or stepbias.shape[0] != L or stepbias.shape[1] not in (1, B) or stepbias.stride(2) != 1:
+            raise ValueError(f"stepbias must be [L={L}, 1 or B={B}, {6 * C}], got {tuple(stepbias.shape)}")
+        sb_layer = stepbias.stride(0)
+        sb_batch = stepbias.stride(1) if stepbias.shape[1] == B and B > 1 else 0
         specb = ops.cast_scale_bf16(x32s)
         xb0 = torch.empty((B, T, C), device=dev, dtype=bf16)
         xb1 = torch.empty((B, T, C), device=dev, dtype=bf16)
-        x32 = torch.empty((B, T, C), device=dev, dtype=f32)
         skip32 = torch.empty((B, T, C), device=dev, dtype=f32)
-        ops.linear_bf16(specb, plan.w_in, plan.b_in, act=ops.ACT_RELU, out_bf16=xb0, out_f32=x32)
-        cur, nxt = xb0, xb1
-        for i, lw in enumerate(plan.layers):
-            ops.diffnet_block_bf16(cur, nxt, x32, skip32, condb, lw["w1p"], lw["woutp"], stepbias[i], lw["bout"],
-                                   dilation=lw["dilation"], stepbias_batch_stride=stride, init_skip=(i == 0),
-                                   write_x=(i < L - 1), time_tile=getattr(self, "time_tile", 0))
-            cur, nxt = nxt, cur
+        time_tile = getattr(self, "time_tile", 0)
+        use_stack = (not time_tile and os.environ.get("SVSK_DIFFNET_STACK", "1") != "0" and max(plan.dilations) <= 8
+                     and os.environ.get("SVSK_DIFFNET_KERNEL", "3") == "3" and ops.diffnet_stack_fits(B, T, C, plan.H))
+        if use_stack:
+            # one launch for all L blocks: every CTA pair keeps its 256-frame tile, neighbours exchange 8 edge rows per layer
+            ops.linear_bf16(specb, plan.w_in, plan.b_in, act=ops.ACT_RELU, out_bf16=xb0)
+            xb2 = torch.empty((B, T, C), device=dev, dtype=bf16)
+            flags = torch.empty((B * 2 * ((T + 255) // 256),), device=dev, dtype=torch.int32)
+            ops.diffnet_stack_bf16(xb0, xb1, xb2, skip32, condb, plan.w1p_all, plan.woutp_all, stepbias, plan.bout_all,
+                                   flags, plan.dilations, stepbias_batch_stride=sb_batch, stepbias_layer_stride=sb_layer)
+        else:
+            x32 = torch.empty((B, T, C), device=dev, dtype=f32)
+            ops.linear_bf16(specb, plan.w_in, plan.b_in, act=ops.ACT_RELU, out_bf16=xb0, out_f32=x32)
+            cur, nxt = xb0, xb1
+            for i, lw in enumerate(plan.layers):
+                ops.diffnet_block_bf16(cur, nxt, x32, skip32, condb, lw["w1p"], lw["woutp"], stepbias[i], lw["bout"],
+                                       dilation=lw["dilation"], stepbias_batch_stride=sb_batch, init_skip=(i == 0),
+                                       write_x=(i < L - 1), time_tile=time_tile)
+                cur, nxt = nxt, cur
         skipb = ops.cast_scale_bf16(skip32, alpha=1.0 / sqrt(L))
         hb, _ = ops.linear_bf16(skipb, plan.w_skip, plan.b_skip, act=ops.ACT_RELU, want_bf16=True)
         _, eps = ops.linear_bf16(hb, plan.w_out, plan.b_out, want_f32=True)
@@ -240,7 +266,7 @@ class DiffNet(nn.Module):
         _, x32s = ops.nct_to_ntc(x_in, Cp=plan.Mp, want_bf16=False, want_f32=True)
         condb, _ = ops.nct_to_ntc(cond)
         sb = self.step_bias_bf16(t)
-        eps = self.denoise_ntc_bf16(x32s, condb, sb, stride=6 * plan.C)
+        eps = self.denoise_ntc_bf16(x32s, condb, sb)
         return ops.ntc_to_nct_f32(eps, plan.M)[:, None]
 
     def forward(self, spec, diffusion_step, cond):

@@ -173,10 +173,10 @@ class GaussianDiffusion(BaseModel):
 
     # ------------------------------------------------------------------ sampling (diffusion.py:302-336)
     def _step_table(self):
-        """[L] tensors of [K, 3*2C] tap biases for t = 0..K-1 (cached with the denoiser's packed weights)."""
+        """[L, K, 3*2C] tap biases for t = 0..K-1 (cached with the denoiser's packed weights)."""
         den = self.denoise_fn
         plan = den.bf16_plan()
-        if plan.step_table is None or plan.step_table[0].shape[0] != self.K_step:
+        if plan.step_table is None or plan.step_table.shape[1] != self.K_step:
             t_all = torch.arange(self.K_step, device=self.betas.device, dtype=torch.int64)
             plan.step_table = den.step_bias_bf16(t_all)
         return plan.step_table
@@ -189,8 +189,8 @@ class GaussianDiffusion(BaseModel):
         B = x32s.shape[0]
         tabs = self._tables()
         for i in reversed(range(self.K_step)):
-            sb = [tl[i] for tl in table]  # row i of each layer's table; stride 0 broadcasts it over the batch
-            eps = den.denoise_ntc_bf16(x32s, condb, sb, stride=0, plan=plan)
+            # row i of every layer's table, shared by the whole batch
+            eps = den.denoise_ntc_bf16(x32s, condb, table[:, i:i + 1], plan=plan)
             ops.ddpm_update_f32(x32s, eps, z_ntc[i], self._t_const[i], tabs, True, out=x32s)
         return x32s
 

@@ -48,11 +48,13 @@ def conv1d_f32(x, w, bias=None, *, dilation=1, tap_origin=None, pad_mode=PAD_ZER
     return out
 
 
-def linear_f32(x, w, bias=None, act=ACT_NONE):
-    """nn.Linear on [Bt,Cin] (svsk_linear_f32); w [Cout,Cin] or [Cout,Cin,1]."""
+def linear_f32(x, w, bias=None, act=ACT_NONE, out=None):
+    """nn.Linear on [Bt,Cin] (svsk_linear_f32); w [Cout,Cin] or [Cout,Cin,1]; out: optional contiguous [Bt,Cout]."""
     Bt, Cin = x.shape
     Cout = w.shape[0]
-    y = torch.empty((Bt, Cout), device=x.device, dtype=f32)
+    y = torch.empty((Bt, Cout), device=x.device, dtype=f32) if out is None else out
+    if out is not None and (tuple(out.shape) != (Bt, Cout) or not out.is_contiguous()):
+        raise ValueError(f"linear_f32: out must be a contiguous [{Bt}, {Cout}] tensor")
     L.check(L.lib().svsk_linear_f32(L.ptr(x, f32, "x"), L.ptr(w, f32, "w"), L.ptr(bias, f32, "bias"), L.ptr(y), Bt, Cin,
                                     Cout, act, L.stream_ptr()), "linear_f32")
     return y
@@ -218,6 +220,35 @@ def diffnet_block_bf16(xb_in, xb_out, x32, skip32, cond, w1p, woutp, stepbias, b
     p.init_skip, p.write_x, p.time_tile = int(init_skip), int(write_x), int(time_tile)
     fn = {1: L.lib().svsk_diffnet_block_bf16, 2: L.lib().svsk_diffnet_block2_bf16, 3: L.lib().svsk_diffnet_block3_bf16}[kernel]
     L.check(fn(C.byref(p), L.stream_ptr()), "diffnet_block_bf16")
+
+
+def diffnet_stack_fits(B, T, Cc, H):
+    """True if the one-launch residual stack (svsk_diffnet_stack_bf16) can hold all its CTA pairs on the device at once."""
+    return L.lib().svsk_diffnet_stack_fits(int(B), int(T), int(Cc), int(H)) == 1
+
+
+def diffnet_stack_bf16(xb_in, edge0, edge1, skip32, cond, w1p_all, woutp_all, stepbias, bout_all, flags, dilations, *,
+                       stepbias_batch_stride, stepbias_layer_stride, init_skip=True):
+    """All residual blocks in one launch.  w1p_all [L,2C,3C+H], woutp_all [L,2C,C], bout_all [L,2C]; stepbias: any fp32
+    tensor whose element (layer l, batch row b) row starts at l*layer_stride + b*batch_stride floats."""
+    B, T, Cc = xb_in.shape
+    nl = w1p_all.shape[0]
+    p = L.DiffnetStackParams()
+    p.xb_in, p.edge0, p.edge1 = L.ptr(xb_in, bf16, "xb_in"), L.ptr(edge0, bf16, "edge0"), L.ptr(edge1, bf16, "edge1")
+    p.skip32, p.cond = L.ptr(skip32, f32, "skip32"), L.ptr(cond, bf16, "cond")
+    p.w1p, p.woutp = L.ptr(w1p_all, bf16, "w1p"), L.ptr(woutp_all, bf16, "woutp")
+    if not stepbias.is_cuda or stepbias.dtype != f32:
+        raise RuntimeError("stepbias must be a CUDA float32 tensor")
+    p.stepbias, p.bout = C.c_void_p(stepbias.data_ptr()), L.ptr(bout_all, f32, "bout")
+    p.flags = L.ptr(flags, torch.int32, "flags")
+    if flags.numel() < B * 2 * ((T + 255) // 256):
+        raise ValueError("diffnet_stack_bf16: flags too small")
+    dil = (C.c_int32 * nl)(*[int(d) for d in dilations])
+    p.dilation = C.cast(dil, C.POINTER(C.c_int32))
+    p.B, p.T, p.C, p.H, p.L = B, T, Cc, cond.shape[2], nl
+    p.stepbias_batch_stride, p.stepbias_layer_stride = int(stepbias_batch_stride), int(stepbias_layer_stride)
+    p.init_skip = int(init_skip)
+    L.check(L.lib().svsk_diffnet_stack_bf16(C.byref(p), L.stream_ptr()), "diffnet_stack_bf16")
 
 
 def linear_bf16(a, w, bias=None, *, act=ACT_NONE, want_bf16=False, want_f32=False, out_bf16=None, out_f32=None):

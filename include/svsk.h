@@ -201,6 +201,39 @@ SVSK_API int svsk_diffnet_block2_bf16(const svsk_diffnet_block_params* p, void* 
  * (pack once, up front); every other operand may be.  This is the kernel the drop-in modules use. */
 SVSK_API int svsk_diffnet_block3_bf16(const svsk_diffnet_block_params* p, void* stream);
 
+/* All L residual blocks of one denoiser call in ONE launch (the loop denoiser.py:114-118): every CTA pair keeps its
+ * 256-frame tile for all layers, the residual epilogue rewrites the activation window in place, and only the 8 edge
+ * rows per side travel between neighbouring tiles (through edge0 / edge1 and a per-tile layer counter).  Operands are
+ * the per-layer ones stacked along a leading layer dimension:
+ *   w1p [L][2C][3C+H], woutp [L][2C][C] (svsk_diffnet_pack_block per layer), bout [L][2C],
+ *   stepbias: row of layer l and batch row b at stepbias + b*stepbias_batch_stride + l*stepbias_layer_stride (floats),
+ *   dilation[L] (host array, each 1..8), xb_in [B][T][C] bf16 = input of layer 0 (never written),
+ *   edge0 / edge1 [B][T][C] bf16 scratch (only edge rows are touched; contents need not be initialised),
+ *   flags: B * 2*ceil(T/256) ints of scratch (reset by this call), skip32 [B][T][C] fp32 = sum of the L skip outputs
+ *   (stored if init_skip, else accumulated).  The residual stream after the last layer is not produced (it is dead,
+ *   denoiser.py:117-120).
+ * All CTA pairs must be resident at once: svsk_diffnet_stack_fits(B,T,C,H) returns 1 if they are, 0 if not (then run
+ * the layers one by one with svsk_diffnet_block3_bf16), -1 without an sm_100 device. */
+typedef struct svsk_diffnet_stack_params {
+  const void* xb_in;
+  void* edge0;
+  void* edge1;
+  float* skip32;
+  const void* cond;      /* [B][T][H] bf16 */
+  const void* w1p;
+  const void* woutp;
+  const float* stepbias;
+  const float* bout;
+  int32_t* flags;
+  const int32_t* dilation; /* host pointer, L entries */
+  int32_t B, T, C, H, L;
+  int32_t stepbias_batch_stride;  /* floats; 0 = same for every batch row */
+  int32_t stepbias_layer_stride;  /* floats; >= 6C */
+  int32_t init_skip;
+} svsk_diffnet_stack_params;
+SVSK_API int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* p, void* stream);
+SVSK_API int svsk_diffnet_stack_fits(int B, int T, int C, int H);
+
 /* Pack one block's weights (fp32, reference state_dict layout) for svsk_diffnet_block_bf16.
  *   dilated_w [2C][C][3], cond_w [2C][H][1], out_w [2C][C][1]  ->  w1p [2C][3C+H] bf16, woutp [2C][C] bf16.
  * Row r of the reference maps to packed row perm(r): gate rows of channel block q at 256q..256q+127, filter rows at

@@ -306,6 +306,11 @@ def _bf(x):
     return x.to(torch.bfloat16).float()
 
 
+def _launches():
+    from ensemble_svs_with_interactions_b200 import _lib
+    return _lib.launch_count
+
+
 @pytest.mark.parametrize("N,K,Cout,act", [(300, 80, 256, 1), (129, 256, 80, 0), (1000, 256, 256, 1), (64, 64, 16, 2),
                                           (12000, 80, 256, 1)])
 def test_linear_bf16(N, K, Cout, act):
@@ -398,6 +403,46 @@ def test_diffnet_block3_rejects_wide_dilation_and_default_falls_back():
     ops.diffnet_block_bf16(xb, out, x32, skip, cond, lw["w1p"], lw["woutp"], sb, lw["bout"], **kw)
     torch.cuda.synchronize()
     assert torch.isfinite(out.float()).all()
+
+
+@pytest.mark.parametrize("C,H,M,L,B,T", [(256, 256, 80, 6, 2, 300), (256, 256, 80, 5, 1, 1000), (128, 128, 5, 6, 3, 517),
+                                         (256, 128, 60, 4, 2, 128), (128, 256, 60, 3, 2, 40), (256, 256, 80, 20, 6, 2000)])
+def test_diffnet_stack_matches_per_layer_kernels(C, H, M, L, B, T):
+    """The one-launch residual stack (tiles resident across layers, edge rows exchanged between neighbours) against the
+    same layers run one kernel at a time: same bf16 operands, only the fp32 accumulation order of the K loop differs."""
+    import os
+    m = _random_diffnet(C, H, M, L, seed=C + L + T).to(DEV)
+    g = torch.Generator().manual_seed(T)
+    spec = torch.randn(B, 1, M, T, generator=g).to(DEV); cond = torch.randn(B, H, T, generator=g).to(DEV)
+    t = torch.randint(0, 100, (B,), generator=g).to(DEV)
+    ops = _ops()
+    assert ops.diffnet_stack_fits(B, T, C, H)
+    os.environ["SVSK_DIFFNET_STACK"] = "0"
+    try:
+        ref = m(spec, t, cond)
+    finally:
+        os.environ.pop("SVSK_DIFFNET_STACK")
+    n0 = _launches()
+    y = m(spec, t, cond)
+    torch.cuda.synchronize()
+    n_stack = _launches() - n0
+    assert torch.isfinite(y).all()
+    r, mx = close_bf16(y, ref, 1e-2, 3e-2)
+    print(f"stack vs per-layer: rel_l2={r:.3e} max={mx:.3e}, {n_stack} launches")
+    y2 = m(spec, t, cond)   # same launch again: deterministic
+    assert torch.equal(y, y2)
+
+
+def test_diffnet_stack_refuses_grids_that_do_not_fit():
+    ops = _ops()
+    assert not ops.diffnet_stack_fits(64, 2000, 256, 256)   # 512 CTA pairs
+    assert ops.diffnet_stack_fits(6, 2000, 256, 256)        # BASELINE config 2: 48 pairs
+    # the module then runs the layers one launch at a time
+    m = _random_diffnet(128, 64, 16, 2, seed=1).to(DEV)
+    B, T = 40, 1100
+    assert not ops.diffnet_stack_fits(B, T, 128, 64)
+    y = m(torch.randn(B, 1, 16, T, device=DEV), torch.zeros(B, dtype=torch.long, device=DEV), torch.randn(B, 64, T, device=DEV))
+    assert torch.isfinite(y).all()
 
 
 def test_diffnet_bf16_forward_vs_oracle():
