@@ -9,11 +9,18 @@
 //   * set-up once per call instead of once per layer;
 //   * the centre rows of the activation window are updated in place by the residual epilogue and are already the next
 //     layer's centre tap: only the 8 halo rows either side come from the neighbouring tiles, through global memory
-//     (8 edge rows per side TMA-stored per layer, a per-tile layer counter with release/acquire semantics, the
-//     neighbour TMA-loads them into its window's halo rows);
+//     Two transports: when a whole track fits one thread-block cluster (<= 16 tiles = 2048 frames, the reference
+//     workload) the epilogue threads of the edge rows write them straight into the neighbouring CTAs' windows through
+//     distributed shared memory (~1 k cycles door to door); otherwise they are TMA-stored to a scratch tensor, a
+//     per-tile layer counter is released, and the neighbour TMA-loads them (~8 k cycles: every hop is an L2 round trip
+//     of ~2.5 k cycles under the weight stream's load, profiles/r01x_bench_stack_timeline.log);
 //   * the next layer's weights stream in while the skip epilogue of this layer drains TMEM: GEMM1 of layer l+1 starts
 //     on the first 256 TMEM columns as soon as the residual half has been read out.
 // Everything else (operand layouts, row-offset tap descriptors, gating, TMA epilogues) is the per-layer kernel's.
+//
+// In that one-cluster-per-track mode the weight tiles, identical for every tile of the track, are TMA-multicast: each
+// CTA pair fetches 1/n_pairs of every tile for all CTAs of its parity, so L2 serves each weight byte once per track
+// instead of once per tile, and a ring slot is refilled when ALL pairs have released it (cluster-wide empty barrier).
 //
 // Per layer, ring entries (16 KB weight tiles) in this order — producer, MMA issuer and the peer's forwarder agree:
 //   0: centre tap, block 0        (A = window rows 8..135, needs only this CTA pair's own previous epilogue)
@@ -49,7 +56,7 @@ struct DiffnetStackArgs {
   const float* stepbias;  // [batch][layer][6C] (strides below)
   const float* bout;      // [layer][2C]
   int* flags;             // [B * tiles_per_track] layers published per tile; zero at launch
-  int proxy_fence;        // 1: fence.proxy.async.global around the flag hand-over (default); 0: profiling experiment
+  int dsmem_halo;         // 1: one cluster per track, halo rows through distributed shared memory; 0: through global memory
   int B, T, C, H, L, sb_batch_stride, sb_layer_stride, init_skip, nentries, tiles_per_track;
   int dilation[kSMaxLayers];
   unsigned long long* dbg;
@@ -60,12 +67,14 @@ struct __align__(8) DiffnetStackBarriers {
   uint64_t empty[kSMaxEntries];
   uint64_t cd_full[8];          // conditioner tile hb of this layer landed (leader: in both CTAs)
   uint64_t xw_full;             // layer 0: whole window landed; later layers: halo rows landed (leader: in both CTAs)
+  uint64_t xh_full;             // DSMEM mode: the neighbours' edge threads have written this CTA's halo rows (leader: both CTAs)
+  uint64_t halo_free;           // DSMEM mode: the CTA pairs that read the halo rows this CTA writes have finished GEMM1
   uint64_t xc_ready;            // leader: centre rows updated in place by every epilogue thread of both CTAs
   uint64_t xe_ready;            // this CTA's centre rows updated (-> activation producer publishes the edge rows)
   uint64_t d1_full[2];
   uint64_t d2_full[2];
   uint64_t d2_drained[2];       // leader: every epilogue thread of both CTAs has read block j out of TMEM
-  uint64_t g_ready;
+  uint64_t g_ready[2];          // leader: gating block j written to G by every epilogue thread of both CTAs
   uint64_t gc_free;             // this CTA's G buffer is free again (skip slabs read by the TMA unit)
   uint32_t tmem_base;
 };
@@ -124,7 +133,18 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
   DiffnetStackBarriers* bars = reinterpret_cast<DiffnetStackBarriers*>(bo_s + twoC);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = ptx::cluster_ctarank();
+  const uint32_t crank = ptx::cluster_ctarank();   // rank in the cluster (a CTA pair, or a whole track in DSMEM mode)
+  const uint32_t rank = crank & 1u;                // rank in the CTA pair (tcgen05 cta_group::2): 0 = leader
+  const uint32_t lead = crank & ~1u;               // cluster rank of this pair's leader
+  const uint32_t csize = ptx::cluster_nctarank();
+  const uint16_t pair_mask = (uint16_t)(3u << lead);
+  const bool nb_left = a.dsmem_halo && crank > 0, nb_right = a.dsmem_halo && crank + 1 < csize;  // DSMEM neighbours
+  // weight multicast (one cluster per track): every pair fetches rows [pidx, pidx+1) * 128/n_pairs of each half-tile
+  const bool mc = a.dsmem_halo != 0;
+  const int n_pairs = mc ? (int)(csize >> 1) : 1, pidx = mc ? (int)(crank >> 1) : 0;
+  const int slice_rows = 128 / n_pairs;
+  const uint16_t parity_mask = (uint16_t)((0x5555u << rank) & ((1u << csize) - 1u));  // CTAs with this CTA's pair rank
+  const uint16_t empty_mask = mc ? (uint16_t)((1u << csize) - 1u) : pair_mask;        // whom a freed ring slot is told to
   const int b = blockIdx.y;
   const int t_cta0 = (blockIdx.x >> 1) * 256 + (int)rank * 128;  // first frame of this CTA's 128 TMEM lanes
   const int w_row0 = (int)rank * 128;                             // this CTA's half of a 256-row weight block
@@ -148,10 +168,14 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
     const uint32_t all = rank == 0 ? 2u * 256u : 1u; // leader barriers every epilogue thread of the pair arrives on
     for (int i = 0; i < a.nentries; ++i) {
       ptx::mbar_init(&bars->full[i], two);
-      ptx::mbar_init(&bars->empty[i], 1);  // one multicast tcgen05.commit
+      ptx::mbar_init(&bars->empty[i], (uint32_t)n_pairs);  // one multicast tcgen05.commit per CTA pair sharing the weights
     }
     for (int i = 0; i < HB; ++i) ptx::mbar_init(&bars->cd_full[i], two);
     ptx::mbar_init(&bars->xw_full, two);
+    // halo rows: 16 arrivals per neighbour (8 rows x the 2 epilogue warps of a lane quarter) + the peer's forward
+    ptx::mbar_init(&bars->xh_full, max(1u, 16u * ((nb_left ? 1u : 0u) + (nb_right ? 1u : 0u)) + (rank == 0 ? 1u : 0u)));
+    // credits: this pair's GEMM1 + the GEMM1 of the pair on the other side of this CTA's outer edge
+    ptx::mbar_init(&bars->halo_free, 1u + ((rank == 0 ? nb_left : nb_right) ? 1u : 0u));
     ptx::mbar_init(&bars->xc_ready, all);
     ptx::mbar_init(&bars->xe_ready, 256);
     for (int i = 0; i < 2; ++i) {
@@ -159,10 +183,11 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
       ptx::mbar_init(&bars->d2_full[i], 1);
       ptx::mbar_init(&bars->d2_drained[i], all);
     }
-    ptx::mbar_init(&bars->g_ready, all);
-    ptx::mbar_init(&bars->gc_free, 1);
+    ptx::mbar_init(&bars->g_ready[0], all);
+    ptx::mbar_init(&bars->g_ready[1], all);
+    ptx::mbar_init(&bars->gc_free, 8);  // one arrival per epilogue warp
     ptx::fence_mbar_init();
-    pre_issued = min(a.nentries, n_total);
+    pre_issued = mc ? 0 : min(a.nentries, n_total);  // (multicast writes into CTAs that may not have set up their barriers yet)
     for (int e = 0; e < pre_issued; ++e) {
       int kcol, blk;
       bool wout;
@@ -193,7 +218,9 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         bool wout;
         stack_entry(i, CB, HB, NB, KB2, kcol, blk, wout);
         ptx::mbar_arrive_expect_tx(&bars->full[s], kSTile);
-        ptx::tma_load_3d(ring + s * kSTile, wout ? &tm_wout : &tm_w1, &bars->full[s], kcol * 64, blk * 256 + w_row0, l);
+        if (mc) ptx::tma_load_3d_mc(ring + s * kSTile + pidx * slice_rows * 128, wout ? &tm_wout : &tm_w1, &bars->full[s],
+                                    kcol * 64, blk * 256 + w_row0 + pidx * slice_rows, l, parity_mask);
+        else ptx::tma_load_3d(ring + s * kSTile, wout ? &tm_wout : &tm_w1, &bars->full[s], kcol * 64, blk * 256 + w_row0, l);
         if (++s == a.nentries) { s = 0; ph ^= 1; }
         if (++i == n_layer) { i = 0; ++l; }
       }
@@ -214,6 +241,14 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
       for (int l = 1; l < L; ++l) {
         const uint32_t pp = (uint32_t)(l - 1) & 1u;
         const CUtensorMap* tm_e = pp ? &tm_e1 : &tm_e0;
+        if (a.dsmem_halo) {  // the halo rows travel through distributed shared memory: only the conditioner tiles here
+          ptx::mbar_wait(&bars->gc_free, pp);
+          for (int hb = 0; hb < HB; ++hb) {
+            ptx::mbar_arrive_expect_tx(&bars->cd_full[hb], kSTile);
+            ptx::tma_load_3d(g_smem + hb * kSTile, &tm_cond, &bars->cd_full[hb], hb * 64, t_cta0, b);
+          }
+          continue;
+        }
         // publish the first / last 8 rows of layer l-1's output (the epilogue has written them in place)
         ptx::mbar_wait(&bars->xe_ready, pp);
         if (l == 1) SVSK_STAMP(9);
@@ -225,7 +260,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         ptx::bulk_commit_group();
         ptx::bulk_wait_all();  // the stores are complete (not merely read out of shared memory)
         if (l == 1) SVSK_STAMP(10);
-        if (a.proxy_fence) fence_proxy_async_global();
+        fence_proxy_async_global();
         st_release_gpu(a.flags + tile_idx, l);
         if (l == 1) SVSK_STAMP(11);
         // halo rows of layer l's input: the neighbours' edge rows of layer l-1's output
@@ -237,7 +272,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         }
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
         if (l == 1) SVSK_STAMP(12);
-        if (a.proxy_fence) fence_proxy_async_global();
+        fence_proxy_async_global();
         ptx::mbar_arrive_expect_tx(&bars->xw_full, 2 * CB * kSHaloBytes);
         for (int cb = 0; cb < CB; ++cb) {
           uint8_t* tile = xw_smem + cb * kSWinBytes;
@@ -262,12 +297,19 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
       const uint32_t xw_lo = ptx::umma_desc_lo(ptx::smem_u32(xw_smem));
       int s = 0;
       uint32_t ph = 0;
+      // CTAs that write halo rows this pair's GEMM1 reads: the pair itself and the outer neighbour on either side
+      const uint16_t halo_mask = (uint16_t)(pair_mask | (lead > 0 ? 1u << (lead - 1) : 0u) | (lead + 2 < csize ? 1u << (lead + 2) : 0u));
       bool ready = false;  // the barrier of ring entry (s, ph) was already seen complete by the previous group's probe
+      long long acc_wait = 0, n_miss = 0;
       // An mbarrier wait whose result is needed at once stalls this thread ~160 cycles even on a long-completed phase
       // (tools/ubench_umma.py): every MMA group therefore probes the NEXT entry's barrier while its MMAs are issued.
 #define SVSK_WAIT_ENTRY()                                 \
   do {                                                    \
-    if (!ready) ptx::mbar_wait(&bars->full[s], ph);       \
+    if (!ready) {                                         \
+      const long long c_0 = dbg ? clock64() : 0ll;        \
+      ptx::mbar_wait(&bars->full[s], ph);                 \
+      if (dbg) { acc_wait += clock64() - c_0; ++n_miss; } \
+    }                                                     \
     ready = false;                                        \
     ptx::tc_fence_after();                                \
   } while (0)
@@ -276,7 +318,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
   do {                                                                                                             \
     const int sn = (s + 1 == a.nentries) ? 0 : s + 1;                                                              \
     ready = ptx::umma2_bf16_x4_probe(tmem + (dcol), alo, blo, idesc, acc0, 4, &bars->full[sn], sn ? ph : ph ^ 1);  \
-    ptx::umma_commit2_mc(&bars->empty[s], 3);                                                                      \
+    ptx::umma_commit2_mc(&bars->empty[s], empty_mask);                                                                      \
     SVSK_NEXT_ENTRY();                                                                                             \
   } while (0)
       for (int l = 0; l < L; ++l) {
@@ -296,8 +338,9 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
           SVSK_ISSUE4(0, xw_lo + cb * (kSWinBytes >> 4) + kSHalo * 8, ring_lo + s * (kSTile >> 4), cb != 0);
         }
         // ---- side taps, block 0
-        if (l != 0) {
-          ptx::mbar_wait(&bars->xw_full, pl);  // halo rows of this layer
+        if (l != 0) {  // halo rows of this layer
+          if (a.dsmem_halo) ptx::mbar_wait(&bars->xh_full, pp);
+          else ptx::mbar_wait(&bars->xw_full, pl);
           ptx::tc_fence_after();
         }
         if (l == 1) SVSK_STAMP(3);
@@ -320,7 +363,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
             SVSK_ISSUE4(j * 256, a_lo, ring_lo + s * (kSTile >> 4), (j == 0 || hb != 0) ? 1 : 0);
           }
         }
-        ptx::umma_commit2_mc(&bars->d1_full[0], 3);
+        ptx::umma_commit2_mc(&bars->d1_full[0], pair_mask);
         if (l == 1) SVSK_STAMP(5);
         // ---- all taps, blocks 1..
         for (int j = 1; j < NB; ++j) {
@@ -331,22 +374,29 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
               SVSK_ISSUE4(j * 256, row_lo + cb * (kSWinBytes >> 4), ring_lo + s * (kSTile >> 4), 1);
             }
           }
-          ptx::umma_commit2_mc(&bars->d1_full[j], 3);
+          ptx::umma_commit2_mc(&bars->d1_full[j], pair_mask);
         }
+        // GEMM1 of this layer has read the window for the last time: the neighbouring tiles may overwrite its halo rows
+        if (a.dsmem_halo) ptx::umma_commit2_mc(&bars->halo_free, halo_mask);
         if (l == 1) SVSK_STAMP(6);
-        // ---- GEMM2
-        ptx::mbar_wait(&bars->g_ready, pl);
+        // ---- GEMM2: G tiles of gating block 0 first (its k-blocks of output block 0 run while block 1 is still gated)
+        ptx::mbar_wait(&bars->g_ready[0], pl);
         ptx::tc_fence_after();
-        if (l == 1) SVSK_STAMP(7);
         for (int j = 0; j < NB; ++j) {
           for (int kb = 0; kb < KB2; ++kb) {
+            if (NB > 1 && j == 0 && kb == KB2 / 2) {  // G tiles KB2/2.. come from gating block 1
+              ptx::mbar_wait(&bars->g_ready[1], pl);
+              ptx::tc_fence_after();
+              if (l == 1) SVSK_STAMP(7);
+            }
             SVSK_WAIT_ENTRY();
             SVSK_ISSUE4(j * 256, g_lo + kb * (kSTile >> 4), ring_lo + s * (kSTile >> 4), kb != 0);
           }
-          ptx::umma_commit2_mc(&bars->d2_full[j], 3);
+          ptx::umma_commit2_mc(&bars->d2_full[j], pair_mask);
         }
         if (l == 1) SVSK_STAMP(8);
       }
+      if (dbg) { dbg[16] = acc_wait; dbg[17] = n_miss; }  // blocking waits for ring entries: cycles, count
 #undef SVSK_WAIT_ENTRY
 #undef SVSK_NEXT_ENTRY
 #undef SVSK_ISSUE4
@@ -354,7 +404,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
       // peer CTA: second arrival on the leader's barriers ("mine has landed too"), in the order the leader waits
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t leader_full0 = ptx::mapa(ptx::smem_u32(&bars->full[0]), 0);
+      const uint32_t leader_full0 = ptx::mapa(ptx::smem_u32(&bars->full[0]), lead);
       for (int l = 0; l < L; ++l) {
         const uint32_t pl = (uint32_t)l & 1u;
         int i = 0;
@@ -366,8 +416,13 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
           }
         };
         auto forward_xw = [&]() {
+          if (a.dsmem_halo && l != 0) {
+            ptx::mbar_wait(&bars->xh_full, pl ^ 1u);
+            ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->xh_full), lead));
+            return;
+          }
           ptx::mbar_wait(&bars->xw_full, pl);
-          ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->xw_full), 0));
+          ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->xw_full), lead));
         };
         if (l == 0) forward_xw();
         forward_entries(CB);
@@ -375,7 +430,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         forward_entries(2 * CB);
         for (int hb = 0; hb < HB; ++hb) {
           ptx::mbar_wait(&bars->cd_full[hb], pl);
-          ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->cd_full[hb]), 0));
+          ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->cd_full[hb]), lead));
           forward_entries(NB);
         }
         forward_entries((NB - 1) * 3 * CB + NB * KB2);
@@ -390,10 +445,16 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
     const bool in_seq = t < T;
     const bool elected = (warp == 2 && lane == 0);
-    const uint32_t xc_leader = ptx::mapa(ptx::smem_u32(&bars->xc_ready), 0);
-    const uint32_t gr_leader = ptx::mapa(ptx::smem_u32(&bars->g_ready), 0);
-    const uint32_t dr_leader = ptx::mapa(ptx::smem_u32(&bars->d2_drained[0]), 0);
+    const uint32_t xc_leader = ptx::mapa(ptx::smem_u32(&bars->xc_ready), lead);
+    const uint32_t gr_leader = ptx::mapa(ptx::smem_u32(&bars->g_ready[0]), lead);
+    const uint32_t dr_leader = ptx::mapa(ptx::smem_u32(&bars->d2_drained[0]), lead);
     const float s2 = 0.70710678118654752f;
+    // DSMEM mode: this thread's row is one of the tile's first / last 8 -> it is also a halo row of a neighbouring CTA
+    const bool send_left = nb_left && row < kSHalo, send_right = nb_right && row >= 128 - kSHalo;
+    const uint32_t nb_rank = send_left ? crank - 1 : (send_right ? crank + 1 : crank);
+    const uint32_t nb_row = send_left ? (uint32_t)(kSHalo + 128 + row) : (uint32_t)(row - (128 - kSHalo));
+    const uint32_t nb_xw = ptx::mapa(ptx::smem_u32(xw_smem), nb_rank);       // the neighbour's window, cluster address
+    const uint32_t nb_bar = ptx::mapa(ptx::smem_u32(&bars->xh_full), nb_rank);
 
     for (int l = 0; l < L; ++l) {
       const uint32_t pl = (uint32_t)l & 1u;
@@ -460,97 +521,117 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
           ptx::st_shared_v4(gk + ptx::sw128_offset((uint32_t)row, ch16 + 1), ptx::pack_bf16(z[8], z[9]),
                             ptx::pack_bf16(z[10], z[11]), ptx::pack_bf16(z[12], z[13]), ptx::pack_bf16(z[14], z[15]));
         }
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async_smem();  // G (generic-proxy stores) -> visible to the tensor cores' async proxy
+        ptx::mbar_arrive_cluster(gr_leader + (uint32_t)j * 8u);
       }
-      ptx::tc_fence_before();
-      ptx::fence_proxy_async_smem();  // G (generic-proxy stores) -> visible to the tensor cores' async proxy
-      ptx::mbar_arrive_cluster(gr_leader);
 
       // ---- epilogue 2: residual -> in place over the window's centre rows (the next layer's centre tap) ;
       //      skip -> fp32 slabs in the G buffer -> TMA reduce-add (or plain store on the first layer)
-      int skip_slab = 0;  // running index of this layer's 32-column skip slabs
       for (int j = 0; j < NB; ++j) {
         ptx::mbar_wait(&bars->d2_full[j], pl);
         ptx::tc_fence_after();
+        if (l == 1 && elected) SVSK_STAMP(24 + 2 * j);  // 24: D2[0] complete, 26: D2[1] complete
         const int res_cols = min(max(C - j * 256, 0), 256);  // residual columns in this 256-column block
         if (res_cols > 0 && !last) {
           if (l == 0) ptx::mbar_wait(&bars->xw_full, 0);  // (long complete) makes the TMA-written window visible here
-#pragma unroll 1
-          for (int i = 0; i < res_cols / 32; ++i) {
-            const int c0 = 16 * (2 * i + sub);
-            const int oc0 = j * 256 + c0;  // output channel = residual channel
-            uint32_t r[16];
-            ptx::tmem_ld16(tmem + tlane + j * 256 + c0, r);
-            ptx::tmem_ld_wait();
-            uint8_t* xt = xw_smem + (oc0 >> 6) * kSWinBytes + kSHalo * 128;  // centre rows of the window tile
-            const uint32_t ch16 = (uint32_t)((oc0 & 63) >> 3);
-            uint8_t* p0 = xt + ptx::sw128_offset((uint32_t)row, ch16);
-            uint8_t* p1 = xt + ptx::sw128_offset((uint32_t)row, ch16 + 1);
-            const uint4 xa = ptx::ld_shared_v4(p0), xb = ptx::ld_shared_v4(p1);
-            const uint32_t xo[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-            uint32_t o[8];
+          if (send_left || send_right) ptx::mbar_wait(&bars->halo_free, pl);  // the neighbour's GEMM1 of this layer is done
+          const int n_res = res_cols / 32;
+          uint32_t rr[2][16];
+          ptx::tmem_ld16(tmem + tlane + j * 256 + 16 * sub, rr[0]);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float lo = (ptx::bf16_lo(xo[e]) + __uint_as_float(r[2 * e]) + bo_s[oc0 + 2 * e]) * s2;
-              const float hi = (ptx::bf16_hi(xo[e]) + __uint_as_float(r[2 * e + 1]) + bo_s[oc0 + 2 * e + 1]) * s2;
-              o[e] = in_seq ? ptx::pack_bf16(lo, hi) : 0u;  // rows past the end stay zero: they are the conv's zero padding
+          for (int i = 0; i < 8; ++i) {
+            if (i < n_res) {
+              const int c0 = 16 * (2 * i + sub);
+              const int oc0 = j * 256 + c0;  // output channel = residual channel
+              ptx::tmem_ld_wait();
+              if (i + 1 < n_res) ptx::tmem_ld16(tmem + tlane + j * 256 + c0 + 32, rr[(i + 1) & 1]);  // flies during the maths
+              const uint32_t* r = rr[i & 1];
+              uint8_t* xt = xw_smem + (oc0 >> 6) * kSWinBytes + kSHalo * 128;  // centre rows of the window tile
+              const uint32_t ch16 = (uint32_t)((oc0 & 63) >> 3);
+              uint8_t* p0 = xt + ptx::sw128_offset((uint32_t)row, ch16);
+              uint8_t* p1 = xt + ptx::sw128_offset((uint32_t)row, ch16 + 1);
+              const uint4 xa = ptx::ld_shared_v4(p0), xb = ptx::ld_shared_v4(p1);
+              const uint32_t xo[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+              uint32_t o[8];
+#pragma unroll
+              for (int e = 0; e < 8; e += 2) {
+                const float4 bo = ptx::ld_shared_v4f(bo_s + oc0 + 2 * e);
+                const float v0 = (ptx::bf16_lo(xo[e]) + __uint_as_float(r[2 * e]) + bo.x) * s2;
+                const float v1 = (ptx::bf16_hi(xo[e]) + __uint_as_float(r[2 * e + 1]) + bo.y) * s2;
+                const float v2 = (ptx::bf16_lo(xo[e + 1]) + __uint_as_float(r[2 * e + 2]) + bo.z) * s2;
+                const float v3 = (ptx::bf16_hi(xo[e + 1]) + __uint_as_float(r[2 * e + 3]) + bo.w) * s2;
+                o[e] = in_seq ? ptx::pack_bf16(v0, v1) : 0u;  // rows past the end stay zero: they are the conv's zero padding
+                o[e + 1] = in_seq ? ptx::pack_bf16(v2, v3) : 0u;
+              }
+              ptx::st_shared_v4(p0, o[0], o[1], o[2], o[3]);
+              ptx::st_shared_v4(p1, o[4], o[5], o[6], o[7]);
+              if (send_left || send_right) {  // the same 32 bytes into the neighbour's halo row
+                const uint32_t dst = nb_xw + (uint32_t)(oc0 >> 6) * kSWinBytes;
+                ptx::st_cluster_v4(dst + ptx::sw128_offset(nb_row, ch16), o[0], o[1], o[2], o[3]);
+                ptx::st_cluster_v4(dst + ptx::sw128_offset(nb_row, ch16 + 1), o[4], o[5], o[6], o[7]);
+              }
             }
-            ptx::st_shared_v4(p0, o[0], o[1], o[2], o[3]);
-            ptx::st_shared_v4(p1, o[4], o[5], o[6], o[7]);
           }
           if (j * 256 + 256 >= C) {  // all residual columns of this frame are written
             ptx::fence_proxy_async_smem();
-            ptx::mbar_arrive_cluster(xc_leader);
+            ptx::mbar_arrive_cluster(xc_leader);  // first: the next layer's centre tap is waiting for this
             ptx::mbar_arrive(&bars->xe_ready);
+            if (send_left || send_right) {
+              ptx::fence_proxy_async_cluster_release();  // remote generic-proxy stores -> the neighbour's tensor cores
+              ptx::mbar_arrive_cluster(nb_bar);
+            }
           }
         }
-        // skip part: columns [res_cols, 256) of this block, 32 at a time (one 128-byte fp32 row per frame)
+        if (l == 1 && elected && j == 0) SVSK_STAMP(25);  // residual half written
+        // skip part: columns [res_cols, 256) of this block in slabs of 32 (one 128-byte fp32 row per frame).  Each warp
+        // owns whole slabs (the two warps of a lane quarter alternate) and its 32 rows of them: it stages them in a
+        // private 2 x 4 KB piece of the G buffer and issues its own TMA reduce-add — no CTA-wide barrier, no shared
+        // staging buffer to wait for.
         if (res_cols < 256) {
           if (j != NB - 1) __trap();  // skip columns only live in the last block: GEMM2 is done, the G buffer is free
+          const int n_skip = (256 - res_cols) / 32;
+          int m = 0;  // this warp's staging slot: tile sub*2 + m of the G buffer, rows 32q .. 32q+31
 #pragma unroll 1
-          for (int i = res_cols / 32; i < 8; i += 2, skip_slab += 2) {
+          for (int k = sub; k < n_skip; k += 2, m ^= 1) {
+            const int c0 = res_cols + 32 * k;
             uint32_t r0[16], r1[16];
-            ptx::tmem_ld16(tmem + tlane + j * 256 + 16 * (2 * i + sub), r0);
-            ptx::tmem_ld16(tmem + tlane + j * 256 + 16 * (2 * i + 2 + sub), r1);
-            ptx::tmem_ld_wait();
-            if (skip_slab != 0 && (skip_slab & 3) == 0) {  // the four slab buffers go round: wait until they were read
-              if (elected) ptx::bulk_wait_read_all();
-              ptx::named_bar_sync(1, 256);
+            ptx::tmem_ld16(tmem + tlane + j * 256 + c0, r0);
+            ptx::tmem_ld16(tmem + tlane + j * 256 + c0 + 16, r1);
+            if (k >= sub + 4) {  // the slot is used for the second time: its previous TMA must have read it
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              __syncwarp();
             }
-            uint8_t* slab[2];
+            uint8_t* slab = g_smem + (sub * 2 + m) * kSTile;
+            ptx::tmem_ld_wait();
+            const int oc0 = j * 256 + c0;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) slab[u] = g_smem + ((skip_slab + u) & 3) * kSTile;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const uint32_t* r = u ? r1 : r0;
-              const int oc0 = j * 256 + 16 * (2 * (i + u) + sub);
-#pragma unroll
-              for (int e = 0; e < 16; e += 4) {
-                const float4 bo = ptx::ld_shared_v4f(bo_s + oc0 + e);
-                ptx::st_shared_v4f(slab[u] + ptx::sw128_offset((uint32_t)row, (uint32_t)(sub * 4 + (e >> 2))),
-                                   __uint_as_float(r[e]) + bo.x, __uint_as_float(r[e + 1]) + bo.y,
-                                   __uint_as_float(r[e + 2]) + bo.z, __uint_as_float(r[e + 3]) + bo.w);
-              }
+            for (int e = 0; e < 32; e += 4) {
+              const uint32_t* r = e < 16 ? r0 : r1;
+              const float4 bo = ptx::ld_shared_v4f(bo_s + oc0 + e);
+              ptx::st_shared_v4f(slab + ptx::sw128_offset((uint32_t)row, (uint32_t)(e >> 2)),
+                                 __uint_as_float(r[e & 15]) + bo.x, __uint_as_float(r[(e & 15) + 1]) + bo.y,
+                                 __uint_as_float(r[(e & 15) + 2]) + bo.z, __uint_as_float(r[(e & 15) + 3]) + bo.w);
             }
             ptx::fence_proxy_async_smem();
-            ptx::named_bar_sync(1, 256);
-            if (elected) {
-#pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const int ch0 = j * 256 + 32 * (i + u) - C;  // first skip channel of the slab
-                if (l == 0 && a.init_skip) ptx::tma_store_3d(&tm_skip, slab[u], ch0, t_cta0, b);
-                else ptx::tma_reduce_add_3d(&tm_skip, slab[u], ch0, t_cta0, b);
-              }
+            __syncwarp();
+            if (lane == 0) {
+              const int ch0 = oc0 - C;  // first skip channel of the slab
+              if (l == 0 && a.init_skip) ptx::tma_store_3d(&tm_skip, slab + q * 4096, ch0, t_cta0 + q * 32, b);
+              else ptx::tma_reduce_add_3d(&tm_skip, slab + q * 4096, ch0, t_cta0 + q * 32, b);
               ptx::bulk_commit_group();
             }
           }
+          if (l == 1 && elected) SVSK_STAMP(29);
+          if (lane == 0) {
+            ptx::bulk_wait_read_all();  // this warp's slabs are read: the G buffer may take the next conditioner tiles
+            ptx::mbar_arrive(&bars->gc_free);
+          }
+          if (l == 1 && elected) SVSK_STAMP(30);
         }
         // block j has been read out of TMEM: the next layer's GEMM1 may overwrite it
         ptx::tc_fence_before();
         ptx::mbar_arrive_cluster(dr_leader + (uint32_t)j * 8u);
-      }
-      if (elected) {
-        ptx::bulk_wait_read_all();  // skip slabs read: the G buffer may take the next layer's conditioner tiles
-        ptx::mbar_arrive(&bars->gc_free);
       }
       // the bias arrays are rewritten at the top of the next layer: every epilogue thread must be done reading them
       ptx::named_bar_sync(1, 256);
@@ -590,20 +671,32 @@ static int stack_prepare(int C, int H, int* nentries, int* smem_bytes) {
   static bool attr_set[64] = {false};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(diffnet_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(diffnet_stack_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return fail((int)e, "diffnet_stack_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   return 0;
 }
 
+// One cluster per track (halo rows through distributed shared memory) when the track has at most 16 tiles: the cluster
+// size is the next power of two (extra CTAs work on frames past the end: zeros in, nothing out).  Otherwise CTA pairs.
+static int stack_cluster_size(int T) {
+  const int tiles = 2 * ceil_div(T, 256);
+  if (tiles > 16 || getenv("SVSK_STACK_NO_DSMEM")) return 2;
+  int c = 2;
+  while (c < tiles) c *= 2;
+  return c;
+}
+
 static void stack_launch_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int B, int T, int smem_bytes, void* stream) {
   *cfg = cudaLaunchConfig_t{};
-  cfg->gridDim = dim3(2 * ceil_div(T, 256), B);
+  const int csize = stack_cluster_size(T);
+  cfg->gridDim = dim3(csize > 2 ? csize : 2 * ceil_div(T, 256), B);
   cfg->blockDim = dim3(kSThreads);
   cfg->dynamicSmemBytes = smem_bytes;
   cfg->stream = as_stream(stream);
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = csize;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg->attrs = attr;
@@ -624,7 +717,7 @@ extern "C" int svsk_diffnet_stack_fits(int B, int T, int C, int H) {
     cudaGetLastError();
     return 0;
   }
-  return ceil_div(T, 256) * B <= max_clusters ? 1 : 0;
+  return (int)(cfg.gridDim.x / attr[0].val.clusterDim.x) * B <= max_clusters ? 1 : 0;
 }
 
 extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void* stream) {
@@ -655,10 +748,14 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
   int max_clusters = 0;
   cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, diffnet_stack_kernel, &cfg);
   if (oe != cudaSuccess) return fail((int)oe, "diffnet_stack_bf16: cudaOccupancyMaxActiveClusters: %s", cudaGetErrorString(oe));
-  SVSK_REQUIRE(ceil_div(p.T, 256) * p.B <= max_clusters, SVSK_E_ARG,
-               "diffnet_stack_bf16: %d CTA pairs do not fit the device at once (%d); run the layers with svsk_diffnet_block3_bf16",
-               ceil_div(p.T, 256) * p.B, max_clusters);
+  const int n_clusters = (int)(cfg.gridDim.x / attr[0].val.clusterDim.x) * p.B;
+  SVSK_REQUIRE(n_clusters <= max_clusters, SVSK_E_ARG,
+               "diffnet_stack_bf16: %d clusters of %d CTAs do not fit the device at once (%d); run the layers with "
+               "svsk_diffnet_block3_bf16", n_clusters, (int)attr[0].val.clusterDim.x, max_clusters);
 
+  // one cluster per track: each CTA pair fetches (and multicasts) 1/n_pairs of every weight half-tile
+  const uint32_t csz = attr[0].val.clusterDim.x;
+  const uint32_t w_box_rows = csz > 2 ? 128u / (csz / 2) : 128u;
   CUtensorMap tm_xw0, tm_e0, tm_e1, tm_cond, tm_w1, tm_wout, tm_skip;
   {
     uint64_t dims[3] = {(uint64_t)p.C, (uint64_t)p.T, (uint64_t)p.B};
@@ -669,7 +766,7 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
     if ((rc = make_tmap_bf16(&tm_e0, p.edge0, 3, dims, str, boxe))) return rc;
     if ((rc = make_tmap_bf16(&tm_e1, p.edge1, 3, dims, str, boxe))) return rc;
     uint64_t str4[2] = {(uint64_t)p.C * 4, (uint64_t)p.T * p.C * 4};
-    uint32_t box4[3] = {32, 128, 1};
+    uint32_t box4[3] = {32, 32, 1};  // one warp's 32 rows of a 32-column skip slab
     if ((rc = make_tmap_f32(&tm_skip, p.skip32, 3, dims, str4, box4))) return rc;
   }
   {
@@ -682,13 +779,13 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
     const uint64_t K1 = 3 * (uint64_t)p.C + p.H;
     uint64_t dims[3] = {K1, (uint64_t)2 * p.C, (uint64_t)p.L};
     uint64_t str[2] = {K1 * 2, K1 * 2 * 2 * p.C};
-    uint32_t box[3] = {64, 128, 1};
+    uint32_t box[3] = {64, w_box_rows, 1};
     if ((rc = make_tmap_bf16(&tm_w1, p.w1p, 3, dims, str, box))) return rc;
   }
   {
     uint64_t dims[3] = {(uint64_t)p.C, (uint64_t)2 * p.C, (uint64_t)p.L};
     uint64_t str[2] = {(uint64_t)p.C * 2, (uint64_t)p.C * 2 * 2 * p.C};
-    uint32_t box[3] = {64, 128, 1};
+    uint32_t box[3] = {64, w_box_rows, 1};
     if ((rc = make_tmap_bf16(&tm_wout, p.woutp, 3, dims, str, box))) return rc;
   }
 
@@ -696,7 +793,7 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
   a.stepbias = p.stepbias;
   a.bout = p.bout;
   a.flags = p.flags;
-  a.proxy_fence = getenv("SVSK_STACK_NO_PROXY_FENCE") ? 0 : 1;
+  a.dsmem_halo = attr[0].val.clusterDim.x > 2 ? 1 : 0;
   a.B = p.B; a.T = p.T; a.C = p.C; a.H = p.H; a.L = p.L;
   a.sb_batch_stride = p.stepbias_batch_stride;
   a.sb_layer_stride = p.stepbias_layer_stride;

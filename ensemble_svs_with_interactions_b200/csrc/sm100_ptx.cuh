@@ -256,6 +256,11 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -335,6 +340,15 @@ __device__ __forceinline__ void umma_commit2_mc(uint64_t* bar, uint16_t mask) {
                "h"(mask)
                : "memory");
 }
+// 16-byte store into another CTA's shared memory (address from mapa)
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// Before signalling another CTA that generic-proxy stores into ITS shared memory are done and may be read by its tensor
+// cores (async proxy): make them visible cluster-wide, then cross the proxy.
+__device__ __forceinline__ void fence_proxy_async_cluster_release() {
+  asm volatile("fence.acq_rel.cluster;\n\tfence.proxy.async.shared::cluster;" ::: "memory");
+}
 __device__ __forceinline__ void st_shared_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -349,6 +363,16 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
                    reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
+}
+// TMA load multicast to the CTAs of `cta_mask` (bit = rank in the cluster): the tile lands at the same CTA-relative
+// shared-memory offset in each of them and each one's mbarrier (same offset) gets the complete_tx.
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], "
+      "[%2], %6;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+      : "memory");
 }
 // global[tile] += smem[tile] (element type and shape come from the tensor map; fp32 here), performed at L2
 __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {

@@ -52,9 +52,14 @@ torch.cuda.synchronize()
 os.environ.pop("SVSK_DIFFNET_TIMELINE")
 d = dbg.view(512, 32).cpu()
 d = d[(d[:, 15] > 0) & (d[:, 2] > 0)]
-names = {9: "layer 0 output in place (act producer)", 10: "edge rows stored", 11: "flag published", 12: "neighbours' flags seen",
+d[:, 18:] = torch.where(d[:, 18:] == 0, d[:, :1], d[:, 18:])   # stamps a mode does not take
+d[:, 1:16] = torch.where(d[:, 1:16] == 0, d[:, :1], d[:, 1:16])
+names = {24: "epilogue: D2[0] complete", 25: "residual written", 26: "D2[1] complete", 27: "4 skip slabs staged", 28: "... and read by TMA",
+         29: "8 skip slabs staged", 30: "G buffer released", 9: "layer 0 output in place (act producer)", 10: "edge rows stored", 11: "flag published", 12: "neighbours' flags seen",
          13: "halo loads issued", 14: "G buffer free", 2: "layer 1: centre rows ready (MMA thread)", 3: "halo rows landed", 4: "first cond tile + D1[1] drained", 5: "block 0 issued",
          6: "block 1 issued", 7: "G ready", 8: "GEMM2 issued", 15: "kernel end"}
 rel = (d - d[:, :1]).float().median(dim=0).values
 print(f"{d.shape[0]} leader CTAs; median cycles since CTA start: " + " | ".join(f"{n} @{int(rel[i])}" for i, n in names.items()))
+raw = d.float().median(dim=0).values
+print(f"   MMA thread: {int(raw[17])} of {plan.L * 40} ring entries not yet landed when reached, {int(raw[16])} cycles waiting for them")
 print(f"   whole kernel {int(rel[15])} cycles = {int(rel[15]) / plan.L:.0f} per layer")
