@@ -89,6 +89,22 @@ def _block_fp32(layer: ResidualBlock, x, cond, dp, skip=None, init_skip=True):
     return x, skip
 
 
+_STACK_FIT_CACHE = {}
+
+
+def _stack_tracks_per_launch(B, T, C, H):
+    """Largest number of tracks whose CTA pairs all fit the device at once (0 if not even one track does)."""
+    key = (B, T, C, H)
+    if key not in _STACK_FIT_CACHE:
+        b = B
+        while b > 0 and not ops.diffnet_stack_fits(b, T, C, H):
+            b -= 1
+        if len(_STACK_FIT_CACHE) > 256:
+            _STACK_FIT_CACHE.clear()
+        _STACK_FIT_CACHE[key] = b
+    return _STACK_FIT_CACHE[key]
+
+
 class _Bf16Plan:
     """Packed weights of one DiffNet for the tensor-core path (rebuilt when any parameter changes)."""
 
@@ -220,15 +236,23 @@ class DiffNet(nn.Module):
         xb1 = torch.empty((B, T, C), device=dev, dtype=bf16)
         skip32 = torch.empty((B, T, C), device=dev, dtype=f32)
         time_tile = getattr(self, "time_tile", 0)
-        use_stack = (not time_tile and os.environ.get("SVSK_DIFFNET_STACK", "1") != "0" and max(plan.dilations) <= 8
-                     and os.environ.get("SVSK_DIFFNET_KERNEL", "3") == "3" and ops.diffnet_stack_fits(B, T, C, plan.H))
-        if use_stack:
-            # one launch for all L blocks: every CTA pair keeps its 256-frame tile, neighbours exchange 8 edge rows per layer
+        stack_b = 0  # tracks per launch of the one-launch residual stack (0: run the layers one kernel at a time)
+        if (not time_tile and os.environ.get("SVSK_DIFFNET_STACK", "1") != "0" and max(plan.dilations) <= 8
+                and os.environ.get("SVSK_DIFFNET_KERNEL", "3") == "3"):
+            stack_b = _stack_tracks_per_launch(B, T, C, plan.H)
+        if stack_b:
+            # one launch for all L blocks of `stack_b` tracks: every CTA pair keeps its 256-frame tile across the layers,
+            # neighbouring tiles exchange 8 edge rows per layer.  All pairs of a launch must be resident at once, so a
+            # batch that exceeds one wave (e.g. 6 x 6000 frames) is split into groups of tracks.
             ops.linear_bf16(specb, plan.w_in, plan.b_in, act=ops.ACT_RELU, out_bf16=xb0)
             xb2 = torch.empty((B, T, C), device=dev, dtype=bf16)
             flags = torch.empty((B * 2 * ((T + 255) // 256),), device=dev, dtype=torch.int32)
-            ops.diffnet_stack_bf16(xb0, xb1, xb2, skip32, condb, plan.w1p_all, plan.woutp_all, stepbias, plan.bout_all,
-                                   flags, plan.dilations, stepbias_batch_stride=sb_batch, stepbias_layer_stride=sb_layer)
+            per_row = stepbias.shape[1] == B and B > 1
+            for b0 in range(0, B, stack_b):
+                b1 = min(B, b0 + stack_b)
+                ops.diffnet_stack_bf16(xb0[b0:b1], xb1[b0:b1], xb2[b0:b1], skip32[b0:b1], condb[b0:b1], plan.w1p_all,
+                                       plan.woutp_all, stepbias[:, b0:b1] if per_row else stepbias, plan.bout_all, flags,
+                                       plan.dilations, stepbias_batch_stride=sb_batch, stepbias_layer_stride=sb_layer)
         else:
             x32 = torch.empty((B, T, C), device=dev, dtype=f32)
             ops.linear_bf16(specb, plan.w_in, plan.b_in, act=ops.ACT_RELU, out_bf16=xb0, out_f32=x32)

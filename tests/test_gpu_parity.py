@@ -437,12 +437,22 @@ def test_diffnet_stack_refuses_grids_that_do_not_fit():
     ops = _ops()
     assert not ops.diffnet_stack_fits(64, 2000, 256, 256)   # 512 CTA pairs
     assert ops.diffnet_stack_fits(6, 2000, 256, 256)        # BASELINE config 2: 48 pairs
-    # the module then runs the layers one launch at a time
+    # the module then splits the batch into groups of tracks that do fit (one stack launch per group) ...
+    import os
     m = _random_diffnet(128, 64, 16, 2, seed=1).to(DEV)
     B, T = 40, 1100
     assert not ops.diffnet_stack_fits(B, T, 128, 64)
-    y = m(torch.randn(B, 1, 16, T, device=DEV), torch.zeros(B, dtype=torch.long, device=DEV), torch.randn(B, 64, T, device=DEV))
+    spec = torch.randn(B, 1, 16, T, device=DEV); cond = torch.randn(B, 64, T, device=DEV)
+    t = torch.arange(B, device=DEV) % 100
+    y = m(spec, t, cond)
     assert torch.isfinite(y).all()
+    # ... and gets what the layer-at-a-time kernels compute (per-row step biases must follow their tracks into the groups)
+    os.environ["SVSK_DIFFNET_STACK"] = "0"
+    try:
+        ref = m(spec, t, cond)
+    finally:
+        os.environ.pop("SVSK_DIFFNET_STACK")
+    close_bf16(y, ref, 1e-2, 3e-2)
 
 
 def test_diffnet_bf16_forward_vs_oracle():
