@@ -49,6 +49,17 @@ class DiffnetStackParams(C.Structure):
     ]
 
 
+class DiffnetStepParams(C.Structure):
+    _fields_ = [
+        ("skip32", C.c_void_p), ("x32s", C.c_void_p), ("z", C.c_void_p), ("eps_out", C.c_void_p), ("xb_out", C.c_void_p),
+        ("w_skip", C.c_void_p), ("w_out", C.c_void_p), ("w_in", C.c_void_p),
+        ("b_skip", C.c_void_p), ("b_out", C.c_void_p), ("b_in", C.c_void_p), ("t", C.c_void_p),
+        ("sra", C.c_void_p), ("srm1", C.c_void_p), ("c1", C.c_void_p), ("c2", C.c_void_p), ("plv", C.c_void_p),
+        ("skip_scale", C.c_float),
+        ("B", C.c_int32), ("T", C.c_int32), ("C", C.c_int32), ("Mp", C.c_int32), ("clip_denoised", C.c_int32),
+    ]
+
+
 class LinearBf16Params(C.Structure):
     _fields_ = [
         ("a", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("y_bf16", C.c_void_p), ("y_f32", C.c_void_p),
@@ -102,6 +113,7 @@ _SIGNATURES = {
     "svsk_diffnet_block3_bf16": [C.POINTER(DiffnetBlockParams), _V],
     "svsk_diffnet_stack_bf16": [C.POINTER(DiffnetStackParams), _V],
     "svsk_diffnet_stack_fits": [C.c_int, C.c_int, C.c_int, C.c_int],
+    "svsk_diffnet_step_bf16": [C.POINTER(DiffnetStepParams), _V],
     "svsk_diffnet_pack_block": [_V, _V, _V, _V, _V, _I, _I, _V],
     "svsk_diffnet_packed_row": [_I, _I],
     "svsk_linear_bf16": [C.POINTER(LinearBf16Params), _V],

@@ -220,19 +220,26 @@ class DiffNet(nn.Module):
         return out
 
     # ------------------------------------------------------------------ engines
-    def denoise_ntc_bf16(self, x32s, condb, stepbias, plan=None):
-        """x32s [B,T,Mp] fp32 (channels >= M are ignored), condb [B,T,H] bf16, stepbias [L, Bt, 3*2C] fp32 (any layer
-        stride; Bt = B rows, or 1 row shared by the batch).  Returns eps [B,T,Mp] fp32 (padded channels = 0)."""
+    def project_in_bf16(self, x32s, plan=None, out=None):
+        """relu(input_projection(x)) (denoiser.py:109-112) as bf16 [B,T,C], from the fp32 NTC state [B,T,Mp]."""
         plan = self.bf16_plan() if plan is None else plan
         B, T, _ = x32s.shape
-        C, L = plan.C, plan.L
-        dev = x32s.device
+        xb0 = torch.empty((B, T, plan.C), device=x32s.device, dtype=bf16) if out is None else out
+        ops.linear_bf16(ops.cast_scale_bf16(x32s), plan.w_in, plan.b_in, act=ops.ACT_RELU, out_bf16=xb0)
+        return xb0
+
+    def residual_stack_bf16(self, xb0, condb, stepbias, plan=None):
+        """The L residual blocks (denoiser.py:114-118) on xb0 [B,T,C] bf16 (clobbered); returns the fp32 sum of the skip
+        outputs [B,T,C].  stepbias [L, Bt, 3*2C] fp32 (any layer stride; Bt = B rows, or 1 row shared by the batch)."""
+        plan = self.bf16_plan() if plan is None else plan
+        B, T, C = xb0.shape
+        L = plan.L
+        dev = xb0.device
         if stepbias.dim() != 3 or stepbias.shape[0] != L or stepbias.shape[1] not in (1, B) or stepbias.stride(2) != 1:
             raise ValueError(f"stepbias must be [L={L}, 1 or B={B}, {6 * C}], got {tuple(stepbias.shape)}")
         sb_layer = stepbias.stride(0)
-        sb_batch = stepbias.stride(1) if stepbias.shape[1] == B and B > 1 else 0
-        specb = ops.cast_scale_bf16(x32s)
-        xb0 = torch.empty((B, T, C), device=dev, dtype=bf16)
+        per_row = stepbias.shape[1] == B and B > 1
+        sb_batch = stepbias.stride(1) if per_row else 0
         xb1 = torch.empty((B, T, C), device=dev, dtype=bf16)
         skip32 = torch.empty((B, T, C), device=dev, dtype=f32)
         time_tile = getattr(self, "time_tile", 0)
@@ -244,24 +251,51 @@ class DiffNet(nn.Module):
             # one launch for all L blocks of `stack_b` tracks: every CTA pair keeps its 256-frame tile across the layers,
             # neighbouring tiles exchange 8 edge rows per layer.  All pairs of a launch must be resident at once, so a
             # batch that exceeds one wave (e.g. 6 x 6000 frames) is split into groups of tracks.
-            ops.linear_bf16(specb, plan.w_in, plan.b_in, act=ops.ACT_RELU, out_bf16=xb0)
             xb2 = torch.empty((B, T, C), device=dev, dtype=bf16)
             flags = torch.empty((B * 2 * ((T + 255) // 256),), device=dev, dtype=torch.int32)
-            per_row = stepbias.shape[1] == B and B > 1
             for b0 in range(0, B, stack_b):
                 b1 = min(B, b0 + stack_b)
                 ops.diffnet_stack_bf16(xb0[b0:b1], xb1[b0:b1], xb2[b0:b1], skip32[b0:b1], condb[b0:b1], plan.w1p_all,
                                        plan.woutp_all, stepbias[:, b0:b1] if per_row else stepbias, plan.bout_all, flags,
                                        plan.dilations, stepbias_batch_stride=sb_batch, stepbias_layer_stride=sb_layer)
         else:
-            x32 = torch.empty((B, T, C), device=dev, dtype=f32)
-            ops.linear_bf16(specb, plan.w_in, plan.b_in, act=ops.ACT_RELU, out_bf16=xb0, out_f32=x32)
+            x32 = torch.empty((B, T, C), device=dev, dtype=f32) if time_tile else skip32  # (only the single-CTA kernel uses it)
             cur, nxt = xb0, xb1
             for i, lw in enumerate(plan.layers):
                 ops.diffnet_block_bf16(cur, nxt, x32, skip32, condb, lw["w1p"], lw["woutp"], stepbias[i], lw["bout"],
                                        dilation=lw["dilation"], stepbias_batch_stride=sb_batch, init_skip=(i == 0),
                                        write_x=(i < L - 1), time_tile=time_tile)
                 cur, nxt = nxt, cur
+        return skip32
+
+    def denoise_ntc_bf16(self, x32s, condb, stepbias, plan=None):
+        """x32s [B,T,Mp] fp32 (channels >= M are ignored), condb [B,T,H] bf16, stepbias as in residual_stack_bf16.
+        Returns eps [B,T,Mp] fp32 (padded channels = 0)."""
+        plan = self.bf16_plan() if plan is None else plan
+        if getattr(self, "time_tile", 0):  # the single-CTA kernel keeps an fp32 master of the residual stream
+            return self._denoise_ntc_bf16_v1(x32s, condb, stepbias, plan)
+        skip32 = self.residual_stack_bf16(self.project_in_bf16(x32s, plan), condb, stepbias, plan)
+        skipb = ops.cast_scale_bf16(skip32, alpha=1.0 / sqrt(plan.L))
+        hb, _ = ops.linear_bf16(skipb, plan.w_skip, plan.b_skip, act=ops.ACT_RELU, want_bf16=True)
+        _, eps = ops.linear_bf16(hb, plan.w_out, plan.b_out, want_f32=True)
+        return eps
+
+    def _denoise_ntc_bf16_v1(self, x32s, condb, stepbias, plan):
+        B, T, _ = x32s.shape
+        C, L = plan.C, plan.L
+        dev = x32s.device
+        sb_batch = stepbias.stride(1) if stepbias.shape[1] == B and B > 1 else 0
+        xb0 = torch.empty((B, T, C), device=dev, dtype=bf16)
+        xb1 = torch.empty((B, T, C), device=dev, dtype=bf16)
+        x32 = torch.empty((B, T, C), device=dev, dtype=f32)
+        skip32 = torch.empty((B, T, C), device=dev, dtype=f32)
+        ops.linear_bf16(ops.cast_scale_bf16(x32s), plan.w_in, plan.b_in, act=ops.ACT_RELU, out_bf16=xb0, out_f32=x32)
+        cur, nxt = xb0, xb1
+        for i, lw in enumerate(plan.layers):
+            ops.diffnet_block_bf16(cur, nxt, x32, skip32, condb, lw["w1p"], lw["woutp"], stepbias[i], lw["bout"],
+                                   dilation=lw["dilation"], stepbias_batch_stride=sb_batch, init_skip=(i == 0),
+                                   write_x=(i < L - 1), time_tile=self.time_tile)
+            cur, nxt = nxt, cur
         skipb = ops.cast_scale_bf16(skip32, alpha=1.0 / sqrt(L))
         hb, _ = ops.linear_bf16(skipb, plan.w_skip, plan.b_skip, act=ops.ACT_RELU, want_bf16=True)
         _, eps = ops.linear_bf16(hb, plan.w_out, plan.b_out, want_f32=True)

@@ -11,6 +11,9 @@ from __future__ import annotations
 from collections import deque
 
 import numpy as np
+import math
+import os
+
 import torch
 
 from .. import _lib as _L
@@ -188,6 +191,18 @@ class GaussianDiffusion(BaseModel):
         table = self._step_table()
         B = x32s.shape[0]
         tabs = self._tables()
+        if os.environ.get("SVSK_DIFFNET_STEP", "1") != "0" and not getattr(den, "time_tile", 0) and plan.Mp <= 128:
+            # per step: the residual stack, then ONE kernel for tail projections + p_sample update + the next step's
+            # input projection (svsk_diffnet_step_bf16)
+            sched = [tabs[k] for k in ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+                                       "posterior_mean_coef2", "posterior_log_variance_clipped")]
+            xb0 = den.project_in_bf16(x32s, plan)
+            for i in reversed(range(self.K_step)):
+                skip32 = den.residual_stack_bf16(xb0, condb, table[:, i:i + 1], plan)   # row i of every layer's table
+                ops.diffnet_step_bf16(skip32, x32s, z_ntc[i], self._t_const[i], sched, plan.w_skip, plan.b_skip, plan.w_out,
+                                      plan.b_out, skip_scale=1.0 / math.sqrt(plan.L), w_in=plan.w_in, b_in=plan.b_in,
+                                      xb_out=xb0 if i > 0 else None)
+            return x32s
         for i in reversed(range(self.K_step)):
             # row i of every layer's table, shared by the whole batch
             eps = den.denoise_ntc_bf16(x32s, condb, table[:, i:i + 1], plan=plan)

@@ -251,6 +251,23 @@ def diffnet_stack_bf16(xb_in, edge0, edge1, skip32, cond, w1p_all, woutp_all, st
     L.check(L.lib().svsk_diffnet_stack_bf16(C.byref(p), L.stream_ptr()), "diffnet_stack_bf16")
 
 
+def diffnet_step_bf16(skip32, x32s, z, t, tables, w_skip, b_skip, w_out, b_out, *, skip_scale, w_in=None, b_in=None, xb_out=None,
+                      eps_out=None, clip_denoised=True):
+    """Tail projections + DDPM update (x32s in place) + the next call's input projection (into xb_out, if given).
+    tables: the five schedule vectors of ddpm_update_f32, in its order."""
+    B, T, Cc = skip32.shape
+    p = L.DiffnetStepParams()
+    p.skip32, p.x32s, p.z = L.ptr(skip32, f32, "skip32"), L.ptr(x32s, f32, "x32s"), L.ptr(z, f32, "z")
+    p.eps_out, p.xb_out = L.ptr(eps_out, f32, "eps_out"), L.ptr(xb_out, bf16, "xb_out")
+    p.w_skip, p.w_out, p.w_in = L.ptr(w_skip, bf16, "w_skip"), L.ptr(w_out, bf16, "w_out"), L.ptr(w_in, bf16, "w_in")
+    p.b_skip, p.b_out, p.b_in = L.ptr(b_skip, f32, "b_skip"), L.ptr(b_out, f32, "b_out"), L.ptr(b_in, f32, "b_in")
+    p.t = L.ptr(t, torch.int64, "t")
+    p.sra, p.srm1, p.c1, p.c2, p.plv = [L.ptr(x, f32, "schedule table") for x in tables]
+    p.skip_scale = float(skip_scale)
+    p.B, p.T, p.C, p.Mp, p.clip_denoised = B, T, Cc, x32s.shape[2], int(clip_denoised)
+    L.check(L.lib().svsk_diffnet_step_bf16(C.byref(p), L.stream_ptr()), "diffnet_step_bf16")
+
+
 def linear_bf16(a, w, bias=None, *, act=ACT_NONE, want_bf16=False, want_f32=False, out_bf16=None, out_f32=None):
     """a [..., K] bf16 (row-major rows), w [Cout, K] bf16 -> [..., Cout]."""
     K = a.shape[-1]

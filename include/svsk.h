@@ -234,6 +234,38 @@ typedef struct svsk_diffnet_stack_params {
 SVSK_API int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* p, void* stream);
 SVSK_API int svsk_diffnet_stack_fits(int B, int T, int C, int H);
 
+/* Everything between two residual-stack launches of a DDPM sampling step in one launch per 128-frame tile:
+ *   eps = output_projection(relu(skip_projection(skip32 * skip_scale)))      denoiser.py:120-123
+ *   x   = p_sample update of x with eps, noise z and the step's schedule coefficients, in place (the arithmetic of
+ *         svsk_ddpm_update_f32; diffusion.py:164-204)
+ *   xb_out = relu(input_projection(x)) as bf16 [B][T][C] for the next denoiser call (denoiser.py:109-112); pass
+ *         xb_out = NULL on the last step (w_in / b_in are then unused).
+ * NTC fp32 state tensors [B][T][Mp] (Mp = M rounded up to 16; padded channels carry zeros through zero weights and
+ * biases), bf16 weights w_skip [C][C], w_out [Mp][C], w_in [C][Mp], fp32 biases (b_out has Mp entries), t [B] int64.
+ * eps_out (optional) receives eps. */
+typedef struct svsk_diffnet_step_params {
+  const float* skip32;
+  float* x32s;
+  const float* z;
+  float* eps_out;
+  void* xb_out;
+  const void* w_skip;
+  const void* w_out;
+  const void* w_in;
+  const float* b_skip;
+  const float* b_out;
+  const float* b_in;
+  const int64_t* t;
+  const float* sqrt_recip_alphas_cumprod;
+  const float* sqrt_recipm1_alphas_cumprod;
+  const float* posterior_mean_coef1;
+  const float* posterior_mean_coef2;
+  const float* posterior_log_variance_clipped;
+  float skip_scale;
+  int32_t B, T, C, Mp, clip_denoised;
+} svsk_diffnet_step_params;
+SVSK_API int svsk_diffnet_step_bf16(const svsk_diffnet_step_params* p, void* stream);
+
 /* Pack one block's weights (fp32, reference state_dict layout) for svsk_diffnet_block_bf16.
  *   dilated_w [2C][C][3], cond_w [2C][H][1], out_w [2C][C][1]  ->  w1p [2C][3C+H] bf16, woutp [2C][C] bf16.
  * Row r of the reference maps to packed row perm(r): gate rows of channel block q at 256q..256q+127, filter rows at

@@ -455,6 +455,45 @@ def test_diffnet_stack_refuses_grids_that_do_not_fit():
     close_bf16(y, ref, 1e-2, 3e-2)
 
 
+@pytest.mark.parametrize("C,H,M,B,T", [(256, 256, 80, 2, 300), (128, 128, 5, 3, 517), (256, 128, 60, 1, 128), (128, 64, 60, 2, 40)])
+def test_diffnet_step_kernel_matches_separate_kernels(C, H, M, B, T):
+    """svsk_diffnet_step_bf16 (tail projections + p_sample update + next input projection in one launch) against the
+    same chain run as separate libsvsk kernels: same bf16 operands and fp32 accumulation."""
+    from ensemble_svs_with_interactions_b200.diffsinger import GaussianDiffusion
+    ops = _ops()
+    den = _random_diffnet(C, H, M, 3, seed=C + M + T)
+    m = GaussianDiffusion(H, M, den, K_step=100).to(DEV).eval()
+    plan = den.bf16_plan()
+    g = torch.Generator().manual_seed(T + M)
+    skip32 = (torch.randn(B, T, C, generator=g) * 2).to(DEV)
+    x = torch.randn(B, T, plan.Mp, generator=g).to(DEV); x[:, :, M:] = 0
+    z = torch.randn(B, T, plan.Mp, generator=g).to(DEV); z[:, :, M:] = 0
+    t = torch.tensor([0, 57, 99][:B] if B <= 3 else list(range(B)), device=DEV)
+    tabs = m._tables()
+    scale = 1.0 / math.sqrt(plan.L)
+    # reference chain
+    hb, _ = ops.linear_bf16(ops.cast_scale_bf16(skip32, alpha=scale), plan.w_skip, plan.b_skip, act=ops.ACT_RELU, want_bf16=True)
+    _, eps_ref = ops.linear_bf16(hb, plan.w_out, plan.b_out, want_f32=True)
+    x_ref = ops.ddpm_update_f32(x, eps_ref, z, t, tabs, True)
+    xb_ref = den.project_in_bf16(x_ref, plan)
+    # fused
+    sched = [tabs[k] for k in ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+                               "posterior_mean_coef2", "posterior_log_variance_clipped")]
+    x_new = x.clone(); eps = torch.full_like(x, float("nan")); xb = torch.full((B, T, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.diffnet_step_bf16(skip32, x_new, z, t, sched, plan.w_skip, plan.b_skip, plan.w_out, plan.b_out, skip_scale=scale,
+                          w_in=plan.w_in, b_in=plan.b_in, xb_out=xb, eps_out=eps)
+    torch.cuda.synchronize()
+    close32(eps, eps_ref, 1e-4)
+    close32(x_new, x_ref, 1e-4)
+    if plan.Mp > M:
+        assert float((x_new[:, :, M:]).abs().max()) == 0.0      # padded channels stay inert
+    close_bf16(xb.float(), xb_ref.float(), 4e-3, 2e-2)
+    # last step: no head
+    x_last = x.clone()
+    ops.diffnet_step_bf16(skip32, x_last, z, t, sched, plan.w_skip, plan.b_skip, plan.w_out, plan.b_out, skip_scale=scale)
+    assert torch.equal(x_last, x_new)
+
+
 def test_diffnet_bf16_forward_vs_oracle():
     """Full 20-layer denoiser at the recipe width vs the fp32 CPU oracle (true bf16-vs-fp32 error)."""
     m = _random_diffnet(256, 256, 80, 20, seed=7)
