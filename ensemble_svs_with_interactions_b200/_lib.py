@@ -114,6 +114,8 @@ _SIGNATURES = {
     "svsk_diffnet_stack_bf16": [C.POINTER(DiffnetStackParams), _V],
     "svsk_diffnet_stack_fits": [C.c_int, C.c_int, C.c_int, C.c_int],
     "svsk_diffnet_step_bf16": [C.POINTER(DiffnetStepParams), _V],
+    "svsk_upsample_fused": [_V, _V, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_int, _V, _V, C.c_int, _V],
+    "svsk_expand1_bf16": [_V, C.c_longlong, _V, _V, _V, C.c_int, C.c_int, C.c_int, _V],
     "svsk_diffnet_pack_block": [_V, _V, _V, _V, _V, _I, _I, _V],
     "svsk_diffnet_packed_row": [_I, _I],
     "svsk_linear_bf16": [C.POINTER(LinearBf16Params), _V],

@@ -251,6 +251,40 @@ def diffnet_stack_bf16(xb_in, edge0, edge1, skip32, cond, w1p_all, woutp_all, st
     L.check(L.lib().svsk_diffnet_stack_bf16(C.byref(p), L.stream_ptr()), "diffnet_stack_bf16")
 
 
+def upsample_fused_supported(scales, A):
+    hop = 1
+    for sc in scales:
+        hop *= int(sc)
+    return (1 <= len(scales) <= 6 and all(2 <= int(sc) <= 16 for sc in scales) and A <= 128
+            and sum(2 * int(sc) + 1 for sc in scales) <= 128 and 127 // hop + 2 * len(scales) + 4 <= 48)
+
+
+def upsample_fused(c, taps, scales, *, want_bf16=True, want_f32=False):
+    """UpsampleNetwork in one pass: c [B,A,F] fp32 -> NTC [B, F*prod(scales), Ap] (bf16 and/or fp32), Ap = A rounded up to 8."""
+    B, A, F = c.shape
+    hop = 1
+    for sc in scales:
+        hop *= int(sc)
+    Ap = (A + 7) // 8 * 8
+    ob = torch.empty((B, F * hop, Ap), device=c.device, dtype=bf16) if want_bf16 else None
+    of = torch.empty((B, F * hop, Ap), device=c.device, dtype=f32) if want_f32 else None
+    sc = (C.c_int32 * len(scales))(*[int(x) for x in scales])
+    L.check(L.lib().svsk_upsample_fused(L.ptr(c, f32, "c"), L.ptr(taps, f32, "taps"), sc, len(scales), B, A, F, L.ptr(ob, bf16),
+                                        L.ptr(of, f32), Ap, L.stream_ptr()), "upsample_fused")
+    return ob, of
+
+
+def expand1_bf16(x_row, w, bias, Cc):
+    """x_row: [B, T] fp32 view whose rows are contiguous (any batch stride) -> [B, T, Cc] bf16 = w * x + bias."""
+    B, T = x_row.shape
+    if not x_row.is_cuda or x_row.dtype != f32 or x_row.stride(1) != 1:
+        raise RuntimeError("expand1_bf16: x_row must be a CUDA float32 [B, T] view with unit time stride")
+    out = torch.empty((B, T, Cc), device=x_row.device, dtype=bf16)
+    L.check(L.lib().svsk_expand1_bf16(C.c_void_p(x_row.data_ptr()), x_row.stride(0) if B > 1 else T, L.ptr(w, f32, "w"),
+                                      L.ptr(bias, f32, "bias"), L.ptr(out), B, T, Cc, L.stream_ptr()), "expand1_bf16")
+    return out
+
+
 def diffnet_step_bf16(skip32, x32s, z, t, tables, w_skip, b_skip, w_out, b_out, *, skip_scale, w_in=None, b_in=None, xb_out=None,
                       eps_out=None, clip_denoised=True):
     """Tail projections + DDPM update (x32s in place) + the next call's input projection (into xb_out, if given).

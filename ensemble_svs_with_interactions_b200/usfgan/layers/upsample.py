@@ -50,6 +50,16 @@ class UpsampleNetwork(torch.nn.Module):
             c = ops.upsample_smooth_f32(c, taps, scale)
         return c
 
+    def supports_fused(self, channels):
+        return ops.upsample_fused_supported(self.upsample_scales, channels)
+
+    def forward_ntc(self, c, want_bf16=True, want_f32=False):
+        """All stages in one pass, channel-last output (svsk_upsample_fused): c (B, C, T') fp32 ->
+        (B, T' * prod(scales), C rounded up to 8) bf16 and/or fp32."""
+        taps = torch.cat([effective_weight(self.up_layers[2 * n + 1]).reshape(-1) for n in range(len(self.upsample_scales))])
+        return ops.upsample_fused(c.to(torch.float32).contiguous(), taps.to(torch.float32).contiguous(), self.upsample_scales,
+                                  want_bf16=want_bf16, want_f32=want_f32)
+
 
 class ConvInUpsampleNetwork(torch.nn.Module):
     def __init__(self, upsample_scales, nonlinear_activation=None, nonlinear_activation_params={},
@@ -69,3 +79,12 @@ class ConvInUpsampleNetwork(torch.nn.Module):
         c = ops.conv1d_f32(c.to(torch.float32).contiguous(), effective_weight(self.conv_in), None,
                            pad_mode=ops.PAD_VALID)
         return self.upsample(c)
+
+    def supports_fused(self):
+        return self.upsample.supports_fused(self.conv_in.out_channels)
+
+    def forward_ntc_bf16(self, c):
+        """c (B, C, T' + 2*window) -> (B, T' * prod(scales), C rounded up to 8) bf16, no fp32 sample-rate intermediate."""
+        c = ops.conv1d_f32(c.to(torch.float32).contiguous(), effective_weight(self.conv_in), None,
+                           pad_mode=ops.PAD_VALID)
+        return self.upsample.forward_ntc(c)[0]

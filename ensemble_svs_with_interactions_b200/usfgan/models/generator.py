@@ -22,6 +22,12 @@ def _conv1x1(m, x, in_relu=False):
     return ops.conv1d_f32(x, effective_weight(m), m.bias, in_relu=in_relu)
 
 
+def _conv1x1_expand_ntc(m, x_row):
+    """1 -> C pointwise conv of one input channel ([B, T] view) straight to NTC bf16."""
+    w = effective_weight(m).reshape(-1).to(f32).contiguous()
+    return ops.expand1_bf16(x_row, w, m.bias.to(f32).contiguous() if m.bias is not None else None, w.numel())
+
+
 class _GeneratorBase(nn.Module):
     precision = "auto"   # "auto" | "bf16" | "fp32": bf16 = fused tcgen05 block kernel for the residual stacks
 
@@ -264,14 +270,17 @@ class ParallelHnUSFGANGenerator(_HnBase):
         self._check(x)
         cache = {}
         if wave_only and self._ntc_fast_path_ok():
-            # everything after the aux upsampling stays NTC bf16 on tensor cores
-            c = self.upsample_net(c)
-            assert c.size(-1) == x.size(-1)
-            auxb = self._aux_ntc(c)
+            # everything stays NTC bf16: the aux features are upsampled straight into that layout (one pass over all
+            # stages), the two 1 -> C input convs write it directly
+            if self.upsample_net.supports_fused():
+                auxb = self.upsample_net.forward_ntc_bf16(c)
+            else:
+                auxb = self._aux_ntc(self.upsample_net(c))
+            assert auxb.size(1) == x.size(-1)
             ab = self.periodicity_estimator.forward_ntc_bf16(auxb)
-            xf = x.to(f32)
-            hb, _ = ops.nct_to_ntc(_conv1x1(self.conv_first_sine, xf[:, 0:1].contiguous()))
-            nb, _ = ops.nct_to_ntc(_conv1x1(self.conv_first_noise, xf[:, 1:2].contiguous()))
+            xf = x.to(f32).contiguous()
+            hb = _conv1x1_expand_ntc(self.conv_first_sine, xf[:, 0])
+            nb = _conv1x1_expand_ntc(self.conv_first_noise, xf[:, 1])
             hb = self.harmonic_network.forward_ntc_bf16(hb, auxb, d, cache)
             nb = self.noise_network.forward_ntc_bf16(nb, auxb, d, cache)
             sb = ops.periodic_mix_bf16(ab, hb, nb)

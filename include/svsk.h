@@ -266,6 +266,20 @@ typedef struct svsk_diffnet_step_params {
 } svsk_diffnet_step_params;
 SVSK_API int svsk_diffnet_step_bf16(const svsk_diffnet_step_params* p, void* stream);
 
+/* The whole UpsampleNetwork (nnsvs/usfgan/layers/upsample.py:61-128) in one pass from frame rate to sample rate, written
+ * channel-last: c [B][A][F] fp32 (the output of conv_in) -> out [B][T = F * prod(scales)][Ap] as bf16 and/or fp32
+ * (Ap >= A, a multiple of 8; channels A..Ap-1 are zero).  taps: the (2 s_k + 1)-tap smoothing filters of the stages,
+ * concatenated; scales: host array.  Same arithmetic as n_stages calls of svsk_upsample_smooth_f32 up to fp32 summation
+ * order, including the zero padding of every stage at the sequence ends.  Needs 2 <= s_k <= 16, A <= 128 and
+ * 127 / prod(scales) + 2 n_stages + 4 <= 48. */
+SVSK_API int svsk_upsample_fused(const float* c, const float* taps, const int32_t* scales, int n_stages, int B, int A, int F,
+                                 void* out_bf16, float* out_f32, int Ap, void* stream);
+
+/* Pointwise 1 -> C Conv1d straight to NTC bf16 (generator.py conv_first_sine / conv_first_noise):
+ * out[b][t][c] = w[c] * x[b * x_batch_stride + t] + bias[c]. */
+SVSK_API int svsk_expand1_bf16(const float* x, long long x_batch_stride, const float* w, const float* bias, void* out, int B,
+                               int T, int C, void* stream);
+
 /* Pack one block's weights (fp32, reference state_dict layout) for svsk_diffnet_block_bf16.
  *   dilated_w [2C][C][3], cond_w [2C][H][1], out_w [2C][C][1]  ->  w1p [2C][3C+H] bf16, woutp [2C][C] bf16.
  * Row r of the reference maps to packed row perm(r): gate rows of channel block q at 256q..256q+127, filter rows at

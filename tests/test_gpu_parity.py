@@ -615,6 +615,47 @@ def test_usfgan_block_bf16(T, dil, adaptive, A, kernel):
     close_bf16(out.float().transpose(1, 2), ref, 4e-3, 1.5e-2)
 
 
+@pytest.mark.parametrize("scales,A,Fr,B", [([5, 4, 3, 2], 80, 37, 2), ([4, 3], 12, 9, 2), ([5, 4, 3, 2], 80, 3, 1),
+                                           ([2, 2], 24, 70, 3), ([8, 3, 5], 80, 600, 1)])
+def test_upsample_fused_matches_staged_path(scales, A, Fr, B):
+    """svsk_upsample_fused (all stages in one pass, NTC output) vs the stage-by-stage svsk_upsample_smooth_f32 + layout
+    conversion, and the staged path vs the oracle: same arithmetic up to fp32 summation order, exact zero padding."""
+    from ensemble_svs_with_interactions_b200.usfgan.layers.upsample import UpsampleNetwork
+    ops = _ops()
+    torch.manual_seed(sum(scales) + A)
+    net = UpsampleNetwork(scales).to(DEV)
+    with torch.no_grad():
+        for n in range(len(scales)):
+            wt = net.up_layers[2 * n + 1].weight
+            wt.copy_(torch.rand_like(wt) + 0.1)
+    c = torch.randn(B, A, Fr, device=DEV)
+    assert net.supports_fused(A)
+    staged = net(c)                                        # [B, A, T] fp32
+    yb, yf = net.forward_ntc(c, want_bf16=True, want_f32=True)
+    torch.cuda.synchronize()
+    T = Fr * int(np.prod(scales))
+    assert yf.shape == (B, T, (A + 7) // 8 * 8)
+    close32(yf[:, :, :A].transpose(1, 2), staged, 2e-6)
+    if yf.shape[2] > A:
+        assert float(yf[:, :, A:].abs().max()) == 0.0
+    ref_b, _ = ops.nct_to_ntc(staged, Cp=yf.shape[2])
+    diff = (yb.float() - ref_b.float()).abs()
+    assert float(diff.max()) <= 2 ** -7 * float(ref_b.float().abs().max())   # at most one bf16 rounding flip apart
+    assert float((diff > 0).float().mean()) < 1e-3
+
+
+def test_expand1_matches_conv1x1():
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(3, 2, 1000, generator=g).to(DEV)
+    w = torch.randn(64, 1, 1, generator=g).to(DEV); b = torch.randn(64, generator=g).to(DEV)
+    ref, _ = ops.nct_to_ntc(ops.conv1d_f32(x[:, 1:2].contiguous(), w, b))
+    y = ops.expand1_bf16(x[:, 1], w.reshape(-1).contiguous(), b, 64)
+    torch.cuda.synchronize()
+    diff = (y.float() - ref.float()).abs()
+    assert float(diff.max()) <= 2 ** -7 * float(ref.float().abs().max()) and float((diff > 0).float().mean()) < 1e-3
+
+
 def test_parallel_hn_fullwidth_bf16_vs_oracle():
     """Recipe-width generator (64/128/64, aux 80) with short stacks: bf16 tensor-core stacks vs the fp32 CPU oracle."""
     from ensemble_svs_with_interactions_b200.usfgan.models import ParallelHnUSFGANGenerator
