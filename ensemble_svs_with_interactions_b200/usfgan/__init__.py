@@ -34,3 +34,38 @@ class USFGANWrapper(nn.Module):
         if getattr(self.generator, "supports_wave_only", False):
             return self.generator(in_signal, c.contiguous(), df, wave_only=True)[0]
         return self.generator(in_signal, c.contiguous(), df)[0]
+
+    @torch.no_grad()
+    def inference_batch(self, f0, aux_feats):
+        """Batched form of ``inference`` (the reference wrapper has no batch dimension and the
+        multi-track synthesis loops over tracks, synthesis_multitrack.py:113-118).
+
+        f0: (B, T, 1) numpy array or tensor, aux_feats: (B, T, C) tensor on the generator's device; all tracks of a call
+        have the same number of frames (pad and trim outside, as the reference pads).  Returns (B, 1, T * hop).
+        Everything runs on the device: no numpy round trip for the dilation factors."""
+        data = self.config.data
+        assert data.sine_f0_type in ["contf0", "cf0", "f0"]
+        assert data.df_f0_type in ["contf0", "cf0", "f0"]
+        if "aux_context_window" not in self.config.generator:
+            raise NotImplementedError("SiFi-GAN generators are not part of this build (uSFGAN family only)")
+        device = aux_feats.device
+        if aux_feats.dim() != 3:
+            raise ValueError(f"aux_feats must be (B, T, C), got {tuple(aux_feats.shape)}")
+        f0 = torch.as_tensor(f0, dtype=torch.float32).to(device)
+        if f0.dim() != 3 or f0.shape[:2] != aux_feats.shape[:2] or f0.shape[2] != 1:
+            raise ValueError(f"f0 must be (B, T, 1) matching aux_feats, got {tuple(f0.shape)}")
+        window = self.config.generator.aux_context_window
+        f0 = f0.transpose(2, 1).contiguous()                                      # (B, 1, T)
+        # dilated_factor (features.py:56-75) on the device: unvoiced frames count as fs / dense_factor, i.e. factor 1
+        # (in float64 like the reference's numpy expression, then rounded to fp32 once: the tap offsets round(d * dilation)
+        # must come out identical)
+        f0_df = torch.where(f0 == 0, torch.full_like(f0, data.sample_rate / data.dense_factor), f0).double()
+        df = (float(data.sample_rate) / f0_df / data.dense_factor).float().repeat_interleave(data.hop_size, dim=2)
+        c = nn.functional.pad(aux_feats.transpose(2, 1), (window, window), mode="replicate")
+        signal_generator = SignalGenerator(sample_rate=data.sample_rate, hop_size=data.hop_size,
+                                           sine_amp=data.sine_amp, noise_amp=data.noise_amp,
+                                           signal_types=data.signal_types)
+        in_signal = signal_generator(f0)
+        if getattr(self.generator, "supports_wave_only", False):
+            return self.generator(in_signal, c.contiguous(), df.contiguous(), wave_only=True)[0]
+        return self.generator(in_signal, c.contiguous(), df.contiguous())[0]

@@ -824,3 +824,20 @@ def test_usfgan_wrapper_recipe_width_bf16():
     torch.manual_seed(9)
     w2 = USFGANWrapper(config, gen).inference(f0, aux)
     close_bf16(w1, w2, 5e-2, 1.5e-1)
+    # batched wrapper (row f2): B tracks in one call == the same tracks one call at a time (deterministic source signal)
+    gen.precision = "auto"
+    config.data.signal_types = ["sine", "uv"]
+    config.data.noise_amp = 0.0
+    wr = USFGANWrapper(config, gen)
+    f0s = np.stack([f0, f0 * 1.5, np.where(f0 > 0, 110.0, 0.0).astype(np.float32)])
+    auxs = torch.randn(3, frames, 65, device=DEV)
+    wb = wr.inference_batch(f0s, auxs)
+    assert wb.shape == (3, 1, frames * 120)
+    # identical shapes -> identical arithmetic: a batch of one IS the reference-signature call, bit for bit
+    assert torch.equal(wr.inference_batch(f0s[1:2], auxs[1:2]), wr.inference(f0s[1].copy(), auxs[1]))
+    for i in range(3):
+        wi = wr.inference(f0s[i].copy(), auxs[i])
+        # (not bit-equal: the source signal's fp32 cumsum over 4800 samples is a parallel scan whose blocking depends on
+        # the batch shape, and a last-bit phase difference flips bf16 roundings downstream)
+        r, mx = close_bf16(wb[i:i + 1], wi, 1e-2, 5e-2)
+        print(f"track {i}: batched vs single-track wrapper rel_l2={r:.2e} max={mx:.2e}")
