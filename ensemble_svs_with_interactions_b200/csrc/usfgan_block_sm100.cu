@@ -245,6 +245,12 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
       const int b = tile / a.tiles_per_row, t0 = (tile - b * a.tiles_per_row) * 128;
       const bool gather = tile_needs_gather(t0, T, a.dilation, a.adaptive);
       const int t = t0 + r;
+      // this row's two tap indices, requested before the slot waits so that their (L2) latency is off the slot's chain
+      int ip = -1, ifu = -1;
+      if (a.adaptive && t < T) {
+        ip = __ldg(a.idx_past + (size_t)b * T + t);
+        ifu = __ldg(a.idx_future + (size_t)b * T + t);
+      }
       for (int kb = 0; kb < KB; ++kb) {
         // Wait on EVERY slot, also the ones the TMA producer fills: parity waits only tell two consecutive phases apart,
         // so this warp group must never run more than one ring wrap ahead of the MMA issuer.
@@ -253,7 +259,7 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
           int src = -1;
           if (t < T) {
             if (a.adaptive) {
-              src = (kb == 0 ? a.idx_past : a.idx_future)[(size_t)b * T + t];
+              src = kb == 0 ? ip : ifu;
             } else {
               src = t + (kb - 1) * a.dilation;
               if (src < 0) src = -src;
