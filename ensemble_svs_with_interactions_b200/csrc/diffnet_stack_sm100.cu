@@ -699,8 +699,12 @@ static void stack_launch_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at
   attr[0].val.clusterDim.x = csize;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  // cooperative: the driver starts the grid only when ALL its CTAs can be resident at once — the guarantee the
+  // neighbour hand-shakes need even when other work shares the device
+  attr[1].id = cudaLaunchAttributeCooperative;
+  attr[1].val.cooperative = 1;
   cfg->attrs = attr;
-  cfg->numAttrs = 1;
+  cfg->numAttrs = getenv("SVSK_STACK_NO_COOPERATIVE") ? 1 : 2;
 }
 
 extern "C" int svsk_diffnet_stack_fits(int B, int T, int C, int H) {
@@ -710,7 +714,7 @@ extern "C" int svsk_diffnet_stack_fits(int B, int T, int C, int H) {
   if (B <= 0 || T <= 0 || B > 65535) return 0;
   if (stack_prepare(C, H, &nentries, &smem_bytes)) return 0;
   cudaLaunchConfig_t cfg;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   stack_launch_config(&cfg, attr, B, T, smem_bytes, nullptr);
   int max_clusters = 0;
   if (cudaOccupancyMaxActiveClusters(&max_clusters, diffnet_stack_kernel, &cfg) != cudaSuccess) {
@@ -743,7 +747,7 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
   if ((rc = stack_prepare(p.C, p.H, &nentries, &smem_bytes))) return rc;
 
   cudaLaunchConfig_t cfg;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   stack_launch_config(&cfg, attr, p.B, p.T, smem_bytes, stream);
   int max_clusters = 0;
   cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, diffnet_stack_kernel, &cfg);

@@ -212,8 +212,11 @@ SVSK_API int svsk_diffnet_block3_bf16(const svsk_diffnet_block_params* p, void* 
  *   flags: B * 2*ceil(T/256) ints of scratch (reset by this call), skip32 [B][T][C] fp32 = sum of the L skip outputs
  *   (stored if init_skip, else accumulated).  The residual stream after the last layer is not produced (it is dead,
  *   denoiser.py:117-120).
- * All CTA pairs must be resident at once: svsk_diffnet_stack_fits(B,T,C,H) returns 1 if they are, 0 if not (then run
- * the layers one by one with svsk_diffnet_block3_bf16), -1 without an sm_100 device. */
+ * All CTA pairs must be resident at once (the launch is cooperative, so the driver guarantees it or waits):
+ * svsk_diffnet_stack_fits(B,T,C,H) returns 1 if the device can hold them, 0 if not (then split the batch into groups of
+ * tracks that fit, or run the layers one by one with svsk_diffnet_block3_bf16), -1 without an sm_100 device.
+ * Tracks of at most 2048 frames run as one thread-block cluster each (edge rows through distributed shared memory,
+ * weight tiles TMA-multicast); longer tracks exchange edge rows through edge0 / edge1 and the flags. */
 typedef struct svsk_diffnet_stack_params {
   const void* xb_in;
   void* edge0;

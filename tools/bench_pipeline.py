@@ -58,6 +58,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--songs", type=int, default=64)
     ap.add_argument("--warmup-songs", type=int, default=1)
+    ap.add_argument("--breakdown", action="store_true", help="also print ms per phase of the last song")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
@@ -68,14 +69,26 @@ def main():
     mine = sharding.assign([FRAMES] * args.songs, world)[rank]
     host = song_inputs(0, dev)   # same shapes for every song; contents re-seeded per song below (cheap host RNG is not timed)
 
+    phases = {}   # --breakdown: ms per phase of the last song (events around the three models)
+
     def synth(song):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if args.breakdown else None
+        if ev: ev[0].record()
         cond_mgc, cond_bap, d, sig = (t.to(dev, non_blocking=True) for t in host)
+        if ev: ev[1].record()
         m = mgc.inference(cond_mgc)                       # (6, 6000, 60)
+        if ev: ev[2].record()
         b = bap.inference(cond_bap)                       # (6, 6000, 5)
+        if ev: ev[3].record()
         aux = torch.cat([m, b], dim=-1).transpose(1, 2)   # (6, 65, 6000) == vocoder frames at 5 ms
         aux = torch.nn.functional.pad(aux, (2, 2), mode="replicate").contiguous()
         wav = voc(sig, aux, d, wave_only=True)[0]
-        return wav.cpu()                                  # D2H of the 6 waveforms
+        if ev: ev[4].record()
+        out = wav.cpu()                                   # D2H of the 6 waveforms
+        if ev:
+            names = ["h2d", "mgc diffusion", "bap diffusion", "vocoder"]
+            phases.update({n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(names)})
+        return out
 
     for s in range(args.warmup_songs):
         synth(s)
@@ -98,7 +111,8 @@ def main():
                           "value": audio / sec, "unit": "audio-sec/s", "n_gpus": world, "songs": args.songs,
                           "seconds": sec, "wall_seconds_rank0": wall, "scaling": "strong",
                           "ms_per_song_rank0": 1e3 * sec / max(1, len(mine)), "gpu_launches_rank0": _lib.launch_count - n0,
-                          "config": {"workload": f"{args.songs} songs x {TRACKS} tracks x {SECONDS:.0f} s, K=100, 24 kHz"}}))
+                          "config": {"workload": f"{args.songs} songs x {TRACKS} tracks x {SECONDS:.0f} s, K=100, 24 kHz"},
+                          **({"phases_ms_last_song": phases} if args.breakdown else {})}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -11,7 +11,13 @@ from ensemble_svs_with_interactions_b200 import ops  # noqa: E402
 B, T = bench.B, bench.T
 if len(sys.argv) > 2:
     B, T = int(sys.argv[1]), int(sys.argv[2])
-m = bench.build_model().to("cuda")
+if os.environ.get("SVSK_STACK_BENCH_MODEL"):   # "M,H,L,C", e.g. 5,128,10,128 = the pipeline's bap model
+    from ensemble_svs_with_interactions_b200.diffsinger import DiffNet, GaussianDiffusion
+    M_, H_, L_, C_ = (int(v) for v in os.environ["SVSK_STACK_BENCH_MODEL"].split(","))
+    torch.manual_seed(0)
+    m = GaussianDiffusion(H_, M_, DiffNet(M_, H_, L_, C_, 4), K_step=100).to("cuda").eval()
+else:
+    m = bench.build_model().to("cuda")
 plan = m.denoise_fn.bf16_plan()
 cond = torch.randn(B, T, plan.H, device="cuda").to(torch.bfloat16)
 table = m._step_table()
@@ -42,7 +48,7 @@ for _ in range(20):
     launch()
 b.record(); b.synchronize()
 us = a.elapsed_time(b) * 1e3 / 20
-flops = 2.0 * B * T * bench.BLOCK_MAC_PER_FRAME * plan.L
+flops = 2.0 * B * T * (2 * plan.C * (3 * plan.C + plan.H) + 2 * plan.C * plan.C) * plan.L
 print(f"B={B} T={T}: stack of {plan.L} blocks {us:8.1f} us/launch = {us / plan.L:6.2f} us/layer, {flops / us / 1e6:7.1f} TFLOP/s", flush=True)
 
 dbg = torch.zeros(512 * 32, dtype=torch.int64, device="cuda")
