@@ -76,20 +76,35 @@ diffnet_step_kernel(const __grid_constant__ CUtensorMap tm_wskip, const __grid_c
     ptx::tmem_relinquish();
   }
 
-  // ---- A = bf16(skip32 * scale): 16 bytes (8 channels) per thread and step, rows past the end of the track = 0
+  // ---- A = bf16(skip32 * scale): 16 bytes (8 channels) per thread and step, rows past the end of the track = 0.
+  //      Four steps' loads are in flight together (the loop is bound by the latency of its 128 KB of fp32 reads).
   {
     const int chunks = C / 8;  // 16-byte bf16 chunks per row
-    for (int i = threadIdx.x; i < 128 * chunks; i += kStepThreads) {
-      const int r = i / chunks, ch = i - r * chunks;
-      uint4 o = make_uint4(0, 0, 0, 0);
-      if (t0 + r < T) {
-        const float4* src = reinterpret_cast<const float4*>(a.skip32 + ((size_t)b * T + t0 + r) * C + ch * 8);
-        const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
-        const float s = a.skip_scale;
-        o = make_uint4(ptx::pack_bf16(v0.x * s, v0.y * s), ptx::pack_bf16(v0.z * s, v0.w * s),
-                       ptx::pack_bf16(v1.x * s, v1.y * s), ptx::pack_bf16(v1.z * s, v1.w * s));
+    const int total = 128 * chunks;
+    const float s = a.skip_scale;
+    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * kStepThreads) {
+      float4 v[4][2];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kStepThreads;
+        const int r = i / chunks, ch = i - r * chunks;
+        v[u][0] = v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < total && t0 + r < T) {
+          const float4* src = reinterpret_cast<const float4*>(a.skip32 + ((size_t)b * T + t0 + r) * C + ch * 8);
+          v[u][0] = __ldg(src);
+          v[u][1] = __ldg(src + 1);
+        }
       }
-      ptx::st_shared_v4(ah + (ch >> 3) * kStepTile + ptx::sw128_offset((uint32_t)r, (uint32_t)(ch & 7)), o.x, o.y, o.z, o.w);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kStepThreads;
+        if (i < total) {
+          const int r = i / chunks, ch = i - r * chunks;
+          ptx::st_shared_v4(ah + (ch >> 3) * kStepTile + ptx::sw128_offset((uint32_t)r, (uint32_t)(ch & 7)),
+                            ptx::pack_bf16(v[u][0].x * s, v[u][0].y * s), ptx::pack_bf16(v[u][0].z * s, v[u][0].w * s),
+                            ptx::pack_bf16(v[u][1].x * s, v[u][1].y * s), ptx::pack_bf16(v[u][1].z * s, v[u][1].w * s));
+        }
+      }
     }
   }
   ptx::fence_proxy_async_smem();
@@ -157,6 +172,22 @@ diffnet_step_kernel(const __grid_constant__ CUtensorMap tm_wskip, const __grid_c
         ptx::umma_bf16_lo(tm_b, h_lo + kb * (kStepTile >> 4) + 2 * k4, w_lo + kb * (kStepTile >> 4) + 2 * k4, idesc, (kb | k4) != 0);
     ptx::umma_commit(&bars->mma_done[1]);
   }
+  // x and z of this thread's first three 16-channel chunks are requested while GEMM-b runs (z streams from HBM)
+  float4 xr[3][4], zr[3][4];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int c0 = 16 * half + 32 * k;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) xr[k][e] = zr[k][e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in_seq && c0 < Mp) {
+      const size_t base = ((size_t)b * T + tt) * Mp + c0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        xr[k][e] = *reinterpret_cast<const float4*>(a.x32s + base + 4 * e);
+        zr[k][e] = __ldg(reinterpret_cast<const float4*>(a.z + base + 4 * e));
+      }
+    }
+  }
   ptx::mbar_wait(&bars->mma_done[1], 0);
   ptx::tc_fence_after();
 
@@ -165,40 +196,48 @@ diffnet_step_kernel(const __grid_constant__ CUtensorMap tm_wskip, const __grid_c
     const long long tb = a.t[b];
     const float ca = a.sra[tb], cb = a.srm1[tb], c1 = a.c1[tb], c2 = a.c2[tb];
     const float sigma = tb == 0 ? 0.f : expf(0.5f * a.plv[tb]);
-    for (int c0 = 16 * half; c0 < Mp; c0 += 32) {
-      uint32_t r[16];
-      ptx::tmem_ld16(tm_b + tlane + c0, r);
-      ptx::tmem_ld_wait();
-      uint32_t o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      if (in_seq) {
-        const size_t base = ((size_t)b * T + tt) * Mp + c0;
-        float xn[16];
 #pragma unroll
-        for (int e = 0; e < 16; e += 4) {
-          const float4 xv = *reinterpret_cast<const float4*>(a.x32s + base + e);
-          const float4 zv = __ldg(reinterpret_cast<const float4*>(a.z + base + e));
-          const float4 bo = __ldg(reinterpret_cast<const float4*>(a.b_out + c0 + e));
-          const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, zs[4] = {zv.x, zv.y, zv.z, zv.w}, bs[4] = {bo.x, bo.y, bo.z, bo.w};
-          float ep[4];
+    for (int k = 0; k < 4; ++k) {
+      const int c0 = 16 * half + 32 * k;
+      if (c0 < Mp) {
+        uint32_t r[16];
+        ptx::tmem_ld16(tm_b + tlane + c0, r);
+        ptx::tmem_ld_wait();
+        uint32_t o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (in_seq) {
+          const size_t base = ((size_t)b * T + tt) * Mp + c0;
+          float xn[16];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            ep[u] = __uint_as_float(r[e + u]) + bs[u];
-            float x0 = ca * xs[u] - cb * ep[u];
-            if (a.clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
-            const float mean = c1 * x0 + c2 * xs[u];
-            xn[e + u] = mean + sigma * zs[u];
+          for (int e = 0; e < 16; e += 4) {
+            float4 xv, zv;
+            if (k < 3) { xv = xr[k < 3 ? k : 0][e >> 2]; zv = zr[k < 3 ? k : 0][e >> 2]; }
+            else {
+              xv = *reinterpret_cast<const float4*>(a.x32s + base + e);
+              zv = __ldg(reinterpret_cast<const float4*>(a.z + base + e));
+            }
+            const float4 bo = __ldg(reinterpret_cast<const float4*>(a.b_out + c0 + e));
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, zs[4] = {zv.x, zv.y, zv.z, zv.w}, bs[4] = {bo.x, bo.y, bo.z, bo.w};
+            float ep[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              ep[u] = __uint_as_float(r[e + u]) + bs[u];
+              float x0 = ca * xs[u] - cb * ep[u];
+              if (a.clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+              const float mean = c1 * x0 + c2 * xs[u];
+              xn[e + u] = mean + sigma * zs[u];
+            }
+            *reinterpret_cast<float4*>(a.x32s + base + e) = make_float4(xn[e], xn[e + 1], xn[e + 2], xn[e + 3]);
+            if (a.eps_out) *reinterpret_cast<float4*>(a.eps_out + base + e) = make_float4(ep[0], ep[1], ep[2], ep[3]);
           }
-          *reinterpret_cast<float4*>(a.x32s + base + e) = make_float4(xn[e], xn[e + 1], xn[e + 2], xn[e + 3]);
-          if (a.eps_out) *reinterpret_cast<float4*>(a.eps_out + base + e) = make_float4(ep[0], ep[1], ep[2], ep[3]);
-        }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = ptx::pack_bf16(xn[2 * e], xn[2 * e + 1]);
-      }
-      if (a.head) {
-        uint8_t* tile = ah + (c0 >> 6) * kStepTile;
-        const uint32_t ch = (uint32_t)((c0 & 63) >> 3);
-        ptx::st_shared_v4(tile + ptx::sw128_offset((uint32_t)row, ch), o[0], o[1], o[2], o[3]);
-        ptx::st_shared_v4(tile + ptx::sw128_offset((uint32_t)row, ch + 1), o[4], o[5], o[6], o[7]);
+          for (int e = 0; e < 8; ++e) o[e] = ptx::pack_bf16(xn[2 * e], xn[2 * e + 1]);
+        }
+        if (a.head) {
+          uint8_t* tile = ah + (c0 >> 6) * kStepTile;
+          const uint32_t ch = (uint32_t)((c0 & 63) >> 3);
+          ptx::st_shared_v4(tile + ptx::sw128_offset((uint32_t)row, ch), o[0], o[1], o[2], o[3]);
+          ptx::st_shared_v4(tile + ptx::sw128_offset((uint32_t)row, ch + 1), o[4], o[5], o[6], o[7]);
+        }
       }
     }
   }
