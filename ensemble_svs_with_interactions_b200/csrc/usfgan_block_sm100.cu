@@ -191,27 +191,25 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             ptx::tc_fence_after();
             const long long c_2 = (kProf ? clock64() : 0ll);
             acc_fence += c_2 - c_1;
-            // probe the next k-block of this tile (the next tile's first k-block is waited for normally)
+            // probe the next k-block of this tile (the next tile's first k-block is waited for normally).  The probe is
+            // issued before this k-block's MMAs and its result consumed after them (ptx::umma_bf16_x4_probe): a test whose
+            // result is needed at once stalls this thread ~130 cycles per k-block (tools/ubench_umma.py).
             const int s_next = (s + 1 == a.nstages) ? 0 : s + 1;
-            ready = false;
-            if (kb + 1 < KB) {
-              const bool ng = gather && (kb + 1 == 0 || kb + 1 == 2);
-              ready = ptx::mbar_test(ng ? &bars->full_g[s_next] : &bars->full_t[s_next],
-                                     ng ? ((phg >> s_next) & 1) : ((pht >> s_next) & 1));
-            }
+            const bool ng = gather && (kb + 1 == 0 || kb + 1 == 2);
+            uint64_t* nbar = ng ? &bars->full_g[s_next] : &bars->full_t[s_next];
+            const uint32_t npar = ng ? ((phg >> s_next) & 1) : ((pht >> s_next) & 1);
             const long long c_2b = (kProf ? clock64() : 0ll);
             acc_probe += c_2b - c_2;
             const uint32_t a_lo = ring_lo + s * (kUTile >> 4), b_lo = w1_lo + kb * (kUTile >> 4);
             const int ks = (kb == KB - 1) ? a.last_ksteps : 4;
-            if (!((kFlags ? a.dbg_flags : 0) & 4)) {
+            ready = false;
+            if ((kFlags ? a.dbg_flags : 0) & 256) {  // A/B: the earlier synchronous probe
+              if (kb + 1 < KB) ready = ptx::mbar_test(nbar, npar);
               ptx::umma_bf16_lo(tmem + p * 128, a_lo, b_lo, idesc1, kb != 0);
-              if (ks == 4) {
-                ptx::umma_bf16_lo(tmem + p * 128, a_lo + 2, b_lo + 2, idesc1, 1);
-                ptx::umma_bf16_lo(tmem + p * 128, a_lo + 4, b_lo + 4, idesc1, 1);
-                ptx::umma_bf16_lo(tmem + p * 128, a_lo + 6, b_lo + 6, idesc1, 1);
-              } else {
-                for (int k4 = 1; k4 < ks; ++k4) ptx::umma_bf16_lo(tmem + p * 128, a_lo + 2 * k4, b_lo + 2 * k4, idesc1, 1);
-              }
+              for (int k4 = 1; k4 < ks; ++k4) ptx::umma_bf16_lo(tmem + p * 128, a_lo + 2 * k4, b_lo + 2 * k4, idesc1, 1);
+            } else if (!((kFlags ? a.dbg_flags : 0) & 4)) {
+              const bool r = ptx::umma_bf16_x4_probe(tmem + p * 128, a_lo, b_lo, idesc1, kb != 0, ks, nbar, npar);
+              ready = r && (kb + 1 < KB);
             }
             const long long c_3 = (kProf ? clock64() : 0ll);
             acc_mma += c_3 - c_2b;
