@@ -28,8 +28,8 @@
 //   2: conditioner, blocks 0..NB-1 (A = conditioner tiles in the G buffer, which the previous skip epilogue released)
 //   3: all taps, blocks 1..NB-1
 //   4: output projection, blocks 0..NB-1 (A = G)
-// Warps: 0 = weight producer (both CTAs), 1 = MMA issuer (leader) / forwarder (peer) + TMEM owner, 2..9 = epilogue,
-// 10 = activation producer (conditioner tiles, window / halo rows, edge-row publication).
+// Warps: 0 = weight producer (both CTAs), 1 = MMA issuer (leader) / forwarder (peer) + TMEM owner, 2..9 = epilogue
+// (kSW = 2 per TMEM lane quarter), 10 = activation producer (conditioner tiles, window / halo rows, edge-row publication).
 // All CTAs must be co-resident (neighbours wait for each other): the host entry checks the grid against
 // cudaOccupancyMaxActiveClusters and refuses otherwise (callers fall back to one svsk_diffnet_block3_bf16 per layer).
 #include <cuda_bf16.h>
@@ -49,7 +49,13 @@ constexpr int kSHaloBytes = kSHalo * 128;    // 1 KB per window tile and side
 constexpr int kSMaxEntries = 8;
 constexpr int kSSmemLimit = 232448;
 constexpr int kSTmemCols = 512;
-constexpr int kSThreads = 352;
+// Epilogue warps per TMEM lane quarter (they alternate 16-column chunks).  2 and 4 measure the same (403 vs 395 us per
+// 20-layer launch): the epilogues are bound by the TMEM read port (64 B/cycle/SM: 128 KB per gating block, per residual
+// half and per skip half = 2 k cycles each), not by warp-level latency hiding; 4 costs 96-register threads.
+constexpr int kSW = 2;
+constexpr int kSEpi = 128 * kSW;             // epilogue threads per CTA
+constexpr int kSActWarp = 2 + 4 * kSW;       // the activation producer's warp
+constexpr int kSThreads = 32 * (kSActWarp + 1);
 constexpr int kSMaxLayers = 64;
 
 struct DiffnetStackArgs {
@@ -165,19 +171,19 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
     ptx::prefetch_tmap(&tm_wout);
     ptx::prefetch_tmap(&tm_skip);
     const uint32_t two = rank == 0 ? 2u : 1u;        // leader barriers also count the peer's forwarded arrival
-    const uint32_t all = rank == 0 ? 2u * 256u : 1u; // leader barriers every epilogue thread of the pair arrives on
+    const uint32_t all = rank == 0 ? 2u * kSEpi : 1u; // leader barriers every epilogue thread of the pair arrives on
     for (int i = 0; i < a.nentries; ++i) {
       ptx::mbar_init(&bars->full[i], two);
       ptx::mbar_init(&bars->empty[i], (uint32_t)n_pairs);  // one multicast tcgen05.commit per CTA pair sharing the weights
     }
     for (int i = 0; i < HB; ++i) ptx::mbar_init(&bars->cd_full[i], two);
     ptx::mbar_init(&bars->xw_full, two);
-    // halo rows: 16 arrivals per neighbour (8 rows x the 2 epilogue warps of a lane quarter) + the peer's forward
-    ptx::mbar_init(&bars->xh_full, max(1u, 16u * ((nb_left ? 1u : 0u) + (nb_right ? 1u : 0u)) + (rank == 0 ? 1u : 0u)));
+    // halo rows: 8 * kSW arrivals per neighbour (8 rows x the kSW epilogue warps of a lane quarter) + the peer's forward
+    ptx::mbar_init(&bars->xh_full, max(1u, 8u * kSW * ((nb_left ? 1u : 0u) + (nb_right ? 1u : 0u)) + (rank == 0 ? 1u : 0u)));
     // credits: this pair's GEMM1 + the GEMM1 of the pair on the other side of this CTA's outer edge
     ptx::mbar_init(&bars->halo_free, 1u + ((rank == 0 ? nb_left : nb_right) ? 1u : 0u));
     ptx::mbar_init(&bars->xc_ready, all);
-    ptx::mbar_init(&bars->xe_ready, 256);
+    ptx::mbar_init(&bars->xe_ready, kSEpi);
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars->d1_full[i], 1);
       ptx::mbar_init(&bars->d2_full[i], 1);
@@ -185,7 +191,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
     }
     ptx::mbar_init(&bars->g_ready[0], all);
     ptx::mbar_init(&bars->g_ready[1], all);
-    ptx::mbar_init(&bars->gc_free, 8);  // one arrival per epilogue warp
+    ptx::mbar_init(&bars->gc_free, 4 * kSW);  // one arrival per epilogue warp
     ptx::fence_mbar_init();
     pre_issued = mc ? 0 : min(a.nentries, n_total);  // (multicast writes into CTAs that may not have set up their barriers yet)
     for (int e = 0; e < pre_issued; ++e) {
@@ -225,7 +231,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         if (++i == n_layer) { i = 0; ++l; }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == kSActWarp) {
     // ------------------------------------------------------------------ activation producer (both CTAs)
     if (lane == 0) {
       const int tile_idx = b * a.tiles_per_track + (t_cta0 >> 7);
@@ -436,10 +442,10 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         forward_entries((NB - 1) * 3 * CB + NB * KB2);
       }
     }
-  } else if (warp >= 2 && warp < 10) {
+  } else if (warp >= 2 && warp < kSActWarp) {
     // ------------------------------------------------------------------ epilogue warps (thread = one frame)
     const int q = warp & 3;           // TMEM lane quarter this warp may read
-    const int sub = (warp - 2) >> 2;  // the two warps of a quarter alternate 16-column chunks
+    const int sub = (warp - 2) >> 2;  // the kSW warps of a quarter alternate 16-column chunks
     const int row = q * 32 + lane;
     const int t = t_cta0 + row;
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
@@ -465,14 +471,14 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
       {
         const float* sb = a.stepbias + (size_t)b * a.sb_batch_stride + (size_t)l * a.sb_layer_stride;
         const float* bo = a.bout + (size_t)l * twoC;
-        for (int i = threadIdx.x - 64; i < twoC; i += 256) {
+        for (int i = threadIdx.x - 64; i < twoC; i += kSEpi) {
           const float lft = sb[i], c = sb[twoC + i], r = sb[2 * twoC + i];
           sb_full[i] = c + lft + r;
           sb_l[i] = lft;
           sb_r[i] = r;
           bo_s[i] = bo[i];
         }
-        ptx::named_bar_sync(1, 256);
+        ptx::named_bar_sync(1, kSEpi);
       }
 
       // ---- epilogue 1: gating -> G
@@ -483,12 +489,12 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         ptx::tmem_ld16(tmem + tlane + j * 256 + 16 * sub, rgb[0]);
         ptx::tmem_ld16(tmem + tlane + j * 256 + 128 + 16 * sub, rfb[0]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c0 = 16 * (2 * i + sub);
+        for (int i = 0; i < 8 / kSW; ++i) {
+          const int c0 = 16 * (kSW * i + sub);
           ptx::tmem_ld_wait();
-          if (i + 1 < 4) {  // next chunk's TMEM loads fly while this chunk is gated
-            ptx::tmem_ld16(tmem + tlane + j * 256 + c0 + 32, rgb[(i + 1) & 1]);
-            ptx::tmem_ld16(tmem + tlane + j * 256 + 128 + c0 + 32, rfb[(i + 1) & 1]);
+          if (i + 1 < 8 / kSW) {  // next chunk's TMEM loads fly while this chunk is gated
+            ptx::tmem_ld16(tmem + tlane + j * 256 + c0 + 16 * kSW, rgb[(i + 1) & 1]);
+            ptx::tmem_ld16(tmem + tlane + j * 256 + 128 + c0 + 16 * kSW, rfb[(i + 1) & 1]);
           }
           const uint32_t* rg = rgb[i & 1];
           const uint32_t* rf = rfb[i & 1];
@@ -536,16 +542,16 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         if (res_cols > 0 && !last) {
           if (l == 0) ptx::mbar_wait(&bars->xw_full, 0);  // (long complete) makes the TMA-written window visible here
           if (send_left || send_right) ptx::mbar_wait(&bars->halo_free, pl);  // the neighbour's GEMM1 of this layer is done
-          const int n_res = res_cols / 32;
+          const int n_res = res_cols / (16 * kSW);
           uint32_t rr[2][16];
           ptx::tmem_ld16(tmem + tlane + j * 256 + 16 * sub, rr[0]);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 16 / kSW; ++i) {
             if (i < n_res) {
-              const int c0 = 16 * (2 * i + sub);
+              const int c0 = 16 * (kSW * i + sub);
               const int oc0 = j * 256 + c0;  // output channel = residual channel
               ptx::tmem_ld_wait();
-              if (i + 1 < n_res) ptx::tmem_ld16(tmem + tlane + j * 256 + c0 + 32, rr[(i + 1) & 1]);  // flies during the maths
+              if (i + 1 < n_res) ptx::tmem_ld16(tmem + tlane + j * 256 + c0 + 16 * kSW, rr[(i + 1) & 1]);  // flies during the maths
               const uint32_t* r = rr[i & 1];
               uint8_t* xt = xw_smem + (oc0 >> 6) * kSWinBytes + kSHalo * 128;  // centre rows of the window tile
               const uint32_t ch16 = (uint32_t)((oc0 & 63) >> 3);
@@ -591,18 +597,22 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         if (res_cols < 256) {
           if (j != NB - 1) __trap();  // skip columns only live in the last block: GEMM2 is done, the G buffer is free
           const int n_skip = (256 - res_cols) / 32;
-          int m = 0;  // this warp's staging slot: tile sub*2 + m of the G buffer, rows 32q .. 32q+31
+          constexpr int kSlots = 4 / kSW;  // staging slots per warp: tiles sub*kSlots + m of the G buffer, rows 32q .. 32q+31
+          int m = 0;
 #pragma unroll 1
-          for (int k = sub; k < n_skip; k += 2, m ^= 1) {
+          for (int k = sub; k < n_skip; k += kSW, m = (m + 1) % kSlots) {
             const int c0 = res_cols + 32 * k;
             uint32_t r0[16], r1[16];
             ptx::tmem_ld16(tmem + tlane + j * 256 + c0, r0);
             ptx::tmem_ld16(tmem + tlane + j * 256 + c0 + 16, r1);
-            if (k >= sub + 4) {  // the slot is used for the second time: its previous TMA must have read it
-              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (k >= sub + kSW * kSlots) {  // the slot is used again: its previous TMA must have read it
+              if (lane == 0) {
+                if (kSlots == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              }
               __syncwarp();
             }
-            uint8_t* slab = g_smem + (sub * 2 + m) * kSTile;
+            uint8_t* slab = g_smem + (sub * kSlots + m) * kSTile;
             ptx::tmem_ld_wait();
             const int oc0 = j * 256 + c0;
 #pragma unroll
@@ -634,7 +644,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         ptx::mbar_arrive_cluster(dr_leader + (uint32_t)j * 8u);
       }
       // the bias arrays are rewritten at the top of the next layer: every epilogue thread must be done reading them
-      ptx::named_bar_sync(1, 256);
+      ptx::named_bar_sync(1, kSEpi);
     }
   }
 
