@@ -219,12 +219,15 @@ class GaussianDiffusion(BaseModel):
         return x
 
     def _prepare_t_const(self, B, device):
-        key = (B, str(device))
-        if getattr(self, "_t_const_key", None) != key:
-            # one [B] int64 tensor per step (views of a [K,B] table): no per-step host->device traffic
+        # One [B] int64 tensor per step (views of a [K,B] table): no per-step host->device traffic.  The tables are kept
+        # per (K, B, device) for the module's lifetime: captured CUDA graphs hold their device addresses, so a table
+        # must not be freed when a call with another batch size comes in between two replays.
+        key = (self.K_step, B, str(device))
+        cache = self.__dict__.setdefault("_t_const_cache", {})
+        if key not in cache:
             tt = torch.arange(self.K_step, device=device, dtype=torch.int64)[:, None].expand(self.K_step, B).contiguous()
-            self._t_const = [tt[i] for i in range(self.K_step)]
-            self._t_const_key = key
+            cache[key] = [tt[i] for i in range(self.K_step)]
+        self._t_const = cache[key]
 
     @torch.no_grad()
     def sample(self, cond_t, x_T=None, z=None):
@@ -265,7 +268,7 @@ class GaussianDiffusion(BaseModel):
 
     def _graph_replay(self, condb, x32s, z_ntc):
         """Capture the whole K-step loop once per (B,T) and replay it (static buffers, ~26 K launches -> 1)."""
-        key = (tuple(condb.shape), tuple(x32s.shape), self.denoise_fn._param_key())
+        key = (tuple(condb.shape), tuple(x32s.shape), self.K_step, self.denoise_fn._param_key())
         ent = self._graphs.get(key)
         if ent is None:
             if len(self._graphs) >= 4:

@@ -1,0 +1,95 @@
+"""Batched (song, track) synthesis: mgc + bap diffusion followed by the uSFGAN vocoder, many tracks per launch.
+
+Replaces the reference's driver loop for this path (first part): ``nnsvs/bin/synthesis_multitrack.py
+:113-118`` walks all utterance pairs and runs every model with batch size 1 (``multistream.py:1684-1696`` calls the mgc
+and bap ``GaussianDiffusion.inference`` once per track, ``gen.py:1694`` the vocoder once per track).  Every (song, track)
+item is independent once its conditioning exists, so here they are
+
+* partitioned over the ranks with ``sharding.assign`` (no collective),
+* grouped into padded batches under a frame budget with ``sharding.batches``,
+* run through ``GaussianDiffusion.inference`` (all tracks of a batch per denoiser launch) and
+  ``USFGANWrapper.inference_batch`` (all tracks per vocoder launch),
+* trimmed back to their own lengths and returned in input order.
+
+What stays outside (the reference's CPU code between the models, SURVEY §8(f) row 3 second part): GV post-filtering and
+the scipy low-pass of ``postprocess_acoustic`` (gen.py:1394-1518), the pyworld bap round trip (gen.py:1639-1670) and the
+feature scalers — they enter through ``aux_fn``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence
+
+import torch
+
+from . import sharding
+
+
+@dataclass
+class BatchPlan:
+    """One padded batch: ``items`` (indices into the caller's list), all padded to ``frames`` frames."""
+    items: List[int]
+    frames: int
+
+
+def plan_batches(lengths: Sequence[int], max_frames: int, world_size: int = 1, rank: int = 0, multiple: int = 1) -> List[BatchPlan]:
+    """This rank's batches.  Items go to ranks longest-first (``sharding.assign``); within the rank they are grouped so
+    that ``len(batch) * padded_frames <= max_frames`` (a single item longer than the budget still gets its own batch).
+    ``multiple``: pad the batch length up to a multiple of it (the reference pads to the models' reduction factor,
+    util.py:77,163-164)."""
+    if max_frames < 1 or multiple < 1:
+        raise ValueError("max_frames and multiple must be positive")
+    mine = sharding.assign(lengths, world_size)[rank]
+    padded = [-(-int(n) // multiple) * multiple for n in lengths]
+    return [BatchPlan(items=list(b), frames=max(padded[i] for i in b)) for b in sharding.batches(mine, padded, max_frames)]
+
+
+def _pad_time(x: torch.Tensor, frames: int, mode: str) -> torch.Tensor:
+    """x [T, C] -> [frames, C]; ``replicate`` repeats the last frame (the reference's pad_inference), ``zeros`` appends 0."""
+    T = x.shape[0]
+    if T == frames:
+        return x
+    if T > frames:
+        raise ValueError(f"item of {T} frames in a batch of {frames}")
+    tail = x[-1:].expand(frames - T, -1) if mode == "replicate" else x.new_zeros((frames - T, x.shape[1]))
+    return torch.cat([x, tail], dim=0)
+
+
+class EnsembleSynthesizer:
+    """mgc / bap diffusion + vocoder over batches of tracks.
+
+    mgc, bap: ``GaussianDiffusion`` drop-ins (already on the device, eval mode); vocoder: ``USFGANWrapper``.
+    aux_fn(mgc [B,T,M1], bap [B,T,M2], f0 [B,T,1]) -> vocoder aux features [B,T,C]; default: concatenate mgc and bap.
+    max_frames: frame budget of one batch (tracks x padded frames)."""
+
+    def __init__(self, mgc, bap, vocoder, max_frames: int = 36000,
+                 aux_fn: Optional[Callable[[torch.Tensor, torch.Tensor, torch.Tensor], torch.Tensor]] = None):
+        self.mgc, self.bap, self.vocoder = mgc, bap, vocoder
+        self.max_frames = int(max_frames)
+        self.aux_fn = aux_fn if aux_fn is not None else (lambda m, b, f0: torch.cat([m, b], dim=-1))
+
+    @torch.no_grad()
+    def synthesize(self, cond_mgc: Sequence[torch.Tensor], cond_bap: Sequence[torch.Tensor], f0: Sequence[torch.Tensor],
+                   world_size: int = 1, rank: int = 0) -> List[Optional[torch.Tensor]]:
+        """Per item i: cond_mgc[i] [T_i, H1], cond_bap[i] [T_i, H2], f0[i] [T_i, 1] (Hz, 0 = unvoiced), any device.
+        Returns the waveforms [T_i * hop] of this rank's items in input order (None for items of other ranks)."""
+        n = len(cond_mgc)
+        if not (len(cond_bap) == n and len(f0) == n):
+            raise ValueError("cond_mgc, cond_bap and f0 must have one entry per item")
+        lengths = [int(c.shape[0]) for c in cond_mgc]
+        for i in range(n):
+            if cond_bap[i].shape[0] != lengths[i] or f0[i].shape[0] != lengths[i]:
+                raise ValueError(f"item {i}: conditioning and f0 lengths differ")
+        dev = next(self.mgc.parameters()).device
+        hop = int(self.vocoder.config.data.hop_size)
+        out: List[Optional[torch.Tensor]] = [None] * n
+        for plan in plan_batches(lengths, self.max_frames, world_size, rank):
+            cm = torch.stack([_pad_time(cond_mgc[i].to(dev, torch.float32), plan.frames, "replicate") for i in plan.items])
+            cb = torch.stack([_pad_time(cond_bap[i].to(dev, torch.float32), plan.frames, "replicate") for i in plan.items])
+            f = torch.stack([_pad_time(f0[i].to(dev, torch.float32), plan.frames, "zeros") for i in plan.items])
+            m = self.mgc.inference(cm)                      # [B, T, M1]
+            b = self.bap.inference(cb)                      # [B, T, M2]
+            wav = self.vocoder.inference_batch(f, self.aux_fn(m, b, f).contiguous())   # [B, 1, T * hop]
+            for k, i in enumerate(plan.items):
+                out[i] = wav[k, 0, :lengths[i] * hop].clone()
+        return out

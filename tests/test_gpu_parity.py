@@ -533,6 +533,14 @@ def test_diffusion_bf16_sampling_vs_oracle(M, C, H, L):
     assert torch.equal(y_again, y_graph)                      # deterministic
     y_rng = m.inference(cond.to(DEV))
     assert y_rng.shape == (B, T, M) and torch.isfinite(y_rng).all()
+    # a call with another batch size between two replays must not disturb the first graph (captured graphs hold device
+    # addresses of per-batch-size tables), nor may unrelated allocations in between
+    y_one = m.inference(cond[:1].to(DEV), x_T=x_T[:1].to(DEV), z=z[:, :1].to(DEV))
+    assert torch.equal(y_one, y_eager[:1]) or rel_l2(y_one.cpu(), y_eager[:1].cpu()) < 1e-2
+    junk = [torch.randn(1 << 20, device=DEV) for _ in range(8)]
+    y_back = m.inference(cond.to(DEV), x_T=x_T.to(DEV), z=z.to(DEV))
+    del junk
+    assert torch.equal(y_back, y_graph)
 
 
 def test_diffnet_bf16_full_size_properties():
@@ -841,3 +849,54 @@ def test_usfgan_wrapper_recipe_width_bf16():
         # the batch shape, and a last-bit phase difference flips bf16 roundings downstream)
         r, mx = close_bf16(wb[i:i + 1], wi, 1e-2, 5e-2)
         print(f"track {i}: batched vs single-track wrapper rel_l2={r:.2e} max={mx:.2e}")
+
+
+def test_pipeline_batched_synthesis():
+    """EnsembleSynthesizer (row f3, first part): mgc + bap diffusion + vocoder over batches of tracks — same numbers as
+    the models called by hand on the same batch, correct lengths and order for ragged items."""
+    from types import SimpleNamespace as NS
+    from ensemble_svs_with_interactions_b200.diffsinger import DiffNet, GaussianDiffusion
+    from ensemble_svs_with_interactions_b200.pipeline import EnsembleSynthesizer
+    from ensemble_svs_with_interactions_b200.usfgan import USFGANWrapper
+    from ensemble_svs_with_interactions_b200.usfgan.models import ParallelHnUSFGANGenerator
+    torch.manual_seed(11)
+    mgc = GaussianDiffusion(128, 60, DiffNet(60, 128, 4, 128, 4), K_step=6).to(DEV).eval()
+    bap = GaussianDiffusion(64, 5, DiffNet(5, 64, 2, 128, 2), K_step=6).to(DEV).eval()
+    for m in (mgc, bap):
+        with torch.no_grad():
+            m.denoise_fn.output_projection.weight.normal_(0, 0.05)
+    pe = {"conv_layers": 3, "kernel_size": 5, "dilation": 1, "padding_mode": "replicate"}
+    gen = ParallelHnUSFGANGenerator(harmonic_network_params={"blockA": 2, "cycleA": 2, "blockF": 0, "cycleF": 0, "cascade_mode": 0},
+                                    noise_network_params={"blockA": 0, "cycleA": 0, "blockF": 2, "cycleF": 2, "cascade_mode": 0},
+                                    filter_network_params={"blockA": 0, "cycleA": 0, "blockF": 2, "cycleF": 2, "cascade_mode": 0},
+                                    periodicity_estimator_params=pe, aux_channels=65).to(DEV).eval()
+    gen.remove_weight_norm()
+
+    class Cfg(dict):
+        __getattr__ = dict.__getitem__
+    config = NS(data=NS(sample_rate=24000, hop_size=120, sine_amp=0.1, noise_amp=0.0, signal_types=["sine", "uv"],
+                        sine_f0_type="contf0", df_f0_type="contf0", dense_factor=4),
+                generator=Cfg(aux_context_window=2))
+    voc = USFGANWrapper(config, gen)
+    synth = EnsembleSynthesizer(mgc, bap, voc, max_frames=1000)
+    g = torch.Generator().manual_seed(5)
+    T = 64
+    cm = [torch.randn(T, 128, generator=g) for _ in range(3)]
+    cb = [torch.randn(T, 64, generator=g) for _ in range(3)]
+    f0 = [torch.full((T, 1), 150.0 + 50 * i) for i in range(3)]
+    torch.manual_seed(77)
+    got = synth.synthesize(cm, cb, f0)
+    # by hand, same batch, same RNG stream
+    torch.manual_seed(77)
+    m = mgc.inference(torch.stack(cm).to(DEV)); b = bap.inference(torch.stack(cb).to(DEV))
+    ref = voc.inference_batch(torch.stack(f0).to(DEV), torch.cat([m, b], dim=-1).contiguous())
+    for i in range(3):
+        assert got[i].shape == (T * 120,) and torch.equal(got[i], ref[i, 0])
+    # ragged items, two "ranks": every item comes back once, with its own length
+    lens = [64, 40, 52, 64, 17]
+    cm = [torch.randn(n, 128, generator=g) for n in lens]; cb = [torch.randn(n, 64, generator=g) for n in lens]
+    f0 = [torch.full((n, 1), 220.0) for n in lens]
+    outs = [synth.synthesize(cm, cb, f0, world_size=2, rank=r) for r in range(2)]
+    for i, n in enumerate(lens):
+        w = [o[i] for o in outs if o[i] is not None]
+        assert len(w) == 1 and w[0].shape == (n * 120,) and torch.isfinite(w[0]).all()

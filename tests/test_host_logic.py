@@ -121,3 +121,27 @@ def test_dilated_factor_and_signal_generator_cpu():
     torch.manual_seed(53)
     sig = sg(torch.FloatTensor(f0).unsqueeze(0).transpose(2, 1))
     assert torch.allclose(sig, g.out["in_signal"], atol=1e-6)
+
+
+def test_pipeline_plan_batches():
+    """Host side of the batched (song, track) synthesis: ranks get items longest-first, batches
+    respect the frame budget after padding, every item is scheduled exactly once."""
+    from ensemble_svs_with_interactions_b200.pipeline import plan_batches
+    lengths = [6000, 5990, 3000, 3001, 2999, 100, 6000, 42]
+    seen = []
+    for rank in range(2):
+        plans = plan_batches(lengths, max_frames=12000, world_size=2, rank=rank, multiple=4)
+        for p in plans:
+            assert p.frames % 4 == 0 and p.frames >= max(lengths[i] for i in p.items)
+            assert len(p.items) == 1 or len(p.items) * p.frames <= 12000
+            seen += p.items
+    assert sorted(seen) == list(range(len(lengths)))
+    # one rank, huge budget: a single batch padded to the longest item
+    (p,) = plan_batches(lengths, max_frames=10 ** 9)
+    assert sorted(p.items) == list(range(len(lengths))) and p.frames == 6000
+    # an item longer than the budget still runs, alone
+    plans = plan_batches([50, 5000, 60], max_frames=1000)
+    assert [sorted(p.items) for p in plans] == [[1], [0, 2]]
+    import pytest
+    with pytest.raises(ValueError):
+        plan_batches(lengths, max_frames=0)
