@@ -120,7 +120,6 @@ _SIGNATURES = {
     "svsk_diffnet_packed_row": [_I, _I],
     "svsk_linear_bf16": [C.POINTER(LinearBf16Params), _V],
     "svsk_usfgan_block_bf16": [C.POINTER(UsfganBlockParams), _V],
-    "svsk_usfgan_block2_bf16": [C.POINTER(UsfganBlockParams), _V],
     "svsk_usfgan_pack_block": [_V, _V, _V, _V, _V, _I, _I, _I, _V],
     "svsk_ntc_bf16_to_nct_f32": [_V, _V, _I, _I, _I, _I, _V],
     "svsk_conv1d_bf16": [C.POINTER(Conv1dBf16Params), _V],

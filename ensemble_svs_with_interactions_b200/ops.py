@@ -382,11 +382,8 @@ def dot_rows_bf16(x, w, bias):
 
 
 def usfgan_block_bf16(xb_in, xb_out, aux, w1p, woutp, bias1, bout, *, dilation=1, idx=None, out_scale=math.sqrt(0.5),
-                      out_relu=False, kernel=None):
-    """kernel=1: single-CTA persistent kernel (default); kernel=2: CTA-pair variant (same speed on B200: both are bound
-    by shared-memory traffic, see DESIGN.md §4 — kept for A/B measurements)."""
-    if kernel is None:
-        kernel = int(os.environ.get("SVSK_USFGAN_KERNEL", "1"))
+                      out_relu=False):
+    """One fused uSFGAN Fixed / Adaptive block (svsk_usfgan_block_bf16)."""
     B, T, Cc = xb_in.shape
     p = L.UsfganBlockParams()
     p.xb_in, p.xb_out, p.aux = L.ptr(xb_in, bf16, "xb_in"), L.ptr(xb_out, bf16, "xb_out"), L.ptr(aux, bf16, "aux")
@@ -397,5 +394,4 @@ def usfgan_block_bf16(xb_in, xb_out, aux, w1p, woutp, bias1, bout, *, dilation=1
     p.B, p.T, p.A = B, T, aux.shape[2]
     p.dilation, p.adaptive, p.out_scale = int(dilation), int(idx is not None), float(out_scale)
     p.out_relu = int(out_relu)
-    fn = L.lib().svsk_usfgan_block2_bf16 if kernel == 2 else L.lib().svsk_usfgan_block_bf16
-    L.check(fn(C.byref(p), L.stream_ptr()), "usfgan_block_bf16")
+    L.check(L.lib().svsk_usfgan_block_bf16(C.byref(p), L.stream_ptr()), "usfgan_block_bf16")

@@ -315,10 +315,6 @@ typedef struct svsk_usfgan_block_params {
   int32_t out_relu;    /* 1: xb_out = relu(...) — folds conv_last's leading ReLU into the last block (generator.py:461) */
 } svsk_usfgan_block_params;
 SVSK_API int svsk_usfgan_block_bf16(const svsk_usfgan_block_params* p, void* stream);
-/* Same contract, CTA-pair variant (tcgen05 cta_group::2, M = 256 samples per MMA, each CTA stages half of the weights,
- * 8-slot activation ring).  Measured equal to the single-CTA kernel on B200 (both shared-memory-traffic bound); the
- * drop-in generators use svsk_usfgan_block_bf16. */
-SVSK_API int svsk_usfgan_block2_bf16(const svsk_usfgan_block_params* p, void* stream);
 /* w_taps [128][64][3] (k=3 conv, or stacked convP/convC/convF), w_aux [128][A], w_out [64][64] (fp32) -> packed bf16 */
 SVSK_API int svsk_usfgan_pack_block(const float* w_taps, const float* w_aux, const float* w_out, void* w1p, void* woutp,
                                     int C, int A, int G, void* stream);

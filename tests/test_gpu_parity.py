@@ -598,8 +598,7 @@ def _usfgan_block_ref(w_taps, b1, w_aux, w_out, b_out, x, c, taps):
                                                (130, 2, False, 72), (1000, 4, True, 80), (333, 16, True, 80),
                                                (20000, 8, False, 80), (20000, 2, True, 80),
                                                (400000, 512, False, 80), (400000, 16, True, 80)])
-@pytest.mark.parametrize("kernel", [2, 1])
-def test_usfgan_block_bf16(T, dil, adaptive, A, kernel):
+def test_usfgan_block_bf16(T, dil, adaptive, A):
     ops = _ops()
     g = torch.Generator().manual_seed(T + dil)
     B = 2
@@ -618,7 +617,7 @@ def test_usfgan_block_bf16(T, dil, adaptive, A, kernel):
     w1p, woutp = ops.usfgan_pack_block(w_taps.to(DEV), w_aux[:, :, 0].contiguous().to(DEV), w_out[:, :, 0].contiguous().to(DEV))
     out = torch.full_like(xb, float("nan"))
     idx = ops.pd_index(d.to(DEV), dil) if adaptive else None
-    ops.usfgan_block_bf16(xb, out, auxb, w1p, woutp, b1.to(DEV), b_out.to(DEV), dilation=dil, idx=idx, kernel=kernel)
+    ops.usfgan_block_bf16(xb, out, auxb, w1p, woutp, b1.to(DEV), b_out.to(DEV), dilation=dil, idx=idx)
     torch.cuda.synchronize()
     close_bf16(out.float().transpose(1, 2), ref, 4e-3, 1.5e-2)
 
@@ -793,10 +792,9 @@ def test_usfgan_block_bf16_short_sequences(T, dil):
     ref = _usfgan_block_ref(w_taps, b1, w_aux, w_out, b_out, x, c, taps)
     xb, _ = ops.nct_to_ntc(x.to(DEV)); auxb, _ = ops.nct_to_ntc(c.to(DEV))
     w1p, woutp = ops.usfgan_pack_block(w_taps.to(DEV), w_aux[:, :, 0].contiguous().to(DEV), w_out[:, :, 0].contiguous().to(DEV))
-    for kernel in (1, 2):
-        out = torch.full_like(xb, float("nan"))
-        ops.usfgan_block_bf16(xb, out, auxb, w1p, woutp, b1.to(DEV), b_out.to(DEV), dilation=dil, kernel=kernel)
-        close_bf16(out.float().transpose(1, 2), ref, 4e-3, 1.5e-2)
+    out = torch.full_like(xb, float("nan"))
+    ops.usfgan_block_bf16(xb, out, auxb, w1p, woutp, b1.to(DEV), b_out.to(DEV), dilation=dil)
+    close_bf16(out.float().transpose(1, 2), ref, 4e-3, 1.5e-2)
     with pytest.raises(RuntimeError, match="reflect"):
         ops.usfgan_block_bf16(xb, out, auxb, w1p, woutp, b1.to(DEV), b_out.to(DEV), dilation=T)
 

@@ -8,7 +8,6 @@ import torch  # noqa: E402
 from ensemble_svs_with_interactions_b200 import ops  # noqa: E402
 
 B, T = 6, 720000
-KERNEL = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 g = torch.Generator().manual_seed(0)
 xb = torch.randn(B, T, 64, device="cuda").to(torch.bfloat16)
 out = torch.empty_like(xb)
@@ -19,23 +18,21 @@ b1 = torch.zeros(128, device="cuda"); bo = torch.zeros(64, device="cuda")
 d = torch.empty(B, 1, T, device="cuda").uniform_(2, 40)
 idx = ops.pd_index(d, 4)
 for name, kw in (("fixed d=8", dict(dilation=8)), ("adaptive", dict(idx=idx))):
-    for ab in ((0,) if KERNEL == 2 else (0, 256, 0, 256, 1, 4, 5)):
+    for ab in (0, 256, 0, 256, 1, 4, 5):
         os.environ["SVSK_USFGAN_ABLATE"] = str(ab)
         for _ in range(2):
-            ops.usfgan_block_bf16(xb, out, auxb, w1p, woutp, b1, bo, kernel=KERNEL, **kw)
+            ops.usfgan_block_bf16(xb, out, auxb, w1p, woutp, b1, bo, **kw)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(5):
-            ops.usfgan_block_bf16(xb, out, auxb, w1p, woutp, b1, bo, kernel=KERNEL, **kw)
+            ops.usfgan_block_bf16(xb, out, auxb, w1p, woutp, b1, bo, **kw)
         e1.record(); e1.synchronize()
         us = e0.elapsed_time(e1) / 5 * 1e3
         print(f"{name:10s} ablate={ab:2d} (1=no epilogue, 4=no MMAs, 256=synchronous probe): {us:7.1f} us  "
               f"-> {us * 1e-6 * 1.85e9 / (B * ((T + 127) // 128) / 148):6.0f} cycles/tile", flush=True)
 
 # role accounting (cycles per tile, averaged over CTAs)
-if KERNEL == 2:
-    sys.exit(0)
 names = ["prod wait empty", "mma wait operands", "mma wait G", "mma loop total", "tiles", "epi wait D1", "epi gating",
          "epi wait D2", "epi residual", "epi sync/store", "mma fence_after", "mma commit/arrive", "mma probe", "mma issue"]
 for ab, name, kw in ((0, "fixed d=8", dict(dilation=8)), (0, "adaptive", dict(idx=idx)), (4, "fixed, no MMAs", dict(dilation=8)),
@@ -43,7 +40,7 @@ for ab, name, kw in ((0, "fixed d=8", dict(dilation=8)), (0, "adaptive", dict(id
     os.environ["SVSK_USFGAN_ABLATE"] = str(ab)
     dbg = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
     os.environ["SVSK_USFGAN_TIMELINE"] = str(dbg.data_ptr())
-    ops.usfgan_block_bf16(xb, out, auxb, w1p, woutp, b1, bo, kernel=KERNEL, **kw)
+    ops.usfgan_block_bf16(xb, out, auxb, w1p, woutp, b1, bo, **kw)
     torch.cuda.synchronize()
     os.environ.pop("SVSK_USFGAN_TIMELINE")
     dd = dbg.view(148, 16).float()
