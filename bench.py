@@ -343,7 +343,7 @@ def main():
             "clocks": clk.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf,
-                         "traffic": _ncu_traffic("r01x_stack_ncu_full_summary.json" if use_stack else "r01h_block2_ncu_full_summary.json"),
+                         "traffic": _ncu_traffic("r01z_stack_ncu_full_summary.json" if use_stack else "r01h_block2_ncu_full_summary.json"),
                          "kernel": ("diffnet_stack_kernel (all 20 residual blocks in one launch; CTA pairs, tcgen05 cta_group::2)"
                                     if use_stack else "diffnet_block3_kernel (one residual block; CTA pairs, tcgen05 cta_group::2)"),
                          "us_per_launch": block_ms * 1e3, "flops_per_launch": flops_per_launch,
