@@ -239,16 +239,25 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     const int r = threadIdx.x - 64;
     int s = 0;
     uint32_t ph = 0;
+    // This row's two tap indices are requested one tile ahead, so that their (L2) latency is off the slot's chain.
+    auto load_idx = [&](int tile, int& ip_, int& ifu_) {
+      ip_ = ifu_ = -1;
+      if (a.adaptive && tile < a.total_tiles) {
+        const int b_ = tile / a.tiles_per_row, t_ = (tile - b_ * a.tiles_per_row) * 128 + r;
+        if (t_ < T) {
+          ip_ = __ldg(a.idx_past + (size_t)b_ * T + t_);
+          ifu_ = __ldg(a.idx_future + (size_t)b_ * T + t_);
+        }
+      }
+    };
+    int ip_next, ifu_next;
+    load_idx(blockIdx.x, ip_next, ifu_next);
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const int b = tile / a.tiles_per_row, t0 = (tile - b * a.tiles_per_row) * 128;
       const bool gather = tile_needs_gather(t0, T, a.dilation, a.adaptive);
       const int t = t0 + r;
-      // this row's two tap indices, requested before the slot waits so that their (L2) latency is off the slot's chain
-      int ip = -1, ifu = -1;
-      if (a.adaptive && t < T) {
-        ip = __ldg(a.idx_past + (size_t)b * T + t);
-        ifu = __ldg(a.idx_future + (size_t)b * T + t);
-      }
+      const int ip = ip_next, ifu = ifu_next;
+      load_idx(tile + gridDim.x, ip_next, ifu_next);
       for (int kb = 0; kb < KB; ++kb) {
         // Wait on EVERY slot, also the ones the TMA producer fills: parity waits only tell two consecutive phases apart,
         // so this warp group must never run more than one ring wrap ahead of the MMA issuer.
