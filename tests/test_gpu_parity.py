@@ -433,6 +433,29 @@ def test_diffnet_stack_matches_per_layer_kernels(C, H, M, L, B, T):
     assert torch.equal(y, y2)
 
 
+@pytest.mark.parametrize("C,H,M,L", [(128, 192, 60, 3), (256, 64, 33, 2)])
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 7), (3, 9), (2, 129), (1, 257), (2, 2049)])
+def test_diffnet_sampling_odd_shapes(C, H, M, L, B, T):
+    """Ragged and tiny shapes through the one-launch stack (one cluster per track up to 2048 frames, CTA pairs + edge rows
+    through global memory beyond) and the fused step kernel, against the layer-at-a-time kernels."""
+    import os
+    from ensemble_svs_with_interactions_b200.diffsinger import GaussianDiffusion
+    den = _random_diffnet(C, H, M, L, seed=T + M)
+    m = GaussianDiffusion(H, M, den, K_step=3).to(DEV).eval()
+    m.use_cuda_graph = False
+    g = torch.Generator().manual_seed(T)
+    cond = torch.randn(B, T, H, generator=g).to(DEV); x_T = torch.randn(B, 1, M, T, generator=g).to(DEV)
+    z = torch.randn(3, B, 1, M, T, generator=g).to(DEV)
+    y = m.inference(cond, x_T=x_T, z=z)
+    os.environ["SVSK_DIFFNET_STACK"] = "0"; os.environ["SVSK_DIFFNET_STEP"] = "0"
+    try:
+        ref = m.inference(cond, x_T=x_T, z=z)
+    finally:
+        os.environ.pop("SVSK_DIFFNET_STACK"); os.environ.pop("SVSK_DIFFNET_STEP")
+    assert torch.isfinite(y).all()
+    close_bf16(y, ref, 2e-2, 6e-2)
+
+
 def test_diffnet_stack_refuses_grids_that_do_not_fit():
     ops = _ops()
     assert not ops.diffnet_stack_fits(64, 2000, 256, 256)   # 512 CTA pairs
