@@ -310,6 +310,7 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     const int row = q * 32 + lane;
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
     const bool elected = (warp == 6 && lane == 0);
+    const bool qlead = (sub == 0 && lane == 0);  // issues the TMA stores of this lane quarter's 32 rows
     // Software-pipelined: iteration `it` gates tile it (so GEMM2(it) can be queued) and THEN finishes tile it-1, whose
     // GEMM2 ran behind GEMM1(it) in the in-order tensor pipe while this warp group was gating.
     const int my_tiles = a.total_tiles > (int)blockIdx.x ? (a.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -336,9 +337,9 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         }
         uint8_t* gb = gbuf + (it % 3) * kUTile;
         long long c_0 = (kProf ? clock64() : 0ll);
-        if (it >= 3) {  // buffer it%3 was the output tile of tile it-3: its TMA store must have finished reading
-          if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          ptx::named_bar_sync(2, 256);
+        if (it >= 3) {  // buffer it%3 held the output tile of tile it-3: this quarter's TMA store must have read its rows
+          if (qlead) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          ptx::named_bar_sync(4 + q, 64);
         }
         acc_sync += (kProf ? clock64() : 0ll) - c_0;
         c_0 = (kProf ? clock64() : 0ll);
@@ -405,9 +406,11 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         ptx::fence_proxy_async_smem();
         acc_e2 += (kProf ? clock64() : 0ll) - c_0;
         c_0 = (kProf ? clock64() : 0ll);
-        ptx::named_bar_sync(3, 256);
-        if (elected) {
-          ptx::tma_store_3d(&tm_xout, gb, 0, t0, b);
+        // each TMEM lane quarter (two warps, 32 rows of the tile) stores its own rows: a 64-thread barrier and four
+        // TMA issuers instead of a CTA-wide barrier and one
+        ptx::named_bar_sync(4 + q, 64);
+        if (qlead) {
+          ptx::tma_store_3d(&tm_xout, gb + q * 4096, 0, t0 + q * 32, b);
           ptx::bulk_commit_group();
         }
         acc_sync += (kProf ? clock64() : 0ll) - c_0;
@@ -415,7 +418,7 @@ usfgan_block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
 #pragma unroll
       for (int i = 0; i < 2; ++i) { xr_prev[i][0] = xr_cur[i][0]; xr_prev[i][1] = xr_cur[i][1]; }
     }
-    if (elected) ptx::bulk_wait_read_all();
+    if (qlead) ptx::bulk_wait_read_all();
     if (kProf && a.dbg && elected) {
       a.dbg[blockIdx.x * 16 + 5] = acc_d1;    // epilogue: waiting for D1
       a.dbg[blockIdx.x * 16 + 6] = acc_gate;  // epilogue: gating + G stores + arrive
@@ -490,8 +493,9 @@ extern "C" int svsk_usfgan_block_bf16(const svsk_usfgan_block_params* pp, void* 
     uint64_t dims[3] = {64, (uint64_t)p.T, (uint64_t)p.B};
     uint64_t str[2] = {128, (uint64_t)p.T * 128};
     uint32_t box[3] = {64, 128, 1};
+    uint32_t box_q[3] = {64, 32, 1};  // stores go out per TMEM lane quarter: 32 rows
     if ((rc = make_tmap_bf16(&tm_x, p.xb_in, 3, dims, str, box))) return rc;
-    if ((rc = make_tmap_bf16(&tm_xout, p.xb_out, 3, dims, str, box))) return rc;
+    if ((rc = make_tmap_bf16(&tm_xout, p.xb_out, 3, dims, str, box_q))) return rc;
   }
   {
     uint64_t dims[3] = {(uint64_t)p.A, (uint64_t)p.T, (uint64_t)p.B};
