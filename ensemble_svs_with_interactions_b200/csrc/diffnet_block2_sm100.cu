@@ -259,7 +259,7 @@ diffnet_block2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     const int row = q * 32 + lane;
     const int t = t_cta0 + row;
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
-    const bool has_l = (t - a.dilation) >= 0, has_r = (t + a.dilation) < T, valid = t < T;
+    const bool has_l = (t - a.dilation) >= 0, has_r = (t + a.dilation) < T;
     const bool stamp = (warp == 2 && lane == 0);
 
     // ---- epilogue 1: gating -> G

@@ -480,7 +480,6 @@ extern "C" int svsk_diffnet_block3_bf16(const svsk_diffnet_block_params* pp, voi
   const int fixed = CB * k3WinBytes + gc_tiles * k3Tile + 4 * 2 * p.C * (int)sizeof(float) + (int)sizeof(Diffnet3Barriers) + 1024;
   int nentries = (k3SmemLimit - fixed) / k3Tile;
   if (nentries > k3MaxEntries) nentries = k3MaxEntries;
-  const int NB = (2 * p.C) / 256;
   // skip slabs are staged in the ring entries and in G: 32 fp32 columns each
   SVSK_REQUIRE(nentries >= 3 && nentries + CB >= p.C / 32, SVSK_E_ARG, "diffnet_block3_bf16: not enough shared memory");
   const int smem_bytes = nentries * k3Tile + fixed;

@@ -32,7 +32,6 @@ namespace svsk {
 constexpr int kUTile = 128 * 128;  // 128 rows x 64 bf16
 constexpr int kUMaxStages = 6;
 constexpr int kUThreads = 480;  // producer, GEMM1 issuer, 4 gather, 8 epilogue, GEMM2 issuer warps
-constexpr int kUMaxKB = 8;         // 3 taps + up to 5 aux k-blocks (aux <= 320 channels)
 
 struct UsfganArgs {
   const __nv_bfloat16* xb_in;
