@@ -1,0 +1,47 @@
+"""Race hunt (debug aid): repeat the persistent kernels many times on fixed inputs; every output must be bit-identical."""
+import os, sys, math
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from ensemble_svs_with_interactions_b200 import ops
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+m = bench.build_model().to("cuda"); den = m.denoise_fn; plan = den.bf16_plan(); table = m._step_table()
+bad = 0
+for B, T in ((6, 2000), (3, 6000), (5, 517), (2, 2049)):
+    g = torch.Generator().manual_seed(B * T)
+    cond = torch.randn(B, T, plan.H, generator=g).cuda().to(torch.bfloat16)
+    xb0 = torch.randn(B, T, plan.C, generator=g).cuda().to(torch.bfloat16)
+    e0, e1 = torch.empty_like(xb0), torch.empty_like(xb0)
+    flags = torch.empty((B * 2 * ((T + 255) // 256),), device="cuda", dtype=torch.int32)
+    ref = None
+    for it in range(n):
+        skip = torch.empty(B, T, plan.C, device="cuda")
+        ops.diffnet_stack_bf16(xb0, e0, e1, skip, cond, plan.w1p_all, plan.woutp_all, table[:, 50:51], plan.bout_all, flags,
+                               plan.dilations, stepbias_batch_stride=0, stepbias_layer_stride=table.stride(0))
+        if ref is None:
+            ref = skip.clone()
+        elif not torch.equal(skip, ref):
+            bad += 1
+            print(f"stack B={B} T={T}: run {it} differs, max|d|={float((skip - ref).abs().max()):.3e}", flush=True)
+    torch.cuda.synchronize()
+    print(f"stack B={B} T={T}: {n} runs, finite={bool(torch.isfinite(ref).all())}", flush=True)
+# uSFGAN block, fixed and adaptive
+B, T = 3, 200000
+xb = torch.randn(B, T, 64, device="cuda").to(torch.bfloat16); aux = torch.randn(B, T, 80, device="cuda").to(torch.bfloat16)
+w1p, woutp = ops.usfgan_pack_block(torch.randn(128, 64, 3, device="cuda") * 0.05, torch.randn(128, 80, device="cuda") * 0.05,
+                                   torch.randn(64, 64, device="cuda") * 0.1)
+b1 = torch.randn(128, device="cuda") * 0.1; bo = torch.randn(64, device="cuda") * 0.1
+idx = ops.pd_index(torch.empty(B, 1, T, device="cuda").uniform_(2, 40), 4)
+for name, kw in (("fixed", dict(dilation=8)), ("adaptive", dict(idx=idx))):
+    ref = None
+    for it in range(n):
+        out = torch.empty_like(xb)
+        ops.usfgan_block_bf16(xb, out, aux, w1p, woutp, b1, bo, **kw)
+        if ref is None:
+            ref = out.clone()
+        elif not torch.equal(out, ref):
+            bad += 1
+            print(f"usfgan {name}: run {it} differs", flush=True)
+    print(f"usfgan {name}: {n} runs", flush=True)
+print("mismatching runs:", bad)
