@@ -187,15 +187,14 @@ conv1d_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
-    const bool elected = (warp == 6 && lane == 0);
     int n = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++n) {
       const int b = tile / a.tiles_per_row, t0 = (tile - b * a.tiles_per_row) * 128;
       const int p = n & 1;
       uint8_t* ob = obuf + p * a.out_chunks * kCTile;
-      if (n >= 2) {
-        if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        ptx::named_bar_sync(2, 128);
+      if (n >= 2) {  // this warp's 32 rows of the buffer: its own TMA store of tile n-2 must have read them
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
       }
       ptx::mbar_wait(&bars->d_full[p], (n >> 1) & 1);
       ptx::tc_fence_after();
@@ -220,13 +219,14 @@ conv1d_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bars->d_empty[p]);
       ptx::fence_proxy_async_smem();
-      ptx::named_bar_sync(2, 128);
-      if (elected) {
-        for (int oc = 0; oc < a.out_chunks; ++oc) ptx::tma_store_3d(&tm_y, ob + oc * kCTile, oc * 64, t0, b);
+      __syncwarp();
+      if (lane == 0) {  // one store per warp (= TMEM lane quarter = 32 rows): no CTA-wide barrier, four issuers
+        for (int oc = 0; oc < a.out_chunks; ++oc)
+          ptx::tma_store_3d(&tm_y, ob + oc * kCTile + q * 4096, oc * 64, t0 + q * 32, b);
         ptx::bulk_commit_group();
       }
     }
-    if (elected) ptx::bulk_wait_read_all();
+    if (lane == 0) ptx::bulk_wait_read_all();
   }
 
   ptx::tc_fence_before();
@@ -333,7 +333,7 @@ extern "C" int svsk_conv1d_bf16(const svsk_conv1d_bf16_params* pp, void* stream)
   {
     uint64_t dims[3] = {(uint64_t)p.Cout, (uint64_t)p.T, (uint64_t)p.B};
     uint64_t str[2] = {(uint64_t)p.Cout * 2, (uint64_t)p.T * p.Cout * 2};
-    uint32_t box[3] = {64, 128, 1};
+    uint32_t box[3] = {64, 32, 1};  // stores go out per epilogue warp: 32 rows
     if ((rc = make_tmap_bf16(&tm_y, p.y, 3, dims, str, box))) return rc;
   }
   int dev = 0, num_sms = 148;
