@@ -178,7 +178,7 @@ def vocoder_bench(dev, peaks, tracks=6, seconds=30.0, reps=3):
             "unit": "audio-sec/s", "ms_per_pass": ms, "precision": m.resolved_precision(),
             "config": {"workload": f"{tracks} tracks x {seconds:.0f} s @ 24 kHz, hop 120, aux 80, 20A+5F+30F blocks"},
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                         "traffic": None, "kernel": "usfgan_block_kernel", "us_per_launch": blk_ms * 1e3,
+                         "traffic": _ncu_traffic("r01z_usfgan_block_ncu_full_summary.json"), "kernel": "usfgan_block_kernel", "us_per_launch": blk_ms * 1e3,
                          "tflops": 2.0 * tracks * Tn * 38912 / (blk_ms * 1e-3) / 1e12}}
 
 
