@@ -77,15 +77,15 @@ diffnet_step_kernel(const __grid_constant__ CUtensorMap tm_wskip, const __grid_c
   }
 
   // ---- A = bf16(skip32 * scale): 16 bytes (8 channels) per thread and step, rows past the end of the track = 0.
-  //      Four steps' loads are in flight together (the loop is bound by the latency of its 128 KB of fp32 reads).
+  //      Eight steps' loads are in flight together (the loop is bound by the latency of its 128 KB of fp32 reads).
   {
     const int chunks = C / 8;  // 16-byte bf16 chunks per row
     const int total = 128 * chunks;
     const float s = a.skip_scale;
-    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * kStepThreads) {
-      float4 v[4][2];
+    for (int i0 = threadIdx.x; i0 < total; i0 += 8 * kStepThreads) {
+      float4 v[8][2];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int i = i0 + u * kStepThreads;
         const int r = i / chunks, ch = i - r * chunks;
         v[u][0] = v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -96,7 +96,7 @@ diffnet_step_kernel(const __grid_constant__ CUtensorMap tm_wskip, const __grid_c
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int i = i0 + u * kStepThreads;
         if (i < total) {
           const int r = i / chunks, ch = i - r * chunks;
