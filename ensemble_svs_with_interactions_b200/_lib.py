@@ -68,6 +68,26 @@ class LinearBf16Params(C.Structure):
     ]
 
 
+class LstmParams(C.Structure):
+    _fields_ = [
+        ("pre", C.c_void_p), ("w_hh", C.c_void_p), ("lengths", C.c_void_p), ("h_f32", C.c_void_p), ("h_bf16", C.c_void_p),
+        ("pre_stride_b", C.c_int64), ("pre_stride_t", C.c_int64), ("pre_stride_r", C.c_int64),
+        ("hf_stride_b", C.c_int64), ("hf_stride_t", C.c_int64), ("hf_stride_c", C.c_int64),
+        ("hb_stride_b", C.c_int64), ("hb_stride_t", C.c_int64),
+        ("B", C.c_int32), ("T", C.c_int32), ("H", C.c_int32), ("ndir", C.c_int32),
+    ]
+
+
+class TapGemmBf16Params(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("wp", C.c_void_p), ("bias", C.c_void_p), ("y_bf16", C.c_void_p), ("y_f32", C.c_void_p),
+        ("B", C.c_int32), ("T", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32), ("ksize", C.c_int32),
+        ("Tp_x", C.c_int32), ("ldx", C.c_int32),
+        ("Tp_y", C.c_int32), ("y_row0", C.c_int32), ("ldy_b", C.c_int32), ("ldy_f", C.c_int32),
+        ("act", C.c_int32),
+    ]
+
+
 class UsfganBlockParams(C.Structure):
     _fields_ = [
         ("xb_in", C.c_void_p), ("xb_out", C.c_void_p), ("aux", C.c_void_p),
@@ -126,6 +146,12 @@ _SIGNATURES = {
     "svsk_conv1d_pack_bf16": [_V, _V, _I, _I, _I, _V],
     "svsk_periodic_mix_bf16": [_V, _V, _V, _V, _Z, _V],
     "svsk_dot_rows_bf16": [_V, _V, _F, _V, _Z, _I, _V],
+    "svsk_lstm_f32": [C.POINTER(LstmParams), _V],
+    "svsk_lstm_supported": [C.c_int],
+    "svsk_tapgemm_bf16": [C.POINTER(TapGemmBf16Params), _V],
+    "svsk_tapgemm_pack_bf16": [_V, _V, _V, _I, _I, _I, _V],
+    "svsk_reflect_pad_rows_bf16": [_V, _I, _I, _I, _I, _I, _V],
+    "svsk_encoder_front": [_V, _V, _V, C.c_longlong, _I, _I, _I, _I, _I, _V],
 }
 EXPORTED_SYMBOLS = ["svsk_last_error"] + list(_SIGNATURES)
 

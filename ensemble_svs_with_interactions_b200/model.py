@@ -1,0 +1,289 @@
+"""FFConvLSTM encoder — drop-in for ``nnsvs.model.FFConvLSTM`` / ``MultiSpeakerFFConvLSTM`` (nnsvs/model.py:779-1015).
+
+SURVEY.md §8(f) row 1: the step right in front of the denoiser.  In the multi-track recipe it is the ``encoder`` of both
+``GaussianDiffusion`` streams (conf/train_acoustic/model/multitrack_acoustic_nnsvs_world_multi_ar_f0_diff_mgcbap.yaml:
+104-116,146-158) and runs once per track; its output is the ``cond`` tensor of every denoiser call.
+
+Same constructor kwargs, ``forward`` / ``inference`` signatures and ``state_dict`` keys and order as the reference
+(``emb``, ``fc_in``, ``ff.{0,2,4}``, ``conv.{1,2,5,6,9,10}``, ``lstm.*``, ``fc``); the ``nn`` sub-modules only hold
+parameters, their ``forward`` never runs.  Eval-mode forward only (BatchNorm running statistics, no dropout):
+
+* ``precision="fp32"``: svsk_conv1d_f32 for every Linear (k = 1) and for the reflect-padded k = 7 convolutions with the
+  BatchNorm folded into weights and bias, svsk_lstm_f32 for the recurrences — the reference's fp32 arithmetic.
+* ``precision="bf16"``: svsk_tapgemm_bf16 (tcgen05) for every matrix product on frame-major bf16 activations, the
+  recurrence itself stays fp32 (svsk_lstm_f32 with W_hh in registers).
+* ``precision="auto"`` (default): bf16 when every width is a multiple of 16, fp32 otherwise.
+
+Not built: ``use_mdn=True`` (the MDN head) and training mode — both raise.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from .base import BaseModel, PredictionType
+
+__all__ = ["FFConvLSTM", "MultiSpeakerFFConvLSTM", "init_weights"]
+
+
+def init_weights(net: nn.Module, init_type: str = "normal", init_gain: float = 0.02) -> None:
+    """nnsvs/util.py:31-67: (re)initialise Conv*/Linear weights, zero their biases; ``"none"`` leaves torch's defaults."""
+    if init_type == "none":
+        return
+    inits = {
+        "normal": lambda w: nn.init.normal_(w, 0.0, init_gain),
+        "xavier_normal": lambda w: nn.init.xavier_normal_(w, gain=init_gain),
+        "kaiming_normal": lambda w: nn.init.kaiming_normal_(w, a=0, mode="fan_in"),
+        "orthogonal": lambda w: nn.init.orthogonal_(w, gain=init_gain),
+    }
+    if init_type not in inits:
+        raise NotImplementedError("initialization method [%s] is not implemented" % init_type)
+
+    def visit(m):
+        name = type(m).__name__
+        if hasattr(m, "weight") and ("Conv" in name or "Linear" in name):
+            inits[init_type](m.weight.data)
+            if getattr(m, "bias", None) is not None:
+                nn.init.constant_(m.bias.data, 0.0)
+        elif "BatchNorm2d" in name:
+            nn.init.normal_(m.weight.data, 1.0, init_gain)
+            nn.init.constant_(m.bias.data, 0.0)
+
+    net.apply(visit)
+
+
+class _Plan:
+    """Weights in the layouts the kernels read, built once per parameter version."""
+
+    def __init__(self, m: "FFConvLSTM", precision: str):
+        with torch.no_grad():
+            self.precision = precision
+            f = lambda t: t.detach().float().contiguous()
+            # front: emb(argmax(onehot)) + fc_in(rest) == [fc_in | emb^T] applied to the input with an exact one-hot block
+            if m.embed_dim is not None:
+                s, V = m.in_ph_start_idx, m.num_vocab
+                wc = torch.empty((m.embed_dim, m.in_dim), device=m.fc_in.weight.device, dtype=torch.float32)
+                wc[:, :s] = m.fc_in.weight[:, :s]
+                wc[:, s:s + V] = m.emb.weight.t()
+                wc[:, s + V:] = m.fc_in.weight[:, s:]
+                front = [(wc, f(m.fc_in.bias))]
+            else:
+                front = []
+            ff = [(f(m.ff[i].weight), f(m.ff[i].bias)) for i in (0, 2, 4)]
+            conv = []
+            for i in (1, 5, 9):
+                bn = m.conv[i + 1]
+                scale = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
+                bias = (m.conv[i].bias.float() - bn.running_mean.float()) * scale + bn.bias.float()
+                conv.append((f(m.conv[i].weight), scale.contiguous(), bias.contiguous()))
+            lstm = []
+            for l in range(m.lstm.num_layers):
+                g = lambda n: getattr(m.lstm, n.format(l))
+                w_ih = torch.cat([g("weight_ih_l{}"), g("weight_ih_l{}_reverse")], 0).float().contiguous()
+                b = torch.cat([g("bias_ih_l{}") + g("bias_hh_l{}"), g("bias_ih_l{}_reverse") + g("bias_hh_l{}_reverse")], 0)
+                w_hh = torch.stack([g("weight_hh_l{}"), g("weight_hh_l{}_reverse")], 0).float().contiguous()
+                lstm.append((w_ih, b.float().contiguous(), w_hh))
+            fc = (f(m.fc.weight), f(m.fc.bias))
+
+            if precision == "fp32":
+                k1 = lambda w: w.unsqueeze(-1).contiguous()
+                self.front = [(k1(w), b) for w, b in front]
+                self.ff = [(k1(w), b) for w, b in ff]
+                self.conv = [((w * s[:, None, None]).contiguous(), b) for w, s, b in conv]
+                self.lstm = [(k1(w), b, whh) for w, b, whh in lstm]
+                self.fc = (k1(fc[0]), fc[1])
+            else:
+                self.front = [(ops.tapgemm_pack_bf16(w), b) for w, b in front]
+                self.ff = [(ops.tapgemm_pack_bf16(w), b) for w, b in ff]
+                self.conv = [(ops.tapgemm_pack_bf16(w, s), b) for w, s, b in conv]
+                self.lstm = [(ops.tapgemm_pack_bf16(w), b, whh) for w, b, whh in lstm]
+                out_p = -(-m.out_dim // 16) * 16     # the GEMM writes 16 output channels at a time
+                wf = torch.zeros((out_p, fc[0].shape[1]), device=fc[0].device, dtype=torch.float32)
+                wf[:m.out_dim] = fc[0]
+                bf = torch.zeros(out_p, device=fc[0].device, dtype=torch.float32)
+                bf[:m.out_dim] = fc[1]
+                self.fc = (ops.tapgemm_pack_bf16(wf), bf)
+                self.out_p = out_p
+
+
+class FFConvLSTM(BaseModel):
+    """nnsvs/model.py:779-926.  ``precision``: "auto" | "bf16" | "fp32" (see the module docstring)."""
+
+    def __init__(self, in_dim, ff_hidden_dim=2048, conv_hidden_dim=1024, lstm_hidden_dim=256, out_dim=67, dropout=0.0,
+                 num_lstm_layers=2, bidirectional=True, init_type="none", use_mdn=False, dim_wise=True, num_gaussians=4,
+                 in_ph_start_idx: int = 1, in_ph_end_idx: int = 50, embed_dim=None, precision="auto"):
+        super().__init__()
+        if use_mdn:
+            raise NotImplementedError("FFConvLSTM(use_mdn=True): the MDN head is not built in this package")
+        self.in_dim, self.out_dim = in_dim, out_dim
+        self.in_ph_start_idx, self.in_ph_end_idx = in_ph_start_idx, in_ph_end_idx
+        self.num_vocab = in_ph_end_idx - in_ph_start_idx
+        self.embed_dim = embed_dim
+        self.use_mdn = use_mdn
+        self.precision = precision
+        self.ff_hidden_dim, self.conv_hidden_dim, self.lstm_hidden_dim = ff_hidden_dim, conv_hidden_dim, lstm_hidden_dim
+
+        if embed_dim is not None:
+            assert in_dim > self.num_vocab
+            self.emb = nn.Embedding(self.num_vocab, embed_dim)
+            self.fc_in = nn.Linear(in_dim - self.num_vocab, embed_dim)
+            ff_in_dim = embed_dim
+        else:
+            ff_in_dim = in_dim
+        self.ff = nn.Sequential(nn.Linear(ff_in_dim, ff_hidden_dim), nn.ReLU(), nn.Linear(ff_hidden_dim, ff_hidden_dim), nn.ReLU(),
+                                nn.Linear(ff_hidden_dim, ff_hidden_dim), nn.ReLU())
+        layers, c_in = [], ff_hidden_dim
+        for _ in range(3):
+            layers += [nn.ReflectionPad1d(3), nn.Conv1d(c_in, conv_hidden_dim, kernel_size=7, padding=0),
+                       nn.BatchNorm1d(conv_hidden_dim), nn.ReLU()]
+            c_in = conv_hidden_dim
+        self.conv = nn.Sequential(*layers)
+        # the reference builds the LSTM bidirectional whatever `bidirectional` says (model.py:861-868)
+        self.lstm = nn.LSTM(conv_hidden_dim, lstm_hidden_dim, num_lstm_layers, bidirectional=True, batch_first=True, dropout=dropout)
+        self.fc = nn.Linear((2 if bidirectional else 1) * lstm_hidden_dim, out_dim)
+        init_weights(self, init_type)
+        self._plan: Optional[_Plan] = None
+        self._plan_key = None
+
+    def prediction_type(self):
+        return PredictionType.DETERMINISTIC
+
+    # ------------------------------------------------------------------ precision / plan
+    def resolved_precision(self) -> str:
+        widths = [self.ff_hidden_dim, self.conv_hidden_dim, 8 * self.lstm_hidden_dim] + ([self.embed_dim] if self.embed_dim else [])
+        ok = all(w % 16 == 0 for w in widths)
+        if self.precision == "auto":
+            return "bf16" if ok else "fp32"
+        if self.precision == "bf16" and not ok:
+            raise RuntimeError(f"FFConvLSTM precision='bf16' needs every layer width to be a multiple of 16, got {widths}")
+        if self.precision not in ("bf16", "fp32"):
+            raise RuntimeError(f"unknown precision {self.precision!r}")
+        return self.precision
+
+    def plan(self) -> _Plan:
+        prec = self.resolved_precision()
+        key = (prec,) + tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+        if self._plan is None or self._plan_key != key:
+            self._plan, self._plan_key = _Plan(self, prec), key
+        return self._plan
+
+    # ------------------------------------------------------------------ forward
+    def _check(self, x, lengths):
+        if self.training:
+            raise RuntimeError("FFConvLSTM: only the eval-mode forward is built (BatchNorm running statistics, no dropout); call .eval()")
+        if not x.is_cuda:
+            raise RuntimeError("FFConvLSTM: input must be a CUDA tensor (libsvsk has no CPU path)")
+        if x.dim() != 3 or x.shape[-1] != self.in_dim:
+            raise RuntimeError(f"FFConvLSTM: expected input [B, T, {self.in_dim}], got {tuple(x.shape)}")
+        if x.shape[1] < 4:
+            raise RuntimeError("FFConvLSTM: ReflectionPad1d(3) needs at least 4 frames")
+        if not ops.lstm_supported(self.lstm_hidden_dim):
+            raise RuntimeError(f"FFConvLSTM: lstm_hidden_dim={self.lstm_hidden_dim} has no layout in svsk_lstm_f32")
+        B, T = x.shape[0], x.shape[1]
+        if lengths is None:
+            lens = [T] * B
+        else:
+            lens = [int(n) for n in (lengths.tolist() if isinstance(lengths, torch.Tensor) else lengths)]
+            if len(lens) != B or max(lens) > T or min(lens) < 1:
+                raise RuntimeError(f"FFConvLSTM: lengths {lens} do not fit a batch of {B} x {T} frames")
+        return lens
+
+    def forward(self, x, lengths=None, y=None, spk_embs=None):
+        lens = self._check(x, lengths)
+        plan = self.plan()
+        x = x.detach().float().contiguous()
+        lens_dev = torch.tensor(lens, dtype=torch.int32, device=x.device)
+        if spk_embs is not None:
+            spk_embs = spk_embs.detach().float().expand(x.shape[0], x.shape[1], spk_embs.shape[-1]).contiguous()
+        out = self._forward_fp32(x, lens_dev, spk_embs, plan) if plan.precision == "fp32" else self._forward_bf16(x, lens_dev, spk_embs, plan)
+        return out[:, :max(lens)].contiguous()
+
+    def inference(self, x, lengths=None, spk_embs=None):
+        return self(x, lengths, spk_embs=spk_embs)
+
+    def _forward_fp32(self, x, lens_dev, spk, plan):
+        B, T, _ = x.shape
+        H = self.lstm_hidden_dim
+        if self.embed_dim is not None:
+            xf = torch.empty((B * T, self.in_dim), device=x.device, dtype=torch.float32)
+            ops.encoder_front(x.view(B * T, self.in_dim), self.in_ph_start_idx, self.num_vocab, y_f32=xf)
+            h = ops.ntc_to_nct_f32(xf.view(B, T, self.in_dim), self.in_dim)
+            h = ops.conv1d_f32(h, plan.front[0][0], plan.front[0][1])
+        else:
+            h = ops.ntc_to_nct_f32(x, self.in_dim)
+        if spk is not None:
+            h = ops.lincomb_f32([h, ops.ntc_to_nct_f32(spk, spk.shape[-1])], [1.0, 1.0])
+        for w, b in plan.ff:
+            h = ops.conv1d_f32(h, w, b, act=ops.ACT_RELU)
+        for w, b in plan.conv:
+            h = ops.conv1d_f32(h, w, b, pad_mode=ops.PAD_REFLECT, act=ops.ACT_RELU)
+        for w_ih, b, w_hh in plan.lstm:
+            pre = ops.conv1d_f32(h, w_ih, b)                                   # [B, 8H, T]
+            h = torch.empty((B, 2 * H, T), device=x.device, dtype=torch.float32)
+            ops.lstm_f32(pre, w_hh, lens_dev, H, pre_layout="nct", h_f32=h)
+        y = ops.conv1d_f32(h, plan.fc[0], plan.fc[1])                          # [B, out, T]
+        return ops.nct_to_ntc(y, want_bf16=False, want_f32=True)[1]
+
+    def _forward_bf16(self, x, lens_dev, spk, plan):
+        B, T, _ = x.shape
+        dev, H, bf = x.device, self.lstm_hidden_dim, torch.bfloat16
+        ld0 = -(-self.in_dim // 8) * 8
+        if spk is not None and self.embed_dim is None:
+            x = ops.lincomb_f32([x, spk], [1.0, 1.0])
+        h = torch.empty((B, T, ld0), device=dev, dtype=bf)
+        ops.encoder_front(x.view(B * T, self.in_dim), self.in_ph_start_idx, self.num_vocab if self.embed_dim is not None else 0,
+                          y_bf16=h.view(B * T, ld0))
+        c_in = self.in_dim
+        if self.embed_dim is not None:
+            E = self.embed_dim
+            if spk is None:
+                e = torch.empty((B, T, E), device=dev, dtype=bf)
+                ops.tapgemm_bf16(h, plan.front[0][0], plan.front[0][1], c_in, T=T, y_bf16=e)
+            else:
+                e32 = torch.empty((B, T, E), device=dev, dtype=torch.float32)
+                ops.tapgemm_bf16(h, plan.front[0][0], plan.front[0][1], c_in, T=T, y_f32=e32)
+                e = ops.cast_scale_bf16(ops.lincomb_f32([e32, spk], [1.0, 1.0]))
+            h, c_in = e, E
+        # ff: the last layer writes into the time-padded input buffer of the first convolution
+        F_, Cc = self.ff_hidden_dim, self.conv_hidden_dim
+        for i, (w, b) in enumerate(plan.ff):
+            last = i == len(plan.ff) - 1
+            y = torch.empty((B, T + 6 if last else T, F_), device=dev, dtype=bf)
+            ops.tapgemm_bf16(h, w, b, c_in, T=T, act=ops.ACT_RELU, y_bf16=y, y_row0=3 if last else 0)
+            h, c_in = y, F_
+        for i, (w, b) in enumerate(plan.conv):
+            ops.reflect_pad_rows_bf16(h, T, 3)
+            last = i == len(plan.conv) - 1
+            y = torch.empty((B, T if last else T + 6, Cc), device=dev, dtype=bf)
+            ops.tapgemm_bf16(h, w, b, c_in, T=T, act=ops.ACT_RELU, y_bf16=y, y_row0=0 if last else 3)
+            h, c_in = y, Cc
+        for w_ih, b, w_hh in plan.lstm:
+            pre = torch.empty((B, T, 8 * H), device=dev, dtype=torch.float32)
+            ops.tapgemm_bf16(h, w_ih, b, c_in, T=T, y_f32=pre)
+            h = torch.empty((B, T, 2 * H), device=dev, dtype=bf)
+            ops.lstm_f32(pre, w_hh, lens_dev, H, pre_layout="ntc", h_bf16=h)
+            c_in = 2 * H
+        y = torch.empty((B, T, plan.out_p), device=dev, dtype=torch.float32)
+        ops.tapgemm_bf16(h, plan.fc[0], plan.fc[1], c_in, T=T, y_f32=y)
+        return y[:, :, :self.out_dim]
+
+
+class MultiSpeakerFFConvLSTM(FFConvLSTM):
+    """nnsvs/model.py:929-1015: the speaker embedding of ``spks`` is broadcast over time and added in front of ``ff``."""
+
+    def __init__(self, in_dim, speaker_embedding, ff_hidden_dim=2048, conv_hidden_dim=1024, lstm_hidden_dim=256, out_dim=67,
+                 dropout=0.0, num_lstm_layers=2, bidirectional=True, init_type="none", use_mdn=False, dim_wise=True,
+                 num_gaussians=4, in_ph_start_idx: int = 1, in_ph_end_idx: int = 50, embed_dim=None, precision="auto"):
+        super().__init__(in_dim, ff_hidden_dim, conv_hidden_dim, lstm_hidden_dim, out_dim, dropout, num_lstm_layers, bidirectional,
+                         init_type, use_mdn, dim_wise, num_gaussians, in_ph_start_idx, in_ph_end_idx, embed_dim, precision)
+        self.speaker_embedding = speaker_embedding
+
+    def forward(self, x, spks, lengths=None, y=None):
+        spk_embs = self.speaker_embedding(spks)
+        return super().forward(x, lengths, spk_embs=spk_embs.expand(spk_embs.shape[0], x.shape[1], spk_embs.shape[-1]))
+
+    def inference(self, x, spks, lengths=None):
+        return self(x, spks, lengths)

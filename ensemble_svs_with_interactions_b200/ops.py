@@ -395,3 +395,82 @@ def usfgan_block_bf16(xb_in, xb_out, aux, w1p, woutp, bias1, bout, *, dilation=1
     p.dilation, p.adaptive, p.out_scale = int(dilation), int(idx is not None), float(out_scale)
     p.out_relu = int(out_relu)
     L.check(L.lib().svsk_usfgan_block_bf16(C.byref(p), L.stream_ptr()), "usfgan_block_bf16")
+
+
+# ---- FFConvLSTM encoder pieces (include/svsk.h, "FFConvLSTM encoder pieces") ---------------------------------------
+def lstm_supported(H):
+    return bool(L.lib().svsk_lstm_supported(int(H)))
+
+
+def lstm_f32(pre, w_hh, lengths, H, *, pre_layout, h_f32=None, h_bf16=None):
+    """svsk_lstm_f32.  pre: gate pre-activations of both directions, ``pre_layout`` "ntc" = [B, T, ndir*4H] or "nct" =
+    [B, ndir*4H, T] (fp32); w_hh [ndir, 4H, H]; lengths int32 [B] or None.  h_f32: [B, 2H, T] (NCT) output or None;
+    h_bf16: [B, T, >= 2H] bf16 output or None."""
+    ndir = w_hh.shape[0]
+    if pre_layout == "ntc":
+        B, T, R = pre.shape
+        sb, st_, sr = T * R, R, 1
+    elif pre_layout == "nct":
+        B, R, T = pre.shape
+        sb, st_, sr = T * R, 1, T
+    else:
+        raise ValueError("pre_layout must be 'ntc' or 'nct'")
+    if R != ndir * 4 * H or tuple(w_hh.shape) != (ndir, 4 * H, H):
+        raise RuntimeError(f"lstm_f32: pre has {R} gate rows, w_hh is {tuple(w_hh.shape)}; expected {ndir * 4 * H} and ({ndir}, {4 * H}, {H})")
+    p = L.LstmParams()
+    p.pre, p.w_hh, p.lengths = L.ptr(pre, f32, "pre"), L.ptr(w_hh, f32, "w_hh"), L.ptr(lengths, torch.int32, "lengths")
+    p.pre_stride_b, p.pre_stride_t, p.pre_stride_r = sb, st_, sr
+    if h_f32 is not None:
+        if tuple(h_f32.shape) != (B, ndir * H, T):
+            raise RuntimeError("lstm_f32: h_f32 must be [B, ndir*H, T]")
+        p.h_f32 = L.ptr(h_f32, f32, "h_f32")
+        p.hf_stride_b, p.hf_stride_t, p.hf_stride_c = ndir * H * T, 1, T
+    if h_bf16 is not None:
+        if h_bf16.shape[0] != B or h_bf16.shape[1] != T or h_bf16.shape[2] < ndir * H:
+            raise RuntimeError("lstm_f32: h_bf16 must be [B, T, >= ndir*H]")
+        p.h_bf16 = L.ptr(h_bf16, bf16, "h_bf16")
+        p.hb_stride_b, p.hb_stride_t = T * h_bf16.shape[2], h_bf16.shape[2]
+    p.B, p.T, p.H, p.ndir = B, T, H, ndir
+    L.check(L.lib().svsk_lstm_f32(C.byref(p), L.stream_ptr()), "lstm_f32")
+
+
+def tapgemm_pack_bf16(w, scale=None):
+    """w [Cout, Cin, k] (or [Cout, Cin]) fp32 -> packed [k, Cout, ceil64(Cin)] bf16 with ``scale`` [Cout] folded in."""
+    if w.dim() == 2:
+        w = w.unsqueeze(-1)
+    w = w.contiguous()
+    Cout, Cin, k = w.shape
+    wp = torch.empty((k, Cout, (Cin + 63) // 64 * 64), device=w.device, dtype=bf16)
+    L.check(L.lib().svsk_tapgemm_pack_bf16(L.ptr(w, f32, "w"), L.ptr(scale, f32, "scale"), L.ptr(wp), Cout, Cin, k,
+                                           L.stream_ptr()), "tapgemm_pack_bf16")
+    return wp
+
+
+def tapgemm_bf16(x, wp, bias, Cin, *, T, act=ACT_NONE, y_bf16=None, y_row0=0, y_f32=None):
+    """svsk_tapgemm_bf16.  x [B, Tp_x, ldx] bf16 (time-padded by the caller), wp from tapgemm_pack_bf16;
+    y_bf16 [B, Tp_y, ldy_b] receives frame t at row y_row0 + t; y_f32 [B, T, ldy_f]."""
+    B, Tp_x, ldx = x.shape
+    k, Cout, _ = wp.shape
+    p = L.TapGemmBf16Params()
+    p.x, p.wp, p.bias = L.ptr(x, bf16, "x"), L.ptr(wp, bf16, "wp"), L.ptr(bias, f32, "bias")
+    p.B, p.T, p.Cin, p.Cout, p.ksize, p.Tp_x, p.ldx, p.act = B, T, Cin, Cout, k, Tp_x, ldx, act
+    if y_bf16 is not None:
+        p.y_bf16, p.Tp_y, p.y_row0, p.ldy_b = L.ptr(y_bf16, bf16, "y_bf16"), y_bf16.shape[1], y_row0, y_bf16.shape[2]
+    if y_f32 is not None:
+        if y_f32.shape[0] != B or y_f32.shape[1] != T:
+            raise RuntimeError("tapgemm_bf16: y_f32 must be [B, T, ldy_f]")
+        p.y_f32, p.ldy_f = L.ptr(y_f32, f32, "y_f32"), y_f32.shape[2]
+    L.check(L.lib().svsk_tapgemm_bf16(C.byref(p), L.stream_ptr()), "tapgemm_bf16")
+
+
+def reflect_pad_rows_bf16(buf, T, pad):
+    B, Tp, Cc = buf.shape
+    L.check(L.lib().svsk_reflect_pad_rows_bf16(L.ptr(buf, bf16, "buf"), B, Tp, Cc, T, pad, L.stream_ptr()), "reflect_pad_rows_bf16")
+
+
+def encoder_front(x, onehot_start, onehot_len, *, y_f32=None, y_bf16=None):
+    """x [rows, in_dim] fp32 -> copies with the one-hot block replaced by one-hot(argmax) (svsk_encoder_front)."""
+    rows, in_dim = x.shape
+    L.check(L.lib().svsk_encoder_front(L.ptr(x, f32, "x"), L.ptr(y_f32, f32, "y_f32"), L.ptr(y_bf16, bf16, "y_bf16"), rows, in_dim,
+                                       onehot_start, onehot_len, 0 if y_f32 is None else y_f32.shape[1],
+                                       0 if y_bf16 is None else y_bf16.shape[1], L.stream_ptr()), "encoder_front")

@@ -352,6 +352,56 @@ typedef struct svsk_linear_bf16_params {
 } svsk_linear_bf16_params;
 SVSK_API int svsk_linear_bf16(const svsk_linear_bf16_params* p, void* stream);
 
+/* ---- FFConvLSTM encoder pieces (nnsvs/model.py:779-926) ---------------------------------- */
+
+/* Recurrent half of one bidirectional nn.LSTM layer over a padded batch of packed sequences (model.py:861-868,917-919):
+ *   a_t = pre_t + W_hh h_{t-1} ; c_t = sigmoid(f) c_{t-1} + sigmoid(i) tanh(g) ; h_t = sigmoid(o) tanh(c_t)
+ * with gate rows in torch order i, f, g, o, h_0 = c_0 = 0; direction 1 runs from frame lengths[b]-1 down to 0; frames
+ * >= lengths[b] are written as zeros (pack_padded_sequence / pad_packed_sequence).  One thread-block cluster per
+ * (track, direction); W_hh lives in registers.  pre = W_ih x + b_ih + b_hh (a GEMM done by the caller), addressed as
+ * pre[b*pre_stride_b + t*pre_stride_t + (dir*4H + row)*pre_stride_r]; outputs h_f32[b*hf_stride_b + t*hf_stride_t +
+ * (dir*H + u)*hf_stride_c] and / or h_bf16[b*hb_stride_b + t*hb_stride_t + dir*H + u] (either may be NULL). */
+typedef struct svsk_lstm_params {
+  const float* pre;
+  const float* w_hh;        /* [ndir][4H][H] */
+  const int32_t* lengths;   /* [B] or NULL (= T) */
+  float* h_f32;
+  void* h_bf16;
+  int64_t pre_stride_b, pre_stride_t, pre_stride_r;
+  int64_t hf_stride_b, hf_stride_t, hf_stride_c;
+  int64_t hb_stride_b, hb_stride_t;
+  int32_t B, T, H, ndir;
+} svsk_lstm_params;
+SVSK_API int svsk_lstm_f32(const svsk_lstm_params* p, void* stream);
+/* 1 when svsk_lstm_f32 has a cluster layout for hidden size H (H <= 256, H % 4 == 0, H / 2^k <= 32 for a k <= 3). */
+SVSK_API int svsk_lstm_supported(int H);
+
+/* Frame-major bf16 GEMM over row-shifted taps — the ff Linears (ksize 1), the three ReflectionPad1d(3) + Conv1d(k=7) +
+ * BatchNorm1d(eval) + ReLU layers (model.py:846-859), the LSTM input projections and the output Linear of the encoder:
+ *   Y[b][t][co] = act( bias[co] + sum_{j<ksize} sum_ci W[co][ci][j] * X[b][t + j][ci] ),  t < T
+ * x: [B][Tp_x][ldx] bf16, already padded in time by the caller (Tp_x >= T + ksize - 1; see svsk_reflect_pad_rows_bf16);
+ * wp: packed by svsk_tapgemm_pack_bf16; y_bf16 row (b, t) lives at ((b*Tp_y + y_row0 + t)*ldy_b), so a layer can write
+ * straight into the padded input buffer of the next one; y_f32 is [B][T][ldy_f].  Cout % 16 == 0; act NONE or RELU. */
+typedef struct svsk_tapgemm_bf16_params {
+  const void* x; const void* wp; const float* bias;
+  void* y_bf16; float* y_f32;
+  int32_t B, T, Cin, Cout, ksize;
+  int32_t Tp_x, ldx;
+  int32_t Tp_y, y_row0, ldy_b, ldy_f;
+  int32_t act;
+} svsk_tapgemm_bf16_params;
+SVSK_API int svsk_tapgemm_bf16(const svsk_tapgemm_bf16_params* p, void* stream);
+/* wp[j][co][k] = bf16(w[co][k][j] * scale[co]) for k < Cin, 0 up to ceil64(Cin); scale (folded BatchNorm) may be NULL. */
+SVSK_API int svsk_tapgemm_pack_bf16(const float* w /* [Cout][Cin][ksize] */, const float* scale, void* wp, int Cout, int Cin,
+                                    int ksize, void* stream);
+/* nn.ReflectionPad1d(pad) in place on buf [B][Tp][C] bf16 whose rows pad..pad+T-1 hold the data (model.py:847,851,855). */
+SVSK_API int svsk_reflect_pad_rows_bf16(void* buf, int B, int Tp, int C, int T, int pad, void* stream);
+/* Input side of the embedding front (model.py:897-910): copies x [rows][in_dim] to y_f32 [rows][ldy_f] and / or y_bf16
+ * [rows][ldy_b] (zero-filled pitch) with the one-hot block [onehot_start, +onehot_len) replaced by the exact one-hot of
+ * its argmax, so that emb(argmax) + fc_in(rest) becomes one GEMM with the weights [fc_in | emb^T].  onehot_len 0 = copy. */
+SVSK_API int svsk_encoder_front(const float* x, float* y_f32, void* y_bf16, long long rows, int in_dim, int onehot_start,
+                                int onehot_len, int ldy_f, int ldy_b, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -263,6 +263,42 @@ def golden_frontend(ns):
           {}, dict(f0=f0, noise_sine=n_sine, noise_in=n_in), dict(in_signal=sig, df=df.astype(np.float64)))
 
 
+def golden_encoder(ns):
+    """FFConvLSTM in eval mode (model.py:779-926): the recipe's embedding front with ragged lengths and all-zero phoneme
+    blocks, and the shape of the reference's own test (tests/test_model.py:190-205)."""
+    for name, cfg, B, T, lengths in (
+        ("ffconvlstm_embed", dict(in_dim=60, in_ph_start_idx=3, in_ph_end_idx=20, embed_dim=24, ff_hidden_dim=32,
+                                  conv_hidden_dim=24, lstm_hidden_dim=40, num_lstm_layers=2, out_dim=16), 3, 50, [50, 41, 17]),
+        ("ffconvlstm_test_shape", dict(in_dim=300, ff_hidden_dim=8, conv_hidden_dim=8, lstm_hidden_dim=8, dropout=0.1,
+                                       num_lstm_layers=2, bidirectional=True, out_dim=180, init_type="none"), 2, 33, [33, 29]),
+    ):
+        torch.manual_seed(61)
+        g = torch.Generator().manual_seed(62)
+        m = ns.FFConvLSTM(**cfg).eval()
+        for k, v in m.state_dict().items():
+            if k.endswith("running_mean"):
+                v.copy_(torch.randn(v.shape, generator=g) * 0.2)
+            elif k.endswith("running_var"):
+                v.copy_(torch.rand(v.shape, generator=g) + 0.5)
+            elif ".bias" in k and v.dim() == 1 and "lstm" not in k:
+                v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+        for k in (2, 6, 10):  # BatchNorm scale away from 1
+            m.conv[k].weight.data.copy_(torch.rand(m.conv[k].weight.shape, generator=g) + 0.5)
+        x = torch.randn(B, T, cfg["in_dim"], generator=g)
+        if cfg.get("embed_dim") is not None:
+            s, V = cfg["in_ph_start_idx"], cfg["in_ph_end_idx"] - cfg["in_ph_start_idx"]
+            ph = torch.randint(0, V, (B, T), generator=g)
+            onehot = torch.nn.functional.one_hot(ph, V).float()
+            onehot[:, ::7] = 0.0  # frames without a phoneme: argmax of zeros -> phoneme 0 (model.py:908)
+            x[..., s:s + V] = onehot
+        with torch.no_grad():
+            y = m(x.clone(), lengths)
+            ff = m.ff(x if cfg.get("embed_dim") is None else
+                      m.emb(torch.argmax(x[..., s:s + V], -1)) + m.fc_in(torch.cat([x[..., :s], x[..., s + V:]], -1)))
+            conv = m.conv(ff.transpose(1, 2)).transpose(1, 2)
+        _save(name, cfg, m.state_dict(), dict(x=x, lengths=torch.tensor(lengths)), dict(y=y, ff=ff, conv=conv))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = load_reference()
@@ -273,6 +309,7 @@ def main():
     golden_wavenet(ns)
     golden_usfgan(ns)
     golden_frontend(ns)
+    golden_encoder(ns)
 
 
 if __name__ == "__main__":

@@ -48,6 +48,13 @@ def load_reference():
         sys.modules["nnsvs"] = pkg
     _stub("h5py")
     _stub("tkinter", W="w")
+    # nnsvs/model.py:9,12 import split_streams (needs nnmnkwii) and init_weights (nnsvs.util needs pyworld / hydra);
+    # neither is on the FFConvLSTM path when init_type == "none" (util.py:40-41 returns at once).
+    _stub("nnsvs.multistream", split_streams=None)
+
+    def _init_weights(net, init_type="none", init_gain=0.02):
+        assert init_type == "none", "the shim only covers init_type='none'"
+    _stub("nnsvs.util", init_weights=_init_weights)
 
     ns = types.SimpleNamespace()
     from nnsvs.diffsinger.denoiser import DiffNet
@@ -59,6 +66,7 @@ def load_reference():
     import nnsvs.usfgan.utils.index as index
     import nnsvs.usfgan.utils.features as features
     from nnsvs.usfgan import USFGANWrapper
+    from nnsvs.model import FFConvLSTM
 
     # pd_indexing/index_initial call .cuda() whenever CUDA is visible
     # (nnsvs/usfgan/utils/index.py:32-33,44-45,81-83); the CPU oracle use of the
@@ -80,4 +88,5 @@ def load_reference():
     ns.SignalGenerator = features.SignalGenerator
     ns.dilated_factor = features.dilated_factor
     ns.USFGANWrapper = USFGANWrapper
+    ns.FFConvLSTM = FFConvLSTM
     return ns

@@ -529,3 +529,81 @@ def usfgan_wrapper_inputs(f0: np.ndarray, aux: Tensor, *, sample_rate: int, hop_
     f0_t = torch.FloatTensor(f0).unsqueeze(0).transpose(2, 1)
     sine = sine_source(f0_t, sample_rate, hop_size, sine_amp, noise_amp, noise_sine)
     return torch.cat([sine, noise_in], dim=1), c, d
+
+
+# --------------------------------------------------------------------------- #
+# FFConvLSTM encoder  (nnsvs/model.py:779-926) — SURVEY.md §8(f) row 1
+# --------------------------------------------------------------------------- #
+def lstm_direction(pre: Tensor, w_hh: Tensor, length: int, reverse: bool) -> Tensor:
+    """One direction of one ``nn.LSTM`` layer over ONE packed sequence (model.py:917-919).
+
+    pre [T, 4H] = W_ih x_t + b_ih + b_hh; gate rows in torch order i, f, g, o.  The recurrence runs over the first
+    ``length`` frames only (``pack_padded_sequence``), from the last of them when ``reverse``; frames beyond stay 0
+    (``pad_packed_sequence``).  h_0 = c_0 = 0.
+    """
+    T, H = pre.shape[0], w_hh.shape[1]
+    out = pre.new_zeros((T, H))
+    h = pre.new_zeros(H)
+    c = pre.new_zeros(H)
+    order = range(length - 1, -1, -1) if reverse else range(length)
+    for t in order:
+        a = pre[t] + w_hh @ h
+        i, f, g, o = a[:H], a[H:2 * H], a[2 * H:3 * H], a[3 * H:]
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        out[t] = h
+    return out
+
+
+def bilstm_stack(sd: SD, prefix: str, x: Tensor, lengths: Sequence[int], num_layers: int) -> Tensor:
+    """``nn.LSTM(bidirectional=True, batch_first=True)`` in eval mode on a padded batch x [B, T, C] -> [B, T, 2H]."""
+    for layer in range(num_layers):
+        outs = []
+        for suffix, reverse in (("", False), ("_reverse", True)):
+            w_ih = sd[f"{prefix}weight_ih_l{layer}{suffix}"]
+            w_hh = sd[f"{prefix}weight_hh_l{layer}{suffix}"]
+            b = sd[f"{prefix}bias_ih_l{layer}{suffix}"] + sd[f"{prefix}bias_hh_l{layer}{suffix}"]
+            pre = x @ w_ih.t() + b
+            outs.append(torch.stack([lstm_direction(pre[i], w_hh, int(lengths[i]), reverse) for i in range(x.shape[0])]))
+        x = torch.cat(outs, dim=-1)
+    return x
+
+
+def ffconvlstm_front(sd: SD, x: Tensor, *, in_ph_start_idx: int, in_ph_end_idx: int, embed_dim: Optional[int],
+                     spk_embs: Optional[Tensor] = None) -> Tensor:
+    """model.py:897-913: phoneme embedding of the one-hot block (argmax, so an all-zero block means phoneme 0) plus a
+    Linear over the remaining columns; then the optional speaker embedding is added."""
+    if embed_dim is not None:
+        s, V = in_ph_start_idx, in_ph_end_idx - in_ph_start_idx
+        ph = torch.argmax(x[..., s:s + V], dim=-1)
+        rest = torch.cat([x[..., :s], x[..., s + V:]], dim=-1)
+        x = sd["emb.weight"][ph] + rest @ sd["fc_in.weight"].t() + sd["fc_in.bias"]
+    if spk_embs is not None:
+        x = x + spk_embs
+    return x
+
+
+def ffconvlstm_forward(sd: SD, x: Tensor, lengths: Sequence[int], *, in_ph_start_idx: int = 1, in_ph_end_idx: int = 50,
+                       embed_dim: Optional[int] = None, num_lstm_layers: int = 2, spk_embs: Optional[Tensor] = None,
+                       bn_eps: float = 1e-5, want_parts: bool = False):
+    """FFConvLSTM.forward in eval mode, use_mdn=False (model.py:893-922).  x [B, T, in_dim] -> [B, max(lengths), out_dim].
+
+    ff: 3 x (Linear, ReLU); conv: 3 x (ReflectionPad1d(3), Conv1d k=7, BatchNorm1d with running statistics, ReLU) over
+    the whole padded batch; 2-layer BiLSTM over the packed sequences; Linear.
+    """
+    x = ffconvlstm_front(sd, x, in_ph_start_idx=in_ph_start_idx, in_ph_end_idx=in_ph_end_idx, embed_dim=embed_dim,
+                         spk_embs=spk_embs)
+    for i in (0, 2, 4):
+        x = torch.relu(x @ sd[f"ff.{i}.weight"].t() + sd[f"ff.{i}.bias"])
+    ff = x
+    y = x.transpose(1, 2)
+    for i in (1, 5, 9):
+        y = F.conv1d(F.pad(y, (3, 3), mode="reflect"), sd[f"conv.{i}.weight"], sd[f"conv.{i}.bias"])
+        n = i + 1
+        y = (y - sd[f"conv.{n}.running_mean"][None, :, None]) / torch.sqrt(sd[f"conv.{n}.running_var"][None, :, None] + bn_eps)
+        y = torch.relu(y * sd[f"conv.{n}.weight"][None, :, None] + sd[f"conv.{n}.bias"][None, :, None])
+    conv = y.transpose(1, 2)
+    h = bilstm_stack(sd, "lstm.", conv, lengths, num_lstm_layers)
+    h = h[:, :max(int(n) for n in lengths)]
+    out = h @ sd["fc.weight"].t() + sd["fc.bias"]
+    return (out, dict(ff=ff, conv=conv, lstm=h)) if want_parts else out

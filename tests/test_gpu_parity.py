@@ -921,3 +921,133 @@ def test_pipeline_batched_synthesis():
     for i, n in enumerate(lens):
         w = [o[i] for o in outs if o[i] is not None]
         assert len(w) == 1 and w[0].shape == (n * 120,) and torch.isfinite(w[0]).all()
+
+
+# ------------------------------------------------------------------------------------------------ FFConvLSTM encoder
+@pytest.mark.parametrize("H", [8, 40, 64, 96, 128, 160, 256])
+@pytest.mark.parametrize("layout", ["ntc", "nct"])
+def test_lstm_recurrence_matches_oracle(H, layout):
+    """svsk_lstm_f32 against oracle.lstm_direction (model.py:917-919): ragged lengths, both directions; fp32 tolerance."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(H)
+    B, T = 3, 61
+    lengths = [61, 37, 1]
+    pre = torch.randn(B, T, 8 * H, generator=g)
+    w_hh = torch.randn(2, 4 * H, H, generator=g) * (1.0 / math.sqrt(H))
+    ref = torch.stack([torch.cat([O.lstm_direction(pre[b, :, d * 4 * H:(d + 1) * 4 * H], w_hh[d], lengths[b], d == 1)
+                                  for d in range(2)], -1) for b in range(B)])            # [B, T, 2H]
+    lens = torch.tensor(lengths, dtype=torch.int32, device=DEV)
+    h32 = torch.full((B, 2 * H, T), float("nan"), device=DEV)
+    hb = torch.full((B, T, 2 * H), float("nan"), device=DEV, dtype=torch.bfloat16)
+    p = pre.to(DEV) if layout == "ntc" else pre.transpose(1, 2).contiguous().to(DEV)
+    ops.lstm_f32(p, w_hh.to(DEV), lens, H, pre_layout=layout, h_f32=h32, h_bf16=hb)
+    close32(h32.transpose(1, 2), ref)
+    assert (hb.float().cpu() - ref).abs().max().item() <= 4e-3       # one bf16 rounding of |h| <= 1
+    assert torch.count_nonzero(h32[1, :, 37:]) == 0 and torch.count_nonzero(hb[2, 1:]) == 0
+
+
+def test_lstm_rejects_unsupported_hidden_size():
+    ops = _ops()
+    assert not ops.lstm_supported(200) and not ops.lstm_supported(512) and ops.lstm_supported(256)
+    with pytest.raises(RuntimeError, match="hidden size"):
+        ops.lstm_f32(torch.zeros(1, 4, 8 * 200, device=DEV), torch.zeros(2, 800, 200, device=DEV), None, 200, pre_layout="ntc",
+                     h_f32=torch.zeros(1, 400, 4, device=DEV))
+
+
+@pytest.mark.parametrize("k,Cin,Cout,T", [(1, 87, 256, 300), (1, 512, 512, 129), (7, 512, 256, 300), (7, 96, 48, 77), (1, 256, 1024, 40)])
+def test_tapgemm_matches_fp32_conv(k, Cin, Cout, T):
+    """svsk_tapgemm_bf16 against F.conv1d on the bf16-rounded operands (fp32 accumulate on both sides)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(k * 1000 + Cin + Cout)
+    B, pad = 2, (k - 1) // 2
+    ld = -(-Cin // 8) * 8
+    x = torch.randn(B, T, Cin, generator=g)
+    w = torch.randn(Cout, Cin, k, generator=g) / math.sqrt(Cin * k)
+    scale = torch.rand(Cout, generator=g) + 0.5
+    bias = torch.randn(Cout, generator=g) * 0.1
+    xb = torch.zeros(B, T + 2 * pad, ld, dtype=torch.bfloat16)
+    xb[:, pad:pad + T, :Cin] = x.to(torch.bfloat16)
+    xb = xb.to(DEV)
+    if pad:
+        ops.reflect_pad_rows_bf16(xb, T, pad)
+    wp = ops.tapgemm_pack_bf16(w.to(DEV), scale.to(DEV))
+    y32 = torch.full((B, T, Cout), float("nan"), device=DEV)
+    yb = torch.zeros(B, T + 6, Cout, device=DEV, dtype=torch.bfloat16)
+    ops.tapgemm_bf16(xb, wp, bias.to(DEV), Cin, T=T, act=ops.ACT_RELU, y_f32=y32, y_bf16=yb, y_row0=3)
+    xr = x.to(torch.bfloat16).float().transpose(1, 2)
+    if pad:
+        xr = torch.nn.functional.pad(xr, (pad, pad), mode="reflect")
+    wr = (w * scale[:, None, None]).to(torch.bfloat16).float()
+    ref = torch.relu(torch.nn.functional.conv1d(xr, wr, bias)).transpose(1, 2)
+    close32(y32, ref, tol=1e-3)
+    assert (yb[:, 3:3 + T].float().cpu() - ref).abs().max().item() <= 1e-2 * max(1.0, ref.abs().max().item())
+    assert torch.count_nonzero(yb[:, :3]) == 0 and torch.count_nonzero(yb[:, 3 + T:]) == 0     # rows outside [y_row0, +T) untouched
+
+
+def _ffconvlstm_from_golden(name, precision="auto"):
+    from ensemble_svs_with_interactions_b200.model import FFConvLSTM
+    g = Golden(name)
+    m = FFConvLSTM(**g.cfg, precision=precision)
+    m.load_state_dict(g.sd, strict=True)
+    return g, m.to(DEV).eval()
+
+
+@pytest.mark.parametrize("name", ["ffconvlstm_embed", "ffconvlstm_test_shape"])
+def test_ffconvlstm_matches_reference_golden(name):
+    """The fp32 path against the unmodified reference's output (tests/golden/ffconvlstm_*.npz): 2e-4 * max(1, |ref|)."""
+    g, m = _ffconvlstm_from_golden(name)
+    assert m.resolved_precision() == "fp32"
+    y = m(g.inp["x"].to(DEV), g.inp["lengths"].tolist())
+    close32(y, g.out["y"])
+    y2 = m.inference(g.inp["x"].to(DEV), g.inp["lengths"])           # tensor lengths, the inference entry point
+    assert torch.equal(y, y2)
+
+
+def _recipe_encoder(precision, gen, H=128, spk=False):
+    from ensemble_svs_with_interactions_b200.model import FFConvLSTM
+    torch.manual_seed(5)
+    m = FFConvLSTM(87, ff_hidden_dim=512, conv_hidden_dim=256, lstm_hidden_dim=H, out_dim=256 if not spk else 60, in_ph_start_idx=3,
+                   in_ph_end_idx=50, embed_dim=256, precision=precision)
+    for k, v in m.state_dict().items():
+        if k.endswith("running_mean"):
+            v.copy_(torch.randn(v.shape, generator=gen) * 0.2)
+        elif k.endswith("running_var"):
+            v.copy_(torch.rand(v.shape, generator=gen) + 0.5)
+    return m.eval()
+
+
+@pytest.mark.parametrize("H,spk", [(128, False), (64, True), (256, False)])
+def test_ffconvlstm_recipe_shape_both_precisions(H, spk):
+    """Recipe encoder (multitrack_acoustic_..._diff_mgcbap.yaml:104-116) on ragged tracks: fp32 within 2e-4 of the oracle,
+    bf16 within rel-L2 2e-2; speaker embedding added in front of ff when given."""
+    g = torch.Generator().manual_seed(77 + H)
+    m = _recipe_encoder("fp32", g, H, spk)
+    B, T, lengths = 3, 200, [200, 131, 64]
+    x = torch.randn(B, T, 87, generator=g)
+    ph = torch.randint(0, 47, (B, T), generator=g)
+    onehot = torch.nn.functional.one_hot(ph, 47).float()
+    onehot[:, ::5] = 0.0
+    x[..., 3:50] = onehot
+    se = torch.randn(B, 1, 256, generator=g) * 0.3 if spk else None
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    ref = O.ffconvlstm_forward(sd, x, lengths, in_ph_start_idx=3, in_ph_end_idx=50, embed_dim=256, spk_embs=se)
+    m = m.to(DEV)
+    y32 = m(x.to(DEV), lengths, spk_embs=None if se is None else se.to(DEV))
+    close32(y32, ref)
+    m.precision = "bf16"
+    yb = m(x.to(DEV), lengths, spk_embs=None if se is None else se.to(DEV))
+    close_bf16(yb, ref)
+
+
+def test_gaussian_diffusion_with_encoder():
+    """GaussianDiffusion(encoder=FFConvLSTM) end to end (diffusion.py:283-284): the encoder output is the cond of the sampler."""
+    from ensemble_svs_with_interactions_b200.diffsinger import DiffNet, GaussianDiffusion
+    g = torch.Generator().manual_seed(3)
+    enc = _recipe_encoder("auto", g, 128)
+    torch.manual_seed(9)
+    m = GaussianDiffusion(87, 60, DiffNet(in_dim=60, encoder_hidden_dim=256, residual_layers=4, residual_channels=256),
+                          encoder=enc, K_step=4).to(DEV).eval()
+    x = torch.randn(2, 160, 87, generator=g)
+    x[..., 3:50] = torch.nn.functional.one_hot(torch.randint(0, 47, (2, 160), generator=g), 47).float()
+    y = m.inference(x.to(DEV), [160, 160])
+    assert y.shape == (2, 160, 60) and torch.isfinite(y).all()

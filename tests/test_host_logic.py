@@ -8,6 +8,7 @@ import torch
 
 from ensemble_svs_with_interactions_b200.base import BaseModel, PredictionType
 from ensemble_svs_with_interactions_b200.diffsinger import DiffNet, GaussianDiffusion, MultiSpeakerGaussianDiffusion
+from ensemble_svs_with_interactions_b200.model import FFConvLSTM, MultiSpeakerFFConvLSTM
 from ensemble_svs_with_interactions_b200.usfgan.models import (CascadeHnUSFGANGenerator, ParallelHnUSFGANGenerator,
                                                               USFGANGenerator)
 from ensemble_svs_with_interactions_b200.wavenet import WaveNet, receptive_field_size
@@ -145,3 +146,31 @@ def test_pipeline_plan_batches():
     import pytest
     with pytest.raises(ValueError):
         plan_batches(lengths, max_frames=0)
+
+
+@pytest.mark.parametrize("name", ["ffconvlstm_embed", "ffconvlstm_test_shape"])
+def test_ffconvlstm_state_dict_layout(name):
+    """same keys, order and shapes as nnsvs.model.FFConvLSTM (model.py:801-890)."""
+    g = Golden(name)
+    m = FFConvLSTM(**g.cfg)
+    _same_layout(m, g.sd)
+    assert m.prediction_type() == PredictionType.DETERMINISTIC and not m.is_autoregressive()
+    assert m.resolved_precision() == "fp32"          # widths 24 / 8 are not multiples of 16
+
+
+def test_ffconvlstm_ctor_and_loud_failures():
+    names = list(inspect.signature(FFConvLSTM.__init__).parameters)[1:16]
+    assert names == ["in_dim", "ff_hidden_dim", "conv_hidden_dim", "lstm_hidden_dim", "out_dim", "dropout", "num_lstm_layers",
+                     "bidirectional", "init_type", "use_mdn", "dim_wise", "num_gaussians", "in_ph_start_idx", "in_ph_end_idx",
+                     "embed_dim"]
+    assert list(inspect.signature(MultiSpeakerFFConvLSTM.__init__).parameters)[1:3] == ["in_dim", "speaker_embedding"]
+    with pytest.raises(NotImplementedError):
+        FFConvLSTM(20, use_mdn=True)
+    m = FFConvLSTM(87, ff_hidden_dim=64, conv_hidden_dim=32, lstm_hidden_dim=16, out_dim=32, in_ph_start_idx=3, in_ph_end_idx=50,
+                   embed_dim=32, init_type="kaiming_normal")
+    assert m.resolved_precision() == "bf16"
+    assert torch.count_nonzero(m.fc.bias) == 0        # init_weights zeroes Linear / Conv biases (util.py:60-61)
+    with pytest.raises(RuntimeError, match="eval"):
+        m(torch.zeros(1, 8, 87))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.eval()(torch.zeros(1, 8, 87))
