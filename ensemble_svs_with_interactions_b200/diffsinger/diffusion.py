@@ -295,11 +295,13 @@ class GaussianDiffusion(BaseModel):
         return s_x
 
     @torch.no_grad()
-    def inference(self, cond, lengths=None, spk_embs=None, *, x_T=None, z=None):
+    def inference(self, cond, lengths=None, spk_embs=None, *, x_T=None, z=None, cond_is_encoded=False):
+        """diffusion.py:296-336.  ``cond_is_encoded``: ``cond`` already is the encoder's output (pipeline.py runs the
+        encoders of several streams side by side), so the encoder is skipped."""
         self._require_cuda(cond)
         B = cond.shape[0]
         device = cond.device
-        if self.encoder is not None:
+        if self.encoder is not None and not cond_is_encoded:
             cond = self.encoder(cond, lengths, spk_embs=spk_embs)
         cond = cond.transpose(1, 2)  # (B, H, T)
         if self.pndm_speedup:

@@ -58,7 +58,9 @@ def _pad_time(x: torch.Tensor, frames: int, mode: str) -> torch.Tensor:
 class EnsembleSynthesizer:
     """mgc / bap diffusion + vocoder over batches of tracks.
 
-    mgc, bap: ``GaussianDiffusion`` drop-ins (already on the device, eval mode); vocoder: ``USFGANWrapper``.
+    mgc, bap: ``GaussianDiffusion`` drop-ins (already on the device, eval mode), with or without an ``encoder``
+    (``model.FFConvLSTM``: then ``cond_*`` are the linguistic features and every item's own length drives its packed
+    BiLSTM); vocoder: ``USFGANWrapper``.
     aux_fn(mgc [B,T,M1], bap [B,T,M2], f0 [B,T,1]) -> vocoder aux features [B,T,C]; default: concatenate mgc and bap.
     max_frames: frame budget of one batch (tracks x padded frames)."""
 
@@ -67,6 +69,24 @@ class EnsembleSynthesizer:
         self.mgc, self.bap, self.vocoder = mgc, bap, vocoder
         self.max_frames = int(max_frames)
         self.aux_fn = aux_fn if aux_fn is not None else (lambda m, b, f0: torch.cat([m, b], dim=-1))
+        self._side = None
+
+    def _encode(self, cm, cb, lens):
+        """The two streams' encoders are independent and latency-bound (a BiLSTM recurrence on a few dozen SMs each):
+        run the bap one on a side stream while the mgc one runs on the current stream."""
+        em, eb = getattr(self.mgc, "encoder", None), getattr(self.bap, "encoder", None)
+        if em is None or eb is None:
+            return (cm if em is None else em(cm, lens)), (cb if eb is None else eb(cb, lens))
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=cm.device)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            hb = eb(cb, lens)
+        hm = em(cm, lens)
+        cur.wait_stream(self._side)
+        hb.record_stream(cur)
+        return hm, hb
 
     @torch.no_grad()
     def synthesize(self, cond_mgc: Sequence[torch.Tensor], cond_bap: Sequence[torch.Tensor], f0: Sequence[torch.Tensor],
@@ -87,8 +107,10 @@ class EnsembleSynthesizer:
             cm = torch.stack([_pad_time(cond_mgc[i].to(dev, torch.float32), plan.frames, "replicate") for i in plan.items])
             cb = torch.stack([_pad_time(cond_bap[i].to(dev, torch.float32), plan.frames, "replicate") for i in plan.items])
             f = torch.stack([_pad_time(f0[i].to(dev, torch.float32), plan.frames, "zeros") for i in plan.items])
-            m = self.mgc.inference(cm)                      # [B, T, M1]
-            b = self.bap.inference(cb)                      # [B, T, M2]
+            lens = [lengths[i] for i in plan.items]         # used by the streams' encoders (packed BiLSTM), if any
+            hm, hb = self._encode(cm, cb, lens)
+            m = self.mgc.inference(hm, cond_is_encoded=True)   # [B, T, M1]
+            b = self.bap.inference(hb, cond_is_encoded=True)   # [B, T, M2]
             wav = self.vocoder.inference_batch(f, self.aux_fn(m, b, f).contiguous())   # [B, 1, T * hop]
             for k, i in enumerate(plan.items):
                 out[i] = wav[k, 0, :lengths[i] * hop].clone()

@@ -923,6 +923,49 @@ def test_pipeline_batched_synthesis():
         assert len(w) == 1 and w[0].shape == (n * 120,) and torch.isfinite(w[0]).all()
 
 
+def test_pipeline_with_encoders_matches_sequential_calls():
+    """EnsembleSynthesizer with FFConvLSTM encoders in both streams (run side by side on two CUDA streams) gives exactly
+    what mgc.inference / bap.inference give when called one after the other with the items' lengths."""
+    from types import SimpleNamespace as NS
+    from ensemble_svs_with_interactions_b200.diffsinger import DiffNet, GaussianDiffusion
+    from ensemble_svs_with_interactions_b200.model import FFConvLSTM
+    from ensemble_svs_with_interactions_b200.pipeline import EnsembleSynthesizer
+    torch.manual_seed(21)
+    kw = dict(in_ph_start_idx=3, in_ph_end_idx=50, embed_dim=64, ff_hidden_dim=64, conv_hidden_dim=32)
+    mgc = GaussianDiffusion(87, 60, DiffNet(60, 128, 4, 128, 4), encoder=FFConvLSTM(87, lstm_hidden_dim=64, out_dim=128, **kw),
+                            K_step=4).to(DEV).eval()
+    bap = GaussianDiffusion(87, 5, DiffNet(5, 64, 2, 128, 2), encoder=FFConvLSTM(87, lstm_hidden_dim=32, out_dim=64, **kw),
+                            K_step=4).to(DEV).eval()
+    for m in (mgc, bap):
+        with torch.no_grad():
+            m.denoise_fn.output_projection.weight.normal_(0, 0.05)
+    seen = {}
+
+    class Voc:   # stands in for the vocoder: records what the acoustic side hands over
+        config = NS(data=NS(hop_size=4))
+
+        def inference_batch(self, f0, aux):
+            seen["aux"] = aux.clone()
+            return aux.new_zeros((aux.shape[0], 1, aux.shape[1] * 4))
+    synth = EnsembleSynthesizer(mgc, bap, Voc(), max_frames=1000)
+    g = torch.Generator().manual_seed(6)
+    lens = [48, 48, 31]
+    ling = []
+    for n in lens:
+        x = torch.randn(n, 87, generator=g)
+        x[:, 3:50] = torch.nn.functional.one_hot(torch.randint(0, 47, (n,), generator=g), 47).float()
+        ling.append(x)
+    f0 = [torch.full((n, 1), 200.0) for n in lens]
+    torch.manual_seed(5)
+    out = synth.synthesize(ling, ling, f0)
+    assert [o.shape[0] for o in out] == [n * 4 for n in lens]
+    from ensemble_svs_with_interactions_b200.pipeline import _pad_time
+    batch = torch.stack([_pad_time(x, 48, "replicate") for x in ling]).to(DEV)
+    torch.manual_seed(5)
+    m = mgc.inference(batch, lens); b = bap.inference(batch, lens)
+    assert torch.equal(seen["aux"], torch.cat([m, b], dim=-1))
+
+
 # ------------------------------------------------------------------------------------------------ FFConvLSTM encoder
 @pytest.mark.parametrize("H", [8, 40, 64, 96, 128, 160, 256])
 @pytest.mark.parametrize("layout", ["ntc", "nct"])

@@ -22,6 +22,8 @@ import torch.distributed as dist  # noqa: E402
 
 from ensemble_svs_with_interactions_b200 import _lib, sharding  # noqa: E402
 from ensemble_svs_with_interactions_b200.diffsinger import DiffNet, GaussianDiffusion  # noqa: E402
+from ensemble_svs_with_interactions_b200.model import FFConvLSTM  # noqa: E402
+from ensemble_svs_with_interactions_b200.pipeline import EnsembleSynthesizer  # noqa: E402
 from ensemble_svs_with_interactions_b200.usfgan.models import ParallelHnUSFGANGenerator  # noqa: E402
 
 FS, HOP, TRACKS, SECONDS = 24000, 120, 6, 30.0
@@ -29,10 +31,20 @@ FRAMES = int(SECONDS * 200)          # 5 ms acoustic frames
 VFRAMES = int(SECONDS * FS / HOP)    # vocoder frames (hop 120 @ 24 kHz = 5 ms)
 
 
-def build(dev):
+LING = 87   # linguistic features + lf0 per frame (recipe yaml in_dim)
+
+
+def build(dev, encoders=False):
     torch.manual_seed(1234)
-    mgc = GaussianDiffusion(256, 60, DiffNet(60, 256, 20, 256, 4), K_step=100)
-    bap = GaussianDiffusion(128, 5, DiffNet(5, 128, 10, 128, 4), K_step=100)
+    if encoders:   # the recipe's FFConvLSTM encoders in front of both denoisers (yaml lines 104-116, 146-158)
+        kw = dict(in_ph_start_idx=3, in_ph_end_idx=50, embed_dim=256, num_lstm_layers=2)
+        enc_m = FFConvLSTM(LING, ff_hidden_dim=512, conv_hidden_dim=256, lstm_hidden_dim=128, out_dim=256, **kw)
+        enc_b = FFConvLSTM(LING, ff_hidden_dim=256, conv_hidden_dim=128, lstm_hidden_dim=64, out_dim=128, **kw)
+        mgc = GaussianDiffusion(LING, 60, DiffNet(60, 256, 20, 256, 4), encoder=enc_m, K_step=100)
+        bap = GaussianDiffusion(LING, 5, DiffNet(5, 128, 10, 128, 4), encoder=enc_b, K_step=100)
+    else:
+        mgc = GaussianDiffusion(256, 60, DiffNet(60, 256, 20, 256, 4), K_step=100)
+        bap = GaussianDiffusion(128, 5, DiffNet(5, 128, 10, 128, 4), K_step=100)
     for m in (mgc, bap):
         with torch.no_grad():
             m.denoise_fn.output_projection.weight.normal_(0, 0.02)
@@ -44,10 +56,15 @@ def build(dev):
     return mgc.to(dev).eval(), bap.to(dev).eval(), voc.to(dev).eval()
 
 
-def song_inputs(song, dev):
+def song_inputs(song, dev, encoders=False):
     g = torch.Generator().manual_seed(1234 + song)
-    cond_mgc = torch.randn(TRACKS, FRAMES, 256, generator=g)
-    cond_bap = torch.randn(TRACKS, FRAMES, 128, generator=g)
+    if encoders:
+        ling = torch.randn(TRACKS, FRAMES, LING, generator=g)
+        ling[..., 3:50] = torch.nn.functional.one_hot(torch.randint(0, 47, (TRACKS, FRAMES), generator=g), 47).float()
+        cond_mgc = cond_bap = ling
+    else:
+        cond_mgc = torch.randn(TRACKS, FRAMES, 256, generator=g)
+        cond_bap = torch.randn(TRACKS, FRAMES, 128, generator=g)
     f0 = torch.empty(TRACKS, 1, VFRAMES).uniform_(110, 880, generator=g)
     d = (FS / (f0 * 4)).repeat_interleave(HOP, dim=-1)
     sig = torch.randn(TRACKS, 2, VFRAMES * HOP, generator=g) * 0.1
@@ -58,6 +75,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--songs", type=int, default=64)
     ap.add_argument("--warmup-songs", type=int, default=1)
+    ap.add_argument("--encoders", action="store_true", help="run the recipe's FFConvLSTM encoders in front of both denoisers "
+                    "(input = 87 linguistic features per frame instead of pre-computed conditioning)")
     ap.add_argument("--breakdown", action="store_true", help="also print ms per phase of the last song")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -65,9 +84,10 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    mgc, bap, voc = build(dev)
+    mgc, bap, voc = build(dev, args.encoders)
+    enc = EnsembleSynthesizer(mgc, bap, None)
     mine = sharding.assign([FRAMES] * args.songs, world)[rank]
-    host = song_inputs(0, dev)   # same shapes for every song; contents re-seeded per song below (cheap host RNG is not timed)
+    host = song_inputs(0, dev, args.encoders)   # same shapes for every song; contents re-seeded per song below (cheap host RNG is not timed)
 
     phases = {}   # --breakdown: ms per phase of the last song (events around the three models)
 
@@ -76,9 +96,11 @@ def main():
         if ev: ev[0].record()
         cond_mgc, cond_bap, d, sig = (t.to(dev, non_blocking=True) for t in host)
         if ev: ev[1].record()
-        m = mgc.inference(cond_mgc)                       # (6, 6000, 60)
+        if args.encoders:                                 # both encoders side by side (pipeline.EnsembleSynthesizer._encode)
+            cond_mgc, cond_bap = enc._encode(cond_mgc, cond_bap, [FRAMES] * TRACKS)
+        m = mgc.inference(cond_mgc, cond_is_encoded=True)  # (6, 6000, 60)
         if ev: ev[2].record()
-        b = bap.inference(cond_bap)                       # (6, 6000, 5)
+        b = bap.inference(cond_bap, cond_is_encoded=True)  # (6, 6000, 5)
         if ev: ev[3].record()
         aux = torch.cat([m, b], dim=-1).transpose(1, 2)   # (6, 65, 6000) == vocoder frames at 5 ms
         aux = torch.nn.functional.pad(aux, (2, 2), mode="replicate").contiguous()
@@ -86,7 +108,7 @@ def main():
         if ev: ev[4].record()
         out = wav.cpu()                                   # D2H of the 6 waveforms
         if ev:
-            names = ["h2d", "mgc diffusion", "bap diffusion", "vocoder"]
+            names = ["h2d", "encoders + mgc diffusion" if args.encoders else "mgc diffusion", "bap diffusion", "vocoder"]
             phases.update({n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(names)})
         return out
 
@@ -111,7 +133,8 @@ def main():
                           "value": audio / sec, "unit": "audio-sec/s", "n_gpus": world, "songs": args.songs,
                           "seconds": sec, "wall_seconds_rank0": wall, "scaling": "strong",
                           "ms_per_song_rank0": 1e3 * sec / max(1, len(mine)), "gpu_launches_rank0": _lib.launch_count - n0,
-                          "config": {"workload": f"{args.songs} songs x {TRACKS} tracks x {SECONDS:.0f} s, K=100, 24 kHz"},
+                          "config": {"workload": f"{args.songs} songs x {TRACKS} tracks x {SECONDS:.0f} s, K=100, 24 kHz",
+                                     "encoders": bool(args.encoders)},
                           **({"phases_ms_last_song": phases} if args.breakdown else {})}))
     if world > 1:
         dist.destroy_process_group()
