@@ -10,7 +10,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["svsk_api.cu", "simt_f32.cu", "tma_util.cu", "diffnet_block_sm100.cu", "diffnet_block2_sm100.cu", "diffnet_block3_sm100.cu", "diffnet_stack_sm100.cu", "diffnet_step_sm100.cu", "linear_sm100.cu",
-           "usfgan_block_sm100.cu", "conv1d_sm100.cu", "usfgan_front.cu", "lstm_sm100.cu", "encoder_sm100.cu", "ubench_sm100.cu"]
+           "usfgan_block_sm100.cu", "conv1d_sm100.cu", "usfgan_front.cu", "lstm_sm100.cu", "encoder_sm100.cu", "postproc.cu", "ubench_sm100.cu"]
 LIB = os.path.join(HERE, "libsvsk.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

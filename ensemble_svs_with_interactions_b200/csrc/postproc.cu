@@ -1,0 +1,140 @@
+// Acoustic post-processing between the diffusion models and the vocoder on the device:
+//   * svsk_filtfilt_f32 — nnsvs.dsp.lowpass_filter (dsp.py:10-33; called per feature dimension at gen.py:1500-1513):
+//     scipy.signal.filtfilt with its defaults, i.e. odd extension by `pad` samples, a direct-form-II-transposed IIR pass
+//     forward started from zi * ext[0], the same pass backward started from zi * y[last], extension dropped;
+//   * svsk_variance_scaling_f32 — nnsvs.postfilters.variance_scaling (postfilters.py:9-46; gen.py:1394-1418).
+// Both walk feature trajectories [track][frame][dim] with one thread per (track, dim): neighbouring threads read
+// neighbouring dims of the same frame (coalesced), the recurrences run in fp64 like the reference's numpy / scipy code.
+// The work is tiny (hundreds of trajectories) and purely latency-bound; what it buys is that the features never leave
+// the GPU between GaussianDiffusion.inference and the vocoder.
+#include "svsk_common.cuh"
+
+namespace svsk {
+
+constexpr int kMaxOrder = 8;
+
+struct FiltArgs {
+  const float* x;
+  float* y;
+  double* scratch;
+  const int32_t* lengths;
+  double b[kMaxOrder + 1], a[kMaxOrder + 1], zi[kMaxOrder];
+  int B, T, D, pad, min_len;
+};
+
+template <int N>
+__device__ __forceinline__ double df2t_step(const double (&b)[N + 1], const double (&a)[N + 1], double (&z)[N], double x) {
+  const double y = fma(b[0], x, z[0]);
+#pragma unroll
+  for (int i = 0; i < N - 1; ++i) z[i] = fma(b[i + 1], x, fma(-a[i + 1], y, z[i + 1]));
+  z[N - 1] = fma(b[N], x, -a[N] * y);
+  return y;
+}
+
+template <int N>
+__global__ void filtfilt_kernel(const FiltArgs p) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x, bi = blockIdx.y;
+  if (d >= p.D) return;
+  const int len = p.lengths ? min(max(p.lengths[bi], 0), p.T) : p.T;
+  const float* x = p.x + (size_t)bi * p.T * p.D + d;
+  float* y = p.y + (size_t)bi * p.T * p.D + d;
+  for (int t = len; t < p.T; ++t) y[(size_t)t * p.D] = x[(size_t)t * p.D];   // padding frames pass through
+  if (len <= p.min_len) {                                                       // dsp.py:26-28: too short, returned as is
+    for (int t = 0; t < len; ++t) y[(size_t)t * p.D] = x[(size_t)t * p.D];
+    return;
+  }
+  double b[N + 1], a[N + 1], z[N];
+#pragma unroll
+  for (int i = 0; i <= N; ++i) { b[i] = p.b[i]; a[i] = p.a[i]; }
+  const int pad = p.pad, E = len + 2 * pad;
+  double* s = p.scratch + (size_t)bi * (p.T + 2 * pad) * p.D + d;
+  const double x0 = x[0], xl = x[(size_t)(len - 1) * p.D];
+  auto ext = [&](int e) -> double {   // odd extension of the first `len` frames
+    if (e < pad) return 2.0 * x0 - (double)x[(size_t)(pad - e) * p.D];
+    if (e < pad + len) return (double)x[(size_t)(e - pad) * p.D];
+    return 2.0 * xl - (double)x[(size_t)(len - 2 - (e - pad - len)) * p.D];
+  };
+  const double e0 = ext(0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) z[i] = p.zi[i] * e0;
+  double last = 0.0;
+  for (int e = 0; e < E; ++e) {
+    last = df2t_step<N>(b, a, z, ext(e));
+    s[(size_t)e * p.D] = last;
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) z[i] = p.zi[i] * last;
+  for (int e = E - 1; e >= 0; --e) {
+    const double v = df2t_step<N>(b, a, z, s[(size_t)e * p.D]);
+    if (e >= pad && e < pad + len) y[(size_t)(e - pad) * p.D] = (float)v;
+  }
+}
+
+template <int N>
+static void launch_filtfilt(const FiltArgs& a, cudaStream_t st) {
+  dim3 grid((unsigned)((a.D + 63) / 64), (unsigned)a.B);
+  filtfilt_kernel<N><<<grid, 64, 0, st>>>(a);
+}
+
+__global__ void variance_scaling_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ gv,
+                                        const uint8_t* __restrict__ mask, const int32_t* __restrict__ lengths, int offset, int B,
+                                        int T, int D) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x, bi = blockIdx.y;
+  if (d >= D) return;
+  const int len = lengths ? min(max(lengths[bi], 0), T) : T;
+  const float* xs = x + (size_t)bi * T * D + d;
+  float* ys = y + (size_t)bi * T * D + d;
+  const uint8_t* m = mask ? mask + (size_t)bi * T : nullptr;
+  double sum = 0.0;
+  int n = 0;
+  for (int t = 0; t < len; ++t)
+    if (!m || m[t]) { sum += xs[(size_t)t * D]; ++n; }
+  const double mu = n ? sum / n : 0.0;
+  double ss = 0.0;
+  for (int t = 0; t < len; ++t)
+    if (!m || m[t]) { const double v = xs[(size_t)t * D] - mu; ss = fma(v, v, ss); }
+  const bool scale = n > 0 && d >= offset;                  // postfilters.py:24-25: no note frames -> unchanged
+  const double g = scale ? sqrt((double)gv[d] / (ss / n)) : 1.0;
+  for (int t = 0; t < T; ++t) {
+    const float v = xs[(size_t)t * D];
+    ys[(size_t)t * D] = (scale && t < len && (!m || m[t])) ? (float)fma(g, (double)v - mu, mu) : v;
+  }
+}
+
+}  // namespace svsk
+
+using namespace svsk;
+
+extern "C" int svsk_filtfilt_f32(const float* x, float* y, double* scratch, const int32_t* lengths, const double* b, const double* a,
+                                 const double* zi, int order, int pad, int min_len, int B, int T, int D, void* stream) {
+  SVSK_REQUIRE(x && y && scratch && b && a && zi, SVSK_E_ARG, "filtfilt_f32: null argument");
+  SVSK_REQUIRE(order >= 1 && order <= kMaxOrder, SVSK_E_ARG, "filtfilt_f32: order %d (1..%d)", order, kMaxOrder);
+  SVSK_REQUIRE(B > 0 && T > 0 && D > 0 && pad >= 1 && min_len >= pad, SVSK_E_ARG,
+               "filtfilt_f32: B=%d T=%d D=%d pad=%d min_len=%d (sequences must be longer than the extension)", B, T, D, pad, min_len);
+  SVSK_REQUIRE(a[0] == 1.0, SVSK_E_ARG, "filtfilt_f32: a[0] must be 1 (normalised coefficients)");
+  FiltArgs p = {};
+  p.x = x; p.y = y; p.scratch = scratch; p.lengths = lengths;
+  for (int i = 0; i <= order; ++i) { p.b[i] = b[i]; p.a[i] = a[i]; }
+  for (int i = 0; i < order; ++i) p.zi[i] = zi[i];
+  p.B = B; p.T = T; p.D = D; p.pad = pad; p.min_len = min_len;
+  cudaStream_t st = as_stream(stream);
+  switch (order) {
+    case 1: launch_filtfilt<1>(p, st); break;
+    case 2: launch_filtfilt<2>(p, st); break;
+    case 3: launch_filtfilt<3>(p, st); break;
+    case 4: launch_filtfilt<4>(p, st); break;
+    case 5: launch_filtfilt<5>(p, st); break;
+    case 6: launch_filtfilt<6>(p, st); break;
+    case 7: launch_filtfilt<7>(p, st); break;
+    default: launch_filtfilt<8>(p, st); break;
+  }
+  return check_launch("filtfilt_f32");
+}
+
+extern "C" int svsk_variance_scaling_f32(const float* x, float* y, const float* gv, const uint8_t* note_mask, const int32_t* lengths,
+                                         int offset, int B, int T, int D, void* stream) {
+  SVSK_REQUIRE(x && y && gv && B > 0 && T > 0 && D > 0 && offset >= 0, SVSK_E_ARG, "variance_scaling_f32: bad args");
+  dim3 grid((unsigned)((D + 63) / 64), (unsigned)B);
+  variance_scaling_kernel<<<grid, 64, 0, as_stream(stream)>>>(x, y, gv, note_mask, lengths, offset, B, T, D);
+  return check_launch("variance_scaling_f32");
+}

@@ -474,3 +474,27 @@ def encoder_front(x, onehot_start, onehot_len, *, y_f32=None, y_bf16=None):
     L.check(L.lib().svsk_encoder_front(L.ptr(x, f32, "x"), L.ptr(y_f32, f32, "y_f32"), L.ptr(y_bf16, bf16, "y_bf16"), rows, in_dim,
                                        onehot_start, onehot_len, 0 if y_f32 is None else y_f32.shape[1],
                                        0 if y_bf16 is None else y_bf16.shape[1], L.stream_ptr()), "encoder_front")
+
+
+# ---- acoustic post-processing (include/svsk.h, "acoustic post-processing on the device") ----------------------------
+def filtfilt_f32(x, b, a, zi, *, min_len, lengths=None, out=None):
+    """svsk_filtfilt_f32.  x [B, T, D] fp32; b, a, zi: float64 sequences (host); lengths int32 [B] or None."""
+    B, T, D = x.shape
+    order = len(a) - 1
+    pad = 3 * (order + 1)
+    out = torch.empty_like(x) if out is None else out
+    scratch = torch.empty((B, T + 2 * pad, D), device=x.device, dtype=torch.float64)
+    arr = lambda v: (C.c_double * len(v))(*[float(t) for t in v])
+    L.check(L.lib().svsk_filtfilt_f32(L.ptr(x, f32, "x"), L.ptr(out, f32, "out"), L.ptr(scratch), L.ptr(lengths, torch.int32, "lengths"),
+                                      arr(b), arr(a), arr(zi), order, pad, int(min_len), B, T, D, L.stream_ptr()), "filtfilt_f32")
+    return out
+
+
+def variance_scaling_f32(x, gv, *, offset=2, note_mask=None, lengths=None, out=None):
+    """svsk_variance_scaling_f32.  x [B, T, D] fp32, gv [D] fp32, note_mask uint8 [B, T] or None, lengths int32 [B] or None."""
+    B, T, D = x.shape
+    out = torch.empty_like(x) if out is None else out
+    L.check(L.lib().svsk_variance_scaling_f32(L.ptr(x, f32, "x"), L.ptr(out, f32, "out"), L.ptr(gv, f32, "gv"),
+                                              L.ptr(note_mask, torch.uint8, "note_mask"), L.ptr(lengths, torch.int32, "lengths"),
+                                              int(offset), B, T, D, L.stream_ptr()), "variance_scaling_f32")
+    return out

@@ -11,9 +11,10 @@ item is independent once its conditioning exists, so here they are
   ``USFGANWrapper.inference_batch`` (all tracks per vocoder launch),
 * trimmed back to their own lengths and returned in input order.
 
-What stays outside (the reference's CPU code between the models, SURVEY §8(f) row 3 second part): GV post-filtering and
-the scipy low-pass of ``postprocess_acoustic`` (gen.py:1394-1518), the pyworld bap round trip (gen.py:1639-1670) and the
-feature scalers — they enter through ``aux_fn``.
+Between the models, on the device (second part): the GV post-filter of the mgc stream and the
+zero-phase low-pass of both streams (``postprocess.variance_scaling`` / ``postprocess.lowpass_filter`` — gen.py:1394-1418,
+1500-1513 do these per utterance and per dimension in numpy / scipy on the host).  What stays outside: the pyworld bap
+round trip (gen.py:1639-1670), the learned post-filters and the feature scalers — they enter through ``aux_fn``.
 """
 from __future__ import annotations
 
@@ -22,7 +23,7 @@ from typing import Callable, List, Optional, Sequence
 
 import torch
 
-from . import sharding
+from . import postprocess, sharding
 
 
 @dataclass
@@ -62,12 +63,20 @@ class EnsembleSynthesizer:
     (``model.FFConvLSTM``: then ``cond_*`` are the linguistic features and every item's own length drives its packed
     BiLSTM); vocoder: ``USFGANWrapper``.
     aux_fn(mgc [B,T,M1], bap [B,T,M2], f0 [B,T,1]) -> vocoder aux features [B,T,C]; default: concatenate mgc and bap.
-    max_frames: frame budget of one batch (tracks x padded frames)."""
+    max_frames: frame budget of one batch (tracks x padded frames).
+    smoothing_cutoff: Hz, or None — ``trajectory_smoothing`` of gen.postprocess_acoustic (its default: 50 at
+    ``frame_rate`` = 200 frames per second) applied to both streams.
+    gv_mgc: global variance of the mgc stream [M1] (the scaler's ``var_``), or None — the GV post-filter, applied to
+    the frames marked in ``note_masks`` (all valid frames when no masks are given), dimensions >= ``gv_offset``."""
 
     def __init__(self, mgc, bap, vocoder, max_frames: int = 36000,
-                 aux_fn: Optional[Callable[[torch.Tensor, torch.Tensor, torch.Tensor], torch.Tensor]] = None):
+                 aux_fn: Optional[Callable[[torch.Tensor, torch.Tensor, torch.Tensor], torch.Tensor]] = None,
+                 smoothing_cutoff: Optional[float] = None, frame_rate: int = 200, gv_mgc: Optional[torch.Tensor] = None,
+                 gv_offset: int = 2):
         self.mgc, self.bap, self.vocoder = mgc, bap, vocoder
         self.max_frames = int(max_frames)
+        self.smoothing_cutoff, self.frame_rate = smoothing_cutoff, int(frame_rate)
+        self.gv_mgc, self.gv_offset = gv_mgc, int(gv_offset)
         self.aux_fn = aux_fn if aux_fn is not None else (lambda m, b, f0: torch.cat([m, b], dim=-1))
         self._side = None
 
@@ -90,8 +99,10 @@ class EnsembleSynthesizer:
 
     @torch.no_grad()
     def synthesize(self, cond_mgc: Sequence[torch.Tensor], cond_bap: Sequence[torch.Tensor], f0: Sequence[torch.Tensor],
-                   world_size: int = 1, rank: int = 0) -> List[Optional[torch.Tensor]]:
-        """Per item i: cond_mgc[i] [T_i, H1], cond_bap[i] [T_i, H2], f0[i] [T_i, 1] (Hz, 0 = unvoiced), any device.
+                   world_size: int = 1, rank: int = 0,
+                   note_masks: Optional[Sequence[torch.Tensor]] = None) -> List[Optional[torch.Tensor]]:
+        """Per item i: cond_mgc[i] [T_i, H1], cond_bap[i] [T_i, H2], f0[i] [T_i, 1] (Hz, 0 = unvoiced), any device;
+        note_masks[i] [T_i] bool (frames inside notes, for the GV post-filter).
         Returns the waveforms [T_i * hop] of this rank's items in input order (None for items of other ranks)."""
         n = len(cond_mgc)
         if not (len(cond_bap) == n and len(f0) == n):
@@ -111,6 +122,15 @@ class EnsembleSynthesizer:
             hm, hb = self._encode(cm, cb, lens)
             m = self.mgc.inference(hm, cond_is_encoded=True)   # [B, T, M1]
             b = self.bap.inference(hb, cond_is_encoded=True)   # [B, T, M2]
+            if self.gv_mgc is not None:                        # gen.py:1394-1418
+                mask = None
+                if note_masks is not None:
+                    mask = torch.stack([_pad_time(note_masks[i].to(dev).to(torch.uint8)[:, None], plan.frames, "zeros")[:, 0]
+                                        for i in plan.items])
+                m = postprocess.variance_scaling(self.gv_mgc, m, offset=self.gv_offset, note_mask=mask, lengths=lens)
+            if self.smoothing_cutoff is not None:              # gen.py:1500-1513
+                m = postprocess.lowpass_filter(m, self.frame_rate, cutoff=self.smoothing_cutoff, lengths=lens)
+                b = postprocess.lowpass_filter(b, self.frame_rate, cutoff=self.smoothing_cutoff, lengths=lens)
             wav = self.vocoder.inference_batch(f, self.aux_fn(m, b, f).contiguous())   # [B, 1, T * hop]
             for k, i in enumerate(plan.items):
                 out[i] = wav[k, 0, :lengths[i] * hop].clone()

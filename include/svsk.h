@@ -402,6 +402,22 @@ SVSK_API int svsk_reflect_pad_rows_bf16(void* buf, int B, int Tp, int C, int T, 
 SVSK_API int svsk_encoder_front(const float* x, float* y_f32, void* y_bf16, long long rows, int in_dim, int onehot_start,
                                 int onehot_len, int ldy_f, int ldy_b, void* stream);
 
+/* ---- acoustic post-processing on the device ----------------------------------------------- */
+
+/* nnsvs.dsp.lowpass_filter over whole batches (dsp.py:10-33; gen.py:1500-1513 calls it per feature dimension):
+ * scipy.signal.filtfilt(b, a, x) with default padding on every trajectory x[bi, :lengths[bi], d] of x [B][T][D] fp32 ->
+ * y (may alias x).  b, a (a[0] == 1, order+1 values each) and zi = lfilter_zi(b, a) (order values) are HOST pointers
+ * read at call time; pad = 3 * (order + 1); trajectories of at most min_len (>= pad) frames, and the frames beyond
+ * lengths[bi], are copied unchanged (dsp.py:26-28).  scratch: B * (T + 2 pad) * D doubles.  fp64 arithmetic. */
+SVSK_API int svsk_filtfilt_f32(const float* x, float* y, double* scratch, const int32_t* lengths, const double* b,
+                               const double* a, const double* zi, int order, int pad, int min_len, int B, int T, int D,
+                               void* stream);
+/* nnsvs.postfilters.variance_scaling per track (postfilters.py:9-46; gen.py:1410-1418): mean / population variance of
+ * x[bi, t, d] over the frames t < lengths[bi] with note_mask[bi][t] != 0 (NULL mask = all frames), then
+ * y = sqrt(gv[d] / var) * (x - mean) + mean on those frames for d >= offset; everything else is copied.  x, y [B][T][D]. */
+SVSK_API int svsk_variance_scaling_f32(const float* x, float* y, const float* gv, const uint8_t* note_mask,
+                                       const int32_t* lengths, int offset, int B, int T, int D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

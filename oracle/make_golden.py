@@ -299,6 +299,27 @@ def golden_encoder(ns):
         _save(name, cfg, m.state_dict(), dict(x=x, lengths=torch.tensor(lengths)), dict(y=y, ff=ff, conv=conv))
 
 
+def golden_postprocess(ns):
+    """nnsvs.dsp.lowpass_filter and nnsvs.postfilters.variance_scaling as gen.postprocess_acoustic calls them
+    (gen.py:1394-1418,1500-1513): 5 ms frames (modfs 200), cutoffs 50 (mgc / bap) and 20 (lf0)."""
+    g = np.random.RandomState(71)
+    T, D = 400, 7
+    t = np.arange(T)[:, None] / 200.0
+    x = np.sin(2 * np.pi * (3.0 + np.arange(D)[None]) * t) + 0.3 * g.randn(T, D)        # float64, like the scaler's output
+    y50 = np.stack([ns.lowpass_filter(x[:, d], 200, cutoff=50) for d in range(D)], 1)
+    y20 = np.stack([ns.lowpass_filter(x[:, d], 200, cutoff=20) for d in range(D)], 1)
+    short = x[:18, 0].copy()
+    y_short = ns.lowpass_filter(short, 200, cutoff=50)                                   # too short: returned as is
+    y_19 = ns.lowpass_filter(x[:19, 0].copy(), 200, cutoff=50)
+    gv = g.rand(D) + 0.5
+    notes = np.sort(g.choice(T, 300, replace=False))
+    vs_notes = ns.variance_scaling(gv, x, offset=2, note_frame_indices=notes)
+    vs_all = ns.variance_scaling(gv, x, offset=2)
+    vs_none = ns.variance_scaling(gv, x, offset=2, note_frame_indices=np.array([], dtype=np.int64))
+    _save("postprocess", dict(fs=200, N=5), {}, dict(x=x, gv=gv, notes=notes, short=short),
+          dict(y50=y50, y20=y20, y_short=y_short, y_19=y_19, vs_notes=vs_notes, vs_all=vs_all, vs_none=vs_none))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = load_reference()
@@ -310,6 +331,7 @@ def main():
     golden_usfgan(ns)
     golden_frontend(ns)
     golden_encoder(ns)
+    golden_postprocess(ns)
 
 
 if __name__ == "__main__":

@@ -67,6 +67,8 @@ def load_reference():
     import nnsvs.usfgan.utils.features as features
     from nnsvs.usfgan import USFGANWrapper
     from nnsvs.model import FFConvLSTM
+    from nnsvs.dsp import lowpass_filter
+    from nnsvs.postfilters import variance_scaling
 
     # pd_indexing/index_initial call .cuda() whenever CUDA is visible
     # (nnsvs/usfgan/utils/index.py:32-33,44-45,81-83); the CPU oracle use of the
@@ -89,4 +91,6 @@ def load_reference():
     ns.dilated_factor = features.dilated_factor
     ns.USFGANWrapper = USFGANWrapper
     ns.FFConvLSTM = FFConvLSTM
+    ns.lowpass_filter = lowpass_filter
+    ns.variance_scaling = variance_scaling
     return ns

@@ -607,3 +607,81 @@ def ffconvlstm_forward(sd: SD, x: Tensor, lengths: Sequence[int], *, in_ph_start
     h = h[:, :max(int(n) for n in lengths)]
     out = h @ sd["fc.weight"].t() + sd["fc.bias"]
     return (out, dict(ff=ff, conv=conv, lstm=h)) if want_parts else out
+
+
+# --------------------------------------------------------------------------- #
+# Acoustic post-processing between the diffusion models and the vocoder — SURVEY.md §8(f) row 3
+# (nnsvs/postfilters.py:9-46, nnsvs/dsp.py:10-33, call sites nnsvs/gen.py:1394-1418,1500-1513)
+# --------------------------------------------------------------------------- #
+def variance_scaling(gv: np.ndarray, feats: np.ndarray, offset: int = 2, note_frame_indices=None) -> np.ndarray:
+    """postfilters.py:9-46: per-dimension mean / population variance over the note frames of ONE utterance, then
+    ``sqrt(gv / utt_gv) * (x - mu) + mu`` on those frames for the dimensions >= offset; no note frames -> unchanged."""
+    if note_frame_indices is not None and len(note_frame_indices) == 0:
+        return feats
+    sel = feats if note_frame_indices is None else feats[note_frame_indices]
+    mu, var = sel.mean(0), sel.var(0)
+    out = feats.copy()
+    rows = slice(None) if note_frame_indices is None else note_frame_indices
+    out[rows, offset:] = np.sqrt(gv[offset:] / var[offset:]) * (sel[:, offset:] - mu[offset:]) + mu[offset:]
+    return out
+
+
+def butter_lowpass(N: int, Wn: float) -> Tuple[np.ndarray, np.ndarray]:
+    """``scipy.signal.butter(N, Wn, "lowpass")`` (third-party dependency of dsp.py:25; scipy's published algorithm):
+    analog Butterworth prototype -> frequency warp -> bilinear transform (fs = 2) -> polynomial coefficients."""
+    m = np.arange(-N + 1, N, 2)
+    p = -np.exp(1j * np.pi * m / (2 * N))
+    warped = 4.0 * np.tan(np.pi * Wn / 2.0)
+    p = warped * p
+    k = warped ** N
+    fs2 = 4.0
+    pd = (fs2 + p) / (fs2 - p)
+    kd = k * np.real(1.0 / np.prod(fs2 - p))
+    b = kd * np.poly(-np.ones(N))
+    a = np.real(np.poly(pd))
+    return b, a
+
+
+def lfilter_zi(b: np.ndarray, a: np.ndarray) -> np.ndarray:
+    """``scipy.signal.lfilter_zi``: the direct-form-II-transposed state of the step response's steady state,
+    (I - A^T) zi = b[1:] - a[1:] b[0] with A the companion matrix of a (a[0] == 1)."""
+    n = len(a) - 1
+    comp = np.zeros((n, n))
+    comp[0] = -a[1:]
+    comp[1:, :-1] = np.eye(n - 1)
+    return np.linalg.solve(np.eye(n) - comp.T, b[1:] - a[1:] * b[0])
+
+
+def lfilter_df2t(b: np.ndarray, a: np.ndarray, x: np.ndarray, zi: np.ndarray) -> np.ndarray:
+    """``scipy.signal.lfilter(b, a, x, zi=zi)[0]``: y = b0 x + z0; z_i = b_{i+1} x - a_{i+1} y + z_{i+1}."""
+    n = len(a) - 1
+    z = zi.astype(np.float64).copy()
+    y = np.empty(len(x))
+    for t, xt in enumerate(x):
+        yt = b[0] * xt + z[0]
+        for i in range(n - 1):
+            z[i] = b[i + 1] * xt - a[i + 1] * yt + z[i + 1]
+        z[n - 1] = b[n] * xt - a[n] * yt
+        y[t] = yt
+    return y
+
+
+def filtfilt(b: np.ndarray, a: np.ndarray, x: np.ndarray) -> np.ndarray:
+    """``scipy.signal.filtfilt(b, a, x)`` with its defaults (dsp.py:31): odd extension by 3 * max(len(a), len(b))
+    samples, forward pass started from zi * ext[0], backward pass started from zi * y[-1], extension removed."""
+    pad = 3 * max(len(a), len(b))
+    x = np.asarray(x, dtype=np.float64)
+    ext = np.concatenate([2 * x[0] - x[pad:0:-1], x, 2 * x[-1] - x[-2:-pad - 2:-1]])
+    zi = lfilter_zi(b, a)
+    y = lfilter_df2t(b, a, ext, zi * ext[0])
+    y = lfilter_df2t(b, a, y[::-1], zi * y[-1])[::-1]
+    return np.ascontiguousarray(y[pad:-pad])
+
+
+def lowpass_filter(x: np.ndarray, fs: int, cutoff: float = 5, N: int = 5) -> np.ndarray:
+    """dsp.py:10-33: zero-phase Butterworth low-pass of one trajectory; sequences of at most
+    max(len(a), len(b)) * (N // 2 + 1) samples come back unchanged."""
+    b, a = butter_lowpass(N, cutoff / (fs // 2))
+    if len(x) <= max(len(a), len(b)) * (N // 2 + 1):
+        return x
+    return filtfilt(b, a, x)

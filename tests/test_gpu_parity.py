@@ -964,6 +964,19 @@ def test_pipeline_with_encoders_matches_sequential_calls():
     torch.manual_seed(5)
     m = mgc.inference(batch, lens); b = bap.inference(batch, lens)
     assert torch.equal(seen["aux"], torch.cat([m, b], dim=-1))
+    # with the device post-processing between the models (GV post-filter on note frames + 50 Hz smoothing)
+    from ensemble_svs_with_interactions_b200 import postprocess as pp
+    gv = torch.rand(60, generator=g) + 0.5
+    notes = [torch.rand(n, generator=g) > 0.3 for n in lens]
+    synth2 = EnsembleSynthesizer(mgc, bap, Voc(), max_frames=1000, smoothing_cutoff=50, gv_mgc=gv)
+    torch.manual_seed(5)
+    synth2.synthesize(ling, ling, f0, note_masks=notes)
+    for i, n in enumerate(lens):
+        ref = O.variance_scaling(gv.double().numpy(), m[i, :n].cpu().double().numpy(), 2, np.nonzero(notes[i].numpy())[0])
+        ref = np.stack([O.lowpass_filter(ref[:, d], 200, cutoff=50) for d in range(60)], 1)
+        close32(seen["aux"][i, :n, :60], torch.from_numpy(ref), tol=2e-5)
+        refb = np.stack([O.lowpass_filter(b[i, :n, d].cpu().double().numpy(), 200, cutoff=50) for d in range(5)], 1)
+        close32(seen["aux"][i, :n, 60:], torch.from_numpy(refb), tol=2e-5)
 
 
 # ------------------------------------------------------------------------------------------------ FFConvLSTM encoder
@@ -1094,3 +1107,52 @@ def test_gaussian_diffusion_with_encoder():
     x[..., 3:50] = torch.nn.functional.one_hot(torch.randint(0, 47, (2, 160), generator=g), 47).float()
     y = m.inference(x.to(DEV), [160, 160])
     assert y.shape == (2, 160, 60) and torch.isfinite(y).all()
+
+
+# ------------------------------------------------------------------------------------------------ post-processing (row f3)
+def test_lowpass_filter_matches_reference_golden():
+    """postprocess.lowpass_filter against nnsvs.dsp.lowpass_filter outputs (float64 filtfilt; the device works in fp64 and
+    stores fp32): max-abs <= 2e-6 * max(1, |ref|)."""
+    from ensemble_svs_with_interactions_b200.postprocess import lowpass_filter
+    g = Golden("postprocess")
+    x = g.inp["x"].float()[None].to(DEV)                                  # [1, 400, 7]
+    for cutoff, key in ((50, "y50"), (20, "y20")):
+        y = lowpass_filter(x, 200, cutoff=cutoff)
+        ref = torch.from_numpy(np.stack([O.lowpass_filter(x[0, :, d].cpu().double().numpy(), 200, cutoff=cutoff) for d in range(7)], 1))
+        close32(y[0], ref, tol=2e-6)                                      # same fp32-rounded input on both sides
+        close32(y[0], g.out[key], tol=2e-6)                               # and the reference's own float64 run
+    # ragged batch: per-track lengths, a too-short track (<= 18 frames) and padding frames pass through unchanged
+    gen = torch.Generator().manual_seed(4)
+    xb = torch.randn(4, 120, 5, generator=gen)
+    lens = [120, 77, 18, 19]
+    yb = lowpass_filter(xb.to(DEV), 200, cutoff=50, lengths=lens).cpu()
+    for b, n in enumerate(lens):
+        ref = np.stack([O.lowpass_filter(xb[b, :n, d].double().numpy(), 200, cutoff=50) for d in range(5)], 1)
+        close32(yb[b, :n], torch.from_numpy(ref), tol=2e-6)
+        assert torch.equal(yb[b, n:], xb[b, n:])
+    assert torch.equal(yb[2, :18], xb[2, :18])
+    # a wide, long batch (6 tracks x 6000 frames x 65 dims, the pipeline's shape): smooth output, finite, same length
+    big = torch.randn(6, 6000, 65, device=DEV)
+    out = lowpass_filter(big, 200, cutoff=50)
+    d0 = O.lowpass_filter(big[3, :, 11].cpu().double().numpy(), 200, cutoff=50)
+    close32(out[3, :, 11], torch.from_numpy(d0), tol=2e-6)
+
+
+def test_variance_scaling_matches_reference_golden():
+    from ensemble_svs_with_interactions_b200.postprocess import variance_scaling
+    g = Golden("postprocess")
+    x, gv, notes = g.inp["x"].float(), g.inp["gv"].float(), g.inp["notes"]
+    mask = torch.zeros(400, dtype=torch.bool)
+    mask[notes] = True
+    xb = torch.stack([x, x, x])
+    masks = torch.stack([mask, torch.ones(400, dtype=torch.bool), torch.zeros(400, dtype=torch.bool)])
+    y = variance_scaling(gv.to(DEV), xb.to(DEV), offset=2, note_mask=masks.to(DEV)).cpu()
+    close32(y[0], g.out["vs_notes"], tol=1e-5)
+    close32(y[1], g.out["vs_all"], tol=1e-5)
+    assert torch.equal(y[2], x)                                           # no note frames: unchanged (postfilters.py:24-25)
+    assert torch.equal(y[0][:, :2], x[:, :2])                             # dims below `offset` untouched
+    # lengths: statistics over the valid frames only
+    y2 = variance_scaling(gv.to(DEV), xb[:1].to(DEV), offset=2, lengths=[250]).cpu()
+    ref = O.variance_scaling(gv.double().numpy(), x[:250].double().numpy(), 2)
+    close32(y2[0, :250], torch.from_numpy(ref), tol=1e-5)
+    assert torch.equal(y2[0, 250:], x[250:])

@@ -174,3 +174,18 @@ def test_ffconvlstm_ctor_and_loud_failures():
         m(torch.zeros(1, 8, 87))
     with pytest.raises(RuntimeError, match="CUDA"):
         m.eval()(torch.zeros(1, 8, 87))
+
+
+def test_postprocess_filter_design_matches_scipy():
+    """Host side of row f3: the Butterworth design and lfilter_zi the device filter is fed with equal scipy's (dsp.py:25)."""
+    from scipy import signal
+    from ensemble_svs_with_interactions_b200.postprocess import butter_lowpass, lfilter_zi, lowpass_filter
+    for N, Wn in ((5, 0.5), (5, 0.2), (3, 0.05), (8, 0.7)):
+        b, a = butter_lowpass(N, Wn)
+        bs, as_ = signal.butter(N, [Wn], "lowpass")
+        assert np.abs(np.array(b) - bs).max() <= 1e-12 and np.abs(np.array(a) - as_).max() <= 1e-10
+        assert np.abs(lfilter_zi(b, a) - signal.lfilter_zi(bs, as_)).max() <= 1e-9
+    with pytest.raises(ValueError):
+        butter_lowpass(5, 1.0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        lowpass_filter(torch.zeros(1, 40, 3), 200, cutoff=50)
