@@ -24,10 +24,12 @@ struct FiltArgs {
 
 template <int N>
 __device__ __forceinline__ double df2t_step(const double (&b)[N + 1], const double (&a)[N + 1], double (&z)[N], double x) {
-  const double y = fma(b[0], x, z[0]);
+  // y_t -> z0_t -> y_{t+1} is the serial chain: everything that does not need y is computed off it, leaving one add and
+  // one fma per sample (same arithmetic as scipy's lfilter up to the rounding of b0 x + z0)
+  const double y = z[0] + b[0] * x;
 #pragma unroll
-  for (int i = 0; i < N - 1; ++i) z[i] = fma(b[i + 1], x, fma(-a[i + 1], y, z[i + 1]));
-  z[N - 1] = fma(b[N], x, -a[N] * y);
+  for (int i = 0; i < N - 1; ++i) z[i] = fma(-a[i + 1], y, fma(b[i + 1], x, z[i + 1]));
+  z[N - 1] = fma(-a[N], y, b[N] * x);
   return y;
 }
 
@@ -49,24 +51,46 @@ __global__ void filtfilt_kernel(const FiltArgs p) {
   const int pad = p.pad, E = len + 2 * pad;
   double* s = p.scratch + (size_t)bi * (p.T + 2 * pad) * p.D + d;
   const double x0 = x[0], xl = x[(size_t)(len - 1) * p.D];
-  auto ext = [&](int e) -> double {   // odd extension of the first `len` frames
-    if (e < pad) return 2.0 * x0 - (double)x[(size_t)(pad - e) * p.D];
-    if (e < pad + len) return (double)x[(size_t)(e - pad) * p.D];
-    return 2.0 * xl - (double)x[(size_t)(len - 2 - (e - pad - len)) * p.D];
+  // odd extension of the first `len` frames, branch-free so that a chunk's loads issue back to back:
+  // ext(e) = base + sign * x[idx]
+  auto ext = [&](int e) -> double {
+    const bool head = e < pad, tail = e >= pad + len;
+    const int idx = head ? pad - e : (tail ? 2 * len - 2 + pad - e : e - pad);
+    const double v = (double)x[(size_t)idx * p.D];
+    return head ? 2.0 * x0 - v : (tail ? 2.0 * xl - v : v);
   };
   const double e0 = ext(0);
 #pragma unroll
   for (int i = 0; i < N; ++i) z[i] = p.zi[i] * e0;
+  // the recurrence is serial but its inputs are not: fetch kChunk samples at once (independent loads in flight), then run
+  // the dependent chain over registers — one thread per trajectory cannot hide a load per step otherwise
+  constexpr int kChunk = 32;
+  double v[kChunk];
   double last = 0.0;
-  for (int e = 0; e < E; ++e) {
-    last = df2t_step<N>(b, a, z, ext(e));
-    s[(size_t)e * p.D] = last;
+  for (int e0 = 0; e0 < E; e0 += kChunk) {
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) v[i] = ext(min(e0 + i, E - 1));
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) {
+      if (e0 + i < E) {
+        last = df2t_step<N>(b, a, z, v[i]);
+        s[(size_t)(e0 + i) * p.D] = last;
+      }
+    }
   }
 #pragma unroll
   for (int i = 0; i < N; ++i) z[i] = p.zi[i] * last;
-  for (int e = E - 1; e >= 0; --e) {
-    const double v = df2t_step<N>(b, a, z, s[(size_t)e * p.D]);
-    if (e >= pad && e < pad + len) y[(size_t)(e - pad) * p.D] = (float)v;
+  for (int e0 = E - 1; e0 >= 0; e0 -= kChunk) {
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) v[i] = s[(size_t)max(e0 - i, 0) * p.D];
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) {
+      const int e = e0 - i;
+      if (e >= 0) {
+        const double r = df2t_step<N>(b, a, z, v[i]);
+        if (e >= pad && e < pad + len) y[(size_t)(e - pad) * p.D] = (float)r;
+      }
+    }
   }
 }
 
@@ -76,26 +100,47 @@ static void launch_filtfilt(const FiltArgs& a, cudaStream_t st) {
   filtfilt_kernel<N><<<grid, 64, 0, st>>>(a);
 }
 
-__global__ void variance_scaling_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ gv,
-                                        const uint8_t* __restrict__ mask, const int32_t* __restrict__ lengths, int offset, int B,
-                                        int T, int D) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x, bi = blockIdx.y;
-  if (d >= D) return;
+constexpr int kVsSlices = 8;  // threads along time per (track, dim)
+
+__global__ void __launch_bounds__(64 * kVsSlices)
+variance_scaling_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ gv,
+                        const uint8_t* __restrict__ mask, const int32_t* __restrict__ lengths, int offset, int B, int T, int D) {
+  __shared__ double red[kVsSlices][64];
+  __shared__ int cnt[kVsSlices][64];
+  const int dx = threadIdx.x, sl = threadIdx.y;
+  const int d = blockIdx.x * 64 + dx, bi = blockIdx.y;
+  const bool live = d < D;
   const int len = lengths ? min(max(lengths[bi], 0), T) : T;
-  const float* xs = x + (size_t)bi * T * D + d;
-  float* ys = y + (size_t)bi * T * D + d;
+  const float* xs = x + (size_t)bi * T * D + (live ? d : 0);
+  float* ys = y + (size_t)bi * T * D + (live ? d : 0);
   const uint8_t* m = mask ? mask + (size_t)bi * T : nullptr;
   double sum = 0.0;
   int n = 0;
-  for (int t = 0; t < len; ++t)
-    if (!m || m[t]) { sum += xs[(size_t)t * D]; ++n; }
+  if (live)
+    for (int t = sl; t < len; t += kVsSlices)
+      if (!m || m[t]) { sum += xs[(size_t)t * D]; ++n; }
+  red[sl][dx] = sum;
+  cnt[sl][dx] = n;
+  __syncthreads();
+  sum = 0.0;
+  n = 0;
+#pragma unroll
+  for (int i = 0; i < kVsSlices; ++i) { sum += red[i][dx]; n += cnt[i][dx]; }   // same order on every slice: identical mu
   const double mu = n ? sum / n : 0.0;
+  __syncthreads();
   double ss = 0.0;
-  for (int t = 0; t < len; ++t)
-    if (!m || m[t]) { const double v = xs[(size_t)t * D] - mu; ss = fma(v, v, ss); }
+  if (live)
+    for (int t = sl; t < len; t += kVsSlices)
+      if (!m || m[t]) { const double v = xs[(size_t)t * D] - mu; ss = fma(v, v, ss); }
+  red[sl][dx] = ss;
+  __syncthreads();
+  ss = 0.0;
+#pragma unroll
+  for (int i = 0; i < kVsSlices; ++i) ss += red[i][dx];
+  if (!live) return;
   const bool scale = n > 0 && d >= offset;                  // postfilters.py:24-25: no note frames -> unchanged
   const double g = scale ? sqrt((double)gv[d] / (ss / n)) : 1.0;
-  for (int t = 0; t < T; ++t) {
+  for (int t = sl; t < T; t += kVsSlices) {
     const float v = xs[(size_t)t * D];
     ys[(size_t)t * D] = (scale && t < len && (!m || m[t])) ? (float)fma(g, (double)v - mu, mu) : v;
   }
@@ -135,6 +180,6 @@ extern "C" int svsk_variance_scaling_f32(const float* x, float* y, const float* 
                                          int offset, int B, int T, int D, void* stream) {
   SVSK_REQUIRE(x && y && gv && B > 0 && T > 0 && D > 0 && offset >= 0, SVSK_E_ARG, "variance_scaling_f32: bad args");
   dim3 grid((unsigned)((D + 63) / 64), (unsigned)B);
-  variance_scaling_kernel<<<grid, 64, 0, as_stream(stream)>>>(x, y, gv, note_mask, lengths, offset, B, T, D);
+  variance_scaling_kernel<<<grid, dim3(64, kVsSlices), 0, as_stream(stream)>>>(x, y, gv, note_mask, lengths, offset, B, T, D);
   return check_launch("variance_scaling_f32");
 }

@@ -129,8 +129,9 @@ class EnsembleSynthesizer:
                                         for i in plan.items])
                 m = postprocess.variance_scaling(self.gv_mgc, m, offset=self.gv_offset, note_mask=mask, lengths=lens)
             if self.smoothing_cutoff is not None:              # gen.py:1500-1513
-                m = postprocess.lowpass_filter(m, self.frame_rate, cutoff=self.smoothing_cutoff, lengths=lens)
-                b = postprocess.lowpass_filter(b, self.frame_rate, cutoff=self.smoothing_cutoff, lengths=lens)
+                M1 = m.shape[-1]                               # one launch for both streams: every trajectory is independent
+                mb = postprocess.lowpass_filter(torch.cat([m, b], dim=-1), self.frame_rate, cutoff=self.smoothing_cutoff, lengths=lens)
+                m, b = mb[..., :M1], mb[..., M1:]
             wav = self.vocoder.inference_batch(f, self.aux_fn(m, b, f).contiguous())   # [B, 1, T * hop]
             for k, i in enumerate(plan.items):
                 out[i] = wav[k, 0, :lengths[i] * hop].clone()

@@ -20,7 +20,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from ensemble_svs_with_interactions_b200 import _lib, sharding  # noqa: E402
+from ensemble_svs_with_interactions_b200 import _lib, postprocess, sharding  # noqa: E402
 from ensemble_svs_with_interactions_b200.diffsinger import DiffNet, GaussianDiffusion  # noqa: E402
 from ensemble_svs_with_interactions_b200.model import FFConvLSTM  # noqa: E402
 from ensemble_svs_with_interactions_b200.pipeline import EnsembleSynthesizer  # noqa: E402
@@ -77,6 +77,8 @@ def main():
     ap.add_argument("--warmup-songs", type=int, default=1)
     ap.add_argument("--encoders", action="store_true", help="run the recipe's FFConvLSTM encoders in front of both denoisers "
                     "(input = 87 linguistic features per frame instead of pre-computed conditioning)")
+    ap.add_argument("--postprocess", action="store_true", help="GV post-filter of the mgc stream + 50 Hz trajectory smoothing of both "
+                    "streams on the device between the diffusion models and the vocoder (gen.postprocess_acoustic's defaults)")
     ap.add_argument("--breakdown", action="store_true", help="also print ms per phase of the last song")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -86,6 +88,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     mgc, bap, voc = build(dev, args.encoders)
     enc = EnsembleSynthesizer(mgc, bap, None)
+    gv = torch.rand(60, device=dev) + 0.5
     mine = sharding.assign([FRAMES] * args.songs, world)[rank]
     host = song_inputs(0, dev, args.encoders)   # same shapes for every song; contents re-seeded per song below (cheap host RNG is not timed)
 
@@ -102,13 +105,18 @@ def main():
         if ev: ev[2].record()
         b = bap.inference(cond_bap, cond_is_encoded=True)  # (6, 6000, 5)
         if ev: ev[3].record()
+        if args.postprocess:
+            m = postprocess.variance_scaling(gv, m, offset=2)
+            mb = postprocess.lowpass_filter(torch.cat([m, b], dim=-1), 200, cutoff=50)
+            m, b = mb[..., :60], mb[..., 60:]
         aux = torch.cat([m, b], dim=-1).transpose(1, 2)   # (6, 65, 6000) == vocoder frames at 5 ms
         aux = torch.nn.functional.pad(aux, (2, 2), mode="replicate").contiguous()
         wav = voc(sig, aux, d, wave_only=True)[0]
         if ev: ev[4].record()
         out = wav.cpu()                                   # D2H of the 6 waveforms
         if ev:
-            names = ["h2d", "encoders + mgc diffusion" if args.encoders else "mgc diffusion", "bap diffusion", "vocoder"]
+            names = ["h2d", "encoders + mgc diffusion" if args.encoders else "mgc diffusion", "bap diffusion",
+                     "postprocess + vocoder" if args.postprocess else "vocoder"]
             phases.update({n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(names)})
         return out
 
@@ -134,7 +142,7 @@ def main():
                           "seconds": sec, "wall_seconds_rank0": wall, "scaling": "strong",
                           "ms_per_song_rank0": 1e3 * sec / max(1, len(mine)), "gpu_launches_rank0": _lib.launch_count - n0,
                           "config": {"workload": f"{args.songs} songs x {TRACKS} tracks x {SECONDS:.0f} s, K=100, 24 kHz",
-                                     "encoders": bool(args.encoders)},
+                                     "encoders": bool(args.encoders), "postprocess": bool(args.postprocess)},
                           **({"phases_ms_last_song": phases} if args.breakdown else {})}))
     if world > 1:
         dist.destroy_process_group()
