@@ -45,6 +45,19 @@ def plan_batches(lengths: Sequence[int], max_frames: int, world_size: int = 1, r
     return [BatchPlan(items=list(b), frames=max(padded[i] for i in b)) for b in sharding.batches(mine, padded, max_frames)]
 
 
+def pair_items(utt_ids: Sequence[str]) -> List[tuple]:
+    """The (main, interacting) utterance pairs the reference synthesises, in its order, without its O(N^2) scan.
+
+    ``synthesis_multitrack.py:113-118`` walks every ordered pair of utterance ids ``<singer>_<segment...>`` and keeps those
+    whose segment part (everything after the first ``_``) is equal — a track paired with every track of the same
+    segment, itself included.  Here the ids are bucketed by segment once and the pairs are emitted bucket-wise in the
+    same order (outer id in list order, inner ids in list order)."""
+    buckets = {}
+    for u in utt_ids:
+        buckets.setdefault(tuple(u.split("_")[1:]), []).append(u)
+    return [(u0, u1) for u0 in utt_ids for u1 in buckets[tuple(u0.split("_")[1:])]]
+
+
 def _pad_time(x: torch.Tensor, frames: int, mode: str) -> torch.Tensor:
     """x [T, C] -> [frames, C]; ``replicate`` repeats the last frame (the reference's pad_inference), ``zeros`` appends 0."""
     T = x.shape[0]

@@ -189,3 +189,13 @@ def test_postprocess_filter_design_matches_scipy():
         butter_lowpass(5, 1.0)
     with pytest.raises(RuntimeError, match="CUDA"):
         lowpass_filter(torch.zeros(1, 40, 3), 200, cutoff=50)
+
+
+def test_pipeline_pair_items_matches_reference_double_loop():
+    """Row f3: same pairs, same order as the scan of nnsvs/bin/synthesis_multitrack.py:113-118."""
+    from ensemble_svs_with_interactions_b200.pipeline import pair_items
+    ids = ["alto_song1_seg0", "bass_song1_seg0", "alto_song1_seg1", "sop_song1_seg0", "bass_song2_seg0", "ritsu_song1_seg1", "solo"]
+    brute = [(a, b) for a in ids for b in ids if a.split("_")[1:] == b.split("_")[1:]]
+    assert pair_items(ids) == brute
+    assert ("alto_song1_seg0", "alto_song1_seg0") in brute and ("solo", "solo") in brute and len(brute) == 3 * 3 + 2 * 2 + 1 + 1
+    assert pair_items([]) == []
