@@ -1095,6 +1095,29 @@ def test_ffconvlstm_recipe_shape_both_precisions(H, spk):
     close_bf16(yb, ref)
 
 
+@pytest.mark.parametrize("B,T,lengths", [(1, 5, [5]), (2, 129, [77, 129]), (3, 40, [9, 40, 23])])
+def test_ffconvlstm_odd_shapes_and_default_widths(B, T, lengths):
+    """Model-default widths (ff 2048 / conv 1024 / H 256: eight 256-channel output blocks per GEMM, K up to 7 x 2048),
+    shortest legal sequence, tile tails, lengths in any order (the reference needs them sorted, model.py:916)."""
+    from ensemble_svs_with_interactions_b200.model import FFConvLSTM
+    g = torch.Generator().manual_seed(B * 100 + T)
+    torch.manual_seed(B + T)
+    m = FFConvLSTM(44, out_dim=67).eval()              # everything else at its default
+    for k, v in m.state_dict().items():
+        if k.endswith("running_mean"):
+            v.copy_(torch.randn(v.shape, generator=g) * 0.2)
+        elif k.endswith("running_var"):
+            v.copy_(torch.rand(v.shape, generator=g) + 0.5)
+    x = torch.randn(B, T, 44, generator=g)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    ref = O.ffconvlstm_forward(sd, x, lengths)
+    m = m.to(DEV)
+    assert m.resolved_precision() == "bf16"
+    close_bf16(m(x.to(DEV), lengths), ref)
+    m.precision = "fp32"
+    close32(m(x.to(DEV), torch.tensor(lengths)), ref)
+
+
 def test_gaussian_diffusion_with_encoder():
     """GaussianDiffusion(encoder=FFConvLSTM) end to end (diffusion.py:283-284): the encoder output is the cond of the sampler."""
     from ensemble_svs_with_interactions_b200.diffsinger import DiffNet, GaussianDiffusion
