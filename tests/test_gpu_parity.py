@@ -1002,6 +1002,20 @@ def test_lstm_recurrence_matches_oracle(H, layout):
     assert torch.count_nonzero(h32[1, :, 37:]) == 0 and torch.count_nonzero(hb[2, 1:]) == 0
 
 
+def test_lstm_recurrence_long_sequence_no_drift():
+    """3000 dependent steps (15 s of frames), H = 128: the ex2 / rcp gate activations must not drift from the oracle's
+    exact ones; same tolerance as the short case."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(99)
+    H, T = 128, 3000
+    pre = torch.randn(1, T, 8 * H, generator=g)
+    w_hh = torch.randn(2, 4 * H, H, generator=g) * (1.0 / math.sqrt(H))
+    ref = torch.cat([O.lstm_direction(pre[0, :, d * 4 * H:(d + 1) * 4 * H], w_hh[d], T, d == 1) for d in range(2)], -1)
+    h32 = torch.empty((1, 2 * H, T), device=DEV)
+    ops.lstm_f32(pre.to(DEV), w_hh.to(DEV), None, H, pre_layout="ntc", h_f32=h32)
+    close32(h32[0].t(), ref)
+
+
 def test_lstm_rejects_unsupported_hidden_size():
     ops = _ops()
     assert not ops.lstm_supported(200) and not ops.lstm_supported(512) and ops.lstm_supported(256)

@@ -44,4 +44,21 @@ for name, kw in (("fixed", dict(dilation=8)), ("adaptive", dict(idx=idx))):
             bad += 1
             print(f"usfgan {name}: run {it} differs", flush=True)
     print(f"usfgan {name}: {n} runs", flush=True)
+# LSTM recurrence (cross-CTA st.async hand-off every step), ragged lengths, many clusters in flight
+for H in (64, 128, 256, 160):
+    B, T = 9, 700
+    g = torch.Generator().manual_seed(H)
+    pre = torch.randn(B, T, 8 * H, generator=g).cuda()
+    w_hh = (torch.randn(2, 4 * H, H, generator=g) / H ** 0.5).cuda()
+    lens = torch.tensor([700, 699, 512, 300, 257, 256, 100, 3, 1], dtype=torch.int32, device="cuda")
+    ref = None
+    for it in range(n):
+        h = torch.full((B, 2 * H, T), float("nan"), device="cuda")
+        ops.lstm_f32(pre, w_hh, lens, H, pre_layout="ntc", h_f32=h)
+        if ref is None:
+            ref = h.clone()
+        elif not torch.equal(h, ref):
+            bad += 1
+            print(f"lstm H={H}: run {it} differs", flush=True)
+    print(f"lstm H={H}: {n} runs, finite={bool(torch.isfinite(ref).all())}", flush=True)
 print("mismatching runs:", bad)
