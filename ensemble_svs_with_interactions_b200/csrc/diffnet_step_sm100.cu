@@ -12,6 +12,7 @@
 // The weight region holds Wskip first (C/64 tiles of C rows), then Wout (C/64 tiles of Mp rows) and Win (ceil(Mp/64)
 // tiles of C rows), TMA-loaded as soon as GEMM-a has completed.
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "sm100_ptx.cuh"
 #include "svsk_common.cuh"
