@@ -146,6 +146,16 @@ variance_scaling_kernel(const float* __restrict__ x, float* __restrict__ y, cons
   }
 }
 
+// y[r][d] = mode 0: x * a[d] + b[d]   |   mode 1: (x - b[d]) / a[d]      (feature scalers, nnsvs/util.py:288-292,335-339)
+__global__ void scale_features_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ a,
+                                      const float* __restrict__ b, int mode, long long n, int D) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const float v = x[i];
+    y[i] = mode == 0 ? v * a[d] + b[d] : (v - b[d]) / a[d];
+  }
+}
+
 }  // namespace svsk
 
 using namespace svsk;
@@ -182,4 +192,13 @@ extern "C" int svsk_variance_scaling_f32(const float* x, float* y, const float* 
   dim3 grid((unsigned)((D + 63) / 64), (unsigned)B);
   variance_scaling_kernel<<<grid, dim3(64, kVsSlices), 0, as_stream(stream)>>>(x, y, gv, note_mask, lengths, offset, B, T, D);
   return check_launch("variance_scaling_f32");
+}
+
+extern "C" int svsk_scale_features_f32(const float* x, float* y, const float* a, const float* b, int mode, long long rows, int D,
+                                       void* stream) {
+  SVSK_REQUIRE(x && y && a && b && rows > 0 && D > 0 && (mode == 0 || mode == 1), SVSK_E_ARG, "scale_features_f32: bad args");
+  const long long n = rows * D;
+  const unsigned grid = (unsigned)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  scale_features_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, y, a, b, mode, n, D);
+  return check_launch("scale_features_f32");
 }

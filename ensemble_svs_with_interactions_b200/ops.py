@@ -498,3 +498,12 @@ def variance_scaling_f32(x, gv, *, offset=2, note_mask=None, lengths=None, out=N
                                               L.ptr(note_mask, torch.uint8, "note_mask"), L.ptr(lengths, torch.int32, "lengths"),
                                               int(offset), B, T, D, L.stream_ptr()), "variance_scaling_f32")
     return out
+
+
+def scale_features_f32(x, a, b, mode, out=None):
+    """svsk_scale_features_f32 over the last dimension of x (fp32, contiguous): mode 0 x*a+b, mode 1 (x-b)/a."""
+    D = x.shape[-1]
+    out = torch.empty_like(x) if out is None else out
+    L.check(L.lib().svsk_scale_features_f32(L.ptr(x, f32, "x"), L.ptr(out, f32, "out"), L.ptr(a, f32, "a"), L.ptr(b, f32, "b"), int(mode),
+                                            x.numel() // D, D, L.stream_ptr()), "scale_features_f32")
+    return out

@@ -80,16 +80,20 @@ class EnsembleSynthesizer:
     smoothing_cutoff: Hz, or None — ``trajectory_smoothing`` of gen.postprocess_acoustic (its default: 50 at
     ``frame_rate`` = 200 frames per second) applied to both streams.
     gv_mgc: global variance of the mgc stream [M1] (the scaler's ``var_``), or None — the GV post-filter, applied to
-    the frames marked in ``note_masks`` (all valid frames when no masks are given), dimensions >= ``gv_offset``."""
+    the frames marked in ``note_masks`` (all valid frames when no masks are given), dimensions >= ``gv_offset``.
+    out_scaler_mgc / out_scaler_bap: ``postprocess.StandardScaler`` / ``MinMaxScaler`` whose ``inverse_transform`` takes
+    the streams back to feature units right after sampling (gen.py:1145); vocoder_in_scaler: its ``transform`` is applied
+    to the assembled aux features (gen.predict_waveform).  All on the device."""
 
     def __init__(self, mgc, bap, vocoder, max_frames: int = 36000,
                  aux_fn: Optional[Callable[[torch.Tensor, torch.Tensor, torch.Tensor], torch.Tensor]] = None,
                  smoothing_cutoff: Optional[float] = None, frame_rate: int = 200, gv_mgc: Optional[torch.Tensor] = None,
-                 gv_offset: int = 2):
+                 gv_offset: int = 2, out_scaler_mgc=None, out_scaler_bap=None, vocoder_in_scaler=None):
         self.mgc, self.bap, self.vocoder = mgc, bap, vocoder
         self.max_frames = int(max_frames)
         self.smoothing_cutoff, self.frame_rate = smoothing_cutoff, int(frame_rate)
         self.gv_mgc, self.gv_offset = gv_mgc, int(gv_offset)
+        self.out_scaler_mgc, self.out_scaler_bap, self.vocoder_in_scaler = out_scaler_mgc, out_scaler_bap, vocoder_in_scaler
         self.aux_fn = aux_fn if aux_fn is not None else (lambda m, b, f0: torch.cat([m, b], dim=-1))
         self._side = None
 
@@ -135,6 +139,10 @@ class EnsembleSynthesizer:
             hm, hb = self._encode(cm, cb, lens)
             m = self.mgc.inference(hm, cond_is_encoded=True)   # [B, T, M1]
             b = self.bap.inference(hb, cond_is_encoded=True)   # [B, T, M2]
+            if self.out_scaler_mgc is not None:
+                m = self.out_scaler_mgc.inverse_transform(m)
+            if self.out_scaler_bap is not None:
+                b = self.out_scaler_bap.inverse_transform(b)
             if self.gv_mgc is not None:                        # gen.py:1394-1418
                 mask = None
                 if note_masks is not None:
@@ -145,7 +153,10 @@ class EnsembleSynthesizer:
                 M1 = m.shape[-1]                               # one launch for both streams: every trajectory is independent
                 mb = postprocess.lowpass_filter(torch.cat([m, b], dim=-1), self.frame_rate, cutoff=self.smoothing_cutoff, lengths=lens)
                 m, b = mb[..., :M1], mb[..., M1:]
-            wav = self.vocoder.inference_batch(f, self.aux_fn(m, b, f).contiguous())   # [B, 1, T * hop]
+            aux = self.aux_fn(m, b, f).contiguous()
+            if self.vocoder_in_scaler is not None:
+                aux = self.vocoder_in_scaler.transform(aux)
+            wav = self.vocoder.inference_batch(f, aux)       # [B, 1, T * hop]
             for k, i in enumerate(plan.items):
                 out[i] = wav[k, 0, :lengths[i] * hop].clone()
         return out

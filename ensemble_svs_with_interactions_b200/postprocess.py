@@ -22,7 +22,7 @@ import torch
 
 from . import ops
 
-__all__ = ["variance_scaling", "lowpass_filter", "butter_lowpass", "lfilter_zi"]
+__all__ = ["variance_scaling", "lowpass_filter", "butter_lowpass", "lfilter_zi", "StandardScaler", "MinMaxScaler"]
 
 
 @lru_cache(maxsize=64)
@@ -95,3 +95,46 @@ def variance_scaling(gv: torch.Tensor, feats: torch.Tensor, offset: int = 2, not
             raise ValueError(f"note_mask must be [B, T] = {(B, T)}, got {tuple(note_mask.shape)}")
         note_mask = note_mask.to(feats.device).to(torch.uint8).contiguous()
     return ops.variance_scaling_f32(feats, gv, offset=offset, note_mask=note_mask, lengths=_lengths(lengths, B, feats.device))
+
+
+def _vec(v, device, D, what):
+    t = torch.as_tensor(np.asarray(v, dtype=np.float64) if not torch.is_tensor(v) else v).to(torch.float32).reshape(-1).to(device).contiguous()
+    if t.numel() != D:
+        raise ValueError(f"{what} must have one entry per feature ({D}), got {t.numel()}")
+    return t
+
+
+class _Scaler:
+    def _apply(self, x, a, b, mode):
+        if not x.is_cuda:
+            raise RuntimeError("scaler: features must be a CUDA tensor (libsvsk has no CPU path)")
+        x = x.detach().float().contiguous()
+        D = x.shape[-1]
+        return ops.scale_features_f32(x, _vec(a, x.device, D, "scale"), _vec(b, x.device, D, "offset"), mode)
+
+
+class StandardScaler(_Scaler):
+    """nnsvs/util.py:272-292 on CUDA tensors [..., D]: transform (x - mean_) / scale_, inverse_transform x * scale_ + mean_."""
+
+    def __init__(self, mean, var, scale):
+        self.mean_, self.var_, self.scale_ = mean, var, scale
+
+    def transform(self, x):
+        return self._apply(x, self.scale_, self.mean_, 1)
+
+    def inverse_transform(self, x):
+        return self._apply(x, self.scale_, self.mean_, 0)
+
+
+class MinMaxScaler(_Scaler):
+    """nnsvs/util.py:316-339: transform scale_ * x + min_, inverse_transform (x - min_) / scale_."""
+
+    def __init__(self, min, scale, data_min=None, data_max=None, feature_range=(0, 1)):
+        self.min_, self.scale_ = min, scale
+        self.data_min_, self.data_max_, self.feature_range = data_min, data_max, feature_range
+
+    def transform(self, x):
+        return self._apply(x, self.scale_, self.min_, 0)
+
+    def inverse_transform(self, x):
+        return self._apply(x, self.scale_, self.min_, 1)

@@ -417,6 +417,12 @@ SVSK_API int svsk_filtfilt_f32(const float* x, float* y, double* scratch, const 
  * y = sqrt(gv[d] / var) * (x - mean) + mean on those frames for d >= offset; everything else is copied.  x, y [B][T][D]. */
 SVSK_API int svsk_variance_scaling_f32(const float* x, float* y, const float* gv, const uint8_t* note_mask,
                                        const int32_t* lengths, int offset, int B, int T, int D, void* stream);
+/* Feature scalers between the models (nnsvs/util.py:272-340; gen.py:1145 inverse_transform of the acoustic output,
+ * gen.py predict_waveform: transform of the vocoder input): per-feature affine maps over x [rows][D] (y may alias x).
+ * mode 0: y = x * a[d] + b[d]  (StandardScaler.inverse_transform with a = scale_, b = mean_; MinMaxScaler.transform with
+ * a = scale_, b = min_);  mode 1: y = (x - b[d]) / a[d]  (StandardScaler.transform; MinMaxScaler.inverse_transform). */
+SVSK_API int svsk_scale_features_f32(const float* x, float* y, const float* a, const float* b, int mode, long long rows, int D,
+                                     void* stream);
 
 #ifdef __cplusplus
 }

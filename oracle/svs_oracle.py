@@ -685,3 +685,15 @@ def lowpass_filter(x: np.ndarray, fs: int, cutoff: float = 5, N: int = 5) -> np.
     if len(x) <= max(len(a), len(b)) * (N // 2 + 1):
         return x
     return filtfilt(b, a, x)
+
+
+def standard_scaler(x: np.ndarray, mean: np.ndarray, scale: np.ndarray, inverse: bool) -> np.ndarray:
+    """nnsvs/util.py:288-292 (StandardScaler.transform / inverse_transform).  PARITY UNPINNED for this two-line
+    arithmetic: nnsvs.util cannot be imported in the build container (pyworld, hydra, omegaconf), so no fixture was
+    generated from the reference class."""
+    return x * scale + mean if inverse else (x - mean) / scale
+
+
+def minmax_scaler(x: np.ndarray, min_: np.ndarray, scale: np.ndarray, inverse: bool) -> np.ndarray:
+    """nnsvs/util.py:335-339 (MinMaxScaler.transform / inverse_transform).  PARITY UNPINNED, as above."""
+    return (x - min_) / scale if inverse else scale * x + min_

@@ -968,11 +968,17 @@ def test_pipeline_with_encoders_matches_sequential_calls():
     from ensemble_svs_with_interactions_b200 import postprocess as pp
     gv = torch.rand(60, generator=g) + 0.5
     notes = [torch.rand(n, generator=g) > 0.3 for n in lens]
-    synth2 = EnsembleSynthesizer(mgc, bap, Voc(), max_frames=1000, smoothing_cutoff=50, gv_mgc=gv)
+    sc_mean, sc_scale = torch.randn(60, generator=g).numpy().astype(np.float64), (torch.rand(60, generator=g) + 0.5).numpy().astype(np.float64)
+    vin_mean, vin_scale = torch.randn(65, generator=g).numpy().astype(np.float64), (torch.rand(65, generator=g) + 0.5).numpy().astype(np.float64)
+    synth2 = EnsembleSynthesizer(mgc, bap, Voc(), max_frames=1000, smoothing_cutoff=50, gv_mgc=gv,
+                                 out_scaler_mgc=pp.StandardScaler(sc_mean, sc_scale ** 2, sc_scale),
+                                 vocoder_in_scaler=pp.StandardScaler(vin_mean, vin_scale ** 2, vin_scale))
     torch.manual_seed(5)
     synth2.synthesize(ling, ling, f0, note_masks=notes)
+    seen["aux"] = torch.from_numpy(O.standard_scaler(seen["aux"].cpu().double().numpy(), vin_mean, vin_scale, True)).float()  # undo the vocoder scaler
     for i, n in enumerate(lens):
-        ref = O.variance_scaling(gv.double().numpy(), m[i, :n].cpu().double().numpy(), 2, np.nonzero(notes[i].numpy())[0])
+        mi = O.standard_scaler(m[i, :n].cpu().double().numpy(), sc_mean, sc_scale, True)
+        ref = O.variance_scaling(gv.double().numpy(), mi, 2, np.nonzero(notes[i].numpy())[0])
         ref = np.stack([O.lowpass_filter(ref[:, d], 200, cutoff=50) for d in range(60)], 1)
         close32(seen["aux"][i, :n, :60], torch.from_numpy(ref), tol=2e-5)
         refb = np.stack([O.lowpass_filter(b[i, :n, d].cpu().double().numpy(), 200, cutoff=50) for d in range(5)], 1)
@@ -1193,3 +1199,21 @@ def test_variance_scaling_matches_reference_golden():
     ref = O.variance_scaling(gv.double().numpy(), x[:250].double().numpy(), 2)
     close32(y2[0, :250], torch.from_numpy(ref), tol=1e-5)
     assert torch.equal(y2[0, 250:], x[250:])
+
+
+def test_feature_scalers_match_oracle():
+    """postprocess.StandardScaler / MinMaxScaler (util.py:272-340) on the device against the numpy arithmetic (float64)."""
+    from ensemble_svs_with_interactions_b200.postprocess import MinMaxScaler, StandardScaler
+    g = np.random.RandomState(3)
+    x = g.randn(3, 50, 65)
+    mean, scale = g.randn(65), g.rand(65) + 0.5
+    xs = torch.from_numpy(x).float().to(DEV)
+    st = StandardScaler(mean, scale ** 2, scale)
+    close32(st.transform(xs), torch.from_numpy(O.standard_scaler(x, mean, scale, False)), tol=2e-6)
+    close32(st.inverse_transform(xs), torch.from_numpy(O.standard_scaler(x, mean, scale, True)), tol=2e-6)
+    mm = MinMaxScaler(mean, scale)
+    close32(mm.transform(xs), torch.from_numpy(O.minmax_scaler(x, mean, scale, False)), tol=2e-6)
+    close32(mm.inverse_transform(xs), torch.from_numpy(O.minmax_scaler(x, mean, scale, True)), tol=2e-6)
+    close32(st.inverse_transform(st.transform(xs)), xs, tol=2e-6)
+    with pytest.raises(ValueError):
+        StandardScaler(mean[:3], None, scale[:3]).transform(xs)
