@@ -93,11 +93,37 @@ def main():
     host = song_inputs(0, dev, args.encoders)   # same shapes for every song; contents re-seeded per song below (cheap host RNG is not timed)
 
     phases = {}   # --breakdown: ms per phase of the last song (events around the three models)
+    # Host <-> device traffic runs on its own stream, double-buffered: the inputs of song k+1 are uploaded and the
+    # waveforms of song k-1 are downloaded (into pinned memory) while song k computes, and the host never blocks inside
+    # the loop, so its ~700 kernel launches per song are issued ahead of the GPU.
+    copy = torch.cuda.Stream(device=dev)
+    dev_in = [None, None]      # uploaded inputs of the next song + the event that marks them complete
+    pinned_out = [torch.empty((TRACKS, 1, VFRAMES * HOP), dtype=torch.float32).pin_memory() for _ in range(2)]
+    out_done = [None, None]
+    count = [0]
+
+    def upload(slot):
+        with torch.cuda.stream(copy):
+            tensors = [t.to(dev, non_blocking=True) for t in host]
+            e = torch.cuda.Event()
+            e.record(copy)
+        dev_in[slot] = (tensors, e)
 
     def synth(song):
+        k = count[0]
+        count[0] += 1
+        main = torch.cuda.current_stream()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if args.breakdown else None
         if ev: ev[0].record()
-        cond_mgc, cond_bap, d, sig = (t.to(dev, non_blocking=True) for t in host)
+        if dev_in[k & 1] is None:
+            upload(k & 1)
+        tensors, e_in = dev_in[k & 1]
+        dev_in[k & 1] = None
+        main.wait_event(e_in)
+        for t in tensors:
+            t.record_stream(main)
+        cond_mgc, cond_bap, d, sig = tensors
+        upload((k + 1) & 1)                               # next song's inputs, behind this song's compute
         if ev: ev[1].record()
         if args.encoders:                                 # both encoders side by side (pipeline.EnsembleSynthesizer._encode)
             cond_mgc, cond_bap = enc._encode(cond_mgc, cond_bap, [FRAMES] * TRACKS)
@@ -113,8 +139,19 @@ def main():
         aux = torch.nn.functional.pad(aux, (2, 2), mode="replicate").contiguous()
         wav = voc(sig, aux, d, wave_only=True)[0]
         if ev: ev[4].record()
-        out = wav.cpu()                                   # D2H of the 6 waveforms
+        if out_done[k & 1] is not None:
+            out_done[k & 1].synchronize()                 # the pinned buffer of two songs ago has long been written
+        e_wav = torch.cuda.Event()
+        e_wav.record(main)
+        with torch.cuda.stream(copy):
+            copy.wait_event(e_wav)
+            pinned_out[k & 1].copy_(wav, non_blocking=True)   # D2H of the 6 waveforms
+            out_done[k & 1] = torch.cuda.Event()
+            out_done[k & 1].record(copy)
+        wav.record_stream(copy)
+        out = pinned_out[k & 1]
         if ev:
+            ev[4].synchronize()
             names = ["h2d", "encoders + mgc diffusion" if args.encoders else "mgc diffusion", "bap diffusion",
                      "postprocess + vocoder" if args.postprocess else "vocoder"]
             phases.update({n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(names)})
@@ -131,6 +168,7 @@ def main():
     e0.record()
     for s in mine:
         synth(s)
+    torch.cuda.current_stream().wait_stream(copy)         # the last downloads are part of the job
     e1.record()
     e1.synchronize()
     sec = sharding.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
