@@ -76,6 +76,21 @@ class _GeneratorBase(nn.Module):
         x = _conv1x1(self.conv_last[1], x, in_relu=True)
         return _conv1x1(self.conv_last[3], x, in_relu=True)
 
+    def _conv_last_ntc_bf16(self, yb_relu):
+        """conv_last on an NTC bf16 tensor that already went through the leading ReLU: 1x1 (tensor cores, ReLU fused)
+        then the C -> 1 projection.  Returns (B, 1, T) fp32."""
+        l1, l3 = self.conv_last[1], self.conv_last[3]
+        key = tuple((p.data_ptr(), p._version) for p in self.conv_last.parameters())
+        if getattr(self, "_last_key", None) != key:
+            with torch.no_grad():
+                self._last_plan = (ops.conv1d_pack_bf16(effective_weight(l1).to(f32).contiguous()),
+                                   l1.bias.detach().to(f32).contiguous(),
+                                   effective_weight(l3).to(f32).reshape(-1).contiguous(), float(l3.bias.detach()[0]))
+            self._last_key = key
+        wp, b1, w2, b2 = self._last_plan
+        hb = ops.conv1d_bf16(yb_relu, wp, b1, l1.out_channels, 1, act=ops.ACT_RELU)
+        return ops.dot_rows_bf16(hb, w2, b2).unsqueeze(1)
+
     @staticmethod
     def _check(x):
         if not x.is_cuda:
@@ -133,6 +148,22 @@ class USFGANGenerator(_GeneratorBase):
         """x (B,1,T), c (B,C,T'), d (B,1,T) -> (x, s)   (generator.py:113-144)."""
         self._check(x)
         cache = {}
+        l1, l3 = self.conv_last[1], self.conv_last[3]
+        if (self.resolved_precision() == "bf16" and self.in_channels == 1 and l3.out_channels == 1 and l1.in_channels % 8 == 0
+                and l1.out_channels % 16 == 0):
+            # everything stays NTC bf16 (as in ParallelHnUSFGANGenerator's wave-only path): aux features upsampled straight
+            # into that layout, the 1 -> C convs write it directly, conv_last runs on the tensor cores
+            if self.upsample_net.supports_fused():
+                auxb = self.upsample_net.forward_ntc_bf16(c)
+            else:
+                auxb = self._aux_ntc(self.upsample_net(c))
+            assert auxb.size(1) == x.size(-1)
+            xb = _conv1x1_expand_ntc(self.conv_first, x.to(f32).contiguous()[:, 0])
+            yb = self.source_network.forward_ntc_bf16(xb, auxb, d, cache, relu_last=True)
+            s = self._conv_last_ntc_bf16(yb)
+            xb = _conv1x1_expand_ntc(self.conv_mid, s[:, 0])
+            yb = self.filter_network.forward_ntc_bf16(xb, auxb, d, cache, relu_last=True)
+            return self._conv_last_ntc_bf16(yb), s
         c = self.upsample_net(c)
         assert c.size(-1) == x.size(-1)
         auxb = self._aux_ntc(c)
@@ -179,21 +210,6 @@ class _HnBase(_GeneratorBase):
         sine, noise = x[:, 0:1].contiguous(), x[:, 1:2].contiguous()
         return c, a, _conv1x1(self.conv_first_sine, sine), _conv1x1(self.conv_first_noise, noise)
 
-    def _conv_last_ntc_bf16(self, yb_relu):
-        """conv_last on an NTC bf16 tensor that already went through the leading ReLU: 1x1 (tensor cores, ReLU fused)
-        then the C -> 1 projection.  Returns (B, 1, T) fp32."""
-        l1, l3 = self.conv_last[1], self.conv_last[3]
-        key = tuple((p.data_ptr(), p._version) for p in self.conv_last.parameters())
-        if getattr(self, "_last_key", None) != key:
-            with torch.no_grad():
-                self._last_plan = (ops.conv1d_pack_bf16(effective_weight(l1).to(f32).contiguous()),
-                                   l1.bias.detach().to(f32).contiguous(),
-                                   effective_weight(l3).to(f32).reshape(-1).contiguous(), float(l3.bias.detach()[0]))
-            self._last_key = key
-        wp, b1, w2, b2 = self._last_plan
-        hb = ops.conv1d_bf16(yb_relu, wp, b1, l1.out_channels, 1, act=ops.ACT_RELU)
-        return ops.dot_rows_bf16(hb, w2, b2).unsqueeze(1)
-
     def _ntc_fast_path_ok(self):
         l1, l3 = self.conv_last[1], self.conv_last[3]
         pe_ok = self.periodicity_estimator.supports_bf16() and \
@@ -236,6 +252,31 @@ class CascadeHnUSFGANGenerator(_HnBase):
         """(x, s, h, n, a)   (generator.py:283-334): harmonic -> a*h -> merge with noise input -> noise net."""
         self._check(x)
         cache = {}
+        if wave_only and self._ntc_fast_path_ok() and self.conv_merge.in_channels % 8 == 0 and self.conv_merge.out_channels % 16 == 0:
+            # NTC bf16 throughout, like ParallelHnUSFGANGenerator's wave-only path.  s = a h + (1 - a) n is formed from the
+            # two stacks' raw outputs in one pass; a h alone is only needed as the merge conv's input.
+            if self.upsample_net.supports_fused():
+                auxb = self.upsample_net.forward_ntc_bf16(c)
+            else:
+                auxb = self._aux_ntc(self.upsample_net(c))
+            assert auxb.size(1) == x.size(-1)
+            ab = self.periodicity_estimator.forward_ntc_bf16(auxb)
+            xf = x.to(f32).contiguous()
+            hb = _conv1x1_expand_ntc(self.conv_first_sine, xf[:, 0])
+            nb = _conv1x1_expand_ntc(self.conv_first_noise, xf[:, 1])
+            hb = self.harmonic_network.forward_ntc_bf16(hb, auxb, d, cache)
+            zeros = torch.zeros_like(hb)
+            hm = ops.periodic_mix_bf16(ab, hb, zeros)                       # a * h
+            key = tuple((p.data_ptr(), p._version) for p in self.conv_merge.parameters())
+            if getattr(self, "_merge_key", None) != key:
+                self._merge_plan = (ops.conv1d_pack_bf16(effective_weight(self.conv_merge).to(f32).contiguous()),
+                                    self.conv_merge.bias.detach().to(f32).contiguous())
+                self._merge_key = key
+            nb = ops.conv1d_bf16(torch.cat([hm, nb], dim=2), self._merge_plan[0], self._merge_plan[1], self.conv_merge.out_channels, 1)
+            nb = self.noise_network.forward_ntc_bf16(nb, auxb, d, cache)
+            sb = ops.periodic_mix_bf16(ab, hb, nb)                          # a * h + (1 - a) * n
+            yb = self.filter_network.forward_ntc_bf16(sb, auxb, d, cache, relu_last=True)
+            return self._conv_last_ntc_bf16(yb), None, None, None, ab
         c, a, h, n = self._front(x, c)
         auxb = self._aux_ntc(c)
         h = self._run_stack(self.harmonic_network, h, c, d, cache, auxb)

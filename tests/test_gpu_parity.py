@@ -1217,3 +1217,54 @@ def test_feature_scalers_match_oracle():
     close32(st.inverse_transform(st.transform(xs)), xs, tol=2e-6)
     with pytest.raises(ValueError):
         StandardScaler(mean[:3], None, scale[:3]).transform(xs)
+
+
+def test_plain_usfgan_default_widths_bf16_fast_path():
+    """USFGANGenerator at its default widths (64 / 128 / 64, aux 80 — BASELINE config 3's second generator): the NTC bf16
+    path (fused upsampler, 1 -> C convs channel-last, conv_last on tcgen05) against the fp32 kernels; both outputs."""
+    from ensemble_svs_with_interactions_b200.usfgan.models import USFGANGenerator
+    torch.manual_seed(8)
+    m = USFGANGenerator(source_network_params={"blockA": 4, "cycleA": 2, "blockF": 0, "cycleF": 0, "cascade_mode": 0},
+                        filter_network_params={"blockA": 0, "cycleA": 0, "blockF": 4, "cycleF": 2, "cascade_mode": 0}).eval()
+    m.remove_weight_norm()
+    m = m.to(DEV)
+    g = torch.Generator().manual_seed(9)
+    Fr, hop = 30, 120
+    c = torch.randn(2, 80, Fr + 4, generator=g).to(DEV)
+    f0 = torch.empty(2, 1, Fr).uniform_(110, 880, generator=g)
+    d = (24000 / (f0 * 4)).repeat_interleave(hop, dim=-1).to(DEV)
+    x = (torch.randn(2, 1, Fr * hop, generator=g) * 0.1).to(DEV)
+    m.precision = "fp32"
+    y32, s32 = m(x, c, d)
+    m.precision = "bf16"
+    yb, sb = m(x, c, d)
+    assert yb.shape == y32.shape == (2, 1, Fr * hop) and sb.shape == s32.shape
+    close_bf16(sb, s32, l2=3e-2, mx=8e-2)
+    close_bf16(yb, y32, l2=4e-2, mx=1e-1)
+
+
+def test_cascade_usfgan_default_widths_wave_only_fast_path():
+    """CascadeHnUSFGANGenerator, wave-only NTC bf16 path against the fp32 kernels (default widths, short stacks)."""
+    from ensemble_svs_with_interactions_b200.usfgan.models import CascadeHnUSFGANGenerator
+    torch.manual_seed(18)
+    pe = {"conv_layers": 3, "kernel_size": 5, "dilation": 1, "padding_mode": "replicate"}
+    m = CascadeHnUSFGANGenerator(harmonic_network_params={"blockA": 4, "cycleA": 2, "blockF": 0, "cycleF": 0, "cascade_mode": 0},
+                                 noise_network_params={"blockA": 0, "cycleA": 0, "blockF": 2, "cycleF": 2, "cascade_mode": 0},
+                                 filter_network_params={"blockA": 0, "cycleA": 0, "blockF": 4, "cycleF": 2, "cascade_mode": 0},
+                                 periodicity_estimator_params=pe).eval()
+    with torch.no_grad():
+        m.periodicity_estimator.layers[-2].weight_v.normal_(0, 0.05)
+    m.remove_weight_norm()
+    m = m.to(DEV)
+    g = torch.Generator().manual_seed(19)
+    Fr, hop = 30, 120
+    c = torch.randn(2, 80, Fr + 4, generator=g).to(DEV)
+    f0 = torch.empty(2, 1, Fr).uniform_(110, 880, generator=g)
+    d = (24000 / (f0 * 4)).repeat_interleave(hop, dim=-1).to(DEV)
+    x = (torch.randn(2, 2, Fr * hop, generator=g) * 0.1).to(DEV)
+    m.precision = "fp32"
+    y32 = m(x, c, d, wave_only=True)[0]
+    m.precision = "bf16"
+    out = m(x, c, d, wave_only=True)
+    assert out[1] is None and out[0].shape == y32.shape == (2, 1, Fr * hop)
+    close_bf16(out[0], y32, l2=4e-2, mx=1e-1)
