@@ -1268,3 +1268,23 @@ def test_cascade_usfgan_default_widths_wave_only_fast_path():
     out = m(x, c, d, wave_only=True)
     assert out[1] is None and out[0].shape == y32.shape == (2, 1, Fr * hop)
     close_bf16(out[0], y32, l2=4e-2, mx=1e-1)
+
+
+def test_encoder_and_postprocess_entry_points_reject_bad_arguments():
+    """Loud failures of the newer C-ABI entry points (include/svsk.h): RuntimeError with the library's message."""
+    ops = _ops()
+    xb = torch.zeros(1, 40, 24, device=DEV, dtype=torch.bfloat16)
+    wp = ops.tapgemm_pack_bf16(torch.zeros(40, 24, 7, device=DEV))            # Cout = 40 is not a multiple of 16
+    with pytest.raises(RuntimeError, match="multiple of 16"):
+        ops.tapgemm_bf16(xb, wp, None, 24, T=34, y_f32=torch.zeros(1, 34, 40, device=DEV))
+    wp = ops.tapgemm_pack_bf16(torch.zeros(48, 24, 7, device=DEV))
+    with pytest.raises(RuntimeError, match="rows per track"):
+        ops.tapgemm_bf16(xb, wp, None, 24, T=40, y_f32=torch.zeros(1, 40, 48, device=DEV))   # needs T + 6 input rows
+    with pytest.raises(RuntimeError, match="T > pad"):
+        ops.reflect_pad_rows_bf16(torch.zeros(1, 9, 8, device=DEV, dtype=torch.bfloat16), 3, 3)
+    with pytest.raises(RuntimeError, match="order"):
+        ops.filtfilt_f32(torch.zeros(1, 64, 2, device=DEV), [1.0] * 10, [1.0] * 10, [0.0] * 9, min_len=30)
+    with pytest.raises(RuntimeError, match="must be contiguous|CUDA"):
+        ops.variance_scaling_f32(torch.zeros(1, 8, 4), torch.ones(4, device=DEV))
+    with pytest.raises(RuntimeError, match="one-hot block"):
+        ops.encoder_front(torch.zeros(4, 10, device=DEV), 8, 5, y_f32=torch.zeros(4, 10, device=DEV))
