@@ -1288,3 +1288,25 @@ def test_encoder_and_postprocess_entry_points_reject_bad_arguments():
         ops.variance_scaling_f32(torch.zeros(1, 8, 4), torch.ones(4, device=DEV))
     with pytest.raises(RuntimeError, match="one-hot block"):
         ops.encoder_front(torch.zeros(4, 10, device=DEV), 8, 5, y_f32=torch.zeros(4, 10, device=DEV))
+
+
+def test_multispeaker_ffconvlstm_forward():
+    """MultiSpeakerFFConvLSTM (model.py:929-1015): the embedding of ``spks`` is broadcast over time and added in front of
+    ``ff``; same numbers as the oracle with that tensor passed as ``spk_embs``; state_dict carries the embedding last."""
+    from ensemble_svs_with_interactions_b200.model import MultiSpeakerFFConvLSTM
+    torch.manual_seed(31)
+    emb = torch.nn.Embedding(3, 64)
+    m = MultiSpeakerFFConvLSTM(87, emb, ff_hidden_dim=64, conv_hidden_dim=32, lstm_hidden_dim=32, out_dim=48, in_ph_start_idx=3,
+                               in_ph_end_idx=50, embed_dim=64).eval()
+    assert list(m.state_dict().keys())[-1] == "speaker_embedding.weight"
+    g = torch.Generator().manual_seed(32)
+    B, T, lengths = 2, 60, [60, 44]
+    x = torch.randn(B, T, 87, generator=g)
+    x[..., 3:50] = torch.nn.functional.one_hot(torch.randint(0, 47, (B, T), generator=g), 47).float()
+    spks = torch.tensor([[2], [0]])
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items() if not k.startswith("speaker_embedding")}
+    ref = O.ffconvlstm_forward(sd, x, lengths, in_ph_start_idx=3, in_ph_end_idx=50, embed_dim=64, spk_embs=emb(spks).detach())
+    m = m.to(DEV)
+    close_bf16(m(x.to(DEV), spks.to(DEV), lengths), ref)
+    m.precision = "fp32"
+    close32(m.inference(x.to(DEV), spks.to(DEV), lengths), ref)
