@@ -211,6 +211,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vocoder", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the config-4 pipeline probe (N = 1 only)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -353,6 +354,14 @@ def main():
         if voc is not None:
             voc["value"] *= world   # one 6-track vocoder batch per rank, no collective
             line["vocoder"] = voc
+        if world == 1 and not args.no_pipeline:
+            # BASELINE configs[3] in short (tools/bench_pipeline.py has the full run): 6 songs of 6 tracks x 30 s through the
+            # FFConvLSTM encoders, both diffusion models, the device post-processing and the vocoder, host to host
+            from types import SimpleNamespace
+            from tools import bench_pipeline
+            pl = bench_pipeline.run(SimpleNamespace(songs=6, warmup_songs=2, encoders=True, postprocess=True, breakdown=False), 0, 1, dev)
+            line["pipeline"] = {k: pl[k] for k in ("metric", "value", "unit", "songs", "ms_per_song_rank0", "gpu_launches_rank0",
+                                                   "config")}
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample, dt = cpu_baseline(sample_steps=2)
             line["cpu_baseline"] = {"value": v, "unit": "frame-steps/s", "cores": cores, "kind": "port",

@@ -86,6 +86,15 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    line = run(args, rank, world, dev)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run(args, rank, world, dev):
+    """One measurement (args: songs, warmup_songs, encoders, postprocess, breakdown); returns the JSON line's dict on rank 0."""
     mgc, bap, voc = build(dev, args.encoders)
     enc = EnsembleSynthesizer(mgc, bap, None)
     gv = torch.rand(60, device=dev) + 0.5
@@ -173,17 +182,16 @@ def main():
     e1.synchronize()
     sec = sharding.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
     wall = time.perf_counter() - t0
-    if rank == 0:
-        audio = args.songs * TRACKS * SECONDS
-        print(json.dumps({"metric": "ensemble pipeline audio-sec/sec (mgc+bap diffusion + ParallelHn-uSFGAN)",
-                          "value": audio / sec, "unit": "audio-sec/s", "n_gpus": world, "songs": args.songs,
-                          "seconds": sec, "wall_seconds_rank0": wall, "scaling": "strong",
-                          "ms_per_song_rank0": 1e3 * sec / max(1, len(mine)), "gpu_launches_rank0": _lib.launch_count - n0,
-                          "config": {"workload": f"{args.songs} songs x {TRACKS} tracks x {SECONDS:.0f} s, K=100, 24 kHz",
-                                     "encoders": bool(args.encoders), "postprocess": bool(args.postprocess)},
-                          **({"phases_ms_last_song": phases} if args.breakdown else {})}))
-    if world > 1:
-        dist.destroy_process_group()
+    if rank != 0:
+        return None
+    audio = args.songs * TRACKS * SECONDS
+    return {"metric": "ensemble pipeline audio-sec/sec (mgc+bap diffusion + ParallelHn-uSFGAN)",
+            "value": audio / sec, "unit": "audio-sec/s", "n_gpus": world, "songs": args.songs,
+            "seconds": sec, "wall_seconds_rank0": wall, "scaling": "strong",
+            "ms_per_song_rank0": 1e3 * sec / max(1, len(mine)), "gpu_launches_rank0": _lib.launch_count - n0,
+            "config": {"workload": f"{args.songs} songs x {TRACKS} tracks x {SECONDS:.0f} s, K=100, 24 kHz",
+                       "encoders": bool(args.encoders), "postprocess": bool(args.postprocess)},
+            **({"phases_ms_last_song": phases} if args.breakdown else {})}
 
 
 if __name__ == "__main__":
