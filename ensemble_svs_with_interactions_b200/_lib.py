@@ -155,6 +155,7 @@ _SIGNATURES = {
     "svsk_filtfilt_f32": [_V, _V, _V, _V, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), _I, _I, _I, _I, _I, _I, _V],
     "svsk_variance_scaling_f32": [_V, _V, _V, _V, _V, _I, _I, _I, _I, _V],
     "svsk_scale_features_f32": [_V, _V, _V, _V, _I, C.c_longlong, _I, _V],
+    "svsk_mdn_head_f32": [_V, _V, _V, _V, _V, _V, C.c_longlong, _I, _I, _I, _V],
 }
 EXPORTED_SYMBOLS = ["svsk_last_error"] + list(_SIGNATURES)
 

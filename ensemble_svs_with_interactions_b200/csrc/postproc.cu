@@ -156,6 +156,37 @@ __global__ void scale_features_kernel(const float* __restrict__ x, float* __rest
   }
 }
 
+// MDN head (nnsvs/mdn.py:45-74,165-212), one thread per (row, output dim): raw [rows][ld] holds the three Linears' outputs
+// side by side ([log_pi | log_sigma | mu], G*D columns each, component-major).  Writes log_softmax over the G components
+// of log_pi and copies of the other two as [rows][G][D]; optionally the (sigma, mu) of the most probable component.
+__global__ void mdn_head_kernel(const float* __restrict__ raw, float* __restrict__ log_pi, float* __restrict__ log_sigma,
+                                float* __restrict__ mu, float* __restrict__ best_sigma, float* __restrict__ best_mu, long long rows,
+                                int G, int D, int ld) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= rows * D) return;
+  const long long r = i / D;
+  const int d = (int)(i % D);
+  const float* p = raw + r * ld + d;
+  float mx = -INFINITY;
+  int best = 0;
+  for (int g = 0; g < G; ++g) {
+    const float v = p[(size_t)g * D];
+    if (v > mx) { mx = v; best = g; }      // first maximum, like torch.max
+  }
+  float sum = 0.f;
+  for (int g = 0; g < G; ++g) sum += expf(p[(size_t)g * D] - mx);
+  const float lse = mx + logf(sum);
+  const size_t GD = (size_t)G * D;
+  for (int g = 0; g < G; ++g) {
+    const size_t o = (size_t)r * GD + (size_t)g * D + d;
+    if (log_pi) log_pi[o] = p[(size_t)g * D] - lse;
+    if (log_sigma) log_sigma[o] = p[GD + (size_t)g * D];
+    if (mu) mu[o] = p[2 * GD + (size_t)g * D];
+  }
+  if (best_sigma) best_sigma[r * D + d] = expf(p[GD + (size_t)best * D]);
+  if (best_mu) best_mu[r * D + d] = p[2 * GD + (size_t)best * D];
+}
+
 }  // namespace svsk
 
 using namespace svsk;
@@ -201,4 +232,13 @@ extern "C" int svsk_scale_features_f32(const float* x, float* y, const float* a,
   const unsigned grid = (unsigned)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
   scale_features_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, y, a, b, mode, n, D);
   return check_launch("scale_features_f32");
+}
+
+extern "C" int svsk_mdn_head_f32(const float* raw, float* log_pi, float* log_sigma, float* mu, float* best_sigma, float* best_mu,
+                                 long long rows, int G, int D, int ld, void* stream) {
+  SVSK_REQUIRE(raw && rows > 0 && G >= 1 && D >= 1 && ld >= 3 * G * D, SVSK_E_ARG, "mdn_head_f32: bad args (ld >= 3 G D)");
+  SVSK_REQUIRE(log_pi || log_sigma || mu || best_sigma || best_mu, SVSK_E_ARG, "mdn_head_f32: no output requested");
+  const long long n = rows * D;
+  mdn_head_kernel<<<(unsigned)((n + 127) / 128), 128, 0, as_stream(stream)>>>(raw, log_pi, log_sigma, mu, best_sigma, best_mu, rows, G, D, ld);
+  return check_launch("mdn_head_f32");
 }

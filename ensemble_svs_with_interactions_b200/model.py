@@ -14,7 +14,9 @@ parameters, their ``forward`` never runs.  Eval-mode forward only (BatchNorm run
   recurrence itself stays fp32 (svsk_lstm_f32 with W_hh in registers).
 * ``precision="auto"`` (default): bf16 when every width is a multiple of 16, fp32 otherwise.
 
-Not built: ``use_mdn=True`` (the MDN head) and training mode — both raise.
+``use_mdn=True`` puts a dimension-wise mixture-density head (``MDNLayer``, nnsvs/mdn.py:6-74) in place of the output
+Linear: ``forward`` returns (log_pi, log_sigma, mu) [B, T, G, D], ``inference`` the (mu, sigma) of the most probable
+component (svsk_mdn_head_f32).  Not built: training mode (it raises).
 """
 from __future__ import annotations
 
@@ -26,7 +28,7 @@ from torch import nn
 from . import ops
 from .base import BaseModel, PredictionType
 
-__all__ = ["FFConvLSTM", "MultiSpeakerFFConvLSTM", "init_weights"]
+__all__ = ["FFConvLSTM", "MultiSpeakerFFConvLSTM", "MDNLayer", "init_weights"]
 
 
 def init_weights(net: nn.Module, init_type: str = "normal", init_gain: float = 0.02) -> None:
@@ -53,6 +55,20 @@ def init_weights(net: nn.Module, init_type: str = "normal", init_gain: float = 0
             nn.init.constant_(m.bias.data, 0.0)
 
     net.apply(visit)
+
+
+class MDNLayer(nn.Module):
+    """Parameter holder with the reference's layout (nnsvs/mdn.py:32-43): ``log_pi``, ``log_sigma``, ``mu`` Linears.  Only
+    the dimension-wise form (one 1-D mixture per output dimension) is built — the one FFConvLSTM uses (model.py:872)."""
+
+    def __init__(self, in_dim, out_dim, num_gaussians=30, dim_wise=False):
+        super().__init__()
+        if not dim_wise:
+            raise NotImplementedError("MDNLayer(dim_wise=False) is not built in this package")
+        self.in_dim, self.out_dim, self.num_gaussians, self.dim_wise = in_dim, out_dim, num_gaussians, dim_wise
+        self.log_pi = nn.Linear(in_dim, out_dim * num_gaussians)
+        self.log_sigma = nn.Linear(in_dim, out_dim * num_gaussians)
+        self.mu = nn.Linear(in_dim, out_dim * num_gaussians)
 
 
 class _Plan:
@@ -86,7 +102,12 @@ class _Plan:
                 b = torch.cat([g("bias_ih_l{}") + g("bias_hh_l{}"), g("bias_ih_l{}_reverse") + g("bias_hh_l{}_reverse")], 0)
                 w_hh = torch.stack([g("weight_hh_l{}"), g("weight_hh_l{}_reverse")], 0).float().contiguous()
                 lstm.append((w_ih, b.float().contiguous(), w_hh))
-            fc = (f(m.fc.weight), f(m.fc.bias))
+            if m.use_mdn:   # the three Linears of the head as one product: columns [log_pi | log_sigma | mu]
+                fc = (torch.cat([f(m.fc.log_pi.weight), f(m.fc.log_sigma.weight), f(m.fc.mu.weight)], 0).contiguous(),
+                      torch.cat([f(m.fc.log_pi.bias), f(m.fc.log_sigma.bias), f(m.fc.mu.bias)], 0).contiguous())
+            else:
+                fc = (f(m.fc.weight), f(m.fc.bias))
+            n_out = fc[0].shape[0]
 
             if precision == "fp32":
                 k1 = lambda w: w.unsqueeze(-1).contiguous()
@@ -100,11 +121,11 @@ class _Plan:
                 self.ff = [(ops.tapgemm_pack_bf16(w), b) for w, b in ff]
                 self.conv = [(ops.tapgemm_pack_bf16(w, s), b) for w, s, b in conv]
                 self.lstm = [(ops.tapgemm_pack_bf16(w), b, whh) for w, b, whh in lstm]
-                out_p = -(-m.out_dim // 16) * 16     # the GEMM writes 16 output channels at a time
+                out_p = -(-n_out // 16) * 16         # the GEMM writes 16 output channels at a time
                 wf = torch.zeros((out_p, fc[0].shape[1]), device=fc[0].device, dtype=torch.float32)
-                wf[:m.out_dim] = fc[0]
+                wf[:n_out] = fc[0]
                 bf = torch.zeros(out_p, device=fc[0].device, dtype=torch.float32)
-                bf[:m.out_dim] = fc[1]
+                bf[:n_out] = fc[1]
                 self.fc = (ops.tapgemm_pack_bf16(wf), bf)
                 self.out_p = out_p
 
@@ -116,9 +137,8 @@ class FFConvLSTM(BaseModel):
                  num_lstm_layers=2, bidirectional=True, init_type="none", use_mdn=False, dim_wise=True, num_gaussians=4,
                  in_ph_start_idx: int = 1, in_ph_end_idx: int = 50, embed_dim=None, precision="auto"):
         super().__init__()
-        if use_mdn:
-            raise NotImplementedError("FFConvLSTM(use_mdn=True): the MDN head is not built in this package")
         self.in_dim, self.out_dim = in_dim, out_dim
+        self.num_gaussians = num_gaussians
         self.in_ph_start_idx, self.in_ph_end_idx = in_ph_start_idx, in_ph_end_idx
         self.num_vocab = in_ph_end_idx - in_ph_start_idx
         self.embed_dim = embed_dim
@@ -143,13 +163,18 @@ class FFConvLSTM(BaseModel):
         self.conv = nn.Sequential(*layers)
         # the reference builds the LSTM bidirectional whatever `bidirectional` says (model.py:861-868)
         self.lstm = nn.LSTM(conv_hidden_dim, lstm_hidden_dim, num_lstm_layers, bidirectional=True, batch_first=True, dropout=dropout)
-        self.fc = nn.Linear((2 if bidirectional else 1) * lstm_hidden_dim, out_dim)
+        last_in_dim = (2 if bidirectional else 1) * lstm_hidden_dim
+        if use_mdn:
+            assert dim_wise
+            self.fc = MDNLayer(in_dim=last_in_dim, out_dim=out_dim, num_gaussians=num_gaussians, dim_wise=dim_wise)
+        else:
+            self.fc = nn.Linear(last_in_dim, out_dim)
         init_weights(self, init_type)
         self._plan: Optional[_Plan] = None
         self._plan_key = None
 
     def prediction_type(self):
-        return PredictionType.DETERMINISTIC
+        return PredictionType.PROBABILISTIC if self.use_mdn else PredictionType.DETERMINISTIC
 
     # ------------------------------------------------------------------ precision / plan
     def resolved_precision(self) -> str:
@@ -191,7 +216,8 @@ class FFConvLSTM(BaseModel):
                 raise RuntimeError(f"FFConvLSTM: lengths {lens} do not fit a batch of {B} x {T} frames")
         return lens
 
-    def forward(self, x, lengths=None, y=None, spk_embs=None):
+    def _raw(self, x, lengths, spk_embs):
+        """Output of the last product, [B, max(lengths), >= n_out] fp32 (a view when the GEMM padded its columns)."""
         lens = self._check(x, lengths)
         plan = self.plan()
         x = x.detach().float().contiguous()
@@ -199,9 +225,19 @@ class FFConvLSTM(BaseModel):
         if spk_embs is not None:
             spk_embs = spk_embs.detach().float().expand(x.shape[0], x.shape[1], spk_embs.shape[-1]).contiguous()
         out = self._forward_fp32(x, lens_dev, spk_embs, plan) if plan.precision == "fp32" else self._forward_bf16(x, lens_dev, spk_embs, plan)
-        return out[:, :max(lens)].contiguous()
+        return out[:, :max(lens)]
+
+    def forward(self, x, lengths=None, y=None, spk_embs=None):
+        raw = self._raw(x, lengths, spk_embs)
+        if self.use_mdn:     # (log_pi, log_sigma, mu), each [B, T, G, D]  (mdn.py:45-74)
+            return ops.mdn_head_f32(raw.contiguous(), self.num_gaussians, self.out_dim)[0]
+        return raw[:, :, :self.out_dim].contiguous()
 
     def inference(self, x, lengths=None, spk_embs=None):
+        if self.use_mdn:     # (mu, sigma) of the most probable component (model.py:925-928; no speaker embedding there)
+            raw = self._raw(x, lengths, None)
+            sigma, mu = ops.mdn_head_f32(raw.contiguous(), self.num_gaussians, self.out_dim, want_params=False, want_best=True)[1]
+            return mu, sigma
         return self(x, lengths, spk_embs=spk_embs)
 
     def _forward_fp32(self, x, lens_dev, spk, plan):
@@ -224,7 +260,7 @@ class FFConvLSTM(BaseModel):
             pre = ops.conv1d_f32(h, w_ih, b)                                   # [B, 8H, T]
             h = torch.empty((B, 2 * H, T), device=x.device, dtype=torch.float32)
             ops.lstm_f32(pre, w_hh, lens_dev, H, pre_layout="nct", h_f32=h)
-        y = ops.conv1d_f32(h, plan.fc[0], plan.fc[1])                          # [B, out, T]
+        y = ops.conv1d_f32(h, plan.fc[0], plan.fc[1])                          # [B, n_out, T]
         return ops.nct_to_ntc(y, want_bf16=False, want_f32=True)[1]
 
     def _forward_bf16(self, x, lens_dev, spk, plan):
@@ -268,7 +304,7 @@ class FFConvLSTM(BaseModel):
             c_in = 2 * H
         y = torch.empty((B, T, plan.out_p), device=dev, dtype=torch.float32)
         ops.tapgemm_bf16(h, plan.fc[0], plan.fc[1], c_in, T=T, y_f32=y)
-        return y[:, :, :self.out_dim]
+        return y
 
 
 class MultiSpeakerFFConvLSTM(FFConvLSTM):

@@ -507,3 +507,15 @@ def scale_features_f32(x, a, b, mode, out=None):
     L.check(L.lib().svsk_scale_features_f32(L.ptr(x, f32, "x"), L.ptr(out, f32, "out"), L.ptr(a, f32, "a"), L.ptr(b, f32, "b"), int(mode),
                                             x.numel() // D, D, L.stream_ptr()), "scale_features_f32")
     return out
+
+
+def mdn_head_f32(raw, G, D, *, want_params=True, want_best=False):
+    """svsk_mdn_head_f32.  raw [B, T, ld] fp32 ([log_pi | log_sigma | mu] columns) -> (log_pi, log_sigma, mu) [B, T, G, D]
+    and / or (best_sigma, best_mu) [B, T, D]."""
+    B, T, ld = raw.shape
+    mk = lambda *shape: torch.empty(shape, device=raw.device, dtype=f32)
+    lp, ls, mu = (mk(B, T, G, D), mk(B, T, G, D), mk(B, T, G, D)) if want_params else (None, None, None)
+    bs, bm = (mk(B, T, D), mk(B, T, D)) if want_best else (None, None)
+    L.check(L.lib().svsk_mdn_head_f32(L.ptr(raw, f32, "raw"), L.ptr(lp), L.ptr(ls), L.ptr(mu), L.ptr(bs), L.ptr(bm), B * T, G, D, ld,
+                                      L.stream_ptr()), "mdn_head_f32")
+    return (lp, ls, mu), (bs, bm)

@@ -423,6 +423,13 @@ SVSK_API int svsk_variance_scaling_f32(const float* x, float* y, const float* gv
  * a = scale_, b = min_);  mode 1: y = (x - b[d]) / a[d]  (StandardScaler.transform; MinMaxScaler.inverse_transform). */
 SVSK_API int svsk_scale_features_f32(const float* x, float* y, const float* a, const float* b, int mode, long long rows, int D,
                                      void* stream);
+/* Dimension-wise mixture-density head (nnsvs/mdn.py:45-74 MDNLayer.forward, :165-212 most probable component): raw
+ * [rows][ld] holds the outputs of the log_pi, log_sigma and mu Linears side by side (G*D columns each, component-major).
+ * log_pi <- log_softmax over the G components per output dimension, log_sigma / mu <- copies, all [rows][G][D];
+ * best_sigma / best_mu [rows][D] <- exp(log_sigma) and mu of the component with the largest weight.  Any output may be
+ * NULL. */
+SVSK_API int svsk_mdn_head_f32(const float* raw, float* log_pi, float* log_sigma, float* mu, float* best_sigma, float* best_mu,
+                               long long rows, int G, int D, int ld, void* stream);
 
 #ifdef __cplusplus
 }

@@ -271,6 +271,9 @@ def golden_encoder(ns):
                                   conv_hidden_dim=24, lstm_hidden_dim=40, num_lstm_layers=2, out_dim=16), 3, 50, [50, 41, 17]),
         ("ffconvlstm_test_shape", dict(in_dim=300, ff_hidden_dim=8, conv_hidden_dim=8, lstm_hidden_dim=8, dropout=0.1,
                                        num_lstm_layers=2, bidirectional=True, out_dim=180, init_type="none"), 2, 33, [33, 29]),
+        # the MDN head (tests/test_model.py builds the same model with use_mdn=True)
+        ("ffconvlstm_mdn", dict(in_dim=40, ff_hidden_dim=32, conv_hidden_dim=16, lstm_hidden_dim=16, num_lstm_layers=2,
+                                out_dim=11, use_mdn=True, dim_wise=True, num_gaussians=3), 2, 25, [25, 18]),
     ):
         torch.manual_seed(61)
         g = torch.Generator().manual_seed(62)
@@ -293,10 +296,16 @@ def golden_encoder(ns):
             x[..., s:s + V] = onehot
         with torch.no_grad():
             y = m(x.clone(), lengths)
+            extra = {}
+            if cfg.get("use_mdn"):
+                log_pi, log_sigma, mu = y
+                mu_best, sigma_best = m.inference(x.clone(), lengths)     # (mu, sigma) of the most probable component
+                extra = dict(log_pi=log_pi, log_sigma=log_sigma, mu=mu, mu_best=mu_best, sigma_best=sigma_best)
+                y = mu
             ff = m.ff(x if cfg.get("embed_dim") is None else
                       m.emb(torch.argmax(x[..., s:s + V], -1)) + m.fc_in(torch.cat([x[..., :s], x[..., s + V:]], -1)))
             conv = m.conv(ff.transpose(1, 2)).transpose(1, 2)
-        _save(name, cfg, m.state_dict(), dict(x=x, lengths=torch.tensor(lengths)), dict(y=y, ff=ff, conv=conv))
+        _save(name, cfg, m.state_dict(), dict(x=x, lengths=torch.tensor(lengths)), dict(y=y, ff=ff, conv=conv, **extra))
 
 
 def golden_postprocess(ns):

@@ -585,7 +585,7 @@ def ffconvlstm_front(sd: SD, x: Tensor, *, in_ph_start_idx: int, in_ph_end_idx: 
 
 def ffconvlstm_forward(sd: SD, x: Tensor, lengths: Sequence[int], *, in_ph_start_idx: int = 1, in_ph_end_idx: int = 50,
                        embed_dim: Optional[int] = None, num_lstm_layers: int = 2, spk_embs: Optional[Tensor] = None,
-                       bn_eps: float = 1e-5, want_parts: bool = False):
+                       bn_eps: float = 1e-5, want_parts: bool = False, num_gaussians: int = 4):
     """FFConvLSTM.forward in eval mode, use_mdn=False (model.py:893-922).  x [B, T, in_dim] -> [B, max(lengths), out_dim].
 
     ff: 3 x (Linear, ReLU); conv: 3 x (ReflectionPad1d(3), Conv1d k=7, BatchNorm1d with running statistics, ReLU) over
@@ -605,8 +605,27 @@ def ffconvlstm_forward(sd: SD, x: Tensor, lengths: Sequence[int], *, in_ph_start
     conv = y.transpose(1, 2)
     h = bilstm_stack(sd, "lstm.", conv, lengths, num_lstm_layers)
     h = h[:, :max(int(n) for n in lengths)]
-    out = h @ sd["fc.weight"].t() + sd["fc.bias"]
+    if "fc.log_pi.weight" in sd:           # use_mdn=True: the head is an MDNLayer (model.py:871-878)
+        out = mdn_layer(sd, "fc.", h, num_gaussians)
+    else:
+        out = h @ sd["fc.weight"].t() + sd["fc.bias"]
     return (out, dict(ff=ff, conv=conv, lstm=h)) if want_parts else out
+
+
+def mdn_layer(sd: SD, prefix: str, h: Tensor, num_gaussians: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """MDNLayer.forward with dim_wise=True (nnsvs/mdn.py:45-74): three Linears viewed as [B, T, G, D]; log_softmax of the
+    mixture weights over the G components of every output dimension."""
+    B, T = h.shape[0], h.shape[1]
+    def lin(name):
+        return (h @ sd[prefix + name + ".weight"].t() + sd[prefix + name + ".bias"]).view(B, T, num_gaussians, -1)
+    return torch.log_softmax(lin("log_pi"), dim=2), lin("log_sigma"), lin("mu")
+
+
+def mdn_most_probable_sigma_and_mu(log_pi: Tensor, log_sigma: Tensor, mu: Tensor) -> Tuple[Tensor, Tensor]:
+    """mdn_get_most_probable_sigma_and_mu for dim-wise mixtures (mdn.py:165-212): per output dimension the component with
+    the largest weight; returns (exp(log_sigma), mu) of that component, [B, T, D] each."""
+    idx = torch.argmax(log_pi, dim=2, keepdim=True)
+    return torch.exp(torch.gather(log_sigma, 2, idx))[:, :, 0], torch.gather(mu, 2, idx)[:, :, 0]
 
 
 # --------------------------------------------------------------------------- #

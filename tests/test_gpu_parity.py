@@ -1310,3 +1310,29 @@ def test_multispeaker_ffconvlstm_forward():
     close_bf16(m(x.to(DEV), spks.to(DEV), lengths), ref)
     m.precision = "fp32"
     close32(m.inference(x.to(DEV), spks.to(DEV), lengths), ref)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_ffconvlstm_mdn_head(precision):
+    """FFConvLSTM(use_mdn=True) against the reference's outputs (tests/golden/ffconvlstm_mdn.npz): the three mixture
+    parameter tensors of ``forward`` and the most probable (mu, sigma) of ``inference``."""
+    from ensemble_svs_with_interactions_b200.model import FFConvLSTM
+    g = Golden("ffconvlstm_mdn")
+    m = FFConvLSTM(**g.cfg, precision=precision)
+    m.load_state_dict(g.sd, strict=True)
+    m = m.to(DEV).eval()
+    x, lens = g.inp["x"].to(DEV), g.inp["lengths"].tolist()
+    log_pi, log_sigma, mu = m(x, lens)
+    mu_best, sigma_best = m.inference(x, lens)
+    assert log_pi.shape == tuple(g.out["log_pi"].shape) and mu_best.shape == tuple(g.out["mu_best"].shape)
+    if precision == "fp32":
+        close32(log_pi, g.out["log_pi"]); close32(log_sigma, g.out["log_sigma"]); close32(mu, g.out["mu"])
+        close32(mu_best, g.out["mu_best"]); close32(sigma_best, g.out["sigma_best"])
+    else:
+        close_bf16(log_sigma, g.out["log_sigma"]); close_bf16(mu, g.out["mu"])
+        assert (log_pi.cpu() - g.out["log_pi"]).abs().max().item() <= 5e-2
+        # the selected component may flip where two weights are within the bf16 error: compare where the choice is clear
+        top2 = g.out["log_pi"].topk(2, dim=2).values
+        clear = (top2[:, :, 0] - top2[:, :, 1]) > 0.1
+        assert clear.float().mean() > 0.5
+        assert ((mu_best.cpu() - g.out["mu_best"]).abs()[clear]).max().item() <= 6e-2 * g.out["mu_best"].abs().max().item()

@@ -164,8 +164,13 @@ def test_ffconvlstm_ctor_and_loud_failures():
                      "bidirectional", "init_type", "use_mdn", "dim_wise", "num_gaussians", "in_ph_start_idx", "in_ph_end_idx",
                      "embed_dim"]
     assert list(inspect.signature(MultiSpeakerFFConvLSTM.__init__).parameters)[1:3] == ["in_dim", "speaker_embedding"]
+    from ensemble_svs_with_interactions_b200.model import MDNLayer
     with pytest.raises(NotImplementedError):
-        FFConvLSTM(20, use_mdn=True)
+        MDNLayer(8, 4, 3, dim_wise=False)
+    gm = Golden("ffconvlstm_mdn")
+    mm = FFConvLSTM(**gm.cfg)
+    _same_layout(mm, gm.sd)                           # fc.log_pi / fc.log_sigma / fc.mu, in the reference's order
+    assert mm.prediction_type() == PredictionType.PROBABILISTIC
     m = FFConvLSTM(87, ff_hidden_dim=64, conv_hidden_dim=32, lstm_hidden_dim=16, out_dim=32, in_ph_start_idx=3, in_ph_end_idx=50,
                    embed_dim=32, init_type="kaiming_normal")
     assert m.resolved_precision() == "bf16"
