@@ -83,17 +83,23 @@ class EnsembleSynthesizer:
     the frames marked in ``note_masks`` (all valid frames when no masks are given), dimensions >= ``gv_offset``.
     out_scaler_mgc / out_scaler_bap: ``postprocess.StandardScaler`` / ``MinMaxScaler`` whose ``inverse_transform`` takes
     the streams back to feature units right after sampling (gen.py:1145); vocoder_in_scaler: its ``transform`` is applied
-    to the assembled aux features (gen.predict_waveform).  All on the device."""
+    to the assembled aux features (gen.predict_waveform).  All on the device.
+    vuv: the V/UV stream's model (``model.FFConvLSTM`` in the recipe), or None.  As in the composite acoustic model
+    (acoustic_models/multistream.py:1684-1720, main track) it reads ``cat([x, mgc, lf0])`` where ``cond_mgc = cat([x, lf0])``
+    and ``mgc`` is the diffusion output before any scaler; frames whose (inverse-scaled) output is below
+    ``vuv_threshold`` get f0 = 0 before the vocoder (gen.py: ``f0[vuv < vuv_threshold] = 0``)."""
 
     def __init__(self, mgc, bap, vocoder, max_frames: int = 36000,
                  aux_fn: Optional[Callable[[torch.Tensor, torch.Tensor, torch.Tensor], torch.Tensor]] = None,
                  smoothing_cutoff: Optional[float] = None, frame_rate: int = 200, gv_mgc: Optional[torch.Tensor] = None,
-                 gv_offset: int = 2, out_scaler_mgc=None, out_scaler_bap=None, vocoder_in_scaler=None):
+                 gv_offset: int = 2, out_scaler_mgc=None, out_scaler_bap=None, vocoder_in_scaler=None,
+                 vuv=None, vuv_threshold: float = 0.5, out_scaler_vuv=None):
         self.mgc, self.bap, self.vocoder = mgc, bap, vocoder
         self.max_frames = int(max_frames)
         self.smoothing_cutoff, self.frame_rate = smoothing_cutoff, int(frame_rate)
         self.gv_mgc, self.gv_offset = gv_mgc, int(gv_offset)
         self.out_scaler_mgc, self.out_scaler_bap, self.vocoder_in_scaler = out_scaler_mgc, out_scaler_bap, vocoder_in_scaler
+        self.vuv, self.vuv_threshold, self.out_scaler_vuv = vuv, float(vuv_threshold), out_scaler_vuv
         self.aux_fn = aux_fn if aux_fn is not None else (lambda m, b, f0: torch.cat([m, b], dim=-1))
         self._side = None
 
@@ -139,6 +145,11 @@ class EnsembleSynthesizer:
             hm, hb = self._encode(cm, cb, lens)
             m = self.mgc.inference(hm, cond_is_encoded=True)   # [B, T, M1]
             b = self.bap.inference(hb, cond_is_encoded=True)   # [B, T, M2]
+            if self.vuv is not None:
+                v = self.vuv.inference(torch.cat([cm[..., :-1], m, cm[..., -1:]], dim=-1).contiguous(), lens)   # [B, T, 1]
+                if self.out_scaler_vuv is not None:
+                    v = self.out_scaler_vuv.inverse_transform(v)
+                f = torch.where(v < self.vuv_threshold, torch.zeros_like(f), f)
             if self.out_scaler_mgc is not None:
                 m = self.out_scaler_mgc.inverse_transform(m)
             if self.out_scaler_bap is not None:

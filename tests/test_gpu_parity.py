@@ -964,6 +964,22 @@ def test_pipeline_with_encoders_matches_sequential_calls():
     torch.manual_seed(5)
     m = mgc.inference(batch, lens); b = bap.inference(batch, lens)
     assert torch.equal(seen["aux"], torch.cat([m, b], dim=-1))
+    # V/UV stream: FFConvLSTM over cat([x, mgc, lf0]) decides which frames keep their f0
+    vuv_model = FFConvLSTM(87 + 60, lstm_hidden_dim=32, out_dim=1, **kw).to(DEV).eval()
+    seen_f0 = {}
+
+    class Voc2(Voc):
+        def inference_batch(self, f0, aux):
+            seen_f0["f0"] = f0.clone()
+            return super().inference_batch(f0, aux)
+    v_ref = vuv_model(torch.cat([batch[..., :-1], m, batch[..., -1:]], dim=-1).contiguous(), lens)
+    thr = float(v_ref[0].median())                       # so that some frames of the first track are voiced and some are not
+    synth_v = EnsembleSynthesizer(mgc, bap, Voc2(), max_frames=1000, vuv=vuv_model, vuv_threshold=thr)
+    torch.manual_seed(5)
+    synth_v.synthesize(ling, ling, f0)
+    f_ref = torch.stack([_pad_time(x.to(DEV), 48, "zeros") for x in f0])
+    f_ref = torch.where(v_ref < thr, torch.zeros_like(f_ref), f_ref)
+    assert torch.equal(seen_f0["f0"], f_ref) and 0 < int((f_ref[0] == 0).sum()) < 48
     # with the device post-processing between the models (GV post-filter on note frames + 50 Hz smoothing)
     from ensemble_svs_with_interactions_b200 import postprocess as pp
     gv = torch.rand(60, generator=g) + 0.5
