@@ -75,3 +75,32 @@ def test_wavenet_live(ns):
         ref = m(c, x)
     sd = {k: v.detach() for k, v in m.state_dict().items()}
     close(O.wavenet_forward(sd, c, x, layers=3, stacks=1), ref)
+
+
+def test_parallel_hn_usfgan_live(ns):
+    """Another seed, another shape than tests/golden/usfgan_parallel_hn_small.npz (aux 10, scales [2, 2], hop 4)."""
+    torch.manual_seed(105)
+    g = torch.Generator().manual_seed(106)
+    common = dict(residual_channels=8, gate_channels=16, skip_channels=8, aux_channels=10, aux_context_window=2,
+                  use_weight_norm=True, upsample_params={"upsample_scales": [2, 2]})
+    pe = {"conv_layers": 3, "kernel_size": 5, "dilation": 1, "padding_mode": "replicate", "residual_channels": 8}
+    hp = {"blockA": 3, "cycleA": 3, "blockF": 0, "cycleF": 0, "cascade_mode": 0}
+    np_ = {"blockA": 0, "cycleA": 0, "blockF": 2, "cycleF": 1, "cascade_mode": 0}
+    fp = {"blockA": 0, "cycleA": 0, "blockF": 4, "cycleF": 2, "cascade_mode": 0}
+    m = ns.ParallelHnUSFGANGenerator(harmonic_network_params=dict(hp), noise_network_params=dict(np_),
+                                     filter_network_params=dict(fp), periodicity_estimator_params=dict(pe), **common).eval()
+    with torch.no_grad():
+        m.periodicity_estimator.layers[-2].weight_v.normal_(0, 0.2, generator=g)
+    B, Fr, hop = 2, 30, 4
+    c = torch.randn(B, 10, Fr + 4, generator=g)
+    f0 = torch.empty(B, Fr).uniform_(20.0, 60.0, generator=g)
+    f0[:, 5:9] = 0.0
+    d = torch.tensor(np.stack([ns.dilated_factor(f.numpy().astype(np.float64).copy(), 240, 4) for f in f0]),
+                     dtype=torch.float32).repeat_interleave(hop, dim=-1)[:, None]
+    x = torch.randn(B, 2, Fr * hop, generator=g) * 0.3
+    with torch.no_grad():
+        ref = m(x, c, d)
+    pe_o = dict(pe); pe_o.pop("residual_channels")
+    outs = O.parallel_hn_usfgan_forward(m.state_dict(), x, c, d, harmonic=hp, noise=np_, filt=fp, upsample_scales=[2, 2], pe=pe_o)
+    for o, r in zip(outs, ref):
+        close(o, r, 5e-5)
