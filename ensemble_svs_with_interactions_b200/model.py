@@ -71,6 +71,35 @@ class MDNLayer(nn.Module):
         self.mu = nn.Linear(in_dim, out_dim * num_gaussians)
 
 
+def _padded_hidden(H: int) -> int:
+    """Smallest hidden size >= H that svsk_lstm_f32 has a layout for (H itself when it has one; 0 if none up to 256).
+    Padded units get zero weights: their gates see 0, the cell stays 0 and they emit h = 0 at every step."""
+    for hp in range(H, 257):
+        if ops.lstm_supported(hp):
+            return hp
+    return 0
+
+
+def _pad_gate_rows(w, H, Hp):
+    """[4H, ...] (torch gate blocks i, f, g, o) -> [4Hp, ...] with zero rows appended to every gate block."""
+    if Hp == H:
+        return w
+    w4 = w.reshape(4, H, *w.shape[1:])
+    out = w4.new_zeros((4, Hp) + tuple(w.shape[1:]))
+    out[:, :H] = w4
+    return out.reshape(4 * Hp, *w.shape[1:])
+
+
+def _pad_bidir_cols(w, H, Hp):
+    """[..., 2H] (forward | backward outputs of a BiLSTM layer) -> [..., 2Hp]: each half zero-padded to Hp columns."""
+    if Hp == H:
+        return w
+    out = w.new_zeros(tuple(w.shape[:-1]) + (2 * Hp,))
+    out[..., :H] = w[..., :H]
+    out[..., Hp:Hp + H] = w[..., H:]
+    return out
+
+
 class _Plan:
     """Weights in the layouts the kernels read, built once per parameter version."""
 
@@ -95,18 +124,30 @@ class _Plan:
                 scale = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
                 bias = (m.conv[i].bias.float() - bn.running_mean.float()) * scale + bn.bias.float()
                 conv.append((f(m.conv[i].weight), scale.contiguous(), bias.contiguous()))
+            # hidden sizes without a cluster layout (the recipe's bap stream has 62 units) run zero-padded to the next one
+            H, Hp = m.lstm_hidden_dim, m.padded_hidden
+            self.Hp = Hp
             lstm = []
             for l in range(m.lstm.num_layers):
-                g = lambda n: getattr(m.lstm, n.format(l))
-                w_ih = torch.cat([g("weight_ih_l{}"), g("weight_ih_l{}_reverse")], 0).float().contiguous()
-                b = torch.cat([g("bias_ih_l{}") + g("bias_hh_l{}"), g("bias_ih_l{}_reverse") + g("bias_hh_l{}_reverse")], 0)
-                w_hh = torch.stack([g("weight_hh_l{}"), g("weight_hh_l{}_reverse")], 0).float().contiguous()
-                lstm.append((w_ih, b.float().contiguous(), w_hh))
+                g = lambda n: getattr(m.lstm, n.format(l)).float()
+                parts = []
+                for suf in ("", "_reverse"):
+                    w_ih = g("weight_ih_l{}" + suf)
+                    if l > 0:
+                        w_ih = _pad_bidir_cols(w_ih, H, Hp)
+                    parts.append((_pad_gate_rows(w_ih, H, Hp), _pad_gate_rows(g("bias_ih_l{}" + suf) + g("bias_hh_l{}" + suf), H, Hp),
+                                  _pad_gate_rows(g("weight_hh_l{}" + suf), H, Hp)))
+                w_ih = torch.cat([parts[0][0], parts[1][0]], 0).contiguous()
+                b = torch.cat([parts[0][1], parts[1][1]], 0).contiguous()
+                w_hh = torch.stack([torch.nn.functional.pad(parts[0][2], (0, Hp - H)), torch.nn.functional.pad(parts[1][2], (0, Hp - H))], 0).contiguous()
+                lstm.append((w_ih, b, w_hh))
             if m.use_mdn:   # the three Linears of the head as one product: columns [log_pi | log_sigma | mu]
                 fc = (torch.cat([f(m.fc.log_pi.weight), f(m.fc.log_sigma.weight), f(m.fc.mu.weight)], 0).contiguous(),
                       torch.cat([f(m.fc.log_pi.bias), f(m.fc.log_sigma.bias), f(m.fc.mu.bias)], 0).contiguous())
             else:
                 fc = (f(m.fc.weight), f(m.fc.bias))
+            if fc[0].shape[1] == 2 * H:
+                fc = (_pad_bidir_cols(fc[0], H, Hp).contiguous(), fc[1])
             n_out = fc[0].shape[0]
 
             if precision == "fp32":
@@ -145,6 +186,7 @@ class FFConvLSTM(BaseModel):
         self.use_mdn = use_mdn
         self.precision = precision
         self.ff_hidden_dim, self.conv_hidden_dim, self.lstm_hidden_dim = ff_hidden_dim, conv_hidden_dim, lstm_hidden_dim
+        self._padded_hidden = None
 
         if embed_dim is not None:
             assert in_dim > self.num_vocab
@@ -176,9 +218,16 @@ class FFConvLSTM(BaseModel):
     def prediction_type(self):
         return PredictionType.PROBABILISTIC if self.use_mdn else PredictionType.DETERMINISTIC
 
+    @property
+    def padded_hidden(self) -> int:
+        """Hidden size the recurrence kernel runs with (>= lstm_hidden_dim; the extra units are inert zeros)."""
+        if self._padded_hidden is None:
+            self._padded_hidden = _padded_hidden(self.lstm_hidden_dim)
+        return self._padded_hidden
+
     # ------------------------------------------------------------------ precision / plan
     def resolved_precision(self) -> str:
-        widths = [self.ff_hidden_dim, self.conv_hidden_dim, 8 * self.lstm_hidden_dim] + ([self.embed_dim] if self.embed_dim else [])
+        widths = [self.ff_hidden_dim, self.conv_hidden_dim] + ([self.embed_dim] if self.embed_dim else [])
         ok = all(w % 16 == 0 for w in widths)
         if self.precision == "auto":
             return "bf16" if ok else "fp32"
@@ -205,8 +254,8 @@ class FFConvLSTM(BaseModel):
             raise RuntimeError(f"FFConvLSTM: expected input [B, T, {self.in_dim}], got {tuple(x.shape)}")
         if x.shape[1] < 4:
             raise RuntimeError("FFConvLSTM: ReflectionPad1d(3) needs at least 4 frames")
-        if not ops.lstm_supported(self.lstm_hidden_dim):
-            raise RuntimeError(f"FFConvLSTM: lstm_hidden_dim={self.lstm_hidden_dim} has no layout in svsk_lstm_f32")
+        if not self.padded_hidden:
+            raise RuntimeError(f"FFConvLSTM: lstm_hidden_dim={self.lstm_hidden_dim} has no layout in svsk_lstm_f32 (at most 256 units)")
         B, T = x.shape[0], x.shape[1]
         if lengths is None:
             lens = [T] * B
@@ -242,7 +291,7 @@ class FFConvLSTM(BaseModel):
 
     def _forward_fp32(self, x, lens_dev, spk, plan):
         B, T, _ = x.shape
-        H = self.lstm_hidden_dim
+        H = plan.Hp
         if self.embed_dim is not None:
             xf = torch.empty((B * T, self.in_dim), device=x.device, dtype=torch.float32)
             ops.encoder_front(x.view(B * T, self.in_dim), self.in_ph_start_idx, self.num_vocab, y_f32=xf)
@@ -265,7 +314,7 @@ class FFConvLSTM(BaseModel):
 
     def _forward_bf16(self, x, lens_dev, spk, plan):
         B, T, _ = x.shape
-        dev, H, bf = x.device, self.lstm_hidden_dim, torch.bfloat16
+        dev, H, bf = x.device, plan.Hp, torch.bfloat16
         ld0 = -(-self.in_dim // 8) * 8
         if spk is not None and self.embed_dim is None:
             x = ops.lincomb_f32([x, spk], [1.0, 1.0])

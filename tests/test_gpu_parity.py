@@ -1108,10 +1108,12 @@ def _recipe_encoder(precision, gen, H=128, spk=False):
     return m.eval()
 
 
-@pytest.mark.parametrize("H,spk", [(128, False), (64, True), (256, False)])
+@pytest.mark.parametrize("H,spk", [(128, False), (64, True), (256, False), (62, False)])
 def test_ffconvlstm_recipe_shape_both_precisions(H, spk):
     """Recipe encoder (multitrack_acoustic_..._diff_mgcbap.yaml:104-116) on ragged tracks: fp32 within 2e-4 of the oracle,
-    bf16 within rel-L2 2e-2; speaker embedding added in front of ff when given."""
+    bf16 within rel-L2 2e-2; speaker embedding added in front of ff when given.  H = 62 is the bap stream of the recipe's
+    default (non-diffusion) acoustic model (multitrack_acoustic_nnsvs_world_multi_ar_f0.yaml:134-145): it has no cluster
+    layout of its own and runs zero-padded to 64 units."""
     g = torch.Generator().manual_seed(77 + H)
     m = _recipe_encoder("fp32", g, H, spk)
     B, T, lengths = 3, 200, [200, 131, 64]
