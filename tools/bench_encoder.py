@@ -19,6 +19,9 @@ SIZES = {  # recipe: conf/train_acoustic/model/multitrack_acoustic_nnsvs_world_m
     "recipe_bap": dict(in_dim=87, ff_hidden_dim=256, conv_hidden_dim=128, lstm_hidden_dim=64, out_dim=128, in_ph_start_idx=3,
                        in_ph_end_idx=50, embed_dim=256),
     "default": dict(in_dim=87),  # model.py:803-806: 2048 / 1024 / 256
+    # the stream models of the recipe's default (non-diffusion) config, multitrack_acoustic_nnsvs_world_multi_ar_f0.yaml:106-145
+    "stream_mgc": dict(in_dim=1026, ff_hidden_dim=1024, conv_hidden_dim=512, lstm_hidden_dim=256, out_dim=60),
+    "stream_bap": dict(in_dim=1026, ff_hidden_dim=256, conv_hidden_dim=128, lstm_hidden_dim=62, out_dim=5),
 }
 
 
@@ -66,7 +69,7 @@ def main():
     for prec in ("bf16", "fp32"):
         m = FFConvLSTM(**cfg, precision=prec).cuda().eval()
         out[f"forward_ms_{prec}"] = round(timed(lambda: m(x, [T] * B)), 3)
-    H = m.lstm_hidden_dim
+    H = m.padded_hidden
     pre = torch.randn(B, T, 8 * H, device="cuda")
     w_hh = torch.randn(2, 4 * H, H, device="cuda") / H ** 0.5
     hb = torch.empty(B, T, 2 * H, device="cuda", dtype=torch.bfloat16)
