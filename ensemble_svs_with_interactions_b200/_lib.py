@@ -35,7 +35,7 @@ class DiffnetBlockParams(C.Structure):
         ("bout", C.c_void_p),
         ("B", C.c_int32), ("T", C.c_int32), ("C", C.c_int32), ("H", C.c_int32),
         ("dilation", C.c_int32), ("stepbias_batch_stride", C.c_int32), ("init_skip", C.c_int32),
-        ("write_x", C.c_int32), ("time_tile", C.c_int32),
+        ("write_x", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -128,8 +128,6 @@ _SIGNATURES = {
     "svsk_nct_to_ntc": [_V, _V, _V, _I, _I, _I, _I, _V],
     "svsk_ntc_to_nct_f32": [_V, _V, _I, _I, _I, _I, _F, _V],
     "svsk_cast_scale_bf16": [_V, _V, _Z, _F, _I, _V],
-    "svsk_diffnet_block_bf16": [C.POINTER(DiffnetBlockParams), _V],
-    "svsk_diffnet_block2_bf16": [C.POINTER(DiffnetBlockParams), _V],
     "svsk_diffnet_block3_bf16": [C.POINTER(DiffnetBlockParams), _V],
     "svsk_diffnet_stack_bf16": [C.POINTER(DiffnetStackParams), _V],
     "svsk_diffnet_stack_fits": [C.c_int, C.c_int, C.c_int, C.c_int],

@@ -9,9 +9,13 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["svsk_api.cu", "simt_f32.cu", "tma_util.cu", "diffnet_block_sm100.cu", "diffnet_block2_sm100.cu", "diffnet_block3_sm100.cu", "diffnet_stack_sm100.cu", "diffnet_step_sm100.cu", "linear_sm100.cu",
-           "usfgan_block_sm100.cu", "conv1d_sm100.cu", "usfgan_front.cu", "lstm_sm100.cu", "encoder_sm100.cu", "postproc.cu", "ubench_sm100.cu"]
+SOURCES = ["svsk_api.cu", "simt_f32.cu", "tma_util.cu", "diffnet_pack.cu", "diffnet_block3_sm100.cu", "diffnet_stack_sm100.cu",
+           "diffnet_step_sm100.cu", "linear_sm100.cu", "usfgan_block_sm100.cu", "conv1d_sm100.cu", "usfgan_front.cu",
+           "lstm_sm100.cu", "encoder_sm100.cu", "postproc.cu"]
 LIB = os.path.join(HERE, "libsvsk.so")
+# micro-benchmarks behind tools/ubench_*.py: their own library, NOT part of the product libsvsk.so
+TOOLS = os.path.join(HERE, "..", "..", "tools")
+UBENCH_LIB = os.path.join(TOOLS, "libsvsk_ubench.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
@@ -56,5 +60,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_ubench(force: bool = False) -> str:
+    """tools/libsvsk_ubench.so: tools/ubench_sm100.cu + the error-string helpers of svsk_api.cu."""
+    src = os.path.join(TOOLS, "ubench_sm100.cu")
+    if not force and os.path.exists(UBENCH_LIB) and os.path.getmtime(UBENCH_LIB) >= max(_deps_mtime(), os.path.getmtime(src)):
+        return UBENCH_LIB
+    cmd = [_nvcc(), *NVCC_FLAGS, "-I", HERE, "-shared", "-o", UBENCH_LIB, src, os.path.join(HERE, "svsk_api.cu"),
+           "-cudart", "static"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for ubench:\n{r.stdout}\n{r.stderr}")
+    return UBENCH_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    if "--ubench" in sys.argv:
+        print(build_ubench(force="--force" in sys.argv))

@@ -715,7 +715,10 @@ static void stack_launch_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at
   // CTAs that talk to each other — so it needs no such guarantee (and no per-tile counters to reset): a plain cluster
   // launch measures 0.9 % faster per sampling pass (same-box A/B against SVSK_STACK_COOPERATIVE=1: 41.70 vs 42.07 ms).  (A programmatic-dependent-launch edge between the stack and the
   // step kernel was measured as well: no gain — the early CTAs of the next kernel only fragment the cluster placement.)
-  if (csize > 2 && !getenv("SVSK_STACK_COOPERATIVE")) {
+  // A track that is a single CTA pair (T <= 256) has no neighbour at all: same plain launch (which also keeps small
+  // calls such as __graft_entry__.smoke() replayable by ncu, whose kernel replay cannot re-launch a cooperative grid).
+  const bool single_pair = ceil_div(T, 256) == 1;
+  if ((csize > 2 || single_pair) && !getenv("SVSK_STACK_COOPERATIVE")) {
     cfg->attrs = attr;
     cfg->numAttrs = 1;
     return;

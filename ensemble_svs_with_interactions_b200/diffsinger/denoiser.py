@@ -4,11 +4,12 @@ Same constructor kwargs, ``forward(spec, diffusion_step, cond)`` signature and `
 ``nn.Conv1d`` / ``nn.Linear`` sub-modules only HOLD the parameters (so checkpoints load with strict=True); the
 arithmetic runs in libsvsk:
 
-* ``precision="bf16"``: one fused tcgen05 kernel per residual layer (svsk_diffnet_block_bf16) + tcgen05 1x1
-  projections (svsk_linear_bf16); fp32 residual/skip masters, bf16 MMA operands, fp32 accumulation.
+* ``precision="bf16"``: all residual layers of a call in one tcgen05 launch (svsk_diffnet_stack_bf16; one launch per
+  layer, svsk_diffnet_block3_bf16, for tracks too long for it) + tcgen05 1x1 projections (svsk_linear_bf16); bf16
+  residual stream and MMA operands, fp32 accumulation and skip sum.
 * ``precision="fp32"``: CUDA-core kernels in the reference's own fp32 arithmetic (svsk_conv1d_f32 ...).
-* ``precision="auto"`` (default): bf16 when the shapes fit the tensor-core kernel (C in {128,256}, H % 64 == 0),
-  else fp32.  Both are CUDA kernels of this library; there is no PyTorch/CPU path for the forward pass.
+* ``precision="auto"`` (default): bf16 when the shapes fit the tensor-core kernels (C in {128,256}, H % 64 == 0,
+  dilations <= 8, i.e. dilation_cycle_length <= 4 as in every recipe), else fp32.  Both are CUDA kernels of this library; there is no PyTorch/CPU path for the forward pass.
 """
 from __future__ import annotations
 
@@ -182,12 +183,14 @@ class DiffNet(nn.Module):
 
     # ------------------------------------------------------------------ precision / plans
     def resolved_precision(self) -> str:
-        ok = self.residual_channels in (128, 256) and self.encoder_hidden_dim % 64 == 0
+        max_dil = max((int(layer.dilation) for layer in self.residual_layers), default=1)
+        ok = self.residual_channels in (128, 256) and self.encoder_hidden_dim % 64 == 0 and max_dil <= 8
         if self.precision == "auto":
             return "bf16" if ok else "fp32"
         if self.precision == "bf16" and not ok:
-            raise RuntimeError("DiffNet precision='bf16' needs residual_channels in {128,256} and "
-                               f"encoder_hidden_dim % 64 == 0 (got {self.residual_channels}, {self.encoder_hidden_dim})")
+            raise RuntimeError("DiffNet precision='bf16' needs residual_channels in {128,256}, encoder_hidden_dim % 64 == 0 "
+                               f"and dilations <= 8 (got {self.residual_channels}, {self.encoder_hidden_dim}, {max_dil}); "
+                               "precision='fp32' / 'auto' run such shapes on the fp32 kernels")
         if self.precision not in ("bf16", "fp32"):
             raise RuntimeError(f"unknown precision {self.precision!r}")
         return self.precision
@@ -242,10 +245,8 @@ class DiffNet(nn.Module):
         sb_batch = stepbias.stride(1) if per_row else 0
         xb1 = torch.empty((B, T, C), device=dev, dtype=bf16)
         skip32 = torch.empty((B, T, C), device=dev, dtype=f32)
-        time_tile = getattr(self, "time_tile", 0)
         stack_b = 0  # tracks per launch of the one-launch residual stack (0: run the layers one kernel at a time)
-        if (not time_tile and os.environ.get("SVSK_DIFFNET_STACK", "1") != "0" and max(plan.dilations) <= 8
-                and os.environ.get("SVSK_DIFFNET_KERNEL", "3") == "3"):
+        if os.environ.get("SVSK_DIFFNET_STACK", "1") != "0":
             stack_b = _stack_tracks_per_launch(B, T, C, plan.H)
         if stack_b:
             # one launch for all L blocks of `stack_b` tracks: every CTA pair keeps its 256-frame tile across the layers,
@@ -259,12 +260,11 @@ class DiffNet(nn.Module):
                                        plan.woutp_all, stepbias[:, b0:b1] if per_row else stepbias, plan.bout_all, flags,
                                        plan.dilations, stepbias_batch_stride=sb_batch, stepbias_layer_stride=sb_layer)
         else:
-            x32 = torch.empty((B, T, C), device=dev, dtype=f32) if time_tile else skip32  # (only the single-CTA kernel uses it)
             cur, nxt = xb0, xb1
             for i, lw in enumerate(plan.layers):
-                ops.diffnet_block_bf16(cur, nxt, x32, skip32, condb, lw["w1p"], lw["woutp"], stepbias[i], lw["bout"],
+                ops.diffnet_block_bf16(cur, nxt, skip32, skip32, condb, lw["w1p"], lw["woutp"], stepbias[i], lw["bout"],
                                        dilation=lw["dilation"], stepbias_batch_stride=sb_batch, init_skip=(i == 0),
-                                       write_x=(i < L - 1), time_tile=time_tile)
+                                       write_x=(i < L - 1))
                 cur, nxt = nxt, cur
         return skip32
 
@@ -272,31 +272,8 @@ class DiffNet(nn.Module):
         """x32s [B,T,Mp] fp32 (channels >= M are ignored), condb [B,T,H] bf16, stepbias as in residual_stack_bf16.
         Returns eps [B,T,Mp] fp32 (padded channels = 0)."""
         plan = self.bf16_plan() if plan is None else plan
-        if getattr(self, "time_tile", 0):  # the single-CTA kernel keeps an fp32 master of the residual stream
-            return self._denoise_ntc_bf16_v1(x32s, condb, stepbias, plan)
         skip32 = self.residual_stack_bf16(self.project_in_bf16(x32s, plan), condb, stepbias, plan)
         skipb = ops.cast_scale_bf16(skip32, alpha=1.0 / sqrt(plan.L))
-        hb, _ = ops.linear_bf16(skipb, plan.w_skip, plan.b_skip, act=ops.ACT_RELU, want_bf16=True)
-        _, eps = ops.linear_bf16(hb, plan.w_out, plan.b_out, want_f32=True)
-        return eps
-
-    def _denoise_ntc_bf16_v1(self, x32s, condb, stepbias, plan):
-        B, T, _ = x32s.shape
-        C, L = plan.C, plan.L
-        dev = x32s.device
-        sb_batch = stepbias.stride(1) if stepbias.shape[1] == B and B > 1 else 0
-        xb0 = torch.empty((B, T, C), device=dev, dtype=bf16)
-        xb1 = torch.empty((B, T, C), device=dev, dtype=bf16)
-        x32 = torch.empty((B, T, C), device=dev, dtype=f32)
-        skip32 = torch.empty((B, T, C), device=dev, dtype=f32)
-        ops.linear_bf16(ops.cast_scale_bf16(x32s), plan.w_in, plan.b_in, act=ops.ACT_RELU, out_bf16=xb0, out_f32=x32)
-        cur, nxt = xb0, xb1
-        for i, lw in enumerate(plan.layers):
-            ops.diffnet_block_bf16(cur, nxt, x32, skip32, condb, lw["w1p"], lw["woutp"], stepbias[i], lw["bout"],
-                                   dilation=lw["dilation"], stepbias_batch_stride=sb_batch, init_skip=(i == 0),
-                                   write_x=(i < L - 1), time_tile=self.time_tile)
-            cur, nxt = nxt, cur
-        skipb = ops.cast_scale_bf16(skip32, alpha=1.0 / sqrt(L))
         hb, _ = ops.linear_bf16(skipb, plan.w_skip, plan.b_skip, act=ops.ACT_RELU, want_bf16=True)
         _, eps = ops.linear_bf16(hb, plan.w_out, plan.b_out, want_f32=True)
         return eps

@@ -184,14 +184,15 @@ class GaussianDiffusion(BaseModel):
             plan.step_table = den.step_bias_bf16(t_all)
         return plan.step_table
 
-    def _sample_loop_bf16(self, condb, x32s, z_ntc):
-        """x32s [B,T,Mp] fp32 (updated in place), z_ntc [K,B,T,Mp] fp32."""
+    def _sample_loop_bf16(self, condb, x32s, z_ntc, trace=None):
+        """x32s [B,T,Mp] fp32 (updated in place), z_ntc [K,B,T,Mp] fp32.  ``trace``: {t: None} -> filled with the
+        denoiser output of step t, [B,T,Mp] fp32 (parity harness; eager launches only)."""
         den = self.denoise_fn
         plan = den.bf16_plan()
         table = self._step_table()
         B = x32s.shape[0]
         tabs = self._tables()
-        if os.environ.get("SVSK_DIFFNET_STEP", "1") != "0" and not getattr(den, "time_tile", 0) and plan.Mp <= 128:
+        if os.environ.get("SVSK_DIFFNET_STEP", "1") != "0" and plan.Mp <= 128:
             # per step: the residual stack, then ONE kernel for tail projections + p_sample update + the next step's
             # input projection (svsk_diffnet_step_bf16)
             sched = [tabs[k] for k in ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
@@ -199,22 +200,29 @@ class GaussianDiffusion(BaseModel):
             xb0 = den.project_in_bf16(x32s, plan)
             for i in reversed(range(self.K_step)):
                 skip32 = den.residual_stack_bf16(xb0, condb, table[:, i:i + 1], plan)   # row i of every layer's table
+                eps_out = torch.empty_like(x32s) if trace is not None and i in trace else None
                 ops.diffnet_step_bf16(skip32, x32s, z_ntc[i], self._t_const[i], sched, plan.w_skip, plan.b_skip, plan.w_out,
                                       plan.b_out, skip_scale=1.0 / math.sqrt(plan.L), w_in=plan.w_in, b_in=plan.b_in,
-                                      xb_out=xb0 if i > 0 else None)
+                                      xb_out=xb0 if i > 0 else None, eps_out=eps_out)
+                if eps_out is not None:
+                    trace[i] = eps_out
             return x32s
         for i in reversed(range(self.K_step)):
             # row i of every layer's table, shared by the whole batch
             eps = den.denoise_ntc_bf16(x32s, condb, table[:, i:i + 1], plan=plan)
+            if trace is not None and i in trace:
+                trace[i] = eps.clone()
             ops.ddpm_update_f32(x32s, eps, z_ntc[i], self._t_const[i], tabs, True, out=x32s)
         return x32s
 
-    def _sample_loop_fp32(self, cond_nct, x, z):
+    def _sample_loop_fp32(self, cond_nct, x, z, trace=None):
         den = self.denoise_fn
         tabs = self._tables()
         for i in reversed(range(self.K_step)):
             t = self._t_const[i]
             eps = den.denoise_nct_fp32(x[:, 0], cond_nct, t)[:, None]
+            if trace is not None and i in trace:
+                trace[i] = eps.clone()
             ops.ddpm_update_f32(x, eps.contiguous(), z[i], t, tabs, True, out=x)
         return x
 
@@ -230,9 +238,11 @@ class GaussianDiffusion(BaseModel):
         self._t_const = cache[key]
 
     @torch.no_grad()
-    def sample(self, cond_t, x_T=None, z=None):
+    def sample(self, cond_t, x_T=None, z=None, trace=None):
         """Core of ``inference`` after the encoder.  cond_t (B,H,T) fp32; optional injected x_T (B,1,M,T) and
-        z (K,B,1,M,T) (z[i] is consumed at step t=i).  Returns (B,T,M) * norm_scale."""
+        z (K,B,1,M,T) (z[i] is consumed at step t=i).  Returns (B,T,M) * norm_scale.
+        ``trace`` (parity harness): a dict whose keys are step indices t; on return trace[t] is the denoiser output of
+        that step as (B,1,M,T) fp32.  Tracing runs the eager launches (bit-identical to the graph replay)."""
         den = self.denoise_fn
         B, H, T = cond_t.shape
         M = self.out_dim
@@ -242,39 +252,50 @@ class GaussianDiffusion(BaseModel):
         if den.resolved_precision() == "fp32":
             x = torch.randn((B, 1, M, T), device=device) if x_T is None else x_T.to(f32).clone()
             zz = torch.randn((self.K_step, B, 1, M, T), device=device) if z is None else z.to(f32).contiguous()
-            x = self._sample_loop_fp32(cond_t, x.contiguous(), zz)
+            x = self._sample_loop_fp32(cond_t, x.contiguous(), zz, trace)
             return (x[:, 0].transpose(1, 2) * self.norm_scale).contiguous()
 
         plan = den.bf16_plan()
         Mp = plan.Mp
         condb, _ = ops.nct_to_ntc(cond_t)
-        if x_T is None:
-            x32s = torch.randn((B, T, Mp), device=device)
-        else:
+        x32s = z_ntc = None
+        if x_T is not None:
             _, x32s = ops.nct_to_ntc(x_T[:, 0].to(f32).contiguous(), Cp=Mp, want_bf16=False, want_f32=True)
-        if z is None:
-            z_ntc = torch.randn((self.K_step, B, T, Mp), device=device)
-        else:
+        if z is not None:
             zf = z.to(f32).reshape(self.K_step * B, M, T).contiguous()
             _, z_ntc = ops.nct_to_ntc(zf, Cp=Mp, want_bf16=False, want_f32=True)
             z_ntc = z_ntc.view(self.K_step, B, T, Mp)
         self._step_table()  # make sure the table exists before a graph capture
-        if self.use_cuda_graph:
-            x32s = self._graph_replay(condb, x32s, z_ntc)
+        if self.use_cuda_graph and trace is None:
+            x32s = self._graph_replay(condb, x32s, z_ntc, (B, T, Mp))
         else:
-            x32s = self._sample_loop_bf16(condb, x32s, z_ntc)
+            # same draw order as the graph path: x_T first, then the K noise tensors
+            if x32s is None:
+                x32s = torch.randn((B, T, Mp), device=device)
+            if z_ntc is None:
+                z_ntc = torch.randn((self.K_step, B, T, Mp), device=device)
+            x32s = self._sample_loop_bf16(condb, x32s, z_ntc, trace)
+            if trace is not None:
+                for k in list(trace):
+                    if trace[k] is not None:
+                        trace[k] = trace[k][:, :, :M].transpose(1, 2)[:, None].contiguous()
         out = x32s[:, :, :M] * self.norm_scale
         return out.contiguous()
 
-    def _graph_replay(self, condb, x32s, z_ntc):
-        """Capture the whole K-step loop once per (B,T) and replay it (static buffers, ~26 K launches -> 1)."""
-        key = (tuple(condb.shape), tuple(x32s.shape), self.K_step, self.denoise_fn._param_key())
+    def _graph_replay(self, condb, x32s, z_ntc, xshape):
+        """Capture the whole K-step loop once per (B,T) and replay it (static buffers, ~26 K launches -> 1).
+        ``x32s`` / ``z_ntc`` None: the Gaussian draws go straight into the graph's static buffers (no 384 MB staging
+        tensor and copy per pass at BASELINE config 2)."""
+        zshape = (self.K_step,) + tuple(xshape)
+        key = (tuple(condb.shape), tuple(xshape), self.K_step, self.denoise_fn._param_key())
         ent = self._graphs.get(key)
         if ent is None:
             if len(self._graphs) >= 4:
                 self._graphs.clear()
-            s_cond, s_x, s_z = torch.empty_like(condb), torch.empty_like(x32s), torch.empty_like(z_ntc)
-            s_cond.copy_(condb); s_x.copy_(x32s); s_z.copy_(z_ntc)
+            s_cond = torch.empty_like(condb)
+            s_x = torch.zeros(xshape, device=condb.device, dtype=f32)
+            s_z = torch.zeros(zshape, device=condb.device, dtype=f32)
+            s_cond.copy_(condb)
             # warm-up outside capture (function attributes, tensor-map cache, allocator pools)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -289,13 +310,21 @@ class GaussianDiffusion(BaseModel):
             _L.launch_count = n0  # capture enqueues nothing; replays are counted below
             self._graphs[key] = ent
         g, s_cond, s_x, s_z, n_kernels = ent
-        s_cond.copy_(condb); s_x.copy_(x32s); s_z.copy_(z_ntc)
+        s_cond.copy_(condb)
+        if x32s is None:
+            s_x.normal_()
+        else:
+            s_x.copy_(x32s)
+        if z_ntc is None:
+            s_z.normal_()
+        else:
+            s_z.copy_(z_ntc)
         g.replay()
         _L.launch_count += n_kernels
         return s_x
 
     @torch.no_grad()
-    def inference(self, cond, lengths=None, spk_embs=None, *, x_T=None, z=None, cond_is_encoded=False):
+    def inference(self, cond, lengths=None, spk_embs=None, *, x_T=None, z=None, cond_is_encoded=False, trace=None):
         """diffusion.py:296-336.  ``cond_is_encoded``: ``cond`` already is the encoder's output (pipeline.py runs the
         encoders of several streams side by side), so the encoder is skipped."""
         self._require_cuda(cond)
@@ -313,7 +342,7 @@ class GaussianDiffusion(BaseModel):
             for i in reversed(range(0, t, interval)):
                 x = self.p_sample_plms(x, torch.full((B,), i, device=device, dtype=torch.long), interval, cond_c)
             return self._denorm(x[:, 0].transpose(1, 2), self.norm_scale)
-        return self.sample(cond, x_T=x_T, z=z)
+        return self.sample(cond, x_T=x_T, z=z, trace=trace)
 
 
 class MultiSpeakerGaussianDiffusion(GaussianDiffusion):

@@ -202,13 +202,8 @@ def diffnet_packed_rows(Cc):
 
 
 def diffnet_block_bf16(xb_in, xb_out, x32, skip32, cond, w1p, woutp, stepbias, bout, *, dilation, stepbias_batch_stride,
-                       init_skip, write_x=True, time_tile=0, kernel=None):
-    """kernel=3: CTA-pair kernel with the resident activation window (default; dilation <= 8, else kernel 2);
-    kernel=2: CTA-pair kernel streaming every tap; kernel=1: single-CTA kernel (time_tile selects its N tile)."""
-    if kernel is None:
-        kernel = 1 if time_tile else int(os.environ.get("SVSK_DIFFNET_KERNEL", "3"))
-        if kernel == 3 and int(dilation) > 8:
-            kernel = 2
+                       init_skip, write_x=True):
+    """One residual block per launch (svsk_diffnet_block3_bf16: CTA pair, resident activation window; dilation <= 8)."""
     B, T, Cc = xb_in.shape
     p = L.DiffnetBlockParams()
     p.xb_in, p.xb_out = L.ptr(xb_in, bf16, "xb_in"), L.ptr(xb_out, bf16, "xb_out")
@@ -217,9 +212,8 @@ def diffnet_block_bf16(xb_in, xb_out, x32, skip32, cond, w1p, woutp, stepbias, b
     p.stepbias, p.bout = L.ptr(stepbias, f32, "stepbias"), L.ptr(bout, f32, "bout")
     p.B, p.T, p.C, p.H = B, T, Cc, cond.shape[2]
     p.dilation, p.stepbias_batch_stride = int(dilation), int(stepbias_batch_stride)
-    p.init_skip, p.write_x, p.time_tile = int(init_skip), int(write_x), int(time_tile)
-    fn = {1: L.lib().svsk_diffnet_block_bf16, 2: L.lib().svsk_diffnet_block2_bf16, 3: L.lib().svsk_diffnet_block3_bf16}[kernel]
-    L.check(fn(C.byref(p), L.stream_ptr()), "diffnet_block_bf16")
+    p.init_skip, p.write_x, p.reserved0 = int(init_skip), int(write_x), 0
+    L.check(L.lib().svsk_diffnet_block3_bf16(C.byref(p), L.stream_ptr()), "diffnet_block_bf16")
 
 
 def diffnet_stack_fits(B, T, Cc, H):

@@ -123,10 +123,13 @@ class EnsembleSynthesizer:
     @torch.no_grad()
     def synthesize(self, cond_mgc: Sequence[torch.Tensor], cond_bap: Sequence[torch.Tensor], f0: Sequence[torch.Tensor],
                    world_size: int = 1, rank: int = 0,
-                   note_masks: Optional[Sequence[torch.Tensor]] = None) -> List[Optional[torch.Tensor]]:
+                   note_masks: Optional[Sequence[torch.Tensor]] = None,
+                   noise: Optional[dict] = None) -> List[Optional[torch.Tensor]]:
         """Per item i: cond_mgc[i] [T_i, H1], cond_bap[i] [T_i, H2], f0[i] [T_i, 1] (Hz, 0 = unvoiced), any device;
         note_masks[i] [T_i] bool (frames inside notes, for the GV post-filter).
-        Returns the waveforms [T_i * hop] of this rank's items in input order (None for items of other ranks)."""
+        Returns the waveforms [T_i * hop] of this rank's items in input order (None for items of other ranks).
+        ``noise`` (parity harness only; the call must form a single batch): {"mgc": (x_T, z), "bap": (x_T, z),
+        "vocoder": {"sine": ..., "noise": ...}} replaces the Gaussian draws of the three models, tracks in plan order."""
         n = len(cond_mgc)
         if not (len(cond_bap) == n and len(f0) == n):
             raise ValueError("cond_mgc, cond_bap and f0 must have one entry per item")
@@ -137,14 +140,20 @@ class EnsembleSynthesizer:
         dev = next(self.mgc.parameters()).device
         hop = int(self.vocoder.config.data.hop_size)
         out: List[Optional[torch.Tensor]] = [None] * n
-        for plan in plan_batches(lengths, self.max_frames, world_size, rank):
+        plans = plan_batches(lengths, self.max_frames, world_size, rank)
+        if noise is not None and len(plans) != 1:
+            raise ValueError("noise injection needs all items in one batch")
+        nz = noise or {}
+        for plan in plans:
             cm = torch.stack([_pad_time(cond_mgc[i].to(dev, torch.float32), plan.frames, "replicate") for i in plan.items])
             cb = torch.stack([_pad_time(cond_bap[i].to(dev, torch.float32), plan.frames, "replicate") for i in plan.items])
             f = torch.stack([_pad_time(f0[i].to(dev, torch.float32), plan.frames, "zeros") for i in plan.items])
             lens = [lengths[i] for i in plan.items]         # used by the streams' encoders (packed BiLSTM), if any
             hm, hb = self._encode(cm, cb, lens)
-            m = self.mgc.inference(hm, cond_is_encoded=True)   # [B, T, M1]
-            b = self.bap.inference(hb, cond_is_encoded=True)   # [B, T, M2]
+            xm, zm = nz.get("mgc", (None, None))
+            xb_, zb_ = nz.get("bap", (None, None))
+            m = self.mgc.inference(hm, cond_is_encoded=True, x_T=xm, z=zm)   # [B, T, M1]
+            b = self.bap.inference(hb, cond_is_encoded=True, x_T=xb_, z=zb_)   # [B, T, M2]
             if self.vuv is not None:
                 v = self.vuv.inference(torch.cat([cm[..., :-1], m, cm[..., -1:]], dim=-1).contiguous(), lens)   # [B, T, 1]
                 if self.out_scaler_vuv is not None:
@@ -167,7 +176,10 @@ class EnsembleSynthesizer:
             aux = self.aux_fn(m, b, f).contiguous()
             if self.vocoder_in_scaler is not None:
                 aux = self.vocoder_in_scaler.transform(aux)
-            wav = self.vocoder.inference_batch(f, aux)       # [B, 1, T * hop]
+            if "vocoder" in nz:
+                wav = self.vocoder.inference_batch(f, aux, noise=nz["vocoder"])
+            else:
+                wav = self.vocoder.inference_batch(f, aux)       # [B, 1, T * hop]
             for k, i in enumerate(plan.items):
                 out[i] = wav[k, 0, :lengths[i] * hop].clone()
         return out

@@ -14,8 +14,10 @@ class USFGANWrapper(nn.Module):
         self.config = config
 
     @torch.no_grad()
-    def inference(self, f0, aux_feats):
-        """f0: numpy (T, 1); aux_feats: Tensor (T, C) on the generator's device -> waveform (1, 1, T * hop)."""
+    def inference(self, f0, aux_feats, *, noise=None):
+        """f0: numpy (T, 1); aux_feats: Tensor (T, C) on the generator's device -> waveform (1, 1, T * hop).
+        ``noise`` (parity harness only): {"sine": ..., "noise": ...} tensors (1, 1, T * hop) that replace the source
+        signal's two Gaussian draws."""
         data = self.config.data
         assert data.sine_f0_type in ["contf0", "cf0", "f0"]
         assert data.df_f0_type in ["contf0", "cf0", "f0"]
@@ -30,13 +32,14 @@ class USFGANWrapper(nn.Module):
         signal_generator = SignalGenerator(sample_rate=data.sample_rate, hop_size=data.hop_size,
                                            sine_amp=data.sine_amp, noise_amp=data.noise_amp,
                                            signal_types=data.signal_types)
+        signal_generator.injected_noise = noise
         in_signal = signal_generator(f0)
         if getattr(self.generator, "supports_wave_only", False):
             return self.generator(in_signal, c.contiguous(), df, wave_only=True)[0]
         return self.generator(in_signal, c.contiguous(), df)[0]
 
     @torch.no_grad()
-    def inference_batch(self, f0, aux_feats):
+    def inference_batch(self, f0, aux_feats, *, noise=None):
         """Batched form of ``inference`` (the reference wrapper has no batch dimension and the
         multi-track synthesis loops over tracks, synthesis_multitrack.py:113-118).
 
@@ -65,6 +68,7 @@ class USFGANWrapper(nn.Module):
         signal_generator = SignalGenerator(sample_rate=data.sample_rate, hop_size=data.hop_size,
                                            sine_amp=data.sine_amp, noise_amp=data.noise_amp,
                                            signal_types=data.signal_types)
+        signal_generator.injected_noise = noise
         in_signal = signal_generator(f0)
         if getattr(self.generator, "supports_wave_only", False):
             return self.generator(in_signal, c.contiguous(), df.contiguous(), wave_only=True)[0]

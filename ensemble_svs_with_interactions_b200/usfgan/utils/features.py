@@ -33,6 +33,17 @@ class SignalGenerator:
         self.sine_amp = sine_amp
         self.noise_amp = noise_amp
         self.signal_types = signal_types
+        # parity harness only: {"sine": (B,1,T) tensor, "noise": (B,1,T) tensor} replaces the two Gaussian draws
+        # (the reference draws them from torch's global generator, features.py:131,160 — CPU and CUDA streams differ)
+        self.injected_noise = None
+
+    def _randn(self, which, shape, device):
+        if self.injected_noise is not None and which in self.injected_noise:
+            z = self.injected_noise[which].to(device=device, dtype=torch.float32)
+            if tuple(z.shape) != tuple(shape):
+                raise ValueError(f"injected {which} noise has shape {tuple(z.shape)}, expected {tuple(shape)}")
+            return z
+        return torch.randn(shape, device=device)
 
     def _hold(self, frames):
         # F.interpolate(nearest) rather than repeat_interleave: identical index arithmetic to the reference
@@ -43,7 +54,7 @@ class SignalGenerator:
 
     @torch.no_grad()
     def random_noise(self, f0):
-        return torch.randn((f0.shape[0], 1, f0.shape[-1] * self.hop_size), device=f0.device)
+        return self._randn("noise", (f0.shape[0], 1, f0.shape[-1] * self.hop_size), f0.device)
 
     @torch.no_grad()
     def vuv_binary(self, f0):
@@ -58,7 +69,7 @@ class SignalGenerator:
         if self.noise_amp > 0:
             # voiced frames get noise_amp, unvoiced ones a third of it (NSF)
             sigma = voiced * self.noise_amp + (1.0 - voiced) * self.noise_amp / 3.0
-            wave = wave + torch.randn(wave.shape, device=f0.device) * sigma
+            wave = wave + self._randn("sine", wave.shape, f0.device) * sigma
         return wave
 
     @torch.no_grad()

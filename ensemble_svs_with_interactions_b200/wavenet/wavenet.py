@@ -52,20 +52,26 @@ class WaveNet(nn.Module):
         for t in steps:
             if t > 0:
                 current = outputs[-1]
-            ct = c[:, t, :].unsqueeze(1)
-            x = self.first_conv.incremental_forward(current)
-            skips = 0
-            for f in self.main_conv_layers:
-                x, h = f.incremental_forward(x, ct)
-                skips = skips + h
-            x = skips
-            for f in self.last_conv_layers:
-                x = f.incremental_forward(x) if hasattr(f, "incremental_forward") else f(x)
+            x = self.incremental_logits(current, c[:, t, :].unsqueeze(1))
             probs = F.softmax(x.view(B, -1), dim=1)
             outputs.append(torch.distributions.OneHotCategorical(probs).sample().view(B, 1, -1))
         out = torch.cat(outputs, dim=1)
         self.clear_buffer()
         return out
+
+    @torch.no_grad()
+    def incremental_logits(self, current, ct):
+        """One step of the incremental network (wavenet.py:117-139): current (B,1,out_dim) = the previous frame's
+        output (zeros at t = 0), ct (B,1,in_dim) -> logits (B,1,out_dim); the per-layer ring buffers advance by one."""
+        x = self.first_conv.incremental_forward(current)
+        skips = 0
+        for f in self.main_conv_layers:
+            x, h = f.incremental_forward(x, ct)
+            skips = skips + h
+        x = skips
+        for f in self.last_conv_layers:
+            x = f.incremental_forward(x) if hasattr(f, "incremental_forward") else f(x)
+        return x
 
     def clear_buffer(self):
         self.first_conv.clear_buffer()

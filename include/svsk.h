@@ -183,22 +183,18 @@ typedef struct svsk_diffnet_block_params {
   int32_t stepbias_batch_stride; /* in floats; 0 = same for every batch row */
   int32_t init_skip;   /* 1: skip32 = ..., 0: skip32 += ... */
   int32_t write_x;     /* 0 on the last layer (x is dead after it, denoiser.py:117-120) */
-  int32_t time_tile;   /* 0 = choose; else one of 32..128, multiple of 16 */
+  int32_t reserved0;   /* must be 0 (was: time tile of the retired single-CTA kernel) */
 } svsk_diffnet_block_params;
-SVSK_API int svsk_diffnet_block_bf16(const svsk_diffnet_block_params* p, void* stream);
 
-/* Same contract and packed operands, CTA-pair kernel (tcgen05 cta_group::2, clusters of 2): time is the MMA M
- * dimension (256 frames per pair), each SM stages half of every weight tile, N = 256 per MMA.  `time_tile` is ignored.
- * Additionally requires x32 / skip32 / xb_out to be 16-byte aligned. */
-SVSK_API int svsk_diffnet_block2_bf16(const svsk_diffnet_block_params* p, void* stream);
-
-/* Same contract and packed operands again, CTA-pair kernel with a resident activation window: the three taps of the
- * dilated conv (denoiser.py:33-35,58) are one (128 + 16)-row shared-memory tile per 64 channels addressed at row
- * offsets -d / 0 / +d, so activations are read once per tile and only weights stream through the ring.  Requires
- * dilation <= 8 (the reference's dilation_cycle_length = 4 gives 1, 2, 4, 8; use svsk_diffnet_block2_bf16 beyond).
+/* The per-layer kernel: CTA pair (tcgen05 cta_group::2, clusters of 2), time is the MMA M dimension (256 frames per
+ * pair), with a resident activation window: the three taps of the dilated conv (denoiser.py:33-35,58) are one
+ * (128 + 16)-row shared-memory tile per 64 channels addressed at row offsets -d / 0 / +d, so activations are read once
+ * per tile and only weights stream through the ring.  Requires dilation <= 8 (the reference's dilation_cycle_length = 4
+ * gives 1, 2, 4, 8; wider cycles are served by the fp32 kernels — DiffNet(precision="auto") selects them) and x32 /
+ * skip32 / xb_out 16-byte aligned; x32 is not used (the residual stream is carried in bf16).
  * Launched with programmatic stream serialization: the packed weights w1p / woutp are read BEFORE the kernel waits for
  * its predecessor in the stream, so they must not be written by the kernel launched immediately before this one
- * (pack once, up front); every other operand may be.  This is the kernel the drop-in modules use. */
+ * (pack once, up front); every other operand may be.  Used when a track is too long for svsk_diffnet_stack_bf16. */
 SVSK_API int svsk_diffnet_block3_bf16(const svsk_diffnet_block_params* p, void* stream);
 
 /* All L residual blocks of one denoiser call in ONE launch (the loop denoiser.py:114-118): every CTA pair keeps its

@@ -263,6 +263,77 @@ def golden_frontend(ns):
           {}, dict(f0=f0, noise_sine=n_sine, noise_in=n_in), dict(in_signal=sig, df=df.astype(np.float64)))
 
 
+def golden_wrapper(ns):
+    """The whole ``USFGANWrapper.inference`` call (nnsvs/usfgan/__init__.py:13-65) at the recipe's widths (64/128/64,
+    aux 80, 24 kHz, hop 120, upsample 5*4*3*2) with short stacks: f0 + aux in, waveform out.  The two Gaussian draws of
+    the source signal are recorded (the reference takes them from torch's global CPU generator)."""
+    from types import SimpleNamespace as NS
+    g = torch.Generator().manual_seed(71)
+    torch.manual_seed(72)
+    hp = {"blockA": 4, "cycleA": 2, "blockF": 0, "cycleF": 0, "cascade_mode": 0}
+    np_ = {"blockA": 0, "cycleA": 0, "blockF": 2, "cycleF": 2, "cascade_mode": 0}
+    fp = {"blockA": 0, "cycleA": 0, "blockF": 6, "cycleF": 3, "cascade_mode": 0}
+    pe = {"conv_layers": 3, "kernel_size": 5, "dilation": 1, "padding_mode": "replicate"}
+    m = ns.ParallelHnUSFGANGenerator(harmonic_network_params=dict(hp), noise_network_params=dict(np_),
+                                     filter_network_params=dict(fp), periodicity_estimator_params=dict(pe)).eval()
+    for n, p in m.named_parameters():
+        if n.endswith("bias"):
+            _rerandomize(p, 0.1, g)
+    last = m.periodicity_estimator.layers[-2]
+    _rerandomize(last.weight_v, 0.2, g)
+    m.remove_weight_norm()
+
+    class Cfg(dict):
+        __getattr__ = dict.__getitem__
+    fs, hop, Fr = 24000, 120, 40
+    config = NS(data=NS(sample_rate=fs, hop_size=hop, sine_amp=0.1, noise_amp=0.003, signal_types=["sine", "noise"],
+                        sine_f0_type="contf0", df_f0_type="contf0", dense_factor=4),
+                generator=Cfg(aux_context_window=2))
+    f0 = _f0_track(Fr, g, 110.0, 660.0).numpy().astype(np.float32)[:, None]
+    aux = torch.randn(Fr, 80, generator=g)
+    torch.manual_seed(73)
+    with torch.no_grad():
+        wav = ns.USFGANWrapper(config, m).inference(f0.copy(), aux)
+    torch.manual_seed(73)  # the same draws, in the reference's order: the sine's additive noise, then the noise channel
+    n_sine = torch.randn(1, 1, Fr * hop)
+    n_in = torch.randn(1, 1, Fr * hop)
+    _save("usfgan_wrapper", dict(harmonic=hp, noise=np_, filt=fp, pe=pe, sample_rate=fs, hop_size=hop, dense_factor=4,
+                                 sine_amp=0.1, noise_amp=0.003, aux_context_window=2),
+          m.state_dict(), dict(f0=f0, aux=aux, noise_sine=n_sine, noise_in=n_in), dict(wav=wav))
+
+
+def golden_wavenet_incremental(ns):
+    """Teacher-forced incremental evaluation (the loop body of WaveNet.inference, wavenet.py:117-139, fed a given
+    one-hot sequence instead of its own samples) next to the parallel forward of the same network."""
+    torch.manual_seed(81)
+    g = torch.Generator().manual_seed(82)
+    cfg = dict(in_dim=20, out_dim=12, layers=6, stacks=2, residual_channels=16, gate_channels=32, skip_out_channels=16,
+               kernel_size=3)
+    m = ns.WaveNet(**cfg).eval()
+    for n, p in m.named_parameters():
+        if n.endswith("bias"):
+            _rerandomize(p, 0.1, g)
+    B, T = 2, 30
+    c = torch.randn(B, T, cfg["in_dim"], generator=g)
+    x = torch.nn.functional.one_hot(torch.randint(0, cfg["out_dim"], (B, T), generator=g), cfg["out_dim"]).float()
+    with torch.no_grad():
+        par = m(c, x)
+        m.clear_buffer()
+        inc = []
+        for t in range(T):
+            h = m.first_conv.incremental_forward(x[:, t:t + 1])
+            skips = 0
+            for f in m.main_conv_layers:
+                h, sk = f.incremental_forward(h, c[:, t:t + 1])
+                skips = skips + sk
+            h = skips
+            for f in m.last_conv_layers:
+                h = f.incremental_forward(h) if hasattr(f, "incremental_forward") else f(h)
+            inc.append(h)
+        m.clear_buffer()
+    _save("wavenet_incremental", cfg, m.state_dict(), dict(c=c, x=x), dict(parallel=par, incremental=torch.cat(inc, dim=1)))
+
+
 def golden_encoder(ns):
     """FFConvLSTM in eval mode (model.py:779-926): the recipe's embedding front with ragged lengths and all-zero phoneme
     blocks, and the shape of the reference's own test (tests/test_model.py:190-205)."""
@@ -334,13 +405,12 @@ def main():
     ns = load_reference()
     assert not torch.cuda.is_available(), "run with CUDA_VISIBLE_DEVICES='' (index.py calls .cuda())"
     torch.set_num_threads(1)  # deterministic reduction order
-    golden_diffnet(ns)
-    golden_diffusion(ns)
-    golden_wavenet(ns)
-    golden_usfgan(ns)
-    golden_frontend(ns)
-    golden_encoder(ns)
-    golden_postprocess(ns)
+    makers = [golden_diffnet, golden_diffusion, golden_wavenet, golden_usfgan, golden_frontend, golden_encoder,
+              golden_postprocess, golden_wrapper, golden_wavenet_incremental]
+    only = set(sys.argv[1:])          # e.g. "golden_wrapper": regenerate that fixture only
+    for mk in makers:
+        if not only or mk.__name__ in only:
+            mk(ns)
 
 
 if __name__ == "__main__":

@@ -235,12 +235,13 @@ def q_sample(tab: Dict[str, Tensor], x0: Tensor, t: Tensor, noise: Tensor) -> Te
 
 def diffusion_inference(sd: SD, cond: Tensor, x_T: Tensor, z: Tensor, *, K_step: int,
                         residual_layers: int, dilation_cycle_length: int, norm_scale: float = 10.0,
-                        return_trajectory: bool = False):
+                        return_trajectory: bool = False, keep_steps: Optional[Sequence[int]] = None):
     """GaussianDiffusion.inference with INJECTED noise (diffusion.py:302-336, encoder=None).
 
     ``sd`` is the GaussianDiffusion state_dict (12 buffers + ``denoise_fn.*``).
     cond (B,T,H); x_T (B,1,M,T); z (K,B,1,M,T) with z[i] consumed at step t=i.
-    Returns (B,T,M) [, list of per-step (eps, x)].
+    Returns (B,T,M) [, list of per-step (eps, x)]; with ``keep_steps`` the second value is {t: (eps, x)} for those
+    steps only (full-size runs: 100 x 2 tensors would not fit comfortably).
     """
     den = {k[len("denoise_fn."):]: v for k, v in sd.items() if k.startswith("denoise_fn.")}
     tab = {k: sd[k] for k in SCHEDULE_BUFFERS}
@@ -252,9 +253,14 @@ def diffusion_inference(sd: SD, cond: Tensor, x_T: Tensor, z: Tensor, *, K_step:
         t = torch.full((B,), i, dtype=torch.long)
         eps = diffnet_forward(den, x, t, c, residual_layers, dilation_cycle_length)
         x = ddpm_update(tab, x, t, eps, z[i])
-        if return_trajectory:
+        if keep_steps is not None:
+            if i in keep_steps:
+                traj.append((i, (eps, x)))
+        elif return_trajectory:
             traj.append((eps, x))
     out = x[:, 0].transpose(1, 2) * norm_scale
+    if keep_steps is not None:
+        return out, dict(traj)
     return (out, traj) if return_trajectory else out
 
 

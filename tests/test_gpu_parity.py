@@ -339,10 +339,10 @@ def _random_diffnet(C, H, M, L, seed, cycle=4):
     return m.eval()
 
 
-@pytest.mark.parametrize("C,H,T,dil,tile", [(256, 256, 333, 1, 0), (256, 256, 333, 8, 96), (256, 128, 200, 4, 128),
-                                            (128, 128, 97, 2, 32), (256, 256, 40, 8, 64), (128, 64, 517, 1, 112),
-                                            (256, 256, 256, 2, 0), (256, 256, 1000, 8, 0), (128, 128, 300, 4, 0)])
-def test_diffnet_block_bf16_single_layer(C, H, T, dil, tile):
+@pytest.mark.parametrize("C,H,T,dil", [(256, 256, 333, 1), (256, 256, 333, 8), (256, 128, 200, 4),
+                                       (128, 128, 97, 2), (256, 256, 40, 8), (128, 64, 517, 1),
+                                       (256, 256, 256, 2), (256, 256, 1000, 8), (128, 128, 300, 4)])
+def test_diffnet_block_bf16_single_layer(C, H, T, dil):
     """One fused block vs the oracle block evaluated on the same bf16-rounded operands (tight: isolates the kernel)."""
     ops = _ops()
     m = _random_diffnet(C, H, 16, 1, seed=C + T + dil)
@@ -372,23 +372,20 @@ def test_diffnet_block_bf16_single_layer(C, H, T, dil, tile):
     _, skip32 = ops.nct_to_ntc(skip0.to(DEV), want_bf16=False, want_f32=True)
     condb, _ = ops.nct_to_ntc(cond.to(DEV))
     sb = ops.linear_f32(dp.to(DEV), lw["stepw"], lw["stepb"])
-    for kernel in ((1,) if tile else (3, 2)):   # 3 = resident window (default), 2 = every tap streamed, 1 = single CTA
-        xb_out = torch.full_like(xbd, float("nan"))
-        _, skip32 = ops.nct_to_ntc(skip0.to(DEV), want_bf16=False, want_f32=True)
-        ops.diffnet_block_bf16(xbd, xb_out, x32, skip32, condb, lw["w1p"], lw["woutp"], sb, lw["bout"], dilation=dil,
-                               stepbias_batch_stride=6 * C, init_skip=False, write_x=True, time_tile=tile, kernel=kernel)
-        torch.cuda.synchronize()
-        close_bf16(skip32.transpose(1, 2), s_ref, 3e-3, 1e-2)
-        if tile:   # single-CTA kernel: fp32 residual master + its bf16 copy
-            close_bf16(x32.transpose(1, 2), x_ref, 3e-3, 1e-2)
-            assert torch.equal(xb_out.float(), x32.to(torch.bfloat16).float())
-        else:      # CTA-pair kernels: the residual stream is carried in bf16 (reference: x_ref from bf16(x))
-            x_ref_b = (_bf(x) + o[:, :C]) / math.sqrt(2.0)
-            close_bf16(xb_out.float().transpose(1, 2), x_ref_b, 4e-3, 1e-2)
+    xb_out = torch.full_like(xbd, float("nan"))
+    ops.diffnet_block_bf16(xbd, xb_out, x32, skip32, condb, lw["w1p"], lw["woutp"], sb, lw["bout"], dilation=dil,
+                           stepbias_batch_stride=6 * C, init_skip=False, write_x=True)
+    torch.cuda.synchronize()
+    close_bf16(skip32.transpose(1, 2), s_ref, 3e-3, 1e-2)
+    # the residual stream is carried in bf16 (reference: x_ref from bf16(x))
+    x_ref_b = (_bf(x) + o[:, :C]) / math.sqrt(2.0)
+    close_bf16(xb_out.float().transpose(1, 2), x_ref_b, 4e-3, 1e-2)
 
 
-def test_diffnet_block3_rejects_wide_dilation_and_default_falls_back():
-    """The resident window holds 8 halo rows: kernel 3 refuses dilation 16, the default selection uses kernel 2 there."""
+def test_diffnet_wide_dilation_runs_on_the_fp32_kernels():
+    """The resident window holds 8 halo rows: the tensor-core kernels refuse dilation 16 (loudly), and a DiffNet whose
+    dilation cycle exceeds 4 resolves to the fp32 kernels under precision="auto" — with the oracle's numbers."""
+    from ensemble_svs_with_interactions_b200.diffsinger import DiffNet
     ops = _ops()
     C = 128
     m = _random_diffnet(C, 64, 16, 1, seed=3).to(DEV)
@@ -397,12 +394,20 @@ def test_diffnet_block3_rejects_wide_dilation_and_default_falls_back():
     x32 = torch.zeros(1, 200, C, device=DEV); skip = torch.zeros(1, 200, C, device=DEV)
     cond = torch.zeros(1, 200, 64, device=DEV, dtype=torch.bfloat16)
     sb = torch.zeros(1, 6 * C, device=DEV)
-    kw = dict(dilation=16, stepbias_batch_stride=6 * C, init_skip=True, write_x=True)
     with pytest.raises(RuntimeError, match="resident window"):
-        ops.diffnet_block_bf16(xb, out, x32, skip, cond, lw["w1p"], lw["woutp"], sb, lw["bout"], kernel=3, **kw)
-    ops.diffnet_block_bf16(xb, out, x32, skip, cond, lw["w1p"], lw["woutp"], sb, lw["bout"], **kw)
-    torch.cuda.synchronize()
-    assert torch.isfinite(out.float()).all()
+        ops.diffnet_block_bf16(xb, out, x32, skip, cond, lw["w1p"], lw["woutp"], sb, lw["bout"], dilation=16,
+                               stepbias_batch_stride=6 * C, init_skip=True, write_x=True)
+    wide = _random_diffnet(C, 64, 16, 6, seed=4, cycle=6)          # dilations 1 .. 32
+    assert wide.resolved_precision() == "fp32"
+    wide.precision = "bf16"
+    with pytest.raises(RuntimeError, match="dilations <= 8"):
+        wide.resolved_precision()
+    wide.precision = "auto"
+    g = torch.Generator().manual_seed(5)
+    spec = torch.randn(2, 1, 16, 150, generator=g); cnd = torch.randn(2, 64, 150, generator=g); t = torch.tensor([5, 60])
+    ref = O.diffnet_forward({k: v.detach() for k, v in wide.state_dict().items()}, spec, t, cnd, 6, 6)
+    wide = wide.to(DEV)
+    close32(wide(spec.to(DEV), t.to(DEV), cnd.to(DEV)), ref, 5e-4)
 
 
 @pytest.mark.parametrize("C,H,M,L,B,T", [(256, 256, 80, 6, 2, 300), (256, 256, 80, 5, 1, 1000), (128, 128, 5, 6, 3, 517),

@@ -2,7 +2,7 @@
 // shapes the block kernels use, operands resident in shared memory (no TMA traffic), one issuing thread.
 #include <cuda_bf16.h>
 
-#include "sm100_ptx.cuh"
+#include "sm100_ptx.cuh"  // -I ensemble_svs_with_interactions_b200/csrc (csrc/build.py:build_ubench)
 #include "svsk_common.cuh"
 
 namespace svsk {

@@ -6,9 +6,9 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-from ensemble_svs_with_interactions_b200 import _lib  # noqa: E402
+from ensemble_svs_with_interactions_b200.csrc.build import build_ubench  # noqa: E402
 
-l = C.CDLL(_lib.LIB_PATH)
+l = C.CDLL(build_ubench())   # tools/libsvsk_ubench.so — the micro-benchmarks are not part of the product libsvsk.so
 l.svsk_ubench_umma.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
 l.svsk_last_error.restype = C.c_char_p
 iters = 2000
