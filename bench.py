@@ -9,8 +9,14 @@ sampling pass over one batch; the metric is denoiser frame-steps per second (B*T
 
 N > 1 (torchrun): every rank samples its own 6-track batch (tracks are independent work items, no data-path
 collective) -> weak scaling; the time is the max over ranks.
---impl reference: the reference's CPU arithmetic (oracle port, torch CPU fp32, all host threads) on a bounded sample
-of the same workload; rank 0 only.
+--impl reference: the UNMODIFIED reference modules (baseline/_ref, loaded through oracle/ref_shim.py; the oracle port if
+no reference tree travelled) on the box's host cores, fp32, all host threads, on a bounded sample of the same workload;
+rank 0 only.
+
+Besides the headline (config 2) the line carries, for every N: "vocoder" (config 3, one batch per rank), "pipeline"
+(config 4: 64 songs split over the ranks by sharding.assign, STRONG scaling), "training" (config 5: DDP step, 6 x 1000
+frames per rank); and at N = 1 also "wavenet" (config 1, GPU and reference CPU), "reference_gpu_eager" (the reference's
+own modules in eager PyTorch on this GPU: the on-box bar) and "cpu_baseline".
 """
 import argparse
 import json
@@ -30,6 +36,15 @@ CFG = dict(in_dim=80, encoder_hidden_dim=256, residual_layers=20, residual_chann
 K_STEP, B, T = 100, 6, 2000
 MAC_PER_FRAME_STEP = 13_213_696          # reference formulation incl. conditioner projection
 BLOCK_MAC_PER_FRAME = 655_360            # one fused block launch: 2C*(3C+H) + 2C*C per frame
+METRIC = "denoiser frame-steps/sec (DiffNet 20x256, 100-step DDPM sampling)"
+# identical in both arms (the driver compares it)
+CONFIG = {"workload": f"DiffNet(80,256,L20,C256) 100-step DDPM sampling, {B} tracks x {T} frames per GPU",
+          "sharding": "one 6-track batch per rank, no collective",
+          "l2": "GPU arm: 256 MB flush between timed passes; the 384 MB noise tensor of a pass exceeds L2"}
+
+
+STACK_NCU_SUMMARY = "r01z_stack_ncu_full_summary.json"        # dram bytes of diffnet_stack_kernel (ncu --set full)
+USFGAN_NCU_SUMMARY = "r01z_usfgan_block_ncu_full_summary.json"
 
 
 def _peaks():
@@ -100,36 +115,121 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
-def cpu_baseline(sample_steps=2, threads=None):
-    """Oracle port (torch CPU fp32 == the arithmetic the reference runs on a CPU host) on a bounded sample:
-    `sample_steps` DDPM steps of the full B x T batch.  Returns (frame-steps/s, cores, description, seconds)."""
-    from oracle import svs_oracle as O
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    m = build_model()
-    sd = {k: v.detach() for k, v in m.state_dict().items()}
-    g = torch.Generator().manual_seed(1234)
-    cond = torch.randn(B, T, CFG["encoder_hidden_dim"], generator=g)
-    x_T = torch.randn(B, 1, CFG["in_dim"], T, generator=g)
-    z = torch.randn(K_STEP, B, 1, CFG["in_dim"], T, generator=g)[:sample_steps]
-    den = {k[len("denoise_fn."):]: v for k, v in sd.items() if k.startswith("denoise_fn.")}
-    tab = {k: sd[k] for k in O.SCHEDULE_BUFFERS}
-    c = cond.transpose(1, 2).contiguous()
+def load_reference_modules():
+    """The unmodified reference classes (baseline/_ref or /root/reference) or None."""
+    try:
+        from oracle import ref_shim
+        if ref_shim.reference_available():
+            return ref_shim.load_reference()
+    except Exception as e:      # a broken install must not take the bench down: fall back to the port, and say so
+        print(f"bench.py: reference modules unavailable ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+    return None
 
-    def run():
-        x = x_T
-        for i in reversed(range(K_STEP - sample_steps, K_STEP)):
-            t = torch.full((B,), i, dtype=torch.long)
-            eps = O.diffnet_forward(den, x, t, c, CFG["residual_layers"], CFG["dilation_cycle_length"])
-            x = O.ddpm_update(tab, x, t, eps, z[i - (K_STEP - sample_steps)])
-        return x
+
+def reference_model(ns, seed=1234):
+    """nnsvs.diffsinger.GaussianDiffusion(DiffNet) at BASELINE config 2, built by the reference's own constructors."""
+    torch.manual_seed(seed)
+    den = ns.DiffNet(**CFG)
+    with torch.no_grad():
+        den.output_projection.weight.normal_(0, 0.02)
+    return ns.GaussianDiffusion(in_dim=CFG["encoder_hidden_dim"], out_dim=CFG["in_dim"], denoise_fn=den, K_step=K_STEP).eval()
+
+
+def reference_steps(device, sample_steps, repeats=1, threads=None):
+    """`sample_steps` DDPM steps of the full B x T batch through the reference's stock code path (GaussianDiffusion.
+    p_sample -> DiffNet.forward, diffusion.py:193-204) on `device`; the oracle port when no reference tree is present.
+    Returns (frame-steps/s, kind, description, seconds per repeat, threads)."""
+    threads = threads or os.cpu_count() or 1
+    if device.type == "cpu":
+        torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(1234)
+    cond = torch.randn(B, T, CFG["encoder_hidden_dim"], generator=g).transpose(1, 2).contiguous().to(device)
+    x_T = torch.randn(B, 1, CFG["in_dim"], T, generator=g).to(device)
+    ns = load_reference_modules()
+    if ns is not None:
+        m = reference_model(ns).to(device)
+        kind = "reference"
+
+        def run():
+            x = x_T
+            for i in reversed(range(K_STEP - sample_steps, K_STEP)):
+                x = m.p_sample(x, torch.full((B,), i, device=device, dtype=torch.long), cond)
+            return x
+    else:
+        from oracle import svs_oracle as O
+        m = build_model()
+        sd = {k: v.detach().to(device) for k, v in m.state_dict().items()}
+        den = {k[len("denoise_fn."):]: v for k, v in sd.items() if k.startswith("denoise_fn.")}
+        tab = {k: sd[k] for k in O.SCHEDULE_BUFFERS}
+        kind = "port"
+
+        def run():
+            x = x_T
+            for i in reversed(range(K_STEP - sample_steps, K_STEP)):
+                t = torch.full((B,), i, dtype=torch.long, device=device)
+                eps = O.diffnet_forward(den, x, t, cond, CFG["residual_layers"], CFG["dilation_cycle_length"])
+                x = O.ddpm_update(tab, x, t, eps, torch.randn_like(x))
+            return x
+
+    def sync():
+        if device.type == "cuda":
+            torch.cuda.synchronize(device)
 
     with torch.no_grad():
         run()  # warm-up
+        sync()
         t0 = time.perf_counter()
-        run()
-        dt = time.perf_counter() - t0
-    return B * T * sample_steps / dt, threads, f"{sample_steps} of {K_STEP} DDPM steps of the full {B}x{T} batch", dt
+        for _ in range(repeats):
+            run()
+        sync()
+        dt = (time.perf_counter() - t0) / repeats
+    return (B * T * sample_steps / dt, kind,
+            f"{sample_steps} of {K_STEP} DDPM steps of the full {B}x{T} batch (p_sample -> DiffNet.forward, fp32)", dt, threads)
+
+
+def cpu_baseline(sample_steps=2, threads=None):
+    v, kind, sample, dt, threads = reference_steps(torch.device("cpu"), sample_steps, threads=threads)
+    return {"value": v, "unit": "frame-steps/s", "cores": threads, "kind": kind, "sample": sample, "seconds": dt}
+
+
+def wavenet_bench(dev):
+    """BASELINE configs[0]: nnsvs WaveNet forward at the shapes of the reference's tests/test_wavenet.py (in_dim 300,
+    out_dim 206, layers 2), batch 2 x 200 frames, fp32 — this library on the GPU, the reference module on the host."""
+    from ensemble_svs_with_interactions_b200.wavenet import WaveNet
+    kw = dict(in_dim=300, out_dim=206, layers=2)
+    Bw, Tw = 2, 200
+    torch.manual_seed(1234)
+    m = WaveNet(**kw).to(dev).eval()
+    g = torch.Generator().manual_seed(1234)
+    c, x = torch.rand(Bw, Tw, 300, generator=g), torch.rand(Bw, Tw, 206, generator=g)
+    cd, xd = c.to(dev), x.to(dev)
+    for _ in range(5):
+        m(cd, xd)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 50
+    e0.record()
+    for _ in range(reps):
+        m(cd, xd)
+    e1.record(); e1.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    out = {"metric": "WaveNet forward frames/sec (in 300, out 206, layers 2, B 2 x T 200, fp32)", "value": Bw * Tw / (ms / 1e3),
+           "unit": "frames/s", "ms_per_forward": ms, "dtype": "f32"}
+    ns = load_reference_modules()
+    if ns is not None:
+        torch.manual_seed(1234)
+        ref = ns.WaveNet(**kw).eval()
+        torch.set_num_threads(os.cpu_count() or 1)
+        with torch.no_grad():
+            for _ in range(3):
+                ref(c, x)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                ref(c, x)
+            cpu_ms = (time.perf_counter() - t0) / 20 * 1e3
+        out["cpu_reference"] = {"value": Bw * Tw / (cpu_ms / 1e3), "unit": "frames/s", "ms_per_forward": cpu_ms,
+                                "cores": os.cpu_count(), "kind": "reference"}
+    return out
 
 
 def vocoder_bench(dev, peaks, tracks=6, seconds=30.0, reps=3):
@@ -178,7 +278,7 @@ def vocoder_bench(dev, peaks, tracks=6, seconds=30.0, reps=3):
             "unit": "audio-sec/s", "ms_per_pass": ms, "precision": m.resolved_precision(),
             "config": {"workload": f"{tracks} tracks x {seconds:.0f} s @ 24 kHz, hop 120, aux 80, 20A+5F+30F blocks"},
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                         "traffic": _ncu_traffic("r01z_usfgan_block_ncu_full_summary.json"), "kernel": "usfgan_block_kernel", "us_per_launch": blk_ms * 1e3,
+                         "traffic": _ncu_traffic(USFGAN_NCU_SUMMARY), "kernel": "usfgan_block_kernel", "us_per_launch": blk_ms * 1e3,
                          "tflops": 2.0 * tracks * Tn * 38912 / (blk_ms * 1e-3) / 1e12}}
 
 
@@ -187,17 +287,17 @@ def run_reference(args, rank):
         return
     vals = []
     for i in range(args.warmup + args.steps):
-        v, cores, sample, dt = cpu_baseline(sample_steps=1)
+        v, kind, sample, dt, cores = reference_steps(torch.device("cpu"), 1)
         if i >= args.warmup:
             vals.append((v, dt))
     v = sum(x[0] for x in vals) / len(vals)
-    line = {"metric": "denoiser frame-steps/sec (DiffNet 20x256, 100-step DDPM sampling)", "value": v,
+    line = {"metric": METRIC, "value": v,
             "unit": "frame-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sum(x[1] for x in vals) / len(vals), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"DiffNet(80,256,L20,C256) DDPM sampling, {B} tracks x {T} frames",
-                       "note": "each step = 1 DDPM step (bounded sample of the 100-step pass) on host cores"},
-            "cpu_baseline": {"value": v, "unit": "frame-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": dict(CONFIG),
+            "note": "each step = 1 DDPM step of the full batch (bounded sample of the 100-step pass) on the host cores",
+            "cpu_baseline": {"value": v, "unit": "frame-steps/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "frame-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -211,7 +311,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vocoder", action="store_true")
-    ap.add_argument("--no-pipeline", action="store_true", help="skip the config-4 pipeline probe (N = 1 only)")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the config-4 pipeline (64 songs, strong scaling)")
+    ap.add_argument("--pipeline-songs", type=int, default=64)
+    ap.add_argument("--no-training", action="store_true", help="skip the config-5 DDP training step")
+    ap.add_argument("--no-extras", action="store_true", help="skip wavenet / reference_gpu_eager (N = 1 only)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -324,27 +427,38 @@ def main():
 
     voc = vocoder_bench(dev, peaks) if not args.no_vocoder else None
 
+    # BASELINE configs[3]: 64 songs of 6 tracks x 30 s through the FFConvLSTM encoders, both diffusion models, the device
+    # post-processing and the vocoder, host to host; songs are split over the ranks by sharding.assign (strong scaling)
+    pl = None
+    if not args.no_pipeline:
+        from types import SimpleNamespace
+        from tools import bench_pipeline
+        pl = bench_pipeline.run(SimpleNamespace(songs=args.pipeline_songs, warmup_songs=2, encoders=True, postprocess=True,
+                                                breakdown=False), rank, world, dev)
+    # BASELINE configs[4]: data-parallel training step, 6 x 1000 frames per rank, gradient all-reduce over NCCL
+    tr = None
+    if not args.no_training:
+        from tools import bench_train
+        tr = bench_train.run(10, 3, rank, local_rank, world, dev)
+
     if rank == 0:
         total_units = world * B * T * K_STEP * args.steps
         value = total_units / sec
         e2e = total_units / sec_e2e
         line = {
-            "metric": "denoiser frame-steps/sec (DiffNet 20x256, 100-step DDPM sampling)",
+            "metric": METRIC,
             "value": value, "unit": "frame-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"DiffNet(80,256,L20,C256) DDPM sampling, {B} tracks x {T} frames per GPU, "
-                                   f"K_step={K_STEP}", "precision": den.resolved_precision(),
-                       "sharding": "one 6-track batch per rank, no collective",
-                       "l2": "256 MB flush between timed passes; 384 MB noise tensor per pass > L2",
-                       "audio_sec_per_sec_equiv": value / K_STEP / 200.0},
+            "config": dict(CONFIG),
+            "precision": den.resolved_precision(), "audio_sec_per_sec_equiv": value / K_STEP / 200.0,
             "e2e": {"value": e2e, "unit": "frame-steps/s", "h2d_bytes_per_step": cond_host.numel() * 4,
                     "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": 1e3 * sec_e2e / args.steps},
             "gpu_launches": gpu_launches,
             "clocks": clk.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf,
-                         "traffic": _ncu_traffic("r01z_stack_ncu_full_summary.json" if use_stack else "r01h_block2_ncu_full_summary.json"),
+                         "traffic": _ncu_traffic(STACK_NCU_SUMMARY) if use_stack else None,
                          "kernel": ("diffnet_stack_kernel (all 20 residual blocks in one launch; CTA pairs, tcgen05 cta_group::2)"
                                     if use_stack else "diffnet_block3_kernel (one residual block; CTA pairs, tcgen05 cta_group::2)"),
                          "us_per_launch": block_ms * 1e3, "flops_per_launch": flops_per_launch,
@@ -354,18 +468,22 @@ def main():
         if voc is not None:
             voc["value"] *= world   # one 6-track vocoder batch per rank, no collective
             line["vocoder"] = voc
-        if world == 1 and not args.no_pipeline:
-            # BASELINE configs[3] in short (tools/bench_pipeline.py has the full run): 6 songs of 6 tracks x 30 s through the
-            # FFConvLSTM encoders, both diffusion models, the device post-processing and the vocoder, host to host
-            from types import SimpleNamespace
-            from tools import bench_pipeline
-            pl = bench_pipeline.run(SimpleNamespace(songs=6, warmup_songs=2, encoders=True, postprocess=True, breakdown=False), 0, 1, dev)
-            line["pipeline"] = {k: pl[k] for k in ("metric", "value", "unit", "songs", "ms_per_song_rank0", "gpu_launches_rank0",
-                                                   "config")}
+        if pl is not None:
+            line["pipeline"] = {k: pl[k] for k in ("metric", "value", "unit", "songs", "scaling", "seconds", "ms_per_song_rank0",
+                                                   "gpu_launches_rank0", "config")}
+        if tr is not None:
+            line["training"] = tr
+        if world == 1 and not args.no_extras:
+            line["wavenet"] = wavenet_bench(dev)
+            # the reference's own modules in eager PyTorch on this GPU (cuDNN / cuBLAS, fp32 with torch's default TF32
+            # convolution setting): the bar to beat on the same box
+            v, kind, sample, dt, _ = reference_steps(dev, 2, repeats=3)
+            line["reference_gpu_eager"] = {"value": v, "unit": "frame-steps/s", "kind": kind, "sample": sample,
+                                           "ms_per_ddpm_step": 1e3 * dt / 2,
+                                           "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32),
+                                           "speedup_of_value": value / v}
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, sample, dt = cpu_baseline(sample_steps=2)
-            line["cpu_baseline"] = {"value": v, "unit": "frame-steps/s", "cores": cores, "kind": "port",
-                                    "sample": sample, "seconds": dt}
+            line["cpu_baseline"] = cpu_baseline(sample_steps=2)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -7,12 +7,18 @@ pyworld / hydra / omegaconf, and ``nnsvs/usfgan/utils/utils.py:15`` needs h5py,
 the hot path, so this shim registers a namespace stub for ``nnsvs`` (skipping its
 ``__init__``) plus empty stubs for ``h5py``/``tkinter``.
 
-It exists for exactly two users, both of which run only in the build container
-(``/root/reference`` does not travel to the GPU box):
+Where the reference comes from, in order: ``$SVSK_REFERENCE_ROOT``; ``baseline/_ref`` (the unmodified reference
+installed by ``pip install --no-index --no-deps --target baseline/_ref`` — done by ``__graft_entry__.build()`` in the
+build container; git-ignored, but it travels to the GPU box with the snapshot); ``/root/reference`` (build container
+only).
+
+Users:
 
 * ``oracle/make_golden.py`` — generates ``tests/golden/*.npz`` from the reference.
 * ``tests/test_oracle_vs_reference.py`` — pins the oracle restatement against the
-  live reference (skipped when the reference tree is absent).
+  live reference (skipped when no reference tree is found).
+* ``bench.py --impl reference`` and ``bench.py``'s ``cpu_baseline`` / ``reference_gpu_eager`` legs — time the
+  reference's own modules (``kind: "reference"``); the oracle port is the fallback when no tree is found.
 
 Nothing in the product package may import this file.
 """
@@ -20,7 +26,18 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SVSK_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    cands = [os.environ.get("SVSK_REFERENCE_ROOT"), os.path.join(_REPO, "baseline", "_ref"), "/root/reference"]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "nnsvs", "diffsinger")):
+            return c
+    return cands[-1]
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:

@@ -92,10 +92,10 @@ def test_config2_bf16_sampling_vs_oracle(config2):
     assert c.m.denoise_fn.resolved_precision() == "bf16"
     trace = {t: None for t in STEPS}
     y = c.m.inference(c.cond, x_T=c.x_T, z=c.z, trace=trace)
-    check("config 2 bf16  eps_hat t=99", trace[99], c.traj[99][0], 1.5e-2, 5e-2)
-    check("config 2 bf16  eps_hat t=50", trace[50], c.traj[50][0], 3e-2, 1.5e-1)
-    check("config 2 bf16  eps_hat t=0 ", trace[0], c.traj[0][0], 3e-2, 1.5e-1)
-    check("config 2 bf16  final mel   ", y, c.ref, 2e-2, 1e-1)
+    check("config 2 bf16  eps_hat t=99", trace[99], c.traj[99][0], 2e-2, 3e-2)
+    check("config 2 bf16  eps_hat t=50", trace[50], c.traj[50][0], 2e-2, 3e-2)
+    check("config 2 bf16  eps_hat t=0 ", trace[0], c.traj[0][0], 2e-2, 3e-2)
+    check("config 2 bf16  final mel   ", y, c.ref, 1.5e-2, 1.5e-1)
     # the CUDA-graph replay bench.py measures gives the same numbers as the traced eager launches, bit for bit
     assert torch.equal(c.m.inference(c.cond, x_T=c.x_T, z=c.z), y)
 
@@ -108,10 +108,10 @@ def test_config2_fp32_sampling_vs_oracle(config2):
         y = c.m.inference(c.cond, x_T=c.x_T, z=c.z, trace=trace)
     finally:
         c.m.denoise_fn.precision = "auto"
-    check("config 2 fp32  eps_hat t=99", trace[99], c.traj[99][0], 1e-5, 1e-4)
-    check("config 2 fp32  eps_hat t=50", trace[50], c.traj[50][0], 1e-4, 1e-3)
-    check("config 2 fp32  eps_hat t=0 ", trace[0], c.traj[0][0], 1e-4, 1e-3)
-    check("config 2 fp32  final mel   ", y, c.ref, 1e-4, 1e-3)
+    check("config 2 fp32  eps_hat t=99", trace[99], c.traj[99][0], 1e-5, 2e-5)
+    check("config 2 fp32  eps_hat t=50", trace[50], c.traj[50][0], 1e-5, 2e-5)
+    check("config 2 fp32  eps_hat t=0 ", trace[0], c.traj[0][0], 1e-5, 2e-5)
+    check("config 2 fp32  final mel   ", y, c.ref, 1e-5, 2e-5)
 
 
 # ------------------------------------------------------------------------------------------------ config 3
@@ -195,13 +195,13 @@ def test_config3_generator_bf16_and_fp32_vs_oracle(config3):
     c.gen.precision = "auto"
     assert c.gen._ntc_fast_path_ok()
     y = c.gen(x, aux, d, wave_only=True)[0]                   # the NTC bf16 path USFGANWrapper uses
-    check("config 3 bf16  waveform (55 blocks, oracle in_signal)", y, c.ref, 6e-2, 2e-1)
+    check("config 3 bf16  waveform (55 blocks, oracle in_signal)", y, c.ref, 1.5e-2, 3e-2)
     c.gen.precision = "fp32"
     try:
         y32 = c.gen(x, aux, d)[0]
     finally:
         c.gen.precision = "auto"
-    check("config 3 fp32  waveform (55 blocks, oracle in_signal)", y32, c.ref, 2e-4, 2e-3)
+    check("config 3 fp32  waveform (55 blocks, oracle in_signal)", y32, c.ref, 5e-6, 1e-5)
 
 
 def test_config3_wrapper_end_to_end_vs_oracle(config3):
@@ -213,15 +213,15 @@ def test_config3_wrapper_end_to_end_vs_oracle(config3):
     w = USFGANWrapper(vocoder_config(), c.gen)
     c.gen.precision = "auto"
     y = w.inference(c.f0.copy(), c.aux.to(DEV), noise=noise)
-    check("config 3 bf16  USFGANWrapper.inference", y, c.ref, 6e-2, 2e-1)
+    check("config 3 bf16  USFGANWrapper.inference", y, c.ref, 1.5e-2, 3e-2)
     yb = w.inference_batch(c.f0[None].copy(), c.aux[None].to(DEV), noise=noise)
-    check("config 3 bf16  USFGANWrapper.inference_batch", yb, c.ref, 6e-2, 2e-1)
+    check("config 3 bf16  USFGANWrapper.inference_batch", yb, c.ref, 1.5e-2, 3e-2)
     c.gen.precision = "fp32"
     try:
         y32 = w.inference(c.f0.copy(), c.aux.to(DEV), noise=noise)
     finally:
         c.gen.precision = "auto"
-    check("config 3 fp32  USFGANWrapper.inference", y32, c.ref, 1e-3, 1e-2)
+    check("config 3 fp32  USFGANWrapper.inference", y32, c.ref, 2e-5, 1e-4)
 
 
 # ------------------------------------------------------------------------------------------------ config 4
@@ -268,9 +268,9 @@ def _run_config4(c):
 def test_config4_pipeline_item_bf16_vs_oracle(config4):
     c = config4
     wav, m, b = _run_config4(c)
-    check("config 4 bf16  mgc stream (K=100)", m, c.m_ref, 2e-2, 1e-1)
-    check("config 4 bf16  bap stream (K=100)", b, c.b_ref, 2e-2, 1e-1)
-    check("config 4 bf16  waveform, whole chain", wav, c.wav_ref, 1e-1, 3e-1)
+    check("config 4 bf16  mgc stream (K=100)", m, c.m_ref, 1.5e-2, 1.5e-1)
+    check("config 4 bf16  bap stream (K=100)", b, c.b_ref, 1.5e-2, 1e-1)
+    check("config 4 bf16  waveform, whole chain", wav, c.wav_ref, 3e-2, 8e-2)
 
 
 def test_config4_pipeline_item_fp32_vs_oracle(config4):
@@ -283,9 +283,9 @@ def test_config4_pipeline_item_fp32_vs_oracle(config4):
     finally:
         for m_ in mods:
             m_.precision = "auto"
-    check("config 4 fp32  mgc stream (K=100)", m, c.m_ref, 1e-4, 1e-3)
-    check("config 4 fp32  bap stream (K=100)", b, c.b_ref, 1e-4, 1e-3)
-    check("config 4 fp32  waveform, whole chain", wav, c.wav_ref, 2e-3, 2e-2)
+    check("config 4 fp32  mgc stream (K=100)", m, c.m_ref, 5e-6, 2e-5)
+    check("config 4 fp32  bap stream (K=100)", b, c.b_ref, 5e-6, 2e-5)
+    check("config 4 fp32  waveform, whole chain", wav, c.wav_ref, 1e-5, 2e-5)
 
 
 # ------------------------------------------------------------------------------------------------ a16: reference's own wrapper output
@@ -308,12 +308,12 @@ def test_usfgan_wrapper_inference_vs_reference_output():
     noise = {"sine": g.inp["noise_sine"], "noise": g.inp["noise_in"]}
     f0, aux = g.inp["f0"].numpy(), g.inp["aux"].to(DEV)
     gen.precision = "fp32"
-    check("a16 fp32  USFGANWrapper.inference vs reference", w.inference(f0.copy(), aux, noise=noise), g.out["wav"], 2e-5, 2e-4)
+    check("a16 fp32  USFGANWrapper.inference vs reference", w.inference(f0.copy(), aux, noise=noise), g.out["wav"], 2e-5, 5e-5)
     gen.precision = "auto"
     assert gen._ntc_fast_path_ok()
-    check("a16 bf16  USFGANWrapper.inference vs reference", w.inference(f0.copy(), aux, noise=noise), g.out["wav"], 3e-2, 1e-1)
+    check("a16 bf16  USFGANWrapper.inference vs reference", w.inference(f0.copy(), aux, noise=noise), g.out["wav"], 2e-2, 3e-2)
     check("a16 bf16  inference_batch vs reference", w.inference_batch(f0[None].copy(), aux[None], noise=noise), g.out["wav"],
-          3e-2, 1e-1)
+          2e-2, 3e-2)
     # the input construction itself, on the device, against the reference's tensors (tests/golden/usfgan_frontend.npz)
     from ensemble_svs_with_interactions_b200.usfgan.utils import SignalGenerator, dilated_factor
     fg = Golden("usfgan_frontend")
@@ -322,7 +322,9 @@ def test_usfgan_wrapper_inference_vs_reference_output():
                          noise_amp=fc["noise_amp"], signal_types=["sine", "noise"])
     sg.injected_noise = {"sine": fg.inp["noise_sine"], "noise": fg.inp["noise_in"]}
     sig = sg(torch.FloatTensor(fg.inp["f0"].numpy()).unsqueeze(0).transpose(2, 1).to(DEV))
-    assert sig.is_cuda and max_abs(sig.cpu(), fg.out["in_signal"]) <= 2e-6
+    # the phase 2*pi*cumsum(f0/fs) reaches a few hundred radians in fp32 (ulp ~ 3e-5 rad): the device's scan order and its
+    # sin differ from the host's sequential sum by a few ulps of the phase, times the sine amplitude 0.1
+    assert sig.is_cuda and max_abs(sig.cpu(), fg.out["in_signal"]) <= 5e-5
     df = dilated_factor(np.squeeze(fg.inp["f0"].numpy().copy()), fc["sample_rate"], fc["dense_factor"]).repeat(fc["hop_size"])
     assert np.array_equal(df, fg.out["df"].numpy())
 
@@ -341,9 +343,9 @@ def test_wavenet_incremental_logits_equal_parallel_forward():
     m.clear_buffer()
     inc = torch.cat([m.incremental_logits(x[:, t:t + 1], c[:, t:t + 1]) for t in range(x.shape[1])], dim=1)
     m.clear_buffer()
-    check("a18 incremental vs parallel logits (this repo)", inc, par, 1e-5, 1e-4)
-    check("a18 parallel logits vs reference", par, g.out["parallel"], 1e-5, 1e-4)
-    check("a18 incremental logits vs reference", inc, g.out["incremental"], 1e-5, 1e-4)
+    check("a18 incremental vs parallel logits (this repo)", inc, par, 5e-6, 5e-6)
+    check("a18 parallel logits vs reference", par, g.out["parallel"], 5e-6, 5e-6)
+    check("a18 incremental logits vs reference", inc, g.out["incremental"], 5e-6, 5e-6)
     # and the sampler built on it: one-hot frames, the right shape, buffers cleared afterwards
     torch.manual_seed(0)
     y = m.inference(c, num_time_steps=x.shape[1], tqdm=None)

@@ -19,6 +19,77 @@ from torch.nn.parallel import DistributedDataParallel as DDP  # noqa: E402
 from ensemble_svs_with_interactions_b200.diffsinger import DiffNet, GaussianDiffusion  # noqa: E402
 
 
+def run(steps, warmup, rank, local, world, dev):
+    """One measurement inside an already initialised process group (world > 1) or without one (world == 1).
+    Returns the dict of the JSON line on rank 0, None elsewhere."""
+    torch.manual_seed(1234)
+    model = GaussianDiffusion(256, 60, DiffNet(60, 256, 20, 256, 4), K_step=100)
+    with torch.no_grad():
+        model.denoise_fn.output_projection.weight.normal_(0, 0.02)
+    model = model.to(dev).train()
+    ddp = DDP(model, device_ids=[local]) if world > 1 else model
+    opt = torch.optim.AdamW(ddp.parameters(), lr=1e-3, betas=(0.9, 0.98))
+    B, T = 6, 1000
+    g = torch.Generator().manual_seed(1234 + rank)
+    cond = torch.randn(B, T, 256, generator=g).to(dev)
+    y = torch.randn(B, T, 60, generator=g).to(dev)
+
+    def step(sync=True):
+        opt.zero_grad(set_to_none=True)
+        if world > 1 and not sync:
+            with ddp.no_sync():
+                noise, eps = ddp(cond, None, y)
+                loss = (noise - eps).abs().mean()
+                loss.backward()
+        else:
+            noise, eps = ddp(cond, None, y)
+            loss = (noise - eps).abs().mean()
+            loss.backward()
+        torch.nn.utils.clip_grad_norm_(ddp.parameters(), 10.0)
+        opt.step()
+        return loss
+
+    def timed(sync):
+        for _ in range(warmup):
+            step(sync)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step(sync)
+        e1.record(); e1.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / steps, loss
+
+    # exposed communication = step time with the gradient all-reduce minus the same step without it (ranks drift apart
+    # in the no_sync run, so it goes second and the parameters are checked after the synchronised one)
+    ms, loss = timed(True)
+    chk = torch.stack([p.detach().float().sum() for p in model.parameters()]).sum().reshape(1)
+    lo, hi = chk.clone(), chk.clone()
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    ms_nosync = timed(False)[0] if world > 1 else ms
+    if rank != 0:
+        return None
+    n_par = sum(p.numel() for p in model.parameters())
+    grad_bytes = n_par * 4
+    exposed = max(ms - ms_nosync, 0.0)
+    # ring all-reduce moves 2 (N-1)/N of the buffer per rank: bus bandwidth as NCCL's tests define it
+    busbw = (2.0 * (world - 1) / world * grad_bytes / (exposed * 1e-3) / 1e9) if world > 1 and exposed > 0 else None
+    from ensemble_svs_with_interactions_b200.diffsinger import training
+    return {"metric": "DP DiffNet training step", "value": ms, "unit": "ms/step", "higher_is_better": False,
+            "n_gpus": world, "global_batch": f"{world * B} x {T} frames", "frames_per_sec": world * B * T / (ms / 1e3),
+            "tflops_per_gpu": 3 * 2 * 13_203_456 * B * T / (ms * 1e-3) / 1e12,
+            "loss": float(loss), "params_in_sync": bool(torch.equal(lo, hi)),
+            "allreduce_mb_per_step": grad_bytes / 1e6, "ms_per_step_without_allreduce": ms_nosync,
+            "exposed_allreduce_ms": exposed, "allreduce_busbw_gbs_lower_bound": busbw,
+            "backward": getattr(training, "BACKWARD_IMPL", "autograd re-statement")}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
@@ -27,52 +98,14 @@ def main():
     rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    torch.manual_seed(1234)
-    model = GaussianDiffusion(256, 60, DiffNet(60, 256, 20, 256, 4), K_step=100)
-    with torch.no_grad():
-        model.denoise_fn.output_projection.weight.normal_(0, 0.02)
-    model = model.to(dev).train()
-    ddp = DDP(model, device_ids=[local])
-    opt = torch.optim.AdamW(ddp.parameters(), lr=1e-3, betas=(0.9, 0.98))
-    B, T = 6, 1000
-    g = torch.Generator().manual_seed(1234 + rank)
-    cond = torch.randn(B, T, 256, generator=g).to(dev)
-    y = torch.randn(B, T, 60, generator=g).to(dev)
-
-    def step():
-        opt.zero_grad(set_to_none=True)
-        noise, eps = ddp(cond, None, y)
-        loss = (noise - eps).abs().mean()
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(ddp.parameters(), 10.0)
-        opt.step()
-        return loss
-
-    for _ in range(args.warmup):
-        step()
-    dist.barrier(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        loss = step()
-    e1.record(); e1.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    # every rank must hold identical parameters after the all-reduced updates
-    chk = torch.stack([p.detach().float().sum() for p in model.parameters()]).sum().reshape(1)
-    lo, hi = chk.clone(), chk.clone()
-    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    line = run(args.steps, args.warmup, rank, local, world, dev)
     if rank == 0:
-        ms = t.item() / args.steps
-        n_par = sum(p.numel() for p in model.parameters())
-        print(json.dumps({"metric": "DP DiffNet training step", "value": ms, "unit": "ms/step", "higher_is_better": False,
-                          "n_gpus": world, "global_batch": f"{world * B} x {T} frames", "frames_per_sec": world * B * T / (ms / 1e3),
-                          "loss": float(loss), "params_in_sync": bool(torch.equal(lo, hi)),
-                          "allreduce_mb_per_step": n_par * 4 / 1e6,
-                          "note": "forward: libsvsk bf16 kernels; backward: interim PyTorch autograd re-statement"}))
-    dist.destroy_process_group()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
