@@ -88,6 +88,26 @@ class TapGemmBf16Params(C.Structure):
     ]
 
 
+class SegGemmParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p * 4), ("ldx", C.c_int32 * 4), ("kx", C.c_int32 * 4), ("shift", C.c_int32 * 4), ("nseg", C.c_int32),
+        ("wp", C.c_void_p),
+        ("Nrows", C.c_int32), ("B", C.c_int32), ("T", C.c_int32), ("mode", C.c_int32), ("C", C.c_int32), ("init", C.c_int32),
+        ("act", C.c_int32), ("accumulate", C.c_int32),
+        ("bias", C.c_void_p), ("in0", C.c_void_p), ("ld_in0", C.c_int32), ("mask", C.c_void_p), ("ld_mask", C.c_int32),
+        ("dp_next", C.c_void_p), ("out0", C.c_void_p), ("ld_out0", C.c_int32), ("out1", C.c_void_p), ("ld_out1", C.c_int32),
+        ("outf", C.c_void_p), ("ld_outf", C.c_int32), ("alpha", C.c_float),
+    ]
+
+
+class WgradParams(C.Structure):
+    _fields_ = [
+        ("p", C.c_void_p), ("q", C.c_void_p * 5), ("qrows", C.c_int32 * 5), ("shift", C.c_int32 * 5),
+        ("nseg", C.c_int32), ("Prows", C.c_int32), ("B", C.c_int32), ("T", C.c_int32), ("Tp", C.c_int32), ("ldw", C.c_int32),
+        ("accumulate", C.c_int32), ("splits", C.c_int32), ("split_stride", C.c_int64), ("dW", C.c_void_p),
+    ]
+
+
 class UsfganBlockParams(C.Structure):
     _fields_ = [
         ("xb_in", C.c_void_p), ("xb_out", C.c_void_p), ("aux", C.c_void_p),
@@ -135,6 +155,10 @@ _SIGNATURES = {
     "svsk_upsample_fused": [_V, _V, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_int, _V, _V, C.c_int, _V],
     "svsk_expand1_bf16": [_V, C.c_longlong, _V, _V, _V, C.c_int, C.c_int, C.c_int, _V],
     "svsk_diffnet_pack_block": [_V, _V, _V, _V, _V, _I, _I, _V],
+    "svsk_seggemm_bf16": [C.POINTER(SegGemmParams), _V],
+    "svsk_wgrad_bf16": [C.POINTER(WgradParams), _V],
+    "svsk_ntc_to_nct_bf16": [_V, _V, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_int), _V],
+    "svsk_diffnet_train_pack": [_V, _V, _V, _V, _V, _V, _V, _V, _I, _I, _I, _V],
     "svsk_diffnet_packed_row": [_I, _I],
     "svsk_linear_bf16": [C.POINTER(LinearBf16Params), _V],
     "svsk_usfgan_block_bf16": [C.POINTER(UsfganBlockParams), _V],

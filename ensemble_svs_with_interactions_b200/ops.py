@@ -216,6 +216,96 @@ def diffnet_block_bf16(xb_in, xb_out, x32, skip32, cond, w1p, woutp, stepbias, b
     L.check(L.lib().svsk_diffnet_block3_bf16(C.byref(p), L.stream_ptr()), "diffnet_block_bf16")
 
 
+# ------------------------------------------------------------------------------------------------ training kernels
+SEG_PLAIN, SEG_GATE_FWD, SEG_RES_SKIP, SEG_GATE_BWD, SEG_ADD_SCALE = 0, 1, 2, 3, 4
+
+
+def seggemm_bf16(segments, wp, *, mode, bias=None, in0=None, mask=None, dp_next=None, out0=None, out1=None, outf=None,
+                 alpha=1.0, act=ACT_NONE, init=True, accumulate=False):
+    """D[b,t,n] = sum_s x_s[b, t + shift_s, :kx_s] . wp[n, koff_s:koff_s + kx_s]  with the epilogue `mode` of
+    svsk_seggemm_bf16.  segments: list of (x [B,T,ld] bf16, kx, shift); wp [Nrows, sum kx] bf16."""
+    x0 = segments[0][0]
+    B, T = x0.shape[0], x0.shape[1]
+    p = L.SegGemmParams()
+    p.nseg = len(segments)
+    for s, (x, kx, shift) in enumerate(segments):
+        if x.shape[0] != B or x.shape[1] != T:
+            raise ValueError("seggemm_bf16: all segments must be [B, T, .]")
+        p.x[s] = L.ptr(x, bf16, f"segment {s}").value
+        p.ldx[s], p.kx[s], p.shift[s] = x.shape[2], int(kx), int(shift)
+    if wp.shape[1] != sum(int(k) for _, k, _ in segments):
+        raise ValueError(f"seggemm_bf16: wp has K = {wp.shape[1]}, segments sum to {sum(int(k) for _, k, _ in segments)}")
+    p.wp = L.ptr(wp, bf16, "wp")
+    p.Nrows, p.B, p.T, p.mode = wp.shape[0], B, T, int(mode)
+    p.C = wp.shape[0] // 2 if mode == SEG_RES_SKIP else wp.shape[0]
+    p.init, p.act, p.accumulate, p.alpha = int(init), int(act), int(accumulate), float(alpha)
+    p.bias, p.dp_next = L.ptr(bias, f32, "bias"), L.ptr(dp_next, f32, "dp_next")
+    for name, t in (("in0", in0), ("mask", mask), ("out0", out0), ("out1", out1)):
+        setattr(p, name, L.ptr(t, bf16, name))
+        setattr(p, "ld_" + name, 0 if t is None else t.shape[-1])
+    p.outf, p.ld_outf = L.ptr(outf, f32, "outf"), 0 if outf is None else outf.shape[-1]
+    L.check(L.lib().svsk_seggemm_bf16(C.byref(p), L.stream_ptr()), "seggemm_bf16")
+
+
+def wgrad_bf16(p_nct, q_segments, dW, *, T, accumulate=False):
+    """dW[..., n, koff_s + k] (+)= sum_{b,t} p[b, n, t] q_s[b, k, t + shift_s].  p_nct [B, Prows, Tp] bf16,
+    q_segments: list of (q [B, rows, Tp] bf16, shift); dW [Prows, >= sum rows] fp32 — or [S, Prows, ld]: the tracks are
+    cut into S groups whose partial results land in dW[0] .. dW[S-1] (sum them; more CTAs, still no atomics)."""
+    B, Prows, Tp = p_nct.shape
+    p = L.WgradParams()
+    p.p = L.ptr(p_nct, bf16, "p")
+    p.nseg = len(q_segments)
+    for s, (q, shift) in enumerate(q_segments):
+        if q.shape[0] != B or q.shape[2] != Tp:
+            raise ValueError("wgrad_bf16: operands must share B and the time pitch")
+        p.q[s] = L.ptr(q, bf16, f"q {s}").value
+        p.qrows[s], p.shift[s] = q.shape[1], int(shift)
+    p.Prows, p.B, p.T, p.Tp, p.ldw, p.accumulate = Prows, B, int(T), Tp, dW.shape[-1], int(accumulate)
+    p.splits, p.split_stride = (dW.shape[0], dW.stride(0)) if dW.dim() == 3 else (1, 0)
+    if dW.shape[-2] != Prows:
+        raise ValueError(f"wgrad_bf16: dW has {dW.shape[-2]} rows, p has {Prows}")
+    p.dW = L.ptr(dW, f32, "dW")
+    L.check(L.lib().svsk_wgrad_bf16(C.byref(p), L.stream_ptr()), "wgrad_bf16")
+
+
+def wgrad_splits(B, tiles, budget=160):
+    """How many track groups a wgrad launch of `tiles` CTAs per group should use: the largest divisor of B that keeps the
+    grid within about one wave (the kernel is bound by what ONE SM can pull from L2, so it wants many CTAs)."""
+    best = 1
+    for s in range(1, B + 1):
+        if B % s == 0 and tiles * s <= budget:
+            best = s
+    return best
+
+
+def ntc_to_nct_bf16(x, N=None, out=None, row0=0, shifts=(0,)):
+    """out[b, row0 + j * N + n, t] = x[b, t + shifts[j], n] (0 outside the track) for up to three shifts: x [B, T, ld] bf16
+    (first N columns), out [B, rows, Tp] bf16 (Tp = T rounded up to 8; a fresh `out` has exactly len(shifts) * N rows)."""
+    B, T, ld = x.shape
+    N = ld if N is None else N
+    Tp = (T + 7) // 8 * 8
+    if out is None:
+        out = torch.empty((B, len(shifts) * N, Tp), device=x.device, dtype=bf16)
+    sh = (C.c_int * 3)(*([int(v) for v in shifts] + [0] * (3 - len(shifts))))
+    L.check(L.lib().svsk_ntc_to_nct_bf16(L.ptr(x, bf16, "x"), L.ptr(out, bf16, "out"), B, T, N, ld, out.shape[2], out.shape[1],
+                                         int(row0), len(shifts), sh, L.stream_ptr()), "ntc_to_nct_bf16")
+    return out
+
+
+def diffnet_train_pack(wd, wc, wo):
+    """Stacked fp32 parameters (wd [L,2C,C,3], wc [L,2C,H], wo [L,2C,C]) -> dict of the bf16 operands of the training kernels."""
+    Ln, C2, Cc, _ = wd.shape
+    H = wc.shape[2]
+    dev = wd.device
+    out = dict(w1p=torch.empty((Ln, C2, 3 * Cc + H), device=dev, dtype=bf16), woutp=torch.empty((Ln, C2, Cc), device=dev, dtype=bf16),
+               woutT=torch.empty((Ln, Cc, C2), device=dev, dtype=bf16), w1T=torch.empty((Ln, Cc, 3 * C2), device=dev, dtype=bf16),
+               wcT=torch.empty((Ln, H, C2), device=dev, dtype=bf16))
+    L.check(L.lib().svsk_diffnet_train_pack(L.ptr(wd, f32, "wd"), L.ptr(wc, f32, "wc"), L.ptr(wo, f32, "wo"),
+                                            L.ptr(out["w1p"]), L.ptr(out["woutp"]), L.ptr(out["woutT"]), L.ptr(out["w1T"]),
+                                            L.ptr(out["wcT"]), Ln, Cc, H, L.stream_ptr()), "diffnet_train_pack")
+    return out
+
+
 def diffnet_stack_fits(B, T, Cc, H):
     """True if the one-launch residual stack (svsk_diffnet_stack_bf16) can hold all its CTA pairs on the device at once."""
     return L.lib().svsk_diffnet_stack_fits(int(B), int(T), int(Cc), int(H)) == 1

@@ -427,6 +427,70 @@ SVSK_API int svsk_scale_features_f32(const float* x, float* y, const float* a, c
 SVSK_API int svsk_mdn_head_f32(const float* raw, float* log_pi, float* log_sigma, float* mu, float* best_sigma, float* best_mu,
                                long long rows, int G, int D, int ld, void* stream);
 
+/* ---- DiffNet training kernels (dgrad / wgrad / fused gate backward) -------------------------
+ * Replace, inside the training step (nnsvs/bin/train_acoustic_multitrack.py:358-380), what autograd derives from
+ * ResidualBlock.forward / DiffNet.forward (nnsvs/diffsinger/denoiser.py:54-66, 101-124).  See diffnet_train_sm100.cu. */
+enum { SVSK_SEG_PLAIN = 0, SVSK_SEG_GATE_FWD = 1, SVSK_SEG_RES_SKIP = 2, SVSK_SEG_GATE_BWD = 3, SVSK_SEG_ADD_SCALE = 4 };
+
+/* Frame-major segmented GEMM on tcgen05:
+ *   D[b][t][n] = sum_s sum_k x[s][b][t + shift[s]][k] * wp[n][koff_s + k],  koff_s = kx[0] + .. + kx[s-1]
+ * x[s]: [B][T][ldx[s]] bf16 (first kx[s] columns used, kx % 64 == 0); rows outside [0, T) of a track read as 0.
+ * wp: [Nrows][sum kx] bf16.  The epilogue depends on `mode`:
+ *  GATE_FWD  (Nrows = 2C packed rows, svsk_diffnet_train_pack): y = D + bias -> out0 [.][ld_out0] (ypre, packed columns),
+ *            out1 [.][ld_out1] = sigmoid(y_gate) * tanh(y_filter) (z, channel order)
+ *  RES_SKIP  (Nrows = 2C reference rows, C = Nrows / 2): o = D + bias; out0 = x' = (in0 + o[:C]) / sqrt 2 and
+ *            out1 = x' + dp_next[b][:] (either may be NULL); outf (skip32, fp32) = o[C:] if init else += o[C:]
+ *  GATE_BWD  (Nrows = C): dz = D; in0 = ypre (packed columns), out0 = dy (packed columns)
+ *  ADD_SCALE / PLAIN: v = act(D + bias + in0) * alpha, zeroed where mask <= 0; -> out0 (bf16), out1 = v + dp_next[b][n]
+ *            (bf16, dp_next [B][Nrows]) and / or outf (fp32, += if accumulate).  bias, in0, mask, dp_next optional. */
+typedef struct svsk_seggemm_params {
+  const void* x[4];
+  int32_t ldx[4], kx[4], shift[4];
+  int32_t nseg;
+  const void* wp;
+  int32_t Nrows, B, T, mode, C, init, act, accumulate;
+  const float* bias;
+  const void* in0;
+  int32_t ld_in0;
+  const void* mask;
+  int32_t ld_mask;
+  const float* dp_next; /* [B][C] fp32 */
+  void* out0;
+  int32_t ld_out0;
+  void* out1;
+  int32_t ld_out1;
+  float* outf;
+  int32_t ld_outf;
+  float alpha;
+} svsk_seggemm_params;
+SVSK_API int svsk_seggemm_bf16(const svsk_seggemm_params* p, void* stream);
+
+/* Weight gradients: dW[n][koff_s + k] (+)= sum_b sum_t p[b][n][t] * q[s][b][k][t + shift[s]], n < Prows, k < qrows[s];
+ * koff_s = qrows[0] + .. + qrows[s-1].  p, q[s]: [B][rows][Tp] bf16 (time contiguous; svsk_ntc_to_nct_bf16), frames
+ * outside [0, T) read as 0.  shift[s] must be a multiple of 8 frames (16-byte aligned TMA start); other shifts are
+ * written into the operand by svsk_ntc_to_nct_bf16.  Column sums over time (bias gradients) are obtained by appending
+ * rows of ones to a q operand.  dW [Prows][ldw] fp32.  One CTA per 128 x 128 tile of dW, whole contraction, no atomics. */
+typedef struct svsk_wgrad_params {
+  const void* p;
+  const void* q[5];
+  int32_t qrows[5], shift[5];
+  int32_t nseg, Prows, B, T, Tp, ldw, accumulate;
+  int32_t splits;           /* >= 1: the tracks are cut into `splits` groups, group z writes dW + z * split_stride */
+  int64_t split_stride;     /* floats; the caller sums the partial results (deterministic) */
+  float* dW;
+} svsk_wgrad_params;
+SVSK_API int svsk_wgrad_bf16(const svsk_wgrad_params* p, void* stream);
+
+/* y[b][row0 + j * N + n][t] = x[b][t + shifts[j]][n] (0 outside [0, T)) for j < nshift (1..3), n < N, t < Tp:
+ * x [B][T][ldx] bf16, y [B][out_rows][Tp] bf16; N, ldx, Tp multiples of 8.  shifts is a HOST array read at call time. */
+SVSK_API int svsk_ntc_to_nct_bf16(const void* x, void* y, int B, int T, int N, int ldx, int Tp, int out_rows, int row0,
+                                  int nshift, const int* shifts, void* stream);
+/* Packs the stacked fp32 parameters of all L residual layers (wd [L][2C][C][3], wc [L][2C][H], wo [L][2C][C]) into the
+ * bf16 operands of the kernels above: w1p [L][2C][3C+H] (packed rows), woutp [L][2C][C], woutT [L][C][2C],
+ * w1T [L][C][3*2C] (K = packed dy columns per tap), wcT [L][H][2C]. */
+SVSK_API int svsk_diffnet_train_pack(const float* wd, const float* wc, const float* wo, void* w1p, void* woutp, void* woutT,
+                                     void* w1T, void* wcT, int L, int C, int H, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,25 @@ def run(steps, warmup, rank, local, world, dev):
 
     # exposed communication = step time with the gradient all-reduce minus the same step without it (ranks drift apart
     # in the no_sync run, so it goes second and the parameters are checked after the synchronised one)
+    if os.environ.get("SVSK_TRAIN_BREAKDOWN") and rank == 0:
+        # per-phase times of one step, each bracketed by a synchronize (so they do not add up to the pipelined step time)
+        import time
+        for _ in range(3):
+            step(True)
+        ph = {}
+
+        def lap(name, fn):
+            torch.cuda.synchronize(); t0 = time.perf_counter(); out = fn(); torch.cuda.synchronize()
+            ph[name] = ph.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+            return out
+        for _ in range(5):
+            lap("zero_grad", lambda: opt.zero_grad(set_to_none=True))
+            noise, eps = lap("forward", lambda: ddp(cond, None, y))
+            loss_ = lap("loss", lambda: (noise - eps).abs().mean())
+            lap("backward", lambda: loss_.backward())
+            lap("clip_grad_norm", lambda: torch.nn.utils.clip_grad_norm_(ddp.parameters(), 10.0))
+            lap("optimizer", lambda: opt.step())
+        print("breakdown ms/step:", {k: round(v / 5, 3) for k, v in ph.items()}, file=sys.stderr)
     ms, loss = timed(True)
     chk = torch.stack([p.detach().float().sum() for p in model.parameters()]).sum().reshape(1)
     lo, hi = chk.clone(), chk.clone()
