@@ -155,6 +155,7 @@ _SIGNATURES = {
     "svsk_upsample_fused": [_V, _V, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_int, _V, _V, C.c_int, _V],
     "svsk_expand1_bf16": [_V, C.c_longlong, _V, _V, _V, C.c_int, C.c_int, C.c_int, _V],
     "svsk_diffnet_pack_block": [_V, _V, _V, _V, _V, _I, _I, _V],
+    "svsk_usfgan_source": [_V, _V, _V, C.c_longlong, _V, _V, _I, _I, _I, _I, _I, _F, _F, _V],
     "svsk_seggemm_bf16": [C.POINTER(SegGemmParams), _V],
     "svsk_wgrad_bf16": [C.POINTER(WgradParams), _V],
     "svsk_ntc_to_nct_bf16": [_V, _V, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_int), _V],

@@ -8,6 +8,8 @@
 //     reference applies it), then applies them to all channels out of a shared-memory copy of the frames.
 //     Staged path at config 3: 6.1 ms (five fp32 tensors written, the last one 1.4 GB, + NCT->NTC); fused: one 0.7 GB write.
 //   * svsk_expand1_bf16: a 1 -> C pointwise Conv1d (generator.py conv_first_sine / conv_first_noise) straight to NTC bf16.
+//   * svsk_usfgan_source: the sine-based source signal and the pitch-dependent dilation factors from frame-level F0
+//     (nnsvs/usfgan/utils/features.py:56-75, 145-164), one pass over the samples after a per-track scan over the frames.
 #include <cuda_bf16.h>
 
 #include "sm100_ptx.cuh"
@@ -121,6 +123,87 @@ __global__ void __launch_bounds__(256) expand1_bf16_kernel(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------ source signal
+// SignalGenerator.sinusoid (features.py:145-164):
+//   rad = (hold(f0) / fs) mod 1 ; sine = vuv * sin(2 pi cumsum(rad)) * sine_amp + randn * (vuv * na + (1 - vuv) * na / 3)
+// The reference's cumsum is torch's: on a CPU host it accumulates the fp32 values in fp64 and rounds every prefix to fp32
+// (verified bit for bit; a sequential fp32 sum drifts by 1.8 cycles over 720 000 samples).  F0 is constant over the hop
+// samples of a frame, so prefix(f * hop + k) = P[f] + (k + 1) * rad_f with P[f] = hop * sum_{f' < f} rad_f' — both exact
+// to the last bit or so of an fp64 — which makes the scan a per-track prefix over F frames (kernel 1, one block per track)
+// and an independent evaluation per sample (kernel 2).  Everything else follows the reference's fp32 expression order.
+__global__ void __launch_bounds__(1024) source_frame_scan_kernel(const double* __restrict__ f0, double* __restrict__ prefix,
+                                                                 int F, int hop, float fs) {
+  __shared__ double warp_tot[32];
+  __shared__ double carry_s;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) carry_s = 0.0;
+  __syncthreads();
+  for (int base = 0; base < F; base += 1024) {
+    const int f = base + tid;
+    double v = 0.0;
+    if (f < F) {
+      const float x = __fdiv_rn((float)f0[(size_t)b * F + f], fs);
+      v = (double)hop * (double)(x - floorf(x));
+    }
+    double incl = v;                                   // inclusive scan inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      double t = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double n = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += n;
+      }
+      warp_tot[lane] = t;                              // inclusive totals of the warps
+    }
+    __syncthreads();
+    const double before = carry_s + (w > 0 ? warp_tot[w - 1] : 0.0);
+    if (f < F) prefix[(size_t)b * F + f] = before + incl - v;   // exclusive
+    __syncthreads();
+    if (tid == 1023) carry_s = before + incl;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) source_samples_kernel(const double* __restrict__ f0, const double* __restrict__ prefix,
+                                                             const float* __restrict__ noise, float* __restrict__ sine_out,
+                                                             long long sine_bstride, float* __restrict__ d_out, int F, int hop,
+                                                             float fs, int dense_factor, float sine_amp, float noise_amp) {
+  const long long T = (long long)F * hop;
+  const int b = blockIdx.y;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const int f = (int)(t / hop), k = (int)(t - (long long)f * hop);
+  const double f064 = f0[(size_t)b * F + f];
+  const float f032 = (float)f064;                      // torch.FloatTensor(f0)
+  if (sine_out) {
+    const float vuv = f032 > 0.f ? 1.f : 0.f;
+    const float x = __fdiv_rn(f032, fs);
+    const float rad = x - floorf(x);                   // remainder(x, 1), exact
+    const float c32 = (float)(prefix[(size_t)b * F + f] + (double)(k + 1) * (double)rad);
+    const float phase = __fmul_rn(__fmul_rn(c32, 2.0f), 3.14159274101257324f);   // cumsum * 2 * np.pi, fp32 scalars
+    float v = __fmul_rn(__fmul_rn(vuv, sinf(phase)), sine_amp);
+    if (noise) {
+      const float amp = __fadd_rn(__fmul_rn(vuv, noise_amp), __fdiv_rn(__fmul_rn(1.0f - vuv, noise_amp), 3.0f));
+      v = __fadd_rn(v, __fmul_rn(amp, noise[(size_t)b * T + t]));
+    }
+    sine_out[(size_t)b * sine_bstride + t] = v;
+  }
+  if (d_out) {
+    // dilated_factor (features.py:56-75), float64 like the reference's numpy expression: fs / f0 / dense_factor,
+    // unvoiced frames first set to fs / dense_factor
+    const double fsd = (double)fs;
+    const double f0d = f064 == 0.0 ? fsd / (double)dense_factor : f064;
+    d_out[(size_t)b * T + t] = (float)(fsd / f0d / (double)dense_factor);
+  }
+}
+
 }  // namespace svsk
 
 using namespace svsk;
@@ -168,4 +251,24 @@ extern "C" int svsk_expand1_bf16(const float* x, long long x_batch_stride, const
   expand1_bf16_kernel<<<dim3(ceil_div(T, 256), B), 256, 0, as_stream(stream)>>>(x, x_batch_stride, w, bias, (__nv_bfloat16*)out,
                                                                                 T, C);
   return check_launch("expand1_bf16");
+}
+
+extern "C" int svsk_usfgan_source(const double* f0, const float* noise, float* sine_out, long long sine_batch_stride, float* d_out,
+                                  double* scratch, int B, int F, int hop, int sample_rate, int dense_factor, float sine_amp,
+                                  float noise_amp, void* stream) {
+  SVSK_REQUIRE(f0 && scratch && (sine_out || d_out), SVSK_E_ARG, "usfgan_source: null");
+  SVSK_REQUIRE(B > 0 && B <= 65535 && F > 0 && hop > 0 && sample_rate > 0 && dense_factor > 0, SVSK_E_ARG,
+               "usfgan_source: B=%d F=%d hop=%d fs=%d dense_factor=%d", B, F, hop, sample_rate, dense_factor);
+  SVSK_REQUIRE(!sine_out || sine_batch_stride >= (long long)F * hop, SVSK_E_ARG, "usfgan_source: sine batch stride");
+  if (sine_out) {
+    source_frame_scan_kernel<<<B, 1024, 0, as_stream(stream)>>>(f0, scratch, F, hop, (float)sample_rate);
+    int rc = check_launch("usfgan_source (frame scan)");
+    if (rc) return rc;
+  }
+  const long long T = (long long)F * hop;
+  dim3 grid((unsigned)((T + 255) / 256), (unsigned)B);
+  source_samples_kernel<<<grid, 256, 0, as_stream(stream)>>>(f0, scratch, noise_amp > 0.f ? noise : nullptr, sine_out,
+                                                             sine_batch_stride, d_out, F, hop, (float)sample_rate, dense_factor,
+                                                             sine_amp, noise_amp);
+  return check_launch("usfgan_source");
 }

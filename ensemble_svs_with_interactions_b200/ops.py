@@ -216,6 +216,32 @@ def diffnet_block_bf16(xb_in, xb_out, x32, skip32, cond, w1p, woutp, stepbias, b
     L.check(L.lib().svsk_diffnet_block3_bf16(C.byref(p), L.stream_ptr()), "diffnet_block_bf16")
 
 
+def usfgan_source(f0, *, hop, sample_rate, dense_factor=4, sine_amp=0.1, noise_amp=0.0, noise=None, sine_out=None,
+                  want_sine=True, want_d=True):
+    """f0 [B, F] float64 CUDA (Hz, 0 = unvoiced) -> (sine [B, 1, F*hop] fp32 or None, d [B, 1, F*hop] fp32 or None): the
+    sine-based source signal (with `noise` [B, 1, F*hop] added at noise_amp / noise_amp/3) and the dilation factors.
+    sine_out: optional [B, Cs, F*hop] fp32 tensor whose channel 0 receives the sine (the generator's in_signal)."""
+    B, F = f0.shape
+    T = F * int(hop)
+    dev = f0.device
+    sine, stride = None, 0
+    if want_sine:
+        if sine_out is None:
+            sine_out = torch.empty((B, 1, T), device=dev, dtype=f32)
+        if sine_out.dim() != 3 or sine_out.shape[0] != B or sine_out.shape[2] != T or not sine_out.is_contiguous():
+            raise ValueError(f"usfgan_source: sine_out must be a contiguous [B={B}, channels, T={T}] tensor")
+        sine, stride = sine_out, sine_out.stride(0)
+    if noise_amp > 0 and want_sine and (noise is None or noise.numel() != B * T):
+        raise ValueError("usfgan_source: noise_amp > 0 needs the Gaussian draws, [B, 1, T]")
+    d = torch.empty((B, 1, T), device=dev, dtype=f32) if want_d else None
+    scratch = torch.empty((B, F), device=dev, dtype=torch.float64)
+    L.check(L.lib().svsk_usfgan_source(L.ptr(f0, torch.float64, "f0"), L.ptr(noise, f32, "noise") if noise_amp > 0 else C.c_void_p(0),
+                                       L.ptr(sine, f32, "sine_out"), stride, L.ptr(d, f32), L.ptr(scratch), B, F, int(hop),
+                                       int(sample_rate), int(dense_factor), float(sine_amp), float(noise_amp), L.stream_ptr()),
+            "usfgan_source")
+    return sine, d
+
+
 # ------------------------------------------------------------------------------------------------ training kernels
 SEG_PLAIN, SEG_GATE_FWD, SEG_RES_SKIP, SEG_GATE_BWD, SEG_ADD_SCALE = 0, 1, 2, 3, 4
 

@@ -4,6 +4,7 @@ import numpy as np
 import torch
 from torch import nn
 
+from .. import ops
 from .utils import SignalGenerator, dilated_factor
 
 
@@ -25,9 +26,16 @@ class USFGANWrapper(nn.Module):
             raise NotImplementedError("SiFi-GAN generators are not part of this build (uSFGAN family only)")
         device = aux_feats.device
         window = self.config.generator.aux_context_window
-        df = dilated_factor(np.squeeze(f0.copy()), data.sample_rate, data.dense_factor).repeat(data.hop_size, axis=0)
         c = nn.functional.pad(aux_feats.unsqueeze(0).transpose(2, 1), (window, window), mode="replicate").to(device)
-        df = torch.FloatTensor(df).view(1, 1, -1).to(device)
+        if device.type == "cuda":
+            # dilated_factor (features.py:56-75) on the device, in float64 from the caller's own values like the
+            # reference's numpy expression (the tap offsets round(d * dilation) must come out identical)
+            f64 = torch.as_tensor(np.asarray(f0).reshape(1, -1), dtype=torch.float64).to(device)
+            _, df = ops.usfgan_source(f64, hop=data.hop_size, sample_rate=data.sample_rate, dense_factor=data.dense_factor,
+                                      want_sine=False)
+        else:
+            df = dilated_factor(np.squeeze(f0.copy()), data.sample_rate, data.dense_factor).repeat(data.hop_size, axis=0)
+            df = torch.FloatTensor(df).view(1, 1, -1).to(device)
         f0 = torch.FloatTensor(f0).unsqueeze(0).transpose(2, 1).to(device)
         signal_generator = SignalGenerator(sample_rate=data.sample_rate, hop_size=data.hop_size,
                                            sine_amp=data.sine_amp, noise_amp=data.noise_amp,
@@ -62,8 +70,8 @@ class USFGANWrapper(nn.Module):
         # dilated_factor (features.py:56-75) on the device: unvoiced frames count as fs / dense_factor, i.e. factor 1
         # (in float64 like the reference's numpy expression, then rounded to fp32 once: the tap offsets round(d * dilation)
         # must come out identical)
-        f0_df = torch.where(f0 == 0, torch.full_like(f0, data.sample_rate / data.dense_factor), f0).double()
-        df = (float(data.sample_rate) / f0_df / data.dense_factor).float().repeat_interleave(data.hop_size, dim=2)
+        _, df = ops.usfgan_source(f0[:, 0].double().contiguous(), hop=data.hop_size, sample_rate=data.sample_rate,
+                                  dense_factor=data.dense_factor, want_sine=False)
         c = nn.functional.pad(aux_feats.transpose(2, 1), (window, window), mode="replicate")
         signal_generator = SignalGenerator(sample_rate=data.sample_rate, hop_size=data.hop_size,
                                            sine_amp=data.sine_amp, noise_amp=data.noise_amp,

@@ -1,15 +1,19 @@
 """uSFGAN front-end helpers with the API of ``nnsvs.usfgan.utils.features``
 (``dilated_factor`` features.py:56-75, ``SignalGenerator`` features.py:78-180).
 
-Front-end only — SURVEY.md §8(f) row 2 schedules its fusion into libsvsk after the residual stacks.  Until then these
-stay small numpy / torch expressions evaluated on the device ``f0`` lives on (they are inputs to the kernels, and to
-both sides of every parity test).
+On a CUDA device the sine source and the dilation factors are one libsvsk kernel pair (``svsk_usfgan_source``,
+SURVEY.md §8(f) row 2): a per-track fp64 scan over the frames and one pass over the samples — the phase is the fp64
+prefix sum rounded to fp32 per sample, which is bit for bit what ``torch.cumsum`` gives the reference on a CPU host
+(CUDA's own fp32 parallel scan drifts from it).  The numpy ``dilated_factor`` and the torch expressions below remain for
+host-side callers (numpy inputs, CPU tensors in the host-logic tests).
 """
 import math
 
 import numpy as np
 import torch
 import torch.nn.functional as F
+
+from ... import ops
 
 
 def dilated_factor(batch_f0, fs, dense_factor):
@@ -62,6 +66,12 @@ class SignalGenerator:
 
     @torch.no_grad()
     def sinusoid(self, f0):
+        if f0.is_cuda:
+            B, _, Fr = f0.shape
+            noise = self._randn("sine", (B, 1, Fr * self.hop_size), f0.device) if self.noise_amp > 0 else None
+            sine, _ = ops.usfgan_source(f0[:, 0].double().contiguous(), hop=self.hop_size, sample_rate=self.sample_rate,
+                                        sine_amp=self.sine_amp, noise_amp=self.noise_amp, noise=noise, want_d=False)
+            return sine
         voiced = self._voiced_mask(f0)
         cycles_per_sample = torch.remainder(self._hold(f0) / self.sample_rate, 1)
         phase = torch.cumsum(cycles_per_sample, dim=2) * 2 * math.pi

@@ -427,6 +427,19 @@ SVSK_API int svsk_scale_features_f32(const float* x, float* y, const float* a, c
 SVSK_API int svsk_mdn_head_f32(const float* raw, float* log_pi, float* log_sigma, float* mu, float* best_sigma, float* best_mu,
                                long long rows, int G, int D, int ld, void* stream);
 
+/* Source signal and dilation factors of the uSFGAN front end from frame-level F0 (nnsvs/usfgan/utils/features.py:
+ * SignalGenerator.sinusoid :145-164, dilated_factor :56-75; called per utterance by USFGANWrapper.inference,
+ * nnsvs/usfgan/__init__.py:50-63).  f0 [B][F] in Hz as float64 (0 = unvoiced; the sine uses its fp32 rounding like
+ * torch.FloatTensor(f0)); T = F * hop samples per track.
+ *   sine_out[b * sine_batch_stride + t] = vuv * sin(2 pi cumsum((f0 / fs) mod 1)) * sine_amp
+ *                                         + noise[b][t] * (vuv * noise_amp + (1 - vuv) * noise_amp / 3)    (NULL: skipped)
+ *   d_out[b][t] = float(fs / f0 / dense_factor), unvoiced -> 1                                              (NULL: skipped)
+ * The prefix sums are fp64 rounded to fp32 per sample — what torch.cumsum does on a CPU host.  noise [B][T] holds the
+ * caller's Gaussian draws (ignored when noise_amp == 0); scratch: B * F doubles. */
+SVSK_API int svsk_usfgan_source(const double* f0, const float* noise, float* sine_out, long long sine_batch_stride, float* d_out,
+                                double* scratch, int B, int F, int hop, int sample_rate, int dense_factor, float sine_amp,
+                                float noise_amp, void* stream);
+
 /* ---- DiffNet training kernels (dgrad / wgrad / fused gate backward) -------------------------
  * Replace, inside the training step (nnsvs/bin/train_acoustic_multitrack.py:358-380), what autograd derives from
  * ResidualBlock.forward / DiffNet.forward (nnsvs/diffsinger/denoiser.py:54-66, 101-124).  See diffnet_train_sm100.cu. */
