@@ -12,7 +12,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsvsk.so")
+# SVSK_LIB_PATH: A/B measurements of kernel variants on one box (tools/); the product path is the in-tree build
+LIB_PATH = os.environ.get("SVSK_LIB_PATH") or os.path.join(_HERE, "csrc", "libsvsk.so")
 
 _lib = None
 _lock = threading.Lock()

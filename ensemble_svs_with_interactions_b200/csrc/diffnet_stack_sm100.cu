@@ -335,12 +335,15 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
           ptx::mbar_wait(&bars->xw_full, 0);
         } else {
           ptx::mbar_wait(&bars->xc_ready, pp);      // centre rows rewritten in place by the previous layer's epilogue
+          if (l == 2) SVSK_STAMP(27);
           ptx::mbar_wait(&bars->d2_drained[0], pp); // and the first 256 TMEM columns read out
         }
         ptx::tc_fence_after();
         if (l == 1) SVSK_STAMP(2);
+        if (l == 2) SVSK_STAMP(18);
         for (int cb = 0; cb < CB; ++cb) {
           SVSK_WAIT_ENTRY();
+          if (l == 2 && cb == 0) SVSK_STAMP(19);
           SVSK_ISSUE4(0, xw_lo + cb * (kSWinBytes >> 4) + kSHalo * 8, ring_lo + s * (kSTile >> 4), cb != 0);
         }
         // ---- side taps, block 0
@@ -485,6 +488,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
       for (int j = 0; j < NB; ++j) {
         ptx::mbar_wait(&bars->d1_full[j], pl);
         ptx::tc_fence_after();
+        if (l == 1 && elected) SVSK_STAMP(20 + 2 * j);   // 20 / 22: gating of block 0 / 1 starts
         uint32_t rgb[2][16], rfb[2][16];
         ptx::tmem_ld16(tmem + tlane + j * 256 + 16 * sub, rgb[0]);
         ptx::tmem_ld16(tmem + tlane + j * 256 + 128 + 16 * sub, rfb[0]);
@@ -530,6 +534,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         ptx::tc_fence_before();
         ptx::fence_proxy_async_smem();  // G (generic-proxy stores) -> visible to the tensor cores' async proxy
         ptx::mbar_arrive_cluster(gr_leader + (uint32_t)j * 8u);
+        if (l == 1 && elected) SVSK_STAMP(21 + 2 * j);   // 21 / 23: ... and ends (this thread)
       }
 
       // ---- epilogue 2: residual -> in place over the window's centre rows (the next layer's centre tap) ;
@@ -539,9 +544,11 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         ptx::tc_fence_after();
         if (l == 1 && elected) SVSK_STAMP(24 + 2 * j);  // 24: D2[0] complete, 26: D2[1] complete
         const int res_cols = min(max(C - j * 256, 0), 256);  // residual columns in this 256-column block
+        bool drained_said = false;
         if (res_cols > 0 && !last) {
           if (l == 0) ptx::mbar_wait(&bars->xw_full, 0);  // (long complete) makes the TMA-written window visible here
           if (send_left || send_right) ptx::mbar_wait(&bars->halo_free, pl);  // the neighbour's GEMM1 of this layer is done
+          if (l == 1 && warp == 4 && lane == 0) SVSK_STAMP(28);               // an edge thread (row 0) starts its residual part
           const int n_res = res_cols / (16 * kSW);
           uint32_t rr[2][16];
           ptx::tmem_ld16(tmem + tlane + j * 256 + 16 * sub, rr[0]);
@@ -583,6 +590,15 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
             ptx::fence_proxy_async_smem();
             ptx::mbar_arrive_cluster(xc_leader);  // first: the next layer's centre tap is waiting for this
             ptx::mbar_arrive(&bars->xe_ready);
+            if (res_cols == 256) {
+              // ... and for this: the block holds no skip columns, so this thread has read all of it out of TMEM.  Said
+              // BEFORE the edge threads' cluster-scope fence below (MEMBAR.ALL.GPU + L1 invalidate, ~3 k cycles in 4 of the
+              // 8 epilogue warps), during which the next layer's first MMA used to wait on a condition long true:
+              // 392.4 -> 375.9 us per 20-layer launch at config 2, same box (profiles/r02h_stack_ab.log)
+              ptx::tc_fence_before();
+              ptx::mbar_arrive_cluster(dr_leader + (uint32_t)j * 8u);
+              drained_said = true;
+            }
             if (send_left || send_right) {
               ptx::fence_proxy_async_cluster_release();  // remote generic-proxy stores -> the neighbour's tensor cores
               ptx::mbar_arrive_cluster(nb_bar);
@@ -590,6 +606,8 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
           }
         }
         if (l == 1 && elected && j == 0) SVSK_STAMP(25);  // residual half written
+        if (l == 1 && warp == 4 && lane == 0 && j == 0) SVSK_STAMP(9);              // ... by an edge thread (row 0; DSMEM mode)
+        if (l == 1 && warp == kSActWarp - 1 && lane == 31 && j == 0) SVSK_STAMP(10);   // ... by the last epilogue warp
         // skip part: columns [res_cols, 256) of this block in slabs of 32 (one 128-byte fp32 row per frame).  Each warp
         // owns whole slabs (the two warps of a lane quarter alternate) and its 32 rows of them: it stages them in a
         // private 2 x 4 KB piece of the G buffer and issues its own TMA reduce-add — no CTA-wide barrier, no shared
@@ -639,12 +657,14 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
           }
           if (l == 1 && elected) SVSK_STAMP(30);
         }
-        // block j has been read out of TMEM: the next layer's GEMM1 may overwrite it
-        ptx::tc_fence_before();
-        ptx::mbar_arrive_cluster(dr_leader + (uint32_t)j * 8u);
+        if (!drained_said) {
+          ptx::tc_fence_before();
+          ptx::mbar_arrive_cluster(dr_leader + (uint32_t)j * 8u);
+        }
       }
       // the bias arrays are rewritten at the top of the next layer: every epilogue thread must be done reading them
       ptx::named_bar_sync(1, kSEpi);
+      if (l == 1 && elected) SVSK_STAMP(31);             // all epilogue threads of this CTA are through layer 1
     }
   }
 

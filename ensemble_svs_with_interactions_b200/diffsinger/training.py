@@ -24,7 +24,8 @@ it.  Parameters remain ordinary ``nn.Parameter``s (they enter the Function stack
 Numerics: bf16 GEMM operands and bf16 stored activations / gradients, fp32 accumulation, ``tanh.approx`` in the gate and
 in its derivative — the backward differentiates exactly the function the forward computes (up to the bf16 rounding of
 the stored tensors).  Models that resolve to precision "fp32" (C not in {128, 256}, H % 64 != 0, or forced) have no
-tensor-core kernels at all; their training goes through ``torch_restatement`` below (plain fp32 autograd).
+tensor-core kernels at all: their forward stays libsvsk's fp32 path and their backward differentiates
+``torch_restatement`` below (``_DiffNetFp32Fn``).
 """
 from __future__ import annotations
 
@@ -371,11 +372,40 @@ class _DiffNetStackFn(torch.autograd.Function):
                                          ctx.needs_input_grad[2])
 
 
+class _DiffNetFp32Fn(torch.autograd.Function):
+    """precision="fp32" models (widths the tensor-core kernels do not cover, or forced): the forward is libsvsk's exact
+    fp32 path like every other call; the backward differentiates the PyTorch re-statement.  Not the training path of any
+    recipe (C = 256 / 128 resolve to bf16) — it keeps small / odd models trainable."""
+
+    @staticmethod
+    def forward(ctx, net, spec, t, cond, *params):
+        ctx.net = net
+        ctx.save_for_backward(spec, t, cond)
+        with torch.no_grad():
+            return net._forward_no_grad(spec, t, cond)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        net = ctx.net
+        spec, t, cond = ctx.saved_tensors
+        params = list(net.parameters())
+        with torch.enable_grad():
+            spec_ = spec.detach().requires_grad_(ctx.needs_input_grad[1])
+            cond_ = cond.detach().requires_grad_(ctx.needs_input_grad[3])
+            out = torch_restatement(net, spec_, t, cond_)
+            wanted = [x for x in (spec_, cond_) if x.requires_grad] + [p for p in params if p.requires_grad]
+            grads = list(torch.autograd.grad(out, wanted, grad_out.to(out.dtype), allow_unused=True))
+        g_spec = grads.pop(0) if spec_.requires_grad else None
+        g_cond = grads.pop(0) if cond_.requires_grad else None
+        g_params = [grads.pop(0) if p.requires_grad else None for p in params]
+        return (None, g_spec, None, g_cond, *g_params)
+
+
 def diffnet_forward_with_grad(net, spec, diffusion_step, cond):
-    """DiffNet.forward under autograd.  bf16 models: the kernel Function above; fp32 models: the PyTorch re-statement."""
+    """DiffNet.forward under autograd.  bf16 models: forward and backward are the kernel Function above."""
     t = diffusion_step.reshape(-1).to(torch.int64)
     if net.resolved_precision() != "bf16":
-        return torch_restatement(net, spec, t, cond)
+        return _DiffNetFp32Fn.apply(net, spec, t, cond, *net.parameters())
     layers = net.residual_layers
     e = _step_embedding(net, t)                                                          # [B, C]
     Wdp = torch.stack([ly.diffusion_projection.weight for ly in layers])                 # [L, C, C]

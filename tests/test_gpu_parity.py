@@ -326,7 +326,9 @@ def test_linear_bf16(N, K, Cout, act):
     close_bf16(yb.float(), ref, 5e-3, 1e-2)
 
 
-def _random_diffnet(C, H, M, L, seed, cycle=4):
+def _random_diffnet(C, H, M, L, seed, cycle=4, requires_grad=False):
+    """requires_grad=False (inference tests): DiffNet.forward then runs the inference kernels even when the caller has not
+    disabled autograd; with trainable parameters and grad mode on it is the training Function (diffsinger/training.py)."""
     from ensemble_svs_with_interactions_b200.diffsinger import DiffNet
     torch.manual_seed(seed)
     m = DiffNet(in_dim=M, encoder_hidden_dim=H, residual_layers=L, residual_channels=C, dilation_cycle_length=cycle)
@@ -336,7 +338,7 @@ def _random_diffnet(C, H, M, L, seed, cycle=4):
         for p in m.parameters():
             if p.dim() == 1:
                 p.copy_(torch.randn(p.shape, generator=g) * 0.1)
-    return m.eval()
+    return m.eval().requires_grad_(requires_grad)
 
 
 @pytest.mark.parametrize("C,H,T,dil", [(256, 256, 333, 1), (256, 256, 333, 8), (256, 128, 200, 4),
@@ -598,7 +600,7 @@ def test_diffnet_bf16_full_size_properties():
 def test_diffnet_training_forward_backward():
     """GaussianDiffusion.forward in train mode: libsvsk forward and backward kernels."""
     from ensemble_svs_with_interactions_b200.diffsinger import GaussianDiffusion
-    den = _random_diffnet(128, 128, 60, 4, seed=21)
+    den = _random_diffnet(128, 128, 60, 4, seed=21, requires_grad=True)
     m = GaussianDiffusion(128, 60, den, K_step=100).to(DEV).train()
     g = torch.Generator().manual_seed(22)
     B, T = 2, 64
@@ -636,7 +638,7 @@ def test_diffnet_training_gradients_vs_oracle_autograd(C, H, M, L, B, T, cycle, 
     zero, the two forwards disagree on those masks, and every such element is a full-size gradient difference —
     sqrt(0.004) ~ 6 % rel-L2 on EVERY gradient (it enters at the tail), inherent to comparing a bf16 with an fp32 forward.
     Bound there: rel-L2 <= 1.2e-1 and cosine similarity >= 0.993."""
-    m = _random_diffnet(C, H, M, L, seed=C + L + T, cycle=cycle)
+    m = _random_diffnet(C, H, M, L, seed=C + L + T, cycle=cycle, requires_grad=True)
     if relu_margin:
         with torch.no_grad():
             m.input_projection.bias.add_(8.0)
