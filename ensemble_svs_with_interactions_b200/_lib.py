@@ -89,6 +89,15 @@ class TapGemmBf16Params(C.Structure):
     ]
 
 
+class WavenetBlockParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("c", C.c_void_p), ("w1t", C.c_void_p), ("b1", C.c_void_p), ("w2t", C.c_void_p), ("b2", C.c_void_p),
+        ("x_out", C.c_void_p), ("skips", C.c_void_p),
+        ("B", C.c_int32), ("T", C.c_int32), ("R", C.c_int32), ("G", C.c_int32), ("S", C.c_int32), ("Cc", C.c_int32),
+        ("ksize", C.c_int32), ("dilation", C.c_int32), ("first", C.c_int32),
+    ]
+
+
 class SegGemmParams(C.Structure):
     _fields_ = [
         ("x", C.c_void_p * 4), ("ldx", C.c_int32 * 4), ("kx", C.c_int32 * 4), ("shift", C.c_int32 * 4), ("nseg", C.c_int32),
@@ -156,6 +165,8 @@ _SIGNATURES = {
     "svsk_upsample_fused": [_V, _V, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_int, _V, _V, C.c_int, _V],
     "svsk_expand1_bf16": [_V, C.c_longlong, _V, _V, _V, C.c_int, C.c_int, C.c_int, _V],
     "svsk_diffnet_pack_block": [_V, _V, _V, _V, _V, _I, _I, _V],
+    "svsk_wavenet_block_f32": [C.POINTER(WavenetBlockParams), _V],
+    "svsk_wavenet_pack_f32": [_V, _V, _V, _V, _V, _V, _I, _I, _I, _I, _I, _V],
     "svsk_usfgan_source": [_V, _V, _V, C.c_longlong, _V, _V, _I, _I, _I, _I, _I, _F, _F, _V],
     "svsk_seggemm_bf16": [C.POINTER(SegGemmParams), _V],
     "svsk_wgrad_bf16": [C.POINTER(WgradParams), _V],

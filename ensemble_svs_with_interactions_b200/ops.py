@@ -216,6 +216,32 @@ def diffnet_block_bf16(xb_in, xb_out, x32, skip32, cond, w1p, woutp, stepbias, b
     L.check(L.lib().svsk_diffnet_block3_bf16(C.byref(p), L.stream_ptr()), "diffnet_block_bf16")
 
 
+def wavenet_pack_f32(wconv, wc, wskip, wout):
+    """Effective (weight-norm folded) weights of one ResSkipBlock -> (w1t [k*R + Cc, G], w2t [G/2, S + R]) fp32."""
+    G, R, k = wconv.shape
+    Cc, S = wc.shape[1], wskip.shape[0]
+    dev = wconv.device
+    w1t = torch.empty((k * R + Cc, G), device=dev, dtype=f32)
+    w2t = torch.empty((G // 2, S + R), device=dev, dtype=f32)
+    L.check(L.lib().svsk_wavenet_pack_f32(L.ptr(wconv.contiguous(), f32), L.ptr(wc.contiguous(), f32), L.ptr(wskip.contiguous(), f32),
+                                          L.ptr(wout.contiguous(), f32), L.ptr(w1t), L.ptr(w2t), R, G, S, Cc, k, L.stream_ptr()),
+            "wavenet_pack_f32")
+    return w1t, w2t
+
+
+def wavenet_block_f32(x, c, w1t, b1, w2t, b2, skips, *, ksize, dilation, first, out=None):
+    """One fused ResSkipBlock (svsk_wavenet_block_f32): x [B,R,T], c [B,Cc,T] -> new x; skips [B,S,T] set or accumulated."""
+    B, R, T = x.shape
+    out = torch.empty_like(x) if out is None else out
+    p = L.WavenetBlockParams()
+    p.x, p.c, p.w1t, p.b1 = L.ptr(x, f32, "x"), L.ptr(c, f32, "c"), L.ptr(w1t, f32, "w1t"), L.ptr(b1, f32, "b1")
+    p.w2t, p.b2, p.x_out, p.skips = L.ptr(w2t, f32, "w2t"), L.ptr(b2, f32, "b2"), L.ptr(out, f32, "x_out"), L.ptr(skips, f32, "skips")
+    p.B, p.T, p.R, p.G, p.S, p.Cc = B, T, R, w1t.shape[1], skips.shape[1], c.shape[1]
+    p.ksize, p.dilation, p.first = int(ksize), int(dilation), int(first)
+    L.check(L.lib().svsk_wavenet_block_f32(C.byref(p), L.stream_ptr()), "wavenet_block_f32")
+    return out
+
+
 def usfgan_source(f0, *, hop, sample_rate, dense_factor=4, sine_amp=0.1, noise_amp=0.0, noise=None, sine_out=None,
                   want_sine=True, want_d=True):
     """f0 [B, F] float64 CUDA (Hz, 0 = unvoiced) -> (sine [B, 1, F*hop] fp32 or None, d [B, 1, F*hop] fp32 or None): the

@@ -38,15 +38,23 @@ class ResSkipBlock(nn.Module):
         self.conv1x1_out = Conv1d1x1(gate_out_channels, residual_channels)
         self.conv1x1_skip = Conv1d1x1(gate_out_channels, skip_out_channels)
 
+    def _packed(self):
+        """Folded (weight norm) and transposed weights of the fused kernel, rebuilt when any parameter changes."""
+        key = tuple((q.data_ptr(), q._version) for q in self.parameters())
+        if getattr(self, "_pack_key", None) != key:
+            w1t, w2t = ops.wavenet_pack_f32(_w(self.conv).to(f32), _w(self.conv1x1c).to(f32)[:, :, 0],
+                                            _w(self.conv1x1_skip).to(f32)[:, :, 0], _w(self.conv1x1_out).to(f32)[:, :, 0])
+            b1 = None if self.conv.bias is None else self.conv.bias.detach().to(f32).contiguous()
+            b2 = torch.cat([self.conv1x1_skip.bias.detach(), self.conv1x1_out.bias.detach()]).to(f32).contiguous()
+            self._pack, self._pack_key = (w1t, b1, w2t, b2), key
+        return self._pack
+
     def run(self, x, c, skips, first):
-        """x, c NCT fp32.  Returns the new x; accumulates the skip branch into ``skips``.
-        "pad (k-1)d both sides then trim right" (modules.py:99-101) == taps at t-(k-1-j)d, zero for t < 0."""
-        y = ops.conv1d_f32(x, _w(self.conv), self.conv.bias, dilation=self.dilation, tap_origin=self.kernel_size - 1,
-                           pad_mode=ops.PAD_ZEROS)
-        ops.conv1d_f32(c, _w(self.conv1x1c), None, out=y, accumulate=True)
-        z = ops.gated_act_f32(y, ops.GATE_TANH_SIGMOID)
-        ops.conv1d_f32(z, _w(self.conv1x1_skip), self.conv1x1_skip.bias, out=skips, accumulate=not first)
-        return ops.conv1d_f32(z, _w(self.conv1x1_out), self.conv1x1_out.bias, residual=x)
+        """x, c NCT fp32.  Returns the new x; accumulates the skip branch into ``skips``.  One launch
+        (svsk_wavenet_block_f32): "pad (k-1)d both sides then trim right" (modules.py:99-101) == taps at t-(k-1-j)d, zero
+        for t < 0; tanh on the first half of the gate channels, sigmoid on the second; x + res without a sqrt(1/2)."""
+        w1t, b1, w2t, b2 = self._packed()
+        return ops.wavenet_block_f32(x, c, w1t, b1, w2t, b2, skips, ksize=self.kernel_size, dilation=self.dilation, first=first)
 
     @torch.no_grad()
     def forward(self, x, c):

@@ -427,6 +427,27 @@ SVSK_API int svsk_scale_features_f32(const float* x, float* y, const float* a, c
 SVSK_API int svsk_mdn_head_f32(const float* raw, float* log_pi, float* log_sigma, float* mu, float* best_sigma, float* best_mu,
                                long long rows, int G, int D, int ld, void* stream);
 
+/* Fused WaveNet residual block, fp32 — replaces ResSkipBlock._forward (nnsvs/wavenet/modules.py:88-122), one launch:
+ *   y = causal_conv(x; ksize, dilation) + conv1x1c(c) + b1;  z = tanh(y[:G/2]) * sigmoid(y[G/2:])
+ *   skips = (first ? 0 : skips) + conv1x1_skip(z) + b2[:S];  x_out = conv1x1_out(z) + b2[S:] + x
+ * x, x_out [B][R][T], c [B][Cc][T], skips [B][S][T] fp32; x_out must not alias x.  w1t [ksize*R + Cc][G] and
+ * w2t [G/2][S + R] come from svsk_wavenet_pack_f32 (effective, weight-norm-folded weights: conv [G][R][ksize],
+ * conv1x1c [G][Cc], conv1x1_skip [S][G/2], conv1x1_out [R][G/2]); b1 [G] (may be NULL), b2 [S + R] = [skip | out]. */
+typedef struct svsk_wavenet_block_params {
+  const float* x;
+  const float* c;
+  const float* w1t;
+  const float* b1;
+  const float* w2t;
+  const float* b2;
+  float* x_out;
+  float* skips;
+  int32_t B, T, R, G, S, Cc, ksize, dilation, first;
+} svsk_wavenet_block_params;
+SVSK_API int svsk_wavenet_block_f32(const svsk_wavenet_block_params* p, void* stream);
+SVSK_API int svsk_wavenet_pack_f32(const float* wconv, const float* wc, const float* wskip, const float* wout, float* w1t,
+                                   float* w2t, int R, int G, int S, int Cc, int ksize, void* stream);
+
 /* Source signal and dilation factors of the uSFGAN front end from frame-level F0 (nnsvs/usfgan/utils/features.py:
  * SignalGenerator.sinusoid :145-164, dilated_factor :56-75; called per utterance by USFGANWrapper.inference,
  * nnsvs/usfgan/__init__.py:50-63).  f0 [B][F] in Hz as float64 (0 = unvoiced; the sine uses its fp32 rounding like

@@ -27,7 +27,9 @@ def run(steps, warmup, rank, local, world, dev):
     with torch.no_grad():
         model.denoise_fn.output_projection.weight.normal_(0, 0.02)
     model = model.to(dev).train()
-    ddp = DDP(model, device_ids=[local]) if world > 1 else model
+    # the whole stack's gradients appear at once (one autograd node): one bucket that holds them all, and .grad tensors that
+    # ARE the bucket (no copy in, no copy out)
+    ddp = DDP(model, device_ids=[local], gradient_as_bucket_view=True, bucket_cap_mb=128) if world > 1 else model
     opt = torch.optim.AdamW(ddp.parameters(), lr=1e-3, betas=(0.9, 0.98))
     B, T = 6, 1000
     g = torch.Generator().manual_seed(1234 + rank)
