@@ -64,6 +64,12 @@ struct DiffnetStackArgs {
   int* flags;             // [B * tiles_per_track] layers published per tile; zero at launch
   int dsmem_halo;         // 1: one cluster per track, halo rows through distributed shared memory; 0: through global memory
   int B, T, C, H, L, sb_batch_stride, sb_layer_stride, init_skip, nentries, tiles_per_track;
+  // C = 128 only (one 256-column output block): the accumulator alternates between the two halves of TMEM from layer to
+  // layer, so that a layer's GEMM1 does not wait for the previous layer's skip columns to be read out (they share the
+  // block with the residual columns: ~5 k of a 19.4 k-cycle layer, profiles/r02j_stack_c128_timeline.log), and the
+  // conditioner tiles — the same for every layer — stay in their own shared-memory tiles instead of being reloaded into
+  // the G buffer once the skip epilogue has released it (3.8 k cycles into the layer).
+  int pingpong, cond_resident;
   int dilation[kSMaxLayers];
   unsigned long long* dbg;
 };
@@ -131,7 +137,8 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
   const int twoC = 2 * C;
   uint8_t* xw_smem = smem;                         // CB window tiles
   uint8_t* g_smem = xw_smem + CB * kSWinBytes;     // max(HB, KB2, 4) tiles: conditioner tiles, then G, then skip slabs
-  uint8_t* ring = g_smem + max(max(HB, KB2), 4) * kSTile;  // nentries x 16 KB (the G buffer holds >= 4 skip slabs)
+  uint8_t* cond_smem = a.cond_resident ? g_smem + max(max(HB, KB2), 4) * kSTile : g_smem;   // HB resident tiles, or the G buffer
+  uint8_t* ring = g_smem + (max(max(HB, KB2), 4) + (a.cond_resident ? HB : 0)) * kSTile;  // nentries x 16 KB (the G buffer holds >= 4 skip slabs)
   float* sb_full = reinterpret_cast<float*>(ring + a.nentries * kSTile);
   float* sb_l = sb_full + twoC;
   float* sb_r = sb_l + twoC;
@@ -239,7 +246,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
       // layer 0: conditioner tiles and the whole window of the stack's input
       for (int hb = 0; hb < HB; ++hb) {
         ptx::mbar_arrive_expect_tx(&bars->cd_full[hb], kSTile);
-        ptx::tma_load_3d(g_smem + hb * kSTile, &tm_cond, &bars->cd_full[hb], hb * 64, t_cta0, b);
+        ptx::tma_load_3d(cond_smem + hb * kSTile, &tm_cond, &bars->cd_full[hb], hb * 64, t_cta0, b);
       }
       ptx::mbar_arrive_expect_tx(&bars->xw_full, CB * kSWinBytes);
       for (int cb = 0; cb < CB; ++cb)
@@ -248,6 +255,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         const uint32_t pp = (uint32_t)(l - 1) & 1u;
         const CUtensorMap* tm_e = pp ? &tm_e1 : &tm_e0;
         if (a.dsmem_halo) {  // the halo rows travel through distributed shared memory: only the conditioner tiles here
+          if (a.cond_resident) break;  // ... and not even those
           ptx::mbar_wait(&bars->gc_free, pp);
           for (int hb = 0; hb < HB; ++hb) {
             ptx::mbar_arrive_expect_tx(&bars->cd_full[hb], kSTile);
@@ -287,6 +295,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         }
         if (l == 1) SVSK_STAMP(13);
         // conditioner tiles of layer l, once the G buffer is free again
+        if (a.cond_resident) continue;
         ptx::mbar_wait(&bars->gc_free, pp);
         if (l == 1) SVSK_STAMP(14);
         for (int hb = 0; hb < HB; ++hb) {
@@ -300,6 +309,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
     if (rank == 0 && lane == 0) {
       const uint32_t idesc = ptx::umma_idesc_bf16_f32(256, 256);
       const uint32_t ring_lo = ptx::umma_desc_lo(ptx::smem_u32(ring)), g_lo = ptx::umma_desc_lo(ptx::smem_u32(g_smem));
+      const uint32_t cond_lo = ptx::umma_desc_lo(ptx::smem_u32(cond_smem));
       const uint32_t xw_lo = ptx::umma_desc_lo(ptx::smem_u32(xw_smem));
       int s = 0;
       uint32_t ph = 0;
@@ -323,20 +333,24 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
 #define SVSK_ISSUE4(dcol, alo, blo, acc0)                                                                          \
   do {                                                                                                             \
     const int sn = (s + 1 == a.nentries) ? 0 : s + 1;                                                              \
-    ready = ptx::umma2_bf16_x4_probe(tmem + (dcol), alo, blo, idesc, acc0, 4, &bars->full[sn], sn ? ph : ph ^ 1);  \
+    ready = ptx::umma2_bf16_x4_probe(tmem + tb + (dcol), alo, blo, idesc, acc0, 4, &bars->full[sn], sn ? ph : ph ^ 1);  \
     ptx::umma_commit2_mc(&bars->empty[s], empty_mask);                                                                      \
     SVSK_NEXT_ENTRY();                                                                                             \
   } while (0)
       for (int l = 0; l < L; ++l) {
         const uint32_t pl = (uint32_t)l & 1u, pp = pl ^ 1u;
         const int d = a.dilation[l];
+        const uint32_t tb = a.pingpong ? pl * 256u : 0u;  // TMEM column base of this layer's accumulator block(s)
         // ---- centre tap, block 0
         if (l == 0) {
           ptx::mbar_wait(&bars->xw_full, 0);
         } else {
           ptx::mbar_wait(&bars->xc_ready, pp);      // centre rows rewritten in place by the previous layer's epilogue
           if (l == 2) SVSK_STAMP(27);
-          ptx::mbar_wait(&bars->d2_drained[0], pp); // and the first 256 TMEM columns read out
+          // and the accumulator block read out: by the previous layer — or, alternating halves, by the one before it
+          // (barrier pl completes once every two layers)
+          if (!a.pingpong) ptx::mbar_wait(&bars->d2_drained[0], pp);
+          else if (l >= 2) ptx::mbar_wait(&bars->d2_drained[pl], (uint32_t)((l - 2) >> 1) & 1u);
         }
         ptx::tc_fence_after();
         if (l == 1) SVSK_STAMP(2);
@@ -362,11 +376,11 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         }
         // ---- conditioner k-blocks out of the (future) G buffer, all output blocks per tile
         for (int hb = 0; hb < HB; ++hb) {
-          ptx::mbar_wait(&bars->cd_full[hb], pl);
+          if (l == 0 || !a.cond_resident) ptx::mbar_wait(&bars->cd_full[hb], pl);
           if (hb == 0 && l != 0 && NB > 1) ptx::mbar_wait(&bars->d2_drained[1], pp);
           ptx::tc_fence_after();
           if (l == 1 && hb == 0) SVSK_STAMP(4);
-          const uint32_t a_lo = g_lo + hb * (kSTile >> 4);
+          const uint32_t a_lo = cond_lo + hb * (kSTile >> 4);
           for (int j = 0; j < NB; ++j) {
             SVSK_WAIT_ENTRY();
             SVSK_ISSUE4(j * 256, a_lo, ring_lo + s * (kSTile >> 4), (j == 0 || hb != 0) ? 1 : 0);
@@ -438,8 +452,10 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         if (l != 0) forward_xw();
         forward_entries(2 * CB);
         for (int hb = 0; hb < HB; ++hb) {
-          ptx::mbar_wait(&bars->cd_full[hb], pl);
-          ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->cd_full[hb]), lead));
+          if (l == 0 || !a.cond_resident) {
+            ptx::mbar_wait(&bars->cd_full[hb], pl);
+            ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->cd_full[hb]), lead));
+          }
           forward_entries(NB);
         }
         forward_entries((NB - 1) * 3 * CB + NB * KB2);
@@ -468,6 +484,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
     for (int l = 0; l < L; ++l) {
       const uint32_t pl = (uint32_t)l & 1u;
       const int d = a.dilation[l];
+      const uint32_t tcol = tmem + tlane + (a.pingpong ? pl * 256u : 0u);   // this thread's lane, this layer's accumulator
       const bool has_l = (t - d) >= 0, has_r = (t + d) < T;
       const bool last = (l == L - 1);
       // per-column biases of this layer -> smem: sb_full = centre + left + right tap terms (an interior frame's sum)
@@ -490,15 +507,15 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         ptx::tc_fence_after();
         if (l == 1 && elected) SVSK_STAMP(20 + 2 * j);   // 20 / 22: gating of block 0 / 1 starts
         uint32_t rgb[2][16], rfb[2][16];
-        ptx::tmem_ld16(tmem + tlane + j * 256 + 16 * sub, rgb[0]);
-        ptx::tmem_ld16(tmem + tlane + j * 256 + 128 + 16 * sub, rfb[0]);
+        ptx::tmem_ld16(tcol + j * 256 + 16 * sub, rgb[0]);
+        ptx::tmem_ld16(tcol + j * 256 + 128 + 16 * sub, rfb[0]);
 #pragma unroll
         for (int i = 0; i < 8 / kSW; ++i) {
           const int c0 = 16 * (kSW * i + sub);
           ptx::tmem_ld_wait();
           if (i + 1 < 8 / kSW) {  // next chunk's TMEM loads fly while this chunk is gated
-            ptx::tmem_ld16(tmem + tlane + j * 256 + c0 + 16 * kSW, rgb[(i + 1) & 1]);
-            ptx::tmem_ld16(tmem + tlane + j * 256 + 128 + c0 + 16 * kSW, rfb[(i + 1) & 1]);
+            ptx::tmem_ld16(tcol + j * 256 + c0 + 16 * kSW, rgb[(i + 1) & 1]);
+            ptx::tmem_ld16(tcol + j * 256 + 128 + c0 + 16 * kSW, rfb[(i + 1) & 1]);
           }
           const uint32_t* rg = rgb[i & 1];
           const uint32_t* rf = rfb[i & 1];
@@ -551,14 +568,14 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
           if (l == 1 && warp == 4 && lane == 0) SVSK_STAMP(28);               // an edge thread (row 0) starts its residual part
           const int n_res = res_cols / (16 * kSW);
           uint32_t rr[2][16];
-          ptx::tmem_ld16(tmem + tlane + j * 256 + 16 * sub, rr[0]);
+          ptx::tmem_ld16(tcol + j * 256 + 16 * sub, rr[0]);
 #pragma unroll
           for (int i = 0; i < 16 / kSW; ++i) {
             if (i < n_res) {
               const int c0 = 16 * (kSW * i + sub);
               const int oc0 = j * 256 + c0;  // output channel = residual channel
               ptx::tmem_ld_wait();
-              if (i + 1 < n_res) ptx::tmem_ld16(tmem + tlane + j * 256 + c0 + 16 * kSW, rr[(i + 1) & 1]);  // flies during the maths
+              if (i + 1 < n_res) ptx::tmem_ld16(tcol + j * 256 + c0 + 16 * kSW, rr[(i + 1) & 1]);  // flies during the maths
               const uint32_t* r = rr[i & 1];
               uint8_t* xt = xw_smem + (oc0 >> 6) * kSWinBytes + kSHalo * 128;  // centre rows of the window tile
               const uint32_t ch16 = (uint32_t)((oc0 & 63) >> 3);
@@ -590,7 +607,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
             ptx::fence_proxy_async_smem();
             ptx::mbar_arrive_cluster(xc_leader);  // first: the next layer's centre tap is waiting for this
             ptx::mbar_arrive(&bars->xe_ready);
-            if (res_cols == 256) {
+            if (res_cols == 256 && !a.pingpong) {
               // ... and for this: the block holds no skip columns, so this thread has read all of it out of TMEM.  Said
               // BEFORE the edge threads' cluster-scope fence below (MEMBAR.ALL.GPU + L1 invalidate, ~3 k cycles in 4 of the
               // 8 epilogue warps), during which the next layer's first MMA used to wait on a condition long true:
@@ -621,8 +638,8 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
           for (int k = sub; k < n_skip; k += kSW, m = (m + 1) % kSlots) {
             const int c0 = res_cols + 32 * k;
             uint32_t r0[16], r1[16];
-            ptx::tmem_ld16(tmem + tlane + j * 256 + c0, r0);
-            ptx::tmem_ld16(tmem + tlane + j * 256 + c0 + 16, r1);
+            ptx::tmem_ld16(tcol + j * 256 + c0, r0);
+            ptx::tmem_ld16(tcol + j * 256 + c0 + 16, r1);
             if (k >= sub + kSW * kSlots) {  // the slot is used again: its previous TMA must have read it
               if (lane == 0) {
                 if (kSlots == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -659,7 +676,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         }
         if (!drained_said) {
           ptx::tc_fence_before();
-          ptx::mbar_arrive_cluster(dr_leader + (uint32_t)j * 8u);
+          ptx::mbar_arrive_cluster(dr_leader + (a.pingpong ? pl : (uint32_t)j) * 8u);
         }
       }
       // the bias arrays are rewritten at the top of the next layer: every epilogue thread must be done reading them
@@ -680,21 +697,28 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
 
 using namespace svsk;
 
-static int stack_smem(int C, int H, int* nentries_out) {
+static int stack_smem(int C, int H, int* nentries_out, int* cond_resident_out = nullptr) {
   const int CB = C / 64, HB = H / 64;
   int gc_tiles = HB > CB ? HB : CB;
   if (gc_tiles < 4) gc_tiles = 4;
-  const int fixed = CB * kSWinBytes + gc_tiles * kSTile + 4 * 2 * C * (int)sizeof(float) + (int)sizeof(DiffnetStackBarriers) + 1024;
+  int fixed = CB * kSWinBytes + gc_tiles * kSTile + 4 * 2 * C * (int)sizeof(float) + (int)sizeof(DiffnetStackBarriers) + 1024;
+  // C = 128: resident conditioner tiles if that still leaves a ring of 5 (the depth the C = 256 kernel runs with)
+  int resident = 0;
+  if (C == 128 && !getenv("SVSK_STACK_NO_PINGPONG") && (kSSmemLimit - fixed - HB * kSTile) / kSTile >= 5) {
+    resident = 1;
+    fixed += HB * kSTile;
+  }
   int nentries = (kSSmemLimit - fixed) / kSTile;
   if (nentries > kSMaxEntries) nentries = kSMaxEntries;
   *nentries_out = nentries;
+  if (cond_resident_out) *cond_resident_out = resident;
   return fixed + nentries * kSTile;
 }
 
-static int stack_prepare(int C, int H, int* nentries, int* smem_bytes) {
+static int stack_prepare(int C, int H, int* nentries, int* smem_bytes, int* cond_resident = nullptr) {
   SVSK_REQUIRE(C == 128 || C == 256, SVSK_E_ARG, "diffnet_stack_bf16: C=%d (need 128 or 256)", C);
   SVSK_REQUIRE(H > 0 && H % 64 == 0 && H <= 512, SVSK_E_ARG, "diffnet_stack_bf16: H=%d (need a multiple of 64, at most 512)", H);
-  *smem_bytes = stack_smem(C, H, nentries);
+  *smem_bytes = stack_smem(C, H, nentries, cond_resident);
   SVSK_REQUIRE(*nentries >= 3, SVSK_E_ARG, "diffnet_stack_bf16: not enough shared memory");
   int dev = 0;
   cudaGetDevice(&dev);
@@ -785,8 +809,8 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
                "diffnet_stack_bf16: skip32 / edge0 / edge1 must be 16-byte aligned");
   int rc = require_sm100();
   if (rc) return rc;
-  int nentries = 0, smem_bytes = 0;
-  if ((rc = stack_prepare(p.C, p.H, &nentries, &smem_bytes))) return rc;
+  int nentries = 0, smem_bytes = 0, cond_resident = 0;
+  if ((rc = stack_prepare(p.C, p.H, &nentries, &smem_bytes, &cond_resident))) return rc;
 
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[2];
@@ -845,6 +869,8 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
   a.sb_layer_stride = p.stepbias_layer_stride;
   a.init_skip = p.init_skip;
   a.nentries = nentries;
+  a.pingpong = (p.C == 128 && !getenv("SVSK_STACK_NO_PINGPONG")) ? 1 : 0;
+  a.cond_resident = cond_resident;
   a.tiles_per_track = 2 * ceil_div(p.T, 256);
   for (int l = 0; l < kSMaxLayers; ++l) a.dilation[l] = l < p.L ? p.dilation[l] : 1;
   a.dbg = nullptr;
