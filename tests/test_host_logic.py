@@ -204,3 +204,39 @@ def test_pipeline_pair_items_matches_reference_double_loop():
     assert pair_items(ids) == brute
     assert ("alto_song1_seg0", "alto_song1_seg0") in brute and ("solo", "solo") in brute and len(brute) == 3 * 3 + 2 * 2 + 1 + 1
     assert pair_items([]) == []
+
+
+def test_wgrad_splits_choice():
+    """Track groups of a wgrad launch: the largest divisor of B that keeps the grid within about one wave."""
+    from ensemble_svs_with_interactions_b200 import ops
+    assert ops.wgrad_splits(6, 36) == 3          # 108 CTAs; 6 groups would be 216
+    assert ops.wgrad_splits(6, 12) == 6          # 72 CTAs
+    assert ops.wgrad_splits(6, 200) == 1         # already more than a wave
+    assert ops.wgrad_splits(1, 4) == 1
+    assert ops.wgrad_splits(48, 36) == 4         # divisors of 48: 1 2 3 4 6 ...; 4 * 36 = 144 <= 160 < 6 * 36
+
+
+def test_training_indicator_rows():
+    """Rows appended to the wgrad operand: column sums over all / the first d / the last d frames of each track."""
+    from ensemble_svs_with_interactions_b200.diffsinger import training
+    ind = training._indicator_rows(2, 10, 16, 3, torch.device("cpu")).float()
+    assert ind.shape == (2, 16, 16)
+    assert ind[0, 0].tolist() == [1.0] * 10 + [0.0] * 6 and ind[0, 1, :4].tolist() == [1, 1, 1, 0]
+    assert ind[0, 2].nonzero().flatten().tolist() == [7, 8, 9] and float(ind[0, 3:].abs().sum()) == 0   # track 0 owns rows 0..2
+    assert ind[1, 3].sum() == 10 and float(ind[1, :3].abs().sum()) == 0                                 # track 1 owns rows 3..5
+    ones = training._indicator_rows(2, 10, 16, None, torch.device("cpu")).float()
+    assert ones.shape == (2, 16, 16) and ones[:, 0, :10].min() == 1 and float(ones[:, 1:].abs().sum()) == 0
+
+
+def test_reference_root_discovery(tmp_path, monkeypatch):
+    """oracle/ref_shim.py looks for the reference under $SVSK_REFERENCE_ROOT, baseline/_ref (the pip-installed copy that
+    travels to the GPU box), then /root/reference."""
+    import importlib
+    from oracle import ref_shim
+    fake = tmp_path / "ref"
+    (fake / "nnsvs" / "diffsinger").mkdir(parents=True)
+    monkeypatch.setenv("SVSK_REFERENCE_ROOT", str(fake))
+    assert importlib.reload(ref_shim).REFERENCE_ROOT == str(fake)
+    monkeypatch.delenv("SVSK_REFERENCE_ROOT")
+    root = importlib.reload(ref_shim).REFERENCE_ROOT
+    assert root.endswith("baseline/_ref") or root == "/root/reference"
