@@ -2,7 +2,8 @@
 """BASELINE configs[4]: data-parallel DiffNet training step (per rank: 6 x 1000-frame multi-track batch; 48 x 1000 on
 8 GPUs), gradient all-reduce by DistributedDataParallel over NCCL — the reference's own scheme
 (nnsvs/train_util.py:1444-1446, nnsvs/bin/train_acoustic_multitrack.py:358-380: L1 DDPM loss, clip_grad_norm_, AdamW).
-Forward = libsvsk kernels; backward = interim autograd re-statement (see diffsinger/training.py).
+Forward and backward = libsvsk tcgen05 kernels (svsk_seggemm_bf16 / svsk_wgrad_bf16, SURVEY §8(f) row 4, see
+diffsinger/training.py), both captured in CUDA graphs.
 
   python tools/bench_train.py            |  torchrun --nproc-per-node N tools/bench_train.py
 """
