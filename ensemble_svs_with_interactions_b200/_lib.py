@@ -125,6 +125,8 @@ class UsfganBlockParams(C.Structure):
         ("idx_past", C.c_void_p), ("idx_future", C.c_void_p),
         ("B", C.c_int32), ("T", C.c_int32), ("A", C.c_int32),
         ("dilation", C.c_int32), ("adaptive", C.c_int32), ("out_scale", C.c_float), ("out_relu", C.c_int32),
+        ("aux_u", C.c_void_p), ("aux_q", C.c_void_p), ("q_batch_stride", C.c_int64),
+        ("q_ld", C.c_int32), ("q_fpad", C.c_int32), ("hop", C.c_int32), ("reach", C.c_int32),
     ]
 
 
@@ -176,6 +178,9 @@ _SIGNATURES = {
     "svsk_linear_bf16": [C.POINTER(LinearBf16Params), _V],
     "svsk_usfgan_block_bf16": [C.POINTER(UsfganBlockParams), _V],
     "svsk_usfgan_pack_block": [_V, _V, _V, _V, _V, _I, _I, _I, _V],
+    "svsk_usfgan_aux_frames": [_V, _V, _V, _I, _I, _I, _I, _I, _I, _V],
+    "svsk_usfgan_aux_weights": [_V, _V, _I, _I, _I, _V],
+    "svsk_usfgan_frame_base": [_I, _I, _I],
     "svsk_ntc_bf16_to_nct_f32": [_V, _V, _I, _I, _I, _I, _V],
     "svsk_conv1d_bf16": [C.POINTER(Conv1dBf16Params), _V],
     "svsk_conv1d_pack_bf16": [_V, _V, _I, _I, _I, _V],

@@ -18,6 +18,11 @@ struct LinearArgs {
   float* y_f;
   long long N;
   int K, Cout, ldy_b, ldy_f, act, tmem_cols;
+  // transposed bf16 output (svsk_usfgan_aux_frames): row n = (track n / t_rows, frame n % t_rows), column co ->
+  // y_t[track * t_bstride + co * t_ld + frame]
+  __nv_bfloat16* y_t;
+  long long t_bstride;
+  int t_rows, t_ld;
 };
 
 struct __align__(8) LinearBarriers {
@@ -103,6 +108,11 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     ptx::tc_fence_after();
     const bool vec_f = a.y_f && (a.ldy_f % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.y_f) & 15) == 0);
     const bool vec_b = a.y_b && (a.ldy_b % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.y_b) & 15) == 0);
+    __nv_bfloat16* yt = nullptr;
+    if (a.y_t && n < a.N) {
+      const long long trk = n / a.t_rows;
+      yt = a.y_t + trk * a.t_bstride + (n - trk * a.t_rows);
+    }
     for (int c0 = 0; c0 < a.Cout; c0 += 16) {
       uint32_t r[16];
       ptx::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, r);
@@ -110,6 +120,10 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       float v[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = lin_act(__uint_as_float(r[i]) + (a.bias ? a.bias[c0 + i] : 0.f), a.act);
+      if (yt) {  // a warp writes 32 consecutive frames of one output row per store: 64-byte segments
+#pragma unroll
+        for (int i = 0; i < 16; ++i) yt[(size_t)(c0 + i) * a.t_ld] = __float2bfloat16_rn(v[i]);
+      }
       if (n < a.N) {
         if (a.y_f) {
           float* dst = a.y_f + n * a.ldy_f + c0;
@@ -197,7 +211,65 @@ extern "C" int svsk_linear_bf16(const svsk_linear_bf16_params* pp, void* stream)
   a.ldy_f = p.ldy_f;
   a.act = p.act;
   a.tmem_cols = p.Cout <= 32 ? 32 : (p.Cout <= 64 ? 64 : (p.Cout <= 128 ? 128 : 256));
+  a.y_t = nullptr;
+  a.t_bstride = 0;
+  a.t_rows = 1;
+  a.t_ld = 0;
   unsigned grid = (unsigned)((p.N + 127) / 128);
   linear_bf16_kernel<<<grid, 192, smem_bytes, as_stream(stream)>>>(tm_a, tm_w, a);
   return check_launch("linear_bf16");
+}
+
+extern "C" int svsk_usfgan_aux_frames(const void* cin, const void* w, void* q, int B, int Tf, int Ap, int R, int q_ld, int q_fpad,
+                                      void* stream) {
+  SVSK_REQUIRE(cin && w && q, SVSK_E_ARG, "usfgan_aux_frames: null tensor");
+  SVSK_REQUIRE(B > 0 && Tf > 0 && (long long)B * Tf < (1ll << 31), SVSK_E_ARG, "usfgan_aux_frames: B=%d Tf=%d", B, Tf);
+  SVSK_REQUIRE(Ap > 0 && Ap % 8 == 0, SVSK_E_ALIGN, "usfgan_aux_frames: Ap=%d must be a multiple of 8", Ap);
+  SVSK_REQUIRE(R > 0 && R % 16 == 0, SVSK_E_ARG, "usfgan_aux_frames: R=%d must be a multiple of 16", R);
+  SVSK_REQUIRE(q_fpad >= 0 && q_ld >= q_fpad + Tf, SVSK_E_ARG, "usfgan_aux_frames: q_ld=%d < q_fpad + Tf = %d", q_ld, q_fpad + Tf);
+  int rc = require_sm100();
+  if (rc) return rc;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static bool attr_set[64] = {false};
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(linear_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return fail((int)e, "usfgan_aux_frames: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const long long N = (long long)B * Tf;
+  CUtensorMap tm_a;
+  {
+    uint64_t dims[2] = {(uint64_t)Ap, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)Ap * 2};
+    uint32_t box[2] = {64, 128};
+    if ((rc = make_tmap_bf16(&tm_a, cin, 2, dims, str, box))) return rc;
+  }
+  // rows = frames of all tracks, 256 output rows of w (two blocks) per launch, stored transposed: frame index innermost
+  for (int r0 = 0; r0 < R; r0 += 256) {
+    const int cout = R - r0 < 256 ? R - r0 : 256;
+    CUtensorMap tm_w;
+    uint64_t dims[2] = {(uint64_t)Ap, (uint64_t)cout};
+    uint64_t str[1] = {(uint64_t)Ap * 2};
+    uint32_t box[2] = {64, (uint32_t)cout};
+    if ((rc = make_tmap_bf16(&tm_w, static_cast<const __nv_bfloat16*>(w) + (size_t)r0 * Ap, 2, dims, str, box))) return rc;
+    LinearArgs a;
+    a.bias = nullptr;
+    a.y_b = nullptr;
+    a.y_f = nullptr;
+    a.N = N;
+    a.K = Ap;
+    a.Cout = cout;
+    a.ldy_b = a.ldy_f = 0;
+    a.act = SVSK_ACT_NONE;
+    a.tmem_cols = cout <= 32 ? 32 : (cout <= 64 ? 64 : (cout <= 128 ? 128 : 256));
+    a.y_t = static_cast<__nv_bfloat16*>(q) + (size_t)r0 * q_ld + q_fpad;
+    a.t_bstride = (long long)R * q_ld;
+    a.t_rows = Tf;
+    a.t_ld = q_ld;
+    const int smem_bytes = kLinStages * (kLinABytes + cout * 128) + (int)sizeof(LinearBarriers) + 1024;
+    linear_bf16_kernel<<<(unsigned)((N + 127) / 128), 192, smem_bytes, as_stream(stream)>>>(tm_a, tm_w, a);
+    if ((rc = check_launch("usfgan_aux_frames"))) return rc;
+  }
+  return 0;
 }

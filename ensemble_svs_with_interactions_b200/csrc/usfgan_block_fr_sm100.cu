@@ -1,0 +1,521 @@
+// Fused uSFGAN / QPPWG residual block with the aux projection taken at FRAME rate (usfgan_fr.cuh) — the variant
+// svsk_usfgan_block_bf16 runs when the caller passes aux_u / aux_q.  Same arithmetic per block as usfgan_block_sm100.cu
+// (nnsvs/usfgan/layers/residual_block.py:123-157, 198-234; nnsvs/usfgan/utils/index.py:12-54):
+//
+//   D1[t][128] = [x(tap0) ; x(t) ; x(tap2)] . W1p^T  +  U[t][16] . Q[fbase .. fbase+15][128]      K = 192 + 16
+//   z = tanh(D1[:, :64] + b) * sigmoid(D1[:, 64:] + b)
+//   D2[t][64]  = z . Wout^T ;   x'(t) = (D2 + bout + x(t)) * sqrt(1/2)
+//
+// What differs from the sample-rate kernel, and why (profiles/r01n_ablate_usfgan_noprof.log: the MMA-issuing thread, the
+// epilogue chain and the data skeleton were all within 3.1-4.9 k cycles per tile):
+//   * no sample-rate aux stream: 256 instead of 416 DRAM bytes per sample, 13 instead of 17 MMAs per tile, the block's
+//     resident weights shrink from 88 to 56 KB;
+//   * the freed shared memory holds TWO whole-tile operand stages (4 x 16 KB: tap0, centre, tap2, aux) with ONE full and
+//     ONE empty barrier per tile, so the MMA thread does 2 barrier waits and 2 commits per tile instead of 5 + 6 — a wait
+//     whose result is needed at once stalls that thread ~160 cycles even when the phase completed long ago;
+//   * the residual add runs on the tensor cores: the GEMM1 thread also issues D2 = X_centre . I (four N = 64 MMAs against
+//     a resident 64 x 64 identity tile, exact in the fp32 accumulator) and GEMM2 accumulates onto it — the epilogue's
+//     per-row residual loads are gone.  Thread = row epilogue accesses to GLOBAL memory touch 32 different 128-byte
+//     lines per warp instruction; ncu showed the LSU data pipe at 78 % of its peak with them (residual loads + direct
+//     stores: 3.4 -> 2.7 k cycles per tile when either was ablated), while TMA traffic does not pass through that pipe;
+//   * two epilogue groups of 8 warps, group p owning the tiles n with n & 1 == p together with D1[p], G[p] and two D2
+//     accumulators: while one group waits for its GEMM2 or its TMA store the other one gates.
+//
+//   warp 0      TMA producer: centre tap, and both side taps of interior fixed-block tiles
+//   warp 1      GEMM1 issuer (tcgen05.mma cta_group::1, M=128, N=128; + the residual's identity MMAs) + TMEM owner
+//   warp 6      GEMM2 issuer (N=64)
+//   warps 2-5   gather producers (thread = row): the aux operands U (rows = samples) and Q (rows = gate channels) of
+//               every tile, and the side taps of adaptive blocks / reflected boundary tiles, by 16-byte cp.async into the
+//               swizzled tiles; completion through cp.async.mbarrier.arrive.noinc on the tile's full barrier
+//   warps 7-22  epilogue: two groups of 8 warps (thread = sample, two warps per TMEM lane quarter alternating 16-column
+//               chunks); gate -> G[p] (bf16, swizzled smem) -> GEMM2 -> output rows into the same buffer -> one TMA store
+//               per lane quarter
+// TMEM: two D1 (2 x 128 columns, one per epilogue group) and four D2 (4 x 64, two per group: the residual's identity
+// MMAs of the group's next tile are issued while the current one is still being read) = 512 columns.
+#include <cuda_bf16.h>
+#include <cstdlib>
+
+#include "sm100_ptx.cuh"
+#include "svsk_common.cuh"
+#include "tma_util.cuh"
+#include "usfgan_fr.cuh"
+
+namespace svsk {
+
+constexpr int kFTile = 128 * 128;     // 128 rows x 64 bf16
+constexpr int kFStage = 4 * kFTile;   // tap0, centre, tap2, aux
+constexpr int kFThreads = 736;  // producer, GEMM1, 4 gather, GEMM2, 2 x 8 epilogue warps
+
+struct UsfganFrArgs {
+  const __nv_bfloat16* xb_in;
+  __nv_bfloat16* xb_out;
+  const float* bias1;
+  const float* bout;
+  const int32_t* idx_past;
+  const int32_t* idx_future;
+  const __nv_bfloat16* aux_u;  // [ceil128(T)][16]
+  const __nv_bfloat16* aux_q;  // this block's 128 rows of track 0; row n of track b at aux_q + b * q_batch_stride + n * q_ld
+  long long q_batch_stride;
+  int q_ld, q_fpad, hop, reach;
+  int B, T, dilation, adaptive, tiles_per_row, total_tiles;
+  float out_scale;
+  int out_relu;
+  unsigned long long* dbg;  // profiling only: [grid][16] accumulated clock64 deltas per role
+  int dbg_flags;            // profiling only: 1 = skip epilogue math/stores, 2 = no MUFU, 4 = skip MMAs, 8 = no global
+                            // stores, 16 = no TMEM loads
+};
+
+struct __align__(8) UsfganFrBarriers {
+  uint64_t full[2];   // 1 TMA arrival (+ tx bytes) + 128 gather arrivals per tile
+  uint64_t empty[2];  // GEMM1 of the tile has read the stage
+  uint64_t d1_full[2], g_full[2], d2_full[4];
+  uint64_t w_full;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void fr_cp_async_16(void* dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ptx::smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void fr_cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ptx::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool fr_tile_needs_gather(int t0, int T, int d, int adaptive) {
+  if (adaptive) return true;
+  const int last = min(t0 + 127, T - 1);
+  return (t0 - d < 0) || (last + d >= T);  // a reflected tap: rows are not a shifted copy any more
+}
+
+template <bool kProf>
+__global__ void __launch_bounds__(kFThreads, 1)
+usfgan_block_fr_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
+                       const __grid_constant__ CUtensorMap tm_wout, const __grid_constant__ CUtensorMap tm_xout,
+                       const UsfganFrArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w1_s = smem;                       // 3 tiles of [128 rows][64]
+  uint8_t* wout_s = w1_s + 3 * kFTile;        // [64 rows][64] = 8 KB
+  uint8_t* stages = wout_s + 8192;            // 2 x {tap0, centre, tap2, aux}
+  uint8_t* gbuf = stages + 2 * kFStage;       // 2 x 16 KB: G, then the output rows, of the tile of epilogue group p
+  uint8_t* ident_s = gbuf + 2 * kFTile;       // [64 rows][64] identity, 8 KB
+  float* bias_s = reinterpret_cast<float*>(ident_s + 8192);  // [128] gate biases, [64] output biases
+  UsfganFrBarriers* bars = reinterpret_cast<UsfganFrBarriers*>(bias_s + 192);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = a.T;
+  const int flags = kProf ? a.dbg_flags : 0;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_x);
+    ptx::prefetch_tmap(&tm_w1);
+    ptx::prefetch_tmap(&tm_wout);
+    ptx::prefetch_tmap(&tm_xout);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bars->full[i], 129);
+      ptx::mbar_init(&bars->empty[i], 1);
+      ptx::mbar_init(&bars->d1_full[i], 1);
+      ptx::mbar_init(&bars->g_full[i], 256);
+    }
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(&bars->d2_full[i], 1);
+    ptx::mbar_init(&bars->w_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&bars->tmem_base, 512);
+    ptx::tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < 192; i += kFThreads) bias_s[i] = i < 128 ? a.bias1[i] : a.bout[i - 128];
+  // identity tile in the swizzled K-major layout: row n holds 1.0 at K = n (chunk n >> 3 of the row, element n & 7)
+  for (int i = threadIdx.x; i < 8192 / 16; i += kFThreads) {
+    const uint32_t row = (uint32_t)i >> 3, pos = (uint32_t)i & 7u;           // physical 16-byte chunk `pos` of row `row`
+    const uint32_t chunk = pos ^ (row & 7u);                                  // logical chunk stored there
+    const uint32_t one = (chunk == (row >> 3)) ? (0x3f80u << (16 * (row & 1u))) : 0u;
+    const uint32_t w = (row & 7u) >> 1;
+    ptx::st_shared_v4(ident_s + i * 16, w == 0 ? one : 0u, w == 1 ? one : 0u, w == 2 ? one : 0u, w == 3 ? one : 0u);
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(&bars->w_full, 3 * kFTile + 8192);
+      for (int kb = 0; kb < 3; ++kb) ptx::tma_load_2d(w1_s + kb * kFTile, &tm_w1, &bars->w_full, kb * 64, 0);
+      ptx::tma_load_2d(wout_s, &tm_wout, &bars->w_full, 0, 0);
+      long long acc_p = 0;
+      int n = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++n) {
+        const int b = tile / a.tiles_per_row, t0 = (tile - b * a.tiles_per_row) * 128;
+        const bool gather = fr_tile_needs_gather(t0, T, a.dilation, a.adaptive);
+        const int st = n & 1;
+        const long long c_0 = (kProf ? clock64() : 0ll);
+        ptx::mbar_wait(&bars->empty[st], ((n >> 1) & 1) ^ 1);
+        acc_p += (kProf ? clock64() : 0ll) - c_0;
+        uint8_t* slot = stages + st * kFStage;
+        ptx::mbar_arrive_expect_tx(&bars->full[st], gather ? kFTile : 3 * kFTile);
+        ptx::tma_load_3d(slot + kFTile, &tm_x, &bars->full[st], 0, t0, b);
+        if (!gather) {
+          ptx::tma_load_3d(slot, &tm_x, &bars->full[st], 0, t0 - a.dilation, b);
+          ptx::tma_load_3d(slot + 2 * kFTile, &tm_x, &bars->full[st], 0, t0 + a.dilation, b);
+        }
+      }
+      if (kProf && a.dbg) a.dbg[blockIdx.x * 16 + 0] = acc_p;  // producer: cycles waiting for a free stage
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ GEMM1 issuer
+    if (lane == 0) {
+      const uint32_t idesc1 = ptx::umma_idesc_bf16_f32(128, 128);
+      ptx::mbar_wait(&bars->w_full, 0);
+      ptx::tc_fence_after();
+      const uint32_t idesc2 = ptx::umma_idesc_bf16_f32(128, 64);
+      const uint32_t st_lo = ptx::umma_desc_lo(ptx::smem_u32(stages)), w1_lo = ptx::umma_desc_lo(ptx::smem_u32(w1_s));
+      const uint32_t id_lo = ptx::umma_desc_lo(ptx::smem_u32(ident_s));
+      constexpr uint32_t kT16 = kFTile >> 4;
+      // The barriers of tile n+1 are probed while the MMAs of tile n are issued (ptx::umma_bf16_x4_probe): no phase can
+      // complete twice in between, because the stage's next producer waits for this thread's commit.
+      bool full_ready = false, g_ready = false;
+      long long acc_full = 0, acc_g = 0, acc_mma = 0, acc_total = (kProf ? clock64() : 0ll);
+      int n = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++n) {
+        const int p = n & 1;
+        long long c_0 = (kProf ? clock64() : 0ll);
+        // D1[p] is free once the epilogue has gated tile n - 2 out of it
+        if (n >= 2 && !g_ready) ptx::mbar_wait(&bars->g_full[p], ((n - 2) >> 1) & 1);
+        long long c_1 = (kProf ? clock64() : 0ll);
+        acc_g += c_1 - c_0;
+        if (!full_ready) ptx::mbar_wait(&bars->full[p], (n >> 1) & 1);
+        ptx::fence_proxy_async_smem();  // the gather warps' cp.async writes -> tensor-core (async proxy) reads
+        ptx::tc_fence_after();
+        c_0 = (kProf ? clock64() : 0ll);
+        acc_full += c_0 - c_1;
+        const uint32_t s_lo = st_lo + p * (kFStage >> 4);
+        const uint32_t d1 = tmem + p * 128;
+        uint64_t* nfull = &bars->full[p ^ 1];
+        const uint32_t nfull_par = ((n + 1) >> 1) & 1;
+        uint64_t* ng = &bars->g_full[p ^ 1];
+        const uint32_t ng_par = ((n - 1) >> 1) & 1;  // meaningful for n >= 1
+        if (!(flags & 4)) {
+          (void)ptx::umma_bf16_x4_probe(d1, s_lo, w1_lo, idesc1, 0, 4, nfull, nfull_par);
+          const bool r1 = ptx::umma_bf16_x4_probe(d1, s_lo + kT16, w1_lo + kT16, idesc1, 1, 4, ng, ng_par);
+          const bool r2 = ptx::umma_bf16_x4_probe(d1, s_lo + 2 * kT16, w1_lo + 2 * kT16, idesc1, 1, 4, nfull, nfull_par);
+          // aux: A = U (K columns 0..15 of the aux tile's rows), B = Q (K columns 16..31 of the same rows)
+          ptx::umma_bf16_lo(d1, s_lo + 3 * kT16, s_lo + 3 * kT16 + 2, idesc1, 1);
+          // residual: D2 = X_centre . I, GEMM2 accumulates onto it.  This D2 accumulator was last read by the residual
+          // epilogue of tile n - 4, which its group finished before it gated tile n - 2 (waited for above).
+          const uint32_t d2 = tmem + 256 + (p * 2 + ((n >> 1) & 1)) * 64;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) ptx::umma_bf16_lo(d2, s_lo + kT16 + 2 * k4, id_lo + 2 * k4, idesc2, k4 != 0);
+          ptx::umma_commit(&bars->empty[p]);
+          ptx::umma_commit(&bars->d1_full[p]);
+          full_ready = r2;
+          g_ready = r1 && n >= 1;
+        } else {
+          ptx::mbar_arrive(&bars->empty[p]);
+          ptx::mbar_arrive(&bars->d1_full[p]);
+          full_ready = g_ready = false;
+        }
+        acc_mma += (kProf ? clock64() : 0ll) - c_0;
+      }
+      if (kProf && a.dbg) {
+        a.dbg[blockIdx.x * 16 + 1] = acc_full;  // GEMM1 thread: waiting for operands
+        a.dbg[blockIdx.x * 16 + 2] = acc_g;     // GEMM1 thread: waiting for the accumulator to be gated out
+        a.dbg[blockIdx.x * 16 + 3] = (kProf ? clock64() : 0ll) - acc_total;
+        a.dbg[blockIdx.x * 16 + 4] = n;
+        a.dbg[blockIdx.x * 16 + 13] = acc_mma;  // GEMM1 thread: issue + commits
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------ gather producers (thread = row of the tiles)
+    const int r = threadIdx.x - 64;
+    // This row's two tap indices are requested one tile ahead, so that their (L2) latency is off the stage's chain.
+    auto load_idx = [&](int tile, int& ip_, int& ifu_) {
+      ip_ = ifu_ = -1;
+      if (a.adaptive && tile < a.total_tiles) {
+        const int b_ = tile / a.tiles_per_row, t_ = (tile - b_ * a.tiles_per_row) * 128 + r;
+        if (t_ < T) {
+          ip_ = __ldg(a.idx_past + (size_t)b_ * T + t_);
+          ifu_ = __ldg(a.idx_future + (size_t)b_ * T + t_);
+        }
+      }
+    };
+    int ip_next, ifu_next;
+    load_idx(blockIdx.x, ip_next, ifu_next);
+    long long acc_w = 0, acc_i = 0;
+    int n = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++n) {
+      const int b = tile / a.tiles_per_row, t0 = (tile - b * a.tiles_per_row) * 128;
+      const bool gather = fr_tile_needs_gather(t0, T, a.dilation, a.adaptive);
+      const int t = t0 + r;
+      const int ip = ip_next, ifu = ifu_next;
+      load_idx(tile + gridDim.x, ip_next, ifu_next);
+      const int st = n & 1;
+      long long c_0 = (kProf ? clock64() : 0ll);
+      ptx::mbar_wait_warp(&bars->empty[st], ((n >> 1) & 1) ^ 1);
+      long long c_1 = (kProf ? clock64() : 0ll);
+      acc_w += c_1 - c_0;
+      uint8_t* slot = stages + st * kFStage;
+      {
+        uint8_t* aux_s = slot + 3 * kFTile;
+        const uint8_t* us = reinterpret_cast<const uint8_t*>(a.aux_u + (size_t)t * 16);
+        const int fb = usfgan_frame_base(t0, a.reach, a.hop);
+        const uint8_t* qs = reinterpret_cast<const uint8_t*>(a.aux_q + (size_t)b * a.q_batch_stride + (size_t)r * a.q_ld +
+                                                             (a.q_fpad + fb));
+        fr_cp_async_16(aux_s + ptx::sw128_offset((uint32_t)r, 0u), us, 16u);
+        fr_cp_async_16(aux_s + ptx::sw128_offset((uint32_t)r, 1u), us + 16, 16u);
+        fr_cp_async_16(aux_s + ptx::sw128_offset((uint32_t)r, 2u), qs, 16u);
+        fr_cp_async_16(aux_s + ptx::sw128_offset((uint32_t)r, 3u), qs + 16, 16u);
+      }
+      if (gather) {
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          int src = -1;
+          if (t < T) {
+            if (a.adaptive) {
+              src = side == 0 ? ip : ifu;
+            } else {
+              src = t + (side == 0 ? -a.dilation : a.dilation);
+              if (src < 0) src = -src;
+              if (src >= T) src = 2 * (T - 1) - src;
+            }
+          }
+          const bool ok = src >= 0 && src < T;
+          const uint8_t* g = reinterpret_cast<const uint8_t*>(a.xb_in + ((size_t)b * T + (ok ? src : 0)) * 64);
+          uint8_t* dst = slot + side * 2 * kFTile;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            fr_cp_async_16(dst + ptx::sw128_offset((uint32_t)r, (uint32_t)c), g + c * 16, ok ? 16u : 0u);
+        }
+      }
+      fr_cp_async_arrive_noinc(&bars->full[st]);
+      acc_i += (kProf ? clock64() : 0ll) - c_1;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (kProf && a.dbg && r == 0) {
+      a.dbg[blockIdx.x * 16 + 14] = acc_w;  // gather: waiting for a free stage
+      a.dbg[blockIdx.x * 16 + 15] = acc_i;  // gather: issuing copies
+    }
+  } else if (warp == 6) {
+    // ------------------------------------------------------------------ GEMM2 issuer: D2 += G . Wout^T per tile
+    if (lane == 0) {
+      const uint32_t idesc2 = ptx::umma_idesc_bf16_f32(128, 64);
+      ptx::mbar_wait(&bars->w_full, 0);
+      ptx::tc_fence_after();
+      const uint32_t wo_lo = ptx::umma_desc_lo(ptx::smem_u32(wout_s)), g_lo = ptx::umma_desc_lo(ptx::smem_u32(gbuf));
+      int m = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++m) {
+        const int p = m & 1, j = p * 2 + ((m >> 1) & 1);  // D2 accumulator: two per epilogue group, alternating
+        ptx::mbar_wait(&bars->g_full[p], (m >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t gl = g_lo + p * (kFTile >> 4);
+        if (!(flags & 4)) {
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) ptx::umma_bf16_lo(tmem + 256 + j * 64, gl + 2 * k4, wo_lo + 2 * k4, idesc2, 1);
+          ptx::umma_commit(&bars->d2_full[j]);
+        } else {
+          ptx::mbar_arrive(&bars->d2_full[j]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: two groups of 8 warps; group p owns the
+    // tiles n with n & 1 == p and with them D1[p], G[p] and the D2 pair 2p, 2p+1 — the groups share no buffer.
+    // Thread = one sample, half the columns (two warps per TMEM lane quarter alternating 16-column chunks).
+    const int e = warp - 7;
+    const int p = e >> 3;
+    const int sub = (e >> 2) & 1;  // 0: 16-column chunks 0 and 2, 1: chunks 1 and 3
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t tlane = (uint32_t)(q * 32) << 16;
+    const bool elected = ((e & 7) == 0 && lane == 0);
+    const bool qlead = (sub == 0 && lane == 0);  // issues the TMA stores of this lane quarter's 32 rows
+    const uint32_t qbar = 1 + p * 4 + q;         // named barrier of the quarter's two warps
+    const int my_tiles = a.total_tiles > (int)blockIdx.x ? (a.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int own = my_tiles > p ? (my_tiles - 1 - p) / 2 + 1 : 0;  // tiles of this group
+    long long acc_d1 = 0, acc_gate = 0, acc_d2 = 0, acc_e2 = 0;
+    uint8_t* gb = gbuf + p * kFTile;
+    for (int k = 0; k < own; ++k) {
+      const int n = p + 2 * k;
+      const int tile = blockIdx.x + n * gridDim.x;
+      const int b = tile / a.tiles_per_row, t0 = (tile - b * a.tiles_per_row) * 128;
+      long long c_0 = (kProf ? clock64() : 0ll);
+      ptx::mbar_wait_warp(&bars->d1_full[p], k & 1);
+      ptx::tc_fence_after();
+      acc_d1 += (kProf ? clock64() : 0ll) - c_0;
+      c_0 = (kProf ? clock64() : 0ll);
+      if (k >= 1) {  // this quarter's rows of G[p] held the previous output tile: its TMA store must have read them
+        if (qlead) ptx::bulk_wait_read_all();
+        ptx::named_bar_sync(qbar, 64);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (flags & 1) break;
+        const int c0 = 16 * (2 * i + sub);
+        uint32_t ra[16], rb[16];
+        if (!(flags & 16)) {
+          ptx::tmem_ld16(tmem + tlane + p * 128 + c0, ra);
+          ptx::tmem_ld16(tmem + tlane + p * 128 + 64 + c0, rb);
+          ptx::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ra[j] = rb[j] = 0x3dcccccdu + j;
+        }
+        uint32_t o[8];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const uint4 ba = ptx::ld_shared_v4(bias_s + c0 + 4 * v), bb = ptx::ld_shared_v4(bias_s + 64 + c0 + 4 * v);
+          const float fa[4] = {__uint_as_float(ba.x), __uint_as_float(ba.y), __uint_as_float(ba.z), __uint_as_float(ba.w)};
+          const float fb[4] = {__uint_as_float(bb.x), __uint_as_float(bb.y), __uint_as_float(bb.z), __uint_as_float(bb.w)};
+          float z[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float ya = __uint_as_float(ra[4 * v + j]) + fa[j], yb = __uint_as_float(rb[4 * v + j]) + fb[j];
+            z[j] = (flags & 2) ? ya * fmaf(yb, 0.25f, 0.5f) : ptx::tanh_approx(ya) * ptx::sigmoid_approx(yb);
+          }
+          o[2 * v] = ptx::pack_bf16(z[0], z[1]);
+          o[2 * v + 1] = ptx::pack_bf16(z[2], z[3]);
+        }
+        ptx::st_shared_v4(gb + ptx::sw128_offset((uint32_t)row, (uint32_t)(c0 >> 3)), o[0], o[1], o[2], o[3]);
+        ptx::st_shared_v4(gb + ptx::sw128_offset((uint32_t)row, (uint32_t)(c0 >> 3) + 1), o[4], o[5], o[6], o[7]);
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&bars->g_full[p]);
+      acc_gate += (kProf ? clock64() : 0ll) - c_0;
+      c_0 = (kProf ? clock64() : 0ll);
+      const int j2 = p * 2 + (k & 1);
+      ptx::mbar_wait_warp(&bars->d2_full[j2], (k >> 1) & 1);  // D2 = x + G . Wout^T is there, GEMM2 has read G[p]
+      ptx::tc_fence_after();
+      acc_d2 += (kProf ? clock64() : 0ll) - c_0;
+      c_0 = (kProf ? clock64() : 0ll);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (flags & 1) break;
+        const int c0 = 16 * (2 * i + sub);
+        uint32_t rd[16];
+        if (!(flags & 16)) {
+          ptx::tmem_ld16(tmem + tlane + 256 + j2 * 64 + c0, rd);
+          ptx::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) rd[j] = 0x3dcccccdu + j;
+        }
+        uint32_t o[8];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const uint4 bo = ptx::ld_shared_v4(bias_s + 128 + c0 + 4 * v);
+          const float fo[4] = {__uint_as_float(bo.x), __uint_as_float(bo.y), __uint_as_float(bo.z), __uint_as_float(bo.w)};
+          float y[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            y[j] = (__uint_as_float(rd[4 * v + j]) + fo[j]) * a.out_scale;
+            if (a.out_relu) y[j] = fmaxf(y[j], 0.f);
+          }
+          o[2 * v] = ptx::pack_bf16(y[0], y[1]);
+          o[2 * v + 1] = ptx::pack_bf16(y[2], y[3]);
+        }
+        ptx::st_shared_v4(gb + ptx::sw128_offset((uint32_t)row, (uint32_t)(c0 >> 3)), o[0], o[1], o[2], o[3]);
+        ptx::st_shared_v4(gb + ptx::sw128_offset((uint32_t)row, (uint32_t)(c0 >> 3) + 1), o[4], o[5], o[6], o[7]);
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      // each TMEM lane quarter (two warps, 32 rows of the tile) stores its own rows
+      ptx::named_bar_sync(qbar, 64);
+      if (qlead && !(flags & 8)) {
+        ptx::tma_store_3d(&tm_xout, gb + q * 4096, 0, t0 + q * 32, b);
+        ptx::bulk_commit_group();
+      }
+      acc_e2 += (kProf ? clock64() : 0ll) - c_0;
+    }
+    if (qlead) ptx::bulk_wait_read_all();
+    if (kProf && a.dbg && elected) {  // slots 5..8 hold group 0, 9..12 group 1
+      a.dbg[blockIdx.x * 16 + 5 + 4 * p + 0] = acc_d1;    // epilogue: waiting for D1
+      a.dbg[blockIdx.x * 16 + 5 + 4 * p + 1] = acc_gate;  // epilogue: store-read wait + gating + G stores + arrive
+      a.dbg[blockIdx.x * 16 + 5 + 4 * p + 2] = acc_d2;    // epilogue: waiting for D2
+      a.dbg[blockIdx.x * 16 + 5 + 4 * p + 3] = acc_e2;    // epilogue: output maths + staging + TMA store issue
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem, 512);
+}
+
+// Called by svsk_usfgan_block_bf16 (usfgan_block_sm100.cu) after the common argument checks.
+int usfgan_block_fr_launch(const svsk_usfgan_block_params& p, void* stream) {
+  SVSK_REQUIRE(p.aux_u && p.aux_q, SVSK_E_ARG, "usfgan_block_bf16: frame-rate aux needs both aux_u and aux_q");
+  SVSK_REQUIRE(p.hop >= 1 && p.reach >= 0 && (127 + 2 * (long long)p.reach) / p.hop <= 7, SVSK_E_ARG,
+               "usfgan_block_bf16: a 128-sample tile must reach at most 8 frames (hop=%d reach=%d)", p.hop, p.reach);
+  SVSK_REQUIRE(p.q_ld > 0 && p.q_ld % 8 == 0 && p.q_fpad >= 0 && p.q_fpad % 8 == 0 && p.q_batch_stride % 8 == 0 &&
+                   (reinterpret_cast<uintptr_t>(p.aux_q) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.aux_u) & 15) == 0,
+               SVSK_E_ALIGN, "usfgan_block_bf16: aux_q rows / aux_u must be 16-byte aligned (q_ld=%d q_fpad=%d)", p.q_ld, p.q_fpad);
+  const int tiles_per_row = (p.T + 127) / 128;
+  const int fb_first = usfgan_frame_base(0, p.reach, p.hop), fb_last = usfgan_frame_base((tiles_per_row - 1) * 128, p.reach, p.hop);
+  SVSK_REQUIRE(p.q_fpad + fb_first >= 0 && p.q_fpad + fb_last + 16 <= p.q_ld, SVSK_E_ARG,
+               "usfgan_block_bf16: aux_q rows hold columns 0..%d, the tiles read %d..%d", p.q_ld - 1, p.q_fpad + fb_first,
+               p.q_fpad + fb_last + 15);
+  int rc;
+  CUtensorMap tm_x, tm_w1, tm_wout, tm_xout;
+  {
+    uint64_t dims[3] = {64, (uint64_t)p.T, (uint64_t)p.B};
+    uint64_t str[2] = {128, (uint64_t)p.T * 128};
+    uint32_t box[3] = {64, 128, 1};
+    uint32_t box_q[3] = {64, 32, 1};  // stores go out per TMEM lane quarter: 32 rows
+    if ((rc = make_tmap_bf16(&tm_x, p.xb_in, 3, dims, str, box))) return rc;
+    if ((rc = make_tmap_bf16(&tm_xout, p.xb_out, 3, dims, str, box_q))) return rc;
+  }
+  {
+    uint64_t dims[2] = {192, 128};
+    uint64_t str[1] = {192 * 2};
+    uint32_t box[2] = {64, 128};
+    if ((rc = make_tmap_bf16(&tm_w1, p.w1p, 2, dims, str, box))) return rc;
+  }
+  {
+    uint64_t dims[2] = {64, 64};
+    uint64_t str[1] = {128};
+    uint32_t box[2] = {64, 64};
+    if ((rc = make_tmap_bf16(&tm_wout, p.woutp, 2, dims, str, box))) return rc;
+  }
+  const int smem_bytes = 3 * kFTile + 8192 + 2 * kFStage + 2 * kFTile + 8192 + 192 * 4 + (int)sizeof(UsfganFrBarriers) + 1024;
+  int dev = 0, num_sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  static bool attr_set[64] = {false};
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(usfgan_block_fr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(usfgan_block_fr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return fail((int)e, "usfgan_block_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  UsfganFrArgs a;
+  a.xb_in = (const __nv_bfloat16*)p.xb_in;
+  a.xb_out = (__nv_bfloat16*)p.xb_out;
+  a.bias1 = p.bias1;
+  a.bout = p.bout;
+  a.idx_past = p.idx_past;
+  a.idx_future = p.idx_future;
+  a.aux_u = (const __nv_bfloat16*)p.aux_u;
+  a.aux_q = (const __nv_bfloat16*)p.aux_q;
+  a.q_batch_stride = p.q_batch_stride;
+  a.q_ld = p.q_ld; a.q_fpad = p.q_fpad; a.hop = p.hop; a.reach = p.reach;
+  a.B = p.B; a.T = p.T;
+  a.dilation = p.adaptive ? 0 : p.dilation;
+  a.adaptive = p.adaptive;
+  a.tiles_per_row = tiles_per_row;
+  a.total_tiles = p.B * tiles_per_row;
+  a.out_scale = p.out_scale;
+  a.out_relu = p.out_relu;
+  a.dbg_flags = 0;
+  a.dbg = nullptr;
+  if (const char* e = getenv("SVSK_USFGAN_ABLATE")) a.dbg_flags = atoi(e);
+  if (const char* e = getenv("SVSK_USFGAN_TIMELINE")) a.dbg = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
+  const int grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
+  if (a.dbg || a.dbg_flags)  // clock64 role accounting (distorts the timing) and / or ablation flags
+    usfgan_block_fr_kernel<true><<<grid, kFThreads, smem_bytes, as_stream(stream)>>>(tm_x, tm_w1, tm_wout, tm_xout, a);
+  else
+    usfgan_block_fr_kernel<false><<<grid, kFThreads, smem_bytes, as_stream(stream)>>>(tm_x, tm_w1, tm_wout, tm_xout, a);
+  return check_launch("usfgan_block_bf16 (frame-rate aux)");
+}
+
+}  // namespace svsk

@@ -449,14 +449,16 @@ __global__ void usfgan_pack_kernel(const float* __restrict__ w_taps, const float
     for (int k = threadIdx.x; k < G / 2; k += blockDim.x) woutp[(size_t)r * (G / 2) + k] = __float2bfloat16_rn(w_out[(size_t)r * (G / 2) + k]);
 }
 
+int usfgan_block_fr_launch(const svsk_usfgan_block_params& p, void* stream);  // usfgan_block_fr_sm100.cu
+
 }  // namespace svsk
 
 using namespace svsk;
 
 extern "C" int svsk_usfgan_pack_block(const float* w_taps, const float* w_aux, const float* w_out, void* w1p,
                                       void* woutp, int C, int A, int G, void* stream) {
-  SVSK_REQUIRE(w_taps && w_aux && w_out && w1p && woutp, SVSK_E_ARG, "usfgan_pack_block: null");
-  SVSK_REQUIRE(C == 64 && G == 128 && A >= 1 && A <= 320, SVSK_E_ARG,
+  SVSK_REQUIRE(w_taps && (w_aux || A == 0) && w_out && w1p && woutp, SVSK_E_ARG, "usfgan_pack_block: null");
+  SVSK_REQUIRE(C == 64 && G == 128 && A >= 0 && A <= 320, SVSK_E_ARG,
                "usfgan_pack_block: needs residual 64 / gate 128 / aux <= 320 (C=%d G=%d A=%d)", C, G, A);
   const int Ap = (A + 63) / 64 * 64;
   usfgan_pack_kernel<<<G, 128, 0, as_stream(stream)>>>(w_taps, w_aux, w_out, (__nv_bfloat16*)w1p, (__nv_bfloat16*)woutp,
@@ -467,17 +469,20 @@ extern "C" int svsk_usfgan_pack_block(const float* w_taps, const float* w_aux, c
 extern "C" int svsk_usfgan_block_bf16(const svsk_usfgan_block_params* pp, void* stream) {
   SVSK_REQUIRE(pp != nullptr, SVSK_E_ARG, "usfgan_block_bf16: null params");
   const svsk_usfgan_block_params& p = *pp;
-  SVSK_REQUIRE(p.xb_in && p.xb_out && p.aux && p.w1p && p.woutp && p.bias1 && p.bout, SVSK_E_ARG,
+  const bool fr = p.aux_u != nullptr || p.aux_q != nullptr;
+  SVSK_REQUIRE(p.xb_in && p.xb_out && (p.aux || fr) && p.w1p && p.woutp && p.bias1 && p.bout, SVSK_E_ARG,
                "usfgan_block_bf16: null tensor");
   SVSK_REQUIRE(p.xb_in != p.xb_out, SVSK_E_ARG, "usfgan_block_bf16: xb_in and xb_out must differ (taps read neighbours)");
-  SVSK_REQUIRE(p.B > 0 && p.T > 0 && p.A >= 1 && p.A <= 320 && p.A % 8 == 0, SVSK_E_ARG,
-               "usfgan_block_bf16: bad shape B=%d T=%d A=%d (aux row pitch must be a multiple of 16 bytes)", p.B, p.T, p.A);
+  SVSK_REQUIRE(p.B > 0 && p.T > 0, SVSK_E_ARG, "usfgan_block_bf16: bad shape B=%d T=%d", p.B, p.T);
+  SVSK_REQUIRE(fr || (p.A >= 1 && p.A <= 320 && p.A % 8 == 0), SVSK_E_ARG,
+               "usfgan_block_bf16: bad aux width A=%d (aux row pitch must be a multiple of 16 bytes)", p.A);
   if (p.adaptive) SVSK_REQUIRE(p.idx_past && p.idx_future, SVSK_E_ARG, "usfgan_block_bf16: adaptive needs tap indices");
   else SVSK_REQUIRE(p.dilation >= 1 && p.dilation < p.T, SVSK_E_ARG,
                     "usfgan_block_bf16: reflect padding needs T > dilation (T=%d, dilation=%d)", p.T, p.dilation);
   SVSK_REQUIRE((long long)p.B * ((p.T + 127) / 128) < (1ll << 31), SVSK_E_ARG, "usfgan_block_bf16: too many tiles");
   int rc = require_sm100();
   if (rc) return rc;
+  if (fr) return usfgan_block_fr_launch(p, stream);
 
   const int akb = (p.A + 63) / 64, KB = 3 + akb;
   const int K1p = 3 * 64 + akb * 64;

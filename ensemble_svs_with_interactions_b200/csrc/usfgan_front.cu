@@ -14,6 +14,7 @@
 
 #include "sm100_ptx.cuh"
 #include "svsk_common.cuh"
+#include "usfgan_fr.cuh"
 
 namespace svsk {
 
@@ -204,6 +205,28 @@ __global__ void __launch_bounds__(256) source_samples_kernel(const double* __res
   }
 }
 
+// Frame-rate aux projection, operand A of the block kernel (usfgan_fr.cuh): the upsampler's impulse responses, one
+// thread per sample, re-ordered into the 16-frame window of the sample's tile.
+__global__ void usfgan_aux_weights_kernel(const float* __restrict__ imp, __nv_bfloat16* __restrict__ u, int T, int Tpad,
+                                          int hop, int reach) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Tpad) return;
+  uint32_t pk[8];
+  const int fb = usfgan_frame_base(t & ~127, reach, hop);
+#pragma unroll
+  for (int k = 0; k < 16; k += 2) {
+    float v0 = 0.f, v1 = 0.f;
+    if (t < T) {
+      v0 = imp[(size_t)((fb + k) & 15) * T + t];
+      v1 = imp[(size_t)((fb + k + 1) & 15) * T + t];
+    }
+    pk[k >> 1] = ptx::pack_bf16(v0, v1);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(u + (size_t)t * 16);
+  dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+}
+
 }  // namespace svsk
 
 using namespace svsk;
@@ -272,3 +295,16 @@ extern "C" int svsk_usfgan_source(const double* f0, const float* noise, float* s
                                                              sine_amp, noise_amp);
   return check_launch("usfgan_source");
 }
+
+extern "C" int svsk_usfgan_aux_weights(const float* imp, void* u, int T, int hop, int reach, void* stream) {
+  SVSK_REQUIRE(imp && u, SVSK_E_ARG, "usfgan_aux_weights: null tensor");
+  SVSK_REQUIRE(T > 0 && hop >= 1 && reach >= 0, SVSK_E_ARG, "usfgan_aux_weights: T=%d hop=%d reach=%d", T, hop, reach);
+  SVSK_REQUIRE((reinterpret_cast<uintptr_t>(u) & 15) == 0, SVSK_E_ALIGN, "usfgan_aux_weights: u must be 16-byte aligned");
+  // 16 impulse channels tell frames apart only if no sample hears two frames that are 16 apart
+  SVSK_REQUIRE(2ll * reach < 15ll * hop, SVSK_E_ARG, "usfgan_aux_weights: reach %d too long for hop %d", reach, hop);
+  const int Tpad = (T + 127) / 128 * 128;
+  usfgan_aux_weights_kernel<<<(Tpad + 255) / 256, 256, 0, as_stream(stream)>>>(imp, (__nv_bfloat16*)u, T, Tpad, hop, reach);
+  return check_launch("usfgan_aux_weights");
+}
+
+extern "C" int svsk_usfgan_frame_base(int t0, int reach, int hop) { return usfgan_frame_base(t0, reach, hop); }

@@ -466,16 +466,60 @@ def ntc_bf16_to_nct_f32(x, Cc):
 
 
 def usfgan_pack_block(w_taps, w_aux, w_out):
-    """w_taps [128,64,3] (k=3 conv, or stacked convP/convC/convF), w_aux [128,A] (A % 8 == 0), w_out [64,64] -> bf16."""
+    """w_taps [128,64,3] (k=3 conv, or stacked convP/convC/convF), w_aux [128,A] (A % 8 == 0) or None (frame-rate aux
+    projection: the block's w1p holds the taps only), w_out [64,64] -> bf16."""
     G, Cc, _ = w_taps.shape
-    A = w_aux.shape[1]
+    A = 0 if w_aux is None else w_aux.shape[1]
     Ap = (A + 63) // 64 * 64
     w1p = torch.empty((G, 3 * Cc + Ap), device=w_taps.device, dtype=bf16)
     woutp = torch.empty((Cc, G // 2), device=w_taps.device, dtype=bf16)
-    L.check(L.lib().svsk_usfgan_pack_block(L.ptr(w_taps.contiguous(), f32), L.ptr(w_aux.contiguous(), f32),
+    L.check(L.lib().svsk_usfgan_pack_block(L.ptr(w_taps.contiguous(), f32),
+                                           None if w_aux is None else L.ptr(w_aux.contiguous(), f32),
                                            L.ptr(w_out.contiguous(), f32), L.ptr(w1p), L.ptr(woutp), Cc, A, G,
                                            L.stream_ptr()), "usfgan_pack_block")
     return w1p, woutp
+
+
+class UsfganAuxFrames:
+    """Operands of the frame-rate aux projection of one generator call (csrc/usfgan_fr.cuh): ``u`` [ceil128(T), 16] bf16,
+    ``q`` [B, R, q_ld] bf16 (R = 128 x blocks, in the order the stacks were listed), and the window geometry."""
+
+    def __init__(self, u, q, q_fpad, hop, reach):
+        self.u, self.q, self.q_fpad, self.hop, self.reach = u, q, int(q_fpad), int(hop), int(reach)
+
+    def block(self, index):
+        """(aux_q view of block ``index``, batch stride in elements, q_ld)."""
+        return self.q[:, 128 * index:128 * (index + 1)], self.q.stride(0), self.q.stride(1)
+
+
+def usfgan_frame_window_ok(hop, reach):
+    """A 128-sample tile must fit its frames into the 16-frame window (8 for the reach + 7 of alignment slack)."""
+    return hop >= 1 and (127 + 2 * reach) // hop <= 7 and 2 * reach < 15 * hop
+
+
+def usfgan_aux_frames(cin_ntc, w_all, Tf, T, hop, reach):
+    """cin_ntc [B, Tf, Ap] bf16 (conv_in's output, channel-last), w_all [R, Ap] bf16 -> q [B, R, q_ld] bf16 with frame f at
+    column q_fpad + f and zeros elsewhere (svsk_usfgan_aux_frames)."""
+    B, Tf_, Ap = cin_ntc.shape
+    assert Tf_ == Tf
+    R = w_all.shape[0]
+    fpad = -L.lib().svsk_usfgan_frame_base(0, int(reach), int(hop))
+    last = L.lib().svsk_usfgan_frame_base((T - 1) // 128 * 128, int(reach), int(hop))
+    q_ld = (max(fpad + Tf, fpad + last + 16) + 7) // 8 * 8
+    q = torch.zeros((B, R, q_ld), device=cin_ntc.device, dtype=bf16)
+    L.check(L.lib().svsk_usfgan_aux_frames(L.ptr(cin_ntc, bf16, "cin"), L.ptr(w_all, bf16, "w_all"), L.ptr(q), B, Tf, Ap, R,
+                                           q_ld, fpad, L.stream_ptr()), "usfgan_aux_frames")
+    return q, fpad
+
+
+def usfgan_aux_weights(imp, hop, reach):
+    """imp [16, T] fp32 (the upsampler applied to unit impulses at the frames f = channel mod 16) -> u [ceil128(T), 16]
+    bf16 (svsk_usfgan_aux_weights)."""
+    T = imp.shape[1]
+    u = torch.empty(((T + 127) // 128 * 128, 16), device=imp.device, dtype=bf16)
+    L.check(L.lib().svsk_usfgan_aux_weights(L.ptr(imp, f32, "imp"), L.ptr(u), T, int(hop), int(reach), L.stream_ptr()),
+            "usfgan_aux_weights")
+    return u
 
 
 def conv1d_pack_bf16(w):
@@ -518,16 +562,28 @@ def dot_rows_bf16(x, w, bias):
 
 
 def usfgan_block_bf16(xb_in, xb_out, aux, w1p, woutp, bias1, bout, *, dilation=1, idx=None, out_scale=math.sqrt(0.5),
-                      out_relu=False):
-    """One fused uSFGAN Fixed / Adaptive block (svsk_usfgan_block_bf16)."""
+                      out_relu=False, frames=None, frames_block=0):
+    """One fused uSFGAN Fixed / Adaptive block (svsk_usfgan_block_bf16).  ``aux`` [B,T,A8] bf16 at sample rate, or
+    ``frames`` (UsfganAuxFrames) + ``frames_block`` for the frame-rate aux projection (then w1p holds the taps only)."""
     B, T, Cc = xb_in.shape
     p = L.UsfganBlockParams()
-    p.xb_in, p.xb_out, p.aux = L.ptr(xb_in, bf16, "xb_in"), L.ptr(xb_out, bf16, "xb_out"), L.ptr(aux, bf16, "aux")
+    p.xb_in, p.xb_out = L.ptr(xb_in, bf16, "xb_in"), L.ptr(xb_out, bf16, "xb_out")
     p.w1p, p.woutp = L.ptr(w1p, bf16), L.ptr(woutp, bf16)
     p.bias1, p.bout = L.ptr(bias1, f32), L.ptr(bout, f32)
     if idx is not None:
         p.idx_past, p.idx_future = L.ptr(idx[0], torch.int32), L.ptr(idx[1], torch.int32)
-    p.B, p.T, p.A = B, T, aux.shape[2]
+    p.B, p.T = B, T
+    if frames is not None:
+        qv, qbs, qld = frames.block(frames_block)
+        if frames.q.shape[0] != B or frames.u.shape[0] < (T + 127) // 128 * 128:
+            raise RuntimeError(f"usfgan_block_bf16: frame-rate aux operands are for another shape (q {tuple(frames.q.shape)}, "
+                               f"u {tuple(frames.u.shape)}, x {tuple(xb_in.shape)})")
+        p.aux_u, p.aux_q = frames.u.data_ptr(), qv.data_ptr()
+        p.q_batch_stride, p.q_ld, p.q_fpad, p.hop, p.reach = qbs, qld, frames.q_fpad, frames.hop, frames.reach
+        p.A = 0
+    else:
+        p.aux = L.ptr(aux, bf16, "aux")
+        p.A = aux.shape[2]
     p.dilation, p.adaptive, p.out_scale = int(dilation), int(idx is not None), float(out_scale)
     p.out_relu = int(out_relu)
     L.check(L.lib().svsk_usfgan_block_bf16(C.byref(p), L.stream_ptr()), "usfgan_block_bf16")

@@ -170,6 +170,8 @@ class ResidualBlocks(nn.Module):
         return res == 64 and gate == 128 and 0 < aux <= 320 and fixed_ok
 
     def _bf16_plan(self, aux_pad):
+        """Packed bf16 weights per block.  ``aux_pad`` = padded aux width of the sample-rate path, or 0 = the frame-rate
+        aux projection (w1p holds the taps only; the aux weights go into ``aux_weights_bf16``)."""
         key = tuple((p.data_ptr(), p._version) for p in self.parameters()) + (aux_pad,)
         if getattr(self, "_plan_key", None) == key:
             return self._plan
@@ -180,11 +182,14 @@ class ResidualBlocks(nn.Module):
                     w_taps, b1 = block.stacked_taps()
                 else:
                     w_taps, b1 = effective_weight(block.conv).contiguous(), block.conv.bias
-                w_aux = effective_weight(block.conv1x1_aux)[:, :, 0]
-                if aux_pad > w_aux.shape[1]:
-                    w_aux = torch.nn.functional.pad(w_aux, (0, aux_pad - w_aux.shape[1]))
+                w_aux = None
+                if aux_pad:
+                    w_aux = effective_weight(block.conv1x1_aux)[:, :, 0]
+                    if aux_pad > w_aux.shape[1]:
+                        w_aux = torch.nn.functional.pad(w_aux, (0, aux_pad - w_aux.shape[1]))
+                    w_aux = w_aux.to(f32).contiguous()
                 w_out = effective_weight(block.conv1x1_out)[:, :, 0]
-                w1p, woutp = ops.usfgan_pack_block(w_taps.to(f32), w_aux.to(f32).contiguous(), w_out.to(f32).contiguous())
+                w1p, woutp = ops.usfgan_pack_block(w_taps.to(f32), w_aux, w_out.to(f32).contiguous())
                 zeros = torch.zeros(w_taps.shape[0], device=w_taps.device, dtype=f32)
                 plan.append(dict(w1p=w1p, woutp=woutp,
                                  bias1=(b1.detach().to(f32).contiguous() if b1 is not None else zeros),
@@ -193,10 +198,19 @@ class ResidualBlocks(nn.Module):
         self._plan, self._plan_key = plan, key
         return plan
 
-    def forward_ntc_bf16(self, xb, auxb, d, idx_cache=None, relu_last=False):
-        """xb [B,T,64] bf16, auxb [B,T,A8] bf16 (A rounded up to a multiple of 8), d (B,1,T) fp32 -> [B,T,64] bf16.
+    def aux_weights(self, aux_pad):
+        """[128 * blocks, aux_pad] fp32: the blocks' conv1x1_aux weights stacked (rows of the frame-rate projection)."""
+        rows = []
+        for block in self.conv_dilated:
+            w = effective_weight(block.conv1x1_aux)[:, :, 0].to(f32)
+            rows.append(torch.nn.functional.pad(w, (0, aux_pad - w.shape[1])) if aux_pad > w.shape[1] else w)
+        return torch.cat(rows, dim=0)
+
+    def forward_ntc_bf16(self, xb, auxb, d, idx_cache=None, relu_last=False, frames=None, frames_block0=0):
+        """xb [B,T,64] bf16, auxb [B,T,A8] bf16 (A rounded up to a multiple of 8) or ``frames`` (ops.UsfganAuxFrames, this
+        stack's first block at index ``frames_block0``), d (B,1,T) fp32 -> [B,T,64] bf16.
         One svsk_usfgan_block_bf16 launch per block; activations ping-pong between two buffers."""
-        plan = self._bf16_plan(auxb.shape[2])
+        plan = self._bf16_plan(0 if frames is not None else auxb.shape[2])
         idx_cache = {} if idx_cache is None else idx_cache
         cur, nxt = xb, torch.empty_like(xb)
         a_idx = 0
@@ -209,7 +223,8 @@ class ResidualBlocks(nn.Module):
                 idx = idx_cache[dil]
                 a_idx += 1
             ops.usfgan_block_bf16(cur, nxt, auxb, pw["w1p"], pw["woutp"], pw["bias1"], pw["bout"],
-                                  dilation=pw["dilation"], idx=idx, out_relu=(relu_last and n_blk == len(plan) - 1))
+                                  dilation=pw["dilation"], idx=idx, out_relu=(relu_last and n_blk == len(plan) - 1),
+                                  frames=frames, frames_block=frames_block0 + n_blk)
             cur, nxt = nxt, cur
         return cur
 

@@ -74,11 +74,14 @@ class ConvInUpsampleNetwork(torch.nn.Module):
         self.upsample = UpsampleNetwork(upsample_scales, nonlinear_activation, nonlinear_activation_params,
                                         interpolate_mode, freq_axis_kernel_size, use_causal_conv)
 
+    def conv_in_frames(self, c):
+        """c (B, C, T' + 2*window) -> conv_in's output (B, C, T') at frame rate (upsample.py:186-187)."""
+        return ops.conv1d_f32(c.to(torch.float32).contiguous(), effective_weight(self.conv_in), None,
+                              pad_mode=ops.PAD_VALID)
+
     def forward(self, c):
         """c (B, C, T' + 2*window) -> (B, C, T' * prod(scales))."""
-        c = ops.conv1d_f32(c.to(torch.float32).contiguous(), effective_weight(self.conv_in), None,
-                           pad_mode=ops.PAD_VALID)
-        return self.upsample(c)
+        return self.upsample(self.conv_in_frames(c))
 
     def supports_fused(self):
         return self.upsample.supports_fused(self.conv_in.out_channels)

@@ -59,6 +59,45 @@ class _GeneratorBase(nn.Module):
         auxb, _ = ops.nct_to_ntc(c, Cp=(A + 7) // 8 * 8)
         return auxb
 
+    # "auto": the blocks take the aux projection at FRAME rate (csrc/usfgan_fr.cuh) whenever a 128-sample tile fits the
+    # 16-frame window (any hop >= 54 with the recipes' scale lists); "samples": always stream the upsampled features
+    aux_projection = "auto"
+
+    def _aux_frames(self, c, T, stacks):
+        """ops.UsfganAuxFrames for ``stacks`` (block index = position in the concatenation of their blocks), or None when
+        the sample-rate path has to be used.  conv1x1_aux(upsample(conv_in(c))) = U . (conv1x1_aux(conv_in(c))): Q is one
+        bf16 GEMM at frame rate for all blocks, U the upsampler's impulse responses (cached per frame count)."""
+        up = self.upsample_net
+        scales = list(up.upsample.upsample_scales)
+        hop, reach, rate = 1, 0, 1
+        for s_ in scales:
+            hop *= s_
+        for s_ in scales:
+            rate *= s_
+            reach += s_ * (hop // rate)
+        if self.aux_projection == "samples" or not ops.usfgan_frame_window_ok(hop, reach) or not stacks:
+            return None
+        if self.aux_projection not in ("auto", "frames"):
+            raise RuntimeError(f"unknown aux_projection {self.aux_projection!r}")
+        cin = up.conv_in_frames(c)                                  # [B, A, Tf] fp32
+        B, A, Tf = cin.shape
+        if Tf * hop != T:
+            raise RuntimeError(f"aux features give {Tf} x {hop} samples, the source signal has {T}")
+        Ap = (A + 7) // 8 * 8
+        cinb, _ = ops.nct_to_ntc(cin, Cp=Ap)
+        wkey = tuple((p.data_ptr(), p._version) for st in stacks for b in st.conv_dilated for p in b.conv1x1_aux.parameters())
+        if getattr(self, "_auxw_key", None) != wkey:
+            self._auxw = torch.cat([st.aux_weights(Ap) for st in stacks], dim=0).to(torch.bfloat16).contiguous()
+            self._auxw_key = wkey
+        q, fpad = ops.usfgan_aux_frames(cinb, self._auxw, Tf, T, hop, reach)
+        ukey = (Tf, str(c.device)) + tuple((p.data_ptr(), p._version) for p in up.upsample.parameters())
+        if getattr(self, "_auxu_key", None) != ukey:
+            f_idx = torch.arange(Tf, device=c.device)
+            impulses = (f_idx[None, :] % 16 == torch.arange(16, device=c.device)[:, None]).to(f32)[None]
+            self._auxu = ops.usfgan_aux_weights(up.upsample(impulses)[0].contiguous(), hop, reach)
+            self._auxu_key = ukey
+        return ops.UsfganAuxFrames(self._auxu, q, fpad, hop, reach)
+
     def _build_common(self, in_channels, out_channels, residual_channels, skip_channels, aux_channels,
                       aux_context_window, upsample_params):
         self.in_channels = in_channels
@@ -153,16 +192,20 @@ class USFGANGenerator(_GeneratorBase):
                 and l1.out_channels % 16 == 0):
             # everything stays NTC bf16 (as in ParallelHnUSFGANGenerator's wave-only path): aux features upsampled straight
             # into that layout, the 1 -> C convs write it directly, conv_last runs on the tensor cores
-            if self.upsample_net.supports_fused():
-                auxb = self.upsample_net.forward_ntc_bf16(c)
-            else:
-                auxb = self._aux_ntc(self.upsample_net(c))
-            assert auxb.size(1) == x.size(-1)
+            frames = self._aux_frames(c, x.size(-1), [self.source_network, self.filter_network])
+            auxb = None
+            if frames is None:
+                if self.upsample_net.supports_fused():
+                    auxb = self.upsample_net.forward_ntc_bf16(c)
+                else:
+                    auxb = self._aux_ntc(self.upsample_net(c))
+                assert auxb.size(1) == x.size(-1)
             xb = _conv1x1_expand_ntc(self.conv_first, x.to(f32).contiguous()[:, 0])
-            yb = self.source_network.forward_ntc_bf16(xb, auxb, d, cache, relu_last=True)
+            yb = self.source_network.forward_ntc_bf16(xb, auxb, d, cache, relu_last=True, frames=frames)
             s = self._conv_last_ntc_bf16(yb)
             xb = _conv1x1_expand_ntc(self.conv_mid, s[:, 0])
-            yb = self.filter_network.forward_ntc_bf16(xb, auxb, d, cache, relu_last=True)
+            yb = self.filter_network.forward_ntc_bf16(xb, auxb, d, cache, relu_last=True, frames=frames,
+                                                      frames_block0=len(self.source_network.conv_dilated))
             return self._conv_last_ntc_bf16(yb), s
         c = self.upsample_net(c)
         assert c.size(-1) == x.size(-1)
@@ -264,7 +307,10 @@ class CascadeHnUSFGANGenerator(_HnBase):
             xf = x.to(f32).contiguous()
             hb = _conv1x1_expand_ntc(self.conv_first_sine, xf[:, 0])
             nb = _conv1x1_expand_ntc(self.conv_first_noise, xf[:, 1])
-            hb = self.harmonic_network.forward_ntc_bf16(hb, auxb, d, cache)
+            nets = [self.harmonic_network, self.noise_network, self.filter_network]
+            frames = self._aux_frames(c, x.size(-1), nets)
+            first = [0, len(nets[0].conv_dilated), len(nets[0].conv_dilated) + len(nets[1].conv_dilated)]
+            hb = self.harmonic_network.forward_ntc_bf16(hb, auxb, d, cache, frames=frames, frames_block0=first[0])
             zeros = torch.zeros_like(hb)
             hm = ops.periodic_mix_bf16(ab, hb, zeros)                       # a * h
             key = tuple((p.data_ptr(), p._version) for p in self.conv_merge.parameters())
@@ -273,9 +319,9 @@ class CascadeHnUSFGANGenerator(_HnBase):
                                     self.conv_merge.bias.detach().to(f32).contiguous())
                 self._merge_key = key
             nb = ops.conv1d_bf16(torch.cat([hm, nb], dim=2), self._merge_plan[0], self._merge_plan[1], self.conv_merge.out_channels, 1)
-            nb = self.noise_network.forward_ntc_bf16(nb, auxb, d, cache)
+            nb = self.noise_network.forward_ntc_bf16(nb, auxb, d, cache, frames=frames, frames_block0=first[1])
             sb = ops.periodic_mix_bf16(ab, hb, nb)                          # a * h + (1 - a) * n
-            yb = self.filter_network.forward_ntc_bf16(sb, auxb, d, cache, relu_last=True)
+            yb = self.filter_network.forward_ntc_bf16(sb, auxb, d, cache, relu_last=True, frames=frames, frames_block0=first[2])
             return self._conv_last_ntc_bf16(yb), None, None, None, ab
         c, a, h, n = self._front(x, c)
         auxb = self._aux_ntc(c)
@@ -322,10 +368,13 @@ class ParallelHnUSFGANGenerator(_HnBase):
             xf = x.to(f32).contiguous()
             hb = _conv1x1_expand_ntc(self.conv_first_sine, xf[:, 0])
             nb = _conv1x1_expand_ntc(self.conv_first_noise, xf[:, 1])
-            hb = self.harmonic_network.forward_ntc_bf16(hb, auxb, d, cache)
-            nb = self.noise_network.forward_ntc_bf16(nb, auxb, d, cache)
+            nets = [self.harmonic_network, self.noise_network, self.filter_network]
+            frames = self._aux_frames(c, x.size(-1), nets)
+            first = [0, len(nets[0].conv_dilated), len(nets[0].conv_dilated) + len(nets[1].conv_dilated)]
+            hb = self.harmonic_network.forward_ntc_bf16(hb, auxb, d, cache, frames=frames, frames_block0=first[0])
+            nb = self.noise_network.forward_ntc_bf16(nb, auxb, d, cache, frames=frames, frames_block0=first[1])
             sb = ops.periodic_mix_bf16(ab, hb, nb)
-            yb = self.filter_network.forward_ntc_bf16(sb, auxb, d, cache, relu_last=True)
+            yb = self.filter_network.forward_ntc_bf16(sb, auxb, d, cache, relu_last=True, frames=frames, frames_block0=first[2])
             return self._conv_last_ntc_bf16(yb), None, None, None, ab
         c, a, h, n = self._front(x, c)
         auxb = self._aux_ntc(c)

@@ -309,11 +309,33 @@ typedef struct svsk_usfgan_block_params {
   int32_t dilation, adaptive;
   float out_scale;     /* sqrt(0.5) in the reference */
   int32_t out_relu;    /* 1: xb_out = relu(...) — folds conv_last's leading ReLU into the last block (generator.py:461) */
+  /* Frame-rate aux projection (optional; both NULL = the sample-rate `aux` above is used).  When set, `aux` and `A` are
+   * ignored, w1p is [128][192] (svsk_usfgan_pack_block with A = 0) and the block adds
+   *   sum_k aux_u[t][k] * aux_q[b][n][q_fpad + fbase(t) + k],   fbase = svsk_usfgan_frame_base(128*(t/128), reach, hop)
+   * i.e. conv1x1_aux(upsample(c)) with the projection done at frame rate — see svsk_usfgan_aux_frames / _weights. */
+  const void* aux_u;   /* [ceil128(T)][16] bf16 from svsk_usfgan_aux_weights */
+  const void* aux_q;   /* this block's [128][q_ld] bf16 rows of track 0 inside svsk_usfgan_aux_frames' output */
+  int64_t q_batch_stride; /* elements between tracks of aux_q */
+  int32_t q_ld, q_fpad, hop, reach;
 } svsk_usfgan_block_params;
 SVSK_API int svsk_usfgan_block_bf16(const svsk_usfgan_block_params* p, void* stream);
 /* w_taps [128][64][3] (k=3 conv, or stacked convP/convC/convF), w_aux [128][A], w_out [64][64] (fp32) -> packed bf16 */
 SVSK_API int svsk_usfgan_pack_block(const float* w_taps, const float* w_aux, const float* w_out, void* w1p, void* woutp,
                                     int C, int A, int G, void* stream);
+
+/* Frame-rate aux projection for all blocks of a generator (upsample.py:61-128 + residual_block.py:74,100,139-142):
+ *   q[b][r][q_fpad + f] = sum_a w[r][a] * cin[b][f][a]      r < R (= 128 x number of blocks), f < Tf
+ * cin [B][Tf][Ap] bf16 = conv_in's output at frame rate (channels padded with zeros to Ap % 8 == 0), w [R][Ap] bf16 = the
+ * blocks' conv1x1_aux weights stacked, q [B][R][q_ld] bf16 — the CALLER zero-fills q first (columns outside
+ * q_fpad .. q_fpad+Tf-1 are read by the block kernel and must be finite).  R % 16 == 0. */
+SVSK_API int svsk_usfgan_aux_frames(const void* cin, const void* w, void* q, int B, int Tf, int Ap, int R, int q_ld, int q_fpad,
+                                    void* stream);
+/* u[t][k] = imp[(fbase(t) + k) mod 16][t] for t < T, 0 for T <= t < ceil128(T): the upsampler's impulse responses
+ * (imp [16][T] fp32 = upsample_net.upsample applied to 16 channels holding unit impulses at the frames f = ch mod 16)
+ * re-ordered into the per-tile frame window the block kernel multiplies with. */
+SVSK_API int svsk_usfgan_aux_weights(const float* imp, void* u, int T, int hop, int reach, void* stream);
+/* First frame of the 16-frame window of the tile starting at sample t0 (a multiple of 8, may be negative). */
+SVSK_API int svsk_usfgan_frame_base(int t0, int reach, int hop);
 
 /* General NTC bf16 Conv1d on tensor cores (weights resident in smem, persistent over 128-sample tiles):
  *   y[b][t][co] = act(bias[co] + sum_j sum_ci w[co][ci][j] x[b][t + (j - tap_origin)*dilation][ci])

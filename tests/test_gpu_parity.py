@@ -745,6 +745,104 @@ def test_usfgan_block_bf16(T, dil, adaptive, A):
     close_bf16(out.float().transpose(1, 2), ref, 4e-3, 1.5e-2)
 
 
+def _aux_frames_operands(ops, net, cin, w_aux_blocks, scales):
+    """UsfganAuxFrames for conv_in output ``cin`` [B, A, Tf] (device) and a list of [128, A] aux weights (device)."""
+    B, A, Tf = cin.shape
+    hop = int(np.prod(scales))
+    reach, rate = 0, 1
+    for s_ in scales:
+        rate *= s_
+        reach += s_ * (hop // rate)
+    assert ops.usfgan_frame_window_ok(hop, reach)
+    Ap = (A + 7) // 8 * 8
+    cinb, _ = ops.nct_to_ntc(cin, Cp=Ap)
+    w_all = torch.cat([torch.nn.functional.pad(w, (0, Ap - A)) for w in w_aux_blocks]).to(torch.bfloat16).contiguous()
+    q, fpad = ops.usfgan_aux_frames(cinb, w_all, Tf, Tf * hop, hop, reach)
+    impulses = (torch.arange(Tf, device=DEV)[None, :] % 16 == torch.arange(16, device=DEV)[:, None]).float()[None]
+    imp = net(impulses)[0].contiguous()
+    u = ops.usfgan_aux_weights(imp, hop, reach)
+    return ops.UsfganAuxFrames(u, q, fpad, hop, reach), imp, w_all, cinb
+
+
+@pytest.mark.parametrize("scales,Tf,dil,adaptive,A", [([5, 4, 3, 2], 9, 1, False, 80), ([5, 4, 3, 2], 50, 64, False, 80),
+                                                      ([5, 4, 3, 2], 50, 4, True, 80), ([4, 4, 4], 33, 2, False, 72),
+                                                      ([5, 4, 3, 2], 1, 8, False, 80), ([5, 4, 3, 2], 2, 1, True, 65),
+                                                      ([5, 4, 3, 2], 3001, 512, False, 80), ([5, 4, 3, 2], 3001, 16, True, 80)])
+def test_usfgan_block_bf16_frame_rate_aux(scales, Tf, dil, adaptive, A):
+    """The block kernel with the aux projection taken at frame rate (aux_u / aux_q operands) against the oracle's block on
+    the UPSAMPLED aux features, and the two operand kernels against their definitions."""
+    from ensemble_svs_with_interactions_b200.usfgan.layers.upsample import UpsampleNetwork
+    ops = _ops()
+    g = torch.Generator().manual_seed(Tf + dil + A)
+    B = 2
+    hop = int(np.prod(scales))
+    T = Tf * hop
+    net = UpsampleNetwork(scales).to(DEV)
+    with torch.no_grad():
+        for n in range(len(scales)):
+            wt = net.up_layers[2 * n + 1].weight
+            wt.copy_((torch.rand(wt.shape, generator=g) + 0.1).to(DEV) / (2 * scales[n] + 1) * 1.6)
+    cin = torch.randn(B, A, Tf, generator=g)
+    c = net(cin.to(DEV)).cpu()                                  # sample-rate aux features (staged fp32 kernels)
+    x = torch.randn(B, 64, T, generator=g)
+    w_taps = torch.randn(128, 64, 3, generator=g) / math.sqrt(192); b1 = torch.randn(128, generator=g) * 0.1
+    w_aux = torch.randn(128, A, 1, generator=g) / math.sqrt(A)
+    w_other = torch.randn(128, A, generator=g)
+    w_out = torch.randn(64, 64, 1, generator=g) / 8; b_out = torch.randn(64, generator=g) * 0.1
+    if adaptive:
+        d = torch.empty(B, 1, T).uniform_(0.7, 9.0, generator=g)
+        taps = O.pd_gather(_bf(x), d, dil)
+    else:
+        if dil >= T:
+            pytest.skip("reflect padding needs T > dilation")
+        taps = (O.shifted_tap(_bf(x), -dil, "reflect"), O.shifted_tap(_bf(x), dil, "reflect"))
+    ref = _usfgan_block_ref(w_taps, b1, w_aux, w_out, b_out, x, c, taps)
+
+    frames, imp, w_all, cinb = _aux_frames_operands(ops, net, cin.to(DEV), [w_other.to(DEV), w_aux[:, :, 0].to(DEV)], scales)
+    # operand kernels against their definitions
+    qref = torch.einsum("ra,bfa->brf", w_all.float(), cinb.float())
+    qv = frames.q[:, :, frames.q_fpad:frames.q_fpad + Tf].float()
+    assert float((qv - qref).abs().max()) <= 2 ** -7 * float(qref.abs().max())
+    assert float(frames.q[:, :, :frames.q_fpad].abs().max()) == 0.0 and float(frames.q[:, :, frames.q_fpad + Tf:].abs().max()) == 0.0
+    from ensemble_svs_with_interactions_b200 import _lib as L
+    tt = torch.arange(T)
+    fb = torch.tensor([L.lib().svsk_usfgan_frame_base(int(t0), frames.reach, hop) for t0 in range(0, T, 128)])[tt // 128]
+    uref = torch.stack([imp.cpu()[(fb + k) % 16, tt] for k in range(16)], dim=1)
+    assert torch.equal(frames.u[:T].float().cpu(), uref.to(torch.bfloat16).float())
+    assert float(frames.u[T:].abs().max()) == 0.0 if frames.u.shape[0] > T else True
+
+    xb, _ = ops.nct_to_ntc(x.to(DEV))
+    w1p, woutp = ops.usfgan_pack_block(w_taps.to(DEV), None, w_out[:, :, 0].contiguous().to(DEV))
+    assert tuple(w1p.shape) == (128, 192)
+    out = torch.full_like(xb, float("nan"))
+    idx = ops.pd_index(d.to(DEV), dil) if adaptive else None
+    ops.usfgan_block_bf16(xb, out, None, w1p, woutp, b1.to(DEV), b_out.to(DEV), dilation=dil, idx=idx, frames=frames,
+                          frames_block=1)
+    torch.cuda.synchronize()
+    close_bf16(out.float().transpose(1, 2), ref, 4e-3, 1.5e-2)
+    # same launch again: bit-identical (no race between the two operand stages)
+    out2 = torch.full_like(xb, float("nan"))
+    ops.usfgan_block_bf16(xb, out2, None, w1p, woutp, b1.to(DEV), b_out.to(DEV), dilation=dil, idx=idx, frames=frames,
+                          frames_block=1)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+
+
+def test_usfgan_block_frame_rate_aux_rejects_bad_arguments():
+    ops = _ops()
+    xb = torch.zeros(1, 256, 64, device=DEV, dtype=torch.bfloat16)
+    w1p = torch.zeros(128, 192, device=DEV, dtype=torch.bfloat16); wo = torch.zeros(64, 64, device=DEV, dtype=torch.bfloat16)
+    b1 = torch.zeros(128, device=DEV); bo = torch.zeros(64, device=DEV)
+    u = torch.zeros(256, 16, device=DEV, dtype=torch.bfloat16)
+    q = torch.zeros(1, 128, 32, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="reach at most 8 frames"):
+        ops.usfgan_block_bf16(xb, torch.empty_like(xb), None, w1p, wo, b1, bo, frames=ops.UsfganAuxFrames(u, q, 8, 12, 16))
+    with pytest.raises(RuntimeError, match="aux_q rows hold columns"):
+        ops.usfgan_block_bf16(xb, torch.empty_like(xb), None, w1p, wo, b1, bo, frames=ops.UsfganAuxFrames(u, q, 0, 120, 152))
+    with pytest.raises(RuntimeError, match="another shape"):
+        ops.usfgan_block_bf16(xb, torch.empty_like(xb), None, w1p, wo, b1, bo, frames=ops.UsfganAuxFrames(u[:128], q, 8, 120, 152))
+
+
 @pytest.mark.parametrize("scales,A,Fr,B", [([5, 4, 3, 2], 80, 37, 2), ([4, 3], 12, 9, 2), ([5, 4, 3, 2], 80, 3, 1),
                                            ([2, 2], 24, 70, 3), ([8, 3, 5], 80, 600, 1)])
 def test_upsample_fused_matches_staged_path(scales, A, Fr, B):

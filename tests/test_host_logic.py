@@ -240,3 +240,44 @@ def test_reference_root_discovery(tmp_path, monkeypatch):
     monkeypatch.delenv("SVSK_REFERENCE_ROOT")
     root = importlib.reload(ref_shim).REFERENCE_ROOT
     assert root.endswith("baseline/_ref") or root == "/root/reference"
+
+
+@pytest.mark.parametrize("scales,Tf", [([5, 4, 3, 2], 23), ([4, 4, 4], 40), ([8, 8], 17), ([5, 4, 3, 2], 2)])
+def test_usfgan_frame_window_covers_upsampler_reach(scales, Tf):
+    """Frame-rate aux projection (csrc/usfgan_fr.cuh): for every 128-sample tile the 16-frame window that starts at
+    svsk_usfgan_frame_base holds every frame the upsampler lets the tile hear, and 16 impulse channels (frame mod 16)
+    tell those frames apart — checked against the oracle's upsampler on the CPU (the C function runs on the host)."""
+    import math
+    from ensemble_svs_with_interactions_b200 import _lib as L, ops
+    from oracle import svs_oracle as O
+    hop = int(np.prod(scales))
+    reach, rate = 0, 1
+    for s_ in scales:
+        rate *= s_
+        reach += s_ * (hop // rate)
+    assert ops.usfgan_frame_window_ok(hop, reach)
+    g = torch.Generator().manual_seed(Tf)
+    sd = {"conv_in.weight": torch.zeros(1, 1, 1)}
+    for n, s_ in enumerate(scales):
+        sd[f"upsample.up_layers.{2 * n + 1}.weight"] = torch.rand(1, 1, 1, 2 * s_ + 1, generator=g) + 0.1
+
+    def up(c):     # the oracle's stages without conv_in
+        sd["conv_in.weight"] = torch.eye(c.shape[1]).unsqueeze(-1)
+        return O.usfgan_upsample(sd, "", c, scales)
+    c = torch.randn(1, 5, Tf, generator=g, dtype=torch.float64)
+    full = up(c.float())[0].double()                                        # [5, T]
+    T = Tf * hop
+    imp = up((torch.arange(Tf)[None, :] % 16 == torch.arange(16)[:, None]).float()[None])[0].double()   # [16, T]
+    fbase = L.lib().svsk_usfgan_frame_base
+    assert fbase(0, reach, hop) == (math.floor(-reach / hop) // 8) * 8
+    cpad = torch.zeros(5, 64 + Tf + 64, dtype=torch.float64)
+    cpad[:, 64:64 + Tf] = c[0]
+    for t0 in range(0, T, 128):
+        n = min(128, T - t0)
+        fb = fbase(t0, reach, hop)
+        assert fb % 8 == 0 and fb == (math.floor((t0 - reach) / hop) // 8) * 8
+        assert (t0 + 127 + reach) // hop - fb <= 15
+        U = imp[[(fb + k) % 16 for k in range(16)]][:, t0:t0 + n]           # [16, n]
+        rebuilt = cpad[:, 64 + fb:64 + fb + 16] @ U                          # [5, n]
+        assert float((rebuilt - full[:, t0:t0 + n]).abs().max()) < 1e-5 * max(1.0, float(full.abs().max()))
+    assert not ops.usfgan_frame_window_ok(12, 3 * 4 + 4)                     # hop 12 (scales [4, 3]): sample-rate path

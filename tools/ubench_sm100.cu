@@ -152,6 +152,121 @@ __global__ void __launch_bounds__(128, 1) ubench_rowshift_kernel(const __nv_bflo
   if (warp == 1) ptx::tmem_dealloc(tmem, 64);
 }
 
+
+// Throughput of the special-function unit and of candidate gate formulations z = tanh(a) * sigmoid(b) (profiling aid for
+// the uSFGAN / DiffNet epilogues).  Every thread keeps 8 independent chains; out[block] = cycles for `iters` rounds.
+__device__ __forceinline__ float ub_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ub_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// 2^y for y in [-126, 126] on the FMA pipe: round-to-nearest split + degree-4 polynomial on [-0.5, 0.5] + exponent splice
+__device__ __forceinline__ float ub_exp2_fma(float y) {
+  const float magic = 12582912.f;  // 1.5 * 2^23
+  const float yr = y + magic;
+  const float n = yr - magic;
+  const float f = y - n;
+  float p = fmaf(f, 0.0096181291f, 0.0555041087f);
+  p = fmaf(p, f, 0.2402265070f);
+  p = fmaf(p, f, 0.6931471806f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(yr) << 23));
+}
+__global__ void ubench_sfu_kernel(int mode, int iters, unsigned long long* out, float* sink) {
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = 0.001f * (threadIdx.x + 1) + 0.1f * i;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = x[i];
+      if (mode == 0) v = ptx::tanh_approx(v);
+      else if (mode == 1) v = ub_ex2(v) - 1.0f;
+      else if (mode == 2) v = ub_rcp(v) + 0.5f;
+      else if (mode == 3) v = fmaf(v, 0.999f, 0.001f);
+      else if (mode == 4) {  // gate, as the kernels have it: 2 MUFU.TANH
+        v = ptx::tanh_approx(v + 0.1f) * fmaf(ptx::tanh_approx(0.5f * (v - 0.2f)), 0.5f, 0.5f) + 0.3f;
+      } else if (mode == 5) {  // gate with 2 EX2 + 1 RCP
+        const float a = fminf(fmaxf(v + 0.1f, -10.f), 10.f), b = fminf(fmaxf(v - 0.2f, -30.f), 30.f);
+        const float e1 = ub_ex2(a * -2.885390082f), e2 = ub_ex2(b * -1.442695041f);
+        v = (1.f - e1) * ub_rcp((1.f + e1) * (1.f + e2)) + 0.3f;
+      } else if (mode == 6) {  // gate with both exponentials on the FMA pipe + 1 RCP
+        const float a = fminf(fmaxf(v + 0.1f, -10.f), 10.f), b = fminf(fmaxf(v - 0.2f, -30.f), 30.f);
+        const float e1 = ub_exp2_fma(a * -2.885390082f), e2 = ub_exp2_fma(b * -1.442695041f);
+        v = (1.f - e1) * ub_rcp((1.f + e1) * (1.f + e2)) + 0.3f;
+      } else if (mode == 7) {  // one exponential on the SFU, one on the FMA pipe
+        const float a = fminf(fmaxf(v + 0.1f, -10.f), 10.f), b = fminf(fmaxf(v - 0.2f, -30.f), 30.f);
+        const float e1 = ub_ex2(a * -2.885390082f), e2 = ub_exp2_fma(b * -1.442695041f);
+        v = (1.f - e1) * ub_rcp((1.f + e1) * (1.f + e2)) + 0.3f;
+      }
+      x[i] = v;
+    }
+  }
+  const long long t1 = clock64();
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc += x[i];
+  if (acc == 12345.678f) sink[0] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) out[blockIdx.x] = (unsigned long long)(t1 - t0);
+}
+
+
+// TMEM read throughput: every warp reads its own lane quarter, `cols` fp32 columns per round, with tcgen05.ld
+// 32x32b.x16 / .x32 / .x64 and one wait::ld per round (mode 0) or per instruction (mode 1).
+__device__ __forceinline__ void ub_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+      "%25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__global__ void ubench_tmem_ld_kernel(int width, int per_inst_wait, int iters, unsigned long long* out, float* sink) {
+  __shared__ uint32_t tmem_base;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) { ptx::tmem_alloc(&tmem_base, 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t acc = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    // one round = 128 columns of this warp's 32 lanes = 16 KB
+    if (width == 16) {
+#pragma unroll
+      for (int c = 0; c < 128; c += 16) {
+        uint32_t r[16];
+        ptx::tmem_ld16(tmem + ((it * 128 + c) & 511), r);
+        if (per_inst_wait) ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc ^= r[i];
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 128; c += 32) {
+        uint32_t r[32];
+        ub_tmem_ld32(tmem + ((it * 128 + c) & 511), r);
+        if (per_inst_wait) ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc ^= r[i];
+      }
+    }
+    ptx::tmem_ld_wait();
+  }
+  const long long t1 = clock64();
+  if (acc == 0x12345678u) sink[0] = 1.f;
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) out[blockIdx.x] = (unsigned long long)(t1 - t0);
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace svsk
 
 using namespace svsk;
@@ -192,4 +307,22 @@ extern "C" SVSK_API int svsk_ubench_rowshift(const void* win, int rows, int r0, 
   const int smem_bytes = 256 * 128 + 64 * 128 + 1024;
   ubench_rowshift_kernel<<<1, 128, smem_bytes, as_stream(stream)>>>((const __nv_bfloat16*)win, rows, r0, mode, out);
   return check_launch("ubench_rowshift");
+}
+
+// out [grid] cycles; every thread does iters x 8 operations of `mode` (see ubench_sfu_kernel).
+extern "C" SVSK_API int svsk_ubench_sfu(int mode, int warps, int iters, int grid, unsigned long long* out, float* sink, void* stream) {
+  SVSK_REQUIRE(out && sink && warps >= 1 && warps <= 32 && iters > 0 && grid > 0, SVSK_E_ARG, "ubench_sfu: bad args");
+  ubench_sfu_kernel<<<grid, warps * 32, 0, as_stream(stream)>>>(mode, iters, out, sink);
+  return check_launch("ubench_sfu");
+}
+
+// out [grid] cycles for `iters` rounds of 128 columns x 32 lanes per warp (16 KB per warp and round).
+extern "C" SVSK_API int svsk_ubench_tmem_ld(int width, int per_inst_wait, int warps, int iters, int grid, unsigned long long* out,
+                                            float* sink, void* stream) {
+  SVSK_REQUIRE(out && sink && (width == 16 || width == 32) && warps >= 1 && warps <= 32 && iters > 0 && grid > 0, SVSK_E_ARG,
+               "ubench_tmem_ld: bad args");
+  int rc = require_sm100();
+  if (rc) return rc;
+  ubench_tmem_ld_kernel<<<grid, warps * 32, 0, as_stream(stream)>>>(width, per_inst_wait, iters, out, sink);
+  return check_launch("ubench_tmem_ld");
 }
