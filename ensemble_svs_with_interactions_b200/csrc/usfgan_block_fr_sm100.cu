@@ -22,11 +22,15 @@
 //     accumulators: while one group waits for its GEMM2 or its TMA store the other one gates.
 //
 //   warp 0      TMA producer: centre tap, and both side taps of interior fixed-block tiles
-//   warp 1      GEMM1 issuer (tcgen05.mma cta_group::1, M=128, N=128; + the residual's identity MMAs) + TMEM owner
-//   warp 6      GEMM2 issuer (N=64)
+//   warp 1      MMA issuer (tcgen05.mma cta_group::1, M=128): per tile GEMM2 (N=64) of the tile two back, then GEMM1
+//               (N=128) and the residual's identity MMAs of this one — one thread, so their order in the tensor pipe is
+//               fixed; + TMEM owner
+//   warp 6      idle (was the GEMM2 issuer)
 //   warps 2-5   gather producers (thread = row): the aux operands U (rows = samples) and Q (rows = gate channels) of
-//               every tile, and the side taps of adaptive blocks / reflected boundary tiles, by 16-byte cp.async into the
-//               swizzled tiles; completion through cp.async.mbarrier.arrive.noinc on the tile's full barrier
+//               every tile by 16-byte cp.async into the swizzled tiles (completion through
+//               cp.async.mbarrier.arrive.noinc on the tile's full barrier), and the side taps of adaptive blocks /
+//               reflected boundary tiles: one 1 KB TMA box per 8-row group whose sources are consecutive rows, cp.async
+//               rows for the rest
 //   warps 7-22  epilogue: two groups of 8 warps (thread = sample, two warps per TMEM lane quarter alternating 16-column
 //               chunks); gate -> G[p] (bf16, swizzled smem) -> GEMM2 -> output rows into the same buffer -> one TMA store
 //               per lane quarter
@@ -62,7 +66,7 @@ struct UsfganFrArgs {
   int out_relu;
   unsigned long long* dbg;  // profiling only: [grid][16] accumulated clock64 deltas per role
   int dbg_flags;            // profiling only: 1 = skip epilogue math/stores, 2 = no MUFU, 4 = skip MMAs, 8 = no global
-                            // stores, 16 = no TMEM loads
+                            // stores, 16 = no TMEM loads, 64 = no TMA boxes for the gathered taps
 };
 
 struct __align__(8) UsfganFrBarriers {
@@ -79,6 +83,9 @@ __device__ __forceinline__ void fr_cp_async_16(void* dst, const void* src, uint3
 __device__ __forceinline__ void fr_cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ptx::smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void fr_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(ptx::smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ bool fr_tile_needs_gather(int t0, int T, int d, int adaptive) {
   if (adaptive) return true;
   const int last = min(t0 + 127, T - 1);
@@ -89,7 +96,7 @@ template <bool kProf>
 __global__ void __launch_bounds__(kFThreads, 1)
 usfgan_block_fr_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
                        const __grid_constant__ CUtensorMap tm_wout, const __grid_constant__ CUtensorMap tm_xout,
-                       const UsfganFrArgs a) {
+                       const __grid_constant__ CUtensorMap tm_x8, const UsfganFrArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w1_s = smem;                       // 3 tiles of [128 rows][64]
@@ -109,6 +116,7 @@ usfgan_block_fr_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     ptx::prefetch_tmap(&tm_w1);
     ptx::prefetch_tmap(&tm_wout);
     ptx::prefetch_tmap(&tm_xout);
+    ptx::prefetch_tmap(&tm_x8);
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars->full[i], 129);
       ptx::mbar_init(&bars->empty[i], 1);
@@ -177,12 +185,34 @@ usfgan_block_fr_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
       // complete twice in between, because the stage's next producer waits for this thread's commit.
       bool full_ready = false, g_ready = false;
       long long acc_full = 0, acc_g = 0, acc_mma = 0, acc_total = (kProf ? clock64() : 0ll);
+      const uint32_t wo_lo = ptx::umma_desc_lo(ptx::smem_u32(wout_s)), g_lo = ptx::umma_desc_lo(ptx::smem_u32(gbuf));
+      // GEMM2 of this CTA's m-th tile: D2 += G . Wout^T onto the residual the identity MMAs left there
+      auto issue_gemm2 = [&](int m) {
+        const int pm = m & 1, j = pm * 2 + ((m >> 1) & 1);  // D2 accumulator: two per epilogue group, alternating
+        if (!(flags & 4)) {
+          const uint32_t gl = g_lo + pm * (kFTile >> 4);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) ptx::umma_bf16_lo(tmem + 256 + j * 64, gl + 2 * k4, wo_lo + 2 * k4, idesc2, 1);
+          ptx::umma_commit(&bars->d2_full[j]);
+        } else {
+          ptx::mbar_arrive(&bars->d2_full[j]);
+        }
+      };
       int n = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++n) {
         const int p = n & 1;
         long long c_0 = (kProf ? clock64() : 0ll);
-        // D1[p] is free once the epilogue has gated tile n - 2 out of it
-        if (n >= 2 && !g_ready) ptx::mbar_wait(&bars->g_full[p], ((n - 2) >> 1) & 1);
+        // D1[p] is free once the epilogue has gated tile n - 2 out of it — the same event makes G[p] of tile n - 2 ready
+        // for GEMM2, which is therefore issued HERE, ahead of this tile's GEMM1.  With a thread of its own for GEMM2 both
+        // woke on the same barrier, and whenever GEMM1's 17 MMAs won the race the epilogue group waited for four N = 64
+        // MMAs queued behind them: 381 -> 365 us per fixed block.  (Measured and not kept: this thread as an event loop
+        // polling both groups' g_full while it waits, so that neither group's GEMM2 waits for the other's gating — 377 us;
+        // the polls cost more than the head-of-line blocking they remove.)
+        if (n >= 2) {
+          if (!g_ready) ptx::mbar_wait(&bars->g_full[p], ((n - 2) >> 1) & 1);
+          ptx::tc_fence_after();
+          issue_gemm2(n - 2);
+        }
         long long c_1 = (kProf ? clock64() : 0ll);
         acc_g += c_1 - c_0;
         if (!full_ready) ptx::mbar_wait(&bars->full[p], (n >> 1) & 1);
@@ -217,6 +247,11 @@ usfgan_block_fr_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
           full_ready = g_ready = false;
         }
         acc_mma += (kProf ? clock64() : 0ll) - c_0;
+      }
+      for (int m = n >= 2 ? n - 2 : 0; m < n; ++m) {  // GEMM2 of the last two tiles
+        ptx::mbar_wait(&bars->g_full[m & 1], (m >> 1) & 1);
+        ptx::tc_fence_after();
+        issue_gemm2(m);
       }
       if (kProf && a.dbg) {
         a.dbg[blockIdx.x * 16 + 1] = acc_full;  // GEMM1 thread: waiting for operands
@@ -281,11 +316,25 @@ usfgan_block_fr_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             }
           }
           const bool ok = src >= 0 && src < T;
-          const uint8_t* g = reinterpret_cast<const uint8_t*>(a.xb_in + ((size_t)b * T + (ok ? src : 0)) * 64);
           uint8_t* dst = slot + side * 2 * kFTile;
+          // F0 is constant over a hop, so the pitch-dependent taps of most 8-row groups are 8 CONSECUTIVE source rows:
+          // such a group (one 1 KB swizzle atom of the tile) travels as one TMA box issued by its first lane — its bytes
+          // are added to the phase's expected count before this thread's own arrival, so the phase cannot close early —
+          // and only the groups that straddle a frame boundary, a reflection or the end of the track are gathered row by
+          // row (16 cp.async per thread and tile were 1.7 k of the adaptive blocks' 4.1 k cycles per tile).
+          const int base = __shfl_sync(0xffffffffu, src, lane & ~7);
+          const unsigned lin = __ballot_sync(0xffffffffu, ok && src == base + (lane & 7));
+          if (((lin >> (lane & ~7)) & 0xffu) == 0xffu && !(flags & 64)) {
+            if ((lane & 7) == 0) {
+              fr_mbar_expect_tx(&bars->full[st], 1024u);
+              ptx::tma_load_3d(dst + (r >> 3) * 1024, &tm_x8, &bars->full[st], 0, base, b);
+            }
+          } else {
+            const uint8_t* g = reinterpret_cast<const uint8_t*>(a.xb_in + ((size_t)b * T + (ok ? src : 0)) * 64);
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            fr_cp_async_16(dst + ptx::sw128_offset((uint32_t)r, (uint32_t)c), g + c * 16, ok ? 16u : 0u);
+            for (int c = 0; c < 8; ++c)
+              fr_cp_async_16(dst + ptx::sw128_offset((uint32_t)r, (uint32_t)c), g + c * 16, ok ? 16u : 0u);
+          }
         }
       }
       fr_cp_async_arrive_noinc(&bars->full[st]);
@@ -297,27 +346,7 @@ usfgan_block_fr_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
       a.dbg[blockIdx.x * 16 + 15] = acc_i;  // gather: issuing copies
     }
   } else if (warp == 6) {
-    // ------------------------------------------------------------------ GEMM2 issuer: D2 += G . Wout^T per tile
-    if (lane == 0) {
-      const uint32_t idesc2 = ptx::umma_idesc_bf16_f32(128, 64);
-      ptx::mbar_wait(&bars->w_full, 0);
-      ptx::tc_fence_after();
-      const uint32_t wo_lo = ptx::umma_desc_lo(ptx::smem_u32(wout_s)), g_lo = ptx::umma_desc_lo(ptx::smem_u32(gbuf));
-      int m = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++m) {
-        const int p = m & 1, j = p * 2 + ((m >> 1) & 1);  // D2 accumulator: two per epilogue group, alternating
-        ptx::mbar_wait(&bars->g_full[p], (m >> 1) & 1);
-        ptx::tc_fence_after();
-        const uint32_t gl = g_lo + p * (kFTile >> 4);
-        if (!(flags & 4)) {
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) ptx::umma_bf16_lo(tmem + 256 + j * 64, gl + 2 * k4, wo_lo + 2 * k4, idesc2, 1);
-          ptx::umma_commit(&bars->d2_full[j]);
-        } else {
-          ptx::mbar_arrive(&bars->d2_full[j]);
-        }
-      }
-    }
+    // (idle: GEMM2 is issued by the GEMM1 thread, see there)
   } else {
     // ------------------------------------------------------------------ epilogue: two groups of 8 warps; group p owns the
     // tiles n with n & 1 == p and with them D1[p], G[p] and the D2 pair 2p, 2p+1 — the groups share no buffer.
@@ -456,13 +485,15 @@ int usfgan_block_fr_launch(const svsk_usfgan_block_params& p, void* stream) {
                "usfgan_block_bf16: aux_q rows hold columns 0..%d, the tiles read %d..%d", p.q_ld - 1, p.q_fpad + fb_first,
                p.q_fpad + fb_last + 15);
   int rc;
-  CUtensorMap tm_x, tm_w1, tm_wout, tm_xout;
+  CUtensorMap tm_x, tm_w1, tm_wout, tm_xout, tm_x8;
   {
     uint64_t dims[3] = {64, (uint64_t)p.T, (uint64_t)p.B};
     uint64_t str[2] = {128, (uint64_t)p.T * 128};
     uint32_t box[3] = {64, 128, 1};
     uint32_t box_q[3] = {64, 32, 1};  // stores go out per TMEM lane quarter: 32 rows
+    uint32_t box_8[3] = {64, 8, 1};   // side taps of gathered tiles: one swizzle atom (8 consecutive source rows)
     if ((rc = make_tmap_bf16(&tm_x, p.xb_in, 3, dims, str, box))) return rc;
+    if ((rc = make_tmap_bf16(&tm_x8, p.xb_in, 3, dims, str, box_8))) return rc;
     if ((rc = make_tmap_bf16(&tm_xout, p.xb_out, 3, dims, str, box_q))) return rc;
   }
   {
@@ -512,9 +543,9 @@ int usfgan_block_fr_launch(const svsk_usfgan_block_params& p, void* stream) {
   if (const char* e = getenv("SVSK_USFGAN_TIMELINE")) a.dbg = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
   const int grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
   if (a.dbg || a.dbg_flags)  // clock64 role accounting (distorts the timing) and / or ablation flags
-    usfgan_block_fr_kernel<true><<<grid, kFThreads, smem_bytes, as_stream(stream)>>>(tm_x, tm_w1, tm_wout, tm_xout, a);
+    usfgan_block_fr_kernel<true><<<grid, kFThreads, smem_bytes, as_stream(stream)>>>(tm_x, tm_w1, tm_wout, tm_xout, tm_x8, a);
   else
-    usfgan_block_fr_kernel<false><<<grid, kFThreads, smem_bytes, as_stream(stream)>>>(tm_x, tm_w1, tm_wout, tm_xout, a);
+    usfgan_block_fr_kernel<false><<<grid, kFThreads, smem_bytes, as_stream(stream)>>>(tm_x, tm_w1, tm_wout, tm_xout, tm_x8, a);
   return check_launch("usfgan_block_bf16 (frame-rate aux)");
 }
 

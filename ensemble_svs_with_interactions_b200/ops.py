@@ -506,7 +506,9 @@ def usfgan_aux_frames(cin_ntc, w_all, Tf, T, hop, reach):
     fpad = -L.lib().svsk_usfgan_frame_base(0, int(reach), int(hop))
     last = L.lib().svsk_usfgan_frame_base((T - 1) // 128 * 128, int(reach), int(hop))
     q_ld = (max(fpad + Tf, fpad + last + 16) + 7) // 8 * 8
-    q = torch.zeros((B, R, q_ld), device=cin_ntc.device, dtype=bf16)
+    q = torch.empty((B, R, q_ld), device=cin_ntc.device, dtype=bf16)   # 0.5 GB at config 3: only the pad columns are zeroed
+    q[:, :, :fpad].zero_()
+    q[:, :, fpad + Tf:].zero_()
     L.check(L.lib().svsk_usfgan_aux_frames(L.ptr(cin_ntc, bf16, "cin"), L.ptr(w_all, bf16, "w_all"), L.ptr(q), B, Tf, Ap, R,
                                            q_ld, fpad, L.stream_ptr()), "usfgan_aux_frames")
     return q, fpad

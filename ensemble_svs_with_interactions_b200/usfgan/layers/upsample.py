@@ -86,8 +86,7 @@ class ConvInUpsampleNetwork(torch.nn.Module):
     def supports_fused(self):
         return self.upsample.supports_fused(self.conv_in.out_channels)
 
-    def forward_ntc_bf16(self, c):
-        """c (B, C, T' + 2*window) -> (B, T' * prod(scales), C rounded up to 8) bf16, no fp32 sample-rate intermediate."""
-        c = ops.conv1d_f32(c.to(torch.float32).contiguous(), effective_weight(self.conv_in), None,
-                           pad_mode=ops.PAD_VALID)
-        return self.upsample.forward_ntc(c)[0]
+    def forward_ntc_bf16(self, c, cin=None):
+        """c (B, C, T' + 2*window) -> (B, T' * prod(scales), C rounded up to 8) bf16, no fp32 sample-rate intermediate.
+        ``cin`` = conv_in_frames(c) if the caller already has it."""
+        return self.upsample.forward_ntc(self.conv_in_frames(c) if cin is None else cin)[0]

@@ -63,7 +63,7 @@ class _GeneratorBase(nn.Module):
     # 16-frame window (any hop >= 54 with the recipes' scale lists); "samples": always stream the upsampled features
     aux_projection = "auto"
 
-    def _aux_frames(self, c, T, stacks):
+    def _aux_frames(self, c, T, stacks, cin=None):
         """ops.UsfganAuxFrames for ``stacks`` (block index = position in the concatenation of their blocks), or None when
         the sample-rate path has to be used.  conv1x1_aux(upsample(conv_in(c))) = U . (conv1x1_aux(conv_in(c))): Q is one
         bf16 GEMM at frame rate for all blocks, U the upsampler's impulse responses (cached per frame count)."""
@@ -79,7 +79,8 @@ class _GeneratorBase(nn.Module):
             return None
         if self.aux_projection not in ("auto", "frames"):
             raise RuntimeError(f"unknown aux_projection {self.aux_projection!r}")
-        cin = up.conv_in_frames(c)                                  # [B, A, Tf] fp32
+        if cin is None:
+            cin = up.conv_in_frames(c)                              # [B, A, Tf] fp32
         B, A, Tf = cin.shape
         if Tf * hop != T:
             raise RuntimeError(f"aux features give {Tf} x {hop} samples, the source signal has {T}")
@@ -298,17 +299,18 @@ class CascadeHnUSFGANGenerator(_HnBase):
         if wave_only and self._ntc_fast_path_ok() and self.conv_merge.in_channels % 8 == 0 and self.conv_merge.out_channels % 16 == 0:
             # NTC bf16 throughout, like ParallelHnUSFGANGenerator's wave-only path.  s = a h + (1 - a) n is formed from the
             # two stacks' raw outputs in one pass; a h alone is only needed as the merge conv's input.
+            cin = self.upsample_net.conv_in_frames(c)   # once: the periodicity estimator's input and the blocks' Q share it
             if self.upsample_net.supports_fused():
-                auxb = self.upsample_net.forward_ntc_bf16(c)
+                auxb = self.upsample_net.forward_ntc_bf16(c, cin=cin)
             else:
-                auxb = self._aux_ntc(self.upsample_net(c))
+                auxb = self._aux_ntc(self.upsample_net.upsample(cin))
             assert auxb.size(1) == x.size(-1)
             ab = self.periodicity_estimator.forward_ntc_bf16(auxb)
             xf = x.to(f32).contiguous()
             hb = _conv1x1_expand_ntc(self.conv_first_sine, xf[:, 0])
             nb = _conv1x1_expand_ntc(self.conv_first_noise, xf[:, 1])
             nets = [self.harmonic_network, self.noise_network, self.filter_network]
-            frames = self._aux_frames(c, x.size(-1), nets)
+            frames = self._aux_frames(c, x.size(-1), nets, cin=cin)
             first = [0, len(nets[0].conv_dilated), len(nets[0].conv_dilated) + len(nets[1].conv_dilated)]
             hb = self.harmonic_network.forward_ntc_bf16(hb, auxb, d, cache, frames=frames, frames_block0=first[0])
             zeros = torch.zeros_like(hb)
@@ -359,17 +361,18 @@ class ParallelHnUSFGANGenerator(_HnBase):
         if wave_only and self._ntc_fast_path_ok():
             # everything stays NTC bf16: the aux features are upsampled straight into that layout (one pass over all
             # stages), the two 1 -> C input convs write it directly
+            cin = self.upsample_net.conv_in_frames(c)   # once: the periodicity estimator's input and the blocks' Q share it
             if self.upsample_net.supports_fused():
-                auxb = self.upsample_net.forward_ntc_bf16(c)
+                auxb = self.upsample_net.forward_ntc_bf16(c, cin=cin)
             else:
-                auxb = self._aux_ntc(self.upsample_net(c))
+                auxb = self._aux_ntc(self.upsample_net.upsample(cin))
             assert auxb.size(1) == x.size(-1)
             ab = self.periodicity_estimator.forward_ntc_bf16(auxb)
             xf = x.to(f32).contiguous()
             hb = _conv1x1_expand_ntc(self.conv_first_sine, xf[:, 0])
             nb = _conv1x1_expand_ntc(self.conv_first_noise, xf[:, 1])
             nets = [self.harmonic_network, self.noise_network, self.filter_network]
-            frames = self._aux_frames(c, x.size(-1), nets)
+            frames = self._aux_frames(c, x.size(-1), nets, cin=cin)
             first = [0, len(nets[0].conv_dilated), len(nets[0].conv_dilated) + len(nets[1].conv_dilated)]
             hb = self.harmonic_network.forward_ntc_bf16(hb, auxb, d, cache, frames=frames, frames_block0=first[0])
             nb = self.noise_network.forward_ntc_bf16(nb, auxb, d, cache, frames=frames, frames_block0=first[1])

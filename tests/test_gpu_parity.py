@@ -767,7 +767,12 @@ def _aux_frames_operands(ops, net, cin, w_aux_blocks, scales):
 @pytest.mark.parametrize("scales,Tf,dil,adaptive,A", [([5, 4, 3, 2], 9, 1, False, 80), ([5, 4, 3, 2], 50, 64, False, 80),
                                                       ([5, 4, 3, 2], 50, 4, True, 80), ([4, 4, 4], 33, 2, False, 72),
                                                       ([5, 4, 3, 2], 1, 8, False, 80), ([5, 4, 3, 2], 2, 1, True, 65),
-                                                      ([5, 4, 3, 2], 3001, 512, False, 80), ([5, 4, 3, 2], 3001, 16, True, 80)])
+                                                      ([5, 4, 3, 2], 3001, 512, False, 80), ([5, 4, 3, 2], 3001, 16, True, 80),
+                                                      # "hop": dilation factors constant over a hop, as USFGANWrapper makes
+                                                      # them -> most 8-row tap groups travel as TMA boxes, the ones that
+                                                      # straddle a frame / the track's ends row by row
+                                                      ([5, 4, 3, 2], 50, 4, "hop", 80), ([5, 4, 3, 2], 3001, 16, "hop", 80),
+                                                      ([4, 4, 4], 33, 1, "hop", 72), ([5, 4, 3, 2], 2, 64, "hop", 65)])
 def test_usfgan_block_bf16_frame_rate_aux(scales, Tf, dil, adaptive, A):
     """The block kernel with the aux projection taken at frame rate (aux_u / aux_q operands) against the oracle's block on
     the UPSAMPLED aux features, and the two operand kernels against their definitions."""
@@ -789,7 +794,10 @@ def test_usfgan_block_bf16_frame_rate_aux(scales, Tf, dil, adaptive, A):
     w_aux = torch.randn(128, A, 1, generator=g) / math.sqrt(A)
     w_other = torch.randn(128, A, generator=g)
     w_out = torch.randn(64, 64, 1, generator=g) / 8; b_out = torch.randn(64, generator=g) * 0.1
-    if adaptive:
+    if adaptive == "hop":
+        d = torch.empty(B, 1, Tf).uniform_(0.7, 9.0, generator=g).repeat_interleave(hop, dim=-1).contiguous()
+        taps = O.pd_gather(_bf(x), d, dil)
+    elif adaptive:
         d = torch.empty(B, 1, T).uniform_(0.7, 9.0, generator=g)
         taps = O.pd_gather(_bf(x), d, dil)
     else:

@@ -17,9 +17,12 @@ wt, wa, wo = torch.randn(128, 64, 3, device="cuda") * 0.05, torch.randn(128, 80,
 w1p_s, woutp = ops.usfgan_pack_block(wt, wa, wo)
 w1p_f, _ = ops.usfgan_pack_block(wt, None, wo)
 b1 = torch.zeros(128, device="cuda"); bo = torch.zeros(64, device="cuda")
-d = torch.empty(B, 1, T, device="cuda").uniform_(2, 40)
-idx = ops.pd_index(d, 4)
 Tf = T // HOP
+# dilation factors as the wrapper makes them: constant over a hop (F0 is frame-level) -> most 8-row groups of a tile have
+# consecutive source rows; "adaptive rnd" draws them per sample (no such group: every row is gathered by cp.async)
+d = torch.empty(B, 1, Tf, device="cuda").uniform_(2, 40).repeat_interleave(HOP, dim=-1).contiguous()
+idx = ops.pd_index(d, 4)
+idx_rnd = ops.pd_index(torch.empty(B, 1, T, device="cuda").uniform_(2, 40), 4)
 cinb = torch.randn(B, Tf, 80, device="cuda").to(bf)
 w_all = torch.randn(3 * 128, 80, device="cuda").to(bf)
 q, fpad = ops.usfgan_aux_frames(cinb, w_all, Tf, T, HOP, REACH)
@@ -48,15 +51,16 @@ def timed(mode, **kw):
 
 
 os.environ.pop("SVSK_USFGAN_ABLATE", None)
-for name, kw in (("fixed d=8", dict(dilation=8)), ("fixed d=512", dict(dilation=512)), ("adaptive", dict(idx=idx))):
+for name, kw in (("fixed d=8", dict(dilation=8)), ("fixed d=512", dict(dilation=512)), ("adaptive", dict(idx=idx)),
+                 ("adaptive rnd", dict(idx=idx_rnd))):
     for mode in ("samples", "frames", "samples", "frames"):
         us = timed(mode, **kw)
         print(f"{name:12s} {mode:8s}: {us:7.1f} us -> {us * 1e-6 * 1.85e9 / ntile:6.0f} cycles/tile", flush=True)
 for name, kw in (("fixed d=8", dict(dilation=8)), ("adaptive", dict(idx=idx))):
-    for ab in (1, 4, 5, 2, 8, 16, 2 + 8 + 16):
+    for ab in (1, 4, 5, 2, 8, 16, 2 + 8 + 16, 64):
         os.environ["SVSK_USFGAN_ABLATE"] = str(ab)
         us = timed("frames", **kw)
-        print(f"{name:12s} frames ablate={ab} (1=no epilogue, 2=no MUFU, 4=no MMAs, 8=no st.global, 16=no LDTM): {us:7.1f} us -> {us * 1e-6 * 1.85e9 / ntile:6.0f} cycles/tile", flush=True)
+        print(f"{name:12s} frames ablate={ab} (1=no epilogue, 2=no MUFU, 4=no MMAs, 8=no st.global, 16=no LDTM, 64=no TMA tap groups): {us:7.1f} us -> {us * 1e-6 * 1.85e9 / ntile:6.0f} cycles/tile", flush=True)
     os.environ.pop("SVSK_USFGAN_ABLATE")
 
 names = {0: "prod wait empty", 1: "mma wait operands", 2: "mma wait G", 3: "mma loop total", 13: "mma issue+commit",
