@@ -697,6 +697,25 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
 
 using namespace svsk;
 
+namespace svsk {  // diffnet_stack_duo_sm100.cu: C = 128 with two tiles per CTA pair
+bool diffnet_stack_duo_applies(int C, int H);
+int diffnet_stack_duo_fits(int B, int T);
+int diffnet_stack_duo_launch(const svsk_diffnet_stack_params& p, void* stream);
+}  // namespace svsk
+
+static int stack_one_tile_fits(int B, int T, int C, int H);
+
+// C = 128: two tiles per CTA pair as soon as the one-tile kernel cannot hold the whole batch on the device at once — a
+// 6 x 6000 batch is 288 one-tile CTAs = two launches of 245 us in all, but 144 two-tile CTAs = one launch of 164 us.
+// A batch that does fit stays with one tile per pair: each slot's chain is no shorter with two tiles, so on a device that
+// is not full the kernel that spreads the tiles over twice as many SMs is the faster one (6 x 2000: 100 vs 140 us).
+// SVSK_STACK_DUO=1 forces the two-tile kernel wherever it applies (tests, A/B), SVSK_STACK_NO_DUO=1 disables it.
+static bool stack_use_duo(int B, int C, int H, int T) {
+  if (!diffnet_stack_duo_applies(C, H)) return false;
+  if (getenv("SVSK_STACK_DUO")) return true;
+  return stack_one_tile_fits(B, T, C, H) != 1;
+}
+
 static int stack_smem(int C, int H, int* nentries_out, int* cond_resident_out = nullptr) {
   const int CB = C / 64, HB = H / 64;
   int gc_tiles = HB > CB ? HB : CB;
@@ -773,11 +792,8 @@ static void stack_launch_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at
   cfg->numAttrs = getenv("SVSK_STACK_NO_COOPERATIVE") ? 1 : 2;
 }
 
-extern "C" int svsk_diffnet_stack_fits(int B, int T, int C, int H) {
+static int stack_one_tile_fits(int B, int T, int C, int H) {
   int nentries = 0, smem_bytes = 0;
-  int rc = require_sm100();
-  if (rc) return -1;
-  if (B <= 0 || T <= 0 || B > 65535) return 0;
   if (stack_prepare(C, H, &nentries, &smem_bytes)) return 0;
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[2];
@@ -788,6 +804,14 @@ extern "C" int svsk_diffnet_stack_fits(int B, int T, int C, int H) {
     return 0;
   }
   return (int)(cfg.gridDim.x / attr[0].val.clusterDim.x) * B <= max_clusters ? 1 : 0;
+}
+
+extern "C" int svsk_diffnet_stack_fits(int B, int T, int C, int H) {
+  int rc = require_sm100();
+  if (rc) return -1;
+  if (B <= 0 || T <= 0 || B > 65535) return 0;
+  if (stack_use_duo(B, C, H, T)) return diffnet_stack_duo_fits(B, T);
+  return stack_one_tile_fits(B, T, C, H);
 }
 
 extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void* stream) {
@@ -809,6 +833,7 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
                "diffnet_stack_bf16: skip32 / edge0 / edge1 must be 16-byte aligned");
   int rc = require_sm100();
   if (rc) return rc;
+  if (stack_use_duo(p.B, p.C, p.H, p.T)) return diffnet_stack_duo_launch(p, stream);
   int nentries = 0, smem_bytes = 0, cond_resident = 0;
   if ((rc = stack_prepare(p.C, p.H, &nentries, &smem_bytes, &cond_resident))) return rc;
 

@@ -440,6 +440,48 @@ def test_diffnet_stack_matches_per_layer_kernels(C, H, M, L, B, T):
     assert torch.equal(y, y2)
 
 
+@pytest.mark.parametrize("H,M,L,B,T", [(128, 5, 10, 6, 6000), (128, 5, 6, 3, 517), (64, 16, 3, 2, 2049), (128, 5, 4, 1, 100),
+                                       (128, 60, 5, 4, 512), (64, 5, 2, 2, 257), (128, 5, 3, 5, 1281)])
+def test_diffnet_stack_two_tiles_per_pair_c128(H, M, L, B, T):
+    """C = 128: the kernel with two 256-frame tiles per CTA pair (diffnet_stack_duo_sm100.cu; what a batch runs that the
+    one-tile kernel cannot hold on the device at once, e.g. the pipeline's 6 x 6000 bap batches) against the one-tile
+    kernel — BIT-identical: same MMAs in the same order, same epilogue arithmetic — and against the layer-at-a-time
+    kernels; per-track diffusion steps (step biases follow their tracks), odd tile counts, ragged ends."""
+    import os
+    m = _random_diffnet(128, H, M, L, seed=H + L + T).to(DEV)
+    g = torch.Generator().manual_seed(T)
+    spec = torch.randn(B, 1, M, T, generator=g).to(DEV); cond = torch.randn(B, H, T, generator=g).to(DEV)
+    t = torch.randint(0, 100, (B,), generator=g).to(DEV)
+    from ensemble_svs_with_interactions_b200.diffsinger import denoiser as den_mod
+
+    def run(**env):
+        for k_, v_ in env.items():
+            os.environ[k_] = v_
+        den_mod._STACK_FIT_CACHE.clear()
+        try:
+            return m(spec, t, cond)
+        finally:
+            for k_ in env:
+                os.environ.pop(k_)
+            den_mod._STACK_FIT_CACHE.clear()
+
+    duo = run(SVSK_STACK_DUO="1")
+    one = run(SVSK_STACK_NO_DUO="1")
+    ref = run(SVSK_DIFFNET_STACK="0")
+    assert torch.isfinite(duo).all()
+    assert torch.equal(duo, one)
+    close_bf16(duo, ref, 1e-2, 3e-2)
+    assert torch.equal(run(SVSK_STACK_DUO="1"), duo)       # deterministic
+    if (B, T) == (6, 6000):                                 # ... and it is what this batch gets by default: one launch
+        n0 = _launches()
+        auto = m(spec, t, cond)
+        n_auto = _launches() - n0
+        n0 = _launches()
+        run(SVSK_STACK_NO_DUO="1")
+        assert n_auto == (_launches() - n0) - 1, "6 x 6000 at C = 128 should be ONE stack launch instead of two"
+        assert torch.equal(auto, duo)
+
+
 @pytest.mark.parametrize("C,H,M,L", [(128, 192, 60, 3), (256, 64, 33, 2)])
 @pytest.mark.parametrize("B,T", [(1, 1), (2, 7), (3, 9), (2, 129), (1, 257), (2, 2049)])
 def test_diffnet_sampling_odd_shapes(C, H, M, L, B, T):
