@@ -15,7 +15,7 @@
 // batch is 144 virtual pairs = 72 CTA pairs: ONE launch instead of two.
 //
 // Halo rows always travel through global memory + per-tile layer counters here (any track length); the two slots of a
-// pair are adjacent virtual pairs of one track.  All CTAs must be co-resident (cooperative launch), as in the C = 256
+// pair are virtual pairs half a track apart.  All CTAs must be co-resident (cooperative launch), as in the C = 256
 // kernel's global-memory mode.
 //
 // Warps: 0 = weight producer, 1 = MMA issuer (leader CTA) / forwarder (peer) + TMEM owner, then 4 kDW epilogue warps per
@@ -51,7 +51,9 @@ struct DuoArgs {
   int* flags;             // [B * tiles_per_track] layers published per 128-frame tile; zero at launch
   int B, T, H, L, sb_batch_stride, sb_layer_stride, init_skip, nentries, tiles_per_track;
   int dilation[kDMaxLayers];
+  unsigned long long* dbg;  // SVSK_DIFFNET_TIMELINE: [CTA][64] clock64 stamps of layer kDStampLayer (32 per slot), leader CTAs
 };
+constexpr int kDStampLayer = 4;
 
 struct __align__(8) DuoSlotBarriers {
   uint64_t cd_full[2];   // conditioner tile hb of this layer landed (leader: in both CTAs)
@@ -109,9 +111,18 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
   const int pair = blockIdx.x >> 1;
   const int w_row0 = (int)rank * 128;  // this CTA's half of the 256-row weight block
   const int n_g1 = 3 * kDCB + HB;      // ring entries of one slot's GEMM1
-  // slot u works on the virtual pair 2 * pair + u: frames [vp * 256, vp * 256 + 256), this CTA its half
-  const bool live1 = (2 * pair + 1) * 256 < T;  // (slot 0 is always live: the grid has ceil(n256 / 2) pairs per track)
+  // Slot u works on the virtual pair vp = pair + u * (pairs per track): frames [vp * 256, vp * 256 + 256), this CTA its
+  // half.  NOT 2 * pair + u: with adjacent slots, slot 0 waits every layer for the edge rows of slot 1 of its own pair,
+  // whose MMAs are issued after its own — a circular coupling that made the layer period the sum of both slots' chains
+  // (26.5 k cycles, profiles/r02n_stack_duo_timeline.log).  This way slot 0's neighbours are the slots 0 of the
+  // neighbouring pairs (the same phase of the same schedule) and the two families only meet once per track.
+  const int npairs = (int)(gridDim.x >> 1);
+  const int vp0 = pair, vp1 = pair + npairs;
+  const bool live1 = vp1 * 256 < T;  // (slot 0 is always live: the grid has ceil(n256 / 2) pairs per track)
   const int n_slots = live1 ? 2 : 1;
+  unsigned long long* dbg = a.dbg ? a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;
+#define DUO_STAMP(l_, u_, i_) do { if (dbg && (l_) == kDStampLayer) dbg[(u_) * 32 + (i_)] = clock64(); } while (0)
+  if (dbg && threadIdx.x == 0) dbg[63] = clock64();
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_xw0);
@@ -179,7 +190,7 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
       DuoSlotBarriers* sb = &bars->s[u];
       uint8_t* xw_smem = smem + u * kDSlotBytes;
       uint8_t* g_smem = xw_smem + kDCB * kDWinBytes;
-      const int t_cta0 = (2 * pair + u) * 256 + (int)rank * 128;
+      const int t_cta0 = (u ? vp1 : vp0) * 256 + (int)rank * 128;
       const int tile_idx = b * a.tiles_per_track + (t_cta0 >> 7);
       // (the peer's half of the last virtual pair may lie wholly past the end of the track: its stores are clipped, its
       // counter exists — tiles_per_track counts both halves — and nobody waits for it)
@@ -197,6 +208,7 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
         const CUtensorMap* tm_e = pp ? &tm_e1 : &tm_e0;
         // publish the first / last 8 rows of layer l-1's output (the epilogue has written them in place)
         ptx::mbar_wait(&sb->xe_ready, pp);
+        DUO_STAMP(l, u, 0);   // layer l-1's centre rows written (activation producer)
         for (int cb = 0; cb < kDCB; ++cb) {
           uint8_t* centre = xw_smem + cb * kDWinBytes + kDHalo * 128;
           ptx::tma_store_3d(tm_e, centre, cb * 64, t_cta0, b);
@@ -204,8 +216,10 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
         }
         ptx::bulk_commit_group();
         ptx::bulk_wait_all();  // the stores are complete (not merely read out of shared memory)
+        DUO_STAMP(l, u, 1);   // edge rows stored
         duo_fence_proxy_async_global();
         duo_st_release_gpu(a.flags + tile_idx, l);
+        DUO_STAMP(l, u, 2);   // flag published
         // halo rows of layer l's input: the neighbours' edge rows of layer l-1's output
         for (uint32_t spin = 0;; ++spin) {  // both flags per round trip, relaxed; one acquire fence at the end
           const int fl = has_left ? duo_ld_relaxed_gpu(a.flags + tile_idx - 1) : l;
@@ -213,8 +227,13 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
           if (fl >= l && fr >= l) break;
           if (spin > (1u << 21)) __trap();
         }
+        DUO_STAMP(l, u, 3);   // neighbours' flags seen
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
         duo_fence_proxy_async_global();
+        DUO_STAMP(l, u, 4);   // fences done, halo loads issued next
+        // (Measured and not kept: fetching the 4 KB of halo rows with ld.global.cg by the whole warp + st.shared instead of
+        // TMA, which saves the second fence — 141.8 vs 135.4 us per launch: an L2 round trip under this load is ~2 k cycles
+        // whoever issues it.)
         ptx::mbar_arrive_expect_tx(&sb->xw_full, 2 * kDCB * kDHaloBytes);
         for (int cb = 0; cb < kDCB; ++cb) {
           uint8_t* tile = xw_smem + cb * kDWinBytes;
@@ -223,6 +242,7 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
         }
         // conditioner tiles of layer l, once the G buffer is free again
         ptx::mbar_wait(&sb->gc_free, pp);
+        DUO_STAMP(l, u, 5);   // G buffer free: conditioner tiles requested
         for (int hb = 0; hb < HB; ++hb) {
           ptx::mbar_arrive_expect_tx(&sb->cd_full[hb], kDTile);
           ptx::tma_load_3d(g_smem + hb * kDTile, &tm_cond, &sb->cd_full[hb], hb * 64, t_cta0, b);
@@ -268,6 +288,7 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
             ptx::mbar_wait(&sb->d2_drained, pp);  // ... and the accumulator read out (residual and skip halves)
           }
           ptx::tc_fence_after();
+          DUO_STAMP(l, u, 8);   // MMA thread: centre rows + accumulator ready
           for (int cb = 0; cb < kDCB; ++cb) {
             DUO_WAIT_ENTRY();
             DUO_ISSUE4(tb, xw_lo + cb * (kDWinBytes >> 4) + kDHalo * 8, cb != 0);
@@ -276,6 +297,7 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
             ptx::mbar_wait(&sb->xw_full, pl);
             ptx::tc_fence_after();
           }
+          DUO_STAMP(l, u, 9);   // MMA thread: halo rows landed
           for (int jt = 0; jt < 3; jt += 2) {
             const uint32_t row_lo = xw_lo + (uint32_t)(kDHalo + (jt - 1) * d) * 8u;
             for (int cb = 0; cb < kDCB; ++cb) {
@@ -290,6 +312,7 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
             DUO_ISSUE4(tb, g_lo + hb * (kDTile >> 4), 1);
           }
           ptx::umma_commit2_mc(&sb->d1_full, pair_mask);
+          DUO_STAMP(l, u, 10);  // MMA thread: GEMM1 issued
         }
         for (int u = 0; u < n_slots; ++u) {  // ---- GEMM2 of slot u
           DuoSlotBarriers* sb = &bars->s[u];
@@ -297,11 +320,13 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
           const uint32_t tb = (uint32_t)u * 256u;
           ptx::mbar_wait(&sb->g_ready, pl);
           ptx::tc_fence_after();
+          DUO_STAMP(l, u, 11);  // MMA thread: G ready
           for (int kb = 0; kb < kDKB2; ++kb) {
             DUO_WAIT_ENTRY();
             DUO_ISSUE4(tb, g_lo + kb * (kDTile >> 4), kb != 0);
           }
           ptx::umma_commit2_mc(&sb->d2_full, pair_mask);
+          DUO_STAMP(l, u, 12);  // MMA thread: GEMM2 issued
         }
       }
 #undef DUO_WAIT_ENTRY
@@ -354,7 +379,7 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
       const int q = warp & 3;  // TMEM lane quarter this warp may read
       const int row = q * 32 + lane;
       const int et = (int)threadIdx.x - 64 - u * kDEpi;  // 0..127 within the slot's epilogue threads
-      const int t_cta0 = (2 * pair + u) * 256 + (int)rank * 128;
+      const int t_cta0 = (u ? vp1 : vp0) * 256 + (int)rank * 128;
       const int t = t_cta0 + row;
       const bool in_seq = t < T;
       const uint32_t tcol = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)u * 256u;
@@ -385,6 +410,7 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
         // ---- epilogue 1: gating -> G  (accumulator columns [0,128) gate, [128,256) filter)
         ptx::mbar_wait(&sb->d1_full, pl);
         ptx::tc_fence_after();
+        if (et == 0) DUO_STAMP(l, u, 16);  // epilogue: D1 complete
         {
           uint32_t rgb[2][16], rfb[2][16];
           ptx::tmem_ld16(tcol + 16 * sub, rgb[0]);
@@ -431,11 +457,13 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
         ptx::tc_fence_before();
         ptx::fence_proxy_async_smem();  // G (generic-proxy stores) -> visible to the tensor cores' async proxy
         ptx::mbar_arrive_cluster(gr_leader);
+        if (et == 0) DUO_STAMP(l, u, 17);  // epilogue: gated (this thread)
 
         // ---- epilogue 2: residual (columns [0,128)) -> in place over the window's centre rows (the next layer's centre
         //      tap); skip (columns [128,256)) -> fp32 slabs in the G buffer -> TMA reduce-add (plain store on layer 0)
         ptx::mbar_wait(&sb->d2_full, pl);
         ptx::tc_fence_after();
+        if (et == 0) DUO_STAMP(l, u, 18);  // epilogue: D2 complete
         if (!last) {
           if (l == 0) ptx::mbar_wait(&sb->xw_full, 0);  // (long complete) makes the TMA-written window visible here
           uint32_t rr[2][16];
@@ -469,6 +497,7 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
           ptx::fence_proxy_async_smem();
           ptx::mbar_arrive_cluster(xc_leader);  // the next layer's centre tap is waiting for this
           ptx::mbar_arrive(&sb->xe_ready);
+          if (et == 0) DUO_STAMP(l, u, 19);  // epilogue: residual written (this thread)
         }
         // skip: 4 slabs of 32 columns (one 128-byte fp32 row per frame); the kDW warps of a lane quarter alternate slabs,
         // each stages its 32 rows of a slab in its own 4 KB piece of a G tile and issues its own TMA reduce-add
@@ -513,6 +542,7 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
             ptx::mbar_arrive(&sb->gc_free);
           }
         }
+        if (et == 0) DUO_STAMP(l, u, 20);  // epilogue: skip slabs handed to the TMA unit
         ptx::tc_fence_before();
         ptx::mbar_arrive_cluster(dr_leader);
         // the bias arrays are rewritten at the top of the next layer: every epilogue thread of the slot must be done with them
@@ -525,6 +555,8 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
   __syncthreads();
   ptx::cluster_sync_all();  // the peer's smem / TMEM are in use by the leader's MMAs until here
   if (warp == 1) ptx::tmem_dealloc2(tmem, 512);
+  if (dbg && threadIdx.x == 0) dbg[62] = clock64();
+#undef DUO_STAMP
 }
 
 static int duo_smem(int H, int* nentries_out) {
@@ -647,6 +679,8 @@ int diffnet_stack_duo_launch(const svsk_diffnet_stack_params& p, void* stream) {
   a.nentries = nentries;
   a.tiles_per_track = 2 * ceil_div(p.T, 256);
   for (int l = 0; l < kDMaxLayers; ++l) a.dilation[l] = l < p.L ? p.dilation[l] : 1;
+  a.dbg = nullptr;
+  if (const char* e = getenv("SVSK_DIFFNET_TIMELINE")) a.dbg = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
 
   cudaError_t e = cudaMemsetAsync(p.flags, 0, sizeof(int) * (size_t)p.B * a.tiles_per_track, as_stream(stream));
   if (e != cudaSuccess) return fail((int)e, "diffnet_stack_bf16: flag reset: %s", cudaGetErrorString(e));
