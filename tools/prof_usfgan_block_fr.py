@@ -15,7 +15,8 @@ out = torch.empty_like(xb)
 wt, wo = torch.randn(128, 64, 3, device="cuda") * 0.05, torch.randn(64, 64, device="cuda") * 0.1
 w1p, woutp = ops.usfgan_pack_block(wt, None, wo)
 b1 = torch.zeros(128, device="cuda"); bo = torch.zeros(64, device="cuda")
-idx = ops.pd_index(torch.empty(B, 1, T, device="cuda").uniform_(2, 40), 4)
+# dilation factors constant over a hop, as USFGANWrapper makes them (most 8-row tap groups then travel as TMA boxes)
+idx = ops.pd_index(torch.empty(B, 1, T // HOP, device="cuda").uniform_(2, 40).repeat_interleave(HOP, dim=-1).contiguous(), 4)
 Tf = T // HOP
 q, fpad = ops.usfgan_aux_frames(torch.randn(B, Tf, 80, device="cuda").to(bf), torch.randn(128, 80, device="cuda").to(bf), Tf, T, HOP, REACH)
 frames = ops.UsfganAuxFrames((torch.rand((T + 127) // 128 * 128, 16, device="cuda") * 0.2).to(bf), q, fpad, HOP, REACH)
