@@ -3,11 +3,15 @@
 // convs of conv_last (nnsvs/usfgan/models/generator.py:461-466).
 //   y[b][t][co] = act( bias[co] + sum_j sum_ci w[co][ci][j] * x[b][src_j(t)][ci] ),  src_j(t) = t + (j - origin)*dilation
 // Persistent CTAs over 128-sample tiles (time = MMA M, Cout = N <= 256).  The packed weights stay resident in shared
-// memory; taps stream through a TMA ring (zero padding = TMA OOB fill).  Replicate / reflect padding only differs from a
-// shifted copy on tiles that touch a sequence end: those tiles are filled row by row by four gather warps (cp.async).
-// Two TMEM accumulators let the epilogue (bias, ReLU / sigmoid, bf16, swizzled smem, TMA store) of tile n overlap the
-// MMAs of tile n+1.
+// memory; the input streams through a TMA ring (zero padding = TMA OOB fill).  When the taps span at most 32 rows
+// ((ksize - 1) * dilation: the estimator's k = 5 convs) a ring entry is a WINDOW of 128 + span rows per 64 input channels
+// and the taps are row offsets of the MMA's A descriptor, as in the DiffNet kernels: one load and one barrier round per
+// channel block instead of one per tap (the three estimator convs went 2.4 -> 1.x ms at config 3); wider taps stream one
+// shifted 128-row tile per tap.  Replicate / reflect padding only differs from a shifted copy on tiles that touch a
+// sequence end: those tiles are filled row by row by four gather warps (cp.async).  Two TMEM accumulators let the epilogue
+// (8 warps: bias, ReLU / sigmoid, bf16, swizzled smem, one TMA store per lane quarter) of tile n overlap the MMAs of n+1.
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "sm100_ptx.cuh"
 #include "svsk_common.cuh"
@@ -17,13 +21,18 @@ namespace svsk {
 
 constexpr int kCTile = 128 * 128;
 constexpr int kCMaxStages = 6;
-constexpr int kCThreads = 320;
+constexpr int kCThreads = 448;  // producer, MMA, 4 gather, 8 epilogue warps
+constexpr int kCMaxSpan = 32;    // window mode: the taps of a tile span at most this many rows
 
 struct ConvArgs {
   const __nv_bfloat16* x;
   const float* bias;
   int B, T, Cin, Cout, ksize, dilation, origin, pad_mode, act;
   int cb, kb_total, last_ksteps, nstages, tiles_per_row, total_tiles, out_chunks;
+  int window;       // 1: a ring entry is a window of win_rows rows of one channel block, taps = row offsets
+  int win_rows;     // 128 + span rounded up to 8 rows
+  int stage_bytes;  // bytes of a ring entry
+  int entries;      // ring entries per tile: cb (window) or kb_total
 };
 
 struct __align__(8) ConvBarriers {
@@ -57,7 +66,7 @@ conv1d_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   const int wtile = a.Cout * 128;                      // one weight k-block: Cout rows x 64 bf16
   uint8_t* w_s = smem;
   uint8_t* ring = w_s + ((a.kb_total * wtile + 1023) & ~1023);
-  uint8_t* obuf = ring + a.nstages * kCTile;           // 2 x out_chunks x 16 KB output staging
+  uint8_t* obuf = ring + a.nstages * a.stage_bytes;    // 2 x out_chunks x 16 KB output staging
   float* bias_s = reinterpret_cast<float*>(obuf + 2 * a.out_chunks * kCTile);
   ConvBarriers* bars = reinterpret_cast<ConvBarriers*>(bias_s + 256);
 
@@ -75,7 +84,7 @@ conv1d_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars->d_full[i], 1);
-      ptx::mbar_init(&bars->d_empty[i], 128);
+      ptx::mbar_init(&bars->d_empty[i], 256);
     }
     ptx::mbar_init(&bars->w_full, 1);
     ptx::fence_mbar_init();
@@ -99,12 +108,16 @@ conv1d_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         const int b = tile / a.tiles_per_row, t0 = (tile - b * a.tiles_per_row) * 128;
         const bool gather = conv_tile_needs_gather(t0, T, a);
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int e = 0; e < a.entries; ++e) {
           ptx::mbar_wait(&bars->empty[s], ph ^ 1);
           if (!gather) {
-            const int j = kb / a.cb, cb = kb - j * a.cb;
-            ptx::mbar_arrive_expect_tx(&bars->full_t[s], kCTile);
-            ptx::tma_load_3d(ring + s * kCTile, &tm_x, &bars->full_t[s], cb * 64, t0 + (j - a.origin) * a.dilation, b);
+            ptx::mbar_arrive_expect_tx(&bars->full_t[s], a.stage_bytes);
+            if (a.window) {
+              ptx::tma_load_3d(ring + s * a.stage_bytes, &tm_x, &bars->full_t[s], e * 64, t0 - a.origin * a.dilation, b);
+            } else {
+              const int j = e / a.cb, cb = e - j * a.cb;
+              ptx::tma_load_3d(ring + s * a.stage_bytes, &tm_x, &bars->full_t[s], cb * 64, t0 + (j - a.origin) * a.dilation, b);
+            }
           }
           if (++s == a.nstages) { s = 0; ph ^= 1; }
         }
@@ -124,7 +137,7 @@ conv1d_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         const int p = n & 1;
         ptx::mbar_wait(&bars->d_empty[p], ((n >> 1) & 1) ^ 1);  // epilogue of tile n-2 has drained this accumulator
         ptx::tc_fence_after();
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int e = 0; e < a.entries; ++e) {
           if (gather) {
             ptx::mbar_wait(&bars->full_g[s], (phg >> s) & 1);
             phg ^= 1u << s;
@@ -134,12 +147,20 @@ conv1d_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             pht ^= 1u << s;
           }
           ptx::tc_fence_after();
-          const uint32_t a0 = ptx::smem_u32(ring + s * kCTile);
-          const int cb = kb % a.cb;
-          const int ks = (cb == a.cb - 1) ? a.last_ksteps : 4;
-          for (int k4 = 0; k4 < ks; ++k4)
-            ptx::umma_bf16(tmem + p * 256, ptx::umma_desc_k_sw128(a0 + k4 * 32),
-                           ptx::umma_desc_k_sw128(wa + kb * wtile + k4 * 32), idesc, (kb | k4) != 0);
+          const uint32_t a0 = ptx::smem_u32(ring + s * a.stage_bytes);
+          if (a.window) {  // entry = channel block e: every tap is the same window read at a row offset
+            const int ks = (e == a.cb - 1) ? a.last_ksteps : 4;
+            for (int j = 0; j < a.ksize; ++j)
+              for (int k4 = 0; k4 < ks; ++k4)
+                ptx::umma_bf16(tmem + p * 256, ptx::umma_desc_k_sw128(a0 + j * a.dilation * 128 + k4 * 32),
+                               ptx::umma_desc_k_sw128(wa + (j * a.cb + e) * wtile + k4 * 32), idesc, (e | j | k4) != 0);
+          } else {
+            const int cb = e % a.cb;
+            const int ks = (cb == a.cb - 1) ? a.last_ksteps : 4;
+            for (int k4 = 0; k4 < ks; ++k4)
+              ptx::umma_bf16(tmem + p * 256, ptx::umma_desc_k_sw128(a0 + k4 * 32),
+                             ptx::umma_desc_k_sw128(wa + e * wtile + k4 * 32), idesc, (e | k4) != 0);
+          }
           ptx::umma_commit(&bars->empty[s]);
           if (++s == a.nstages) s = 0;
         }
@@ -155,27 +176,30 @@ conv1d_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       const int b = tile / a.tiles_per_row, t0 = (tile - b * a.tiles_per_row) * 128;
       const bool gather = conv_tile_needs_gather(t0, T, a);
       const int t = t0 + r;
-      for (int kb = 0; kb < KB; ++kb) {
+      for (int e = 0; e < a.entries; ++e) {
         ptx::mbar_wait(&bars->empty[s], ph ^ 1);  // every slot: stay within one ring wrap of the MMA issuer
         if (gather) {
-          const int j = kb / a.cb, cb = kb - j * a.cb;
-          int src = -1;
-          if (t < T) {
-            src = t + (j - a.origin) * a.dilation;
-            if (a.pad_mode == SVSK_PAD_REFLECT) {
-              if (src < 0) src = -src;
-              if (src >= T) src = 2 * (T - 1) - src;
-            } else {
-              src = src < 0 ? 0 : (src >= T ? T - 1 : src);
+          const int j = a.window ? 0 : e / a.cb, cb = a.window ? e : e - j * a.cb;
+          uint8_t* slot = ring + s * a.stage_bytes;
+          // window mode: rows r and r + 128 of the window (row i <-> sample t0 - origin * dilation + i); else row r of tap j
+          for (int wr = r; wr < (a.window ? a.win_rows : 128); wr += 128) {
+            int src = -1;
+            if (a.window ? (t0 + wr - a.origin * a.dilation < T + (a.ksize - 1 - a.origin) * a.dilation) : (t < T)) {
+              src = a.window ? t0 - a.origin * a.dilation + wr : t + (j - a.origin) * a.dilation;
+              if (a.pad_mode == SVSK_PAD_REFLECT) {
+                if (src < 0) src = -src;
+                if (src >= T) src = 2 * (T - 1) - src;
+              } else {
+                src = src < 0 ? 0 : (src >= T ? T - 1 : src);
+              }
             }
-          }
-          const bool ok = src >= 0 && src < T;
-          const uint8_t* g = reinterpret_cast<const uint8_t*>(a.x + ((size_t)b * T + (ok ? src : 0)) * a.Cin) + cb * 128;
-          uint8_t* slot = ring + s * kCTile;
+            const bool ok = src >= 0 && src < T;
+            const uint8_t* g = reinterpret_cast<const uint8_t*>(a.x + ((size_t)b * T + (ok ? src : 0)) * a.Cin) + cb * 128;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const bool have = ok && (cb * 8 + c) < row_chunks;
-            cv_cp_async_16(slot + ptx::sw128_offset((uint32_t)r, (uint32_t)c), have ? g + c * 16 : g, have ? 16u : 0u);
+            for (int c = 0; c < 8; ++c) {
+              const bool have = ok && (cb * 8 + c) < row_chunks;
+              cv_cp_async_16(slot + ptx::sw128_offset((uint32_t)wr, (uint32_t)c), have ? g + c * 16 : g, have ? 16u : 0u);
+            }
           }
           cv_cp_async_arrive_noinc(&bars->full_g[s]);
         }
@@ -185,20 +209,22 @@ conv1d_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     asm volatile("cp.async.wait_all;" ::: "memory");
   } else {
     const int q = warp & 3;
+    const int sub = (warp - 6) >> 2;  // the two warps of a TMEM lane quarter alternate 16-column chunks
     const int row = q * 32 + lane;
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
+    const bool qlead = (sub == 0 && lane == 0);  // issues the quarter's TMA stores
     int n = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++n) {
       const int b = tile / a.tiles_per_row, t0 = (tile - b * a.tiles_per_row) * 128;
       const int p = n & 1;
       uint8_t* ob = obuf + p * a.out_chunks * kCTile;
-      if (n >= 2) {  // this warp's 32 rows of the buffer: its own TMA store of tile n-2 must have read them
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        __syncwarp();
+      if (n >= 2) {  // this quarter's 32 rows of the buffer: its TMA store of tile n-2 must have read them
+        if (qlead) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        ptx::named_bar_sync(1 + q, 64);
       }
       ptx::mbar_wait(&bars->d_full[p], (n >> 1) & 1);
       ptx::tc_fence_after();
-      for (int c0 = 0; c0 < a.Cout; c0 += 16) {
+      for (int c0 = 16 * sub; c0 < a.Cout; c0 += 32) {
         uint32_t rd[16];
         ptx::tmem_ld16(tmem + tlane + p * 256 + c0, rd);
         ptx::tmem_ld_wait();
@@ -219,14 +245,14 @@ conv1d_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bars->d_empty[p]);
       ptx::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {  // one store per warp (= TMEM lane quarter = 32 rows): no CTA-wide barrier, four issuers
+      ptx::named_bar_sync(1 + q, 64);
+      if (qlead) {  // one store per TMEM lane quarter (32 rows): no CTA-wide barrier, four issuers
         for (int oc = 0; oc < a.out_chunks; ++oc)
           ptx::tma_store_3d(&tm_y, ob + oc * kCTile + q * 4096, oc * 64, t0 + q * 32, b);
         ptx::bulk_commit_group();
       }
     }
-    if (lane == 0) ptx::bulk_wait_read_all();
+    if (qlead) ptx::bulk_wait_read_all();
   }
 
   ptx::tc_fence_before();
@@ -312,16 +338,21 @@ extern "C" int svsk_conv1d_bf16(const svsk_conv1d_bf16_params* pp, void* stream)
   const int out_chunks = (p.Cout + 63) / 64;
   const int wbytes = (KB * wtile + 1023) & ~1023;
   const int fixed = wbytes + 2 * out_chunks * kCTile + 256 * 4 + (int)sizeof(ConvBarriers) + 1024;
-  int nstages = (232448 - fixed) / kCTile;
+  // window mode: all taps of a tile out of one (128 + span)-row load per channel block
+  const int span = (p.ksize - 1) * p.dilation;
+  const int window = (p.ksize > 1 && span <= kCMaxSpan && !getenv("SVSK_CONV1D_NO_WINDOW")) ? 1 : 0;
+  const int win_rows = window ? (128 + span + 7) / 8 * 8 : 128;
+  const int stage_bytes = win_rows * 128;
+  int nstages = (232448 - fixed) / stage_bytes;
   if (nstages > kCMaxStages) nstages = kCMaxStages;
   SVSK_REQUIRE(nstages >= 3, SVSK_E_ARG, "conv1d_bf16: weights (%d KB) do not fit shared memory", wbytes / 1024);
-  const int smem_bytes = fixed + nstages * kCTile;
+  const int smem_bytes = fixed + nstages * stage_bytes;
 
   CUtensorMap tm_x, tm_w, tm_y;
   {
     uint64_t dims[3] = {(uint64_t)p.Cin, (uint64_t)p.T, (uint64_t)p.B};
     uint64_t str[2] = {(uint64_t)p.Cin * 2, (uint64_t)p.T * p.Cin * 2};
-    uint32_t box[3] = {64, 128, 1};
+    uint32_t box[3] = {64, (uint32_t)win_rows, 1};
     if ((rc = make_tmap_bf16(&tm_x, p.x, 3, dims, str, box))) return rc;
   }
   {
@@ -358,6 +389,10 @@ extern "C" int svsk_conv1d_bf16(const svsk_conv1d_bf16_params* pp, void* stream)
   SVSK_REQUIRE((long long)p.B * a.tiles_per_row < (1ll << 31), SVSK_E_ARG, "conv1d_bf16: too many tiles");
   a.total_tiles = p.B * a.tiles_per_row;
   a.out_chunks = out_chunks;
+  a.window = window;
+  a.win_rows = win_rows;
+  a.stage_bytes = stage_bytes;
+  a.entries = window ? cb : KB;
   const int grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
   conv1d_bf16_kernel<<<grid, kCThreads, smem_bytes, as_stream(stream)>>>(tm_x, tm_w, tm_y, a);
   return check_launch("conv1d_bf16");
