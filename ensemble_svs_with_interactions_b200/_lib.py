@@ -180,6 +180,7 @@ _SIGNATURES = {
     "svsk_usfgan_pack_block": [_V, _V, _V, _V, _V, _I, _I, _I, _V],
     "svsk_usfgan_aux_frames": [_V, _V, _V, _I, _I, _I, _I, _I, _I, _V],
     "svsk_usfgan_aux_weights": [_V, _V, _I, _I, _I, _V],
+    "svsk_upsample_frames_bf16": [_V, _V, _V, _I, _I, _I, _I, _I, _I, _I, _V],
     "svsk_usfgan_frame_base": [_I, _I, _I],
     "svsk_ntc_bf16_to_nct_f32": [_V, _V, _I, _I, _I, _I, _V],
     "svsk_conv1d_bf16": [C.POINTER(Conv1dBf16Params), _V],

@@ -524,6 +524,17 @@ def usfgan_aux_weights(imp, hop, reach):
     return u
 
 
+def upsample_frames_bf16(imp, cin, T, hop, reach, Ap=None):
+    """imp [16, T] fp32 (as for usfgan_aux_weights), cin [B, A, Tf] fp32 (conv_in's output) -> upsampled aux features
+    [B, T, Ap] bf16 channel-last (svsk_upsample_frames_bf16)."""
+    B, A, Tf = cin.shape
+    Ap = (A + 7) // 8 * 8 if Ap is None else Ap
+    out = torch.empty((B, T, Ap), device=cin.device, dtype=bf16)
+    L.check(L.lib().svsk_upsample_frames_bf16(L.ptr(imp, f32, "imp"), L.ptr(cin, f32, "cin"), L.ptr(out), B, A, Ap, Tf, int(T),
+                                              int(hop), int(reach), L.stream_ptr()), "upsample_frames_bf16")
+    return out
+
+
 def conv1d_pack_bf16(w):
     """w [Cout,Cin,k] fp32 -> [Cout, k*ceil64(Cin)] bf16 (tap-major K)."""
     Cout, Cin, k = w.shape

@@ -95,9 +95,15 @@ class _GeneratorBase(nn.Module):
         if getattr(self, "_auxu_key", None) != ukey:
             f_idx = torch.arange(Tf, device=c.device)
             impulses = (f_idx[None, :] % 16 == torch.arange(16, device=c.device)[:, None]).to(f32)[None]
-            self._auxu = ops.usfgan_aux_weights(up.upsample(impulses)[0].contiguous(), hop, reach)
+            self._auximp = up.upsample(impulses)[0].contiguous()        # [16, T] fp32, kept for _aux_ntc_from_frames
+            self._auxu = ops.usfgan_aux_weights(self._auximp, hop, reach)
             self._auxu_key = ukey
         return ops.UsfganAuxFrames(self._auxu, q, fpad, hop, reach)
+
+    def _aux_ntc_from_frames(self, cin, frames, T):
+        """Sample-rate aux features [B, T, A8] bf16 (the periodicity estimator's input) as U . conv_in(c) with the impulse
+        responses _aux_frames has just cached: one pass at the tensor's write rate (svsk_upsample_frames_bf16)."""
+        return ops.upsample_frames_bf16(self._auximp, cin, T, frames.hop, frames.reach)
 
     def _build_common(self, in_channels, out_channels, residual_channels, skip_channels, aux_channels,
                       aux_context_window, upsample_params):
@@ -300,7 +306,11 @@ class CascadeHnUSFGANGenerator(_HnBase):
             # NTC bf16 throughout, like ParallelHnUSFGANGenerator's wave-only path.  s = a h + (1 - a) n is formed from the
             # two stacks' raw outputs in one pass; a h alone is only needed as the merge conv's input.
             cin = self.upsample_net.conv_in_frames(c)   # once: the periodicity estimator's input and the blocks' Q share it
-            if self.upsample_net.supports_fused():
+            nets = [self.harmonic_network, self.noise_network, self.filter_network]
+            frames = self._aux_frames(c, x.size(-1), nets, cin=cin)
+            if frames is not None and cin.shape[1] <= 112:
+                auxb = self._aux_ntc_from_frames(cin, frames, x.size(-1))
+            elif self.upsample_net.supports_fused():
                 auxb = self.upsample_net.forward_ntc_bf16(c, cin=cin)
             else:
                 auxb = self._aux_ntc(self.upsample_net.upsample(cin))
@@ -309,8 +319,6 @@ class CascadeHnUSFGANGenerator(_HnBase):
             xf = x.to(f32).contiguous()
             hb = _conv1x1_expand_ntc(self.conv_first_sine, xf[:, 0])
             nb = _conv1x1_expand_ntc(self.conv_first_noise, xf[:, 1])
-            nets = [self.harmonic_network, self.noise_network, self.filter_network]
-            frames = self._aux_frames(c, x.size(-1), nets, cin=cin)
             first = [0, len(nets[0].conv_dilated), len(nets[0].conv_dilated) + len(nets[1].conv_dilated)]
             hb = self.harmonic_network.forward_ntc_bf16(hb, auxb, d, cache, frames=frames, frames_block0=first[0])
             zeros = torch.zeros_like(hb)
@@ -362,7 +370,11 @@ class ParallelHnUSFGANGenerator(_HnBase):
             # everything stays NTC bf16: the aux features are upsampled straight into that layout (one pass over all
             # stages), the two 1 -> C input convs write it directly
             cin = self.upsample_net.conv_in_frames(c)   # once: the periodicity estimator's input and the blocks' Q share it
-            if self.upsample_net.supports_fused():
+            nets = [self.harmonic_network, self.noise_network, self.filter_network]
+            frames = self._aux_frames(c, x.size(-1), nets, cin=cin)
+            if frames is not None and cin.shape[1] <= 112:
+                auxb = self._aux_ntc_from_frames(cin, frames, x.size(-1))
+            elif self.upsample_net.supports_fused():
                 auxb = self.upsample_net.forward_ntc_bf16(c, cin=cin)
             else:
                 auxb = self._aux_ntc(self.upsample_net.upsample(cin))
@@ -371,8 +383,6 @@ class ParallelHnUSFGANGenerator(_HnBase):
             xf = x.to(f32).contiguous()
             hb = _conv1x1_expand_ntc(self.conv_first_sine, xf[:, 0])
             nb = _conv1x1_expand_ntc(self.conv_first_noise, xf[:, 1])
-            nets = [self.harmonic_network, self.noise_network, self.filter_network]
-            frames = self._aux_frames(c, x.size(-1), nets, cin=cin)
             first = [0, len(nets[0].conv_dilated), len(nets[0].conv_dilated) + len(nets[1].conv_dilated)]
             hb = self.harmonic_network.forward_ntc_bf16(hb, auxb, d, cache, frames=frames, frames_block0=first[0])
             nb = self.noise_network.forward_ntc_bf16(nb, auxb, d, cache, frames=frames, frames_block0=first[1])

@@ -334,6 +334,12 @@ SVSK_API int svsk_usfgan_aux_frames(const void* cin, const void* w, void* q, int
  * (imp [16][T] fp32 = upsample_net.upsample applied to 16 channels holding unit impulses at the frames f = ch mod 16)
  * re-ordered into the per-tile frame window the block kernel multiplies with. */
 SVSK_API int svsk_usfgan_aux_weights(const float* imp, void* u, int T, int hop, int reach, void* stream);
+/* The aux upsampler itself in the same form (nnsvs/usfgan/layers/upsample.py:61-128, the stages after conv_in):
+ *   out[b][t][ch] = sum_k imp[(fbase(t) + k) mod 16][t] * cin[b][ch][fbase(t) + k]      (bf16 [B][T][Ap], channels >= A zero)
+ * cin [B][A][Tf] fp32 = conv_in's output, imp as for svsk_usfgan_aux_weights.  One pass at the write rate of the
+ * sample-rate tensor; same hop / reach limits as the block kernel's frame window. */
+SVSK_API int svsk_upsample_frames_bf16(const float* imp, const float* cin, void* out, int B, int A, int Ap, int Tf, int T,
+                                       int hop, int reach, void* stream);
 /* First frame of the 16-frame window of the tile starting at sample t0 (a multiple of 8, may be negative). */
 SVSK_API int svsk_usfgan_frame_base(int t0, int reach, int hop);
 

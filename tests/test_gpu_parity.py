@@ -922,6 +922,44 @@ def test_upsample_fused_matches_staged_path(scales, A, Fr, B):
     assert float((diff > 0).float().mean()) < 1e-3
 
 
+@pytest.mark.parametrize("scales,A,Fr,B", [([5, 4, 3, 2], 80, 37, 2), ([5, 4, 3, 2], 65, 3, 1), ([4, 4, 4], 72, 70, 3),
+                                           ([5, 4, 3, 2], 80, 1, 1), ([8, 3, 5], 80, 600, 1)])
+def test_upsample_frames_matches_staged_path(scales, A, Fr, B):
+    """svsk_upsample_frames_bf16 (the upsampler as U . c over the blocks' 16-frame window, U = its own impulse responses)
+    against the staged fp32 kernels: the same numbers up to fp32 summation order and the bf16 rounding of the output."""
+    from ensemble_svs_with_interactions_b200.usfgan.layers.upsample import UpsampleNetwork
+    ops = _ops()
+    g = torch.Generator().manual_seed(Fr + A)
+    net = UpsampleNetwork(scales).to(DEV)
+    with torch.no_grad():
+        for n in range(len(scales)):
+            wt = net.up_layers[2 * n + 1].weight
+            wt.copy_((torch.rand(wt.shape, generator=g) + 0.1).to(DEV) / (2 * scales[n] + 1) * 1.6)
+    hop = int(np.prod(scales))
+    reach, rate = 0, 1
+    for s_ in scales:
+        rate *= s_
+        reach += s_ * (hop // rate)
+    assert ops.usfgan_frame_window_ok(hop, reach)
+    cin = torch.randn(B, A, Fr, generator=g).to(DEV)
+    ref = net(cin)                                                    # [B, A, T] fp32, staged kernels
+    T = Fr * hop
+    impulses = (torch.arange(Fr, device=DEV)[None, :] % 16 == torch.arange(16, device=DEV)[:, None]).float()[None]
+    imp = net(impulses)[0].contiguous()
+    out = ops.upsample_frames_bf16(imp, cin, T, hop, reach)
+    torch.cuda.synchronize()
+    Ap = (A + 7) // 8 * 8
+    assert tuple(out.shape) == (B, T, Ap)
+    got = out.float()[:, :, :A].transpose(1, 2)
+    err = float((got - ref).abs().max())
+    assert err <= 2 ** -8 * float(ref.abs().max()) + 1e-6, err        # bf16 rounding of the output
+    assert float((got - ref.to(torch.bfloat16).float()).abs().max()) <= 2 ** -7 * float(ref.abs().max())
+    if Ap > A:
+        assert float(out[:, :, A:].abs().max()) == 0.0
+    with pytest.raises(RuntimeError, match="reach at most 8 frames"):
+        ops.upsample_frames_bf16(imp, cin, T, 12, 16)
+
+
 def test_expand1_matches_conv1x1():
     ops = _ops()
     g = torch.Generator().manual_seed(3)
