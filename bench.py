@@ -232,7 +232,7 @@ def wavenet_bench(dev):
     return out
 
 
-def vocoder_bench(dev, peaks, tracks=6, seconds=30.0, reps=3):
+def vocoder_bench(dev, peaks, tracks=6, seconds=30.0, reps=10):
     """Second half of the headline metric (BASELINE configs[2]): ParallelHn-uSFGAN, recipe config, 6 tracks x 30 s at
     24 kHz, residual stacks on the fused tcgen05 block kernel.  Returns a dict for the JSON line."""
     from ensemble_svs_with_interactions_b200 import ops
@@ -252,15 +252,16 @@ def vocoder_bench(dev, peaks, tracks=6, seconds=30.0, reps=3):
     f0 = torch.empty(tracks, 1, frames).uniform_(110, 880, generator=g)
     d = (fs / (f0 * 4)).repeat_interleave(hop, dim=-1).to(dev)
     x = (torch.randn(tracks, 2, Tn, generator=g) * 0.1).to(dev)
-    for _ in range(2):
+    for _ in range(3):
         m(x, c, d, wave_only=True)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        m(x, c, d, wave_only=True)
-    e1.record()
-    e1.synchronize()
+    with ClockSampler(dev.index or 0) as clk:      # the HBM-heavy block kernel is the one a power cap shows on first
+        e0.record()
+        for _ in range(reps):
+            m(x, c, d, wave_only=True)
+        e1.record()
+        e1.synchronize()
     ms = e0.elapsed_time(e1) / reps
     # dominant kernel of the vocoder: the fused block with the frame-rate aux projection, as the pass runs it (the 30
     # fixed blocks of the filter network timed in isolation)
@@ -270,10 +271,11 @@ def vocoder_bench(dev, peaks, tracks=6, seconds=30.0, reps=3):
     m.filter_network.forward_ntc_bf16(hb, auxb, d, {}, frames=frames_op)
     torch.cuda.synchronize()
     e0.record()
-    m.filter_network.forward_ntc_bf16(hb, auxb, d, {}, frames=frames_op)
+    for _ in range(3):
+        m.filter_network.forward_ntc_bf16(hb, auxb, d, {}, frames=frames_op)
     e1.record()
     e1.synchronize()
-    blk_ms = e0.elapsed_time(e1) / 30
+    blk_ms = e0.elapsed_time(e1) / 90
     hbm = (peaks or {}).get("hbm_gbs", 6650.0)
     # algorithmic bytes per sample-block: bf16 x in + out (256 B); + the 80 sample-rate aux channels (160 B) only when
     # the aux projection cannot be taken at frame rate
@@ -283,6 +285,7 @@ def vocoder_bench(dev, peaks, tracks=6, seconds=30.0, reps=3):
     return {"metric": "vocoded audio-sec/sec (ParallelHn-uSFGAN, 24 kHz)", "value": tracks * seconds / (ms / 1e3),
             "unit": "audio-sec/s", "ms_per_pass": ms, "precision": m.resolved_precision(),
             "config": {"workload": f"{tracks} tracks x {seconds:.0f} s @ 24 kHz, hop 120, aux 80, 20A+5F+30F blocks"},
+            "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                          "traffic": _ncu_traffic(USFGAN_NCU_SUMMARY), "kernel": kernel, "us_per_launch": blk_ms * 1e3,
                          "bytes_per_sample_block": bytes_per,

@@ -70,6 +70,12 @@ struct DiffnetStackArgs {
   // conditioner tiles — the same for every layer — stay in their own shared-memory tiles instead of being reloaded into
   // the G buffer once the skip epilogue has released it (3.8 k cycles into the layer).
   int pingpong, cond_resident;
+  // Experiment (SVSK_STACK_COND_FIRST=1, global-memory halo mode): the conditioner k-blocks issued BEFORE block 0's side
+  // taps, on the idea that the halo rows land ~9.5 k cycles after the previous residual epilogue there and the conditioner
+  // MMAs need none.  Measured at 3 x 6000 frames, C = 256: 446.1 vs 434.5 us per launch — slower: the conditioner tiles
+  // (G buffer released by the previous skip epilogue, then a 64 KB load) arrive no earlier than the halo rows, and the
+  // side taps then queue behind them.  Off by default.
+  int cond_first;
   int dilation[kSMaxLayers];
   unsigned long long* dbg;
 };
@@ -92,14 +98,22 @@ struct __align__(8) DiffnetStackBarriers {
 };
 
 // ring entry i of a layer -> which weight tile (see the order in the header comment)
-__device__ __forceinline__ void stack_entry(int i, int CB, int HB, int NB, int KB2, int& kcol, int& blk, bool& wout) {
+__device__ __forceinline__ void stack_entry(int i, int CB, int HB, int NB, int KB2, int cond_first, int& kcol, int& blk,
+                                            bool& wout) {
   wout = false;
   if (i < CB) { kcol = CB + i; blk = 0; return; }
   i -= CB;
-  if (i < 2 * CB) { kcol = (i / CB) * 2 * CB + i % CB; blk = 0; return; }
-  i -= 2 * CB;
-  if (i < HB * NB) { kcol = 3 * CB + i / NB; blk = i % NB; return; }
-  i -= HB * NB;
+  if (cond_first) {
+    if (i < HB * NB) { kcol = 3 * CB + i / NB; blk = i % NB; return; }
+    i -= HB * NB;
+    if (i < 2 * CB) { kcol = (i / CB) * 2 * CB + i % CB; blk = 0; return; }
+    i -= 2 * CB;
+  } else {
+    if (i < 2 * CB) { kcol = (i / CB) * 2 * CB + i % CB; blk = 0; return; }
+    i -= 2 * CB;
+    if (i < HB * NB) { kcol = 3 * CB + i / NB; blk = i % NB; return; }
+    i -= HB * NB;
+  }
   if (i < (NB - 1) * 3 * CB) { blk = 1 + i / (3 * CB); kcol = i % (3 * CB); return; }
   i -= (NB - 1) * 3 * CB;
   wout = true;
@@ -204,7 +218,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
     for (int e = 0; e < pre_issued; ++e) {
       int kcol, blk;
       bool wout;
-      stack_entry(e, CB, HB, NB, KB2, kcol, blk, wout);
+      stack_entry(e, CB, HB, NB, KB2, a.cond_first, kcol, blk, wout);
       ptx::mbar_arrive_expect_tx(&bars->full[e], kSTile);
       ptx::tma_load_3d(ring + e * kSTile, wout ? &tm_wout : &tm_w1, &bars->full[e], kcol * 64, blk * 256 + w_row0, 0);
     }
@@ -229,7 +243,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         ptx::mbar_wait(&bars->empty[s], ph ^ 1);
         int kcol, blk;
         bool wout;
-        stack_entry(i, CB, HB, NB, KB2, kcol, blk, wout);
+        stack_entry(i, CB, HB, NB, KB2, a.cond_first, kcol, blk, wout);
         ptx::mbar_arrive_expect_tx(&bars->full[s], kSTile);
         if (mc) ptx::tma_load_3d_mc(ring + s * kSTile + pidx * slice_rows * 128, wout ? &tm_wout : &tm_w1, &bars->full[s],
                                     kcol * 64, blk * 256 + w_row0 + pidx * slice_rows, l, parity_mask);
@@ -360,30 +374,35 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
           if (l == 2 && cb == 0) SVSK_STAMP(19);
           SVSK_ISSUE4(0, xw_lo + cb * (kSWinBytes >> 4) + kSHalo * 8, ring_lo + s * (kSTile >> 4), cb != 0);
         }
-        // ---- side taps, block 0
-        if (l != 0) {  // halo rows of this layer
-          if (a.dsmem_halo) ptx::mbar_wait(&bars->xh_full, pp);
-          else ptx::mbar_wait(&bars->xw_full, pl);
-          ptx::tc_fence_after();
-        }
-        if (l == 1) SVSK_STAMP(3);
-        for (int jt = 0; jt < 3; jt += 2) {
-          const uint32_t row_lo = xw_lo + (uint32_t)(kSHalo + (jt - 1) * d) * 8u;
-          for (int cb = 0; cb < CB; ++cb) {
-            SVSK_WAIT_ENTRY();
-            SVSK_ISSUE4(0, row_lo + cb * (kSWinBytes >> 4), ring_lo + s * (kSTile >> 4), 1);
-          }
-        }
-        // ---- conditioner k-blocks out of the (future) G buffer, all output blocks per tile
-        for (int hb = 0; hb < HB; ++hb) {
-          if (l == 0 || !a.cond_resident) ptx::mbar_wait(&bars->cd_full[hb], pl);
-          if (hb == 0 && l != 0 && NB > 1) ptx::mbar_wait(&bars->d2_drained[1], pp);
-          ptx::tc_fence_after();
-          if (l == 1 && hb == 0) SVSK_STAMP(4);
-          const uint32_t a_lo = cond_lo + hb * (kSTile >> 4);
-          for (int j = 0; j < NB; ++j) {
-            SVSK_WAIT_ENTRY();
-            SVSK_ISSUE4(j * 256, a_lo, ring_lo + s * (kSTile >> 4), (j == 0 || hb != 0) ? 1 : 0);
+        for (int part = 0; part < 2; ++part) {
+          if ((part == 0) != (a.cond_first != 0)) {
+            // ---- side taps, block 0
+            if (l != 0) {  // halo rows of this layer
+              if (a.dsmem_halo) ptx::mbar_wait(&bars->xh_full, pp);
+              else ptx::mbar_wait(&bars->xw_full, pl);
+              ptx::tc_fence_after();
+            }
+            if (l == 1) SVSK_STAMP(3);
+            for (int jt = 0; jt < 3; jt += 2) {
+              const uint32_t row_lo = xw_lo + (uint32_t)(kSHalo + (jt - 1) * d) * 8u;
+              for (int cb = 0; cb < CB; ++cb) {
+                SVSK_WAIT_ENTRY();
+                SVSK_ISSUE4(0, row_lo + cb * (kSWinBytes >> 4), ring_lo + s * (kSTile >> 4), 1);
+              }
+            }
+          } else {
+            // ---- conditioner k-blocks out of the (future) G buffer, all output blocks per tile
+            for (int hb = 0; hb < HB; ++hb) {
+              if (l == 0 || !a.cond_resident) ptx::mbar_wait(&bars->cd_full[hb], pl);
+              if (hb == 0 && l != 0 && NB > 1) ptx::mbar_wait(&bars->d2_drained[1], pp);
+              ptx::tc_fence_after();
+              if (l == 1 && hb == 0) SVSK_STAMP(4);
+              const uint32_t a_lo = cond_lo + hb * (kSTile >> 4);
+              for (int j = 0; j < NB; ++j) {
+                SVSK_WAIT_ENTRY();
+                SVSK_ISSUE4(j * 256, a_lo, ring_lo + s * (kSTile >> 4), (j == 0 || hb != 0) ? 1 : 0);
+              }
+            }
           }
         }
         ptx::umma_commit2_mc(&bars->d1_full[0], pair_mask);
@@ -449,14 +468,19 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         };
         if (l == 0) forward_xw();
         forward_entries(CB);
-        if (l != 0) forward_xw();
-        forward_entries(2 * CB);
-        for (int hb = 0; hb < HB; ++hb) {
-          if (l == 0 || !a.cond_resident) {
-            ptx::mbar_wait(&bars->cd_full[hb], pl);
-            ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->cd_full[hb]), lead));
+        for (int part = 0; part < 2; ++part) {
+          if ((part == 0) != (a.cond_first != 0)) {
+            if (l != 0) forward_xw();
+            forward_entries(2 * CB);
+          } else {
+            for (int hb = 0; hb < HB; ++hb) {
+              if (l == 0 || !a.cond_resident) {
+                ptx::mbar_wait(&bars->cd_full[hb], pl);
+                ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->cd_full[hb]), lead));
+              }
+              forward_entries(NB);
+            }
           }
-          forward_entries(NB);
         }
         forward_entries((NB - 1) * 3 * CB + NB * KB2);
       }
@@ -896,6 +920,7 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
   a.nentries = nentries;
   a.pingpong = (p.C == 128 && !getenv("SVSK_STACK_NO_PINGPONG")) ? 1 : 0;
   a.cond_resident = cond_resident;
+  a.cond_first = (!a.dsmem_halo && getenv("SVSK_STACK_COND_FIRST")) ? 1 : 0;  // experiment switch, see DiffnetStackArgs
   a.tiles_per_track = 2 * ceil_div(p.T, 256);
   for (int l = 0; l < kSMaxLayers; ++l) a.dilation[l] = l < p.L ? p.dilation[l] : 1;
   a.dbg = nullptr;
