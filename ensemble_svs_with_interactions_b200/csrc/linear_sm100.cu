@@ -23,6 +23,7 @@ struct LinearArgs {
   __nv_bfloat16* y_t;
   long long t_bstride;
   int t_rows, t_ld;
+  int nstages;
 };
 
 struct __align__(8) LinearBarriers {
@@ -45,7 +46,8 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int wbytes = a.Cout * 128;
   const int stage_bytes = kLinABytes + wbytes;
-  LinearBarriers* bars = reinterpret_cast<LinearBarriers*>(smem + kLinStages * stage_bytes);
+  const int nstages = a.nstages;  // <= kLinStages; fewer when K is short, so that several CTAs share an SM
+  LinearBarriers* bars = reinterpret_cast<LinearBarriers*>(smem + nstages * stage_bytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long n0 = (long long)blockIdx.x * 128;
   const int KB = (a.K + 63) / 64;
@@ -78,8 +80,8 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         uint8_t* As = smem + s * stage_bytes;
         ptx::mbar_arrive_expect_tx(&bars->full[s], stage_bytes);
         ptx::tma_load_2d(As, &tm_a, &bars->full[s], kb * 64, (int)n0);
-        ptx::tma_load_2d(As + kLinABytes, &tm_w, &bars->full[s], kb * 64, 0);
-        if (++s == kLinStages) { s = 0; ph ^= 1; }
+        ptx::tma_load_2d(As + kLinABytes, &tm_w, &bars->full[s], kb * 64, (int)blockIdx.y * a.Cout);  // y: chunk of weight rows
+        if (++s == nstages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -97,7 +99,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           ptx::umma_bf16(tmem, ptx::umma_desc_k_sw128(a0 + k4 * 32), ptx::umma_desc_k_sw128(b0 + k4 * 32), idesc,
                          (kb | k4) != 0);
         ptx::umma_commit(&bars->empty[s]);
-        if (++s == kLinStages) { s = 0; ph ^= 1; }
+        if (++s == nstages) { s = 0; ph ^= 1; }
       }
       ptx::umma_commit(&bars->d_full);
     }
@@ -111,7 +113,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     __nv_bfloat16* yt = nullptr;
     if (a.y_t && n < a.N) {
       const long long trk = n / a.t_rows;
-      yt = a.y_t + trk * a.t_bstride + (n - trk * a.t_rows);
+      yt = a.y_t + trk * a.t_bstride + (n - trk * a.t_rows) + (size_t)blockIdx.y * a.Cout * a.t_ld;
     }
     for (int c0 = 0; c0 < a.Cout; c0 += 16) {
       uint32_t r[16];
@@ -211,6 +213,7 @@ extern "C" int svsk_linear_bf16(const svsk_linear_bf16_params* pp, void* stream)
   a.ldy_f = p.ldy_f;
   a.act = p.act;
   a.tmem_cols = p.Cout <= 32 ? 32 : (p.Cout <= 64 ? 64 : (p.Cout <= 128 ? 128 : 256));
+  a.nstages = kLinStages;
   a.y_t = nullptr;
   a.t_bstride = 0;
   a.t_rows = 1;
@@ -245,11 +248,15 @@ extern "C" int svsk_usfgan_aux_frames(const void* cin, const void* w, void* q, i
     uint32_t box[2] = {64, 128};
     if ((rc = make_tmap_bf16(&tm_a, cin, 2, dims, str, box))) return rc;
   }
-  // rows = frames of all tracks, 256 output rows of w (two blocks) per launch, stored transposed: frame index innermost
+  // rows = frames of all tracks; `chunk` output rows of w per CTA (gridDim.y chunks: ONE launch for all blocks' projections
+  // when R is a multiple of 128 — 55 chunks at the recipe's depth; 28 launches of 256 rows took 0.47 ms at config 3, mostly
+  // launch boundaries), stored transposed: frame index innermost
+  const int chunk = R % 256 == 0 ? 256 : (R % 128 == 0 ? 128 : 0);
   for (int r0 = 0; r0 < R; r0 += 256) {
-    const int cout = R - r0 < 256 ? R - r0 : 256;
+    const int cout = chunk ? chunk : (R - r0 < 256 ? R - r0 : 256);
+    const int rows = chunk ? R : cout;   // weight rows the map covers
     CUtensorMap tm_w;
-    uint64_t dims[2] = {(uint64_t)Ap, (uint64_t)cout};
+    uint64_t dims[2] = {(uint64_t)Ap, (uint64_t)rows};
     uint64_t str[1] = {(uint64_t)Ap * 2};
     uint32_t box[2] = {64, (uint32_t)cout};
     if ((rc = make_tmap_bf16(&tm_w, static_cast<const __nv_bfloat16*>(w) + (size_t)r0 * Ap, 2, dims, str, box))) return rc;
@@ -267,9 +274,15 @@ extern "C" int svsk_usfgan_aux_frames(const void* cin, const void* w, void* q, i
     a.t_bstride = (long long)R * q_ld;
     a.t_rows = Tf;
     a.t_ld = q_ld;
-    const int smem_bytes = kLinStages * (kLinABytes + cout * 128) + (int)sizeof(LinearBarriers) + 1024;
-    linear_bf16_kernel<<<(unsigned)((N + 127) / 128), 192, smem_bytes, as_stream(stream)>>>(tm_a, tm_w, a);
+    // K = Ap is one or two k-blocks: as many stages as k-blocks, so that three or four CTAs fit an SM — the kernel is a
+    // latency chain per CTA (load, a few MMAs, 2-byte transposed stores), 0.45 -> 0.2 ms at config 3
+    a.nstages = (Ap + 63) / 64 < kLinStages ? (Ap + 63) / 64 : kLinStages;
+    const int smem_bytes = a.nstages * (kLinABytes + cout * 128) + (int)sizeof(LinearBarriers) + 1024;
+    const unsigned gy = chunk ? (unsigned)(R / chunk) : 1u;
+    SVSK_REQUIRE(gy <= 65535u, SVSK_E_ARG, "usfgan_aux_frames: R=%d too large", R);
+    linear_bf16_kernel<<<dim3((unsigned)((N + 127) / 128), gy), 192, smem_bytes, as_stream(stream)>>>(tm_a, tm_w, a);
     if ((rc = check_launch("usfgan_aux_frames"))) return rc;
+    if (chunk) break;
   }
   return 0;
 }
