@@ -350,6 +350,11 @@ usfgan_block_fr_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
   } else {
     // ------------------------------------------------------------------ epilogue: two groups of 8 warps; group p owns the
     // tiles n with n & 1 == p and with them D1[p], G[p] and the D2 pair 2p, 2p+1 — the groups share no buffer.
+    // (Measured and not kept: ONE group of 16 warps, one 16-column chunk per thread, software-pipelined gate(n) ;
+    // residual(n - 1) — no idle waits left (D1 0.3 k + D2 0.25 k cycles per tile), but the phases do not get twice as fast
+    // with twice the warps (gate 2.55 k -> 1.79 k, residual 1.70 k -> 1.00 k: barrier, TMEM-load and fence latencies and the
+    // 1.0 k-cycle MUFU floor of a tile's gate do not divide), and serialised they cost more than two half-width groups that
+    // overlap each other: 400 vs 365 us per fixed block; adaptive blocks, bound by the gather, 421 vs 440 us.)
     // Thread = one sample, half the columns (two warps per TMEM lane quarter alternating 16-column chunks).
     const int e = warp - 7;
     const int p = e >> 3;
