@@ -47,6 +47,7 @@ class DiffnetStackParams(C.Structure):
         ("bout", C.c_void_p), ("flags", C.c_void_p), ("dilation", C.POINTER(C.c_int32)),
         ("B", C.c_int32), ("T", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("L", C.c_int32),
         ("stepbias_batch_stride", C.c_int32), ("stepbias_layer_stride", C.c_int32), ("init_skip", C.c_int32),
+        ("pcond_gate", C.c_void_p), ("pcond_filt", C.c_void_p),
     ]
 
 
@@ -163,6 +164,9 @@ _SIGNATURES = {
     "svsk_diffnet_block3_bf16": [C.POINTER(DiffnetBlockParams), _V],
     "svsk_diffnet_stack_bf16": [C.POINTER(DiffnetStackParams), _V],
     "svsk_diffnet_stack_fits": [C.c_int, C.c_int, C.c_int, C.c_int],
+    "svsk_diffnet_stack_uses_pcond": [C.c_int, C.c_int, C.c_int, C.c_int],
+    "svsk_diffnet_cond_project_bf16": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p],
+    "svsk_diffnet_pcond_pack_bf16": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "svsk_diffnet_step_bf16": [C.POINTER(DiffnetStepParams), _V],
     "svsk_upsample_fused": [_V, _V, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_int, _V, _V, C.c_int, _V],
     "svsk_expand1_bf16": [_V, C.c_longlong, _V, _V, _V, C.c_int, C.c_int, C.c_int, _V],

@@ -283,6 +283,7 @@ diffnet_block3_kernel(const __grid_constant__ CUtensorMap tm_xw, const __grid_co
     const int t = t_cta0 + row;
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
     const bool has_l = (t - a.dilation) >= 0, has_r = (t + a.dilation) < T;
+    const bool warp_edge = __any_sync(0xffffffffu, !has_l || !has_r);  // warp-uniform: the bias correction is a branch
     const bool stamp = (warp == 2 && lane == 0);
 
     // per-column biases -> smem (off the path to the first MMA): sb_full = centre + left + right tap terms, what an
@@ -319,26 +320,29 @@ diffnet_block3_kernel(const __grid_constant__ CUtensorMap tm_xw, const __grid_co
         const uint32_t* rg = rgb[i & 1];
         const uint32_t* rf = rfb[i & 1];
         const int pg = j * 256 + c0, pf = pg + 128;
-        float z[16];
+        float gv[16], fv[16];
 #pragma unroll
         for (int e = 0; e < 16; e += 4) {
           const float4 bg = ptx::ld_shared_v4f(sb_full + pg + e);
           const float4 bf = ptx::ld_shared_v4f(sb_full + pf + e);
-          float gv[4] = {__uint_as_float(rg[e]) + bg.x, __uint_as_float(rg[e + 1]) + bg.y,
-                         __uint_as_float(rg[e + 2]) + bg.z, __uint_as_float(rg[e + 3]) + bg.w};
-          float fv[4] = {__uint_as_float(rf[e]) + bf.x, __uint_as_float(rf[e + 1]) + bf.y,
-                         __uint_as_float(rf[e + 2]) + bf.z, __uint_as_float(rf[e + 3]) + bf.w};
+          gv[e] = __uint_as_float(rg[e]) + bg.x; gv[e + 1] = __uint_as_float(rg[e + 1]) + bg.y;
+          gv[e + 2] = __uint_as_float(rg[e + 2]) + bg.z; gv[e + 3] = __uint_as_float(rg[e + 3]) + bg.w;
+          fv[e] = __uint_as_float(rf[e]) + bf.x; fv[e + 1] = __uint_as_float(rf[e + 1]) + bf.y;
+          fv[e + 2] = __uint_as_float(rf[e + 2]) + bf.z; fv[e + 3] = __uint_as_float(rf[e + 3]) + bf.w;
+        }
+        if (warp_edge) {  // a branch around the rare case, not 128 predicated-off instructions per chunk (see diffnet_stack_sm100.cu)
           if (!has_l) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { gv[u] -= sb_l[pg + e + u]; fv[u] -= sb_l[pf + e + u]; }
+            for (int u = 0; u < 16; ++u) { gv[u] -= sb_l[pg + u]; fv[u] -= sb_l[pf + u]; }
           }
           if (!has_r) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { gv[u] -= sb_r[pg + e + u]; fv[u] -= sb_r[pf + e + u]; }
+            for (int u = 0; u < 16; ++u) { gv[u] -= sb_r[pg + u]; fv[u] -= sb_r[pf + u]; }
           }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) z[e + u] = ptx::sigmoid_approx(gv[u]) * ptx::tanh_approx(fv[u]);
         }
+        float z[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) z[u] = ptx::sigmoid_approx(gv[u]) * ptx::tanh_approx(fv[u]);
         const int kc0 = j * 128 + c0;  // first gated channel of the chunk = K index of GEMM2
         uint8_t* gk = g_smem + (kc0 >> 6) * k3Tile;
         const uint32_t ch16 = (uint32_t)((kc0 & 63) >> 3);

@@ -392,6 +392,7 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
         const uint32_t pl = (uint32_t)l & 1u;
         const int d = a.dilation[l];
         const bool has_l = (t - d) >= 0, has_r = (t + d) < T;
+        const bool warp_edge = __any_sync(0xffffffffu, !has_l || !has_r);  // warp-uniform: the bias correction is a branch
         const bool last = (l == L - 1);
         // per-column biases of this layer -> smem: sb_full = centre + left + right tap terms (an interior frame's sum)
         {
@@ -426,26 +427,29 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
             const uint32_t* rg = rgb[i & 1];
             const uint32_t* rf = rfb[i & 1];
             const int pg = c0, pf = c0 + 128;
-            float z[16];
+            float gv[16], fv[16];
 #pragma unroll
             for (int e = 0; e < 16; e += 4) {
               const float4 bg = ptx::ld_shared_v4f(sb_full + pg + e);
               const float4 bf = ptx::ld_shared_v4f(sb_full + pf + e);
-              float gv[4] = {__uint_as_float(rg[e]) + bg.x, __uint_as_float(rg[e + 1]) + bg.y,
-                             __uint_as_float(rg[e + 2]) + bg.z, __uint_as_float(rg[e + 3]) + bg.w};
-              float fv[4] = {__uint_as_float(rf[e]) + bf.x, __uint_as_float(rf[e + 1]) + bf.y,
-                             __uint_as_float(rf[e + 2]) + bf.z, __uint_as_float(rf[e + 3]) + bf.w};
+              gv[e] = __uint_as_float(rg[e]) + bg.x; gv[e + 1] = __uint_as_float(rg[e + 1]) + bg.y;
+              gv[e + 2] = __uint_as_float(rg[e + 2]) + bg.z; gv[e + 3] = __uint_as_float(rg[e + 3]) + bg.w;
+              fv[e] = __uint_as_float(rf[e]) + bf.x; fv[e + 1] = __uint_as_float(rf[e + 1]) + bf.y;
+              fv[e + 2] = __uint_as_float(rf[e + 2]) + bf.z; fv[e + 3] = __uint_as_float(rf[e + 3]) + bf.w;
+            }
+            if (warp_edge) {  // a branch around the rare case, not 128 predicated-off instructions per chunk (see diffnet_stack_sm100.cu)
               if (!has_l) {
 #pragma unroll
-                for (int v = 0; v < 4; ++v) { gv[v] -= sb_l[pg + e + v]; fv[v] -= sb_l[pf + e + v]; }
+                for (int u = 0; u < 16; ++u) { gv[u] -= sb_l[pg + u]; fv[u] -= sb_l[pf + u]; }
               }
               if (!has_r) {
 #pragma unroll
-                for (int v = 0; v < 4; ++v) { gv[v] -= sb_r[pg + e + v]; fv[v] -= sb_r[pf + e + v]; }
+                for (int u = 0; u < 16; ++u) { gv[u] -= sb_r[pg + u]; fv[u] -= sb_r[pf + u]; }
               }
-#pragma unroll
-              for (int v = 0; v < 4; ++v) z[e + v] = ptx::sigmoid_approx(gv[v]) * ptx::tanh_approx(fv[v]);
             }
+            float z[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) z[u] = ptx::sigmoid_approx(gv[u]) * ptx::tanh_approx(fv[u]);
             uint8_t* gk = g_smem + (c0 >> 6) * kDTile;  // gated channel c0.. = K index of GEMM2
             const uint32_t ch16 = (uint32_t)((c0 & 63) >> 3);
             ptx::st_shared_v4(gk + ptx::sw128_offset((uint32_t)row, ch16), ptx::pack_bf16(z[0], z[1]),

@@ -28,6 +28,13 @@
 //   2: conditioner, blocks 0..NB-1 (A = conditioner tiles in the G buffer, which the previous skip epilogue released)
 //   3: all taps, blocks 1..NB-1
 //   4: output projection, blocks 0..NB-1 (A = G)
+// Hoisted conditioner projection (kUseP, svsk_diffnet_stack_params::pcond_*): inside a sampling run cond is the same
+// for all K denoiser calls, so conditioner_projection(cond) of every layer is computed once per run and this kernel skips
+// entry group 2 (K = 3C instead of 3C + H: 20 % of the MMAs at C = H = 256, and the wait for the conditioner tiles).  The
+// projection comes back in the gating epilogue: its gate half is TMA-loaded (bf16, the G tiles' own layout) into the very
+// bytes of the G buffer that the thread overwrites with its gate output — the slot and the moment the conditioner tiles
+// used to take — and its filter half is read from global memory two chunks ahead into 16 registers (a [chunk][frame][16]
+// layout: a warp reads 1 KB contiguous; the lines are prefetched into L2 one layer ahead by the activation producer).
 // Warps: 0 = weight producer (both CTAs), 1 = MMA issuer (leader) / forwarder (peer) + TMEM owner, 2..9 = epilogue
 // (kSW = 2 per TMEM lane quarter), 10 = activation producer (conditioner tiles, window / halo rows, edge-row publication).
 // All CTAs must be co-resident (neighbours wait for each other): the host entry checks the grid against
@@ -76,6 +83,15 @@ struct DiffnetStackArgs {
   // (G buffer released by the previous skip epilogue, then a 64 KB load) arrive no earlier than the halo rows, and the
   // side taps then queue behind them.  Off by default.
   int cond_first;
+  // Hoisted conditioner projection (see the header comment): filter half, [tile][L][NB][8][128][16] bf16 from this launch's
+  // first track on; the gate half comes through tm_cond (then a map of [B*L][T][C]).
+  int use_p;
+  const uint4* pfilt;
+  // The peer CTA's weight loads complete on the LEADER's ring barrier (cta_group::2 TMA, as CUTLASS's 2-SM kernels do)
+  // instead of on its own barrier + a forwarding thread's remote arrival: one hop less per ring entry.
+  int peer_tx;
+  int spin;   // experiment (SVSK_STACK_SPIN=1): weight producer and forwarder poll their barriers instead of suspending
+  int no_mc;  // experiment (SVSK_STACK_NO_MULTICAST=1): one cluster per track, but every pair loads its own weight tiles
   int dilation[kSMaxLayers];
   unsigned long long* dbg;
 };
@@ -83,7 +99,7 @@ struct DiffnetStackArgs {
 struct __align__(8) DiffnetStackBarriers {
   uint64_t full[kSMaxEntries];  // ring entry landed: own TMA bytes, and on the leader also the peer's (forwarded) arrival
   uint64_t empty[kSMaxEntries];
-  uint64_t cd_full[8];          // conditioner tile hb of this layer landed (leader: in both CTAs)
+  uint64_t cd_full[8];          // conditioner tile hb of this layer landed (leader: in both CTAs); use_p: gate-half tile hb of the projection (each CTA its own)
   uint64_t xw_full;             // layer 0: whole window landed; later layers: halo rows landed (leader: in both CTAs)
   uint64_t xh_full;             // DSMEM mode: the neighbours' edge threads have written this CTA's halo rows (leader: both CTAs)
   uint64_t halo_free;           // DSMEM mode: the CTA pairs that read the halo rows this CTA writes have finished GEMM1
@@ -135,7 +151,19 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ uint4 ldg_stream_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
+// kUseP: the conditioner projection is precomputed (DiffnetStackArgs::use_p) — a compile-time switch, so that the instantiation without it
+// keeps the register allocation it had before the projection's prefetch registers existed (168 registers are the cap at
+// 352 threads; a handful of spilled loop invariants cost the MMA-issuing thread 5 % of the launch).
+template <bool kUseP>
 __global__ void __launch_bounds__(kSThreads, 1)
 diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_constant__ CUtensorMap tm_e0,
                      const __grid_constant__ CUtensorMap tm_e1, const __grid_constant__ CUtensorMap tm_cond,
@@ -145,7 +173,9 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int C = a.C, H = a.H, T = a.T, L = a.L;
-  const int CB = C / 64, HB = H / 64;
+  const int CB = C / 64;
+  const int HB = kUseP ? 0 : H / 64;  // conditioner k-blocks of GEMM1 (none when the projection is precomputed)
+  const int PB = kUseP ? CB : 0;      // ... then: gate-half tiles of the projection per layer, loaded where G will be written
   const int KB2 = CB;
   const int NB = (2 * C) / 256;  // 256-column output blocks of either GEMM
   const int twoC = 2 * C;
@@ -167,7 +197,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
   const uint16_t pair_mask = (uint16_t)(3u << lead);
   const bool nb_left = a.dsmem_halo && crank > 0, nb_right = a.dsmem_halo && crank + 1 < csize;  // DSMEM neighbours
   // weight multicast (one cluster per track): every pair fetches rows [pidx, pidx+1) * 128/n_pairs of each half-tile
-  const bool mc = a.dsmem_halo != 0;
+  const bool mc = a.dsmem_halo != 0 && !a.no_mc;
   const int n_pairs = mc ? (int)(csize >> 1) : 1, pidx = mc ? (int)(crank >> 1) : 0;
   const int slice_rows = 128 / n_pairs;
   const uint16_t parity_mask = (uint16_t)((0x5555u << rank) & ((1u << csize) - 1u));  // CTAs with this CTA's pair rank
@@ -194,10 +224,11 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
     const uint32_t two = rank == 0 ? 2u : 1u;        // leader barriers also count the peer's forwarded arrival
     const uint32_t all = rank == 0 ? 2u * kSEpi : 1u; // leader barriers every epilogue thread of the pair arrives on
     for (int i = 0; i < a.nentries; ++i) {
-      ptx::mbar_init(&bars->full[i], two);
+      ptx::mbar_init(&bars->full[i], a.peer_tx ? 1u : two);
       ptx::mbar_init(&bars->empty[i], (uint32_t)n_pairs);  // one multicast tcgen05.commit per CTA pair sharing the weights
     }
     for (int i = 0; i < HB; ++i) ptx::mbar_init(&bars->cd_full[i], two);
+    for (int i = 0; i < PB; ++i) ptx::mbar_init(&bars->cd_full[i], 1);  // read by this CTA's own epilogue threads
     ptx::mbar_init(&bars->xw_full, two);
     // halo rows: 8 * kSW arrivals per neighbour (8 rows x the kSW epilogue warps of a lane quarter) + the peer's forward
     ptx::mbar_init(&bars->xh_full, max(1u, 8u * kSW * ((nb_left ? 1u : 0u) + (nb_right ? 1u : 0u)) + (rank == 0 ? 1u : 0u)));
@@ -214,12 +245,13 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
     ptx::mbar_init(&bars->g_ready[1], all);
     ptx::mbar_init(&bars->gc_free, 4 * kSW);  // one arrival per epilogue warp
     ptx::fence_mbar_init();
-    pre_issued = mc ? 0 : min(a.nentries, n_total);  // (multicast writes into CTAs that may not have set up their barriers yet)
+    // (multicast writes into CTAs that may not have set up their barriers yet; so does a peer counting on its leader's barrier)
+    pre_issued = (mc || (a.peer_tx && rank == 1)) ? 0 : min(a.nentries, n_total);
     for (int e = 0; e < pre_issued; ++e) {
       int kcol, blk;
       bool wout;
       stack_entry(e, CB, HB, NB, KB2, a.cond_first, kcol, blk, wout);
-      ptx::mbar_arrive_expect_tx(&bars->full[e], kSTile);
+      ptx::mbar_arrive_expect_tx(&bars->full[e], a.peer_tx ? 2 * kSTile : kSTile);
       ptx::tma_load_3d(ring + e * kSTile, wout ? &tm_wout : &tm_w1, &bars->full[e], kcol * 64, blk * 256 + w_row0, 0);
     }
   }
@@ -240,14 +272,23 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
       uint32_t ph = (pre_issued == a.nentries) ? 1u : 0u;
       int l = pre_issued / n_layer, i = pre_issued - l * n_layer;
       for (int e = pre_issued; e < n_total; ++e) {
-        ptx::mbar_wait(&bars->empty[s], ph ^ 1);
+        if (a.spin) ptx::mbar_wait_spin(&bars->empty[s], ph ^ 1);
+        else ptx::mbar_wait(&bars->empty[s], ph ^ 1);
         int kcol, blk;
         bool wout;
         stack_entry(i, CB, HB, NB, KB2, a.cond_first, kcol, blk, wout);
-        ptx::mbar_arrive_expect_tx(&bars->full[s], kSTile);
-        if (mc) ptx::tma_load_3d_mc(ring + s * kSTile + pidx * slice_rows * 128, wout ? &tm_wout : &tm_w1, &bars->full[s],
-                                    kcol * 64, blk * 256 + w_row0 + pidx * slice_rows, l, parity_mask);
-        else ptx::tma_load_3d(ring + s * kSTile, wout ? &tm_wout : &tm_w1, &bars->full[s], kcol * 64, blk * 256 + w_row0, l);
+        if (a.peer_tx) {
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&bars->full[s], 2 * kSTile);  // this CTA's 16 KB and the peer's
+          const uint32_t lbar = ptx::leader_bar_addr(&bars->full[s]);
+          if (mc) ptx::tma_load_3d_mc_2sm(ring + s * kSTile + pidx * slice_rows * 128, wout ? &tm_wout : &tm_w1, lbar,
+                                          kcol * 64, blk * 256 + w_row0 + pidx * slice_rows, l, parity_mask);
+          else ptx::tma_load_3d_2sm(ring + s * kSTile, wout ? &tm_wout : &tm_w1, lbar, kcol * 64, blk * 256 + w_row0, l);
+        } else {
+          ptx::mbar_arrive_expect_tx(&bars->full[s], kSTile);
+          if (mc) ptx::tma_load_3d_mc(ring + s * kSTile + pidx * slice_rows * 128, wout ? &tm_wout : &tm_w1, &bars->full[s],
+                                      kcol * 64, blk * 256 + w_row0 + pidx * slice_rows, l, parity_mask);
+          else ptx::tma_load_3d(ring + s * kSTile, wout ? &tm_wout : &tm_w1, &bars->full[s], kcol * 64, blk * 256 + w_row0, l);
+        }
         if (++s == a.nentries) { s = 0; ph ^= 1; }
         if (++i == n_layer) { i = 0; ++l; }
       }
@@ -262,6 +303,19 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         ptx::mbar_arrive_expect_tx(&bars->cd_full[hb], kSTile);
         ptx::tma_load_3d(cond_smem + hb * kSTile, &tm_cond, &bars->cd_full[hb], hb * 64, t_cta0, b);
       }
+      // precomputed projection: gate-half tiles of layer l (frames past T: zero fill); filter half -> L2, one layer ahead
+      const bool pf_ok = kUseP && (t_cta0 >> 7) < a.tiles_per_track;
+      const uint32_t pf_layer_bytes = (uint32_t)NB * 32768u;
+      const uint8_t* pf_tile = reinterpret_cast<const uint8_t*>(a.pfilt) + (size_t)tile_idx * L * pf_layer_bytes;
+      auto load_pgate = [&](int l) {
+        for (int hb = 0; hb < PB; ++hb) {
+          ptx::mbar_arrive_expect_tx(&bars->cd_full[hb], kSTile);
+          ptx::tma_load_3d(g_smem + hb * kSTile, &tm_cond, &bars->cd_full[hb], hb * 64, t_cta0, b * L + l);
+        }
+        if (pf_ok && l + 1 < L) prefetch_l2_bulk(pf_tile + (size_t)(l + 1) * pf_layer_bytes, pf_layer_bytes);
+      };
+      if (pf_ok) prefetch_l2_bulk(pf_tile, pf_layer_bytes);
+      load_pgate(0);
       ptx::mbar_arrive_expect_tx(&bars->xw_full, CB * kSWinBytes);
       for (int cb = 0; cb < CB; ++cb)
         ptx::tma_load_3d(xw_smem + cb * kSWinBytes, &tm_xw0, &bars->xw_full, cb * 64, t_cta0 - kSHalo, b);
@@ -269,12 +323,13 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         const uint32_t pp = (uint32_t)(l - 1) & 1u;
         const CUtensorMap* tm_e = pp ? &tm_e1 : &tm_e0;
         if (a.dsmem_halo) {  // the halo rows travel through distributed shared memory: only the conditioner tiles here
-          if (a.cond_resident) break;  // ... and not even those
+          if (a.cond_resident && !kUseP) break;  // ... and not even those
           ptx::mbar_wait(&bars->gc_free, pp);
           for (int hb = 0; hb < HB; ++hb) {
             ptx::mbar_arrive_expect_tx(&bars->cd_full[hb], kSTile);
             ptx::tma_load_3d(g_smem + hb * kSTile, &tm_cond, &bars->cd_full[hb], hb * 64, t_cta0, b);
           }
+          load_pgate(l);
           continue;
         }
         // publish the first / last 8 rows of layer l-1's output (the epilogue has written them in place)
@@ -309,13 +364,14 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         }
         if (l == 1) SVSK_STAMP(13);
         // conditioner tiles of layer l, once the G buffer is free again
-        if (a.cond_resident) continue;
+        if (a.cond_resident && !kUseP) continue;
         ptx::mbar_wait(&bars->gc_free, pp);
         if (l == 1) SVSK_STAMP(14);
         for (int hb = 0; hb < HB; ++hb) {
           ptx::mbar_arrive_expect_tx(&bars->cd_full[hb], kSTile);
           ptx::tma_load_3d(g_smem + hb * kSTile, &tm_cond, &bars->cd_full[hb], hb * 64, t_cta0, b);
         }
+        load_pgate(l);
       }
     }
   } else if (warp == 1) {
@@ -409,11 +465,15 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         if (l == 1) SVSK_STAMP(5);
         // ---- all taps, blocks 1..
         for (int j = 1; j < NB; ++j) {
+          if (HB == 0 && l != 0) {  // no conditioner k-blocks ahead of these: the block's first MMAs overwrite the accumulator
+            ptx::mbar_wait(&bars->d2_drained[j], pp);
+            ptx::tc_fence_after();
+          }
           for (int jt = 0; jt < 3; ++jt) {
             const uint32_t row_lo = xw_lo + (uint32_t)(kSHalo + (jt - 1) * d) * 8u;
             for (int cb = 0; cb < CB; ++cb) {
               SVSK_WAIT_ENTRY();
-              SVSK_ISSUE4(j * 256, row_lo + cb * (kSWinBytes >> 4), ring_lo + s * (kSTile >> 4), 1);
+              SVSK_ISSUE4(j * 256, row_lo + cb * (kSWinBytes >> 4), ring_lo + s * (kSTile >> 4), (HB == 0 && jt == 0 && cb == 0) ? 0 : 1);
             }
           }
           ptx::umma_commit2_mc(&bars->d1_full[j], pair_mask);
@@ -451,8 +511,10 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         const uint32_t pl = (uint32_t)l & 1u;
         int i = 0;
         auto forward_entries = [&](int n) {
+          if (a.peer_tx) return;  // the weight loads count on the leader's barrier themselves
           for (int k = 0; k < n; ++k, ++i) {
-            ptx::mbar_wait(&bars->full[s], ph);
+            if (a.spin) ptx::mbar_wait_spin(&bars->full[s], ph);
+            else ptx::mbar_wait(&bars->full[s], ph);
             ptx::mbar_arrive_cluster(leader_full0 + (uint32_t)s * 8u);
             if (++s == a.nentries) { s = 0; ph ^= 1; }
           }
@@ -504,12 +566,22 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
     const uint32_t nb_row = send_left ? (uint32_t)(kSHalo + 128 + row) : (uint32_t)(row - (128 - kSHalo));
     const uint32_t nb_xw = ptx::mapa(ptx::smem_u32(xw_smem), nb_rank);       // the neighbour's window, cluster address
     const uint32_t nb_bar = ptx::mapa(ptx::smem_u32(&bars->xh_full), nb_rank);
+    // precomputed conditioner projection, filter half: this thread's 32 bytes of chunk ci of (layer l, block j) are the two
+    // uint4 at pf_row + ((l * NB + j) * 8 + ci) * 256
+    const bool pf_ok = kUseP && (t_cta0 >> 7) < a.tiles_per_track;
+    const uint4* pf_row = a.pfilt + (size_t)(b * a.tiles_per_track + (t_cta0 >> 7)) * L * NB * 2048 + row * 2;
+    constexpr int kChunks = 8 / kSW;  // 16-column chunks per thread and gating block
+    static_assert(kChunks % 2 == 0, "the two prefetch slots alternate per chunk across blocks");
 
     for (int l = 0; l < L; ++l) {
       const uint32_t pl = (uint32_t)l & 1u;
       const int d = a.dilation[l];
       const uint32_t tcol = tmem + tlane + (a.pingpong ? pl * 256u : 0u);   // this thread's lane, this layer's accumulator
       const bool has_l = (t - d) >= 0, has_r = (t + d) < T;
+      // A track's first / last d frames lack a tap's bias term.  Warp-uniform, so that the correction is a BRANCH around the
+      // rare case: written per element (if (!has_l) ...) it compiled to 64 predicated-off loads + 64 adds per 16-column
+      // chunk in every thread — a third of the gating loop's instructions (profiles/r02p_stack_gating_sass.txt).
+      const bool warp_edge = __any_sync(0xffffffffu, !has_l || !has_r);
       const bool last = (l == L - 1);
       // per-column biases of this layer -> smem: sb_full = centre + left + right tap terms (an interior frame's sum)
       {
@@ -523,6 +595,15 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
           bo_s[i] = bo[i];
         }
         ptx::named_bar_sync(1, kSEpi);
+      }
+      // filter half of the projection: chunks n and n + 1 of the layer's kChunks * NB are in flight while chunk n - 1 is gated
+      uint4 pfq[2][2] = {};
+      if (pf_ok) {
+        const uint4* p0 = pf_row + (size_t)(l * NB * 8 + sub) * 256;
+        pfq[0][0] = ldg_stream_v4(p0);
+        pfq[0][1] = ldg_stream_v4(p0 + 1);
+        pfq[1][0] = ldg_stream_v4(p0 + kSW * 256);
+        pfq[1][1] = ldg_stream_v4(p0 + kSW * 256 + 1);
       }
 
       // ---- epilogue 1: gating -> G
@@ -544,29 +625,56 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
           const uint32_t* rg = rgb[i & 1];
           const uint32_t* rf = rfb[i & 1];
           const int pg = j * 256 + c0, pf = pg + 128;
-          float z[16];
+          const int kc0 = j * 128 + c0;  // first gated channel of the chunk = K index of GEMM2
+          uint8_t* gk = g_smem + (kc0 >> 6) * kSTile;
+          const uint32_t ch16 = (uint32_t)((kc0 & 63) >> 3);
+          uint32_t pfw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          if (kUseP) {
+            // gate half: the bf16 values sit where this thread will store z (tile kc0 / 64 of the G buffer); read 8 bytes
+            // at a time next to their use
+            if ((i & (4 / kSW - 1)) == 0) ptx::mbar_wait(&bars->cd_full[kc0 >> 6], pl);
+            const uint4 fa = pfq[i & 1][0], fb = pfq[i & 1][1];
+            pfw[0] = fa.x; pfw[1] = fa.y; pfw[2] = fa.z; pfw[3] = fa.w;
+            pfw[4] = fb.x; pfw[5] = fb.y; pfw[6] = fb.z; pfw[7] = fb.w;
+            // refill the slot with chunk n + 2 of this layer
+            const int n2 = j * kChunks + i + 2;
+            if (pf_ok && n2 < NB * kChunks) {
+              const int j2 = n2 / kChunks, ci2 = kSW * (n2 % kChunks) + sub;
+              const uint4* p2 = pf_row + (size_t)((l * NB + j2) * 8 + ci2) * 256;
+              pfq[i & 1][0] = ldg_stream_v4(p2);
+              pfq[i & 1][1] = ldg_stream_v4(p2 + 1);
+            }
+          }
+          float gv[16], fv[16];
 #pragma unroll
           for (int e = 0; e < 16; e += 4) {
             const float4 bg = ptx::ld_shared_v4f(sb_full + pg + e);
             const float4 bf = ptx::ld_shared_v4f(sb_full + pf + e);
-            float gv[4] = {__uint_as_float(rg[e]) + bg.x, __uint_as_float(rg[e + 1]) + bg.y,
-                           __uint_as_float(rg[e + 2]) + bg.z, __uint_as_float(rg[e + 3]) + bg.w};
-            float fv[4] = {__uint_as_float(rf[e]) + bf.x, __uint_as_float(rf[e + 1]) + bf.y,
-                           __uint_as_float(rf[e + 2]) + bf.z, __uint_as_float(rf[e + 3]) + bf.w};
+            gv[e] = __uint_as_float(rg[e]) + bg.x; gv[e + 1] = __uint_as_float(rg[e + 1]) + bg.y;
+            gv[e + 2] = __uint_as_float(rg[e + 2]) + bg.z; gv[e + 3] = __uint_as_float(rg[e + 3]) + bg.w;
+            fv[e] = __uint_as_float(rf[e]) + bf.x; fv[e + 1] = __uint_as_float(rf[e + 1]) + bf.y;
+            fv[e + 2] = __uint_as_float(rf[e + 2]) + bf.z; fv[e + 3] = __uint_as_float(rf[e + 3]) + bf.w;
+            if (kUseP) {
+              const uint2 pgw = ptx::ld_shared_v2(gk + ptx::sw128_offset((uint32_t)row, ch16 + (uint32_t)(e >> 3)) + (e & 4) * 2);
+              gv[e] += ptx::bf16_lo(pgw.x); gv[e + 1] += ptx::bf16_hi(pgw.x);
+              gv[e + 2] += ptx::bf16_lo(pgw.y); gv[e + 3] += ptx::bf16_hi(pgw.y);
+              fv[e] += ptx::bf16_lo(pfw[e >> 1]); fv[e + 1] += ptx::bf16_hi(pfw[e >> 1]);
+              fv[e + 2] += ptx::bf16_lo(pfw[(e >> 1) + 1]); fv[e + 3] += ptx::bf16_hi(pfw[(e >> 1) + 1]);
+            }
+          }
+          if (warp_edge) {
             if (!has_l) {
 #pragma unroll
-              for (int u = 0; u < 4; ++u) { gv[u] -= sb_l[pg + e + u]; fv[u] -= sb_l[pf + e + u]; }
+              for (int u = 0; u < 16; ++u) { gv[u] -= sb_l[pg + u]; fv[u] -= sb_l[pf + u]; }
             }
             if (!has_r) {
 #pragma unroll
-              for (int u = 0; u < 4; ++u) { gv[u] -= sb_r[pg + e + u]; fv[u] -= sb_r[pf + e + u]; }
+              for (int u = 0; u < 16; ++u) { gv[u] -= sb_r[pg + u]; fv[u] -= sb_r[pf + u]; }
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) z[e + u] = ptx::sigmoid_approx(gv[u]) * ptx::tanh_approx(fv[u]);
           }
-          const int kc0 = j * 128 + c0;  // first gated channel of the chunk = K index of GEMM2
-          uint8_t* gk = g_smem + (kc0 >> 6) * kSTile;
-          const uint32_t ch16 = (uint32_t)((kc0 & 63) >> 3);
+          float z[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) z[u] = ptx::sigmoid_approx(gv[u]) * ptx::tanh_approx(fv[u]);
           ptx::st_shared_v4(gk + ptx::sw128_offset((uint32_t)row, ch16), ptx::pack_bf16(z[0], z[1]),
                             ptx::pack_bf16(z[2], z[3]), ptx::pack_bf16(z[4], z[5]), ptx::pack_bf16(z[6], z[7]));
           ptx::st_shared_v4(gk + ptx::sw128_offset((uint32_t)row, ch16 + 1), ptx::pack_bf16(z[8], z[9]),
@@ -747,7 +855,7 @@ static int stack_smem(int C, int H, int* nentries_out, int* cond_resident_out = 
   int fixed = CB * kSWinBytes + gc_tiles * kSTile + 4 * 2 * C * (int)sizeof(float) + (int)sizeof(DiffnetStackBarriers) + 1024;
   // C = 128: resident conditioner tiles if that still leaves a ring of 5 (the depth the C = 256 kernel runs with)
   int resident = 0;
-  if (C == 128 && !getenv("SVSK_STACK_NO_PINGPONG") && (kSSmemLimit - fixed - HB * kSTile) / kSTile >= 5) {
+  if (C == 128 && HB > 0 && !getenv("SVSK_STACK_NO_PINGPONG") && (kSSmemLimit - fixed - HB * kSTile) / kSTile >= 5) {
     resident = 1;
     fixed += HB * kSTile;
   }
@@ -758,17 +866,21 @@ static int stack_smem(int C, int H, int* nentries_out, int* cond_resident_out = 
   return fixed + nentries * kSTile;
 }
 
-static int stack_prepare(int C, int H, int* nentries, int* smem_bytes, int* cond_resident = nullptr) {
+// use_p: the conditioner projection is precomputed (no conditioner tiles in shared memory, none resident)
+static int stack_prepare(int C, int H, int* nentries, int* smem_bytes, int* cond_resident = nullptr, bool use_p = false) {
   SVSK_REQUIRE(C == 128 || C == 256, SVSK_E_ARG, "diffnet_stack_bf16: C=%d (need 128 or 256)", C);
   SVSK_REQUIRE(H > 0 && H % 64 == 0 && H <= 512, SVSK_E_ARG, "diffnet_stack_bf16: H=%d (need a multiple of 64, at most 512)", H);
-  *smem_bytes = stack_smem(C, H, nentries, cond_resident);
+  *smem_bytes = stack_smem(C, use_p ? 0 : H, nentries, cond_resident);
+  if (use_p && cond_resident) *cond_resident = 0;
   SVSK_REQUIRE(*nentries >= 3, SVSK_E_ARG, "diffnet_stack_bf16: not enough shared memory");
   int dev = 0;
   cudaGetDevice(&dev);
   static bool attr_set[64] = {false};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(diffnet_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemLimit);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(diffnet_stack_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaError_t e = cudaFuncSetAttribute(diffnet_stack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(diffnet_stack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(diffnet_stack_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(diffnet_stack_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return fail((int)e, "diffnet_stack_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
@@ -823,7 +935,7 @@ static int stack_one_tile_fits(int B, int T, int C, int H) {
   cudaLaunchAttribute attr[2];
   stack_launch_config(&cfg, attr, B, T, smem_bytes, nullptr);
   int max_clusters = 0;
-  if (cudaOccupancyMaxActiveClusters(&max_clusters, diffnet_stack_kernel, &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, diffnet_stack_kernel<false>, &cfg) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
@@ -836,6 +948,53 @@ extern "C" int svsk_diffnet_stack_fits(int B, int T, int C, int H) {
   if (B <= 0 || T <= 0 || B > 65535) return 0;
   if (stack_use_duo(B, C, H, T)) return diffnet_stack_duo_fits(B, T);
   return stack_one_tile_fits(B, T, C, H);
+}
+
+extern "C" int svsk_diffnet_stack_uses_pcond(int B, int T, int C, int H) {
+  int rc = require_sm100();
+  if (rc) return -1;
+  if (B <= 0 || T <= 0 || B > 65535 || getenv("SVSK_STACK_NO_PCOND")) return 0;
+  if (stack_use_duo(B, C, H, T)) return 0;
+  return stack_one_tile_fits(B, T, C, H);
+}
+
+// [L*NB][B*T][256] (gate 128 | filter 128 per block) -> gate half channel-last [B][L][T][C], filter half in the epilogue
+// threads' order [B][tiles][L][NB][8][128][16]; one CTA per (128-frame tile, layer-block), 16 bytes per thread and step.
+__global__ void __launch_bounds__(256) diffnet_pcond_pack_kernel(const uint4* __restrict__ p, uint4* __restrict__ pg,
+                                                                 uint4* __restrict__ pf, int B, int T, int L, int NB, int tiles) {
+  const int lj = blockIdx.y, l = lj / NB, j = lj - l * NB;
+  const int b = blockIdx.x / tiles, tile = blockIdx.x - b * tiles;
+  const int C = NB * 128;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  const uint4* src = p + ((size_t)lj * B + b) * T * 32;                                  // 32 uint4 per frame
+  uint4* pf_blk = pf + (((size_t)(b * tiles + tile) * L + l) * NB + j) * 2048;
+  for (int q = threadIdx.x; q < 128 * 32; q += 256) {
+    const int row = q >> 5, c16 = q & 31;  // 8 columns c16*8 .. +7 of frame tile*128 + row
+    const int t = tile * 128 + row;
+    const uint4 v = t < T ? src[(size_t)t * 32 + c16] : zero;
+    if (c16 < 16) {
+      if (t < T) pg[(((size_t)b * L + l) * T + t) * (C / 8) + j * 16 + c16] = v;
+    } else {
+      const int cc = c16 - 16;             // filter columns cc*8 .. +7: chunk cc / 2, half cc & 1
+      pf_blk[((cc >> 1) * 128 + row) * 2 + (cc & 1)] = v;
+    }
+  }
+}
+
+extern "C" int svsk_diffnet_pcond_pack_bf16(const void* p, void* pcond_gate, void* pcond_filt, int B, int T, int L, int C,
+                                            void* stream) {
+  SVSK_REQUIRE(p && pcond_gate && pcond_filt, SVSK_E_ARG, "diffnet_pcond_pack_bf16: null tensor");
+  SVSK_REQUIRE(C == 128 || C == 256, SVSK_E_ARG, "diffnet_pcond_pack_bf16: C=%d (need 128 or 256)", C);
+  SVSK_REQUIRE(B > 0 && T > 0 && L >= 1 && L <= kSMaxLayers, SVSK_E_ARG, "diffnet_pcond_pack_bf16: bad B/T/L");
+  SVSK_REQUIRE(((uintptr_t)p % 16) == 0 && ((uintptr_t)pcond_gate % 16) == 0 && ((uintptr_t)pcond_filt % 16) == 0, SVSK_E_ALIGN,
+               "diffnet_pcond_pack_bf16: tensors must be 16-byte aligned");
+  const int NB = C / 128, tiles = 2 * ceil_div(T, 256);
+  SVSK_REQUIRE((long long)B * tiles < (1ll << 31) && L * NB <= 65535, SVSK_E_ARG, "diffnet_pcond_pack_bf16: grid too large");
+  int rc = require_sm100();
+  if (rc) return rc;
+  diffnet_pcond_pack_kernel<<<dim3((unsigned)(B * tiles), (unsigned)(L * NB)), 256, 0, as_stream(stream)>>>(
+      static_cast<const uint4*>(p), static_cast<uint4*>(pcond_gate), static_cast<uint4*>(pcond_filt), B, T, L, NB, tiles);
+  return check_launch("diffnet_pcond_pack_bf16");
 }
 
 extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void* stream) {
@@ -857,15 +1016,20 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
                "diffnet_stack_bf16: skip32 / edge0 / edge1 must be 16-byte aligned");
   int rc = require_sm100();
   if (rc) return rc;
+  SVSK_REQUIRE((p.pcond_gate == nullptr) == (p.pcond_filt == nullptr), SVSK_E_ARG,
+               "diffnet_stack_bf16: pcond_gate and pcond_filt go together");
+  SVSK_REQUIRE(((uintptr_t)p.pcond_gate % 16) == 0 && ((uintptr_t)p.pcond_filt % 16) == 0, SVSK_E_ALIGN,
+               "diffnet_stack_bf16: pcond_gate / pcond_filt must be 16-byte aligned");
   if (stack_use_duo(p.B, p.C, p.H, p.T)) return diffnet_stack_duo_launch(p, stream);
+  const bool use_p = p.pcond_gate != nullptr && !getenv("SVSK_STACK_NO_PCOND");
   int nentries = 0, smem_bytes = 0, cond_resident = 0;
-  if ((rc = stack_prepare(p.C, p.H, &nentries, &smem_bytes, &cond_resident))) return rc;
+  if ((rc = stack_prepare(p.C, p.H, &nentries, &smem_bytes, &cond_resident, use_p))) return rc;
 
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[2];
   stack_launch_config(&cfg, attr, p.B, p.T, smem_bytes, stream);
   int max_clusters = 0;
-  cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, diffnet_stack_kernel, &cfg);
+  cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, diffnet_stack_kernel<false>, &cfg);
   if (oe != cudaSuccess) return fail((int)oe, "diffnet_stack_bf16: cudaOccupancyMaxActiveClusters: %s", cudaGetErrorString(oe));
   const int n_clusters = (int)(cfg.gridDim.x / attr[0].val.clusterDim.x) * p.B;
   SVSK_REQUIRE(n_clusters <= max_clusters, SVSK_E_ARG,
@@ -874,7 +1038,8 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
 
   // one cluster per track: each CTA pair fetches (and multicasts) 1/n_pairs of every weight half-tile
   const uint32_t csz = attr[0].val.clusterDim.x;
-  const uint32_t w_box_rows = csz > 2 ? 128u / (csz / 2) : 128u;
+  const bool no_mc = getenv("SVSK_STACK_NO_MULTICAST") != nullptr;
+  const uint32_t w_box_rows = (csz > 2 && !no_mc) ? 128u / (csz / 2) : 128u;
   CUtensorMap tm_xw0, tm_e0, tm_e1, tm_cond, tm_w1, tm_wout, tm_skip;
   {
     uint64_t dims[3] = {(uint64_t)p.C, (uint64_t)p.T, (uint64_t)p.B};
@@ -888,7 +1053,12 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
     uint32_t box4[3] = {32, 32, 1};  // one warp's 32 rows of a 32-column skip slab
     if ((rc = make_tmap_f32(&tm_skip, p.skip32, 3, dims, str4, box4))) return rc;
   }
-  {
+  if (use_p) {  // gate half of the precomputed projection, [B * L][T][C]
+    uint64_t dims[3] = {(uint64_t)p.C, (uint64_t)p.T, (uint64_t)p.B * p.L};
+    uint64_t str[2] = {(uint64_t)p.C * 2, (uint64_t)p.T * p.C * 2};
+    uint32_t box[3] = {64, 128, 1};
+    if ((rc = make_tmap_bf16(&tm_cond, p.pcond_gate, 3, dims, str, box))) return rc;
+  } else {
     uint64_t dims[3] = {(uint64_t)p.H, (uint64_t)p.T, (uint64_t)p.B};
     uint64_t str[2] = {(uint64_t)p.H * 2, (uint64_t)p.T * p.H * 2};
     uint32_t box[3] = {64, 128, 1};
@@ -920,7 +1090,12 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
   a.nentries = nentries;
   a.pingpong = (p.C == 128 && !getenv("SVSK_STACK_NO_PINGPONG")) ? 1 : 0;
   a.cond_resident = cond_resident;
-  a.cond_first = (!a.dsmem_halo && getenv("SVSK_STACK_COND_FIRST")) ? 1 : 0;  // experiment switch, see DiffnetStackArgs
+  a.cond_first = (!a.dsmem_halo && !use_p && getenv("SVSK_STACK_COND_FIRST")) ? 1 : 0;  // experiment switch, see DiffnetStackArgs
+  a.peer_tx = getenv("SVSK_STACK_PEER_TX") ? 1 : 0;
+  a.no_mc = no_mc ? 1 : 0;
+  a.spin = getenv("SVSK_STACK_SPIN") ? 1 : 0;
+  a.use_p = use_p ? 1 : 0;
+  a.pfilt = static_cast<const uint4*>(p.pcond_filt);
   a.tiles_per_track = 2 * ceil_div(p.T, 256);
   for (int l = 0; l < kSMaxLayers; ++l) a.dilation[l] = l < p.L ? p.dilation[l] : 1;
   a.dbg = nullptr;
@@ -931,7 +1106,8 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
     e = cudaMemsetAsync(p.flags, 0, sizeof(int) * (size_t)p.B * a.tiles_per_track, as_stream(stream));
     if (e != cudaSuccess) return fail((int)e, "diffnet_stack_bf16: flag reset: %s", cudaGetErrorString(e));
   }
-  e = cudaLaunchKernelEx(&cfg, diffnet_stack_kernel, tm_xw0, tm_e0, tm_e1, tm_cond, tm_w1, tm_wout, tm_skip, a);
+  if (use_p) e = cudaLaunchKernelEx(&cfg, diffnet_stack_kernel<true>, tm_xw0, tm_e0, tm_e1, tm_cond, tm_w1, tm_wout, tm_skip, a);
+  else e = cudaLaunchKernelEx(&cfg, diffnet_stack_kernel<false>, tm_xw0, tm_e0, tm_e1, tm_cond, tm_w1, tm_wout, tm_skip, a);
   if (e != cudaSuccess) return fail((int)e, "diffnet_stack_bf16: launch: %s", cudaGetErrorString(e));
   return check_launch("diffnet_stack_bf16");
 }

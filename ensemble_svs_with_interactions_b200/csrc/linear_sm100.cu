@@ -24,6 +24,9 @@ struct LinearArgs {
   long long t_bstride;
   int t_rows, t_ld;
   int nstages;
+  // gridDim.y > 1 with row-major outputs (svsk_diffnet_cond_project_bf16): chunk blockIdx.y of Cout weight rows is
+  // written to y_b + blockIdx.y * y_chunk_stride (elements)
+  long long y_chunk_stride;
 };
 
 struct __align__(8) LinearBarriers {
@@ -115,6 +118,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       const long long trk = n / a.t_rows;
       yt = a.y_t + trk * a.t_bstride + (n - trk * a.t_rows) + (size_t)blockIdx.y * a.Cout * a.t_ld;
     }
+    __nv_bfloat16* const y_b = a.y_b ? a.y_b + (size_t)blockIdx.y * a.y_chunk_stride : nullptr;
     for (int c0 = 0; c0 < a.Cout; c0 += 16) {
       uint32_t r[16];
       ptx::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, r);
@@ -137,8 +141,8 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             for (int i = 0; i < 16; ++i) dst[i] = v[i];
           }
         }
-        if (a.y_b) {
-          __nv_bfloat16* dst = a.y_b + n * a.ldy_b + c0;
+        if (y_b) {
+          __nv_bfloat16* dst = y_b + n * a.ldy_b + c0;
           if (vec_b) {
             uint32_t pk[8];
 #pragma unroll
@@ -218,6 +222,7 @@ extern "C" int svsk_linear_bf16(const svsk_linear_bf16_params* pp, void* stream)
   a.t_bstride = 0;
   a.t_rows = 1;
   a.t_ld = 0;
+  a.y_chunk_stride = 0;
   unsigned grid = (unsigned)((p.N + 127) / 128);
   linear_bf16_kernel<<<grid, 192, smem_bytes, as_stream(stream)>>>(tm_a, tm_w, a);
   return check_launch("linear_bf16");
@@ -274,6 +279,7 @@ extern "C" int svsk_usfgan_aux_frames(const void* cin, const void* w, void* q, i
     a.t_bstride = (long long)R * q_ld;
     a.t_rows = Tf;
     a.t_ld = q_ld;
+    a.y_chunk_stride = 0;
     // K = Ap is one or two k-blocks: as many stages as k-blocks, so that three or four CTAs fit an SM — the kernel is a
     // latency chain per CTA (load, a few MMAs, 2-byte transposed stores), 0.45 -> 0.2 ms at config 3
     a.nstages = (Ap + 63) / 64 < kLinStages ? (Ap + 63) / 64 : kLinStages;
@@ -285,4 +291,60 @@ extern "C" int svsk_usfgan_aux_frames(const void* cin, const void* w, void* q, i
     if (chunk) break;
   }
   return 0;
+}
+
+// conditioner_projection(cond) of all layers of a DiffNet (denoiser.py:59) in ONE launch, for a sampling run that reuses
+// it across its K denoiser calls: p[blk][n][0..255] = cond[n][:] . wcp[blk*256 + r][:], blk = layer * (2C/256) + output block
+// (gridDim.y chunks of 256 weight rows; two ring stages so that two CTAs share an SM).  svsk_diffnet_pcond_pack_bf16 then
+// lays the result out for svsk_diffnet_stack_bf16.
+extern "C" int svsk_diffnet_cond_project_bf16(const void* cond, const void* wcp, void* p, long long N, int H, int nblk,
+                                              void* stream) {
+  SVSK_REQUIRE(cond && wcp && p, SVSK_E_ARG, "diffnet_cond_project_bf16: null tensor");
+  SVSK_REQUIRE(N > 0 && N < (1ll << 31), SVSK_E_ARG, "diffnet_cond_project_bf16: N=%lld", N);
+  SVSK_REQUIRE(H > 0 && H % 64 == 0 && H <= 512, SVSK_E_ARG, "diffnet_cond_project_bf16: H=%d (need a multiple of 64, at most 512)", H);
+  SVSK_REQUIRE(nblk >= 1 && nblk <= 65535, SVSK_E_ARG, "diffnet_cond_project_bf16: nblk=%d", nblk);
+  SVSK_REQUIRE(((uintptr_t)p % 16) == 0, SVSK_E_ALIGN, "diffnet_cond_project_bf16: p must be 16-byte aligned");
+  int rc = require_sm100();
+  if (rc) return rc;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static bool attr_set[64] = {false};
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(linear_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return fail((int)e, "diffnet_cond_project_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  CUtensorMap tm_a, tm_w;
+  {
+    uint64_t dims[2] = {(uint64_t)H, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)H * 2};
+    uint32_t box[2] = {64, 128};
+    if ((rc = make_tmap_bf16(&tm_a, cond, 2, dims, str, box))) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)H, (uint64_t)nblk * 256};
+    uint64_t str[1] = {(uint64_t)H * 2};
+    uint32_t box[2] = {64, 256};
+    if ((rc = make_tmap_bf16(&tm_w, wcp, 2, dims, str, box))) return rc;
+  }
+  LinearArgs a;
+  a.bias = nullptr;
+  a.y_b = static_cast<__nv_bfloat16*>(p);
+  a.y_f = nullptr;
+  a.N = N;
+  a.K = H;
+  a.Cout = 256;
+  a.ldy_b = 256;
+  a.ldy_f = 0;
+  a.act = SVSK_ACT_NONE;
+  a.tmem_cols = 256;
+  a.y_t = nullptr;
+  a.t_bstride = 0;
+  a.t_rows = 1;
+  a.t_ld = 0;
+  a.y_chunk_stride = N * 256;
+  a.nstages = 2;
+  const int smem_bytes = a.nstages * (kLinABytes + 256 * 128) + (int)sizeof(LinearBarriers) + 1024;
+  linear_bf16_kernel<<<dim3((unsigned)((N + 127) / 128), (unsigned)nblk), 192, smem_bytes, as_stream(stream)>>>(tm_a, tm_w, a);
+  return check_launch("diffnet_cond_project_bf16");
 }

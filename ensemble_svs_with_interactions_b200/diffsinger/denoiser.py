@@ -133,6 +133,7 @@ class _Bf16Plan:
             self.w1p_all = torch.empty((L, 2 * C, K1), device=device, dtype=bf16)
             self.woutp_all = torch.empty((L, 2 * C, C), device=device, dtype=bf16)
             self.bout_all = torch.empty((L, 2 * C), device=device, dtype=f32)
+            self.wcp_all = None  # [L * 2C/256, 256, H]: conditioner columns of w1p_all per 256-row output block (below)
             self.dilations = [int(layer.dilation) for layer in net.residual_layers]
             self.layers = []
             for i, layer in enumerate(net.residual_layers):
@@ -156,6 +157,7 @@ class _Bf16Plan:
                     stepw=stepw.unsqueeze(-1).contiguous(), stepb=stepb,
                     dpw=layer.diffusion_projection.weight.detach().to(f32).contiguous(),
                     dpb=layer.diffusion_projection.bias.detach().to(f32).contiguous()))
+            self.wcp_all = self.w1p_all[:, :, 3 * C:].reshape(L * (2 * C // 256), 256, H).contiguous()
         self.step_table = None  # [L, K, 3*2C], filled by GaussianDiffusion for t = 0..K-1
 
 
@@ -231,9 +233,22 @@ class DiffNet(nn.Module):
         ops.linear_bf16(ops.cast_scale_bf16(x32s), plan.w_in, plan.b_in, act=ops.ACT_RELU, out_bf16=xb0)
         return xb0
 
-    def residual_stack_bf16(self, xb0, condb, stepbias, plan=None):
+    def cond_projection_bf16(self, condb, plan=None):
+        """conditioner_projection(cond) of ALL layers (denoiser.py:59) for a run of denoiser calls on the same cond
+        (the K steps of diffusion.py:302-336): computed once, handed to every residual_stack_bf16 call of the run as
+        ``pcond``.  Returns None when the stack kernel that would run this shape projects inside its GEMM."""
+        plan = self.bf16_plan() if plan is None else plan
+        B, T, H = condb.shape
+        stack_b = _stack_tracks_per_launch(B, T, plan.C, H) if os.environ.get("SVSK_DIFFNET_STACK", "1") != "0" else 0
+        if not stack_b or not ops.diffnet_stack_uses_pcond(stack_b, T, plan.C, H):
+            return None
+        p = ops.diffnet_cond_project(condb.contiguous(), plan.wcp_all)
+        return ops.diffnet_pcond_pack(p, B, T, plan.L, plan.C)
+
+    def residual_stack_bf16(self, xb0, condb, stepbias, plan=None, pcond=None):
         """The L residual blocks (denoiser.py:114-118) on xb0 [B,T,C] bf16 (clobbered); returns the fp32 sum of the skip
-        outputs [B,T,C].  stepbias [L, Bt, 3*2C] fp32 (any layer stride; Bt = B rows, or 1 row shared by the batch)."""
+        outputs [B,T,C].  stepbias [L, Bt, 3*2C] fp32 (any layer stride; Bt = B rows, or 1 row shared by the batch).
+        pcond: result of cond_projection_bf16(condb) for a run of calls on the same conditioner."""
         plan = self.bf16_plan() if plan is None else plan
         B, T, C = xb0.shape
         L = plan.L
@@ -258,7 +273,8 @@ class DiffNet(nn.Module):
                 b1 = min(B, b0 + stack_b)
                 ops.diffnet_stack_bf16(xb0[b0:b1], xb1[b0:b1], xb2[b0:b1], skip32[b0:b1], condb[b0:b1], plan.w1p_all,
                                        plan.woutp_all, stepbias[:, b0:b1] if per_row else stepbias, plan.bout_all, flags,
-                                       plan.dilations, stepbias_batch_stride=sb_batch, stepbias_layer_stride=sb_layer)
+                                       plan.dilations, stepbias_batch_stride=sb_batch, stepbias_layer_stride=sb_layer,
+                                       pcond=None if pcond is None else (pcond[0][b0:b1], pcond[1][b0:b1]))
         else:
             cur, nxt = xb0, xb1
             for i, lw in enumerate(plan.layers):

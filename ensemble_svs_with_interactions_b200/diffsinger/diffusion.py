@@ -198,8 +198,10 @@ class GaussianDiffusion(BaseModel):
             sched = [tabs[k] for k in ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
                                        "posterior_mean_coef2", "posterior_log_variance_clipped")]
             xb0 = den.project_in_bf16(x32s, plan)
+            # cond is the same for all K calls: its projection through every layer's conditioner_projection once per run
+            pcond = den.cond_projection_bf16(condb, plan) if self.K_step > 1 else None
             for i in reversed(range(self.K_step)):
-                skip32 = den.residual_stack_bf16(xb0, condb, table[:, i:i + 1], plan)   # row i of every layer's table
+                skip32 = den.residual_stack_bf16(xb0, condb, table[:, i:i + 1], plan, pcond=pcond)   # row i of every layer's table
                 eps_out = torch.empty_like(x32s) if trace is not None and i in trace else None
                 ops.diffnet_step_bf16(skip32, x32s, z_ntc[i], self._t_const[i], sched, plan.w_skip, plan.b_skip, plan.w_out,
                                       plan.b_out, skip_scale=1.0 / math.sqrt(plan.L), w_in=plan.w_in, b_in=plan.b_in,

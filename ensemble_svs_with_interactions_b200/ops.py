@@ -363,10 +363,41 @@ def diffnet_stack_fits(B, T, Cc, H):
     return L.lib().svsk_diffnet_stack_fits(int(B), int(T), int(Cc), int(H)) == 1
 
 
+def diffnet_stack_uses_pcond(B, T, Cc, H):
+    """True if svsk_diffnet_stack_bf16 would use a precomputed conditioner projection for this shape."""
+    return L.lib().svsk_diffnet_stack_uses_pcond(int(B), int(T), int(Cc), int(H)) == 1
+
+
+def diffnet_cond_project(cond, wcp):
+    """cond [B,T,H] bf16, wcp [nblk,256,H] bf16 -> p [nblk, B*T, 256] bf16 in one launch."""
+    B, T, H = cond.shape
+    nblk = wcp.shape[0]
+    p = torch.empty((nblk, B * T, 256), device=cond.device, dtype=bf16)
+    L.check(L.lib().svsk_diffnet_cond_project_bf16(L.ptr(cond, bf16, "cond"), L.ptr(wcp, bf16, "wcp"), L.ptr(p), B * T, H, nblk,
+                                                   L.stream_ptr()), "diffnet_cond_project_bf16")
+    return p
+
+
+def diffnet_pcond_pack(p, B, T, nl, Cc):
+    """p [L*2C/256, B*T, 256] bf16 (packed column order per output block) -> (pcond_gate [B,L,T,C],
+    pcond_filt [B, tiles, L, 2C/256, 8, 128, 16]) for diffnet_stack_bf16(pcond=...)."""
+    NB = Cc // 128
+    tiles = 2 * ((T + 255) // 256)
+    if tuple(p.shape) != (nl * NB, B * T, 256):
+        raise ValueError(f"diffnet_pcond_pack: p must be [{nl * NB}, {B * T}, 256], got {tuple(p.shape)}")
+    pg = torch.empty((B, nl, T, Cc), device=p.device, dtype=bf16)
+    pf = torch.empty((B, tiles, nl, NB, 8, 128, 16), device=p.device, dtype=bf16)
+    L.check(L.lib().svsk_diffnet_pcond_pack_bf16(L.ptr(p, bf16, "p"), L.ptr(pg), L.ptr(pf), B, T, nl, Cc, L.stream_ptr()),
+            "diffnet_pcond_pack_bf16")
+    return pg, pf
+
+
 def diffnet_stack_bf16(xb_in, edge0, edge1, skip32, cond, w1p_all, woutp_all, stepbias, bout_all, flags, dilations, *,
-                       stepbias_batch_stride, stepbias_layer_stride, init_skip=True):
+                       stepbias_batch_stride, stepbias_layer_stride, init_skip=True, pcond=None):
     """All residual blocks in one launch.  w1p_all [L,2C,3C+H], woutp_all [L,2C,C], bout_all [L,2C]; stepbias: any fp32
-    tensor whose element (layer l, batch row b) row starts at l*layer_stride + b*batch_stride floats."""
+    tensor whose element (layer l, batch row b) row starts at l*layer_stride + b*batch_stride floats.  pcond: optional
+    (pcond_gate, pcond_filt) of diffnet_pcond_pack for the same tracks (the conditioner projection computed once per
+    sampling run instead of inside every call)."""
     B, T, Cc = xb_in.shape
     nl = w1p_all.shape[0]
     p = L.DiffnetStackParams()
@@ -384,6 +415,11 @@ def diffnet_stack_bf16(xb_in, edge0, edge1, skip32, cond, w1p_all, woutp_all, st
     p.B, p.T, p.C, p.H, p.L = B, T, Cc, cond.shape[2], nl
     p.stepbias_batch_stride, p.stepbias_layer_stride = int(stepbias_batch_stride), int(stepbias_layer_stride)
     p.init_skip = int(init_skip)
+    if pcond is not None:
+        pg, pf = pcond
+        if tuple(pg.shape) != (B, nl, T, Cc) or pf.shape[0] != B or not pg.is_contiguous() or not pf.is_contiguous():
+            raise ValueError("diffnet_stack_bf16: pcond does not match the batch")
+        p.pcond_gate, p.pcond_filt = L.ptr(pg, bf16, "pcond_gate"), L.ptr(pf, bf16, "pcond_filt")
     L.check(L.lib().svsk_diffnet_stack_bf16(C.byref(p), L.stream_ptr()), "diffnet_stack_bf16")
 
 

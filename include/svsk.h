@@ -212,7 +212,13 @@ SVSK_API int svsk_diffnet_block3_bf16(const svsk_diffnet_block_params* p, void* 
  * svsk_diffnet_stack_fits(B,T,C,H) returns 1 if the device can hold them, 0 if not (then split the batch into groups of
  * tracks that fit, or run the layers one by one with svsk_diffnet_block3_bf16), -1 without an sm_100 device.
  * Tracks of at most 2048 frames run as one thread-block cluster each (edge rows through distributed shared memory,
- * weight tiles TMA-multicast); longer tracks exchange edge rows through edge0 / edge1 and the flags. */
+ * weight tiles TMA-multicast); longer tracks exchange edge rows through edge0 / edge1 and the flags.
+ * pcond_gate / pcond_filt (optional, both or neither): the conditioner projection of every layer,
+ * conditioner_projection(cond) (denoiser.py:59), computed ONCE for a whole sampling run — cond does not change between
+ * the K calls of diffusion.py:302-336 — and laid out by svsk_diffnet_pcond_pack_bf16.  With them the kernel skips the H
+ * conditioner k-blocks of every layer's first GEMM (K = 3C instead of 3C + H) and adds the projection in the gating
+ * epilogue; without them (a single denoiser call) the projection is part of the GEMM as before.  `cond` is required
+ * either way (the two-tiles-per-pair kernel for C = 128 always projects in the GEMM). */
 typedef struct svsk_diffnet_stack_params {
   const void* xb_in;
   void* edge0;
@@ -229,9 +235,27 @@ typedef struct svsk_diffnet_stack_params {
   int32_t stepbias_batch_stride;  /* floats; 0 = same for every batch row */
   int32_t stepbias_layer_stride;  /* floats; >= 6C */
   int32_t init_skip;
+  const void* pcond_gate; /* [B][L][T][C] bf16 or NULL */
+  const void* pcond_filt; /* [B][2*ceil(T/256)][L][2C/256][8][128][16] bf16 or NULL */
 } svsk_diffnet_stack_params;
 SVSK_API int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* p, void* stream);
 SVSK_API int svsk_diffnet_stack_fits(int B, int T, int C, int H);
+/* 1 if svsk_diffnet_stack_bf16 would use pcond_gate / pcond_filt for this shape (the one-tile-per-pair kernel runs and
+ * holds the batch), 0 if they would be ignored, -1 without an sm_100 device. */
+SVSK_API int svsk_diffnet_stack_uses_pcond(int B, int T, int C, int H);
+/* p[blk][n][0..255] = cond[n][:] . wcp[blk * 256 + r][:] for blk = 0 .. nblk-1 in one launch: conditioner_projection(cond)
+ * of every layer and 256-row output block (denoiser.py:59), computed once for a sampling run.  cond [N][H] bf16 (N = B*T
+ * frames), wcp [nblk * 256][H] bf16 (the conditioner columns of w1p, block after block), p [nblk][N][256] bf16. */
+SVSK_API int svsk_diffnet_cond_project_bf16(const void* cond, const void* wcp, void* p, long long N, int H, int nblk,
+                                            void* stream);
+/* Lays out the per-layer conditioner projections for svsk_diffnet_stack_bf16.  p [L * 2C/256][B*T][256] bf16: for
+ * layer l and 256-column output block j of the first GEMM, the projection of every frame in PACKED column order
+ * (columns 0..127 = gate rows, 128..255 = filter rows of the block: cond . w1p[l][j*256 + n][3C:]^T).
+ *   pcond_gate [B][L][T][C]: the gate half, channel-last (TMA-loaded into the tile the gate output overwrites);
+ *   pcond_filt [B][2*ceil(T/256)][L][2C/256][8][128][16]: the filter half in the order the epilogue threads read it
+ *   (128-frame tile, 16-column chunk, frame, column); frames >= T are zero. */
+SVSK_API int svsk_diffnet_pcond_pack_bf16(const void* p, void* pcond_gate, void* pcond_filt, int B, int T, int L, int C,
+                                          void* stream);
 
 /* Everything between two residual-stack launches of a DDPM sampling step in one launch per 128-frame tile:
  *   eps = output_projection(relu(skip_projection(skip32 * skip_scale)))      denoiser.py:120-123

@@ -482,6 +482,47 @@ def test_diffnet_stack_two_tiles_per_pair_c128(H, M, L, B, T):
         assert torch.equal(auto, duo)
 
 
+@pytest.mark.parametrize("C,H,M,L,B,T", [(256, 256, 80, 20, 6, 2000), (256, 256, 80, 5, 2, 2300), (128, 128, 5, 6, 3, 517),
+                                         (256, 128, 60, 4, 2, 128), (128, 256, 60, 3, 2, 40), (256, 64, 33, 3, 3, 257)])
+def test_diffnet_stack_hoisted_conditioner_projection(C, H, M, L, B, T):
+    """Inside a sampling run the conditioner projection of every layer (denoiser.py:59) is computed once and handed to the
+    stack kernel (pcond): K = 3C instead of 3C + H per layer, the projection added in the gating epilogue.  Against the
+    same launch that projects inside its GEMM: the only difference is ONE bf16 rounding of the projection (the GEMM keeps
+    it in the fp32 accumulator), so the tolerance is tighter than bf16-vs-fp32: rel-L2 <= 5e-3, max-abs <= 2e-2 * |ref|max
+    on the summed skip output.  One cluster per track (<= 2048 frames) and the global-memory halo mode (2300 frames),
+    both channel widths, ragged tile ends; deterministic."""
+    m = _random_diffnet(C, H, M, L, seed=C + L + T + 1).to(DEV)
+    ops = _ops()
+    plan = m.bf16_plan()
+    g = torch.Generator().manual_seed(T + 3)
+    xb0 = torch.relu(torch.randn(B, T, C, generator=g)).to(DEV).to(torch.bfloat16)
+    condb = torch.randn(B, T, H, generator=g).to(DEV).to(torch.bfloat16)
+    t = torch.randint(0, 100, (B,), generator=g).to(DEV)
+    sb = m.step_bias_bf16(t)
+    with torch.no_grad():
+        ref = m.residual_stack_bf16(xb0.clone(), condb, sb, plan).clone()
+        pcond = m.cond_projection_bf16(condb, plan)
+        assert pcond is not None, "the one-tile stack kernel should take the precomputed projection for this shape"
+        # the packed gate half against a plain matmul of the same bf16 operands
+        wc = plan.w1p_all[:, :, 3 * C:].float()                       # [L, 2C, H] in packed row order
+        pr = torch.einsum("bth,lnh->bltn", condb.float(), wc)           # [B, L, T, 2C]
+        NB = 2 * C // 256
+        gate_cols = torch.cat([torch.arange(j * 256, j * 256 + 128) for j in range(NB)]).to(DEV)
+        close_bf16(pcond[0], pr[..., gate_cols], 4e-3, 1e-2)
+        filt = pcond[1]                                                # [B, tiles, L, NB, 8, 128, 16]
+        tiles = filt.shape[1]
+        f_ref = torch.zeros(B, tiles * 128, L, NB, 128, device=DEV)
+        for j in range(NB):
+            f_ref[:, :T, :, j] = pr[..., j * 256 + 128:j * 256 + 256].permute(0, 2, 1, 3)
+        f_ref = f_ref.view(B, tiles, 128, L, NB, 8, 16).permute(0, 1, 3, 4, 5, 2, 6)
+        close_bf16(filt, f_ref, 4e-3, 1e-2)
+        y = m.residual_stack_bf16(xb0.clone(), condb, sb, plan, pcond=pcond).clone()
+        y2 = m.residual_stack_bf16(xb0.clone(), condb, sb, plan, pcond=pcond)
+    assert torch.isfinite(y).all() and torch.equal(y, y2)
+    r, mx = close_bf16(y, ref, 5e-3, 2e-2)
+    print(f"hoisted conditioner projection vs in-GEMM: rel_l2={r:.3e} max={mx:.3e}")
+
+
 def test_diffnet_stack_cond_first_switch():
     """SVSK_STACK_COND_FIRST=1 (experiment switch of the global-memory halo mode: conditioner k-blocks before block 0's side
     taps; measured slower and off by default) computes the same stack up to the fp32 accumulation order."""

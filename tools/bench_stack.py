@@ -26,11 +26,21 @@ e0b, e1b = torch.empty_like(xb0), torch.empty_like(xb0)
 skip32 = torch.zeros(B, T, plan.C, device="cuda")
 flags = torch.empty((B * 2 * ((T + 255) // 256),), device="cuda", dtype=torch.int32)
 assert ops.diffnet_stack_fits(B, T, plan.C, plan.H)
+# SVSK_STACK_BENCH_PCOND=1: with the conditioner projection precomputed (what a sampling run does), else inside the GEMM
+pcond = None
+if os.environ.get("SVSK_STACK_BENCH_PCOND"):
+    ta, tb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m.denoise_fn.cond_projection_bf16(cond, plan)
+    ta.record()
+    pcond = m.denoise_fn.cond_projection_bf16(cond, plan)
+    tb.record(); tb.synchronize()
+    assert pcond is not None
+    print(f"conditioner projection of all layers, once per run: {ta.elapsed_time(tb) * 1e3:.0f} us", flush=True)
 
 
 def launch():
     ops.diffnet_stack_bf16(xb0, e0b, e1b, skip32, cond, plan.w1p_all, plan.woutp_all, table[:, 50:51], plan.bout_all, flags,
-                           plan.dilations, stepbias_batch_stride=0, stepbias_layer_stride=table.stride(0))
+                           plan.dilations, stepbias_batch_stride=0, stepbias_layer_stride=table.stride(0), pcond=pcond)
 
 
 for _ in range(3):
