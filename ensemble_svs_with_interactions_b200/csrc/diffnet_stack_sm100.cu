@@ -87,11 +87,12 @@ struct DiffnetStackArgs {
   // first track on; the gate half comes through tm_cond (then a map of [B*L][T][C]).
   int use_p;
   const uint4* pfilt;
-  // The peer CTA's weight loads complete on the LEADER's ring barrier (cta_group::2 TMA, as CUTLASS's 2-SM kernels do)
-  // instead of on its own barrier + a forwarding thread's remote arrival: one hop less per ring entry.
-  int peer_tx;
-  int spin;   // experiment (SVSK_STACK_SPIN=1): weight producer and forwarder poll their barriers instead of suspending
-  int no_mc;  // experiment (SVSK_STACK_NO_MULTICAST=1): one cluster per track, but every pair loads its own weight tiles
+  // Measured and removed (gpurun_out/s24, s27; 6 x 2000 frames, hoisted projection, 371 us per launch): the peer CTA's
+  // weight loads completing on the LEADER's ring barrier (cta_group::2 TMA with the peer bit of the barrier address
+  // cleared, as CUTLASS's 2-SM kernels do) instead of a forwarding thread: 384 us; producer / forwarder polling
+  // (mbarrier.test_wait) instead of suspending: 370 us; every pair loading its own weight tiles instead of the
+  // cluster-wide multicast: 366 us with half the ring misses but 8x the L2 reads.  Their run-time switches cost the
+  // single-thread roles more than any of them gained.
   int dilation[kSMaxLayers];
   unsigned long long* dbg;
 };
@@ -197,7 +198,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
   const uint16_t pair_mask = (uint16_t)(3u << lead);
   const bool nb_left = a.dsmem_halo && crank > 0, nb_right = a.dsmem_halo && crank + 1 < csize;  // DSMEM neighbours
   // weight multicast (one cluster per track): every pair fetches rows [pidx, pidx+1) * 128/n_pairs of each half-tile
-  const bool mc = a.dsmem_halo != 0 && !a.no_mc;
+  const bool mc = a.dsmem_halo != 0;
   const int n_pairs = mc ? (int)(csize >> 1) : 1, pidx = mc ? (int)(crank >> 1) : 0;
   const int slice_rows = 128 / n_pairs;
   const uint16_t parity_mask = (uint16_t)((0x5555u << rank) & ((1u << csize) - 1u));  // CTAs with this CTA's pair rank
@@ -224,7 +225,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
     const uint32_t two = rank == 0 ? 2u : 1u;        // leader barriers also count the peer's forwarded arrival
     const uint32_t all = rank == 0 ? 2u * kSEpi : 1u; // leader barriers every epilogue thread of the pair arrives on
     for (int i = 0; i < a.nentries; ++i) {
-      ptx::mbar_init(&bars->full[i], a.peer_tx ? 1u : two);
+      ptx::mbar_init(&bars->full[i], two);
       ptx::mbar_init(&bars->empty[i], (uint32_t)n_pairs);  // one multicast tcgen05.commit per CTA pair sharing the weights
     }
     for (int i = 0; i < HB; ++i) ptx::mbar_init(&bars->cd_full[i], two);
@@ -245,13 +246,12 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
     ptx::mbar_init(&bars->g_ready[1], all);
     ptx::mbar_init(&bars->gc_free, 4 * kSW);  // one arrival per epilogue warp
     ptx::fence_mbar_init();
-    // (multicast writes into CTAs that may not have set up their barriers yet; so does a peer counting on its leader's barrier)
-    pre_issued = (mc || (a.peer_tx && rank == 1)) ? 0 : min(a.nentries, n_total);
+    pre_issued = mc ? 0 : min(a.nentries, n_total);  // (multicast writes into CTAs that may not have set up their barriers yet)
     for (int e = 0; e < pre_issued; ++e) {
       int kcol, blk;
       bool wout;
       stack_entry(e, CB, HB, NB, KB2, a.cond_first, kcol, blk, wout);
-      ptx::mbar_arrive_expect_tx(&bars->full[e], a.peer_tx ? 2 * kSTile : kSTile);
+      ptx::mbar_arrive_expect_tx(&bars->full[e], kSTile);
       ptx::tma_load_3d(ring + e * kSTile, wout ? &tm_wout : &tm_w1, &bars->full[e], kcol * 64, blk * 256 + w_row0, 0);
     }
   }
@@ -272,23 +272,18 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
       uint32_t ph = (pre_issued == a.nentries) ? 1u : 0u;
       int l = pre_issued / n_layer, i = pre_issued - l * n_layer;
       for (int e = pre_issued; e < n_total; ++e) {
-        if (a.spin) ptx::mbar_wait_spin(&bars->empty[s], ph ^ 1);
-        else ptx::mbar_wait(&bars->empty[s], ph ^ 1);
+        // which tile: worked out BEFORE the wait (a few integer divisions by run-time values, ~100 instructions of one
+        // thread) — after it they would sit on the refill path of a ring that is as deep as shared memory allows
         int kcol, blk;
         bool wout;
         stack_entry(i, CB, HB, NB, KB2, a.cond_first, kcol, blk, wout);
-        if (a.peer_tx) {
-          if (rank == 0) ptx::mbar_arrive_expect_tx(&bars->full[s], 2 * kSTile);  // this CTA's 16 KB and the peer's
-          const uint32_t lbar = ptx::leader_bar_addr(&bars->full[s]);
-          if (mc) ptx::tma_load_3d_mc_2sm(ring + s * kSTile + pidx * slice_rows * 128, wout ? &tm_wout : &tm_w1, lbar,
-                                          kcol * 64, blk * 256 + w_row0 + pidx * slice_rows, l, parity_mask);
-          else ptx::tma_load_3d_2sm(ring + s * kSTile, wout ? &tm_wout : &tm_w1, lbar, kcol * 64, blk * 256 + w_row0, l);
-        } else {
-          ptx::mbar_arrive_expect_tx(&bars->full[s], kSTile);
-          if (mc) ptx::tma_load_3d_mc(ring + s * kSTile + pidx * slice_rows * 128, wout ? &tm_wout : &tm_w1, &bars->full[s],
-                                      kcol * 64, blk * 256 + w_row0 + pidx * slice_rows, l, parity_mask);
-          else ptx::tma_load_3d(ring + s * kSTile, wout ? &tm_wout : &tm_w1, &bars->full[s], kcol * 64, blk * 256 + w_row0, l);
-        }
+        const CUtensorMap* tm = wout ? &tm_wout : &tm_w1;
+        const int c0 = kcol * 64, c1 = blk * 256 + w_row0 + (mc ? pidx * slice_rows : 0);
+        uint8_t* dst = ring + s * kSTile + (mc ? pidx * slice_rows * 128 : 0);
+        ptx::mbar_wait(&bars->empty[s], ph ^ 1);
+        ptx::mbar_arrive_expect_tx(&bars->full[s], kSTile);
+        if (mc) ptx::tma_load_3d_mc(dst, tm, &bars->full[s], c0, c1, l, parity_mask);
+        else ptx::tma_load_3d(dst, tm, &bars->full[s], c0, c1, l);
         if (++s == a.nentries) { s = 0; ph ^= 1; }
         if (++i == n_layer) { i = 0; ++l; }
       }
@@ -511,10 +506,8 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         const uint32_t pl = (uint32_t)l & 1u;
         int i = 0;
         auto forward_entries = [&](int n) {
-          if (a.peer_tx) return;  // the weight loads count on the leader's barrier themselves
           for (int k = 0; k < n; ++k, ++i) {
-            if (a.spin) ptx::mbar_wait_spin(&bars->full[s], ph);
-            else ptx::mbar_wait(&bars->full[s], ph);
+            ptx::mbar_wait(&bars->full[s], ph);
             ptx::mbar_arrive_cluster(leader_full0 + (uint32_t)s * 8u);
             if (++s == a.nentries) { s = 0; ph ^= 1; }
           }
@@ -1038,8 +1031,7 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
 
   // one cluster per track: each CTA pair fetches (and multicasts) 1/n_pairs of every weight half-tile
   const uint32_t csz = attr[0].val.clusterDim.x;
-  const bool no_mc = getenv("SVSK_STACK_NO_MULTICAST") != nullptr;
-  const uint32_t w_box_rows = (csz > 2 && !no_mc) ? 128u / (csz / 2) : 128u;
+  const uint32_t w_box_rows = csz > 2 ? 128u / (csz / 2) : 128u;
   CUtensorMap tm_xw0, tm_e0, tm_e1, tm_cond, tm_w1, tm_wout, tm_skip;
   {
     uint64_t dims[3] = {(uint64_t)p.C, (uint64_t)p.T, (uint64_t)p.B};
@@ -1091,9 +1083,6 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
   a.pingpong = (p.C == 128 && !getenv("SVSK_STACK_NO_PINGPONG")) ? 1 : 0;
   a.cond_resident = cond_resident;
   a.cond_first = (!a.dsmem_halo && !use_p && getenv("SVSK_STACK_COND_FIRST")) ? 1 : 0;  // experiment switch, see DiffnetStackArgs
-  a.peer_tx = getenv("SVSK_STACK_PEER_TX") ? 1 : 0;
-  a.no_mc = no_mc ? 1 : 0;
-  a.spin = getenv("SVSK_STACK_SPIN") ? 1 : 0;
   a.use_p = use_p ? 1 : 0;
   a.pfilt = static_cast<const uint4*>(p.pcond_filt);
   a.tiles_per_track = 2 * ceil_div(p.T, 256);

@@ -374,18 +374,6 @@ __device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* m, 
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
       : "memory");
 }
-// The pair leader's copy of a barrier of this CTA, as the address the cta_group::2 TMA forms take for their completion
-// (bit 24 of a shared-window address selects the CTA within the pair: what CUTLASS calls Sm100MmaPeerBitMask).
-__device__ __forceinline__ uint32_t leader_bar_addr(const uint64_t* bar) { return smem_u32(bar) & 0xFEFFFFFFu; }
-// Multicast load whose bytes are counted, in every destination CTA, on the barrier of that CTA's pair LEADER.
-__device__ __forceinline__ void tma_load_3d_mc_2sm(void* dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1, int c2,
-                                                   uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], "
-      "[%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
-      : "memory");
-}
 // global[tile] += smem[tile] (element type and shape come from the tensor map; fp32 here), performed at L2
 __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
   asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
