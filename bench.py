@@ -43,7 +43,8 @@ CONFIG = {"workload": f"DiffNet(80,256,L20,C256) 100-step DDPM sampling, {B} tra
           "l2": "GPU arm: 256 MB flush between timed passes; the 384 MB noise tensor of a pass exceeds L2"}
 
 
-STACK_NCU_SUMMARY = "r02k_stack_ncu_full_summary.json"        # dram bytes of diffnet_stack_kernel (ncu --set full)
+STACK_NCU_SUMMARY = "r02p_stack_ncu_full_summary.json"        # dram bytes of diffnet_stack_kernel<hoisted projection> (ncu --set full)
+STACK_NCU_SUMMARY_IN_GEMM = "r02k_stack_ncu_full_summary.json"
 USFGAN_NCU_SUMMARY = "r02n_usfgan_block_fr_ncu_full_summary.json"
 
 
@@ -478,7 +479,7 @@ def main():
             "clocks": clk.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf,
-                         "traffic": _ncu_traffic(STACK_NCU_SUMMARY) if use_stack else None,
+                         "traffic": (_ncu_traffic(STACK_NCU_SUMMARY if pcond is not None else STACK_NCU_SUMMARY_IN_GEMM) if use_stack else None),
                          "kernel": ("diffnet_stack_kernel (all 20 residual blocks in one launch; CTA pairs, tcgen05 cta_group::2)"
                                     if use_stack else "diffnet_block3_kernel (one residual block; CTA pairs, tcgen05 cta_group::2)"),
                          "us_per_launch": block_ms * 1e3, "flops_per_launch": flops_per_launch,
