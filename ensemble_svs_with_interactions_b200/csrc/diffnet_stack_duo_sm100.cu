@@ -427,29 +427,35 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
             const uint32_t* rg = rgb[i & 1];
             const uint32_t* rf = rfb[i & 1];
             const int pg = c0, pf = c0 + 128;
-            float gv[16], fv[16];
+            uint64_t gv[8], fv[8];  // column pairs (FADD2 / FMUL2 / FFMA2), see diffnet_stack_sm100.cu
 #pragma unroll
             for (int e = 0; e < 16; e += 4) {
               const float4 bg = ptx::ld_shared_v4f(sb_full + pg + e);
               const float4 bf = ptx::ld_shared_v4f(sb_full + pf + e);
-              gv[e] = __uint_as_float(rg[e]) + bg.x; gv[e + 1] = __uint_as_float(rg[e + 1]) + bg.y;
-              gv[e + 2] = __uint_as_float(rg[e + 2]) + bg.z; gv[e + 3] = __uint_as_float(rg[e + 3]) + bg.w;
-              fv[e] = __uint_as_float(rf[e]) + bf.x; fv[e + 1] = __uint_as_float(rf[e + 1]) + bf.y;
-              fv[e + 2] = __uint_as_float(rf[e + 2]) + bf.z; fv[e + 3] = __uint_as_float(rf[e + 3]) + bf.w;
+              gv[e >> 1] = ptx::f2_add(ptx::f2_pack(__uint_as_float(rg[e]), __uint_as_float(rg[e + 1])), ptx::f2_pack(bg.x, bg.y));
+              gv[(e >> 1) + 1] = ptx::f2_add(ptx::f2_pack(__uint_as_float(rg[e + 2]), __uint_as_float(rg[e + 3])), ptx::f2_pack(bg.z, bg.w));
+              fv[e >> 1] = ptx::f2_add(ptx::f2_pack(__uint_as_float(rf[e]), __uint_as_float(rf[e + 1])), ptx::f2_pack(bf.x, bf.y));
+              fv[(e >> 1) + 1] = ptx::f2_add(ptx::f2_pack(__uint_as_float(rf[e + 2]), __uint_as_float(rf[e + 3])), ptx::f2_pack(bf.z, bf.w));
             }
             if (warp_edge) {  // a branch around the rare case, not 128 predicated-off instructions per chunk (see diffnet_stack_sm100.cu)
               if (!has_l) {
 #pragma unroll
-                for (int u = 0; u < 16; ++u) { gv[u] -= sb_l[pg + u]; fv[u] -= sb_l[pf + u]; }
+                for (int u = 0; u < 16; u += 2) {
+                  gv[u >> 1] = ptx::f2_add(gv[u >> 1], ptx::f2_pack(-sb_l[pg + u], -sb_l[pg + u + 1]));
+                  fv[u >> 1] = ptx::f2_add(fv[u >> 1], ptx::f2_pack(-sb_l[pf + u], -sb_l[pf + u + 1]));
+                }
               }
               if (!has_r) {
 #pragma unroll
-                for (int u = 0; u < 16; ++u) { gv[u] -= sb_r[pg + u]; fv[u] -= sb_r[pf + u]; }
+                for (int u = 0; u < 16; u += 2) {
+                  gv[u >> 1] = ptx::f2_add(gv[u >> 1], ptx::f2_pack(-sb_r[pg + u], -sb_r[pg + u + 1]));
+                  fv[u >> 1] = ptx::f2_add(fv[u >> 1], ptx::f2_pack(-sb_r[pf + u], -sb_r[pf + u + 1]));
+                }
               }
             }
             float z[16];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) z[u] = ptx::sigmoid_approx(gv[u]) * ptx::tanh_approx(fv[u]);
+            for (int u = 0; u < 16; u += 2) ptx::f2_unpack(ptx::f2_gate(gv[u >> 1], fv[u >> 1]), z[u], z[u + 1]);
             uint8_t* gk = g_smem + (c0 >> 6) * kDTile;  // gated channel c0.. = K index of GEMM2
             const uint32_t ch16 = (uint32_t)((c0 & 63) >> 3);
             ptx::st_shared_v4(gk + ptx::sw128_offset((uint32_t)row, ch16), ptx::pack_bf16(z[0], z[1]),

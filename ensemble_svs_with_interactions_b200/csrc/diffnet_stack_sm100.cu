@@ -46,6 +46,21 @@
 #include "svsk_common.cuh"
 #include "tma_util.cuh"
 
+// How the three single-thread roles wait for a ring entry (compile-time: a run-time switch in these loops costs more than
+// either flavour gains): suspending try_wait (ptx::mbar_wait) or polling test_wait (ptx::mbar_wait_spin).
+// Measured with -DSVSK_STACK_{PRODUCER,ISSUER,FORWARDER}_WAIT=ptx::mbar_wait_spin builds on one box (gpurun_out/s39_ab.log,
+// 6 x 2000 frames, hoisted projection): 346.1 / 347.4 / 347.0 us, all three 346.6 us, against 345.2-347.1 us suspending —
+// no difference, so the suspending waits stay (they leave the issue slots to the epilogue warps).
+#ifndef SVSK_STACK_PRODUCER_WAIT
+#define SVSK_STACK_PRODUCER_WAIT ptx::mbar_wait
+#endif
+#ifndef SVSK_STACK_ISSUER_WAIT
+#define SVSK_STACK_ISSUER_WAIT ptx::mbar_wait
+#endif
+#ifndef SVSK_STACK_FORWARDER_WAIT
+#define SVSK_STACK_FORWARDER_WAIT ptx::mbar_wait
+#endif
+
 namespace svsk {
 
 constexpr int kSTile = 128 * 128;            // 128 rows x 64 bf16
@@ -280,7 +295,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         const CUtensorMap* tm = wout ? &tm_wout : &tm_w1;
         const int c0 = kcol * 64, c1 = blk * 256 + w_row0 + (mc ? pidx * slice_rows : 0);
         uint8_t* dst = ring + s * kSTile + (mc ? pidx * slice_rows * 128 : 0);
-        ptx::mbar_wait(&bars->empty[s], ph ^ 1);
+        SVSK_STACK_PRODUCER_WAIT(&bars->empty[s], ph ^ 1);
         ptx::mbar_arrive_expect_tx(&bars->full[s], kSTile);
         if (mc) ptx::tma_load_3d_mc(dst, tm, &bars->full[s], c0, c1, l, parity_mask);
         else ptx::tma_load_3d(dst, tm, &bars->full[s], c0, c1, l);
@@ -388,7 +403,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
   do {                                                    \
     if (!ready) {                                         \
       const long long c_0 = dbg ? clock64() : 0ll;        \
-      ptx::mbar_wait(&bars->full[s], ph);                 \
+      SVSK_STACK_ISSUER_WAIT(&bars->full[s], ph);         \
       if (dbg) { acc_wait += clock64() - c_0; ++n_miss; } \
     }                                                     \
     ready = false;                                        \
@@ -507,7 +522,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         int i = 0;
         auto forward_entries = [&](int n) {
           for (int k = 0; k < n; ++k, ++i) {
-            ptx::mbar_wait(&bars->full[s], ph);
+            SVSK_STACK_FORWARDER_WAIT(&bars->full[s], ph);
             ptx::mbar_arrive_cluster(leader_full0 + (uint32_t)s * 8u);
             if (++s == a.nentries) { s = 0; ph ^= 1; }
           }
@@ -638,36 +653,42 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
               pfq[i & 1][1] = ldg_stream_v4(p2 + 1);
             }
           }
-          float gv[16], fv[16];
+          uint64_t gv[8], fv[8];  // column pairs: FADD2 / FMUL2 / FFMA2 halve the issue slots of this issue-bound loop
 #pragma unroll
           for (int e = 0; e < 16; e += 4) {
             const float4 bg = ptx::ld_shared_v4f(sb_full + pg + e);
             const float4 bf = ptx::ld_shared_v4f(sb_full + pf + e);
-            gv[e] = __uint_as_float(rg[e]) + bg.x; gv[e + 1] = __uint_as_float(rg[e + 1]) + bg.y;
-            gv[e + 2] = __uint_as_float(rg[e + 2]) + bg.z; gv[e + 3] = __uint_as_float(rg[e + 3]) + bg.w;
-            fv[e] = __uint_as_float(rf[e]) + bf.x; fv[e + 1] = __uint_as_float(rf[e + 1]) + bf.y;
-            fv[e + 2] = __uint_as_float(rf[e + 2]) + bf.z; fv[e + 3] = __uint_as_float(rf[e + 3]) + bf.w;
+            gv[e >> 1] = ptx::f2_add(ptx::f2_pack(__uint_as_float(rg[e]), __uint_as_float(rg[e + 1])), ptx::f2_pack(bg.x, bg.y));
+            gv[(e >> 1) + 1] = ptx::f2_add(ptx::f2_pack(__uint_as_float(rg[e + 2]), __uint_as_float(rg[e + 3])), ptx::f2_pack(bg.z, bg.w));
+            fv[e >> 1] = ptx::f2_add(ptx::f2_pack(__uint_as_float(rf[e]), __uint_as_float(rf[e + 1])), ptx::f2_pack(bf.x, bf.y));
+            fv[(e >> 1) + 1] = ptx::f2_add(ptx::f2_pack(__uint_as_float(rf[e + 2]), __uint_as_float(rf[e + 3])), ptx::f2_pack(bf.z, bf.w));
             if (kUseP) {
               const uint2 pgw = ptx::ld_shared_v2(gk + ptx::sw128_offset((uint32_t)row, ch16 + (uint32_t)(e >> 3)) + (e & 4) * 2);
-              gv[e] += ptx::bf16_lo(pgw.x); gv[e + 1] += ptx::bf16_hi(pgw.x);
-              gv[e + 2] += ptx::bf16_lo(pgw.y); gv[e + 3] += ptx::bf16_hi(pgw.y);
-              fv[e] += ptx::bf16_lo(pfw[e >> 1]); fv[e + 1] += ptx::bf16_hi(pfw[e >> 1]);
-              fv[e + 2] += ptx::bf16_lo(pfw[(e >> 1) + 1]); fv[e + 3] += ptx::bf16_hi(pfw[(e >> 1) + 1]);
+              gv[e >> 1] = ptx::f2_add(gv[e >> 1], ptx::f2_pack(ptx::bf16_lo(pgw.x), ptx::bf16_hi(pgw.x)));
+              gv[(e >> 1) + 1] = ptx::f2_add(gv[(e >> 1) + 1], ptx::f2_pack(ptx::bf16_lo(pgw.y), ptx::bf16_hi(pgw.y)));
+              fv[e >> 1] = ptx::f2_add(fv[e >> 1], ptx::f2_pack(ptx::bf16_lo(pfw[e >> 1]), ptx::bf16_hi(pfw[e >> 1])));
+              fv[(e >> 1) + 1] = ptx::f2_add(fv[(e >> 1) + 1], ptx::f2_pack(ptx::bf16_lo(pfw[(e >> 1) + 1]), ptx::bf16_hi(pfw[(e >> 1) + 1])));
             }
           }
           if (warp_edge) {
             if (!has_l) {
 #pragma unroll
-              for (int u = 0; u < 16; ++u) { gv[u] -= sb_l[pg + u]; fv[u] -= sb_l[pf + u]; }
+              for (int u = 0; u < 16; u += 2) {
+                gv[u >> 1] = ptx::f2_add(gv[u >> 1], ptx::f2_pack(-sb_l[pg + u], -sb_l[pg + u + 1]));
+                fv[u >> 1] = ptx::f2_add(fv[u >> 1], ptx::f2_pack(-sb_l[pf + u], -sb_l[pf + u + 1]));
+              }
             }
             if (!has_r) {
 #pragma unroll
-              for (int u = 0; u < 16; ++u) { gv[u] -= sb_r[pg + u]; fv[u] -= sb_r[pf + u]; }
+              for (int u = 0; u < 16; u += 2) {
+                gv[u >> 1] = ptx::f2_add(gv[u >> 1], ptx::f2_pack(-sb_r[pg + u], -sb_r[pg + u + 1]));
+                fv[u >> 1] = ptx::f2_add(fv[u >> 1], ptx::f2_pack(-sb_r[pf + u], -sb_r[pf + u + 1]));
+              }
             }
           }
           float z[16];
 #pragma unroll
-          for (int u = 0; u < 16; ++u) z[u] = ptx::sigmoid_approx(gv[u]) * ptx::tanh_approx(fv[u]);
+          for (int u = 0; u < 16; u += 2) ptx::f2_unpack(ptx::f2_gate(gv[u >> 1], fv[u >> 1]), z[u], z[u + 1]);
           ptx::st_shared_v4(gk + ptx::sw128_offset((uint32_t)row, ch16), ptx::pack_bf16(z[0], z[1]),
                             ptx::pack_bf16(z[2], z[3]), ptx::pack_bf16(z[4], z[5]), ptx::pack_bf16(z[6], z[7]));
           ptx::st_shared_v4(gk + ptx::sw128_offset((uint32_t)row, ch16 + 1), ptx::pack_bf16(z[8], z[9]),

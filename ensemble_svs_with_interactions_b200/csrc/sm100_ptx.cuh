@@ -248,6 +248,38 @@ __device__ __forceinline__ float tanh_approx(float x) {
   return y;
 }
 __device__ __forceinline__ float sigmoid_approx(float x) { return fmaf(tanh_approx(0.5f * x), 0.5f, 0.5f); }
+// Packed fp32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100: one issue slot for two lanes' worth of IEEE arithmetic — the gating
+// loops are issue-bound, not MUFU-bound; results are bit-identical to the scalar forms).
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// z = sigmoid(g) * tanh(f) for two columns at once; same arithmetic as sigmoid_approx(g) * tanh_approx(f) per lane
+__device__ __forceinline__ uint64_t f2_gate(uint64_t g, uint64_t f) {
+  const uint64_t half = f2_pack(0.5f, 0.5f);
+  float g0, g1, f0, f1;
+  f2_unpack(f2_mul(g, half), g0, g1);
+  f2_unpack(f, f0, f1);
+  const uint64_t sg = f2_fma(f2_pack(tanh_approx(g0), tanh_approx(g1)), half, half);
+  return f2_mul(sg, f2_pack(tanh_approx(f0), tanh_approx(f1)));
+}
 
 
 // ---------------------------------------------------------------- clusters / CTA pairs (cta_group::2)

@@ -402,10 +402,19 @@ usfgan_block_fr_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
           const float fa[4] = {__uint_as_float(ba.x), __uint_as_float(ba.y), __uint_as_float(ba.z), __uint_as_float(ba.w)};
           const float fb[4] = {__uint_as_float(bb.x), __uint_as_float(bb.y), __uint_as_float(bb.z), __uint_as_float(bb.w)};
           float z[4];
+          if (kProf && (flags & 2)) {  // ablation: no MUFU
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float ya = __uint_as_float(ra[4 * v + j]) + fa[j], yb = __uint_as_float(rb[4 * v + j]) + fb[j];
-            z[j] = (flags & 2) ? ya * fmaf(yb, 0.25f, 0.5f) : ptx::tanh_approx(ya) * ptx::sigmoid_approx(yb);
+            for (int j = 0; j < 4; ++j) {
+              const float ya = __uint_as_float(ra[4 * v + j]) + fa[j], yb = __uint_as_float(rb[4 * v + j]) + fb[j];
+              z[j] = ya * fmaf(yb, 0.25f, 0.5f);
+            }
+          } else {  // column pairs: FADD2 / FMUL2 / FFMA2 — same arithmetic per lane as tanh_approx(ya) * sigmoid_approx(yb)
+#pragma unroll
+            for (int j = 0; j < 4; j += 2) {
+              const uint64_t ya = ptx::f2_add(ptx::f2_pack(__uint_as_float(ra[4 * v + j]), __uint_as_float(ra[4 * v + j + 1])), ptx::f2_pack(fa[j], fa[j + 1]));
+              const uint64_t yb = ptx::f2_add(ptx::f2_pack(__uint_as_float(rb[4 * v + j]), __uint_as_float(rb[4 * v + j + 1])), ptx::f2_pack(fb[j], fb[j + 1]));
+              ptx::f2_unpack(ptx::f2_gate(yb, ya), z[j], z[j + 1]);
+            }
           }
           o[2 * v] = ptx::pack_bf16(z[0], z[1]);
           o[2 * v + 1] = ptx::pack_bf16(z[2], z[3]);
@@ -441,10 +450,15 @@ usfgan_block_fr_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
           const uint4 bo = ptx::ld_shared_v4(bias_s + 128 + c0 + 4 * v);
           const float fo[4] = {__uint_as_float(bo.x), __uint_as_float(bo.y), __uint_as_float(bo.z), __uint_as_float(bo.w)};
           float y[4];
+          const uint64_t sc2 = ptx::f2_pack(a.out_scale, a.out_scale);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            y[j] = (__uint_as_float(rd[4 * v + j]) + fo[j]) * a.out_scale;
-            if (a.out_relu) y[j] = fmaxf(y[j], 0.f);
+          for (int j = 0; j < 4; j += 2) {
+            const uint64_t y2 = ptx::f2_mul(ptx::f2_add(ptx::f2_pack(__uint_as_float(rd[4 * v + j]), __uint_as_float(rd[4 * v + j + 1])), ptx::f2_pack(fo[j], fo[j + 1])), sc2);
+            ptx::f2_unpack(y2, y[j], y[j + 1]);
+          }
+          if (a.out_relu) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
           }
           o[2 * v] = ptx::pack_bf16(y[0], y[1]);
           o[2 * v + 1] = ptx::pack_bf16(y[2], y[3]);
