@@ -730,13 +730,17 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
               const uint4 xa = ptx::ld_shared_v4(p0), xb = ptx::ld_shared_v4(p1);
               const uint32_t xo[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
               uint32_t o[8];
+              const uint64_t s22 = ptx::f2_pack(s2, s2);
 #pragma unroll
-              for (int e = 0; e < 8; e += 2) {
+              for (int e = 0; e < 8; e += 2) {  // column pairs; same order of operations per lane: ((x + r) + bo) * s2
                 const float4 bo = ptx::ld_shared_v4f(bo_s + oc0 + 2 * e);
-                const float v0 = (ptx::bf16_lo(xo[e]) + __uint_as_float(r[2 * e]) + bo.x) * s2;
-                const float v1 = (ptx::bf16_hi(xo[e]) + __uint_as_float(r[2 * e + 1]) + bo.y) * s2;
-                const float v2 = (ptx::bf16_lo(xo[e + 1]) + __uint_as_float(r[2 * e + 2]) + bo.z) * s2;
-                const float v3 = (ptx::bf16_hi(xo[e + 1]) + __uint_as_float(r[2 * e + 3]) + bo.w) * s2;
+                float v0, v1, v2, v3;
+                ptx::f2_unpack(ptx::f2_mul(ptx::f2_add(ptx::f2_add(ptx::f2_pack(ptx::bf16_lo(xo[e]), ptx::bf16_hi(xo[e])),
+                                                                   ptx::f2_pack(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]))),
+                                                       ptx::f2_pack(bo.x, bo.y)), s22), v0, v1);
+                ptx::f2_unpack(ptx::f2_mul(ptx::f2_add(ptx::f2_add(ptx::f2_pack(ptx::bf16_lo(xo[e + 1]), ptx::bf16_hi(xo[e + 1])),
+                                                                   ptx::f2_pack(__uint_as_float(r[2 * e + 2]), __uint_as_float(r[2 * e + 3]))),
+                                                       ptx::f2_pack(bo.z, bo.w)), s22), v2, v3);
                 o[e] = in_seq ? ptx::pack_bf16(v0, v1) : 0u;  // rows past the end stay zero: they are the conv's zero padding
                 o[e + 1] = in_seq ? ptx::pack_bf16(v2, v3) : 0u;
               }
