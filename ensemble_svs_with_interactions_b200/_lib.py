@@ -196,6 +196,8 @@ _SIGNATURES = {
     "svsk_tapgemm_bf16": [C.POINTER(TapGemmBf16Params), _V],
     "svsk_tapgemm_pack_bf16": [_V, _V, _V, _I, _I, _I, _V],
     "svsk_reflect_pad_rows_bf16": [_V, _I, _I, _I, _I, _I, _V],
+    "svsk_bn_batch_stats_f32": [_V, _I, _I, _I, _V, _V, _V, _V, _F, _V],
+    "svsk_bn_apply_f32": [_V, _V, _V, _V, _V, _V, _F, _I, _I, _I, _I, _V],
     "svsk_encoder_front": [_V, _V, _V, C.c_longlong, _I, _I, _I, _I, _I, _V],
     "svsk_filtfilt_f32": [_V, _V, _V, _V, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), _I, _I, _I, _I, _I, _I, _V],
     "svsk_variance_scaling_f32": [_V, _V, _V, _V, _V, _I, _I, _I, _I, _V],

@@ -289,3 +289,80 @@ extern "C" int svsk_tapgemm_bf16(const svsk_tapgemm_bf16_params* pp, void* strea
   tapgemm_bf16_kernel<<<grid, 192, smem_bytes, as_stream(stream)>>>(tm_x, tm_w, a);
   return check_launch("tapgemm_bf16");
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// BatchNorm1d in TRAINING mode (model.py:839-852 under module.train(): the diffusion recipe's encoders have dropout = 0, so
+// this is all that differs from the eval forward): statistics of a [B][C][T] fp32 tensor over all B * T positions of a
+// channel, padded frames included, as torch.nn.BatchNorm1d takes them.  One CTA per channel, fp64 sums; the running
+// buffers move by `momentum` towards (mean, unbiased variance).
+namespace svsk {
+
+__global__ void __launch_bounds__(256) bn_batch_stats_kernel(const float* __restrict__ x, int B, int C, int T,
+                                                             float* __restrict__ mean, float* __restrict__ var,
+                                                             float* __restrict__ run_mean, float* __restrict__ run_var,
+                                                             float momentum) {
+  const int c = blockIdx.x;
+  double s = 0.0, ss = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const float* row = x + ((size_t)b * C + c) * T;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      const double v = row[t];
+      s += v;
+      ss += v * v;
+    }
+  }
+  __shared__ double sh[2][8];
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = ss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = ss = 0.0;
+    for (int w = 0; w < 8; ++w) { s += sh[0][w]; ss += sh[1][w]; }
+    const double n = (double)B * T;
+    const double m = s / n;
+    double v = ss / n - m * m;
+    if (v < 0.0) v = 0.0;
+    mean[c] = (float)m;
+    var[c] = (float)v;
+    if (run_mean) run_mean[c] = (float)((1.0 - momentum) * run_mean[c] + momentum * m);
+    if (run_var) run_var[c] = (float)((1.0 - momentum) * run_var[c] + momentum * v * (n > 1.0 ? n / (n - 1.0) : 1.0));
+  }
+}
+
+__global__ void bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ mean,
+                                const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                float eps, int relu, int C, int T, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = (int)((i / T) % C);
+  float v = (x[i] - mean[c]) * (1.0f / sqrtf(var[c] + eps));
+  v = v * (gamma ? gamma[c] : 1.0f) + (beta ? beta[c] : 0.0f);
+  y[i] = relu ? fmaxf(v, 0.f) : v;
+}
+
+}  // namespace svsk
+
+extern "C" int svsk_bn_batch_stats_f32(const float* x, int B, int C, int T, float* mean, float* var, float* running_mean,
+                                       float* running_var, float momentum, void* stream) {
+  SVSK_REQUIRE(x && mean && var, SVSK_E_ARG, "bn_batch_stats_f32: null tensor");
+  SVSK_REQUIRE(B > 0 && C > 0 && T > 0 && C <= 65535 * 32, SVSK_E_ARG, "bn_batch_stats_f32: bad B/C/T");
+  SVSK_REQUIRE(momentum >= 0.f && momentum <= 1.f, SVSK_E_ARG, "bn_batch_stats_f32: momentum %f", (double)momentum);
+  int rc = require_sm100();
+  if (rc) return rc;
+  bn_batch_stats_kernel<<<(unsigned)C, 256, 0, as_stream(stream)>>>(x, B, C, T, mean, var, running_mean, running_var, momentum);
+  return check_launch("bn_batch_stats_f32");
+}
+
+extern "C" int svsk_bn_apply_f32(const float* x, float* y, const float* mean, const float* var, const float* gamma,
+                                 const float* beta, float eps, int relu, int B, int C, int T, void* stream) {
+  SVSK_REQUIRE(x && y && mean && var, SVSK_E_ARG, "bn_apply_f32: null tensor");
+  SVSK_REQUIRE(B > 0 && C > 0 && T > 0 && eps > 0.f, SVSK_E_ARG, "bn_apply_f32: bad B/C/T/eps");
+  int rc = require_sm100();
+  if (rc) return rc;
+  const size_t n = (size_t)B * C * T;
+  bn_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(x, y, mean, var, gamma, beta, eps, relu, C, T, n);
+  return check_launch("bn_apply_f32");
+}

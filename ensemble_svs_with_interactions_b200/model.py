@@ -16,7 +16,10 @@ parameters, their ``forward`` never runs.  Eval-mode forward only (BatchNorm run
 
 ``use_mdn=True`` puts a dimension-wise mixture-density head (``MDNLayer``, nnsvs/mdn.py:6-74) in place of the output
 Linear: ``forward`` returns (log_pi, log_sigma, mu) [B, T, G, D], ``inference`` the (mu, sigma) of the most probable
-component (svsk_mdn_head_f32).  Not built: training mode (it raises).
+component (svsk_mdn_head_f32).  Training mode (module.train()): the FORWARD is built for dropout = 0 — what the diffusion
+recipe's encoders use — i.e. BatchNorm1d with the batch statistics of the padded batch and the running-buffer update
+(svsk_bn_batch_stats_f32 / svsk_bn_apply_f32; fp32 kernels whatever ``precision`` says, since the statistics are taken
+on the convolution's own output); there are no backward kernels for the encoder, so a call that needs gradients raises.
 """
 from __future__ import annotations
 
@@ -247,7 +250,12 @@ class FFConvLSTM(BaseModel):
     # ------------------------------------------------------------------ forward
     def _check(self, x, lengths):
         if self.training:
-            raise RuntimeError("FFConvLSTM: only the eval-mode forward is built (BatchNorm running statistics, no dropout); call .eval()")
+            if self.lstm.dropout > 0 and self.lstm.num_layers > 1:
+                raise RuntimeError("FFConvLSTM: the training-mode forward is built for dropout = 0 only (the diffusion recipe's "
+                                   f"encoders); got dropout = {self.lstm.dropout}.  Call .eval() for inference")
+            if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+                raise RuntimeError("FFConvLSTM has no backward kernels: the training-mode forward (BatchNorm batch statistics, "
+                                   "running-buffer update) runs under torch.no_grad() or with frozen parameters only")
         if not x.is_cuda:
             raise RuntimeError("FFConvLSTM: input must be a CUDA tensor (libsvsk has no CPU path)")
         if x.dim() != 3 or x.shape[-1] != self.in_dim:
@@ -268,11 +276,21 @@ class FFConvLSTM(BaseModel):
     def _raw(self, x, lengths, spk_embs):
         """Output of the last product, [B, max(lengths), >= n_out] fp32 (a view when the GEMM padded its columns)."""
         lens = self._check(x, lengths)
-        plan = self.plan()
         x = x.detach().float().contiguous()
         lens_dev = torch.tensor(lens, dtype=torch.int32, device=x.device)
         if spk_embs is not None:
             spk_embs = spk_embs.detach().float().expand(x.shape[0], x.shape[1], spk_embs.shape[-1]).contiguous()
+        if self.training:
+            # BatchNorm1d with batch statistics (model.py:839-852 under module.train()): the fp32 kernels, the convolutions'
+            # own weights (nothing folded), the running buffers updated in place -> the cached eval plan is stale afterwards
+            key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+            if self.__dict__.get("_plan_train_key") != key:
+                self.__dict__["_plan_train"], self.__dict__["_plan_train_key"] = _Plan(self, "fp32"), key
+            with torch.no_grad():
+                out = self._forward_fp32(x, lens_dev, spk_embs, self.__dict__["_plan_train"], train=True)
+            self._plan = None
+            return out[:, :max(lens)]
+        plan = self.plan()
         out = self._forward_fp32(x, lens_dev, spk_embs, plan) if plan.precision == "fp32" else self._forward_bf16(x, lens_dev, spk_embs, plan)
         return out[:, :max(lens)]
 
@@ -289,7 +307,7 @@ class FFConvLSTM(BaseModel):
             return mu, sigma
         return self(x, lengths, spk_embs=spk_embs)
 
-    def _forward_fp32(self, x, lens_dev, spk, plan):
+    def _forward_fp32(self, x, lens_dev, spk, plan, train=False):
         B, T, _ = x.shape
         H = plan.Hp
         if self.embed_dim is not None:
@@ -303,8 +321,18 @@ class FFConvLSTM(BaseModel):
             h = ops.lincomb_f32([h, ops.ntc_to_nct_f32(spk, spk.shape[-1])], [1.0, 1.0])
         for w, b in plan.ff:
             h = ops.conv1d_f32(h, w, b, act=ops.ACT_RELU)
-        for w, b in plan.conv:
-            h = ops.conv1d_f32(h, w, b, pad_mode=ops.PAD_REFLECT, act=ops.ACT_RELU)
+        for k, (w, b) in enumerate(plan.conv):
+            if train:
+                conv, bn = self.conv[4 * k + 1], self.conv[4 * k + 2]
+                if bn.momentum is None or not bn.track_running_stats:
+                    raise RuntimeError("FFConvLSTM: BatchNorm1d(momentum=None / track_running_stats=False) is not built")
+                h = ops.conv1d_f32(h, conv.weight.detach().float().contiguous(), conv.bias.detach().float().contiguous(),
+                                   pad_mode=ops.PAD_REFLECT)
+                ops.batchnorm_train_f32(h, bn.weight.detach().float().contiguous(), bn.bias.detach().float().contiguous(),
+                                        bn.running_mean, bn.running_var, eps=bn.eps, momentum=bn.momentum, relu=True)
+                bn.num_batches_tracked += 1
+            else:
+                h = ops.conv1d_f32(h, w, b, pad_mode=ops.PAD_REFLECT, act=ops.ACT_RELU)
         for w_ih, b, w_hh in plan.lstm:
             pre = ops.conv1d_f32(h, w_ih, b)                                   # [B, 8H, T]
             h = torch.empty((B, 2 * H, T), device=x.device, dtype=torch.float32)

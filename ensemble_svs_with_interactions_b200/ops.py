@@ -717,6 +717,19 @@ def encoder_front(x, onehot_start, onehot_len, *, y_f32=None, y_bf16=None):
                                        0 if y_bf16 is None else y_bf16.shape[1], L.stream_ptr()), "encoder_front")
 
 
+def batchnorm_train_f32(x, gamma, beta, running_mean, running_var, *, eps, momentum, relu=True):
+    """nn.BatchNorm1d in training mode (+ ReLU) on x [B, C, T] fp32, in place: batch statistics over all B*T positions,
+    running buffers updated as torch does (svsk_bn_batch_stats_f32 + svsk_bn_apply_f32).  Returns x."""
+    B, Cc, T = x.shape
+    mean = torch.empty((Cc,), device=x.device, dtype=f32)
+    var = torch.empty((Cc,), device=x.device, dtype=f32)
+    L.check(L.lib().svsk_bn_batch_stats_f32(L.ptr(x, f32, "x"), B, Cc, T, L.ptr(mean), L.ptr(var), L.ptr(running_mean, f32),
+                                            L.ptr(running_var, f32), float(momentum), L.stream_ptr()), "bn_batch_stats_f32")
+    L.check(L.lib().svsk_bn_apply_f32(L.ptr(x, f32, "x"), L.ptr(x), L.ptr(mean), L.ptr(var), L.ptr(gamma, f32), L.ptr(beta, f32),
+                                      float(eps), int(relu), B, Cc, T, L.stream_ptr()), "bn_apply_f32")
+    return x
+
+
 # ---- acoustic post-processing (include/svsk.h, "acoustic post-processing on the device") ----------------------------
 def filtfilt_f32(x, b, a, zi, *, min_len, lengths=None, out=None):
     """svsk_filtfilt_f32.  x [B, T, D] fp32; b, a, zi: float64 sequences (host); lengths int32 [B] or None."""

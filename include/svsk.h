@@ -444,6 +444,15 @@ SVSK_API int svsk_tapgemm_pack_bf16(const float* w /* [Cout][Cin][ksize] */, con
                                     int ksize, void* stream);
 /* nn.ReflectionPad1d(pad) in place on buf [B][Tp][C] bf16 whose rows pad..pad+T-1 hold the data (model.py:847,851,855). */
 SVSK_API int svsk_reflect_pad_rows_bf16(void* buf, int B, int Tp, int C, int T, int pad, void* stream);
+/* nn.BatchNorm1d in TRAINING mode on x [B][C][T] fp32 (model.py:839-852 under module.train(); the diffusion recipe's encoders
+ * run with dropout = 0, so the batch statistics are all that differs from the eval forward):
+ *   svsk_bn_batch_stats_f32: mean[c], var[c] (biased) over all B*T positions of channel c, padded frames included; if
+ *     running_mean / running_var are given they move by `momentum` towards (mean, unbiased variance), as torch does;
+ *   svsk_bn_apply_f32: y = act((x - mean[c]) / sqrt(var[c] + eps) * gamma[c] + beta[c]), relu != 0 -> ReLU; y may be x. */
+SVSK_API int svsk_bn_batch_stats_f32(const float* x, int B, int C, int T, float* mean, float* var, float* running_mean,
+                                     float* running_var, float momentum, void* stream);
+SVSK_API int svsk_bn_apply_f32(const float* x, float* y, const float* mean, const float* var, const float* gamma,
+                               const float* beta, float eps, int relu, int B, int C, int T, void* stream);
 /* Input side of the embedding front (model.py:897-910): copies x [rows][in_dim] to y_f32 [rows][ldy_f] and / or y_bf16
  * [rows][ldy_b] (zero-filled pitch) with the one-hot block [onehot_start, +onehot_len) replaced by the exact one-hot of
  * its argmax, so that emb(argmax) + fc_in(rest) becomes one GEMM with the weights [fc_in | emb^T].  onehot_len 0 = copy. */

@@ -379,6 +379,43 @@ def golden_encoder(ns):
         _save(name, cfg, m.state_dict(), dict(x=x, lengths=torch.tensor(lengths)), dict(y=y, ff=ff, conv=conv, **extra))
 
 
+def golden_encoder_train(ns):
+    """FFConvLSTM in TRAINING mode with dropout = 0 (the diffusion recipe's encoders, multitrack_..._diff_mgcbap.yaml:115,157):
+    BatchNorm1d normalises with the batch statistics of the padded batch and updates its running buffers
+    (model.py:839-852,915).  Two consecutive forwards, so that the second one starts from updated buffers."""
+    cfg = dict(in_dim=60, in_ph_start_idx=3, in_ph_end_idx=20, embed_dim=24, ff_hidden_dim=32, conv_hidden_dim=24,
+               lstm_hidden_dim=40, num_lstm_layers=2, out_dim=16, dropout=0.0)
+    B, T, lengths = 3, 50, [50, 41, 17]
+    torch.manual_seed(71)
+    g = torch.Generator().manual_seed(72)
+    m = ns.FFConvLSTM(**cfg).train()
+    for k, v in m.state_dict().items():
+        if k.endswith("running_mean"):
+            v.copy_(torch.randn(v.shape, generator=g) * 0.2)
+        elif k.endswith("running_var"):
+            v.copy_(torch.rand(v.shape, generator=g) + 0.5)
+        elif ".bias" in k and v.dim() == 1 and "lstm" not in k:
+            v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+    for k in (2, 6, 10):
+        m.conv[k].weight.data.copy_(torch.rand(m.conv[k].weight.shape, generator=g) + 0.5)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    s, V = cfg["in_ph_start_idx"], cfg["in_ph_end_idx"] - cfg["in_ph_start_idx"]
+    xs = []
+    for _ in range(2):
+        x = torch.randn(B, T, cfg["in_dim"], generator=g)
+        x[..., s:s + V] = torch.nn.functional.one_hot(torch.randint(0, V, (B, T), generator=g), V).float()
+        xs.append(x)
+    with torch.no_grad():
+        y1 = m(xs[0].clone(), lengths)
+        bn1 = {k: v.clone() for k, v in m.state_dict().items() if "running_" in k or "num_batches" in k}
+        y2 = m(xs[1].clone(), lengths)
+        bn2 = {k: v.clone() for k, v in m.state_dict().items() if "running_" in k or "num_batches" in k}
+    out = dict(y1=y1, y2=y2)
+    out.update({"bn1." + k: v.float() for k, v in bn1.items()})
+    out.update({"bn2." + k: v.float() for k, v in bn2.items()})
+    _save("ffconvlstm_train", cfg, sd0, dict(x1=xs[0], x2=xs[1], lengths=torch.tensor(lengths)), out)
+
+
 def golden_postprocess(ns):
     """nnsvs.dsp.lowpass_filter and nnsvs.postfilters.variance_scaling as gen.postprocess_acoustic calls them
     (gen.py:1394-1418,1500-1513): 5 ms frames (modfs 200), cutoffs 50 (mgc / bap) and 20 (lf0)."""
@@ -406,7 +443,7 @@ def main():
     assert not torch.cuda.is_available(), "run with CUDA_VISIBLE_DEVICES='' (index.py calls .cuda())"
     torch.set_num_threads(1)  # deterministic reduction order
     makers = [golden_diffnet, golden_diffusion, golden_wavenet, golden_usfgan, golden_frontend, golden_encoder,
-              golden_postprocess, golden_wrapper, golden_wavenet_incremental]
+              golden_encoder_train, golden_postprocess, golden_wrapper, golden_wavenet_incremental]
     only = set(sys.argv[1:])          # e.g. "golden_wrapper": regenerate that fixture only
     for mk in makers:
         if not only or mk.__name__ in only:

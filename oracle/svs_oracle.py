@@ -591,11 +591,16 @@ def ffconvlstm_front(sd: SD, x: Tensor, *, in_ph_start_idx: int, in_ph_end_idx: 
 
 def ffconvlstm_forward(sd: SD, x: Tensor, lengths: Sequence[int], *, in_ph_start_idx: int = 1, in_ph_end_idx: int = 50,
                        embed_dim: Optional[int] = None, num_lstm_layers: int = 2, spk_embs: Optional[Tensor] = None,
-                       bn_eps: float = 1e-5, want_parts: bool = False, num_gaussians: int = 4):
-    """FFConvLSTM.forward in eval mode, use_mdn=False (model.py:893-922).  x [B, T, in_dim] -> [B, max(lengths), out_dim].
+                       bn_eps: float = 1e-5, want_parts: bool = False, num_gaussians: int = 4, train: bool = False,
+                       bn_momentum: float = 0.1):
+    """FFConvLSTM.forward, use_mdn=False (model.py:893-922).  x [B, T, in_dim] -> [B, max(lengths), out_dim].
 
-    ff: 3 x (Linear, ReLU); conv: 3 x (ReflectionPad1d(3), Conv1d k=7, BatchNorm1d with running statistics, ReLU) over
-    the whole padded batch; 2-layer BiLSTM over the packed sequences; Linear.
+    ff: 3 x (Linear, ReLU); conv: 3 x (ReflectionPad1d(3), Conv1d k=7, BatchNorm1d, ReLU) over the whole padded batch;
+    2-layer BiLSTM over the packed sequences; Linear.  Eval mode: BatchNorm1d with its running statistics.  ``train``
+    (module.train() with dropout = 0, what the diffusion recipe's encoders have): BatchNorm1d normalises with the BATCH
+    statistics over all B * T positions, padded frames included (biased variance), and moves its running statistics by
+    ``bn_momentum`` towards them (unbiased variance) — torch.nn.BatchNorm1d semantics; with want_parts the new buffers are
+    returned as parts["bn"] = {"conv.N.running_mean" / "running_var": tensor}.
     """
     x = ffconvlstm_front(sd, x, in_ph_start_idx=in_ph_start_idx, in_ph_end_idx=in_ph_end_idx, embed_dim=embed_dim,
                          spk_embs=spk_embs)
@@ -603,10 +608,19 @@ def ffconvlstm_forward(sd: SD, x: Tensor, lengths: Sequence[int], *, in_ph_start
         x = torch.relu(x @ sd[f"ff.{i}.weight"].t() + sd[f"ff.{i}.bias"])
     ff = x
     y = x.transpose(1, 2)
+    bn_new = {}
     for i in (1, 5, 9):
         y = F.conv1d(F.pad(y, (3, 3), mode="reflect"), sd[f"conv.{i}.weight"], sd[f"conv.{i}.bias"])
         n = i + 1
-        y = (y - sd[f"conv.{n}.running_mean"][None, :, None]) / torch.sqrt(sd[f"conv.{n}.running_var"][None, :, None] + bn_eps)
+        if train:
+            cnt = y.shape[0] * y.shape[2]
+            mean = y.mean(dim=(0, 2))
+            var = ((y - mean[None, :, None]) ** 2).mean(dim=(0, 2))
+            bn_new[f"conv.{n}.running_mean"] = (1 - bn_momentum) * sd[f"conv.{n}.running_mean"] + bn_momentum * mean
+            bn_new[f"conv.{n}.running_var"] = (1 - bn_momentum) * sd[f"conv.{n}.running_var"] + bn_momentum * var * cnt / max(cnt - 1, 1)
+        else:
+            mean, var = sd[f"conv.{n}.running_mean"], sd[f"conv.{n}.running_var"]
+        y = (y - mean[None, :, None]) / torch.sqrt(var[None, :, None] + bn_eps)
         y = torch.relu(y * sd[f"conv.{n}.weight"][None, :, None] + sd[f"conv.{n}.bias"][None, :, None])
     conv = y.transpose(1, 2)
     h = bilstm_stack(sd, "lstm.", conv, lengths, num_lstm_layers)
@@ -615,7 +629,7 @@ def ffconvlstm_forward(sd: SD, x: Tensor, lengths: Sequence[int], *, in_ph_start
         out = mdn_layer(sd, "fc.", h, num_gaussians)
     else:
         out = h @ sd["fc.weight"].t() + sd["fc.bias"]
-    return (out, dict(ff=ff, conv=conv, lstm=h)) if want_parts else out
+    return (out, dict(ff=ff, conv=conv, lstm=h, bn=bn_new)) if want_parts else out
 
 
 def mdn_layer(sd: SD, prefix: str, h: Tensor, num_gaussians: int) -> Tuple[Tensor, Tensor, Tensor]:

@@ -1444,6 +1444,45 @@ def test_ffconvlstm_matches_reference_golden(name):
     assert torch.equal(y, y2)
 
 
+def test_ffconvlstm_training_mode_forward_matches_reference_golden():
+    """module.train() with dropout = 0 (the diffusion recipe's encoders): BatchNorm1d normalises with the batch statistics of
+    the padded batch and moves its running buffers (model.py:839-852,915).  Two consecutive forwards against the unmodified
+    reference's outputs and buffers (tests/golden/ffconvlstm_train.npz): 2e-4 * max(1, |ref|); then the eval forward must
+    see the UPDATED buffers (cached plans are rebuilt).  A call that needs gradients raises: there are no backward
+    kernels for the encoder."""
+    from ensemble_svs_with_interactions_b200.model import FFConvLSTM
+    g = Golden("ffconvlstm_train")
+    m = FFConvLSTM(**g.cfg)
+    m.load_state_dict(g.sd, strict=True)
+    m = m.to(DEV).eval()
+    lengths = g.inp["lengths"].tolist()
+    y_eval0 = m(g.inp["x1"].to(DEV), lengths)                       # builds and caches the eval plan (old buffers)
+    m.train()
+    with pytest.raises(RuntimeError, match="no backward kernels"):
+        m(g.inp["x1"].to(DEV), lengths)
+    with torch.no_grad():
+        for k in ("1", "2"):
+            y = m(g.inp["x" + k].to(DEV), lengths)
+            close32(y, g.out["y" + k])
+            sd = m.state_dict()
+            for name in sd:
+                if "running_" in name:
+                    close32(sd[name], g.out[f"bn{k}.{name}"], 1e-5)
+                elif "num_batches" in name:
+                    assert int(sd[name]) == int(k)
+    m.eval()
+    sd_cpu = {n: v.detach().cpu() for n, v in m.state_dict().items()}
+    cfg = g.cfg
+    ref = O.ffconvlstm_forward(sd_cpu, g.inp["x1"], lengths, in_ph_start_idx=cfg["in_ph_start_idx"], in_ph_end_idx=cfg["in_ph_end_idx"],
+                               embed_dim=cfg["embed_dim"], num_lstm_layers=cfg["num_lstm_layers"])
+    y_eval1 = m(g.inp["x1"].to(DEV), lengths)
+    close32(y_eval1, ref)
+    assert not torch.allclose(y_eval0, y_eval1)                      # the buffers did move
+    m2 = FFConvLSTM(**{**g.cfg, "dropout": 0.1}).to(DEV).train()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="dropout = 0 only"):
+        m2(g.inp["x1"].to(DEV), lengths)
+
+
 def _recipe_encoder(precision, gen, H=128, spk=False):
     from ensemble_svs_with_interactions_b200.model import FFConvLSTM
     torch.manual_seed(5)

@@ -175,8 +175,13 @@ def test_ffconvlstm_ctor_and_loud_failures():
                    embed_dim=32, init_type="kaiming_normal")
     assert m.resolved_precision() == "bf16"
     assert torch.count_nonzero(m.fc.bias) == 0        # init_weights zeroes Linear / Conv biases (util.py:60-61)
-    with pytest.raises(RuntimeError, match="eval"):
+    with pytest.raises(RuntimeError, match="no backward kernels"):      # training mode + trainable parameters + grad mode
         m(torch.zeros(1, 8, 87))
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):    # the training-mode forward itself is a CUDA path too
+        m(torch.zeros(1, 8, 87))
+    md = FFConvLSTM(87, ff_hidden_dim=64, conv_hidden_dim=32, lstm_hidden_dim=16, out_dim=32, dropout=0.1)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="dropout = 0 only"):
+        md(torch.zeros(1, 8, 87))
     with pytest.raises(RuntimeError, match="CUDA"):
         m.eval()(torch.zeros(1, 8, 87))
 
