@@ -242,6 +242,13 @@ class DiffNet(nn.Module):
         stack_b = _stack_tracks_per_launch(B, T, plan.C, H) if os.environ.get("SVSK_DIFFNET_STACK", "1") != "0" else 0
         if not stack_b or not ops.diffnet_stack_uses_pcond(stack_b, T, plan.C, H):
             return None
+        # three buffers of B * T * L * 2C bf16 each (GEMM output, gate half + filter half): 0.74 GB at BASELINE config 2,
+        # 2.2 GB for a 6 x 6000 batch; a batch for which they would not be small next to the model's own tensors keeps the
+        # projection inside the GEMM (SVSK_PCOND_MAX_BYTES, default 16 GB)
+        tiles = 2 * ((T + 255) // 256)
+        need = 2 * B * plan.L * 2 * plan.C * (2 * T + tiles * 128)
+        if need > int(os.environ.get("SVSK_PCOND_MAX_BYTES", str(16 << 30))):
+            return None
         p = ops.diffnet_cond_project(condb.contiguous(), plan.wcp_all)
         return ops.diffnet_pcond_pack(p, B, T, plan.L, plan.C)
 
