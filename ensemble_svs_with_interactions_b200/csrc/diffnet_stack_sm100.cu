@@ -92,12 +92,11 @@ struct DiffnetStackArgs {
   // conditioner tiles — the same for every layer — stay in their own shared-memory tiles instead of being reloaded into
   // the G buffer once the skip epilogue has released it (3.8 k cycles into the layer).
   int pingpong, cond_resident;
-  // Experiment (SVSK_STACK_COND_FIRST=1, global-memory halo mode): the conditioner k-blocks issued BEFORE block 0's side
-  // taps, on the idea that the halo rows land ~9.5 k cycles after the previous residual epilogue there and the conditioner
-  // MMAs need none.  Measured at 3 x 6000 frames, C = 256: 446.1 vs 434.5 us per launch — slower: the conditioner tiles
-  // (G buffer released by the previous skip epilogue, then a 64 KB load) arrive no earlier than the halo rows, and the
-  // side taps then queue behind them.  Off by default.
-  int cond_first;
+  // Measured in round 2 and removed (it was a run-time switch inside the single-thread roles' loops, see the template
+  // parameters of the kernel): the conditioner k-blocks issued BEFORE block 0's side taps in global-memory halo mode, on the
+  // idea that the halo rows land ~9.5 k cycles after the previous residual epilogue there and the conditioner MMAs need
+  // none — 446.1 vs 434.5 us per launch at 3 x 6000 frames, slower: the conditioner tiles (G buffer released by the previous
+  // skip epilogue, then a 64 KB load) arrive no earlier than the halo rows, and the side taps then queue behind them.
   // Hoisted conditioner projection (see the header comment): filter half, [tile][L][NB][8][128][16] bf16 from this launch's
   // first track on; the gate half comes through tm_cond (then a map of [B*L][T][C]).
   int use_p;
@@ -130,22 +129,14 @@ struct __align__(8) DiffnetStackBarriers {
 };
 
 // ring entry i of a layer -> which weight tile (see the order in the header comment)
-__device__ __forceinline__ void stack_entry(int i, int CB, int HB, int NB, int KB2, int cond_first, int& kcol, int& blk,
-                                            bool& wout) {
+__device__ __forceinline__ void stack_entry(int i, int CB, int HB, int NB, int KB2, int& kcol, int& blk, bool& wout) {
   wout = false;
   if (i < CB) { kcol = CB + i; blk = 0; return; }
   i -= CB;
-  if (cond_first) {
-    if (i < HB * NB) { kcol = 3 * CB + i / NB; blk = i % NB; return; }
-    i -= HB * NB;
-    if (i < 2 * CB) { kcol = (i / CB) * 2 * CB + i % CB; blk = 0; return; }
-    i -= 2 * CB;
-  } else {
-    if (i < 2 * CB) { kcol = (i / CB) * 2 * CB + i % CB; blk = 0; return; }
-    i -= 2 * CB;
-    if (i < HB * NB) { kcol = 3 * CB + i / NB; blk = i % NB; return; }
-    i -= HB * NB;
-  }
+  if (i < 2 * CB) { kcol = (i / CB) * 2 * CB + i % CB; blk = 0; return; }
+  i -= 2 * CB;
+  if (i < HB * NB) { kcol = 3 * CB + i / NB; blk = i % NB; return; }
+  i -= HB * NB;
   if (i < (NB - 1) * 3 * CB) { blk = 1 + i / (3 * CB); kcol = i % (3 * CB); return; }
   i -= (NB - 1) * 3 * CB;
   wout = true;
@@ -179,7 +170,9 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
 // kUseP: the conditioner projection is precomputed (DiffnetStackArgs::use_p) — a compile-time switch, so that the instantiation without it
 // keeps the register allocation it had before the projection's prefetch registers existed (168 registers are the cap at
 // 352 threads; a handful of spilled loop invariants cost the MMA-issuing thread 5 % of the launch).
-template <bool kUseP>
+// kDsmem (one cluster per track, halo rows through distributed shared memory) and kProf (clock64 stamps for tools/bench_stack.py)
+// are compile-time for the same reason: the single-thread roles pay for every run-time branch in their loops.
+template <bool kUseP, bool kDsmem, bool kProf>
 __global__ void __launch_bounds__(kSThreads, 1)
 diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_constant__ CUtensorMap tm_e0,
                      const __grid_constant__ CUtensorMap tm_e1, const __grid_constant__ CUtensorMap tm_cond,
@@ -211,9 +204,9 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
   const uint32_t lead = crank & ~1u;               // cluster rank of this pair's leader
   const uint32_t csize = ptx::cluster_nctarank();
   const uint16_t pair_mask = (uint16_t)(3u << lead);
-  const bool nb_left = a.dsmem_halo && crank > 0, nb_right = a.dsmem_halo && crank + 1 < csize;  // DSMEM neighbours
+  const bool nb_left = kDsmem && crank > 0, nb_right = kDsmem && crank + 1 < csize;  // DSMEM neighbours
   // weight multicast (one cluster per track): every pair fetches rows [pidx, pidx+1) * 128/n_pairs of each half-tile
-  const bool mc = a.dsmem_halo != 0;
+  const bool mc = kDsmem != 0;
   const int n_pairs = mc ? (int)(csize >> 1) : 1, pidx = mc ? (int)(crank >> 1) : 0;
   const int slice_rows = 128 / n_pairs;
   const uint16_t parity_mask = (uint16_t)((0x5555u << rank) & ((1u << csize) - 1u));  // CTAs with this CTA's pair rank
@@ -223,8 +216,8 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
   const int w_row0 = (int)rank * 128;                             // this CTA's half of a 256-row weight block
   const int n_layer = NB * (3 * CB + HB) + NB * KB2;              // ring entries per layer
   const int n_total = L * n_layer;
-  unsigned long long* dbg = a.dbg ? a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 32 : nullptr;
-#define SVSK_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
+  unsigned long long* dbg = (kProf && a.dbg) ? a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 32 : nullptr;
+#define SVSK_STAMP(i) do { if (kProf && dbg) dbg[i] = clock64(); } while (0)
   if (threadIdx.x == 0) SVSK_STAMP(0);
 
   int pre_issued = 0;  // weight producer: entries issued before the CTA-wide sync
@@ -265,7 +258,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
     for (int e = 0; e < pre_issued; ++e) {
       int kcol, blk;
       bool wout;
-      stack_entry(e, CB, HB, NB, KB2, a.cond_first, kcol, blk, wout);
+      stack_entry(e, CB, HB, NB, KB2, kcol, blk, wout);
       ptx::mbar_arrive_expect_tx(&bars->full[e], kSTile);
       ptx::tma_load_3d(ring + e * kSTile, wout ? &tm_wout : &tm_w1, &bars->full[e], kcol * 64, blk * 256 + w_row0, 0);
     }
@@ -291,7 +284,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         // thread) — after it they would sit on the refill path of a ring that is as deep as shared memory allows
         int kcol, blk;
         bool wout;
-        stack_entry(i, CB, HB, NB, KB2, a.cond_first, kcol, blk, wout);
+        stack_entry(i, CB, HB, NB, KB2, kcol, blk, wout);
         const CUtensorMap* tm = wout ? &tm_wout : &tm_w1;
         const int c0 = kcol * 64, c1 = blk * 256 + w_row0 + (mc ? pidx * slice_rows : 0);
         uint8_t* dst = ring + s * kSTile + (mc ? pidx * slice_rows * 128 : 0);
@@ -332,7 +325,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
       for (int l = 1; l < L; ++l) {
         const uint32_t pp = (uint32_t)(l - 1) & 1u;
         const CUtensorMap* tm_e = pp ? &tm_e1 : &tm_e0;
-        if (a.dsmem_halo) {  // the halo rows travel through distributed shared memory: only the conditioner tiles here
+        if (kDsmem) {  // the halo rows travel through distributed shared memory: only the conditioner tiles here
           if (a.cond_resident && !kUseP) break;  // ... and not even those
           ptx::mbar_wait(&bars->gc_free, pp);
           for (int hb = 0; hb < HB; ++hb) {
@@ -402,9 +395,9 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
 #define SVSK_WAIT_ENTRY()                                 \
   do {                                                    \
     if (!ready) {                                         \
-      const long long c_0 = dbg ? clock64() : 0ll;        \
+      const long long c_0 = (kProf && dbg) ? clock64() : 0ll; \
       SVSK_STACK_ISSUER_WAIT(&bars->full[s], ph);         \
-      if (dbg) { acc_wait += clock64() - c_0; ++n_miss; } \
+      if (kProf && dbg) { acc_wait += clock64() - c_0; ++n_miss; } \
     }                                                     \
     ready = false;                                        \
     ptx::tc_fence_after();                                \
@@ -440,11 +433,11 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
           if (l == 2 && cb == 0) SVSK_STAMP(19);
           SVSK_ISSUE4(0, xw_lo + cb * (kSWinBytes >> 4) + kSHalo * 8, ring_lo + s * (kSTile >> 4), cb != 0);
         }
-        for (int part = 0; part < 2; ++part) {
-          if ((part == 0) != (a.cond_first != 0)) {
+        {
+          {
             // ---- side taps, block 0
             if (l != 0) {  // halo rows of this layer
-              if (a.dsmem_halo) ptx::mbar_wait(&bars->xh_full, pp);
+              if (kDsmem) ptx::mbar_wait(&bars->xh_full, pp);
               else ptx::mbar_wait(&bars->xw_full, pl);
               ptx::tc_fence_after();
             }
@@ -456,7 +449,8 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
                 SVSK_ISSUE4(0, row_lo + cb * (kSWinBytes >> 4), ring_lo + s * (kSTile >> 4), 1);
               }
             }
-          } else {
+          }
+          {
             // ---- conditioner k-blocks out of the (future) G buffer, all output blocks per tile
             for (int hb = 0; hb < HB; ++hb) {
               if (l == 0 || !a.cond_resident) ptx::mbar_wait(&bars->cd_full[hb], pl);
@@ -489,7 +483,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
           ptx::umma_commit2_mc(&bars->d1_full[j], pair_mask);
         }
         // GEMM1 of this layer has read the window for the last time: the neighbouring tiles may overwrite its halo rows
-        if (a.dsmem_halo) ptx::umma_commit2_mc(&bars->halo_free, halo_mask);
+        if (kDsmem) ptx::umma_commit2_mc(&bars->halo_free, halo_mask);
         if (l == 1) SVSK_STAMP(6);
         // ---- GEMM2: G tiles of gating block 0 first (its k-blocks of output block 0 run while block 1 is still gated)
         ptx::mbar_wait(&bars->g_ready[0], pl);
@@ -508,7 +502,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         }
         if (l == 1) SVSK_STAMP(8);
       }
-      if (dbg) { dbg[16] = acc_wait; dbg[17] = n_miss; }  // blocking waits for ring entries: cycles, count
+      if (kProf && dbg) { dbg[16] = acc_wait; dbg[17] = n_miss; }  // blocking waits for ring entries: cycles, count
 #undef SVSK_WAIT_ENTRY
 #undef SVSK_NEXT_ENTRY
 #undef SVSK_ISSUE4
@@ -528,7 +522,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
           }
         };
         auto forward_xw = [&]() {
-          if (a.dsmem_halo && l != 0) {
+          if (kDsmem && l != 0) {
             ptx::mbar_wait(&bars->xh_full, pl ^ 1u);
             ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->xh_full), lead));
             return;
@@ -538,11 +532,12 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         };
         if (l == 0) forward_xw();
         forward_entries(CB);
-        for (int part = 0; part < 2; ++part) {
-          if ((part == 0) != (a.cond_first != 0)) {
+        {
+          {
             if (l != 0) forward_xw();
             forward_entries(2 * CB);
-          } else {
+          }
+          {
             for (int hb = 0; hb < HB; ++hb) {
               if (l == 0 || !a.cond_resident) {
                 ptx::mbar_wait(&bars->cd_full[hb], pl);
@@ -847,6 +842,17 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
 
 using namespace svsk;
 
+using StackKernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
+                               DiffnetStackArgs);
+static StackKernelFn stack_kernel_variant(bool use_p, bool dsmem, bool prof) {
+  static const StackKernelFn table[8] = {
+      diffnet_stack_kernel<false, false, false>, diffnet_stack_kernel<true, false, false>,
+      diffnet_stack_kernel<false, true, false>,  diffnet_stack_kernel<true, true, false>,
+      diffnet_stack_kernel<false, false, true>,  diffnet_stack_kernel<true, false, true>,
+      diffnet_stack_kernel<false, true, true>,   diffnet_stack_kernel<true, true, true>};
+  return table[(use_p ? 1 : 0) | (dsmem ? 2 : 0) | (prof ? 4 : 0)];
+}
+
 namespace svsk {  // diffnet_stack_duo_sm100.cu: C = 128 with two tiles per CTA pair
 bool diffnet_stack_duo_applies(int C, int H);
 int diffnet_stack_duo_fits(int B, int T);
@@ -895,10 +901,11 @@ static int stack_prepare(int C, int H, int* nentries, int* smem_bytes, int* cond
   cudaGetDevice(&dev);
   static bool attr_set[64] = {false};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(diffnet_stack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemLimit);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(diffnet_stack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemLimit);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(diffnet_stack_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(diffnet_stack_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaError_t e = cudaSuccess;
+    for (int v = 0; v < 8 && e == cudaSuccess; ++v) {
+      e = cudaFuncSetAttribute(stack_kernel_variant(v & 1, v & 2, v & 4), cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemLimit);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(stack_kernel_variant(v & 1, v & 2, v & 4), cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    }
     if (e != cudaSuccess) return fail((int)e, "diffnet_stack_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
@@ -953,7 +960,7 @@ static int stack_one_tile_fits(int B, int T, int C, int H) {
   cudaLaunchAttribute attr[2];
   stack_launch_config(&cfg, attr, B, T, smem_bytes, nullptr);
   int max_clusters = 0;
-  if (cudaOccupancyMaxActiveClusters(&max_clusters, diffnet_stack_kernel<false>, &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, stack_kernel_variant(false, false, false), &cfg) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
@@ -1047,7 +1054,7 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
   cudaLaunchAttribute attr[2];
   stack_launch_config(&cfg, attr, p.B, p.T, smem_bytes, stream);
   int max_clusters = 0;
-  cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, diffnet_stack_kernel<false>, &cfg);
+  cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, stack_kernel_variant(false, false, false), &cfg);
   if (oe != cudaSuccess) return fail((int)oe, "diffnet_stack_bf16: cudaOccupancyMaxActiveClusters: %s", cudaGetErrorString(oe));
   const int n_clusters = (int)(cfg.gridDim.x / attr[0].val.clusterDim.x) * p.B;
   SVSK_REQUIRE(n_clusters <= max_clusters, SVSK_E_ARG,
@@ -1107,7 +1114,6 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
   a.nentries = nentries;
   a.pingpong = (p.C == 128 && !getenv("SVSK_STACK_NO_PINGPONG")) ? 1 : 0;
   a.cond_resident = cond_resident;
-  a.cond_first = (!a.dsmem_halo && !use_p && getenv("SVSK_STACK_COND_FIRST")) ? 1 : 0;  // experiment switch, see DiffnetStackArgs
   a.use_p = use_p ? 1 : 0;
   a.pfilt = static_cast<const uint4*>(p.pcond_filt);
   a.tiles_per_track = 2 * ceil_div(p.T, 256);
@@ -1120,8 +1126,8 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
     e = cudaMemsetAsync(p.flags, 0, sizeof(int) * (size_t)p.B * a.tiles_per_track, as_stream(stream));
     if (e != cudaSuccess) return fail((int)e, "diffnet_stack_bf16: flag reset: %s", cudaGetErrorString(e));
   }
-  if (use_p) e = cudaLaunchKernelEx(&cfg, diffnet_stack_kernel<true>, tm_xw0, tm_e0, tm_e1, tm_cond, tm_w1, tm_wout, tm_skip, a);
-  else e = cudaLaunchKernelEx(&cfg, diffnet_stack_kernel<false>, tm_xw0, tm_e0, tm_e1, tm_cond, tm_w1, tm_wout, tm_skip, a);
+  e = cudaLaunchKernelEx(&cfg, stack_kernel_variant(use_p, a.dsmem_halo != 0, a.dbg != nullptr), tm_xw0, tm_e0, tm_e1, tm_cond, tm_w1,
+                         tm_wout, tm_skip, a);
   if (e != cudaSuccess) return fail((int)e, "diffnet_stack_bf16: launch: %s", cudaGetErrorString(e));
   return check_launch("diffnet_stack_bf16");
 }

@@ -523,28 +523,6 @@ def test_diffnet_stack_hoisted_conditioner_projection(C, H, M, L, B, T):
     print(f"hoisted conditioner projection vs in-GEMM: rel_l2={r:.3e} max={mx:.3e}")
 
 
-def test_diffnet_stack_cond_first_switch():
-    """SVSK_STACK_COND_FIRST=1 (experiment switch of the global-memory halo mode: conditioner k-blocks before block 0's side
-    taps; measured slower and off by default) computes the same stack up to the fp32 accumulation order."""
-    import os
-    from ensemble_svs_with_interactions_b200.diffsinger import denoiser as den_mod
-    m = _random_diffnet(256, 256, 80, 5, seed=77).to(DEV)
-    g = torch.Generator().manual_seed(5)
-    B, T = 2, 2300                                           # > 2048 frames: edge rows through global memory
-    spec = torch.randn(B, 1, 80, T, generator=g).to(DEV); cond = torch.randn(B, 256, T, generator=g).to(DEV)
-    t = torch.randint(0, 100, (B,), generator=g).to(DEV)
-    ref = m(spec, t, cond)
-    os.environ["SVSK_STACK_COND_FIRST"] = "1"
-    den_mod._STACK_FIT_CACHE.clear()
-    try:
-        y = m(spec, t, cond)
-        y2 = m(spec, t, cond)
-    finally:
-        os.environ.pop("SVSK_STACK_COND_FIRST")
-    assert torch.isfinite(y).all() and torch.equal(y, y2)
-    close_bf16(y, ref, 1e-2, 3e-2)
-
-
 @pytest.mark.parametrize("C,H,M,L", [(128, 192, 60, 3), (256, 64, 33, 2)])
 @pytest.mark.parametrize("B,T", [(1, 1), (2, 7), (3, 9), (2, 129), (1, 257), (2, 2049)])
 def test_diffnet_sampling_odd_shapes(C, H, M, L, B, T):
