@@ -172,7 +172,7 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
 // 352 threads; a handful of spilled loop invariants cost the MMA-issuing thread 5 % of the launch).
 // kDsmem (one cluster per track, halo rows through distributed shared memory) and kProf (clock64 stamps for tools/bench_stack.py)
 // are compile-time for the same reason: the single-thread roles pay for every run-time branch in their loops.
-template <bool kUseP, bool kDsmem, bool kProf>
+template <bool kUseP, bool kDsmem, bool kProf, int kC>
 __global__ void __launch_bounds__(kSThreads, 1)
 diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_constant__ CUtensorMap tm_e0,
                      const __grid_constant__ CUtensorMap tm_e1, const __grid_constant__ CUtensorMap tm_cond,
@@ -181,17 +181,18 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-  const int C = a.C, H = a.H, T = a.T, L = a.L;
-  const int CB = C / 64;
+  constexpr int C = kC;  // 128 or 256: loop bounds of the single-thread roles are compile-time constants
+  const int H = a.H, T = a.T, L = a.L;
+  constexpr int CB = C / 64;
   const int HB = kUseP ? 0 : H / 64;  // conditioner k-blocks of GEMM1 (none when the projection is precomputed)
   const int PB = kUseP ? CB : 0;      // ... then: gate-half tiles of the projection per layer, loaded where G will be written
-  const int KB2 = CB;
-  const int NB = (2 * C) / 256;  // 256-column output blocks of either GEMM
-  const int twoC = 2 * C;
+  constexpr int KB2 = CB;
+  constexpr int NB = (2 * C) / 256;  // 256-column output blocks of either GEMM
+  constexpr int twoC = 2 * C;
   uint8_t* xw_smem = smem;                         // CB window tiles
   uint8_t* g_smem = xw_smem + CB * kSWinBytes;     // max(HB, KB2, 4) tiles: conditioner tiles, then G, then skip slabs
-  uint8_t* cond_smem = a.cond_resident ? g_smem + max(max(HB, KB2), 4) * kSTile : g_smem;   // HB resident tiles, or the G buffer
-  uint8_t* ring = g_smem + (max(max(HB, KB2), 4) + (a.cond_resident ? HB : 0)) * kSTile;  // nentries x 16 KB (the G buffer holds >= 4 skip slabs)
+  uint8_t* cond_smem = (kC == 128 && a.cond_resident) ? g_smem + max(max(HB, KB2), 4) * kSTile : g_smem;   // HB resident tiles, or the G buffer
+  uint8_t* ring = g_smem + (max(max(HB, KB2), 4) + ((kC == 128 && a.cond_resident) ? HB : 0)) * kSTile;  // nentries x 16 KB (the G buffer holds >= 4 skip slabs)
   float* sb_full = reinterpret_cast<float*>(ring + a.nentries * kSTile);
   float* sb_l = sb_full + twoC;
   float* sb_r = sb_l + twoC;
@@ -326,7 +327,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         const uint32_t pp = (uint32_t)(l - 1) & 1u;
         const CUtensorMap* tm_e = pp ? &tm_e1 : &tm_e0;
         if (kDsmem) {  // the halo rows travel through distributed shared memory: only the conditioner tiles here
-          if (a.cond_resident && !kUseP) break;  // ... and not even those
+          if ((kC == 128 && a.cond_resident) && !kUseP) break;  // ... and not even those
           ptx::mbar_wait(&bars->gc_free, pp);
           for (int hb = 0; hb < HB; ++hb) {
             ptx::mbar_arrive_expect_tx(&bars->cd_full[hb], kSTile);
@@ -367,7 +368,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         }
         if (l == 1) SVSK_STAMP(13);
         // conditioner tiles of layer l, once the G buffer is free again
-        if (a.cond_resident && !kUseP) continue;
+        if ((kC == 128 && a.cond_resident) && !kUseP) continue;
         ptx::mbar_wait(&bars->gc_free, pp);
         if (l == 1) SVSK_STAMP(14);
         for (int hb = 0; hb < HB; ++hb) {
@@ -413,7 +414,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
       for (int l = 0; l < L; ++l) {
         const uint32_t pl = (uint32_t)l & 1u, pp = pl ^ 1u;
         const int d = a.dilation[l];
-        const uint32_t tb = a.pingpong ? pl * 256u : 0u;  // TMEM column base of this layer's accumulator block(s)
+        const uint32_t tb = (kC == 128 && a.pingpong) ? pl * 256u : 0u;  // TMEM column base of this layer's accumulator block(s)
         // ---- centre tap, block 0
         if (l == 0) {
           ptx::mbar_wait(&bars->xw_full, 0);
@@ -422,7 +423,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
           if (l == 2) SVSK_STAMP(27);
           // and the accumulator block read out: by the previous layer — or, alternating halves, by the one before it
           // (barrier pl completes once every two layers)
-          if (!a.pingpong) ptx::mbar_wait(&bars->d2_drained[0], pp);
+          if (!(kC == 128 && a.pingpong)) ptx::mbar_wait(&bars->d2_drained[0], pp);
           else if (l >= 2) ptx::mbar_wait(&bars->d2_drained[pl], (uint32_t)((l - 2) >> 1) & 1u);
         }
         ptx::tc_fence_after();
@@ -453,7 +454,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
           {
             // ---- conditioner k-blocks out of the (future) G buffer, all output blocks per tile
             for (int hb = 0; hb < HB; ++hb) {
-              if (l == 0 || !a.cond_resident) ptx::mbar_wait(&bars->cd_full[hb], pl);
+              if (l == 0 || !(kC == 128 && a.cond_resident)) ptx::mbar_wait(&bars->cd_full[hb], pl);
               if (hb == 0 && l != 0 && NB > 1) ptx::mbar_wait(&bars->d2_drained[1], pp);
               ptx::tc_fence_after();
               if (l == 1 && hb == 0) SVSK_STAMP(4);
@@ -539,7 +540,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
           }
           {
             for (int hb = 0; hb < HB; ++hb) {
-              if (l == 0 || !a.cond_resident) {
+              if (l == 0 || !(kC == 128 && a.cond_resident)) {
                 ptx::mbar_wait(&bars->cd_full[hb], pl);
                 ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->cd_full[hb]), lead));
               }
@@ -579,7 +580,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
     for (int l = 0; l < L; ++l) {
       const uint32_t pl = (uint32_t)l & 1u;
       const int d = a.dilation[l];
-      const uint32_t tcol = tmem + tlane + (a.pingpong ? pl * 256u : 0u);   // this thread's lane, this layer's accumulator
+      const uint32_t tcol = tmem + tlane + ((kC == 128 && a.pingpong) ? pl * 256u : 0u);   // this thread's lane, this layer's accumulator
       const bool has_l = (t - d) >= 0, has_r = (t + d) < T;
       // A track's first / last d frames lack a tap's bias term.  Warp-uniform, so that the correction is a BRANCH around the
       // rare case: written per element (if (!has_l) ...) it compiled to 64 predicated-off loads + 64 adds per 16-column
@@ -752,7 +753,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
             ptx::fence_proxy_async_smem();
             ptx::mbar_arrive_cluster(xc_leader);  // first: the next layer's centre tap is waiting for this
             ptx::mbar_arrive(&bars->xe_ready);
-            if (res_cols == 256 && !a.pingpong) {
+            if (res_cols == 256 && !(kC == 128 && a.pingpong)) {
               // ... and for this: the block holds no skip columns, so this thread has read all of it out of TMEM.  Said
               // BEFORE the edge threads' cluster-scope fence below (MEMBAR.ALL.GPU + L1 invalidate, ~3 k cycles in 4 of the
               // 8 epilogue warps), during which the next layer's first MMA used to wait on a condition long true:
@@ -821,7 +822,7 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
         }
         if (!drained_said) {
           ptx::tc_fence_before();
-          ptx::mbar_arrive_cluster(dr_leader + (a.pingpong ? pl : (uint32_t)j) * 8u);
+          ptx::mbar_arrive_cluster(dr_leader + ((kC == 128 && a.pingpong) ? pl : (uint32_t)j) * 8u);
         }
       }
       // the bias arrays are rewritten at the top of the next layer: every epilogue thread must be done reading them
@@ -844,13 +845,17 @@ using namespace svsk;
 
 using StackKernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
                                DiffnetStackArgs);
-static StackKernelFn stack_kernel_variant(bool use_p, bool dsmem, bool prof) {
-  static const StackKernelFn table[8] = {
-      diffnet_stack_kernel<false, false, false>, diffnet_stack_kernel<true, false, false>,
-      diffnet_stack_kernel<false, true, false>,  diffnet_stack_kernel<true, true, false>,
-      diffnet_stack_kernel<false, false, true>,  diffnet_stack_kernel<true, false, true>,
-      diffnet_stack_kernel<false, true, true>,   diffnet_stack_kernel<true, true, true>};
-  return table[(use_p ? 1 : 0) | (dsmem ? 2 : 0) | (prof ? 4 : 0)];
+static StackKernelFn stack_kernel_variant(bool use_p, bool dsmem, bool prof, int C) {
+  static const StackKernelFn table[16] = {
+      diffnet_stack_kernel<false, false, false, 256>, diffnet_stack_kernel<true, false, false, 256>,
+      diffnet_stack_kernel<false, true, false, 256>,  diffnet_stack_kernel<true, true, false, 256>,
+      diffnet_stack_kernel<false, false, true, 256>,  diffnet_stack_kernel<true, false, true, 256>,
+      diffnet_stack_kernel<false, true, true, 256>,   diffnet_stack_kernel<true, true, true, 256>,
+      diffnet_stack_kernel<false, false, false, 128>, diffnet_stack_kernel<true, false, false, 128>,
+      diffnet_stack_kernel<false, true, false, 128>,  diffnet_stack_kernel<true, true, false, 128>,
+      diffnet_stack_kernel<false, false, true, 128>,  diffnet_stack_kernel<true, false, true, 128>,
+      diffnet_stack_kernel<false, true, true, 128>,   diffnet_stack_kernel<true, true, true, 128>};
+  return table[(use_p ? 1 : 0) | (dsmem ? 2 : 0) | (prof ? 4 : 0) | (C == 128 ? 8 : 0)];
 }
 
 namespace svsk {  // diffnet_stack_duo_sm100.cu: C = 128 with two tiles per CTA pair
@@ -902,9 +907,10 @@ static int stack_prepare(int C, int H, int* nentries, int* smem_bytes, int* cond
   static bool attr_set[64] = {false};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     cudaError_t e = cudaSuccess;
-    for (int v = 0; v < 8 && e == cudaSuccess; ++v) {
-      e = cudaFuncSetAttribute(stack_kernel_variant(v & 1, v & 2, v & 4), cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemLimit);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(stack_kernel_variant(v & 1, v & 2, v & 4), cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    for (int v = 0; v < 16 && e == cudaSuccess; ++v) {
+      StackKernelFn fn = stack_kernel_variant(v & 1, v & 2, v & 4, (v & 8) ? 128 : 256);
+      e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemLimit);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     }
     if (e != cudaSuccess) return fail((int)e, "diffnet_stack_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
@@ -960,7 +966,7 @@ static int stack_one_tile_fits(int B, int T, int C, int H) {
   cudaLaunchAttribute attr[2];
   stack_launch_config(&cfg, attr, B, T, smem_bytes, nullptr);
   int max_clusters = 0;
-  if (cudaOccupancyMaxActiveClusters(&max_clusters, stack_kernel_variant(false, false, false), &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, stack_kernel_variant(false, false, false, C), &cfg) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
@@ -1054,7 +1060,7 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
   cudaLaunchAttribute attr[2];
   stack_launch_config(&cfg, attr, p.B, p.T, smem_bytes, stream);
   int max_clusters = 0;
-  cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, stack_kernel_variant(false, false, false), &cfg);
+  cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, stack_kernel_variant(false, false, false, p.C), &cfg);
   if (oe != cudaSuccess) return fail((int)oe, "diffnet_stack_bf16: cudaOccupancyMaxActiveClusters: %s", cudaGetErrorString(oe));
   const int n_clusters = (int)(cfg.gridDim.x / attr[0].val.clusterDim.x) * p.B;
   SVSK_REQUIRE(n_clusters <= max_clusters, SVSK_E_ARG,
@@ -1126,7 +1132,7 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
     e = cudaMemsetAsync(p.flags, 0, sizeof(int) * (size_t)p.B * a.tiles_per_track, as_stream(stream));
     if (e != cudaSuccess) return fail((int)e, "diffnet_stack_bf16: flag reset: %s", cudaGetErrorString(e));
   }
-  e = cudaLaunchKernelEx(&cfg, stack_kernel_variant(use_p, a.dsmem_halo != 0, a.dbg != nullptr), tm_xw0, tm_e0, tm_e1, tm_cond, tm_w1,
+  e = cudaLaunchKernelEx(&cfg, stack_kernel_variant(use_p, a.dsmem_halo != 0, a.dbg != nullptr, p.C), tm_xw0, tm_e0, tm_e1, tm_cond, tm_w1,
                          tm_wout, tm_skip, a);
   if (e != cudaSuccess) return fail((int)e, "diffnet_stack_bf16: launch: %s", cudaGetErrorString(e));
   return check_launch("diffnet_stack_bf16");
