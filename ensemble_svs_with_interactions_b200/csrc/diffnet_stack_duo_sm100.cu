@@ -90,6 +90,9 @@ __device__ __forceinline__ void duo_st_release_gpu(int* p, int v) {
 }
 __device__ __forceinline__ void duo_fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
+// kHB = H / 64 (1 or 2) and kProf (clock64 stamps) are compile-time: the single-thread roles pay for every run-time loop
+// bound and branch (diffnet_stack_sm100.cu).
+template <int kHB, bool kProf>
 __global__ void __launch_bounds__(kDThreads, 1)
 diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_constant__ CUtensorMap tm_e0,
                          const __grid_constant__ CUtensorMap tm_e1, const __grid_constant__ CUtensorMap tm_cond,
@@ -98,8 +101,8 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-  const int H = a.H, T = a.T, L = a.L;
-  const int HB = H / 64;
+  const int T = a.T, L = a.L;
+  constexpr int HB = kHB;
   uint8_t* ring = smem + 2 * kDSlotBytes;
   float* bias_base = reinterpret_cast<float*>(ring + a.nentries * kDTile);  // per slot: sb_full | sb_l | sb_r | bo_s
   DuoBarriers* bars = reinterpret_cast<DuoBarriers*>(bias_base + 2 * 4 * kDTwoC);
@@ -120,9 +123,9 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
   const int vp0 = pair, vp1 = pair + npairs;
   const bool live1 = vp1 * 256 < T;  // (slot 0 is always live: the grid has ceil(n256 / 2) pairs per track)
   const int n_slots = live1 ? 2 : 1;
-  unsigned long long* dbg = a.dbg ? a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;
-#define DUO_STAMP(l_, u_, i_) do { if (dbg && (l_) == kDStampLayer) dbg[(u_) * 32 + (i_)] = clock64(); } while (0)
-  if (dbg && threadIdx.x == 0) dbg[63] = clock64();
+  unsigned long long* dbg = (kProf && a.dbg) ? a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;
+#define DUO_STAMP(l_, u_, i_) do { if (kProf && dbg && (l_) == kDStampLayer) dbg[(u_) * 32 + (i_)] = clock64(); } while (0)
+  if (kProf && dbg && threadIdx.x == 0) dbg[63] = clock64();
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_xw0);
@@ -565,7 +568,7 @@ diffnet_stack_duo_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __gri
   __syncthreads();
   ptx::cluster_sync_all();  // the peer's smem / TMEM are in use by the leader's MMAs until here
   if (warp == 1) ptx::tmem_dealloc2(tmem, 512);
-  if (dbg && threadIdx.x == 0) dbg[62] = clock64();
+  if (kProf && dbg && threadIdx.x == 0) dbg[62] = clock64();
 #undef DUO_STAMP
 }
 
@@ -576,6 +579,13 @@ static int duo_smem(int H, int* nentries_out) {
   if (nentries > kDMaxEntries) nentries = kDMaxEntries;
   *nentries_out = nentries;
   return fixed + nentries * kDTile;
+}
+
+using DuoKernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
+                             DuoArgs);
+static DuoKernelFn duo_kernel_variant(int hb, bool prof) {
+  if (hb == 1) return prof ? diffnet_stack_duo_kernel<1, true> : diffnet_stack_duo_kernel<1, false>;
+  return prof ? diffnet_stack_duo_kernel<2, true> : diffnet_stack_duo_kernel<2, false>;
 }
 
 bool diffnet_stack_duo_applies(int C, int H) {
@@ -589,7 +599,9 @@ static int duo_prepare(int* nentries, int* smem_bytes) {
   cudaGetDevice(&dev);
   static bool attr_set[64] = {false};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(diffnet_stack_duo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmemLimit);
+    cudaError_t e = cudaSuccess;
+    for (int v = 0; v < 4 && e == cudaSuccess; ++v)
+      e = cudaFuncSetAttribute(duo_kernel_variant(1 + (v & 1), (v & 2) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmemLimit);
     if (e != cudaSuccess) return fail((int)e, "diffnet_stack_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
@@ -623,7 +635,7 @@ int diffnet_stack_duo_fits(int B, int T) {
   cudaLaunchAttribute attr[2];
   duo_launch_config(&cfg, attr, B, T, smem_bytes, nullptr);
   int max_clusters = 0;
-  if (cudaOccupancyMaxActiveClusters(&max_clusters, diffnet_stack_duo_kernel, &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, duo_kernel_variant(2, false), &cfg) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
@@ -638,7 +650,7 @@ int diffnet_stack_duo_launch(const svsk_diffnet_stack_params& p, void* stream) {
   cudaLaunchAttribute attr[2];
   duo_launch_config(&cfg, attr, p.B, p.T, smem_bytes, stream);
   int max_clusters = 0;
-  cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, diffnet_stack_duo_kernel, &cfg);
+  cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, duo_kernel_variant(2, false), &cfg);
   if (oe != cudaSuccess) return fail((int)oe, "diffnet_stack_bf16: cudaOccupancyMaxActiveClusters: %s", cudaGetErrorString(oe));
   const int n_clusters = (int)(cfg.gridDim.x / 2) * p.B;
   SVSK_REQUIRE(n_clusters <= max_clusters, SVSK_E_ARG,
@@ -694,7 +706,7 @@ int diffnet_stack_duo_launch(const svsk_diffnet_stack_params& p, void* stream) {
 
   cudaError_t e = cudaMemsetAsync(p.flags, 0, sizeof(int) * (size_t)p.B * a.tiles_per_track, as_stream(stream));
   if (e != cudaSuccess) return fail((int)e, "diffnet_stack_bf16: flag reset: %s", cudaGetErrorString(e));
-  e = cudaLaunchKernelEx(&cfg, diffnet_stack_duo_kernel, tm_xw0, tm_e0, tm_e1, tm_cond, tm_w1, tm_wout, tm_skip, a);
+  e = cudaLaunchKernelEx(&cfg, duo_kernel_variant(p.H / 64, a.dbg != nullptr), tm_xw0, tm_e0, tm_e1, tm_cond, tm_w1, tm_wout, tm_skip, a);
   if (e != cudaSuccess) return fail((int)e, "diffnet_stack_bf16: launch: %s", cudaGetErrorString(e));
   return check_launch("diffnet_stack_bf16 (two tiles per CTA pair)");
 }
