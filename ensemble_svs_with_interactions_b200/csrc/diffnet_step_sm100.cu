@@ -42,17 +42,22 @@ struct __align__(8) DiffnetStepBarriers {
   uint32_t tmem_base;
 };
 
+// kC = C (128 or 256) is compile-time: the staging loops divide by C / 8 per element, and constants in the single-thread
+// roles' loops are worth several per cent on this library's kernels.
+template <int kC>
 __global__ void __launch_bounds__(kStepThreads, 1)
 diffnet_step_kernel(const __grid_constant__ CUtensorMap tm_wskip, const __grid_constant__ CUtensorMap tm_wout,
                     const __grid_constant__ CUtensorMap tm_win, const __grid_constant__ CUtensorMap tm_xout,
                     const DiffnetStepArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int C = a.C, Mp = a.Mp, T = a.T;
-  const int CB = C / 64, MB = (Mp + 63) / 64;
+  constexpr int C = kC;
+  const int Mp = a.Mp, T = a.T;
+  constexpr int CB = C / 64;
+  const int MB = (Mp + 63) / 64;
   uint8_t* ah = smem;                       // CB tiles: A, then H, then X (2 tiles), then the output tile
   uint8_t* ws = ah + CB * kStepTile;        // CB tiles of C rows (Wskip); later Wout | Win
-  const int ws_tile = C * 128;              // bytes of one Wskip / Win tile
+  constexpr int ws_tile = C * 128;          // bytes of one Wskip / Win tile
   uint8_t* wout_s = ws;                     // CB tiles at a 16 KB pitch (Mp <= 128 rows each)
   uint8_t* win_s = ws + CB * kStepTile;     // MB tiles of C rows
   const int ws_bytes = max(CB * ws_tile, CB * kStepTile + MB * ws_tile);
@@ -361,7 +366,8 @@ extern "C" int svsk_diffnet_step_bf16(const svsk_diffnet_step_params* pp, void* 
   cudaGetDevice(&dev);
   static bool attr_set[64] = {false};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(diffnet_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(diffnet_step_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(diffnet_step_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return fail((int)e, "diffnet_step_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
@@ -377,8 +383,12 @@ extern "C" int svsk_diffnet_step_bf16(const svsk_diffnet_step_params* pp, void* 
   const bool timeline = getenv("SVSK_STEP_TIMELINE") != nullptr;
   if (timeline && !dbg_buf) cudaMalloc(&dbg_buf, 64);
   a.dbg = timeline ? dbg_buf : nullptr;
-  diffnet_step_kernel<<<dim3(ceil_div(p.T, 128), p.B), kStepThreads, smem_bytes, as_stream(stream)>>>(tm_wskip, tm_wout, tm_win,
-                                                                                                       tm_xout, a);
+  if (p.C == 128)
+    diffnet_step_kernel<128><<<dim3(ceil_div(p.T, 128), p.B), kStepThreads, smem_bytes, as_stream(stream)>>>(tm_wskip, tm_wout, tm_win,
+                                                                                                              tm_xout, a);
+  else
+    diffnet_step_kernel<256><<<dim3(ceil_div(p.T, 128), p.B), kStepThreads, smem_bytes, as_stream(stream)>>>(tm_wskip, tm_wout, tm_win,
+                                                                                                              tm_xout, a);
   if (timeline) {  // debugging aid: cycles since the kernel's first instruction at each phase boundary of one CTA
     unsigned h[16];
     cudaStreamSynchronize(as_stream(stream));
