@@ -43,7 +43,7 @@ CONFIG = {"workload": f"DiffNet(80,256,L20,C256) 100-step DDPM sampling, {B} tra
           "l2": "GPU arm: 256 MB flush between timed passes; the 384 MB noise tensor of a pass exceeds L2"}
 
 
-STACK_NCU_SUMMARY = "r02p_stack_ncu_full_summary.json"        # dram bytes of diffnet_stack_kernel<hoisted projection> (ncu --set full)
+STACK_NCU_SUMMARY = "r02q_stack_ncu_full_summary.json"        # dram bytes of diffnet_stack_kernel<hoisted projection> (ncu --set full)
 STACK_NCU_SUMMARY_IN_GEMM = "r02k_stack_ncu_full_summary.json"
 USFGAN_NCU_SUMMARY = "r02n_usfgan_block_fr_ncu_full_summary.json"
 
