@@ -144,6 +144,9 @@ __device__ __forceinline__ void stack_entry(int i, int CB, int HB, int NB, int K
   kcol = i % KB2;
 }
 
+// one cluster per track: are the weight tiles multicast (see the kernel)?
+__host__ __device__ constexpr bool stack_multicast(bool use_p, int C) { return !(use_p && C == 256); }
+
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -207,7 +210,14 @@ diffnet_stack_kernel(const __grid_constant__ CUtensorMap tm_xw0, const __grid_co
   const uint16_t pair_mask = (uint16_t)(3u << lead);
   const bool nb_left = kDsmem && crank > 0, nb_right = kDsmem && crank + 1 < csize;  // DSMEM neighbours
   // weight multicast (one cluster per track): every pair fetches rows [pidx, pidx+1) * 128/n_pairs of each half-tile
-  const bool mc = kDsmem != 0;
+  // Weight multicast inside a track's cluster (every pair fetches 1/n_pairs of a tile for all CTAs of its parity, so L2
+  // serves each weight byte once per track) — except in the hoisted-projection variant at C = 256: once the single-thread
+  // roles' overheads were gone the cluster-wide coupling of the ring (a slot is refilled when ALL pairs
+  // have released it) was that variant's largest stall, and per-pair loads measure 304.3 -> 290.3 us per launch at
+  // 6 x 2000 frames on the same box (ring entries not yet landed when reached: 297 -> 193 of 800, gpurun_out/s50_ab.log).
+  // The in-GEMM variant (326.7 vs 332.4 us) and C = 128 (85.9 vs 87.0 us) are still faster with the multicast
+  // (gpurun_out/s51_ab.log).
+  constexpr bool mc = kDsmem && stack_multicast(kUseP, kC);
   const int n_pairs = mc ? (int)(csize >> 1) : 1, pidx = mc ? (int)(crank >> 1) : 0;
   const int slice_rows = 128 / n_pairs;
   const uint16_t parity_mask = (uint16_t)((0x5555u << rank) & ((1u << csize) - 1u));  // CTAs with this CTA's pair rank
@@ -1069,7 +1079,7 @@ extern "C" int svsk_diffnet_stack_bf16(const svsk_diffnet_stack_params* pp, void
 
   // one cluster per track: each CTA pair fetches (and multicasts) 1/n_pairs of every weight half-tile
   const uint32_t csz = attr[0].val.clusterDim.x;
-  const uint32_t w_box_rows = csz > 2 ? 128u / (csz / 2) : 128u;
+  const uint32_t w_box_rows = (csz > 2 && stack_multicast(use_p, p.C)) ? 128u / (csz / 2) : 128u;
   CUtensorMap tm_xw0, tm_e0, tm_e1, tm_cond, tm_w1, tm_wout, tm_skip;
   {
     uint64_t dims[3] = {(uint64_t)p.C, (uint64_t)p.T, (uint64_t)p.B};
