@@ -14,18 +14,20 @@ for B, T in ((6, 2000), (3, 6000), (5, 517), (2, 2049)):
     xb0 = torch.randn(B, T, plan.C, generator=g).cuda().to(torch.bfloat16)
     e0, e1 = torch.empty_like(xb0), torch.empty_like(xb0)
     flags = torch.empty((B * 2 * ((T + 255) // 256),), device="cuda", dtype=torch.int32)
-    ref = None
-    for it in range(n):
-        skip = torch.empty(B, T, plan.C, device="cuda")
-        ops.diffnet_stack_bf16(xb0, e0, e1, skip, cond, plan.w1p_all, plan.woutp_all, table[:, 50:51], plan.bout_all, flags,
-                               plan.dilations, stepbias_batch_stride=0, stepbias_layer_stride=table.stride(0))
-        if ref is None:
-            ref = skip.clone()
-        elif not torch.equal(skip, ref):
-            bad += 1
-            print(f"stack B={B} T={T}: run {it} differs, max|d|={float((skip - ref).abs().max()):.3e}", flush=True)
-    torch.cuda.synchronize()
-    print(f"stack B={B} T={T}: {n} runs, finite={bool(torch.isfinite(ref).all())}", flush=True)
+    # both variants of the launch: conditioner projection inside the GEMM, and precomputed (what a sampling run issues)
+    for name, pcond in (("in-GEMM", None), ("hoisted", den.cond_projection_bf16(cond, plan))):
+        ref = None
+        for it in range(n):
+            skip = torch.empty(B, T, plan.C, device="cuda")
+            ops.diffnet_stack_bf16(xb0, e0, e1, skip, cond, plan.w1p_all, plan.woutp_all, table[:, 50:51], plan.bout_all, flags,
+                                   plan.dilations, stepbias_batch_stride=0, stepbias_layer_stride=table.stride(0), pcond=pcond)
+            if ref is None:
+                ref = skip.clone()
+            elif not torch.equal(skip, ref):
+                bad += 1
+                print(f"stack {name} B={B} T={T}: run {it} differs, max|d|={float((skip - ref).abs().max()):.3e}", flush=True)
+        torch.cuda.synchronize()
+        print(f"stack {name} B={B} T={T}: {n} runs, finite={bool(torch.isfinite(ref).all())}", flush=True)
 # uSFGAN block, fixed and adaptive
 B, T = 3, 200000
 xb = torch.randn(B, T, 64, device="cuda").to(torch.bfloat16); aux = torch.randn(B, T, 80, device="cuda").to(torch.bfloat16)
