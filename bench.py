@@ -45,7 +45,7 @@ CONFIG = {"workload": f"DiffNet(80,256,L20,C256) 100-step DDPM sampling, {B} tra
 
 STACK_NCU_SUMMARY = "r02q_stack_ncu_full_summary.json"        # dram bytes of diffnet_stack_kernel<hoisted projection> (ncu --set full)
 STACK_NCU_SUMMARY_IN_GEMM = "r02k_stack_ncu_full_summary.json"
-USFGAN_NCU_SUMMARY = "r02n_usfgan_block_fr_ncu_full_summary.json"
+USFGAN_NCU_SUMMARY = "r02r_usfgan_block_fr_ncu_full_summary.json"
 
 
 def _peaks():
