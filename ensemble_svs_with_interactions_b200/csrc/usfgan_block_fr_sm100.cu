@@ -92,11 +92,19 @@ __device__ __forceinline__ bool fr_tile_needs_gather(int t0, int T, int d, int a
   return (t0 - d < 0) || (last + d >= T);  // a reflected tap: rows are not a shifted copy any more
 }
 
-template <bool kProf>
+// kWindow (fixed blocks with dilation <= 8, i.e. 34 of the recipe's 35): the three taps of an interior tile are ONE
+// (128 + 16)-row window load and three row offsets of the A descriptor (as in the DiffNet kernels) instead of three
+// 16 KB loads of the same rows shifted by -d / 0 / +d: 18 instead of 48 KB per tile from L2 into shared memory.  Tiles at
+// a track's ends (reflected taps) keep the gathered layout.
+constexpr int kFWinRows = 128 + 16;
+constexpr int kFWinBytes = kFWinRows * 128;  // 18 KB: the tap0 tile of the stage + the first 2 KB of its centre tile
+
+template <bool kProf, bool kWindow>
 __global__ void __launch_bounds__(kFThreads, 1)
 usfgan_block_fr_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
                        const __grid_constant__ CUtensorMap tm_wout, const __grid_constant__ CUtensorMap tm_xout,
-                       const __grid_constant__ CUtensorMap tm_x8, const UsfganFrArgs a) {
+                       const __grid_constant__ CUtensorMap tm_x8, const __grid_constant__ CUtensorMap tm_xw,
+                       const UsfganFrArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w1_s = smem;                       // 3 tiles of [128 rows][64]
@@ -117,6 +125,7 @@ usfgan_block_fr_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     ptx::prefetch_tmap(&tm_wout);
     ptx::prefetch_tmap(&tm_xout);
     ptx::prefetch_tmap(&tm_x8);
+    if (kWindow) ptx::prefetch_tmap(&tm_xw);
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars->full[i], 129);
       ptx::mbar_init(&bars->empty[i], 1);
@@ -162,11 +171,16 @@ usfgan_block_fr_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         ptx::mbar_wait(&bars->empty[st], ((n >> 1) & 1) ^ 1);
         acc_p += (kProf ? clock64() : 0ll) - c_0;
         uint8_t* slot = stages + st * kFStage;
-        ptx::mbar_arrive_expect_tx(&bars->full[st], gather ? kFTile : 3 * kFTile);
-        ptx::tma_load_3d(slot + kFTile, &tm_x, &bars->full[st], 0, t0, b);
-        if (!gather) {
-          ptx::tma_load_3d(slot, &tm_x, &bars->full[st], 0, t0 - a.dilation, b);
-          ptx::tma_load_3d(slot + 2 * kFTile, &tm_x, &bars->full[st], 0, t0 + a.dilation, b);
+        if (kWindow && !gather) {
+          ptx::mbar_arrive_expect_tx(&bars->full[st], kFWinBytes);
+          ptx::tma_load_3d(slot, &tm_xw, &bars->full[st], 0, t0 - 8, b);
+        } else {
+          ptx::mbar_arrive_expect_tx(&bars->full[st], gather ? kFTile : 3 * kFTile);
+          ptx::tma_load_3d(slot + kFTile, &tm_x, &bars->full[st], 0, t0, b);
+          if (!gather) {
+            ptx::tma_load_3d(slot, &tm_x, &bars->full[st], 0, t0 - a.dilation, b);
+            ptx::tma_load_3d(slot + 2 * kFTile, &tm_x, &bars->full[st], 0, t0 + a.dilation, b);
+          }
         }
       }
       if (kProf && a.dbg) a.dbg[blockIdx.x * 16 + 0] = acc_p;  // producer: cycles waiting for a free stage
@@ -199,6 +213,7 @@ usfgan_block_fr_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         }
       };
       int n = 0;
+      int tt = (int)blockIdx.x % a.tiles_per_row;  // tile index within its track (kWindow: which operand layout the stage holds)
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++n) {
         const int p = n & 1;
         long long c_0 = (kProf ? clock64() : 0ll);
@@ -221,22 +236,33 @@ usfgan_block_fr_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         c_0 = (kProf ? clock64() : 0ll);
         acc_full += c_0 - c_1;
         const uint32_t s_lo = st_lo + p * (kFStage >> 4);
+        // operand rows: three tiles of the stage, or (window) three row offsets of one tile
+        uint32_t a_t0 = s_lo, a_c = s_lo + kT16, a_t2 = s_lo + 2 * kT16;
+        if (kWindow) {
+          if (!fr_tile_needs_gather(tt * 128, T, a.dilation, 0)) {
+            a_t0 = s_lo + (uint32_t)(8 - a.dilation) * 8u;
+            a_c = s_lo + 64u;
+            a_t2 = s_lo + (uint32_t)(8 + a.dilation) * 8u;
+          }
+          tt += (int)gridDim.x;
+          while (tt >= a.tiles_per_row) tt -= a.tiles_per_row;
+        }
         const uint32_t d1 = tmem + p * 128;
         uint64_t* nfull = &bars->full[p ^ 1];
         const uint32_t nfull_par = ((n + 1) >> 1) & 1;
         uint64_t* ng = &bars->g_full[p ^ 1];
         const uint32_t ng_par = ((n - 1) >> 1) & 1;  // meaningful for n >= 1
         if (!(flags & 4)) {
-          (void)ptx::umma_bf16_x4_probe(d1, s_lo, w1_lo, idesc1, 0, 4, nfull, nfull_par);
-          const bool r1 = ptx::umma_bf16_x4_probe(d1, s_lo + kT16, w1_lo + kT16, idesc1, 1, 4, ng, ng_par);
-          const bool r2 = ptx::umma_bf16_x4_probe(d1, s_lo + 2 * kT16, w1_lo + 2 * kT16, idesc1, 1, 4, nfull, nfull_par);
+          (void)ptx::umma_bf16_x4_probe(d1, a_t0, w1_lo, idesc1, 0, 4, nfull, nfull_par);
+          const bool r1 = ptx::umma_bf16_x4_probe(d1, a_c, w1_lo + kT16, idesc1, 1, 4, ng, ng_par);
+          const bool r2 = ptx::umma_bf16_x4_probe(d1, a_t2, w1_lo + 2 * kT16, idesc1, 1, 4, nfull, nfull_par);
           // aux: A = U (K columns 0..15 of the aux tile's rows), B = Q (K columns 16..31 of the same rows)
           ptx::umma_bf16_lo(d1, s_lo + 3 * kT16, s_lo + 3 * kT16 + 2, idesc1, 1);
           // residual: D2 = X_centre . I, GEMM2 accumulates onto it.  This D2 accumulator was last read by the residual
           // epilogue of tile n - 4, which its group finished before it gated tile n - 2 (waited for above).
           const uint32_t d2 = tmem + 256 + (p * 2 + ((n >> 1) & 1)) * 64;
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) ptx::umma_bf16_lo(d2, s_lo + kT16 + 2 * k4, id_lo + 2 * k4, idesc2, k4 != 0);
+          for (int k4 = 0; k4 < 4; ++k4) ptx::umma_bf16_lo(d2, a_c + 2 * k4, id_lo + 2 * k4, idesc2, k4 != 0);
           ptx::umma_commit(&bars->empty[p]);
           ptx::umma_commit(&bars->d1_full[p]);
           full_ready = r2;
@@ -504,7 +530,7 @@ int usfgan_block_fr_launch(const svsk_usfgan_block_params& p, void* stream) {
                "usfgan_block_bf16: aux_q rows hold columns 0..%d, the tiles read %d..%d", p.q_ld - 1, p.q_fpad + fb_first,
                p.q_fpad + fb_last + 15);
   int rc;
-  CUtensorMap tm_x, tm_w1, tm_wout, tm_xout, tm_x8;
+  CUtensorMap tm_x, tm_w1, tm_wout, tm_xout, tm_x8, tm_xw;
   {
     uint64_t dims[3] = {64, (uint64_t)p.T, (uint64_t)p.B};
     uint64_t str[2] = {128, (uint64_t)p.T * 128};
@@ -513,6 +539,8 @@ int usfgan_block_fr_launch(const svsk_usfgan_block_params& p, void* stream) {
     uint32_t box_8[3] = {64, 8, 1};   // side taps of gathered tiles: one swizzle atom (8 consecutive source rows)
     if ((rc = make_tmap_bf16(&tm_x, p.xb_in, 3, dims, str, box))) return rc;
     if ((rc = make_tmap_bf16(&tm_x8, p.xb_in, 3, dims, str, box_8))) return rc;
+    uint32_t box_w[3] = {64, (uint32_t)kFWinRows, 1};  // an interior tile's rows t0 - 8 .. t0 + 135 (window mode)
+    if ((rc = make_tmap_bf16(&tm_xw, p.xb_in, 3, dims, str, box_w))) return rc;
     if ((rc = make_tmap_bf16(&tm_xout, p.xb_out, 3, dims, str, box_q))) return rc;
   }
   {
@@ -533,8 +561,10 @@ int usfgan_block_fr_launch(const svsk_usfgan_block_params& p, void* stream) {
   cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   static bool attr_set[64] = {false};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(usfgan_block_fr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(usfgan_block_fr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(usfgan_block_fr_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(usfgan_block_fr_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(usfgan_block_fr_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(usfgan_block_fr_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return fail((int)e, "usfgan_block_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
@@ -561,10 +591,16 @@ int usfgan_block_fr_launch(const svsk_usfgan_block_params& p, void* stream) {
   if (const char* e = getenv("SVSK_USFGAN_ABLATE")) a.dbg_flags = atoi(e);
   if (const char* e = getenv("SVSK_USFGAN_TIMELINE")) a.dbg = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
   const int grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
-  if (a.dbg || a.dbg_flags)  // clock64 role accounting (distorts the timing) and / or ablation flags
-    usfgan_block_fr_kernel<true><<<grid, kFThreads, smem_bytes, as_stream(stream)>>>(tm_x, tm_w1, tm_wout, tm_xout, tm_x8, a);
+  const bool prof = a.dbg || a.dbg_flags;  // clock64 role accounting (distorts the timing) and / or ablation flags
+  const bool window = !p.adaptive && p.dilation >= 1 && p.dilation <= 8 && !getenv("SVSK_USFGAN_NO_WINDOW");
+  if (prof && window)
+    usfgan_block_fr_kernel<true, true><<<grid, kFThreads, smem_bytes, as_stream(stream)>>>(tm_x, tm_w1, tm_wout, tm_xout, tm_x8, tm_xw, a);
+  else if (prof)
+    usfgan_block_fr_kernel<true, false><<<grid, kFThreads, smem_bytes, as_stream(stream)>>>(tm_x, tm_w1, tm_wout, tm_xout, tm_x8, tm_xw, a);
+  else if (window)
+    usfgan_block_fr_kernel<false, true><<<grid, kFThreads, smem_bytes, as_stream(stream)>>>(tm_x, tm_w1, tm_wout, tm_xout, tm_x8, tm_xw, a);
   else
-    usfgan_block_fr_kernel<false><<<grid, kFThreads, smem_bytes, as_stream(stream)>>>(tm_x, tm_w1, tm_wout, tm_xout, tm_x8, a);
+    usfgan_block_fr_kernel<false, false><<<grid, kFThreads, smem_bytes, as_stream(stream)>>>(tm_x, tm_w1, tm_wout, tm_xout, tm_x8, tm_xw, a);
   return check_launch("usfgan_block_bf16 (frame-rate aux)");
 }
 
