@@ -286,3 +286,15 @@ def test_usfgan_frame_window_covers_upsampler_reach(scales, Tf):
         rebuilt = cpad[:, 64 + fb:64 + fb + 16] @ U                          # [5, n]
         assert float((rebuilt - full[:, t0:t0 + n]).abs().max()) < 1e-5 * max(1.0, float(full.abs().max()))
     assert not ops.usfgan_frame_window_ok(12, 3 * 4 + 4)                     # hop 12 (scales [4, 3]): sample-rate path
+
+
+def test_hoisted_conditioner_projection_host_checks():
+    """Host side of the precomputed conditioner projection (ops.diffnet_pcond_pack / diffnet_stack_bf16(pcond=...)): shapes
+    are checked before anything touches the device, and CPU tensors raise (no CPU path)."""
+    from ensemble_svs_with_interactions_b200 import ops
+    with pytest.raises(ValueError, match="p must be"):
+        ops.diffnet_pcond_pack(torch.zeros(3, 10, 256, dtype=torch.bfloat16), 2, 5, 2, 256)      # L * 2C/256 = 4 blocks expected
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.diffnet_pcond_pack(torch.zeros(4, 10, 256, dtype=torch.bfloat16), 2, 5, 2, 256)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.diffnet_cond_project(torch.zeros(2, 5, 64, dtype=torch.bfloat16), torch.zeros(4, 256, 64, dtype=torch.bfloat16))
