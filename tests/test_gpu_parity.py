@@ -523,6 +523,44 @@ def test_diffnet_stack_hoisted_conditioner_projection(C, H, M, L, B, T):
     print(f"hoisted conditioner projection vs in-GEMM: rel_l2={r:.3e} max={mx:.3e}")
 
 
+def test_diffnet_sampling_hoisted_projection_over_track_groups():
+    """A batch that exceeds one wave (7 tracks x 4100 frames at C = 256: 17 CTA pairs per track, the device holds four
+    tracks per launch) runs the stack in groups of tracks; the precomputed conditioner projection is sliced per group.
+    Against the same sampling run with the projection inside the GEMM (SVSK_STACK_NO_PCOND=1; one bf16 rounding apart) and
+    against the layer-at-a-time kernels."""
+    import os
+    from ensemble_svs_with_interactions_b200.diffsinger import GaussianDiffusion
+    from ensemble_svs_with_interactions_b200.diffsinger import denoiser as den_mod
+    C, H, M, L, B, T, K = 256, 256, 16, 3, 7, 4100, 3
+    den = _random_diffnet(C, H, M, L, seed=91)
+    m = GaussianDiffusion(H, M, den, K_step=K).to(DEV).eval()
+    m.use_cuda_graph = False
+    ops = _ops()
+    per_launch = den_mod._stack_tracks_per_launch(B, T, C, H)
+    assert 0 < per_launch < B, f"expected the batch to need several launches, got {per_launch} tracks per launch"
+    assert ops.diffnet_stack_uses_pcond(per_launch, T, C, H)
+    g = torch.Generator().manual_seed(4)
+    cond = torch.randn(B, T, H, generator=g).to(DEV); x_T = torch.randn(B, 1, M, T, generator=g).to(DEV)
+    z = torch.randn(K, B, 1, M, T, generator=g).to(DEV)
+    y = m.inference(cond, x_T=x_T, z=z)
+
+    def run(**env):
+        for k_, v_ in env.items():
+            os.environ[k_] = v_
+        try:
+            return m.inference(cond, x_T=x_T, z=z)
+        finally:
+            for k_ in env:
+                os.environ.pop(k_)
+
+    in_gemm = run(SVSK_STACK_NO_PCOND="1")
+    per_layer = run(SVSK_DIFFNET_STACK="0", SVSK_DIFFNET_STEP="0")
+    assert torch.isfinite(y).all() and torch.equal(y, m.inference(cond, x_T=x_T, z=z))
+    r, mx = close_bf16(y, in_gemm, 5e-3, 2e-2)
+    print(f"hoisted projection over track groups vs in-GEMM: rel_l2={r:.3e} max={mx:.3e}")
+    close_bf16(y, per_layer, 2e-2, 6e-2)
+
+
 @pytest.mark.parametrize("C,H,M,L", [(128, 192, 60, 3), (256, 64, 33, 2)])
 @pytest.mark.parametrize("B,T", [(1, 1), (2, 7), (3, 9), (2, 129), (1, 257), (2, 2049)])
 def test_diffnet_sampling_odd_shapes(C, H, M, L, B, T):
